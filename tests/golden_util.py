@@ -1,0 +1,69 @@
+"""Loading of the committed golden fixtures (written by oracle/make_golden.py from the LIVE
+reference) and the comparisons shared by the CPU (oracle) and GPU (engine) parity tests."""
+import ast
+import glob
+import os
+
+import numpy
+
+from tree_search_planning_b200.configs import get_config
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def golden_names():
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+
+
+class Golden:
+    def __init__(self, name):
+        z = numpy.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+        self.name = name
+        self.meta = ast.literal_eval(str(z["meta"]))
+        self.out = {k[4:]: z[k] for k in z.files if k.startswith("out:")}
+        self.net = {k[4:]: z[k] for k in z.files if k.startswith("net:")}
+        self.state_dict = {k[2:]: z[k] for k in z.files if k.startswith("w:")}
+        for k in ("obs", "legal", "n_legal", "noise", "tie", "chance"):
+            setattr(self, k, z[k])
+        self.S = int(self.meta["S"])
+        self.N = int(self.meta["N"])
+        cfg = get_config(self.meta["game"], num_simulations=self.S)
+        if self.meta.get("mask_absorbing_states"):
+            cfg = cfg.replace(mask_absorbing_states=True)
+        self.config = cfg
+
+    def run_kwargs(self):
+        return dict(legal_actions=self.legal, num_legal=self.n_legal, noise=self.noise, tie=self.tie,
+                    chance=self.chance, add_exploration_noise=bool(self.meta["add_noise"]),
+                    uniform_policy=bool(self.meta["uniform_policy"]))
+
+
+TREE_KEYS_EXACT = ("visit_counts", "root_value", "child_value", "child_prior", "child_reward", "max_tree_depth")
+
+
+def assert_tree_outputs_bit_exact(got, want, keys=TREE_KEYS_EXACT, what=""):
+    """Bit-exact comparison of everything a consumer reads from `root`."""
+    for k in keys:
+        a, b = numpy.asarray(got[k]), numpy.asarray(want[k])
+        assert a.shape == b.shape, (what, k, a.shape, b.shape)
+        if a.dtype.kind == "f":
+            same = (a.view(numpy.int64) == b.astype(a.dtype).view(numpy.int64)) if a.dtype == numpy.float64 else (a == b)
+            # -0.0 vs 0.0 are the same number to every consumer
+            same = same | ((a == 0) & (b == 0))
+        else:
+            same = a == b
+        assert same.all(), "%s: %s differs at %s: got %s want %s" % (
+            what, k, numpy.argwhere(~same)[:4].tolist(), a[~same][:4], b[~same][:4])
+
+
+def assert_close_quantised(got, want, tol=1e-5, min_fraction=0.98, hard_tol=2e-3, what=""):
+    """Tolerance for scalars that went through the reference's float32 inverse value transform
+    (models.py:1192-1200). That formula subtracts 1 from sqrt(1 + 0.004*(|x|+1.001)) in float32,
+    which quantises its output in steps of ~1.2e-4*(1+|x|); a 1-ulp difference upstream (or torch's
+    not-correctly-rounded CPU sqrt) moves a result by one whole step. So: within `tol` (relative to
+    max(1,|x|)) on at least `min_fraction` of the entries and within `hard_tol` on all of them."""
+    a, b = numpy.asarray(got, numpy.float64), numpy.asarray(want, numpy.float64)
+    err = numpy.abs(a - b) / numpy.maximum(1.0, numpy.abs(b))
+    assert err.max() <= hard_tol, "%s: max error %g > %g" % (what, err.max(), hard_tol)
+    frac = float((err <= tol).mean())
+    assert frac >= min_fraction, "%s: only %.4f of entries within %g" % (what, frac, tol)
