@@ -1,0 +1,192 @@
+/*
+ * tsp.h -- C ABI of the B200 batched MuZero tree-search engine (libtsp_b200.so).
+ *
+ * The reference (Disiok/tree-search-planning) is pure Python and has no FFI of its own; this
+ * header is the boundary a maintainer binds (ctypes stub in INTEGRATION.md) to replace the
+ * planning hot path. Every entry point cites the reference interface it replaces
+ * (paths under /root/reference/muzero-general/).
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, no C++/torch types; every function returns 0 on success or a
+ *     negative TSP_E* code, with a message retrievable through tsp_last_error().
+ *   - ownership: the caller owns every buffer it passes; the engine owns its node pools, hidden
+ *     state pools, weight arena and staging buffers, sized at tsp_create (max_roots, max_simulations).
+ *   - memory spaces: each call states whether its I/O pointers are HOST or DEVICE memory. HOST
+ *     buffers are staged through engine-owned device buffers with cudaMemcpyAsync on the engine's
+ *     stream (pinned host memory makes these truly asynchronous). All calls are asynchronous on
+ *     that stream; tsp_synchronize() waits. One host thread per handle.
+ *   - there is NO CPU fallback: without a CUDA device tsp_create fails with TSP_ENODEVICE.
+ */
+#ifndef TSP_H
+#define TSP_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TSP_ABI_VERSION 1
+#define TSP_REC_WIDTH 16     /* floats per network-evaluation record (see below) */
+#define TSP_MAX_ACTIONS 8    /* |action_space| supported by the node-block layouts */
+#define TSP_MAX_LAYERS 8     /* Linear layers per MLP */
+
+typedef struct tsp_engine *tsp_handle;
+
+/* error codes */
+enum {
+    TSP_OK = 0,
+    TSP_EINVAL = -1,      /* bad argument (mirrors the reference's asserts, self_play.py:354-359) */
+    TSP_ENODEVICE = -2,   /* no CUDA device / wrong architecture */
+    TSP_ECUDA = -3,       /* CUDA runtime error, text in tsp_last_error */
+    TSP_ENOMEM = -4,
+    TSP_ENOTIMPL = -5,    /* e.g. > 1 player (self_play.py:503 raises NotImplementedError for > 2) */
+    TSP_ESTATE = -6       /* weights not loaded / not finalized */
+};
+
+/* which MCTS the engine runs; same dispatch as muzero.py:232-250 */
+enum {
+    TSP_VARIANT_MUZERO = 0,         /* self_play.py:303-503 */
+    TSP_VARIANT_STOCHASTIC = 1,     /* self_play_stochastic.py:259-557 (chance nodes) */
+    TSP_VARIANT_RISK_SENSITIVE = 2  /* self_play_risk_sensitive.py:259-580 */
+};
+
+/* sub-MLPs of models.MuZeroFullyConnectedNetwork / MuZeroStochasticConcat (models.py:156-195, 502-513) */
+enum {
+    TSP_MLP_REPRESENTATION = 0, /* representation_network */
+    TSP_MLP_DYNAMICS = 1,       /* dynamics_encoded_state_network, input [h | onehot(a) (| onehot(z))] */
+    TSP_MLP_REWARD = 2,         /* dynamics_reward_network */
+    TSP_MLP_TERMINAL = 3,       /* dynamics_terminal_network (only evaluated with mask_absorbing_states) */
+    TSP_MLP_POLICY = 4,         /* prediction_policy_network */
+    TSP_MLP_VALUE = 5,          /* prediction_value_network */
+    TSP_MLP_PRIOR = 6,          /* transition_prior_network (stochastic variants) */
+    TSP_NUM_MLP = 7
+};
+
+enum { TSP_MEM_HOST = 0, TSP_MEM_DEVICE = 1 };
+
+/* The attributes of the reference's MuZeroConfig that the hot path reads ("Config"). */
+typedef struct {
+    int32_t variant;               /* TSP_VARIANT_* */
+    int32_t num_actions;           /* len(config.action_space), actions are 0..A-1 */
+    int32_t obs_dim;               /* flattened stacked observation, models.py:157-163 */
+    int32_t encoding_size;         /* config.encoding_size */
+    int32_t support_size;          /* config.support_size */
+    int32_t n_futures;             /* config.n_futures (stochastic variants), else 1 */
+    int32_t mask_absorbing_states; /* config.mask_absorbing_states, self_play.py:415 */
+    int32_t num_players;           /* len(config.players); only 1 is implemented */
+    double discount;               /* config.discount */
+    double pb_c_base;              /* config.pb_c_base */
+    double pb_c_init;              /* config.pb_c_init */
+    double root_exploration_fraction; /* config.root_exploration_fraction */
+    int32_t max_roots;             /* capacity: concurrent roots per tsp_run call */
+    int32_t max_simulations;       /* capacity: config.num_simulations upper bound */
+    int32_t device;                /* CUDA device ordinal */
+    int32_t reserved;
+} tsp_config;
+
+/* Network-evaluation record, float32[TSP_REC_WIDTH], one per network call in call order per root.
+ *   state record      (recurrent_inference / prediction):  [0]=1 [1]=value [2]=reward [3]=terminal logit
+ *                                                           [4..4+A) priors = softmax(policy logits)
+ *   transition record (MuZeroStochasticConcat.dynamics):   [0]=2 [1..1+nf) softmax(prior logits)
+ *                                                           [1+nf..1+2nf) decoded rewards
+ * `trace_*` outputs receive the engine's own network outputs; `fed_*` inputs replace the network
+ * (tree arithmetic with network outputs fed identically -- the parity mode of BASELINE.json). */
+
+typedef struct {
+    int32_t num_roots;             /* B <= max_roots */
+    int32_t num_simulations;       /* S <= max_simulations; 0 == policy_only (self_play.py:381) */
+    int32_t memory;                /* TSP_MEM_HOST / TSP_MEM_DEVICE for every pointer below */
+    int32_t add_exploration_noise; /* MCTS.run argument, self_play.py:372 */
+    int32_t uniform_policy;        /* MCTS.run argument, self_play.py:361,411 */
+    int32_t max_records;           /* rows per root in fed_records / trace_records */
+    int32_t tie_len;               /* T */
+    int32_t chance_len;            /* K */
+    /* inputs */
+    const float *observations;     /* [B][obs_dim]; torch.tensor(observation).float() of self_play.py:336-341 */
+    const int32_t *legal_actions;  /* [B][A] ordered legal-action lists (dict insertion order matters,
+                                      self_play.py:364-370), or NULL = config.action_space */
+    const int32_t *num_legal;      /* [B], or NULL with legal_actions == NULL */
+    const double *noise;           /* [B][A] Dirichlet sample aligned with the legal list (self_play.py:546);
+                                      required when add_exploration_noise */
+    const uint8_t *tie_stream;     /* [B][T] or NULL (= lowest index); replaces numpy.random.choice of
+                                      self_play.py:444-450: tied[stream[k % T] % n_tied], k++ per real tie */
+    const uint8_t *chance_stream;  /* [B][K]; replaces numpy.random.choice of self_play_stochastic.py:530-532:
+                                      z = stream[k % K] % nf, k++ per chance-node traversal (nf > 1) */
+    const float *fed_root;         /* [B][REC] or NULL */
+    const float *fed_records;      /* [B][max_records][REC] or NULL */
+    /* outputs (any may be NULL) -- what consumers read from `root` / `extra_info` */
+    int32_t *visit_counts;         /* [B][A]  root.children[a].visit_count (0 for illegal a) */
+    double *root_value;            /* [B]     root.value() (attribute .value in the risk-sensitive variant) */
+    double *child_value;           /* [B][A]  root.children[a].value() */
+    double *child_prior;           /* [B][A]  root.children[a].prior (after noise) */
+    double *child_reward;          /* [B][A]  root.children[a].reward */
+    int32_t *max_tree_depth;       /* [B]     extra_info["max_tree_depth"] */
+    float *root_predicted_value;   /* [B]     extra_info["root_predicted_value"] */
+    float *root_hidden;            /* [B][H]  root.hidden_state */
+    int32_t *num_records;          /* [B]     network evaluations made per root (excluding the root one) */
+    float *trace_root;             /* [B][REC] */
+    float *trace_records;          /* [B][max_records][REC] */
+} tsp_run_args;
+
+typedef struct {
+    int64_t kernel_launches;       /* kernels launched by this handle so far */
+    int64_t searches;              /* tsp_run calls */
+    int64_t bytes_h2d, bytes_d2h;  /* staged through the engine so far */
+    int64_t pool_bytes;            /* device memory owned by the engine */
+    float last_search_ms;          /* device time of the search kernel(s) of the last tsp_run (CUDA events) */
+    float last_root_ms;            /* device time of the root kernel of the last tsp_run */
+    int32_t sm_count;
+    int32_t search_ctas;           /* grid of the last search kernel */
+    int32_t search_smem_bytes;
+    int32_t trees_per_cta;
+} tsp_stats;
+
+int tsp_abi_version(void);
+
+/* replaces MCTS(config) construction (self_play.py:311-312) plus the model's placement on a device */
+int tsp_create(const tsp_config *cfg, tsp_handle *out);
+int tsp_destroy(tsp_handle h);
+/* message of the last error on this handle (h == NULL: last tsp_create failure) */
+const char *tsp_last_error(tsp_handle h);
+
+/* replaces model.set_weights(state_dict) (models.py:128-129): one call per torch.nn.Linear,
+ * W is [out_dim][in_dim] row-major float32 HOST memory exactly as in the state dict
+ * ("<net>.module.<2*layer>.weight"), b is [out_dim]. Then tsp_finalize_weights() packs and uploads. */
+int tsp_set_layer(tsp_handle h, int32_t mlp, int32_t layer, const float *W, const float *b,
+                  int32_t out_dim, int32_t in_dim);
+int tsp_finalize_weights(tsp_handle h);
+/* packed device-resident weight arena (for an NCCL broadcast / hot refresh between ranks) */
+int tsp_weight_arena(tsp_handle h, void **device_ptr, int64_t *num_bytes);
+
+/* replaces MCTS.run (self_play.py:314-434; self_play_stochastic.py:270-400;
+ * self_play_risk_sensitive.py:270-399) for B independent roots at once */
+int tsp_run(tsp_handle h, const tsp_run_args *args);
+
+/* replaces model.initial_inference + support_to_scalar (models.py:259-281, 1180-1201) for B rows.
+ * outputs (any may be NULL): value[B], policy_logits[B][A], hidden[B][H], value_logits[B][2s+1] */
+int tsp_initial_inference(tsp_handle h, int32_t memory, int32_t B, const float *observations,
+                          float *value, float *policy_logits, float *hidden, float *value_logits);
+/* replaces model.recurrent_inference + support_to_scalar (models.py:283-287) for B rows
+ * (deterministic network). outputs (any may be NULL): value[B], reward[B], terminal[B],
+ * policy_logits[B][A], next_hidden[B][H], value_logits[B][2s+1], reward_logits[B][2s+1] */
+int tsp_recurrent_inference(tsp_handle h, int32_t memory, int32_t B, const float *hidden, const int32_t *action,
+                            float *value, float *reward, float *terminal, float *policy_logits,
+                            float *next_hidden, float *value_logits, float *reward_logits);
+/* replaces MuZeroStochasticConcat.dynamics (models.py:520-550) for B rows:
+ * transition_logits[B][nf], next_hidden[B][nf][H], reward[B][nf] (decoded) */
+int tsp_stochastic_dynamics(tsp_handle h, int32_t memory, int32_t B, const float *hidden, const int32_t *action,
+                            float *transition_logits, float *next_hidden, float *reward);
+/* replaces model.prediction + support_to_scalar (models.py:209-212): value[B], policy_logits[B][A] */
+int tsp_prediction(tsp_handle h, int32_t memory, int32_t B, const float *hidden, float *value,
+                   float *policy_logits);
+
+int tsp_synchronize(tsp_handle h);
+int tsp_get_stats(tsp_handle h, tsp_stats *out);
+/* the CUDA stream the engine launches on (cudaStream_t as void*), for event timing by the caller */
+int tsp_stream(tsp_handle h, void **stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TSP_H */

@@ -1,0 +1,851 @@
+// tsp_device.cuh -- device side of the B200 batched MuZero tree-search engine (sm_100a).
+//
+// Data layout in HBM (per engine, sized at tsp_create):
+//   node pool      [max_roots][blocks_per_tree] NodeBlock<NC>   one 128-byte (NC=5) or 256-byte (NC=8)
+//                  block per EXPANDED node holding the statistics of all its children
+//                  (visit, child index, prior, reward, value sum) + parent link: one cache line
+//                  per tree level during selection.
+//   hidden pool    [max_roots][hidden_per_tree][H] float32
+//   tree headers   [max_roots] TreeHeader (min-max stats, root statistics, counters)
+//   root priors    [max_roots][8] float64 (noise-mixed priors stay double, self_play.py:540-549)
+//
+// Execution model: ONE persistent kernel runs the whole search of TM trees per CTA; a group of
+// 8 lanes owns one tree (lane j <-> child j, shuffle arg-max), all threads of the CTA evaluate
+// the leaf batch through the fused MLP schedule, then each group expands and backs up its tree.
+// Trees are independent, so there is no grid-wide synchronisation and no launch per simulation.
+//
+// Tree arithmetic is IEEE double in exactly the reference's operation order (explicit _rn
+// intrinsics so that nvcc never contracts a*b+c into an FMA); network arithmetic is float32.
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+namespace tsp {
+
+constexpr int GW = 8;    // lanes per tree
+constexpr int REC = 16;  // floats per evaluation record (TSP_REC_WIDTH)
+constexpr int MAX_STAGES = 14;
+constexpr int MAX_OPS = 4;
+
+template <int NC>
+struct alignas(NC <= 5 ? 128 : 256) NodeBlock {
+    int visit[NC];     // child.visit_count
+    int child[NC];     // block id of the child once expanded, -1 before
+    float prior[NC];   // child.prior (float32 softmax output; the root's double priors live apart)
+    float reward[NC];  // child.reward (set when the child is expanded)
+    int parent;        // block id of the parent (-1 for the root)
+    int aux;           // bits 0..7: slot of this node in its parent; bits 8..31: hidden slot
+                       // (state node) or transition ordinal (transition node)
+    double vsum[NC];   // child.value_sum  (risk-sensitive: child.value)
+};
+static_assert(sizeof(NodeBlock<5>) == 128, "NodeBlock<5> must be one 128-byte line");
+static_assert(sizeof(NodeBlock<8>) == 256, "NodeBlock<8> must be two 128-byte lines");
+
+struct alignas(16) TreeHeader {
+    double mm_min, mm_max;  // MinMaxStats, self_play.py:661-678
+    double root_vsum;       // root.value_sum (risk-sensitive: root.value)
+    int root_visit;         // root.visit_count
+    int n_blocks;           // expanded nodes so far
+    int n_tgroups;          // expanded transition nodes so far (stochastic variants)
+    int max_depth;
+    int n_sims;
+    int k_tie, k_chance;    // stream cursors
+    int n_rec;              // network evaluations so far
+    float root_pred;
+    int n_root;             // number of root children (legal actions)
+};
+static_assert(sizeof(TreeHeader) == 64, "TreeHeader must be 64 bytes");
+
+// ------------------------------------------------------------------ MLP schedule ----
+struct LayerOp {
+    int w_off;  // float offset of Wt [K_total][Npad] (transposed, zero padded) in the weight arena
+    int b_off;  // float offset of the bias [Npad]
+    short K;    // dense input width (one-hot rows follow at K, K+1, ...)
+    short N, Npad;
+    short in_off, out_off;  // float offsets inside a row's activation strip
+    unsigned char act;      // 0 identity, 1 ELU
+    unsigned char extra;    // 0 none, 1 + Wt[K + action], 2 + Wt[K + action] + Wt[K + A + z]
+};
+struct Stage {
+    unsigned char n_ops;
+    unsigned char row_op;  // 0 none, 1 min-max normalise r_in -> r_out over r_n elements
+    short r_in, r_out, r_n;
+    LayerOp ops[MAX_OPS];
+};
+struct Schedule {
+    int n_stages;
+    int row_stride;  // floats per row strip, == 4 (mod 32): conflict-free LDS.128 across rows
+    int in_dim;
+    short off_in, off_hidden, off_pl, off_vl, off_rl, off_tl, off_tp, pad0;
+    Stage st[MAX_STAGES];
+};
+
+__device__ __forceinline__ float elu(float v) { return v > 0.0f ? v : expm1f(v); }
+
+__device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
+
+// Evaluate all stages for the TM rows of this CTA. Every thread of the CTA must call it.
+template <int TM, int THREADS>
+__device__ void run_schedule(const Schedule& sc, const float* __restrict__ W, float* __restrict__ act,
+                             const int* __restrict__ row_action, const unsigned char* __restrict__ row_active,
+                             int A, int z) {
+    const int tid = threadIdx.x;
+    const int rs = sc.row_stride;
+    for (int s = 0; s < sc.n_stages; ++s) {
+        const Stage& st = sc.st[s];
+        int total = 0;
+        for (int o = 0; o < st.n_ops; ++o) total += TM * (st.ops[o].Npad >> 2);
+        for (int t = tid; t < total; t += THREADS) {
+            int o = 0, tt = t;
+            while (tt >= TM * (st.ops[o].Npad >> 2)) {
+                tt -= TM * (st.ops[o].Npad >> 2);
+                ++o;
+            }
+            const LayerOp& op = st.ops[o];
+            const int ncg = op.Npad >> 2;
+            const int row = tt / ncg, cg = tt - row * ncg;
+            if (!row_active[row]) continue;
+            const float* x = act + row * rs + op.in_off;
+            const float4* w = reinterpret_cast<const float4*>(W + op.w_off) + cg;
+            float4 acc = ldg4(reinterpret_cast<const float4*>(W + op.b_off) + cg);
+            const int K = op.K;
+            if (op.extra) {
+                const float4 e = ldg4(w + (K + row_action[row]) * ncg);
+                acc.x += e.x; acc.y += e.y; acc.z += e.z; acc.w += e.w;
+                if (op.extra == 2) {
+                    const float4 f = ldg4(w + (K + A + z) * ncg);
+                    acc.x += f.x; acc.y += f.y; acc.z += f.z; acc.w += f.w;
+                }
+            }
+            int k = 0;
+#pragma unroll 2
+            for (; k + 4 <= K; k += 4) {
+                const float4 xv = *reinterpret_cast<const float4*>(x + k);
+                const float4 w0 = ldg4(w + (k + 0) * ncg);
+                const float4 w1 = ldg4(w + (k + 1) * ncg);
+                const float4 w2 = ldg4(w + (k + 2) * ncg);
+                const float4 w3 = ldg4(w + (k + 3) * ncg);
+                acc.x = fmaf(xv.x, w0.x, acc.x); acc.y = fmaf(xv.x, w0.y, acc.y);
+                acc.z = fmaf(xv.x, w0.z, acc.z); acc.w = fmaf(xv.x, w0.w, acc.w);
+                acc.x = fmaf(xv.y, w1.x, acc.x); acc.y = fmaf(xv.y, w1.y, acc.y);
+                acc.z = fmaf(xv.y, w1.z, acc.z); acc.w = fmaf(xv.y, w1.w, acc.w);
+                acc.x = fmaf(xv.z, w2.x, acc.x); acc.y = fmaf(xv.z, w2.y, acc.y);
+                acc.z = fmaf(xv.z, w2.z, acc.z); acc.w = fmaf(xv.z, w2.w, acc.w);
+                acc.x = fmaf(xv.w, w3.x, acc.x); acc.y = fmaf(xv.w, w3.y, acc.y);
+                acc.z = fmaf(xv.w, w3.z, acc.z); acc.w = fmaf(xv.w, w3.w, acc.w);
+            }
+            for (; k < K; ++k) {
+                const float xv = x[k];
+                const float4 w0 = ldg4(w + k * ncg);
+                acc.x = fmaf(xv, w0.x, acc.x); acc.y = fmaf(xv, w0.y, acc.y);
+                acc.z = fmaf(xv, w0.z, acc.z); acc.w = fmaf(xv, w0.w, acc.w);
+            }
+            if (op.act) {
+                acc.x = elu(acc.x); acc.y = elu(acc.y); acc.z = elu(acc.z); acc.w = elu(acc.w);
+            }
+            *reinterpret_cast<float4*>(act + row * rs + op.out_off + cg * 4) = acc;
+        }
+        if (st.row_op == 1) {
+            // models.py:223-231 / 248-255: (x - min) / scale, scale += 1e-5 only where scale < 1e-5
+            const int row = tid >> 3, j = tid & 7;
+            const unsigned gmask = 0xFFu << ((tid & 31) & 24);
+            if (row < TM && row_active[row]) {
+                const float* x = act + row * rs + st.r_in;
+                float mn = CUDART_INF_F, mx = -CUDART_INF_F;
+                for (int i = j; i < st.r_n; i += GW) {
+                    const float v = x[i];
+                    mn = fminf(mn, v);
+                    mx = fmaxf(mx, v);
+                }
+#pragma unroll
+                for (int d = 1; d < GW; d <<= 1) {
+                    mn = fminf(mn, __shfl_xor_sync(gmask, mn, d));
+                    mx = fmaxf(mx, __shfl_xor_sync(gmask, mx, d));
+                }
+                float scale = __fsub_rn(mx, mn);
+                if (scale < 1e-5f) scale = __fadd_rn(scale, 1e-5f);
+                float* y = act + row * rs + st.r_out;
+                for (int i = j; i < st.r_n; i += GW) y[i] = __fdiv_rn(__fsub_rn(x[i], mn), scale);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------ row-group helpers ----
+__device__ __forceinline__ float group_max(float v, unsigned gmask) {
+#pragma unroll
+    for (int d = 1; d < GW; d <<= 1) v = fmaxf(v, __shfl_xor_sync(gmask, v, d));
+    return v;
+}
+__device__ __forceinline__ float group_sum(float v, unsigned gmask) {
+#pragma unroll
+    for (int d = 1; d < GW; d <<= 1) v = __fadd_rn(v, __shfl_xor_sync(gmask, v, d));
+    return v;
+}
+__device__ __forceinline__ double shfl_d(unsigned gmask, double v, int src_lane_in_warp) {
+    int lo = __double2loint(v), hi = __double2hiint(v);
+    lo = __shfl_sync(gmask, lo, src_lane_in_warp);
+    hi = __shfl_sync(gmask, hi, src_lane_in_warp);
+    return __hiloint2double(hi, lo);
+}
+__device__ __forceinline__ double shfl_xor_d(unsigned gmask, double v, int d) {
+    int lo = __double2loint(v), hi = __double2hiint(v);
+    lo = __shfl_xor_sync(gmask, lo, d);
+    hi = __shfl_xor_sync(gmask, hi, d);
+    return __hiloint2double(hi, lo);
+}
+
+// models.py:1192-1200 in torch's float32 operation order (no FMA contraction)
+__device__ __forceinline__ float inverse_value_transform(float x) {
+    const float c4e = (float)(4 * 0.001);
+    const float c2e = (float)(2 * 0.001);
+    float t = __fadd_rn(fabsf(x), 1.0f);
+    t = __fadd_rn(t, 0.001f);
+    t = __fmul_rn(c4e, t);
+    t = __fadd_rn(1.0f, t);
+    t = __fsqrt_rn(t);
+    t = __fsub_rn(t, 1.0f);
+    t = __fdiv_rn(t, c2e);
+    t = __fmul_rn(t, t);
+    t = __fsub_rn(t, 1.0f);
+    const float sgn = (x > 0.0f) ? 1.0f : ((x < 0.0f) ? -1.0f : 0.0f);
+    return __fmul_rn(sgn, t);
+}
+
+// models.py:1180-1201 by one 8-lane group; every lane returns the scalar
+__device__ __forceinline__ float support_to_scalar_group(const float* logits, int support, int j, unsigned gmask) {
+    const int n = 2 * support + 1;
+    float m = -CUDART_INF_F;
+    for (int i = j; i < n; i += GW) m = fmaxf(m, logits[i]);
+    m = group_max(m, gmask);
+    float s = 0.0f, xs = 0.0f;
+    for (int i = j; i < n; i += GW) {
+        const float e = expf(__fsub_rn(logits[i], m));
+        s = __fadd_rn(s, e);
+        xs = fmaf((float)(i - support), e, xs);
+    }
+    s = group_sum(s, gmask);
+    xs = group_sum(xs, gmask);
+    // sum_i support_i * (e_i / s): one division instead of n (differs from torch by rounding only)
+    return inverse_value_transform(__fdiv_rn(xs, s));
+}
+
+// softmax over up to 8 logits held one per lane (lanes >= n pass -inf); returns this lane's probability
+__device__ __forceinline__ float softmax_group(float logit, bool active, unsigned gmask) {
+    const float m = group_max(active ? logit : -CUDART_INF_F, gmask);
+    const float e = active ? expf(__fsub_rn(logit, m)) : 0.0f;
+    const float s = group_sum(e, gmask);
+    return __fdiv_rn(e, s);
+}
+
+// ------------------------------------------------------------------- tree math ----
+struct MinMax {
+    double mn, mx;
+    __device__ __forceinline__ void update(double v) {  // self_play.py:669-671
+        mx = mx > v ? mx : v;
+        mn = mn < v ? mn : v;
+    }
+    __device__ __forceinline__ double normalize(double v) const {  // self_play.py:673-677
+        if (mx > mn) return __ddiv_rn(__dsub_rn(v, mn), __dsub_rn(mx, mn));
+        return v;
+    }
+};
+
+// self_play.py:453-477 (VARIANT 0), self_play_stochastic.py:488-508 (1), self_play_risk_sensitive.py:496-520 (2)
+template <int VARIANT>
+__device__ __forceinline__ double ucb_score(double pb_log, int parent_visits, int visits, double vsum, double prior,
+                                            float reward, double discount, const MinMax& mm) {
+    double pb_c = __dmul_rn(pb_log, __ddiv_rn(__dsqrt_rn((double)parent_visits), (double)(visits + 1)));
+    const double prior_score = __dmul_rn(pb_c, prior);
+    double value_score = 0.0;
+    if (visits > 0) {
+        if (VARIANT == 0) {
+            const double q = __ddiv_rn(vsum, (double)visits);
+            value_score = mm.normalize(__dadd_rn((double)reward, __dmul_rn(discount, q)));
+        } else if (VARIANT == 1) {
+            value_score = mm.normalize(__ddiv_rn(vsum, (double)visits));
+        } else {
+            value_score = mm.normalize(__dadd_rn((double)reward, __dmul_rn(discount, vsum)));
+        }
+    }
+    return __dadd_rn(prior_score, value_score);
+}
+
+// --------------------------------------------------------------------- params ----
+struct NetParams {
+    int B, A, H, nf, support;
+    int mode;  // 0 initial_inference (+ optional tree init), 1 recurrent, 2 stochastic dynamics, 3 prediction
+    const float* W;
+    const float* in;      // observations [B][obs_dim] or hidden [B][H]
+    const int* action;    // [B] (modes 1, 2)
+    // outputs (device, may be null)
+    float* value; float* reward; float* terminal; float* policy_logits; float* hidden_out;
+    float* value_logits; float* reward_logits; float* transition_logits;
+    // tree init (mode 0 when tree_init != 0)
+    int tree_init, add_noise, uniform_policy, blocks_per_tree, hidden_per_tree;
+    double one_minus_frac, frac;
+    void* blocks; float* hidden_pool; TreeHeader* hdr; double* rootprior; int* rootact;
+    const int* legal; const int* num_legal; const double* noise;
+    const float* fed_root; float* trace_root; float* root_pred; float* root_hidden;
+    Schedule sched;
+};
+
+struct SearchParams {
+    int B, S, A, H, nf, support, mask_absorbing, uniform_policy;
+    int blocks_per_tree, hidden_per_tree, max_rec, T, K, max_iters;
+    double discount;
+    const double* pb_table;  // [S + 2]: log((N + base + 1) / base) + init, host libm (bit-equal to math.log)
+    void* blocks; float* hidden_pool; TreeHeader* hdr; const double* rootprior; const int* rootact;
+    const unsigned char* tie; const unsigned char* chance;
+    const float* fed; float* trace;
+    const float* W;
+    int* visit_counts; double* root_value; double* child_value; double* child_prior; double* child_reward;
+    int* max_depth; int* num_records;
+    Schedule sched_a;  // VARIANT 0: recurrent inference; else: transition expansion (dynamics, per future z)
+    Schedule sched_b;  // VARIANT != 0: prediction
+};
+
+// ------------------------------------------------------------- network kernel ----
+template <int NC, int TM>
+__global__ void __launch_bounds__(TM * GW) net_kernel(const __grid_constant__ NetParams p) {
+    extern __shared__ __align__(16) float smem[];
+    constexpr int THREADS = TM * GW;
+    const Schedule& sc = p.sched;
+    const int rs = sc.row_stride;
+    float* act = smem;
+    int* row_action = reinterpret_cast<int*>(act + TM * rs);
+    unsigned char* row_active = reinterpret_cast<unsigned char*>(row_action + TM);
+    const int tid = threadIdx.x, j = tid & 7, row = tid >> 3;
+    const unsigned gmask = 0xFFu << ((tid & 31) & 24);
+    const int b = blockIdx.x * TM + row;
+    const bool valid = b < p.B;
+    const bool fed = p.fed_root != nullptr;
+
+    if (j == 0) {
+        row_active[row] = valid ? 1 : 0;
+        row_action[row] = (valid && p.action) ? p.action[b] : 0;
+    }
+    if (valid && !fed) {
+        const float* src = p.in + (size_t)b * sc.in_dim;
+        float* dst = act + row * rs + sc.off_in;
+        for (int i = j; i < sc.in_dim; i += GW) dst[i] = src[i];
+    }
+    __syncthreads();
+    const int nz = (p.mode == 2) ? p.nf : 1;
+    for (int z = 0; z < nz; ++z) {
+        if (!fed) run_schedule<TM, THREADS>(sc, p.W, act, row_action, row_active, p.A, z);
+        if (valid && !fed) {
+            const float* r = act + row * rs;
+            const int V = 2 * p.support + 1;
+            if (p.mode == 2) {
+                if (p.hidden_out)
+                    for (int i = j; i < p.H; i += GW) p.hidden_out[((size_t)b * p.nf + z) * p.H + i] = r[sc.off_hidden + i];
+                const float rw = support_to_scalar_group(r + sc.off_rl, p.support, j, gmask);
+                if (p.reward && j == 0) p.reward[(size_t)b * p.nf + z] = rw;
+                if (z == 0 && p.transition_logits && j < p.nf) p.transition_logits[(size_t)b * p.nf + j] = r[sc.off_tp + j];
+            } else {
+                if (p.hidden_out && sc.off_hidden >= 0)
+                    for (int i = j; i < p.H; i += GW) p.hidden_out[(size_t)b * p.H + i] = r[sc.off_hidden + i];
+                if (p.policy_logits && j < p.A) p.policy_logits[(size_t)b * p.A + j] = r[sc.off_pl + j];
+                if (p.value_logits)
+                    for (int i = j; i < V; i += GW) p.value_logits[(size_t)b * V + i] = r[sc.off_vl + i];
+                if (p.value) {
+                    const float v = support_to_scalar_group(r + sc.off_vl, p.support, j, gmask);
+                    if (j == 0) p.value[b] = v;
+                }
+                if (p.mode == 1) {
+                    if (p.reward_logits)
+                        for (int i = j; i < V; i += GW) p.reward_logits[(size_t)b * V + i] = r[sc.off_rl + i];
+                    if (p.reward) {
+                        const float v = support_to_scalar_group(r + sc.off_rl, p.support, j, gmask);
+                        if (j == 0) p.reward[b] = v;
+                    }
+                    if (p.terminal && j == 0) p.terminal[b] = sc.off_tl >= 0 ? r[sc.off_tl] : -1.0f;
+                }
+            }
+        }
+        if (nz > 1) __syncthreads();
+    }
+
+    if (p.tree_init && valid) {
+        // ---- root of the search: self_play.py:335-376 ----
+        const float* r = act + row * rs;
+        const int nl = p.num_legal ? p.num_legal[b] : p.A;
+        const int a_j = (j < nl) ? (p.legal ? p.legal[(size_t)b * p.A + j] : j) : 0;
+        float prior, value;
+        if (fed) {
+            value = p.fed_root[(size_t)b * REC + 1];
+            prior = (j < nl) ? p.fed_root[(size_t)b * REC + 4 + j] : 0.0f;
+        } else {
+            value = support_to_scalar_group(r + sc.off_vl, p.support, j, gmask);
+            const float lg = (j < nl && !p.uniform_policy) ? r[sc.off_pl + a_j] : 0.0f;
+            prior = softmax_group(lg, j < nl, gmask);  // Node.expand, self_play.py:532-538
+        }
+        if (p.trace_root) {
+            float* tr = p.trace_root + (size_t)b * REC;
+            for (int i = j; i < REC; i += GW) tr[i] = 0.0f;
+            __syncwarp(gmask);
+            if (j == 0) { tr[0] = 1.0f; tr[1] = value; }
+            if (j < nl) tr[4 + j] = prior;
+        }
+        double pr64 = (double)prior;
+        if (p.add_noise && j < nl)  // add_exploration_noise, self_play.py:540-549
+            pr64 = __dadd_rn(__dmul_rn(pr64, p.one_minus_frac), __dmul_rn(p.noise[(size_t)b * p.A + j], p.frac));
+        p.rootprior[(size_t)b * GW + j] = (j < nl) ? pr64 : 0.0;
+        p.rootact[(size_t)b * GW + j] = a_j;
+        NodeBlock<NC>* blk = reinterpret_cast<NodeBlock<NC>*>(p.blocks) + (size_t)b * p.blocks_per_tree;
+        if (j < NC) {
+            blk->visit[j] = 0;
+            blk->child[j] = -1;
+            blk->prior[j] = prior;
+            blk->reward[j] = 0.0f;
+            blk->vsum[j] = 0.0;
+        }
+        if (j == 0) {
+            blk->parent = -1;
+            blk->aux = 0;
+            TreeHeader h;
+            h.mm_min = CUDART_INF;
+            h.mm_max = -CUDART_INF;
+            h.root_vsum = 0.0;
+            h.root_visit = 0;
+            h.n_blocks = 1;
+            h.n_tgroups = 0;
+            h.max_depth = 0;
+            h.n_sims = 0;
+            h.k_tie = 0;
+            h.k_chance = 0;
+            h.n_rec = 0;
+            h.root_pred = value;
+            h.n_root = nl;
+            p.hdr[b] = h;
+            if (p.root_pred) p.root_pred[b] = value;
+        }
+        if (!fed) {
+            float* hp = p.hidden_pool + (size_t)b * p.hidden_per_tree * p.H;
+            for (int i = j; i < p.H; i += GW) {
+                const float v = r[sc.off_hidden + i];
+                hp[i] = v;
+                if (p.root_hidden) p.root_hidden[(size_t)b * p.H + i] = v;
+            }
+        }
+    }
+}
+
+// -------------------------------------------------------------- search kernel ----
+// VARIANT 0: MCTS.run of self_play.py:378-427; 1: self_play_stochastic.py:329-393; 2: risk-sensitive.
+template <int VARIANT, int NC, int TM>
+__global__ void __launch_bounds__(TM * GW) search_kernel(const __grid_constant__ SearchParams p) {
+    extern __shared__ __align__(16) float smem[];
+    constexpr int THREADS = TM * GW;
+    using Block = NodeBlock<NC>;
+    const int rs = p.sched_a.row_stride;  // the host gives sched_a and sched_b the same row stride
+    double* pb = reinterpret_cast<double*>(smem);
+    const int pb_n = (p.S + 2 + 1) & ~1;
+    float* act = reinterpret_cast<float*>(pb + pb_n);
+    int* row_action = reinterpret_cast<int*>(act + TM * rs);
+    unsigned char* row_active = reinterpret_cast<unsigned char*>(row_action + TM);
+    unsigned char* row_kind = row_active + TM;
+
+    const int tid = threadIdx.x, lane = tid & 31, j = tid & 7, row = tid >> 3;
+    const unsigned gmask = 0xFFu << (lane & 24);
+    const int gl0 = lane & 24;  // first lane of this group inside the warp
+    const int b = blockIdx.x * TM + row;
+    const bool valid = b < p.B;
+    const bool fed = p.fed != nullptr;
+    const int A = p.A, H = p.H, nf = p.nf;
+    const double discount = p.discount;
+
+    for (int i = tid; i < p.S + 2; i += THREADS) pb[i] = p.pb_table[i];
+
+    Block* blocks = reinterpret_cast<Block*>(p.blocks) + (size_t)(valid ? b : 0) * p.blocks_per_tree;
+    float* hpool = p.hidden_pool + (size_t)(valid ? b : 0) * p.hidden_per_tree * H;
+    const float* fed_rec = fed ? p.fed + (size_t)(valid ? b : 0) * p.max_rec * REC : nullptr;
+    float* trace_rec = p.trace ? p.trace + (size_t)(valid ? b : 0) * p.max_rec * REC : nullptr;
+
+    // per-tree state, replicated in the 8 lanes of the group
+    MinMax mm;
+    mm.mn = CUDART_INF;
+    mm.mx = -CUDART_INF;
+    double root_vsum = 0.0, root_prior = 0.0;
+    int root_visit = 0, n_blocks = 1, n_tgroups = 0, max_depth = 0, n_sims = 0, k_tie = 0, k_chance = 0, n_rec = 0;
+    int n_root = 0, root_act = 0;
+    if (valid) {
+        const TreeHeader h = p.hdr[b];
+        n_root = h.n_root;
+        root_prior = p.rootprior[(size_t)b * GW + j];
+        root_act = p.rootact[(size_t)b * GW + j];
+    }
+    __syncthreads();
+
+    for (int it = 0; it < p.max_iters; ++it) {
+        if (fed && n_rec >= p.max_rec) n_sims = p.S;  // fed records exhausted: stop this tree (results will not match)
+        const bool active = valid && n_sims < p.S;
+        if (VARIANT != 0) {
+            if (!__syncthreads_or(active ? 1 : 0)) break;
+        } else {
+            if (it >= p.S) break;
+        }
+
+        // ================= phase 1: selection (one 8-lane group per tree) =================
+        int node = 0, slot = 0, depth = 0, Np = root_visit;
+        bool parent_is_state = true;  // kind of block `node`
+        if (active) {
+            while (true) {
+                const Block* blk = blocks + node;
+                int vis_sel, child_sel;
+                if (VARIANT == 0 || parent_is_state) {
+                    const int nch = (node == 0) ? n_root : A;
+                    const bool on = j < nch;
+                    int vis = 0, ch = -1;
+                    double vs = 0.0, prior = 0.0;
+                    float rw = 0.0f;
+                    if (on) {
+                        vis = blk->visit[j];
+                        ch = blk->child[j];
+                        vs = blk->vsum[j];
+                        rw = blk->reward[j];
+                        prior = (node == 0) ? root_prior : (double)blk->prior[j];
+                    }
+                    double score = -CUDART_INF;
+                    if (on) score = ucb_score<VARIANT>(pb[Np], Np, vis, vs, prior, rw, discount, mm);
+                    double best = score;
+#pragma unroll
+                    for (int d = 1; d < GW; d <<= 1) {
+                        const double o = shfl_xor_d(gmask, best, d);
+                        best = o > best ? o : best;
+                    }
+                    const unsigned tied = (__ballot_sync(gmask, on && score == best) >> gl0) & 0xFFu;
+                    const int nt = __popc(tied);
+                    if (nt == 1) {
+                        slot = __ffs(tied) - 1;
+                    } else {  // self_play.py:444-450 with the external tie stream
+                        int v = 0;
+                        if (p.tie) v = p.tie[(size_t)b * p.T + (k_tie % p.T)];
+                        k_tie++;
+                        slot = __fns(tied, 0, (v % nt) + 1);
+                    }
+                    vis_sel = __shfl_sync(gmask, vis, gl0 + slot);
+                    child_sel = __shfl_sync(gmask, ch, gl0 + slot);
+                } else {  // TransitionNode.select_child, self_play_stochastic.py:517-533
+                    slot = 0;
+                    if (nf > 1) {
+                        const int v = p.chance ? p.chance[(size_t)b * p.K + (k_chance % p.K)] : 0;
+                        k_chance++;
+                        slot = v % nf;
+                    }
+                    vis_sel = blk->visit[slot];
+                    child_sel = blk->child[slot];
+                }
+                depth++;
+                if (child_sel < 0) break;
+                node = child_sel;
+                Np = vis_sel;
+                if (VARIANT != 0) parent_is_state = !parent_is_state;
+            }
+        }
+        // leaf = child `slot` of block `node`
+        const bool leaf_is_state = (VARIANT == 0) ? true : !parent_is_state;
+        int action = 0, hslot = 0;
+        if (active) {
+            if (VARIANT == 0) {
+                action = (node == 0) ? __shfl_sync(gmask, root_act, gl0 + slot) : slot;
+                hslot = node;
+            } else if (!leaf_is_state) {
+                action = (node == 0) ? __shfl_sync(gmask, root_act, gl0 + slot) : slot;
+                hslot = (node == 0) ? 0 : (blocks[node].aux >> 8);
+            } else {
+                hslot = 1 + (blocks[node].aux >> 8) * nf + slot;
+            }
+            if (depth > max_depth) max_depth = depth;
+        }
+        const int kind = !active ? 0 : (leaf_is_state ? 1 : 2);
+
+        // ================= phase 2: network evaluation of the leaf batch =================
+        float value = 0.0f, reward = 0.0f, terminal = -1.0f, prior = 0.0f;  // state-leaf results
+        float tprior = 0.0f, treward = 0.0f;                               // transition-leaf results (lane z)
+        if (!fed) {
+            if (j == 0) {
+                row_action[row] = action;
+                row_kind[row] = (unsigned char)kind;
+                if (VARIANT == 0) row_active[row] = active ? 1 : 0;
+            }
+            if (active) {  // gather the input hidden state of this row
+                const float4* src = reinterpret_cast<const float4*>(hpool + (size_t)hslot * H);
+                float4* dst = reinterpret_cast<float4*>(act + row * rs);  // off_in == 0 in every search schedule
+                for (int i = j; i < (H >> 2); i += GW) dst[i] = src[i];
+            }
+            __syncthreads();
+            if (VARIANT == 0) {
+                run_schedule<TM, THREADS>(p.sched_a, p.W, act, row_action, row_active, A, 0);
+                if (active) {
+                    const float* r = act + row * rs;
+                    value = support_to_scalar_group(r + p.sched_a.off_vl, p.support, j, gmask);
+                    reward = support_to_scalar_group(r + p.sched_a.off_rl, p.support, j, gmask);
+                    if (p.mask_absorbing) terminal = r[p.sched_a.off_tl];
+                    const float lg = (j < A && !p.uniform_policy) ? r[p.sched_a.off_pl + j] : 0.0f;
+                    prior = softmax_group(lg, j < A, gmask);
+                }
+            } else {
+                const int any_t = __syncthreads_or(kind == 2);
+                const int any_s = __syncthreads_or(kind == 1);
+                if (any_t) {
+                    if (j == 0) row_active[row] = (kind == 2) ? 1 : 0;
+                    __syncthreads();
+                    for (int z = 0; z < nf; ++z) {
+                        run_schedule<TM, THREADS>(p.sched_a, p.W, act, row_action, row_active, A, z);
+                        if (kind == 2) {
+                            const float* r = act + row * rs;
+                            const float rw = support_to_scalar_group(r + p.sched_a.off_rl, p.support, j, gmask);
+                            if (j == z) treward = rw;
+                            if (z == 0) {
+                                const float lg = (j < nf) ? r[p.sched_a.off_tp + j] : 0.0f;
+                                tprior = softmax_group(lg, j < nf, gmask);  // self_play_stochastic.py:553-554
+                            }
+                            // children's hidden states: slot 1 + t_ord * nf + z  (t_ord == n_tgroups)
+                            float4* dst = reinterpret_cast<float4*>(hpool + (size_t)(1 + n_tgroups * nf + z) * H);
+                            const float4* src = reinterpret_cast<const float4*>(r + p.sched_a.off_hidden);
+                            for (int i = j; i < (H >> 2); i += GW) dst[i] = src[i];
+                        }
+                        __syncthreads();
+                    }
+                }
+                if (any_s) {
+                    if (j == 0) row_active[row] = (kind == 1) ? 1 : 0;
+                    __syncthreads();
+                    run_schedule<TM, THREADS>(p.sched_b, p.W, act, row_action, row_active, A, 0);
+                    if (kind == 1) {
+                        const float* r = act + row * rs;
+                        value = support_to_scalar_group(r + p.sched_b.off_vl, p.support, j, gmask);
+                        const float lg = (j < A) ? r[p.sched_b.off_pl + j] : 0.0f;
+                        prior = softmax_group(lg, j < A, gmask);
+                    }
+                }
+            }
+        } else if (active) {
+            const float* fr = fed_rec + (size_t)n_rec * REC;
+            if (kind == 1) {
+                value = fr[1];
+                reward = fr[2];
+                terminal = fr[3];
+                prior = (j < A) ? fr[4 + j] : 0.0f;
+            } else {
+                tprior = (j < nf) ? fr[1 + j] : 0.0f;
+                treward = (j < nf) ? fr[1 + nf + j] : 0.0f;
+            }
+        }
+
+        // ================= phase 3: expansion + backup (one group per tree) =================
+        if (active) {
+            if (trace_rec && n_rec < p.max_rec) {
+                float* tr = trace_rec + (size_t)n_rec * REC;
+                for (int i = j; i < REC; i += GW) tr[i] = 0.0f;
+                __syncwarp(gmask);
+                if (kind == 1) {
+                    if (j == 0) {
+                        tr[0] = 1.0f;
+                        tr[1] = value;
+                        if (VARIANT == 0) {
+                            tr[2] = reward;
+                            tr[3] = terminal;
+                        }
+                    }
+                    if (j < A) tr[4 + j] = prior;
+                } else {
+                    if (j == 0) tr[0] = 2.0f;
+                    if (j < nf) {
+                        tr[1 + j] = tprior;
+                        tr[1 + nf + j] = treward;
+                    }
+                }
+            }
+            n_rec++;
+            Block* pblk = blocks + node;
+            if (kind == 2) {
+                // ---- TransitionNode.expand, self_play_stochastic.py:535-557 (no backup, no sim count) ----
+                const int nb = n_blocks++;
+                Block* nblk = blocks + nb;
+                if (j < NC) {
+                    nblk->visit[j] = 0;
+                    nblk->child[j] = -1;
+                    nblk->prior[j] = tprior;
+                    nblk->reward[j] = (j < nf) ? treward : 0.0f;  // decoded child_rewards[z]; read only once visited
+                    nblk->vsum[j] = 0.0;
+                }
+                if (j == 0) {
+                    nblk->parent = node;
+                    nblk->aux = slot | (n_tgroups << 8);
+                    pblk->child[slot] = nb;
+                }
+                n_tgroups++;
+            } else {
+                const bool masked = (VARIANT == 0) && p.mask_absorbing && (terminal >= 0.0f);  // self_play.py:408-417
+                double v = masked ? 0.0 : (double)value;
+                if (!masked) {
+                    // ---- Node.expand, self_play.py:524-538 ----
+                    const int nb = n_blocks++;
+                    Block* nblk = blocks + nb;
+                    if (j < NC) {
+                        nblk->visit[j] = 0;
+                        nblk->child[j] = -1;
+                        nblk->prior[j] = prior;
+                        nblk->reward[j] = 0.0f;
+                        nblk->vsum[j] = 0.0;
+                    }
+                    if (j == 0) {
+                        nblk->parent = node;
+                        nblk->aux = slot | ((VARIANT == 0 ? nb : hslot) << 8);
+                        pblk->child[slot] = nb;
+                        if (VARIANT == 0) pblk->reward[slot] = reward;
+                    }
+                    if (VARIANT == 0 && !fed) {  // hidden state of the new node
+                        float4* dst = reinterpret_cast<float4*>(hpool + (size_t)nb * H);
+                        const float4* src = reinterpret_cast<const float4*>(act + row * rs + p.sched_a.off_hidden);
+                        for (int i = j; i < (H >> 2); i += GW) dst[i] = src[i];
+                    }
+                }
+                __syncwarp(gmask);
+                // ---- backup: every lane of the group walks the path redundantly, lane 0 stores ----
+                int cur = node, cs = slot;
+                if (VARIANT == 0) {
+                    // self_play.py:485-490
+                    while (true) {
+                        Block* bk = blocks + cur;
+                        const double vs = __dadd_rn(bk->vsum[cs], v);
+                        const int vis = bk->visit[cs] + 1;
+                        const double rw = (double)bk->reward[cs];
+                        __syncwarp(gmask);
+                        if (j == 0) {
+                            bk->vsum[cs] = vs;
+                            bk->visit[cs] = vis;
+                        }
+                        mm.update(__dadd_rn(rw, __dmul_rn(discount, __ddiv_rn(vs, (double)vis))));
+                        v = __dadd_rn(rw, __dmul_rn(discount, v));
+                        if (cur == 0) break;
+                        cs = bk->aux & 0xFF;
+                        cur = bk->parent;
+                    }
+                    root_vsum = __dadd_rn(root_vsum, v);
+                    root_visit += 1;
+                    mm.update(__dadd_rn(0.0, __dmul_rn(discount, __ddiv_rn(root_vsum, (double)root_visit))));
+                } else if (VARIANT == 1) {
+                    // self_play_stochastic.py:408-418; entries alternate State (leaf), Transition, State, ...
+                    bool is_state = true;
+                    while (true) {
+                        Block* bk = blocks + cur;
+                        const double vs = __dadd_rn(bk->vsum[cs], v);
+                        const int vis = bk->visit[cs] + 1;
+                        const double rw = (double)bk->reward[cs];
+                        __syncwarp(gmask);
+                        if (j == 0) {
+                            bk->vsum[cs] = vs;
+                            bk->visit[cs] = vis;
+                        }
+                        if (is_state) {
+                            v = __dadd_rn(rw, __dmul_rn(discount, v));
+                            mm.update(__dadd_rn(rw, __dmul_rn(discount, __ddiv_rn(vs, (double)vis))));
+                        }
+                        is_state = !is_state;
+                        if (cur == 0) break;
+                        cs = bk->aux & 0xFF;
+                        cur = bk->parent;
+                    }
+                    root_vsum = __dadd_rn(root_vsum, v);
+                    root_visit += 1;
+                    v = __dadd_rn(0.0, __dmul_rn(discount, v));
+                    mm.update(__dadd_rn(0.0, __dmul_rn(discount, __ddiv_rn(root_vsum, (double)root_visit))));
+                } else {
+                    // self_play_risk_sensitive.py:408-420, 452-461, 529-537
+                    if (j == 0) {
+                        pblk->vsum[slot] = v;  // search_path[-1].value = value
+                        pblk->visit[slot] = pblk->visit[slot] + 1;
+                    }
+                    __syncwarp(gmask);
+                    bool is_transition = true;  // kind of the node that OWNS block `cur`
+                    while (true) {
+                        Block* bk = blocks + cur;  // children statistics of the node being updated
+                        double nv;
+                        if (is_transition) {
+                            double best = 0.0;
+                            bool have = false;
+                            for (int k = 0; k < nf; ++k) {
+                                if (bk->visit[k] > 0) {
+                                    const double t = __dadd_rn((double)bk->reward[k], __dmul_rn(discount, bk->vsum[k]));
+                                    if (!have || t < best) best = t;
+                                    have = true;
+                                }
+                            }
+                            nv = best;
+                        } else {
+                            const int nch = (cur == 0) ? n_root : A;
+                            double sum = 0.0;
+                            int counts = 0;
+                            for (int k = 0; k < nch; ++k) {
+                                const int c = bk->visit[k];
+                                sum = __dadd_rn(sum, __dmul_rn((double)c, bk->vsum[k]));
+                                counts += c;
+                            }
+                            nv = __ddiv_rn(sum, (double)counts);
+                        }
+                        if (cur == 0) {  // the root (a StateNode, reward 0)
+                            root_vsum = nv;
+                            root_visit += 1;
+                            mm.update(__dadd_rn(0.0, __dmul_rn(discount, nv)));
+                            break;
+                        }
+                        const int ps = bk->aux & 0xFF, pc = bk->parent;
+                        Block* pb2 = blocks + pc;
+                        const int vis = pb2->visit[ps] + 1;
+                        const double rw = (double)pb2->reward[ps];
+                        __syncwarp(gmask);
+                        if (j == 0) {
+                            pb2->vsum[ps] = nv;
+                            pb2->visit[ps] = vis;
+                        }
+                        __syncwarp(gmask);
+                        if (!is_transition) mm.update(__dadd_rn(rw, __dmul_rn(discount, nv)));
+                        is_transition = !is_transition;
+                        cur = pc;
+                    }
+                }
+                n_sims++;
+            }
+        }
+        // No CTA barrier here: a row's activation strip is re-filled by the very group that read it in
+        // phase 3, and every tile of this iteration finished before run_schedule's last barrier.
+        __syncwarp(gmask);
+    }
+
+    // ================= outputs: what consumers read from `root` =================
+    if (valid) {
+        const Block* rb = blocks;
+        if (j == 0) {
+            if (p.root_value)
+                p.root_value[b] = (VARIANT == 2) ? root_vsum
+                                                 : (root_visit == 0 ? 0.0 : __ddiv_rn(root_vsum, (double)root_visit));
+            if (p.max_depth) p.max_depth[b] = max_depth;
+            if (p.num_records) p.num_records[b] = n_rec;
+        }
+        if (j < A) {  // zero-fill, then scatter the legal children to their action index
+            if (p.visit_counts) p.visit_counts[(size_t)b * A + j] = 0;
+            if (p.child_value) p.child_value[(size_t)b * A + j] = 0.0;
+            if (p.child_prior) p.child_prior[(size_t)b * A + j] = 0.0;
+            if (p.child_reward) p.child_reward[(size_t)b * A + j] = 0.0;
+        }
+        __syncwarp(gmask);
+        if (j < n_root) {
+            const int a = root_act;
+            const int vis = rb->visit[j];
+            const double vs = rb->vsum[j];
+            if (p.visit_counts) p.visit_counts[(size_t)b * A + a] = vis;
+            if (p.child_value)
+                p.child_value[(size_t)b * A + a] = (VARIANT == 2) ? vs : (vis == 0 ? 0.0 : __ddiv_rn(vs, (double)vis));
+            if (p.child_prior) p.child_prior[(size_t)b * A + a] = root_prior;
+            if (p.child_reward) p.child_reward[(size_t)b * A + a] = (double)rb->reward[j];
+        }
+    }
+}
+
+}  // namespace tsp

@@ -1,0 +1,828 @@
+// tsp_engine.cu -- host side of libtsp_b200.so: engine object, weight packing, MLP schedule
+// construction, pool management, kernel launches and the extern "C" ABI of include/tsp.h.
+// There is no CPU fallback in this file: every entry point either runs CUDA kernels or fails.
+#include "tsp_device.cuh"
+#include "../../include/tsp.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace tsp;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct HostLayer {
+    int out_dim = 0, in_dim = 0;
+    std::vector<float> W, b;
+    int w_off = -1, b_off = -1, npad = 0;  // arena placement
+};
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+// ---- host-side schedule description, lowered to tsp::Schedule ----
+struct HOp {
+    int mlp, layer, in_buf, out_buf, act, extra;
+};
+struct HStage {
+    std::vector<HOp> ops;
+    int rop = 0, r_in = -1, r_out = -1, r_n = 0;
+};
+struct HSched {
+    std::vector<int> width;  // per buffer
+    std::vector<int> ready;  // first stage at which the buffer can be read
+    std::vector<HStage> stages;
+    int in_buf = -1, hidden = -1, pl = -1, vl = -1, rl = -1, tl = -1, tp = -1;
+    int in_dim = 0;
+    int new_buf(int w, int ready_stage) {
+        width.push_back((w + 3) & ~3);
+        ready.push_back(ready_stage);
+        return (int)width.size() - 1;
+    }
+    HStage& stage(int s) {
+        while ((int)stages.size() <= s) stages.emplace_back();
+        return stages[s];
+    }
+};
+
+}  // namespace
+
+struct tsp_engine {
+    tsp_config cfg{};
+    std::string err;
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool ev_valid = false;
+    std::vector<HostLayer> mlp[TSP_NUM_MLP];
+    bool finalized = false;
+    int nc = 5;  // node-block child capacity (5 or 8)
+    int tm_override = 0;
+
+    // device memory
+    DevBuf arena;  // packed weights
+    int64_t arena_floats = 0;
+    DevBuf blocks, hidden, hdr, rootprior, rootact, pbtable;
+    int blocks_per_tree = 0, hidden_per_tree = 0, max_iters = 0;
+    // staging for HOST-memory calls
+    DevBuf s_obs, s_legal, s_nlegal, s_noise, s_tie, s_chance, s_fedroot, s_fed;
+    DevBuf s_visits, s_rootv, s_cval, s_cprior, s_crew, s_depth, s_rpred, s_rhid, s_nrec, s_troot, s_trace;
+    DevBuf n_in, n_act, n_o[8];
+
+    Schedule sch_root{}, sch_recur{}, sch_trans{}, sch_pred{};
+    bool has_root = false, has_recur = false, has_trans = false, has_pred = false;
+
+    tsp_stats stats{};
+    int64_t pool_bytes = 0;
+};
+
+namespace {
+
+int fail(tsp_engine* e, int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (e)
+        e->err = buf;
+    else
+        g_create_error = buf;
+    return code;
+}
+
+#define CK(e, call)                                                                                   \
+    do {                                                                                              \
+        cudaError_t _st = (call);                                                                     \
+        if (_st != cudaSuccess)                                                                       \
+            return fail(e, TSP_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_st), __FILE__, __LINE__); \
+    } while (0)
+
+int ensure(tsp_engine* e, DevBuf& b, size_t bytes) {
+    if (bytes <= b.cap) return TSP_OK;
+    if (b.p) {
+        CK(e, cudaStreamSynchronize(e->stream));
+        CK(e, cudaFree(b.p));
+        e->pool_bytes -= (int64_t)b.cap;
+        b.p = nullptr;
+        b.cap = 0;
+    }
+    cudaError_t st = cudaMalloc(&b.p, bytes);
+    if (st != cudaSuccess) {
+        b.p = nullptr;
+        return fail(e, TSP_ENOMEM, "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(st));
+    }
+    b.cap = bytes;
+    e->pool_bytes += (int64_t)bytes;
+    return TSP_OK;
+}
+
+void release(DevBuf& b) {
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+}
+
+// ---- schedule construction ----
+// Appends the Linear layers of `mlp_id` reading `in_buf`; returns the output buffer.
+int add_chain(tsp_engine* e, HSched& hs, int mlp_id, int in_buf, int extra_first) {
+    const auto& layers = e->mlp[mlp_id];
+    int cur = in_buf;
+    for (size_t l = 0; l < layers.size(); ++l) {
+        int s = hs.ready[cur];
+        while ((int)hs.stage(s).ops.size() >= MAX_OPS) ++s;
+        const int out = hs.new_buf(layers[l].out_dim, s + 1);
+        HOp op{mlp_id, (int)l, cur, out, l + 1 < layers.size() ? 1 : 0, l == 0 ? extra_first : 0};
+        hs.stage(s).ops.push_back(op);
+        cur = out;
+    }
+    return cur;
+}
+
+int add_normalise(HSched& hs, int in_buf, int n) {
+    int s = hs.ready[in_buf];
+    while (hs.stage(s).rop != 0) ++s;
+    const int out = hs.new_buf(n, s + 1);
+    HStage& st = hs.stage(s);
+    st.rop = 1;
+    st.r_in = in_buf;
+    st.r_out = out;
+    st.r_n = n;
+    return out;
+}
+
+int lower(tsp_engine* e, const HSched& hs, Schedule& sc, bool keep_input = false) {
+    const int nb = (int)hs.width.size();
+    const int ns = (int)hs.stages.size();
+    if (ns > MAX_STAGES) return fail(e, TSP_EINVAL, "network too deep: %d stages > %d", ns, MAX_STAGES);
+    const int INF = 1 << 20;
+    std::vector<int> def(nb, INF), last(nb, -1), off(nb, -1);
+    def[hs.in_buf] = -1;
+    for (int s = 0; s < ns; ++s) {
+        for (const HOp& op : hs.stages[s].ops) {
+            def[op.out_buf] = std::min(def[op.out_buf], s);
+            last[op.in_buf] = std::max(last[op.in_buf], s);
+        }
+        if (hs.stages[s].rop) {
+            def[hs.stages[s].r_out] = std::min(def[hs.stages[s].r_out], s);
+            last[hs.stages[s].r_in] = std::max(last[hs.stages[s].r_in], s);
+        }
+    }
+    for (int o : {hs.hidden, hs.pl, hs.vl, hs.rl, hs.tl, hs.tp})
+        if (o >= 0) last[o] = INF;
+    last[hs.in_buf] = std::max(last[hs.in_buf], 0);
+    if (keep_input) last[hs.in_buf] = INF;  // the schedule is evaluated once per future z on the same input
+    // first-fit with liveness: two buffers may share space iff their [def, last] ranges are disjoint
+    std::vector<int> order(nb);
+    for (int i = 0; i < nb; ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return def[a] < def[b]; });
+    int total = 0;
+    for (int idx = 0; idx < nb; ++idx) {
+        const int b = order[idx];
+        int pos = 0;
+        bool moved = true;
+        while (moved) {
+            moved = false;
+            for (int j = 0; j < idx; ++j) {
+                const int o = order[j];
+                const bool live_overlap = !(last[o] < def[b] || last[b] < def[o]);
+                if (live_overlap && pos < off[o] + hs.width[o] && off[o] < pos + hs.width[b]) {
+                    pos = off[o] + hs.width[o];
+                    moved = true;
+                }
+            }
+        }
+        off[b] = pos;
+        total = std::max(total, pos + hs.width[b]);
+    }
+    total += ((4 - total % 32) + 32) % 32;  // row stride == 4 (mod 32)
+    if (total > 32000) return fail(e, TSP_EINVAL, "activation strip too wide (%d floats)", total);
+    memset(&sc, 0, sizeof(sc));
+    sc.n_stages = ns;
+    sc.row_stride = total;
+    sc.in_dim = hs.in_dim;
+    auto o16 = [&](int b) { return (short)(b >= 0 ? off[b] : -1); };
+    sc.off_in = o16(hs.in_buf);
+    sc.off_hidden = o16(hs.hidden);
+    sc.off_pl = o16(hs.pl);
+    sc.off_vl = o16(hs.vl);
+    sc.off_rl = o16(hs.rl);
+    sc.off_tl = o16(hs.tl);
+    sc.off_tp = o16(hs.tp);
+    for (int s = 0; s < ns; ++s) {
+        Stage& st = sc.st[s];
+        const HStage& h = hs.stages[s];
+        st.n_ops = (unsigned char)h.ops.size();
+        st.row_op = (unsigned char)h.rop;
+        if (h.rop) {
+            st.r_in = o16(h.r_in);
+            st.r_out = o16(h.r_out);
+            st.r_n = (short)h.r_n;
+        }
+        for (size_t i = 0; i < h.ops.size(); ++i) {
+            const HOp& op = h.ops[i];
+            const HostLayer& L = e->mlp[op.mlp][op.layer];
+            LayerOp& d = st.ops[i];
+            d.w_off = L.w_off;
+            d.b_off = L.b_off;
+            d.N = (short)L.out_dim;
+            d.Npad = (short)L.npad;
+            d.in_off = o16(op.in_buf);
+            d.out_off = o16(op.out_buf);
+            d.act = (unsigned char)op.act;
+            d.extra = (unsigned char)op.extra;
+            int k = L.in_dim;
+            if (op.extra == 1) k -= e->cfg.num_actions;
+            if (op.extra == 2) k -= e->cfg.num_actions + e->cfg.n_futures;
+            d.K = (short)k;
+        }
+    }
+    return TSP_OK;
+}
+
+int build_schedules(tsp_engine* e) {
+    const tsp_config& c = e->cfg;
+    const int H = c.encoding_size, A = c.num_actions;
+    const bool stochastic = c.variant != TSP_VARIANT_MUZERO;
+    auto have = [&](int m) { return !e->mlp[m].empty(); };
+    auto check_io = [&](int m, int in, int out, const char* name) -> int {
+        if (!have(m)) return fail(e, TSP_ESTATE, "weights of the %s network were not loaded", name);
+        if (e->mlp[m].front().in_dim != in || e->mlp[m].back().out_dim != out)
+            return fail(e, TSP_EINVAL, "%s network has shape %d -> %d, expected %d -> %d", name,
+                        e->mlp[m].front().in_dim, e->mlp[m].back().out_dim, in, out);
+        return TSP_OK;
+    };
+    const int V = 2 * c.support_size + 1;
+    int rc;
+    if ((rc = check_io(TSP_MLP_REPRESENTATION, c.obs_dim, H, "representation"))) return rc;
+    if ((rc = check_io(TSP_MLP_DYNAMICS, H + A + (stochastic ? c.n_futures : 0), H, "dynamics"))) return rc;
+    if ((rc = check_io(TSP_MLP_REWARD, H, V, "reward"))) return rc;
+    if ((rc = check_io(TSP_MLP_POLICY, H, A, "policy"))) return rc;
+    if ((rc = check_io(TSP_MLP_VALUE, H, V, "value"))) return rc;
+    if (stochastic && (rc = check_io(TSP_MLP_PRIOR, H, c.n_futures, "transition prior"))) return rc;
+    if (c.mask_absorbing_states && (rc = check_io(TSP_MLP_TERMINAL, H, 1, "terminal"))) return rc;
+
+    {  // root: models.py:259-281 (reconstruction head skipped: MCTS discards it)
+        HSched hs;
+        hs.in_dim = c.obs_dim;
+        hs.in_buf = hs.new_buf(c.obs_dim, 0);
+        const int raw = add_chain(e, hs, TSP_MLP_REPRESENTATION, hs.in_buf, 0);
+        hs.hidden = add_normalise(hs, raw, H);
+        hs.pl = add_chain(e, hs, TSP_MLP_POLICY, hs.hidden, 0);
+        hs.vl = add_chain(e, hs, TSP_MLP_VALUE, hs.hidden, 0);
+        if ((rc = lower(e, hs, e->sch_root))) return rc;
+        e->has_root = true;
+    }
+    {  // prediction: models.py:209-212
+        HSched hs;
+        hs.in_dim = H;
+        hs.in_buf = hs.new_buf(H, 0);
+        hs.pl = add_chain(e, hs, TSP_MLP_POLICY, hs.in_buf, 0);
+        hs.vl = add_chain(e, hs, TSP_MLP_VALUE, hs.in_buf, 0);
+        if ((rc = lower(e, hs, e->sch_pred))) return rc;
+        e->has_pred = true;
+    }
+    if (!stochastic) {  // recurrent inference: models.py:233-257, 283-287
+        HSched hs;
+        hs.in_dim = H;
+        hs.in_buf = hs.new_buf(H, 0);
+        const int raw = add_chain(e, hs, TSP_MLP_DYNAMICS, hs.in_buf, 1);
+        hs.rl = add_chain(e, hs, TSP_MLP_REWARD, raw, 0);  // reward / terminal read the UN-normalised state
+        if (have(TSP_MLP_TERMINAL) && e->mlp[TSP_MLP_TERMINAL].back().out_dim == 1 &&
+            e->mlp[TSP_MLP_TERMINAL].front().in_dim == H)
+            hs.tl = add_chain(e, hs, TSP_MLP_TERMINAL, raw, 0);
+        hs.hidden = add_normalise(hs, raw, H);
+        hs.pl = add_chain(e, hs, TSP_MLP_POLICY, hs.hidden, 0);
+        hs.vl = add_chain(e, hs, TSP_MLP_VALUE, hs.hidden, 0);
+        if ((rc = lower(e, hs, e->sch_recur))) return rc;
+        e->has_recur = true;
+    } else {  // one future of MuZeroStochasticConcat.dynamics: models.py:520-595
+        HSched hs;
+        hs.in_dim = H;
+        hs.in_buf = hs.new_buf(H, 0);
+        const int raw = add_chain(e, hs, TSP_MLP_DYNAMICS, hs.in_buf, 2);
+        hs.rl = add_chain(e, hs, TSP_MLP_REWARD, raw, 0);
+        hs.hidden = add_normalise(hs, raw, H);
+        hs.tp = add_chain(e, hs, TSP_MLP_PRIOR, hs.in_buf, 0);
+        if ((rc = lower(e, hs, e->sch_trans, true))) return rc;
+        e->has_trans = true;
+        // the search kernel addresses both schedules with one row stride
+        const int rs = std::max(e->sch_trans.row_stride, e->sch_pred.row_stride);
+        e->sch_trans.row_stride = rs;
+        e->sch_pred.row_stride = rs;
+    }
+    for (Schedule* s : {&e->sch_root, &e->sch_pred, &e->sch_recur, &e->sch_trans})
+        if (s->n_stages && s->off_in != 0) return fail(e, TSP_EINVAL, "internal: schedule input not at offset 0");
+    return TSP_OK;
+}
+
+template <typename K>
+int set_smem(tsp_engine* e, K kernel, size_t bytes) {
+    if (bytes > 227 * 1024) return fail(e, TSP_EINVAL, "kernel needs %zu bytes of shared memory (> 227 KB)", bytes);
+    CK(e, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return TSP_OK;
+}
+
+size_t net_smem(const Schedule& sc, int TM) { return (size_t)TM * sc.row_stride * 4 + TM * 4 + TM * 2 + 16; }
+size_t search_smem(const Schedule& sc, int TM, int S) {
+    return (size_t)((S + 3) & ~1) * 8 + (size_t)TM * sc.row_stride * 4 + TM * 4 + TM * 2 + 16;
+}
+
+template <int NC, int TM>
+int launch_net(tsp_engine* e, const NetParams& p) {
+    const size_t smem = net_smem(p.sched, TM);
+    int rc = set_smem(e, net_kernel<NC, TM>, smem);
+    if (rc) return rc;
+    const int grid = (p.B + TM - 1) / TM;
+    net_kernel<NC, TM><<<grid, TM * GW, smem, e->stream>>>(p);
+    CK(e, cudaGetLastError());
+    e->stats.kernel_launches++;
+    return TSP_OK;
+}
+
+int launch_net_any(tsp_engine* e, const NetParams& p) {
+    // wide observation strips: fewer rows per CTA keep the strip under the shared-memory limit
+    const int TM = (net_smem(p.sched, 32) <= 100 * 1024) ? 32 : 16;
+    if (e->nc == 5) return TM == 32 ? launch_net<5, 32>(e, p) : launch_net<5, 16>(e, p);
+    return TM == 32 ? launch_net<8, 32>(e, p) : launch_net<8, 16>(e, p);
+}
+
+template <int VARIANT, int NC, int TM>
+int launch_search(tsp_engine* e, const SearchParams& p) {
+    const size_t smem = search_smem(p.sched_a, TM, p.S);
+    int rc = set_smem(e, search_kernel<VARIANT, NC, TM>, smem);
+    if (rc) return rc;
+    const int grid = (p.B + TM - 1) / TM;
+    search_kernel<VARIANT, NC, TM><<<grid, TM * GW, smem, e->stream>>>(p);
+    CK(e, cudaGetLastError());
+    e->stats.kernel_launches++;
+    e->stats.search_ctas = grid;
+    e->stats.search_smem_bytes = (int)smem;
+    e->stats.trees_per_cta = TM;
+    return TSP_OK;
+}
+
+template <int VARIANT, int NC>
+int launch_search_tm(tsp_engine* e, const SearchParams& p, int TM) {
+    return TM == 32 ? launch_search<VARIANT, NC, 32>(e, p) : launch_search<VARIANT, NC, 16>(e, p);
+}
+
+int launch_search_any(tsp_engine* e, const SearchParams& p) {
+    int TM = 32;
+    // small batches: 16 trees per CTA spreads the work over more SMs
+    if ((p.B + 31) / 32 < 2 * e->sm_count) TM = 16;
+    if (search_smem(p.sched_a, 32, p.S) > 110 * 1024) TM = 16;
+    if (e->tm_override == 16 || e->tm_override == 32) TM = e->tm_override;
+    const int v = e->cfg.variant;
+    if (e->nc == 5) {
+        if (v == 0) return launch_search_tm<0, 5>(e, p, TM);
+        if (v == 1) return launch_search_tm<1, 5>(e, p, TM);
+        return launch_search_tm<2, 5>(e, p, TM);
+    }
+    if (v == 0) return launch_search_tm<0, 8>(e, p, TM);
+    if (v == 1) return launch_search_tm<1, 8>(e, p, TM);
+    return launch_search_tm<2, 8>(e, p, TM);
+}
+
+// copy-in helper: returns the device pointer to use for an input array
+template <typename T>
+int stage_in(tsp_engine* e, int memory, const T* src, size_t count, DevBuf& buf, const T** out) {
+    if (!src) {
+        *out = nullptr;
+        return TSP_OK;
+    }
+    if (memory == TSP_MEM_DEVICE) {
+        *out = src;
+        return TSP_OK;
+    }
+    int rc = ensure(e, buf, count * sizeof(T));
+    if (rc) return rc;
+    CK(e, cudaMemcpyAsync(buf.p, src, count * sizeof(T), cudaMemcpyHostToDevice, e->stream));
+    e->stats.bytes_h2d += (int64_t)(count * sizeof(T));
+    *out = reinterpret_cast<const T*>(buf.p);
+    return TSP_OK;
+}
+
+template <typename T>
+int stage_out(tsp_engine* e, int memory, T* dst, size_t count, DevBuf& buf, T** out) {
+    if (!dst) {
+        *out = nullptr;
+        return TSP_OK;
+    }
+    if (memory == TSP_MEM_DEVICE) {
+        *out = dst;
+        return TSP_OK;
+    }
+    int rc = ensure(e, buf, count * sizeof(T));
+    if (rc) return rc;
+    *out = reinterpret_cast<T*>(buf.p);
+    return TSP_OK;
+}
+
+template <typename T>
+int copy_out(tsp_engine* e, int memory, T* dst, const T* dev, size_t count) {
+    if (!dst || memory == TSP_MEM_DEVICE) return TSP_OK;
+    CK(e, cudaMemcpyAsync(dst, dev, count * sizeof(T), cudaMemcpyDeviceToHost, e->stream));
+    e->stats.bytes_d2h += (int64_t)(count * sizeof(T));
+    return TSP_OK;
+}
+
+}  // namespace
+
+// ================================================================== C ABI ====
+extern "C" {
+
+int tsp_abi_version(void) { return TSP_ABI_VERSION; }
+
+const char* tsp_last_error(tsp_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int tsp_create(const tsp_config* cfg, tsp_handle* out) {
+    if (!cfg || !out) return fail(nullptr, TSP_EINVAL, "tsp_create: null argument");
+    *out = nullptr;
+    if (cfg->num_players != 1)
+        return fail(nullptr, TSP_ENOTIMPL, "only single-player search is implemented (len(players) == %d)", cfg->num_players);
+    if (cfg->variant < 0 || cfg->variant > 2) return fail(nullptr, TSP_EINVAL, "unknown variant %d", cfg->variant);
+    if (cfg->num_actions < 1 || cfg->num_actions > TSP_MAX_ACTIONS)
+        return fail(nullptr, TSP_EINVAL, "num_actions must be in 1..%d", TSP_MAX_ACTIONS);
+    if (cfg->encoding_size < 4 || cfg->encoding_size % 4)
+        return fail(nullptr, TSP_EINVAL, "encoding_size must be a positive multiple of 4");
+    if (cfg->support_size < 0 || cfg->support_size > 300) return fail(nullptr, TSP_EINVAL, "bad support_size");
+    if (cfg->max_roots < 1 || cfg->max_simulations < 0) return fail(nullptr, TSP_EINVAL, "bad capacity");
+    if (cfg->variant != 0 && (cfg->n_futures < 1 || cfg->n_futures > TSP_MAX_ACTIONS))
+        return fail(nullptr, TSP_EINVAL, "n_futures must be in 1..%d", TSP_MAX_ACTIONS);
+    int ndev = 0;
+    cudaError_t st = cudaGetDeviceCount(&ndev);
+    if (st != cudaSuccess || ndev == 0)
+        return fail(nullptr, TSP_ENODEVICE, "no CUDA device (%s); this engine has no CPU fallback",
+                    st == cudaSuccess ? "device count is 0" : cudaGetErrorString(st));
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, TSP_EINVAL, "device %d out of range", cfg->device);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess)
+        return fail(nullptr, TSP_ECUDA, "cudaGetDeviceProperties failed");
+    if (prop.major != 10)
+        return fail(nullptr, TSP_ENODEVICE, "device %d is sm_%d%d; this library is built for sm_100a (B200) only",
+                    cfg->device, prop.major, prop.minor);
+    tsp_engine* e = new tsp_engine();
+    e->cfg = *cfg;
+    if (e->cfg.variant == 0) e->cfg.n_futures = 1;
+    e->device = cfg->device;
+    e->sm_count = prop.multiProcessorCount;
+    e->nc = (std::max(cfg->num_actions, e->cfg.n_futures) <= 5) ? 5 : 8;
+    if (const char* t = getenv("TSP_TREES_PER_CTA")) e->tm_override = atoi(t);
+    auto bail = [&](int rc) {
+        g_create_error = e->err;
+        tsp_destroy(e);
+        return rc;
+    };
+    if (cudaSetDevice(e->device) != cudaSuccess) return bail(fail(e, TSP_ECUDA, "cudaSetDevice failed"));
+    if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess)
+        return bail(fail(e, TSP_ECUDA, "cudaStreamCreate failed"));
+    for (auto& ev : e->ev)
+        if (cudaEventCreate(&ev) != cudaSuccess) return bail(fail(e, TSP_ECUDA, "cudaEventCreate failed"));
+
+    const int S = cfg->max_simulations, A = cfg->num_actions, nf = e->cfg.n_futures, H = cfg->encoding_size;
+    const size_t B = (size_t)cfg->max_roots;
+    if (cfg->variant == 0) {
+        e->blocks_per_tree = S + 1;
+        e->hidden_per_tree = S + 1;
+        e->max_iters = S;
+    } else {
+        // state nodes <= S + 1; every expanded state node has A transition children
+        e->blocks_per_tree = (S + 1) * (A + 1);
+        e->hidden_per_tree = 1 + (S + 1) * A * nf;
+        e->max_iters = S + (S + 1) * A + 1;
+    }
+    const size_t block_bytes = e->nc == 5 ? sizeof(NodeBlock<5>) : sizeof(NodeBlock<8>);
+    int rc;
+    if ((rc = ensure(e, e->blocks, B * e->blocks_per_tree * block_bytes))) return bail(rc);
+    if ((rc = ensure(e, e->hidden, B * e->hidden_per_tree * H * sizeof(float)))) return bail(rc);
+    if ((rc = ensure(e, e->hdr, B * sizeof(TreeHeader)))) return bail(rc);
+    if ((rc = ensure(e, e->rootprior, B * GW * sizeof(double)))) return bail(rc);
+    if ((rc = ensure(e, e->rootact, B * GW * sizeof(int)))) return bail(rc);
+    // pb_c table: log((N + pb_c_base + 1) / pb_c_base) + pb_c_init with the host libm, the same
+    // correctly-rounded log CPython's math.log calls (self_play.py:457-462)
+    std::vector<double> pb(S + 2);
+    for (int n = 0; n < S + 2; ++n)
+        pb[n] = std::log(((double)n + cfg->pb_c_base + 1.0) / cfg->pb_c_base) + cfg->pb_c_init;
+    if ((rc = ensure(e, e->pbtable, pb.size() * sizeof(double)))) return bail(rc);
+    if (cudaMemcpy(e->pbtable.p, pb.data(), pb.size() * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess)
+        return bail(fail(e, TSP_ECUDA, "pb table upload failed"));
+    e->stats.sm_count = e->sm_count;
+    *out = e;
+    return TSP_OK;
+}
+
+int tsp_destroy(tsp_handle e) {
+    if (!e) return TSP_OK;
+    cudaSetDevice(e->device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    for (DevBuf* b : {&e->arena, &e->blocks, &e->hidden, &e->hdr, &e->rootprior, &e->rootact, &e->pbtable, &e->s_obs,
+                      &e->s_legal, &e->s_nlegal, &e->s_noise, &e->s_tie, &e->s_chance, &e->s_fedroot, &e->s_fed,
+                      &e->s_visits, &e->s_rootv, &e->s_cval, &e->s_cprior, &e->s_crew, &e->s_depth, &e->s_rpred,
+                      &e->s_rhid, &e->s_nrec, &e->s_troot, &e->s_trace, &e->n_in, &e->n_act})
+        release(*b);
+    for (auto& b : e->n_o) release(b);
+    for (auto& ev : e->ev)
+        if (ev) cudaEventDestroy(ev);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+    return TSP_OK;
+}
+
+int tsp_set_layer(tsp_handle e, int32_t mlp, int32_t layer, const float* W, const float* b, int32_t out_dim,
+                  int32_t in_dim) {
+    if (!e) return TSP_EINVAL;
+    if (mlp < 0 || mlp >= TSP_NUM_MLP || layer < 0 || layer >= TSP_MAX_LAYERS || !W || !b || out_dim < 1 || in_dim < 1)
+        return fail(e, TSP_EINVAL, "tsp_set_layer: bad argument (mlp %d layer %d %dx%d)", mlp, layer, out_dim, in_dim);
+    auto& v = e->mlp[mlp];
+    if ((int)v.size() <= layer) v.resize(layer + 1);
+    HostLayer& L = v[layer];
+    L.out_dim = out_dim;
+    L.in_dim = in_dim;
+    L.W.assign(W, W + (size_t)out_dim * in_dim);
+    L.b.assign(b, b + out_dim);
+    e->finalized = false;
+    return TSP_OK;
+}
+
+int tsp_finalize_weights(tsp_handle e) {
+    if (!e) return TSP_EINVAL;
+    CK(e, cudaSetDevice(e->device));
+    // pack: per layer Wt[in_dim][npad] (transposed so that consecutive threads read consecutive
+    // output columns), zero padded to a multiple of 4 columns, followed by the bias [npad]
+    int64_t total = 0;
+    for (auto& v : e->mlp)
+        for (size_t l = 0; l < v.size(); ++l) {
+            HostLayer& L = v[l];
+            if (L.out_dim == 0) return fail(e, TSP_ESTATE, "a Linear layer is missing (set every layer index)");
+            if (l > 0 && v[l - 1].out_dim != L.in_dim) return fail(e, TSP_EINVAL, "layer shapes do not chain");
+            L.npad = (L.out_dim + 3) & ~3;
+            L.w_off = (int)total;
+            total += (int64_t)L.in_dim * L.npad;
+            L.b_off = (int)total;
+            total += L.npad;
+        }
+    if (total == 0) return fail(e, TSP_ESTATE, "no weights loaded");
+    std::vector<float> host((size_t)total, 0.0f);
+    for (auto& v : e->mlp)
+        for (HostLayer& L : v) {
+            for (int o = 0; o < L.out_dim; ++o)
+                for (int i = 0; i < L.in_dim; ++i) host[(size_t)L.w_off + (size_t)i * L.npad + o] = L.W[(size_t)o * L.in_dim + i];
+            for (int o = 0; o < L.out_dim; ++o) host[(size_t)L.b_off + o] = L.b[o];
+        }
+    int rc = ensure(e, e->arena, (size_t)total * sizeof(float));
+    if (rc) return rc;
+    CK(e, cudaMemcpyAsync(e->arena.p, host.data(), (size_t)total * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+    CK(e, cudaStreamSynchronize(e->stream));
+    e->arena_floats = total;
+    if ((rc = build_schedules(e))) return rc;
+    e->finalized = true;
+    return TSP_OK;
+}
+
+int tsp_weight_arena(tsp_handle e, void** device_ptr, int64_t* num_bytes) {
+    if (!e || !e->finalized) return e ? fail(e, TSP_ESTATE, "weights not finalized") : TSP_EINVAL;
+    if (device_ptr) *device_ptr = e->arena.p;
+    if (num_bytes) *num_bytes = e->arena_floats * (int64_t)sizeof(float);
+    return TSP_OK;
+}
+
+int tsp_run(tsp_handle e, const tsp_run_args* a) {
+    if (!e || !a) return TSP_EINVAL;
+    const tsp_config& c = e->cfg;
+    const int B = a->num_roots, S = a->num_simulations, A = c.num_actions, H = c.encoding_size;
+    const bool fed = a->fed_root != nullptr || a->fed_records != nullptr;
+    if (!fed && !e->finalized) return fail(e, TSP_ESTATE, "tsp_run before tsp_finalize_weights");
+    if (B < 1 || B > c.max_roots) return fail(e, TSP_EINVAL, "num_roots %d outside 1..%d", B, c.max_roots);
+    if (S < 0 || S > c.max_simulations) return fail(e, TSP_EINVAL, "num_simulations %d outside 0..%d", S, c.max_simulations);
+    if (fed && (!a->fed_root || (S > 0 && !a->fed_records))) return fail(e, TSP_EINVAL, "fed mode needs fed_root and fed_records");
+    if (!fed && !a->observations) return fail(e, TSP_EINVAL, "observations missing");
+    if (a->add_exploration_noise && !a->noise) return fail(e, TSP_EINVAL, "add_exploration_noise without a noise array");
+    if ((a->legal_actions == nullptr) != (a->num_legal == nullptr))
+        return fail(e, TSP_EINVAL, "legal_actions and num_legal must be given together");
+    if ((fed || a->trace_records) && a->max_records < 1 && S > 0) return fail(e, TSP_EINVAL, "max_records must be positive");
+    if (a->tie_stream && a->tie_len < 1) return fail(e, TSP_EINVAL, "tie_stream with tie_len < 1");
+    if (a->chance_stream && a->chance_len < 1) return fail(e, TSP_EINVAL, "chance_stream with chance_len < 1");
+    if (c.variant != 0 && c.n_futures > 1 && !a->chance_stream && S > 0)
+        return fail(e, TSP_EINVAL, "the stochastic variants need a chance_stream");
+    if (a->memory == TSP_MEM_HOST && a->legal_actions) {
+        // mirrors the asserts of self_play.py:354-359
+        for (int b = 0; b < B; ++b) {
+            const int nl = a->num_legal[b];
+            if (nl < 1 || nl > A) return fail(e, TSP_EINVAL, "root %d: legal actions should not be an empty array (got %d)", b, nl);
+            for (int i = 0; i < nl; ++i) {
+                const int x = a->legal_actions[(size_t)b * A + i];
+                if (x < 0 || x >= A) return fail(e, TSP_EINVAL, "root %d: legal actions should be a subset of the action space", b);
+            }
+        }
+    }
+    CK(e, cudaSetDevice(e->device));
+    const int mem = a->memory;
+    const size_t nb = (size_t)B;
+    int rc;
+
+    NetParams np;
+    memset(&np, 0, sizeof(np));
+    np.B = B; np.A = A; np.H = H; np.nf = c.n_futures; np.support = c.support_size; np.mode = 0;
+    np.W = reinterpret_cast<const float*>(e->arena.p);
+    np.tree_init = 1;
+    np.add_noise = a->add_exploration_noise ? 1 : 0;
+    np.uniform_policy = a->uniform_policy ? 1 : 0;
+    np.blocks_per_tree = e->blocks_per_tree;
+    np.hidden_per_tree = e->hidden_per_tree;
+    np.frac = c.root_exploration_fraction;
+    np.one_minus_frac = 1 - c.root_exploration_fraction;
+    np.blocks = e->blocks.p;
+    np.hidden_pool = reinterpret_cast<float*>(e->hidden.p);
+    np.hdr = reinterpret_cast<TreeHeader*>(e->hdr.p);
+    np.rootprior = reinterpret_cast<double*>(e->rootprior.p);
+    np.rootact = reinterpret_cast<int*>(e->rootact.p);
+    np.sched = e->sch_root;
+    if (fed) {  // the network is bypassed: any well-formed schedule shape will do
+        memset(&np.sched, 0, sizeof(np.sched));
+        np.sched.row_stride = 36;
+    }
+    if ((rc = stage_in(e, mem, a->observations, nb * c.obs_dim, e->s_obs, &np.in))) return rc;
+    if ((rc = stage_in(e, mem, a->legal_actions, nb * A, e->s_legal, &np.legal))) return rc;
+    if ((rc = stage_in(e, mem, a->num_legal, nb, e->s_nlegal, &np.num_legal))) return rc;
+    if ((rc = stage_in(e, mem, a->noise, nb * A, e->s_noise, &np.noise))) return rc;
+    if ((rc = stage_in(e, mem, a->fed_root, nb * REC, e->s_fedroot, &np.fed_root))) return rc;
+    if ((rc = stage_out(e, mem, a->trace_root, nb * REC, e->s_troot, &np.trace_root))) return rc;
+    if ((rc = stage_out(e, mem, a->root_predicted_value, nb, e->s_rpred, &np.root_pred))) return rc;
+    if ((rc = stage_out(e, mem, a->root_hidden, nb * H, e->s_rhid, &np.root_hidden))) return rc;
+
+    SearchParams sp;
+    memset(&sp, 0, sizeof(sp));
+    sp.B = B; sp.S = S; sp.A = A; sp.H = H; sp.nf = c.n_futures; sp.support = c.support_size;
+    sp.mask_absorbing = c.mask_absorbing_states ? 1 : 0;
+    sp.uniform_policy = a->uniform_policy ? 1 : 0;
+    sp.blocks_per_tree = e->blocks_per_tree;
+    sp.hidden_per_tree = e->hidden_per_tree;
+    sp.max_rec = a->max_records;
+    sp.T = a->tie_stream ? a->tie_len : 0;
+    sp.K = a->chance_stream ? a->chance_len : 0;
+    sp.max_iters = (c.variant == 0) ? S : S + (S + 1) * A + 1;
+    sp.discount = c.discount;
+    sp.pb_table = reinterpret_cast<const double*>(e->pbtable.p);
+    sp.blocks = e->blocks.p;
+    sp.hidden_pool = reinterpret_cast<float*>(e->hidden.p);
+    sp.hdr = reinterpret_cast<TreeHeader*>(e->hdr.p);
+    sp.rootprior = reinterpret_cast<const double*>(e->rootprior.p);
+    sp.rootact = reinterpret_cast<const int*>(e->rootact.p);
+    sp.W = reinterpret_cast<const float*>(e->arena.p);
+    if (c.variant == 0) {
+        sp.sched_a = e->sch_recur;
+    } else {
+        sp.sched_a = e->sch_trans;
+        sp.sched_b = e->sch_pred;
+    }
+    if (fed) {
+        memset(&sp.sched_a, 0, sizeof(sp.sched_a));
+        memset(&sp.sched_b, 0, sizeof(sp.sched_b));
+        sp.sched_a.row_stride = 4;
+        sp.sched_b.row_stride = 4;
+    }
+    const size_t nrec = nb * (size_t)std::max(a->max_records, 0);
+    if ((rc = stage_in(e, mem, a->tie_stream, nb * sp.T, e->s_tie, &sp.tie))) return rc;
+    if ((rc = stage_in(e, mem, a->chance_stream, nb * sp.K, e->s_chance, &sp.chance))) return rc;
+    if ((rc = stage_in(e, mem, a->fed_records, nrec * REC, e->s_fed, &sp.fed))) return rc;
+    if ((rc = stage_out(e, mem, a->trace_records, nrec * REC, e->s_trace, &sp.trace))) return rc;
+    if ((rc = stage_out(e, mem, a->visit_counts, nb * A, e->s_visits, &sp.visit_counts))) return rc;
+    if ((rc = stage_out(e, mem, a->root_value, nb, e->s_rootv, &sp.root_value))) return rc;
+    if ((rc = stage_out(e, mem, a->child_value, nb * A, e->s_cval, &sp.child_value))) return rc;
+    if ((rc = stage_out(e, mem, a->child_prior, nb * A, e->s_cprior, &sp.child_prior))) return rc;
+    if ((rc = stage_out(e, mem, a->child_reward, nb * A, e->s_crew, &sp.child_reward))) return rc;
+    if ((rc = stage_out(e, mem, a->max_tree_depth, nb, e->s_depth, &sp.max_depth))) return rc;
+    if ((rc = stage_out(e, mem, a->num_records, nb, e->s_nrec, &sp.num_records))) return rc;
+    if (fed && a->fed_records == nullptr) sp.fed = reinterpret_cast<const float*>(e->hdr.p);  // S == 0: never read
+
+    CK(e, cudaEventRecord(e->ev[0], e->stream));
+    if ((rc = launch_net_any(e, np))) return rc;
+    CK(e, cudaEventRecord(e->ev[1], e->stream));
+    if ((rc = launch_search_any(e, sp))) return rc;
+    CK(e, cudaEventRecord(e->ev[2], e->stream));
+    e->ev_valid = true;
+
+    if ((rc = copy_out(e, mem, a->trace_root, np.trace_root, nb * REC))) return rc;
+    if ((rc = copy_out(e, mem, a->root_predicted_value, np.root_pred, nb))) return rc;
+    if ((rc = copy_out(e, mem, a->root_hidden, np.root_hidden, nb * H))) return rc;
+    if ((rc = copy_out(e, mem, a->trace_records, sp.trace, nrec * REC))) return rc;
+    if ((rc = copy_out(e, mem, a->visit_counts, sp.visit_counts, nb * A))) return rc;
+    if ((rc = copy_out(e, mem, a->root_value, sp.root_value, nb))) return rc;
+    if ((rc = copy_out(e, mem, a->child_value, sp.child_value, nb * A))) return rc;
+    if ((rc = copy_out(e, mem, a->child_prior, sp.child_prior, nb * A))) return rc;
+    if ((rc = copy_out(e, mem, a->child_reward, sp.child_reward, nb * A))) return rc;
+    if ((rc = copy_out(e, mem, a->max_tree_depth, sp.max_depth, nb))) return rc;
+    if ((rc = copy_out(e, mem, a->num_records, sp.num_records, nb))) return rc;
+    e->stats.searches++;
+    return TSP_OK;
+}
+
+static int net_call(tsp_handle e, int mode, const Schedule& sc, int memory, int B, const float* in, int in_dim,
+                    const int32_t* action, float* outs[8], const size_t out_counts[8]) {
+    if (!e) return TSP_EINVAL;
+    if (!e->finalized) return fail(e, TSP_ESTATE, "network call before tsp_finalize_weights");
+    if (B < 1 || !in) return fail(e, TSP_EINVAL, "bad batch");
+    CK(e, cudaSetDevice(e->device));
+    const tsp_config& c = e->cfg;
+    NetParams p;
+    memset(&p, 0, sizeof(p));
+    p.B = B; p.A = c.num_actions; p.H = c.encoding_size; p.nf = c.n_futures; p.support = c.support_size; p.mode = mode;
+    p.W = reinterpret_cast<const float*>(e->arena.p);
+    p.sched = sc;
+    int rc;
+    if ((rc = stage_in(e, memory, in, (size_t)B * in_dim, e->n_in, &p.in))) return rc;
+    if ((rc = stage_in(e, memory, action, (size_t)B, e->n_act, &p.action))) return rc;
+    float* dev[8];
+    for (int i = 0; i < 8; ++i)
+        if ((rc = stage_out(e, memory, outs[i], out_counts[i], e->n_o[i], &dev[i]))) return rc;
+    p.value = dev[0]; p.reward = dev[1]; p.terminal = dev[2]; p.policy_logits = dev[3]; p.hidden_out = dev[4];
+    p.value_logits = dev[5]; p.reward_logits = dev[6]; p.transition_logits = dev[7];
+    if ((rc = launch_net_any(e, p))) return rc;
+    for (int i = 0; i < 8; ++i)
+        if ((rc = copy_out(e, memory, outs[i], dev[i], out_counts[i]))) return rc;
+    return TSP_OK;
+}
+
+int tsp_initial_inference(tsp_handle e, int32_t memory, int32_t B, const float* observations, float* value,
+                          float* policy_logits, float* hidden, float* value_logits) {
+    if (!e) return TSP_EINVAL;
+    const tsp_config& c = e->cfg;
+    const size_t n = (size_t)std::max(B, 0), V = 2 * c.support_size + 1;
+    float* outs[8] = {value, nullptr, nullptr, policy_logits, hidden, value_logits, nullptr, nullptr};
+    const size_t cnt[8] = {n, 0, 0, n * c.num_actions, n * c.encoding_size, n * V, 0, 0};
+    return net_call(e, 0, e->sch_root, memory, B, observations, c.obs_dim, nullptr, outs, cnt);
+}
+
+int tsp_recurrent_inference(tsp_handle e, int32_t memory, int32_t B, const float* hidden, const int32_t* action,
+                            float* value, float* reward, float* terminal, float* policy_logits, float* next_hidden,
+                            float* value_logits, float* reward_logits) {
+    if (!e) return TSP_EINVAL;
+    if (!e->has_recur) return fail(e, TSP_ESTATE, "recurrent_inference is only defined for the deterministic network");
+    if (!action) return fail(e, TSP_EINVAL, "action missing");
+    const tsp_config& c = e->cfg;
+    const size_t n = (size_t)std::max(B, 0), V = 2 * c.support_size + 1;
+    float* outs[8] = {value, reward, terminal, policy_logits, next_hidden, value_logits, reward_logits, nullptr};
+    const size_t cnt[8] = {n, n, n, n * c.num_actions, n * c.encoding_size, n * V, n * V, 0};
+    return net_call(e, 1, e->sch_recur, memory, B, hidden, c.encoding_size, action, outs, cnt);
+}
+
+int tsp_stochastic_dynamics(tsp_handle e, int32_t memory, int32_t B, const float* hidden, const int32_t* action,
+                            float* transition_logits, float* next_hidden, float* reward) {
+    if (!e) return TSP_EINVAL;
+    if (!e->has_trans) return fail(e, TSP_ESTATE, "dynamics with futures is only defined for the stochastic network");
+    if (!action) return fail(e, TSP_EINVAL, "action missing");
+    const tsp_config& c = e->cfg;
+    const size_t n = (size_t)std::max(B, 0);
+    float* outs[8] = {nullptr, reward, nullptr, nullptr, next_hidden, nullptr, nullptr, transition_logits};
+    const size_t cnt[8] = {0, n * c.n_futures, 0, 0, n * c.n_futures * c.encoding_size, 0, 0, n * c.n_futures};
+    return net_call(e, 2, e->sch_trans, memory, B, hidden, c.encoding_size, action, outs, cnt);
+}
+
+int tsp_prediction(tsp_handle e, int32_t memory, int32_t B, const float* hidden, float* value, float* policy_logits) {
+    if (!e) return TSP_EINVAL;
+    const tsp_config& c = e->cfg;
+    const size_t n = (size_t)std::max(B, 0);
+    float* outs[8] = {value, nullptr, nullptr, policy_logits, nullptr, nullptr, nullptr, nullptr};
+    const size_t cnt[8] = {n, 0, 0, n * c.num_actions, 0, 0, 0, 0};
+    return net_call(e, 3, e->sch_pred, memory, B, hidden, c.encoding_size, nullptr, outs, cnt);
+}
+
+int tsp_synchronize(tsp_handle e) {
+    if (!e) return TSP_EINVAL;
+    CK(e, cudaSetDevice(e->device));
+    CK(e, cudaStreamSynchronize(e->stream));
+    return TSP_OK;
+}
+
+int tsp_get_stats(tsp_handle e, tsp_stats* out) {
+    if (!e || !out) return TSP_EINVAL;
+    CK(e, cudaSetDevice(e->device));
+    if (e->ev_valid) {
+        CK(e, cudaEventSynchronize(e->ev[2]));
+        CK(e, cudaEventElapsedTime(&e->stats.last_root_ms, e->ev[0], e->ev[1]));
+        CK(e, cudaEventElapsedTime(&e->stats.last_search_ms, e->ev[1], e->ev[2]));
+    }
+    e->stats.pool_bytes = e->pool_bytes;
+    *out = e->stats;
+    return TSP_OK;
+}
+
+int tsp_stream(tsp_handle e, void** stream) {
+    if (!e || !stream) return TSP_EINVAL;
+    *stream = reinterpret_cast<void*>(e->stream);
+    return TSP_OK;
+}
+
+}  // extern "C"

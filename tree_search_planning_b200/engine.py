@@ -1,0 +1,320 @@
+"""ctypes binding of libtsp_b200.so (include/tsp.h): the batched search engine.
+
+Host code stays Python like the reference; everything below the C ABI is hand-written CUDA.
+There is no CPU fallback: without the shared library or without a B200 the constructor raises.
+"""
+import ctypes
+import os
+
+import numpy
+
+from .configs import observation_dim, variant_of
+from .weights import MLP_IDS, extract_mlps
+from . import build as _build
+
+REC_WIDTH = 16
+MEM_HOST, MEM_DEVICE = 0, 1
+_P = ctypes.c_void_p
+
+
+class TspError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__("tsp error %d: %s" % (code, message))
+        self.code = code
+
+
+class _Config(ctypes.Structure):
+    _fields_ = [
+        ("variant", ctypes.c_int32), ("num_actions", ctypes.c_int32), ("obs_dim", ctypes.c_int32),
+        ("encoding_size", ctypes.c_int32), ("support_size", ctypes.c_int32), ("n_futures", ctypes.c_int32),
+        ("mask_absorbing_states", ctypes.c_int32), ("num_players", ctypes.c_int32),
+        ("discount", ctypes.c_double), ("pb_c_base", ctypes.c_double), ("pb_c_init", ctypes.c_double),
+        ("root_exploration_fraction", ctypes.c_double),
+        ("max_roots", ctypes.c_int32), ("max_simulations", ctypes.c_int32), ("device", ctypes.c_int32),
+        ("reserved", ctypes.c_int32),
+    ]
+
+
+class _RunArgs(ctypes.Structure):
+    _fields_ = [
+        ("num_roots", ctypes.c_int32), ("num_simulations", ctypes.c_int32), ("memory", ctypes.c_int32),
+        ("add_exploration_noise", ctypes.c_int32), ("uniform_policy", ctypes.c_int32),
+        ("max_records", ctypes.c_int32), ("tie_len", ctypes.c_int32), ("chance_len", ctypes.c_int32),
+        ("observations", _P), ("legal_actions", _P), ("num_legal", _P), ("noise", _P),
+        ("tie_stream", _P), ("chance_stream", _P), ("fed_root", _P), ("fed_records", _P),
+        ("visit_counts", _P), ("root_value", _P), ("child_value", _P), ("child_prior", _P),
+        ("child_reward", _P), ("max_tree_depth", _P), ("root_predicted_value", _P), ("root_hidden", _P),
+        ("num_records", _P), ("trace_root", _P), ("trace_records", _P),
+    ]
+
+
+class Stats(ctypes.Structure):
+    _fields_ = [
+        ("kernel_launches", ctypes.c_int64), ("searches", ctypes.c_int64), ("bytes_h2d", ctypes.c_int64),
+        ("bytes_d2h", ctypes.c_int64), ("pool_bytes", ctypes.c_int64), ("last_search_ms", ctypes.c_float),
+        ("last_root_ms", ctypes.c_float), ("sm_count", ctypes.c_int32), ("search_ctas", ctypes.c_int32),
+        ("search_smem_bytes", ctypes.c_int32), ("trees_per_cta", ctypes.c_int32),
+    ]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+# every symbol include/tsp.h declares (tests check that the library exports each of them)
+ABI_SYMBOLS = (
+    "tsp_abi_version", "tsp_create", "tsp_destroy", "tsp_last_error", "tsp_set_layer", "tsp_finalize_weights",
+    "tsp_weight_arena", "tsp_run", "tsp_initial_inference", "tsp_recurrent_inference", "tsp_stochastic_dynamics",
+    "tsp_prediction", "tsp_synchronize", "tsp_get_stats", "tsp_stream",
+)
+
+_lib = None
+
+
+def load_library(path=None):
+    """Load libtsp_b200.so (building it in-tree if the sources are newer). Fails loudly."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or _build.LIB_PATH
+    if path is None and _build.needs_build():
+        _build.build()
+    if not os.path.exists(p):
+        raise TspError(-2, "CUDA extension %s is missing; run `python -c 'import __graft_entry__ as g; g.build()'`" % p)
+    lib = ctypes.CDLL(p)
+    lib.tsp_abi_version.restype = ctypes.c_int
+    lib.tsp_last_error.restype = ctypes.c_char_p
+    lib.tsp_last_error.argtypes = [_P]
+    lib.tsp_create.argtypes = [ctypes.POINTER(_Config), ctypes.POINTER(_P)]
+    lib.tsp_destroy.argtypes = [_P]
+    lib.tsp_set_layer.argtypes = [_P, ctypes.c_int32, ctypes.c_int32, _P, _P, ctypes.c_int32, ctypes.c_int32]
+    lib.tsp_finalize_weights.argtypes = [_P]
+    lib.tsp_weight_arena.argtypes = [_P, ctypes.POINTER(_P), ctypes.POINTER(ctypes.c_int64)]
+    lib.tsp_run.argtypes = [_P, ctypes.POINTER(_RunArgs)]
+    lib.tsp_initial_inference.argtypes = [_P, ctypes.c_int32, ctypes.c_int32] + [_P] * 5
+    lib.tsp_recurrent_inference.argtypes = [_P, ctypes.c_int32, ctypes.c_int32] + [_P] * 9
+    lib.tsp_stochastic_dynamics.argtypes = [_P, ctypes.c_int32, ctypes.c_int32] + [_P] * 5
+    lib.tsp_prediction.argtypes = [_P, ctypes.c_int32, ctypes.c_int32] + [_P] * 3
+    lib.tsp_synchronize.argtypes = [_P]
+    lib.tsp_get_stats.argtypes = [_P, ctypes.POINTER(Stats)]
+    lib.tsp_stream.argtypes = [_P, ctypes.POINTER(_P)]
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def _is_torch_tensor(x):
+    return type(x).__module__.startswith("torch") and hasattr(x, "data_ptr")
+
+
+def _ptr(x):
+    if x is None:
+        return None
+    if _is_torch_tensor(x):
+        return _P(x.data_ptr())
+    return x.ctypes.data_as(_P)
+
+
+class Engine:
+    """One engine per (game config, CUDA device). Node pools are sized at construction."""
+
+    def __init__(self, config, max_roots, max_simulations=None, device=0, state_dict=None):
+        self.lib = load_library()
+        self.config = config
+        self.variant = variant_of(config)
+        self.A = len(config.action_space)
+        if list(config.action_space) != list(range(self.A)):
+            raise ValueError("action_space must be list(range(A)) (the networks one-hot encode the action index)")
+        self.H = int(config.encoding_size)
+        self.obs_dim = observation_dim(config)
+        self.nf = int(getattr(config, "n_futures", 1)) if self.variant else 1
+        self.V = 2 * int(config.support_size) + 1
+        self.max_roots = int(max_roots)
+        self.max_simulations = int(config.num_simulations if max_simulations is None else max_simulations)
+        self.device = int(device)
+        if len(config.players) > 2:
+            raise NotImplementedError("More than two player mode not implemented.")  # self_play.py:503
+        c = _Config(self.variant, self.A, self.obs_dim, self.H, int(config.support_size), self.nf,
+                    int(bool(getattr(config, "mask_absorbing_states", False))), len(config.players),
+                    float(config.discount), float(config.pb_c_base), float(config.pb_c_init),
+                    float(config.root_exploration_fraction), self.max_roots, self.max_simulations, self.device, 0)
+        h = _P()
+        rc = self.lib.tsp_create(ctypes.byref(c), ctypes.byref(h))
+        if rc != 0:
+            msg = self.lib.tsp_last_error(None).decode()
+            if rc == -5:
+                raise NotImplementedError(msg)
+            raise TspError(rc, msg)
+        self.handle = h
+        self._keep = []
+        if state_dict is not None:
+            self.load_state_dict(state_dict)
+
+    # -- lifetime ---------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.tsp_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise TspError(rc, self.lib.tsp_last_error(self.handle).decode())
+
+    # -- weights ------------------------------------------------------------------------
+    def load_state_dict(self, state_dict):
+        """model.set_weights equivalent (models.py:128-129): accepts the reference state dict
+        (torch tensors or numpy arrays, with or without the DataParallel `.module.` infix)."""
+        mlps = extract_mlps(state_dict)
+        for name, layers in mlps.items():
+            if name == "prior" and self.variant == 0:
+                continue
+            for i, (W, b) in enumerate(layers):
+                W = numpy.ascontiguousarray(W, numpy.float32)
+                b = numpy.ascontiguousarray(b, numpy.float32)
+                self._check(self.lib.tsp_set_layer(self.handle, MLP_IDS[name], i, _ptr(W), _ptr(b),
+                                                   W.shape[0], W.shape[1]))
+        self._check(self.lib.tsp_finalize_weights(self.handle))
+
+    def weight_arena(self):
+        p, n = _P(), ctypes.c_int64()
+        self._check(self.lib.tsp_weight_arena(self.handle, ctypes.byref(p), ctypes.byref(n)))
+        return p.value, n.value
+
+    # -- search -------------------------------------------------------------------------
+    def max_records(self, S):
+        return S if self.variant == 0 else S * (self.A + 2) + self.A + 2
+
+    def run_raw(self, args):
+        self._check(self.lib.tsp_run(self.handle, ctypes.byref(args)))
+
+    def run(self, num_simulations=None, observations=None, legal_actions=None, num_legal=None, noise=None,
+            tie=None, chance=None, add_exploration_noise=True, uniform_policy=False, fed_root=None,
+            fed_records=None, trace=False, max_records=None, want=("visit_counts", "root_value", "child_value",
+                                                                   "child_prior", "child_reward", "max_tree_depth",
+                                                                   "root_predicted_value", "num_records"),
+            want_root_hidden=False, synchronize=True):
+        """Batched MCTS.run over HOST numpy arrays; returns a dict of numpy arrays."""
+        S = self.max_simulations if num_simulations is None else int(num_simulations)
+        A = self.A
+        keep = []
+
+        def prep(x, dt, shape=None):
+            if x is None:
+                return None
+            x = numpy.ascontiguousarray(x, dt)
+            if shape is not None:
+                x = x.reshape(shape)
+            keep.append(x)
+            return x
+
+        if observations is not None:
+            observations = prep(observations, numpy.float32).reshape(-1, self.obs_dim)
+            B = observations.shape[0]
+        elif fed_root is not None:
+            B = numpy.asarray(fed_root).reshape(-1, REC_WIDTH).shape[0]
+        else:
+            raise ValueError("observations (or fed_root) required")
+        fed_root = prep(fed_root, numpy.float32, (B, REC_WIDTH))
+        if fed_records is not None:
+            fed_records = prep(fed_records, numpy.float32).reshape(B, -1, REC_WIDTH)
+            max_records = fed_records.shape[1]
+        if max_records is None:
+            max_records = self.max_records(S) if trace else 0
+        legal_actions = prep(legal_actions, numpy.int32, (B, A))
+        num_legal = prep(num_legal, numpy.int32, (B,))
+        noise = prep(noise, numpy.float64, (B, A))
+        tie = prep(tie, numpy.uint8)
+        T = 0 if tie is None else tie.reshape(B, -1).shape[1]
+        chance = prep(chance, numpy.uint8)
+        K = 0 if chance is None else chance.reshape(B, -1).shape[1]
+        shapes = dict(visit_counts=((B, A), numpy.int32), root_value=((B,), numpy.float64),
+                      child_value=((B, A), numpy.float64), child_prior=((B, A), numpy.float64),
+                      child_reward=((B, A), numpy.float64), max_tree_depth=((B,), numpy.int32),
+                      root_predicted_value=((B,), numpy.float32), num_records=((B,), numpy.int32))
+        out = {k: numpy.zeros(*shapes[k]) for k in want}
+        if want_root_hidden:
+            out["root_hidden"] = numpy.zeros((B, self.H), numpy.float32)
+        if trace:
+            out["trace_root"] = numpy.zeros((B, REC_WIDTH), numpy.float32)
+            out["trace_records"] = numpy.zeros((B, max(max_records, 1), REC_WIDTH), numpy.float32)
+        a = _RunArgs(B, S, MEM_HOST, int(bool(add_exploration_noise)), int(bool(uniform_policy)),
+                     int(max_records), T, K,
+                     _ptr(observations), _ptr(legal_actions), _ptr(num_legal), _ptr(noise), _ptr(tie), _ptr(chance),
+                     _ptr(fed_root), _ptr(fed_records),
+                     _ptr(out.get("visit_counts")), _ptr(out.get("root_value")), _ptr(out.get("child_value")),
+                     _ptr(out.get("child_prior")), _ptr(out.get("child_reward")), _ptr(out.get("max_tree_depth")),
+                     _ptr(out.get("root_predicted_value")), _ptr(out.get("root_hidden")), _ptr(out.get("num_records")),
+                     _ptr(out.get("trace_root")), _ptr(out.get("trace_records")))
+        self.run_raw(a)
+        if synchronize:
+            self.synchronize()
+        else:
+            self._keep = keep  # keep host inputs alive until the caller synchronizes
+        return out
+
+    # -- network entry points --------------------------------------------------------------
+    def initial_inference(self, observations):
+        obs = numpy.ascontiguousarray(observations, numpy.float32).reshape(-1, self.obs_dim)
+        B = obs.shape[0]
+        out = dict(value=numpy.zeros(B, numpy.float32), policy_logits=numpy.zeros((B, self.A), numpy.float32),
+                   hidden=numpy.zeros((B, self.H), numpy.float32), value_logits=numpy.zeros((B, self.V), numpy.float32))
+        self._check(self.lib.tsp_initial_inference(self.handle, MEM_HOST, B, _ptr(obs), _ptr(out["value"]),
+                                                   _ptr(out["policy_logits"]), _ptr(out["hidden"]),
+                                                   _ptr(out["value_logits"])))
+        self.synchronize()
+        return out
+
+    def recurrent_inference(self, hidden, action):
+        h = numpy.ascontiguousarray(hidden, numpy.float32).reshape(-1, self.H)
+        B = h.shape[0]
+        a = numpy.ascontiguousarray(action, numpy.int32).reshape(B)
+        out = dict(value=numpy.zeros(B, numpy.float32), reward=numpy.zeros(B, numpy.float32),
+                   terminal=numpy.zeros(B, numpy.float32), policy_logits=numpy.zeros((B, self.A), numpy.float32),
+                   hidden=numpy.zeros((B, self.H), numpy.float32), value_logits=numpy.zeros((B, self.V), numpy.float32),
+                   reward_logits=numpy.zeros((B, self.V), numpy.float32))
+        self._check(self.lib.tsp_recurrent_inference(
+            self.handle, MEM_HOST, B, _ptr(h), _ptr(a), _ptr(out["value"]), _ptr(out["reward"]), _ptr(out["terminal"]),
+            _ptr(out["policy_logits"]), _ptr(out["hidden"]), _ptr(out["value_logits"]), _ptr(out["reward_logits"])))
+        self.synchronize()
+        return out
+
+    def stochastic_dynamics(self, hidden, action):
+        h = numpy.ascontiguousarray(hidden, numpy.float32).reshape(-1, self.H)
+        B = h.shape[0]
+        a = numpy.ascontiguousarray(action, numpy.int32).reshape(B)
+        out = dict(transition_logits=numpy.zeros((B, self.nf), numpy.float32),
+                   hidden=numpy.zeros((B, self.nf, self.H), numpy.float32), reward=numpy.zeros((B, self.nf), numpy.float32))
+        self._check(self.lib.tsp_stochastic_dynamics(self.handle, MEM_HOST, B, _ptr(h), _ptr(a),
+                                                     _ptr(out["transition_logits"]), _ptr(out["hidden"]),
+                                                     _ptr(out["reward"])))
+        self.synchronize()
+        return out
+
+    def prediction(self, hidden):
+        h = numpy.ascontiguousarray(hidden, numpy.float32).reshape(-1, self.H)
+        B = h.shape[0]
+        out = dict(value=numpy.zeros(B, numpy.float32), policy_logits=numpy.zeros((B, self.A), numpy.float32))
+        self._check(self.lib.tsp_prediction(self.handle, MEM_HOST, B, _ptr(h), _ptr(out["value"]),
+                                            _ptr(out["policy_logits"])))
+        self.synchronize()
+        return out
+
+    # -- misc ----------------------------------------------------------------------------------
+    def synchronize(self):
+        self._check(self.lib.tsp_synchronize(self.handle))
+        self._keep = []
+
+    def stats(self):
+        s = Stats()
+        self._check(self.lib.tsp_get_stats(self.handle, ctypes.byref(s)))
+        return s.as_dict()
+
+    def stream(self):
+        p = _P()
+        self._check(self.lib.tsp_stream(self.handle, ctypes.byref(p)))
+        return p.value

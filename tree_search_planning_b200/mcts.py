@@ -1,0 +1,168 @@
+"""Host-side mirror of the reference planner interface.
+
+`MCTS(config).run(model, observation, legal_actions, to_play, add_exploration_noise, ...)
+-> (root, extra_info)` keeps the surface of muzero-general/self_play.py:303-434 (and of the
+stochastic / risk-sensitive siblings, picked from the config flags exactly like muzero.py:232-250),
+so `SelfPlay.play_game`, `select_action`, `GameHistory.store_search_statistics` and
+`DiagnoseModel` call it unchanged. Underneath, the search runs on the GPU through the C ABI
+(engine.py -> libtsp_b200.so); `run_batch` exposes the batched form the engine is built for.
+"""
+import numpy
+
+from .configs import variant_of, observation_dim
+from .engine import Engine
+
+# numpy.random.choice over n tied actions / nf chance outcomes is replaced by
+# stream[k] % n; drawing the stream from [0, 240) keeps that unbiased for n in 1..6, 8
+_STREAM_MOD = 240
+
+_engine_cache = {}
+
+
+def _config_key(config, device):
+    keys = ("action_space", "players", "observation_shape", "stacked_observations", "encoding_size", "support_size",
+            "discount", "pb_c_base", "pb_c_init", "root_exploration_fraction", "mask_absorbing_states",
+            "stochastic_dynamics", "risk_sensitive", "n_futures", "fc_representation_layers", "fc_dynamics_layers",
+            "fc_reward_layers", "fc_value_layers", "fc_policy_layers", "fc_prior_layers")
+    return (device,) + tuple(repr(getattr(config, k, None)) for k in keys)
+
+
+def _weights_fingerprint(model):
+    if isinstance(model, dict):
+        return ("dict", id(model))
+    params = list(model.parameters()) if hasattr(model, "parameters") else []
+    return (id(model), sum(int(getattr(p, "_version", 0)) for p in params))
+
+
+class ChildView:
+    """What consumers read from `root.children[a]`: visit_count, prior, reward, value."""
+
+    def __init__(self, visit_count, prior, reward, value, value_is_attribute):
+        self.visit_count = int(visit_count)
+        self.prior = float(prior)
+        self.reward = float(reward)
+        self.children = {}  # deeper levels stay on the device
+        self.hidden_state = None
+        self.to_play = 0
+        self._value = float(value)
+        if value_is_attribute:  # risk-sensitive nodes expose `.value` as an attribute
+            self.value = self._value
+
+    def expanded(self):
+        return self.visit_count > 0
+
+    def value(self):  # shadowed by the instance attribute in the risk-sensitive variant
+        return self._value
+
+
+class RootView(ChildView):
+    def __init__(self, res, i, legal_actions, variant, hidden_state=None):
+        super().__init__(res["visit_counts"][i].sum() if "visit_counts" in res else 0, 0.0, 0.0,
+                         res["root_value"][i], variant == 2)
+        self.children = {
+            int(a): ChildView(res["visit_counts"][i][a], res["child_prior"][i][a], res["child_reward"][i][a],
+                              res["child_value"][i][a], variant == 2)
+            for a in legal_actions
+        }
+        self.hidden_state = hidden_state
+
+    def expanded(self):
+        return len(self.children) > 0
+
+
+class BatchResult(dict):
+    """Arrays of one batched search + per-root `root` views."""
+
+    def __init__(self, res, legal_lists, variant):
+        super().__init__(res)
+        self._legal = legal_lists
+        self._variant = variant
+
+    def root(self, i):
+        hid = self["root_hidden"][i][None] if "root_hidden" in self else None
+        return RootView(self, i, self._legal[i], self._variant, hid)
+
+    def extra_info(self, i):
+        info = {"max_tree_depth": int(self["max_tree_depth"][i]),
+                "root_predicted_value": float(self["root_predicted_value"][i])}
+        if self._variant == 0:
+            info["n_env_interactions"] = 0  # self_play.py:432
+        return info
+
+
+class MCTS:
+    """Drop-in for self_play.MCTS / self_play_stochastic.MCTS / self_play_risk_sensitive.MCTS."""
+
+    def __init__(self, config, device=0, max_roots=1):
+        self.config = config
+        self.device = device
+        self.max_roots = max_roots
+        self.variant = variant_of(config)
+
+    # -- engine management ---------------------------------------------------------------
+    def _engine(self, model, batch, num_simulations):
+        key = _config_key(self.config, self.device)
+        ent = _engine_cache.get(key)
+        if ent is None or ent["engine"].max_roots < batch or ent["engine"].max_simulations < num_simulations:
+            if ent is not None:
+                ent["engine"].close()
+            eng = Engine(self.config, max(batch, self.max_roots), max(num_simulations, self.config.num_simulations),
+                         device=self.device)
+            ent = {"engine": eng, "fingerprint": None}
+            _engine_cache[key] = ent
+        fp = _weights_fingerprint(model)
+        if ent["fingerprint"] != fp:
+            sd = model if isinstance(model, dict) else model.state_dict()
+            ent["engine"].load_state_dict(sd)
+            ent["fingerprint"] = fp
+        return ent["engine"]
+
+    # -- the reference surface ---------------------------------------------------------------
+    def run(self, model, observation, legal_actions, to_play, add_exploration_noise, override_root_with=None,
+            policy_only=False, uniform_policy=False):
+        if override_root_with is not None:
+            raise NotImplementedError("override_root_with: trees live on the device and are rebuilt per search")
+        if self.variant != 0 and (policy_only or uniform_policy):
+            raise TypeError("policy_only / uniform_policy exist only in self_play.MCTS.run")
+        assert legal_actions, f"Legal actions should not be an empty array. Got {legal_actions}."
+        assert set(legal_actions).issubset(set(self.config.action_space)), \
+            "Legal actions should be a subset of the action space."
+        obs = numpy.asarray(observation, dtype=numpy.float32).reshape(1, -1)
+        res = self.run_batch(model, obs, [list(legal_actions)], add_exploration_noise, policy_only=policy_only,
+                             uniform_policy=uniform_policy, want_root_hidden=True)
+        return res.root(0), res.extra_info(0)
+
+    def run_batch(self, model, observations, legal_actions=None, add_exploration_noise=True, noise=None, tie=None,
+                  chance=None, policy_only=False, uniform_policy=False, num_simulations=None,
+                  want_root_hidden=False):
+        """B independent searches at once. `legal_actions`: list of B ordered lists (None = all).
+        Random sources default to numpy.random like the reference (Dirichlet noise is drawn with the
+        very call of self_play.py:546); pass `noise` / `tie` / `chance` for reproducible searches."""
+        cfg = self.config
+        A = len(cfg.action_space)
+        observations = numpy.ascontiguousarray(observations, numpy.float32).reshape(-1, observation_dim(cfg))
+        B = observations.shape[0]
+        S = 0 if policy_only else int(cfg.num_simulations if num_simulations is None else num_simulations)
+        legal_lists = [list(cfg.action_space)] * B if legal_actions is None else [list(l) for l in legal_actions]
+        la = nl = None
+        if legal_actions is not None:
+            la = numpy.zeros((B, A), numpy.int32)
+            nl = numpy.zeros(B, numpy.int32)
+            for i, l in enumerate(legal_lists):
+                assert l, f"Legal actions should not be an empty array. Got {l}."
+                assert set(l).issubset(set(cfg.action_space)), "Legal actions should be a subset of the action space."
+                la[i, :len(l)] = l
+                nl[i] = len(l)
+        if add_exploration_noise and noise is None:
+            noise = numpy.zeros((B, A), numpy.float64)
+            for i, l in enumerate(legal_lists):
+                noise[i, :len(l)] = numpy.random.dirichlet([cfg.root_dirichlet_alpha] * len(l))
+        if tie is None:
+            tie = numpy.random.randint(0, _STREAM_MOD, size=(B, 64)).astype(numpy.uint8)
+        if chance is None and self.variant != 0:
+            chance = numpy.random.randint(0, _STREAM_MOD, size=(B, max(64, 8 * S))).astype(numpy.uint8)
+        eng = self._engine(model, B, S)
+        res = eng.run(S, observations=observations, legal_actions=la, num_legal=nl, noise=noise, tie=tie,
+                      chance=chance, add_exploration_noise=add_exploration_noise, uniform_policy=uniform_policy,
+                      want_root_hidden=want_root_hidden)
+        return BatchResult(res, legal_lists, self.variant)

@@ -9,7 +9,7 @@ module works on anything with ``.items()`` whose values convert with ``numpy.asa
 import re
 import numpy
 
-# engine MLP ids (same numbering as include/tsp.h TSP_MLP_* and the oracle's ORC_*)
+# engine MLP ids (same numbering as include/tsp.h TSP_MLP_*)
 MLP_IDS = {
     "representation": 0,
     "dynamics": 1,
