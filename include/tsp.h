@@ -125,6 +125,8 @@ typedef struct {
     float *root_predicted_value;   /* [B]     extra_info["root_predicted_value"] */
     float *root_hidden;            /* [B][H]  root.hidden_state */
     int32_t *num_records;          /* [B]     network evaluations made per root (excluding the root one) */
+    int32_t *total_select_depth;   /* [B]     sum over all descents of the number of levels walked (for the
+                                              algorithmic-traffic figure of the roofline report) */
     float *trace_root;             /* [B][REC] */
     float *trace_records;          /* [B][max_records][REC] */
 } tsp_run_args;
@@ -134,12 +136,17 @@ typedef struct {
     int64_t searches;              /* tsp_run calls */
     int64_t bytes_h2d, bytes_d2h;  /* staged through the engine so far */
     int64_t pool_bytes;            /* device memory owned by the engine */
-    float last_search_ms;          /* device time of the search kernel(s) of the last tsp_run (CUDA events) */
+    float last_search_ms;          /* device time of the search kernel of the last tsp_run (CUDA events) */
     float last_root_ms;            /* device time of the root kernel of the last tsp_run */
+    double sum_search_ms;          /* accumulated over every tsp_run since tsp_reset_timing (CUDA events on the */
+    double sum_root_ms;            /*   engine's stream, one event triple per run)                              */
+    int64_t timed_runs;
     int32_t sm_count;
     int32_t search_ctas;           /* grid of the last search kernel */
     int32_t search_smem_bytes;
     int32_t trees_per_cta;
+    int32_t threads_per_cta;
+    int32_t reserved;
 } tsp_stats;
 
 int tsp_abi_version(void);
@@ -183,6 +190,12 @@ int tsp_prediction(tsp_handle h, int32_t memory, int32_t B, const float *hidden,
 
 int tsp_synchronize(tsp_handle h);
 int tsp_get_stats(tsp_handle h, tsp_stats *out);
+/* zero sum_search_ms / sum_root_ms / timed_runs (synchronizes the stream) */
+int tsp_reset_timing(tsp_handle h);
+/* developer instrumentation (env TSP_PHASE_TIMING=1 at tsp_create): summed clock64() deltas of thread 0 of
+ * every CTA of the deterministic search kernel: [0] select+gather [1] barrier wait [2] MLP [3] expand+backup
+ * [4] number of samples; [8 + 2s] own work in MLP stage s, [9 + 2s] wait at the barrier of stage s */
+int tsp_debug_phase_cycles(tsp_handle h, uint64_t out[64], int32_t reset);
 /* the CUDA stream the engine launches on (cudaStream_t as void*), for event timing by the caller */
 int tsp_stream(tsp_handle h, void **stream);
 

@@ -149,48 +149,11 @@ def test_terminal_head_parity():
 
 
 # ------------------------------------------------------------ seeded, vs the oracle ----
+from tree_search_planning_b200.synthetic import random_state_dict, synthetic_inputs  # noqa: E402
+
+
 def seeded_inputs(cfg, B, S, seed, legal=False):
-    rng = numpy.random.default_rng(seed)
-    A = len(cfg.action_space)
-    D = tsp.observation_dim(cfg)
-    obs = rng.random((B, D), dtype=numpy.float32)
-    kw = dict(noise=rng.dirichlet([cfg.root_dirichlet_alpha] * A, size=B),
-              tie=rng.integers(0, 240, size=(B, 32)).astype(numpy.uint8),
-              chance=rng.integers(0, 240, size=(B, 8 * S)).astype(numpy.uint8))
-    if legal:
-        la = numpy.zeros((B, A), numpy.int32)
-        nl = rng.integers(1, A + 1, size=B).astype(numpy.int32)
-        for b in range(B):
-            la[b, :nl[b]] = rng.permutation(A)[:nl[b]]
-            nz = rng.dirichlet([cfg.root_dirichlet_alpha] * nl[b]) if nl[b] > 1 else numpy.ones(1)
-            kw["noise"][b] = 0
-            kw["noise"][b, :nl[b]] = nz
-        kw.update(legal_actions=la, num_legal=nl)
-    return obs, kw
-
-
-def random_state_dict(cfg, seed):
-    """Same-shape random-init weights without torch's model classes (nn.Linear default init range)."""
-    rng = numpy.random.default_rng(seed)
-    A, H, V = len(cfg.action_space), cfg.encoding_size, 2 * cfg.support_size + 1
-    stochastic = tsp.variant_of(cfg) != 0
-    nets = {
-        "representation_network": [tsp.observation_dim(cfg)] + list(cfg.fc_representation_layers) + [H],
-        "dynamics_encoded_state_network": [H + A + (cfg.n_futures if stochastic else 0)] + list(cfg.fc_dynamics_layers) + [H],
-        "dynamics_reward_network": [H] + list(cfg.fc_reward_layers) + [V],
-        "dynamics_terminal_network": [H] + list(cfg.fc_reward_layers) + [1],
-        "prediction_policy_network": [H] + list(cfg.fc_policy_layers) + [A],
-        "prediction_value_network": [H] + list(cfg.fc_value_layers) + [V],
-    }
-    if stochastic:
-        nets["transition_prior_network"] = [H] + list(cfg.fc_prior_layers) + [cfg.n_futures]
-    sd = {}
-    for name, sizes in nets.items():
-        for i in range(len(sizes) - 1):
-            bound = 1.0 / numpy.sqrt(sizes[i])
-            sd["%s.module.%d.weight" % (name, 2 * i)] = rng.uniform(-bound, bound, (sizes[i + 1], sizes[i])).astype(numpy.float32)
-            sd["%s.module.%d.bias" % (name, 2 * i)] = rng.uniform(-bound, bound, sizes[i + 1]).astype(numpy.float32)
-    return sd
+    return synthetic_inputs(cfg, B, S, seed, ragged_legal=legal)
 
 
 def check_against_oracle(cfg, B, S, seed, legal=False, min_agree=0.985, **run_opts):

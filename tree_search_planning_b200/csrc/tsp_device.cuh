@@ -66,6 +66,8 @@ struct LayerOp {
     short in_off, out_off;  // float offsets inside a row's activation strip
     unsigned char act;      // 0 identity, 1 ELU
     unsigned char extra;    // 0 none, 1 + Wt[K + action], 2 + Wt[K + action] + Wt[K + A + z]
+    unsigned char ct;       // output columns per thread (4, 8 or 16; divides Npad), set per launch
+    unsigned char pad;
 };
 struct Stage {
     unsigned char n_ops;
@@ -81,70 +83,226 @@ struct Schedule {
     Stage st[MAX_STAGES];
 };
 
-__device__ __forceinline__ float elu(float v) { return v > 0.0f ? v : expm1f(v); }
+// ELU(alpha = 1): exp(v) - 1 for v <= 0. ex2.approx keeps the absolute error below 5e-7 on (-inf, 0],
+// two orders of magnitude inside the 1e-5 network tolerance, at 3 instructions instead of ~25 (expm1f).
+__device__ __forceinline__ float elu(float v) {
+    const float e = __fsub_rn(__expf(fminf(v, 0.0f)), 1.0f);
+    return v > 0.0f ? v : e;
+}
 
-__device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
+// Weights come either from the shared-memory copy (plain loads: the pointer is derived from the
+// extern __shared__ array by offsets only, so the compiler keeps the shared address space and emits
+// LDS.128 that it is free to batch ahead of the FMAs) or from global memory (read-only path).
+template <bool WSMEM>
+__device__ __forceinline__ float4 ldw4(const float4* p) {
+    if (WSMEM) return *p;
+    return __ldg(p);
+}
+
+// One work unit of a Linear layer: ONE row (tree) x CT output columns per thread, lanes of a warp
+// holding different rows. The weight reads are then warp-uniform (one shared-memory broadcast per
+// LDS.128 instead of four 128-byte phases), the activation reads are one conflict-free LDS.128 per lane
+// (row stride == 4 mod 32 words), every lane does useful FMAs, and a thread issues CT*4 FMAs per
+// (1 + CT) loads. Measured alternatives (1x4 tiles: shared-memory pipe bound; 4x4 tiles: the work of a
+// stage collapses onto one warp) are recorded in DESIGN.md.
+template <bool WSMEM, int CT>
+__device__ __forceinline__ void dense_unit(const LayerOp& op, const float* __restrict__ W, float* __restrict__ act,
+                                           int rs, int row, int c0, int action, bool active, int A, int z) {
+    const int npad = op.Npad;
+    const int K = op.K;
+    const float* x = act + row * rs + op.in_off;
+    const float* wp = W + op.w_off + c0;  // row k of Wt starts at wp + k * npad
+    float acc[CT];
+#pragma unroll
+    for (int c = 0; c < CT; c += 4) {
+        const float4 b4 = ldw4<WSMEM>(reinterpret_cast<const float4*>(W + op.b_off + c0 + c));
+        acc[c] = b4.x; acc[c + 1] = b4.y; acc[c + 2] = b4.z; acc[c + 3] = b4.w;
+    }
+    if (op.extra) {
+        const float* we = wp + (K + action) * npad;
+#pragma unroll
+        for (int c = 0; c < CT; c += 4) {
+            const float4 e = ldw4<WSMEM>(reinterpret_cast<const float4*>(we + c));
+            acc[c] += e.x; acc[c + 1] += e.y; acc[c + 2] += e.z; acc[c + 3] += e.w;
+        }
+        if (op.extra == 2) {
+            const float* wf = wp + (K + A + z) * npad;
+#pragma unroll
+            for (int c = 0; c < CT; c += 4) {
+                const float4 f = ldw4<WSMEM>(reinterpret_cast<const float4*>(wf + c));
+                acc[c] += f.x; acc[c + 1] += f.y; acc[c + 2] += f.z; acc[c + 3] += f.w;
+            }
+        }
+    }
+    int k = 0;
+    for (; k + 4 <= K; k += 4) {
+        const float4 xv = *reinterpret_cast<const float4*>(x + k);
+        const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+            for (int c = 0; c < CT; c += 4) {
+                const float4 w4 = ldw4<WSMEM>(reinterpret_cast<const float4*>(wp + c));
+                acc[c] = fmaf(xs[kk], w4.x, acc[c]);
+                acc[c + 1] = fmaf(xs[kk], w4.y, acc[c + 1]);
+                acc[c + 2] = fmaf(xs[kk], w4.z, acc[c + 2]);
+                acc[c + 3] = fmaf(xs[kk], w4.w, acc[c + 3]);
+            }
+            wp += npad;
+        }
+    }
+    for (; k < K; ++k) {
+        const float xk = x[k];
+#pragma unroll
+        for (int c = 0; c < CT; c += 4) {
+            const float4 w4 = ldw4<WSMEM>(reinterpret_cast<const float4*>(wp + c));
+            acc[c] = fmaf(xk, w4.x, acc[c]);
+            acc[c + 1] = fmaf(xk, w4.y, acc[c + 1]);
+            acc[c + 2] = fmaf(xk, w4.z, acc[c + 2]);
+            acc[c + 3] = fmaf(xk, w4.w, acc[c + 3]);
+        }
+        wp += npad;
+    }
+    if (!active) return;
+    float* y = act + row * rs + op.out_off + c0;
+#pragma unroll
+    for (int c = 0; c < CT; c += 4) {
+        float4 v = make_float4(acc[c], acc[c + 1], acc[c + 2], acc[c + 3]);
+        if (op.act) {
+            v.x = elu(v.x); v.y = elu(v.y); v.z = elu(v.z); v.w = elu(v.w);
+        }
+        *reinterpret_cast<float4*>(y + c) = v;
+    }
+}
+
+// Register tile for weights that stay in global memory / L2 (networks too large for the shared-memory
+// copy): RT rows x 4 columns per thread, so that one 16-byte weight load feeds RT * 4 FMAs.
+template <int RT>
+__device__ __forceinline__ void dense_tile_g(const LayerOp& op, const float* __restrict__ W, float* __restrict__ act,
+                                             int rs, int tt, const int* __restrict__ row_action,
+                                             const unsigned char* __restrict__ row_active, int A, int z) {
+    const int ncg = op.Npad >> 2;
+    const int rg = tt / ncg, cg = tt - rg * ncg;
+    const int row0 = rg * RT;
+    bool any = false;
+#pragma unroll
+    for (int r = 0; r < RT; ++r) any |= (row_active[row0 + r] != 0);
+    if (!any) return;
+    const int K = op.K;
+    const float* x = act + row0 * rs + op.in_off;
+    const float4* w = reinterpret_cast<const float4*>(W + op.w_off) + cg;
+    float4 acc[RT];
+    {
+        const float4 bias = __ldg(reinterpret_cast<const float4*>(W + op.b_off) + cg);
+#pragma unroll
+        for (int r = 0; r < RT; ++r) acc[r] = bias;
+    }
+    if (op.extra) {
+#pragma unroll
+        for (int r = 0; r < RT; ++r) {
+            const float4 e = __ldg(w + (K + row_action[row0 + r]) * ncg);
+            acc[r].x += e.x; acc[r].y += e.y; acc[r].z += e.z; acc[r].w += e.w;
+        }
+        if (op.extra == 2) {
+            const float4 f = __ldg(w + (K + A + z) * ncg);
+#pragma unroll
+            for (int r = 0; r < RT; ++r) {
+                acc[r].x += f.x; acc[r].y += f.y; acc[r].z += f.z; acc[r].w += f.w;
+            }
+        }
+    }
+    int k = 0;
+    for (; k + 4 <= K; k += 4) {
+        const float4 w0 = __ldg(w);
+        const float4 w1 = __ldg(w + ncg);
+        const float4 w2 = __ldg(w + 2 * ncg);
+        const float4 w3 = __ldg(w + 3 * ncg);
+        w += 4 * ncg;
+#pragma unroll
+        for (int r = 0; r < RT; ++r) {
+            const float4 xv = *reinterpret_cast<const float4*>(x + r * rs + k);
+            acc[r].x = fmaf(xv.x, w0.x, acc[r].x); acc[r].y = fmaf(xv.x, w0.y, acc[r].y);
+            acc[r].z = fmaf(xv.x, w0.z, acc[r].z); acc[r].w = fmaf(xv.x, w0.w, acc[r].w);
+            acc[r].x = fmaf(xv.y, w1.x, acc[r].x); acc[r].y = fmaf(xv.y, w1.y, acc[r].y);
+            acc[r].z = fmaf(xv.y, w1.z, acc[r].z); acc[r].w = fmaf(xv.y, w1.w, acc[r].w);
+            acc[r].x = fmaf(xv.z, w2.x, acc[r].x); acc[r].y = fmaf(xv.z, w2.y, acc[r].y);
+            acc[r].z = fmaf(xv.z, w2.z, acc[r].z); acc[r].w = fmaf(xv.z, w2.w, acc[r].w);
+            acc[r].x = fmaf(xv.w, w3.x, acc[r].x); acc[r].y = fmaf(xv.w, w3.y, acc[r].y);
+            acc[r].z = fmaf(xv.w, w3.z, acc[r].z); acc[r].w = fmaf(xv.w, w3.w, acc[r].w);
+        }
+    }
+    for (; k < K; ++k) {
+        const float4 w0 = __ldg(w);
+        w += ncg;
+#pragma unroll
+        for (int r = 0; r < RT; ++r) {
+            const float xv = x[r * rs + k];
+            acc[r].x = fmaf(xv, w0.x, acc[r].x); acc[r].y = fmaf(xv, w0.y, acc[r].y);
+            acc[r].z = fmaf(xv, w0.z, acc[r].z); acc[r].w = fmaf(xv, w0.w, acc[r].w);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < RT; ++r) {
+        if (!row_active[row0 + r]) continue;
+        float4 v = acc[r];
+        if (op.act) {
+            v.x = elu(v.x); v.y = elu(v.y); v.z = elu(v.z); v.w = elu(v.w);
+        }
+        *reinterpret_cast<float4*>(act + (row0 + r) * rs + op.out_off + cg * 4) = v;
+    }
+}
+
+// Runtime-indexed reads of kernel parameters compile to indexed constant loads (LDC) with a latency of
+// hundreds of cycles; the schedules are therefore copied to shared memory once per CTA.
+__device__ __forceinline__ void copy_schedule(Schedule* dst, const Schedule& src, int tid, int nthreads) {
+    const int* s = reinterpret_cast<const int*>(&src);
+    int* d = reinterpret_cast<int*>(dst);
+    for (int i = tid; i < (int)(sizeof(Schedule) / sizeof(int)); i += nthreads) d[i] = s[i];
+}
 
 // Evaluate all stages for the TM rows of this CTA. Every thread of the CTA must call it.
-template <int TM, int THREADS>
+template <int TM, int THREADS, bool WSMEM>
 __device__ void run_schedule(const Schedule& sc, const float* __restrict__ W, float* __restrict__ act,
                              const int* __restrict__ row_action, const unsigned char* __restrict__ row_active,
-                             int A, int z) {
+                             int A, int z, unsigned long long* dbg = nullptr) {
     const int tid = threadIdx.x;
     const int rs = sc.row_stride;
     for (int s = 0; s < sc.n_stages; ++s) {
         const Stage& st = sc.st[s];
-        int total = 0;
-        for (int o = 0; o < st.n_ops; ++o) total += TM * (st.ops[o].Npad >> 2);
-        for (int t = tid; t < total; t += THREADS) {
-            int o = 0, tt = t;
-            while (tt >= TM * (st.ops[o].Npad >> 2)) {
-                tt -= TM * (st.ops[o].Npad >> 2);
-                ++o;
+        long long d0 = 0, d1 = 0;
+        if (dbg && tid == 0) d0 = clock64();
+        if (!WSMEM) {
+            // weights in global memory: 4 x 4 register tiles
+            int total = 0;
+            for (int o = 0; o < st.n_ops; ++o) total += (TM / 4) * (st.ops[o].Npad >> 2);
+            for (int t = tid; t < total; t += THREADS) {
+                int o = 0, tt = t;
+                while (tt >= (TM / 4) * (st.ops[o].Npad >> 2)) {
+                    tt -= (TM / 4) * (st.ops[o].Npad >> 2);
+                    ++o;
+                }
+                dense_tile_g<4>(st.ops[o], W, act, rs, tt, row_action, row_active, A, z);
             }
-            const LayerOp& op = st.ops[o];
-            const int ncg = op.Npad >> 2;
-            const int row = tt / ncg, cg = tt - row * ncg;
-            if (!row_active[row]) continue;
-            const float* x = act + row * rs + op.in_off;
-            const float4* w = reinterpret_cast<const float4*>(W + op.w_off) + cg;
-            float4 acc = ldg4(reinterpret_cast<const float4*>(W + op.b_off) + cg);
-            const int K = op.K;
-            if (op.extra) {
-                const float4 e = ldg4(w + (K + row_action[row]) * ncg);
-                acc.x += e.x; acc.y += e.y; acc.z += e.z; acc.w += e.w;
-                if (op.extra == 2) {
-                    const float4 f = ldg4(w + (K + A + z) * ncg);
-                    acc.x += f.x; acc.y += f.y; acc.z += f.z; acc.w += f.w;
+        } else {
+            // units of this stage: (op, chunk of ct columns); thread -> (unit = tid / TM, row = tid % TM)
+            int total = 0;
+            for (int o = 0; o < st.n_ops; ++o) total += st.ops[o].Npad / st.ops[o].ct;
+            const int urow = tid % TM;
+            const bool uactive = row_active[urow] != 0;
+            const int uaction = row_action[urow];
+            for (int u = tid / TM; u < total; u += THREADS / TM) {
+                int o = 0, uu = u;
+                while (uu >= st.ops[o].Npad / st.ops[o].ct) {
+                    uu -= st.ops[o].Npad / st.ops[o].ct;
+                    ++o;
+                }
+                const LayerOp& op = st.ops[o];
+                switch (op.ct) {
+                    case 4: dense_unit<WSMEM, 4>(op, W, act, rs, urow, uu * 4, uaction, uactive, A, z); break;
+                    case 8: dense_unit<WSMEM, 8>(op, W, act, rs, urow, uu * 8, uaction, uactive, A, z); break;
+                    default: dense_unit<WSMEM, 16>(op, W, act, rs, urow, uu * 16, uaction, uactive, A, z); break;
                 }
             }
-            int k = 0;
-#pragma unroll 2
-            for (; k + 4 <= K; k += 4) {
-                const float4 xv = *reinterpret_cast<const float4*>(x + k);
-                const float4 w0 = ldg4(w + (k + 0) * ncg);
-                const float4 w1 = ldg4(w + (k + 1) * ncg);
-                const float4 w2 = ldg4(w + (k + 2) * ncg);
-                const float4 w3 = ldg4(w + (k + 3) * ncg);
-                acc.x = fmaf(xv.x, w0.x, acc.x); acc.y = fmaf(xv.x, w0.y, acc.y);
-                acc.z = fmaf(xv.x, w0.z, acc.z); acc.w = fmaf(xv.x, w0.w, acc.w);
-                acc.x = fmaf(xv.y, w1.x, acc.x); acc.y = fmaf(xv.y, w1.y, acc.y);
-                acc.z = fmaf(xv.y, w1.z, acc.z); acc.w = fmaf(xv.y, w1.w, acc.w);
-                acc.x = fmaf(xv.z, w2.x, acc.x); acc.y = fmaf(xv.z, w2.y, acc.y);
-                acc.z = fmaf(xv.z, w2.z, acc.z); acc.w = fmaf(xv.z, w2.w, acc.w);
-                acc.x = fmaf(xv.w, w3.x, acc.x); acc.y = fmaf(xv.w, w3.y, acc.y);
-                acc.z = fmaf(xv.w, w3.z, acc.z); acc.w = fmaf(xv.w, w3.w, acc.w);
-            }
-            for (; k < K; ++k) {
-                const float xv = x[k];
-                const float4 w0 = ldg4(w + k * ncg);
-                acc.x = fmaf(xv, w0.x, acc.x); acc.y = fmaf(xv, w0.y, acc.y);
-                acc.z = fmaf(xv, w0.z, acc.z); acc.w = fmaf(xv, w0.w, acc.w);
-            }
-            if (op.act) {
-                acc.x = elu(acc.x); acc.y = elu(acc.y); acc.z = elu(acc.z); acc.w = elu(acc.w);
-            }
-            *reinterpret_cast<float4*>(act + row * rs + op.out_off + cg * 4) = acc;
         }
         if (st.row_op == 1) {
             // models.py:223-231 / 248-255: (x - min) / scale, scale += 1e-5 only where scale < 1e-5
@@ -169,7 +327,13 @@ __device__ void run_schedule(const Schedule& sc, const float* __restrict__ W, fl
                 for (int i = j; i < st.r_n; i += GW) y[i] = __fdiv_rn(__fsub_rn(x[i], mn), scale);
             }
         }
+        if (dbg && tid == 0) d1 = clock64();
         __syncthreads();
+        if (dbg && tid == 0) {
+            const long long d2 = clock64();
+            atomicAdd(dbg + 8 + 2 * s, (unsigned long long)(d1 - d0));      // thread 0's own work in stage s
+            atomicAdd(dbg + 9 + 2 * s, (unsigned long long)(d2 - d1));      // its wait at the stage barrier
+        }
     }
 }
 
@@ -255,9 +419,9 @@ struct MinMax {
 
 // self_play.py:453-477 (VARIANT 0), self_play_stochastic.py:488-508 (1), self_play_risk_sensitive.py:496-520 (2)
 template <int VARIANT>
-__device__ __forceinline__ double ucb_score(double pb_log, int parent_visits, int visits, double vsum, double prior,
-                                            float reward, double discount, const MinMax& mm) {
-    double pb_c = __dmul_rn(pb_log, __ddiv_rn(__dsqrt_rn((double)parent_visits), (double)(visits + 1)));
+__device__ __forceinline__ double ucb_score(double pb_log, double sqrt_parent_visits, int visits, double vsum,
+                                            double prior, float reward, double discount, const MinMax& mm) {
+    double pb_c = __dmul_rn(pb_log, __ddiv_rn(sqrt_parent_visits, (double)(visits + 1)));
     const double prior_score = __dmul_rn(pb_c, prior);
     double value_score = 0.0;
     if (visits > 0) {
@@ -294,15 +458,16 @@ struct NetParams {
 
 struct SearchParams {
     int B, S, A, H, nf, support, mask_absorbing, uniform_policy;
-    int blocks_per_tree, hidden_per_tree, max_rec, T, K, max_iters;
+    int blocks_per_tree, hidden_per_tree, max_rec, T, K, max_iters, w_smem_floats, pb_stride;
     double discount;
-    const double* pb_table;  // [S + 2]: log((N + base + 1) / base) + init, host libm (bit-equal to math.log)
+    const double* pb_table;  // [2][S + 2]: log((N + base + 1) / base) + init, then sqrt(N); host libm (bit-equal to math.log / math.sqrt)
     void* blocks; float* hidden_pool; TreeHeader* hdr; const double* rootprior; const int* rootact;
     const unsigned char* tie; const unsigned char* chance;
     const float* fed; float* trace;
     const float* W;
     int* visit_counts; double* root_value; double* child_value; double* child_prior; double* child_reward;
-    int* max_depth; int* num_records;
+    int* max_depth; int* num_records; int* total_depth;
+    unsigned long long* phase_cycles;  // optional [8]: summed clock64 deltas of thread 0 of every CTA
     Schedule sched_a;  // VARIANT 0: recurrent inference; else: transition expansion (dynamics, per future z)
     Schedule sched_b;  // VARIANT != 0: prediction
 };
@@ -312,7 +477,10 @@ template <int NC, int TM>
 __global__ void __launch_bounds__(TM * GW) net_kernel(const __grid_constant__ NetParams p) {
     extern __shared__ __align__(16) float smem[];
     constexpr int THREADS = TM * GW;
-    const Schedule& sc = p.sched;
+    __shared__ Schedule s_sched;
+    copy_schedule(&s_sched, p.sched, threadIdx.x, THREADS);
+    __syncthreads();
+    const Schedule& sc = s_sched;
     const int rs = sc.row_stride;
     float* act = smem;
     int* row_action = reinterpret_cast<int*>(act + TM * rs);
@@ -335,7 +503,7 @@ __global__ void __launch_bounds__(TM * GW) net_kernel(const __grid_constant__ Ne
     __syncthreads();
     const int nz = (p.mode == 2) ? p.nf : 1;
     for (int z = 0; z < nz; ++z) {
-        if (!fed) run_schedule<TM, THREADS>(sc, p.W, act, row_action, row_active, p.A, z);
+        if (!fed) run_schedule<TM, THREADS, false>(sc, p.W, act, row_action, row_active, p.A, z);
         if (valid && !fed) {
             const float* r = act + row * rs;
             const int V = 2 * p.support + 1;
@@ -436,29 +604,49 @@ __global__ void __launch_bounds__(TM * GW) net_kernel(const __grid_constant__ Ne
 
 // -------------------------------------------------------------- search kernel ----
 // VARIANT 0: MCTS.run of self_play.py:378-427; 1: self_play_stochastic.py:329-393; 2: risk-sensitive.
-template <int VARIANT, int NC, int TM>
-__global__ void __launch_bounds__(TM * GW) search_kernel(const __grid_constant__ SearchParams p) {
+// XW: thread multiplier. The first TM * 8 threads own the trees (8 lanes each); the other
+// (XW - 1) * TM * 8 threads only help with the MLP tiles of phase 2.
+template <int VARIANT, int NC, int TM, bool WSMEM, int XW>
+__global__ void __launch_bounds__(TM * GW * XW) search_kernel(const __grid_constant__ SearchParams p) {
     extern __shared__ __align__(16) float smem[];
-    constexpr int THREADS = TM * GW;
+    constexpr int THREADS = TM * GW * XW;
     using Block = NodeBlock<NC>;
+    __shared__ Schedule s_sched[VARIANT == 0 ? 1 : 2];
+    copy_schedule(&s_sched[0], p.sched_a, threadIdx.x, THREADS);
+    if (VARIANT != 0) copy_schedule(&s_sched[VARIANT == 0 ? 0 : 1], p.sched_b, threadIdx.x, THREADS);
+    const Schedule& sched_a = s_sched[0];
+    const Schedule& sched_b = s_sched[VARIANT == 0 ? 0 : 1];
     const int rs = p.sched_a.row_stride;  // the host gives sched_a and sched_b the same row stride
-    double* pb = reinterpret_cast<double*>(smem);
+    // shared-memory carve-out (offsets only -- no integer round trips, so every pointer stays "shared")
+    double* pb = reinterpret_cast<double*>(smem);  // pb[N] = log((N + base + 1) / base) + init
     const int pb_n = (p.S + 2 + 1) & ~1;
-    float* act = reinterpret_cast<float*>(pb + pb_n);
+    double* sq = pb + pb_n;                        // sq[N] = sqrt(N), correctly rounded (host libm)
+    float* wsm = smem + 4 * pb_n;                  // optional copy of the search MLP weights
+    float* act = wsm + (WSMEM ? p.w_smem_floats : 0);
     int* row_action = reinterpret_cast<int*>(act + TM * rs);
     unsigned char* row_active = reinterpret_cast<unsigned char*>(row_action + TM);
     unsigned char* row_kind = row_active + TM;
+    const float* Wp;
+    if (WSMEM) Wp = wsm; else Wp = p.W;
 
     const int tid = threadIdx.x, lane = tid & 31, j = tid & 7, row = tid >> 3;
     const unsigned gmask = 0xFFu << (lane & 24);
     const int gl0 = lane & 24;  // first lane of this group inside the warp
     const int b = blockIdx.x * TM + row;
-    const bool valid = b < p.B;
+    const bool valid = (row < TM) && (b < p.B);  // helper threads (row >= TM) own no tree
     const bool fed = p.fed != nullptr;
     const int A = p.A, H = p.H, nf = p.nf;
     const double discount = p.discount;
 
-    for (int i = tid; i < p.S + 2; i += THREADS) pb[i] = p.pb_table[i];
+    for (int i = tid; i < p.S + 2; i += THREADS) {
+        pb[i] = p.pb_table[i];
+        sq[i] = p.pb_table[p.pb_stride + i];
+    }
+    if (WSMEM) {
+        const float4* src = reinterpret_cast<const float4*>(p.W);
+        float4* dst = reinterpret_cast<float4*>(wsm);
+        for (int i = tid; i < (p.w_smem_floats >> 2); i += THREADS) dst[i] = __ldg(src + i);
+    }
 
     Block* blocks = reinterpret_cast<Block*>(p.blocks) + (size_t)(valid ? b : 0) * p.blocks_per_tree;
     float* hpool = p.hidden_pool + (size_t)(valid ? b : 0) * p.hidden_per_tree * H;
@@ -471,7 +659,7 @@ __global__ void __launch_bounds__(TM * GW) search_kernel(const __grid_constant__
     mm.mx = -CUDART_INF;
     double root_vsum = 0.0, root_prior = 0.0;
     int root_visit = 0, n_blocks = 1, n_tgroups = 0, max_depth = 0, n_sims = 0, k_tie = 0, k_chance = 0, n_rec = 0;
-    int n_root = 0, root_act = 0;
+    int n_root = 0, root_act = 0, depth_total = 0;
     if (valid) {
         const TreeHeader h = p.hdr[b];
         n_root = h.n_root;
@@ -489,6 +677,8 @@ __global__ void __launch_bounds__(TM * GW) search_kernel(const __grid_constant__
             if (it >= p.S) break;
         }
 
+        long long tc0 = 0, tc1 = 0, tc2 = 0, tc3 = 0;
+        if (p.phase_cycles && tid == 0) tc0 = clock64();
         // ================= phase 1: selection (one 8-lane group per tree) =================
         int node = 0, slot = 0, depth = 0, Np = root_visit;
         bool parent_is_state = true;  // kind of block `node`
@@ -510,7 +700,7 @@ __global__ void __launch_bounds__(TM * GW) search_kernel(const __grid_constant__
                         prior = (node == 0) ? root_prior : (double)blk->prior[j];
                     }
                     double score = -CUDART_INF;
-                    if (on) score = ucb_score<VARIANT>(pb[Np], Np, vis, vs, prior, rw, discount, mm);
+                    if (on) score = ucb_score<VARIANT>(pb[Np], sq[Np], vis, vs, prior, rw, discount, mm);
                     double best = score;
 #pragma unroll
                     for (int d = 1; d < GW; d <<= 1) {
@@ -560,6 +750,7 @@ __global__ void __launch_bounds__(TM * GW) search_kernel(const __grid_constant__
                 hslot = 1 + (blocks[node].aux >> 8) * nf + slot;
             }
             if (depth > max_depth) max_depth = depth;
+            depth_total += depth;
         }
         const int kind = !active ? 0 : (leaf_is_state ? 1 : 2);
 
@@ -567,7 +758,7 @@ __global__ void __launch_bounds__(TM * GW) search_kernel(const __grid_constant__
         float value = 0.0f, reward = 0.0f, terminal = -1.0f, prior = 0.0f;  // state-leaf results
         float tprior = 0.0f, treward = 0.0f;                               // transition-leaf results (lane z)
         if (!fed) {
-            if (j == 0) {
+            if (j == 0 && row < TM) {
                 row_action[row] = action;
                 row_kind[row] = (unsigned char)kind;
                 if (VARIANT == 0) row_active[row] = active ? 1 : 0;
@@ -577,49 +768,52 @@ __global__ void __launch_bounds__(TM * GW) search_kernel(const __grid_constant__
                 float4* dst = reinterpret_cast<float4*>(act + row * rs);  // off_in == 0 in every search schedule
                 for (int i = j; i < (H >> 2); i += GW) dst[i] = src[i];
             }
+            if (p.phase_cycles && tid == 0) tc1 = clock64();
             __syncthreads();
+            if (p.phase_cycles && tid == 0) tc2 = clock64();
             if (VARIANT == 0) {
-                run_schedule<TM, THREADS>(p.sched_a, p.W, act, row_action, row_active, A, 0);
+                run_schedule<TM, THREADS, WSMEM>(sched_a, Wp, act, row_action, row_active, A, 0, p.phase_cycles);
+                if (p.phase_cycles && tid == 0) tc3 = clock64();
                 if (active) {
                     const float* r = act + row * rs;
-                    value = support_to_scalar_group(r + p.sched_a.off_vl, p.support, j, gmask);
-                    reward = support_to_scalar_group(r + p.sched_a.off_rl, p.support, j, gmask);
-                    if (p.mask_absorbing) terminal = r[p.sched_a.off_tl];
-                    const float lg = (j < A && !p.uniform_policy) ? r[p.sched_a.off_pl + j] : 0.0f;
+                    value = support_to_scalar_group(r + sched_a.off_vl, p.support, j, gmask);
+                    reward = support_to_scalar_group(r + sched_a.off_rl, p.support, j, gmask);
+                    if (p.mask_absorbing) terminal = r[sched_a.off_tl];
+                    const float lg = (j < A && !p.uniform_policy) ? r[sched_a.off_pl + j] : 0.0f;
                     prior = softmax_group(lg, j < A, gmask);
                 }
             } else {
                 const int any_t = __syncthreads_or(kind == 2);
                 const int any_s = __syncthreads_or(kind == 1);
                 if (any_t) {
-                    if (j == 0) row_active[row] = (kind == 2) ? 1 : 0;
+                    if (j == 0 && row < TM) row_active[row] = (kind == 2) ? 1 : 0;
                     __syncthreads();
                     for (int z = 0; z < nf; ++z) {
-                        run_schedule<TM, THREADS>(p.sched_a, p.W, act, row_action, row_active, A, z);
+                        run_schedule<TM, THREADS, WSMEM>(sched_a, Wp, act, row_action, row_active, A, z);
                         if (kind == 2) {
                             const float* r = act + row * rs;
-                            const float rw = support_to_scalar_group(r + p.sched_a.off_rl, p.support, j, gmask);
+                            const float rw = support_to_scalar_group(r + sched_a.off_rl, p.support, j, gmask);
                             if (j == z) treward = rw;
                             if (z == 0) {
-                                const float lg = (j < nf) ? r[p.sched_a.off_tp + j] : 0.0f;
+                                const float lg = (j < nf) ? r[sched_a.off_tp + j] : 0.0f;
                                 tprior = softmax_group(lg, j < nf, gmask);  // self_play_stochastic.py:553-554
                             }
                             // children's hidden states: slot 1 + t_ord * nf + z  (t_ord == n_tgroups)
                             float4* dst = reinterpret_cast<float4*>(hpool + (size_t)(1 + n_tgroups * nf + z) * H);
-                            const float4* src = reinterpret_cast<const float4*>(r + p.sched_a.off_hidden);
+                            const float4* src = reinterpret_cast<const float4*>(r + sched_a.off_hidden);
                             for (int i = j; i < (H >> 2); i += GW) dst[i] = src[i];
                         }
                         __syncthreads();
                     }
                 }
                 if (any_s) {
-                    if (j == 0) row_active[row] = (kind == 1) ? 1 : 0;
+                    if (j == 0 && row < TM) row_active[row] = (kind == 1) ? 1 : 0;
                     __syncthreads();
-                    run_schedule<TM, THREADS>(p.sched_b, p.W, act, row_action, row_active, A, 0);
+                    run_schedule<TM, THREADS, WSMEM>(sched_b, Wp, act, row_action, row_active, A, 0);
                     if (kind == 1) {
                         const float* r = act + row * rs;
-                        value = support_to_scalar_group(r + p.sched_b.off_vl, p.support, j, gmask);
-                        const float lg = (j < A) ? r[p.sched_b.off_pl + j] : 0.0f;
+                        value = support_to_scalar_group(r + sched_b.off_vl, p.support, j, gmask);
+                        const float lg = (j < A) ? r[sched_b.off_pl + j] : 0.0f;
                         prior = softmax_group(lg, j < A, gmask);
                     }
                 }
@@ -702,7 +896,7 @@ __global__ void __launch_bounds__(TM * GW) search_kernel(const __grid_constant__
                     }
                     if (VARIANT == 0 && !fed) {  // hidden state of the new node
                         float4* dst = reinterpret_cast<float4*>(hpool + (size_t)nb * H);
-                        const float4* src = reinterpret_cast<const float4*>(act + row * rs + p.sched_a.off_hidden);
+                        const float4* src = reinterpret_cast<const float4*>(act + row * rs + sched_a.off_hidden);
                         for (int i = j; i < (H >> 2); i += GW) dst[i] = src[i];
                     }
                 }
@@ -813,6 +1007,14 @@ __global__ void __launch_bounds__(TM * GW) search_kernel(const __grid_constant__
                 n_sims++;
             }
         }
+        if (p.phase_cycles && tid == 0 && VARIANT == 0 && !fed) {
+            const long long tc4 = clock64();
+            atomicAdd(p.phase_cycles + 0, (unsigned long long)(tc1 - tc0));  // select + gather (tree 0 of the CTA)
+            atomicAdd(p.phase_cycles + 1, (unsigned long long)(tc2 - tc1));  // wait for the slowest tree of the CTA
+            atomicAdd(p.phase_cycles + 2, (unsigned long long)(tc3 - tc2));  // MLP schedule
+            atomicAdd(p.phase_cycles + 3, (unsigned long long)(tc4 - tc3));  // decode + expand + backup
+            atomicAdd(p.phase_cycles + 4, 1ull);
+        }
         // No CTA barrier here: a row's activation strip is re-filled by the very group that read it in
         // phase 3, and every tile of this iteration finished before run_schedule's last barrier.
         __syncwarp(gmask);
@@ -827,6 +1029,7 @@ __global__ void __launch_bounds__(TM * GW) search_kernel(const __grid_constant__
                                                  : (root_visit == 0 ? 0.0 : __ddiv_rn(root_vsum, (double)root_visit));
             if (p.max_depth) p.max_depth[b] = max_depth;
             if (p.num_records) p.num_records[b] = n_rec;
+            if (p.total_depth) p.total_depth[b] = depth_total;
         }
         if (j < A) {  // zero-fill, then scatter the legal children to their action index
             if (p.visit_counts) p.visit_counts[(size_t)b * A + j] = 0;

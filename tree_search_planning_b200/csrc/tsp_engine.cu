@@ -63,21 +63,28 @@ struct tsp_engine {
     int device = 0;
     int sm_count = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-    bool ev_valid = false;
+    // ring of event triples (before root kernel, between, after search kernel), drained lazily
+    static constexpr int EV_RING = 1024;
+    std::vector<cudaEvent_t> ev;
+    int ev_head = 0, ev_pending = 0;
     std::vector<HostLayer> mlp[TSP_NUM_MLP];
     bool finalized = false;
     int nc = 5;  // node-block child capacity (5 or 8)
     int tm_override = 0;
+    bool no_wsmem = false;
+    int xw_override = 0;
+    int ct_override = 0;
 
     // device memory
     DevBuf arena;  // packed weights
     int64_t arena_floats = 0;
-    DevBuf blocks, hidden, hdr, rootprior, rootact, pbtable;
+    int64_t search_floats = 0;  // leading part of the arena used by the search kernel (everything but the representation net)
+    DevBuf blocks, hidden, hdr, rootprior, rootact, pbtable, phase;
+    bool phase_timing = false;
     int blocks_per_tree = 0, hidden_per_tree = 0, max_iters = 0;
     // staging for HOST-memory calls
     DevBuf s_obs, s_legal, s_nlegal, s_noise, s_tie, s_chance, s_fedroot, s_fed;
-    DevBuf s_visits, s_rootv, s_cval, s_cprior, s_crew, s_depth, s_rpred, s_rhid, s_nrec, s_troot, s_trace;
+    DevBuf s_visits, s_rootv, s_cval, s_cprior, s_crew, s_depth, s_rpred, s_rhid, s_nrec, s_troot, s_trace, s_tdepth;
     DevBuf n_in, n_act, n_o[8];
 
     Schedule sch_root{}, sch_recur{}, sch_trans{}, sch_pred{};
@@ -327,6 +334,35 @@ int build_schedules(tsp_engine* e) {
     return TSP_OK;
 }
 
+// Columns per thread for every op of a schedule evaluated by a CTA with `slots` = threads / TM
+// unit slots: the widest chunk (fewest loads per FMA) that still gives every slot a unit.
+void set_chunks(Schedule& sc, int slots, int forced) {
+    for (int s = 0; s < sc.n_stages; ++s) {
+        Stage& st = sc.st[s];
+        int best = 4;
+        for (int ct : {16, 8, 4}) {
+            bool ok = true;
+            int units = 0;
+            for (int o = 0; o < st.n_ops; ++o) {
+                int c = ct;
+                while (st.ops[o].Npad % c) c >>= 1;
+                units += st.ops[o].Npad / c;
+            }
+            if (units >= slots || ct == 4) {
+                best = ct;
+                break;
+            }
+            (void)ok;
+        }
+        if (forced == 4 || forced == 8 || forced == 16) best = forced;
+        for (int o = 0; o < st.n_ops; ++o) {
+            int c = best;
+            while (st.ops[o].Npad % c) c >>= 1;
+            st.ops[o].ct = (unsigned char)c;
+        }
+    }
+}
+
 template <typename K>
 int set_smem(tsp_engine* e, K kernel, size_t bytes) {
     if (bytes > 227 * 1024) return fail(e, TSP_EINVAL, "kernel needs %zu bytes of shared memory (> 227 KB)", bytes);
@@ -335,12 +371,14 @@ int set_smem(tsp_engine* e, K kernel, size_t bytes) {
 }
 
 size_t net_smem(const Schedule& sc, int TM) { return (size_t)TM * sc.row_stride * 4 + TM * 4 + TM * 2 + 16; }
-size_t search_smem(const Schedule& sc, int TM, int S) {
-    return (size_t)((S + 3) & ~1) * 8 + (size_t)TM * sc.row_stride * 4 + TM * 4 + TM * 2 + 16;
+size_t search_smem(const Schedule& sc, int TM, int S, size_t w_floats = 0) {
+    return (size_t)((S + 3) & ~1) * 16 + (size_t)TM * sc.row_stride * 4 + TM * 4 + TM * 2 + 32 + w_floats * 4;
 }
 
 template <int NC, int TM>
-int launch_net(tsp_engine* e, const NetParams& p) {
+int launch_net(tsp_engine* e, const NetParams& p_in) {
+    NetParams p = p_in;
+    set_chunks(p.sched, GW, e->ct_override);
     const size_t smem = net_smem(p.sched, TM);
     int rc = set_smem(e, net_kernel<NC, TM>, smem);
     if (rc) return rc;
@@ -358,41 +396,70 @@ int launch_net_any(tsp_engine* e, const NetParams& p) {
     return TM == 32 ? launch_net<8, 32>(e, p) : launch_net<8, 16>(e, p);
 }
 
-template <int VARIANT, int NC, int TM>
-int launch_search(tsp_engine* e, const SearchParams& p) {
-    const size_t smem = search_smem(p.sched_a, TM, p.S);
-    int rc = set_smem(e, search_kernel<VARIANT, NC, TM>, smem);
+template <int VARIANT, int NC, int TM, bool WSMEM, int XW>
+int launch_search_x(tsp_engine* e, const SearchParams& p_in) {
+    SearchParams p = p_in;
+    set_chunks(p.sched_a, GW * XW, e->ct_override);
+    set_chunks(p.sched_b, GW * XW, e->ct_override);
+    const size_t smem = search_smem(p.sched_a, TM, p.S, WSMEM ? (size_t)p.w_smem_floats : 0);
+    int rc = set_smem(e, search_kernel<VARIANT, NC, TM, WSMEM, XW>, smem);
     if (rc) return rc;
     const int grid = (p.B + TM - 1) / TM;
-    search_kernel<VARIANT, NC, TM><<<grid, TM * GW, smem, e->stream>>>(p);
+    search_kernel<VARIANT, NC, TM, WSMEM, XW><<<grid, TM * GW * XW, smem, e->stream>>>(p);
     CK(e, cudaGetLastError());
     e->stats.kernel_launches++;
     e->stats.search_ctas = grid;
     e->stats.search_smem_bytes = (int)smem;
     e->stats.trees_per_cta = TM;
+    e->stats.threads_per_cta = TM * GW * XW;
     return TSP_OK;
 }
 
-template <int VARIANT, int NC>
-int launch_search_tm(tsp_engine* e, const SearchParams& p, int TM) {
-    return TM == 32 ? launch_search<VARIANT, NC, 32>(e, p) : launch_search<VARIANT, NC, 16>(e, p);
+template <int VARIANT, int NC, int TM, bool WSMEM>
+int launch_search_w(tsp_engine* e, const SearchParams& p, int xw) {
+    if (NC == 5 && VARIANT == 0) {
+        if (xw == 2) return launch_search_x<VARIANT, NC, TM, WSMEM, (NC == 5 && VARIANT == 0 ? 2 : 1)>(e, p);
+    }
+    return launch_search_x<VARIANT, NC, TM, WSMEM, 1>(e, p);
 }
 
-int launch_search_any(tsp_engine* e, const SearchParams& p) {
+template <int VARIANT, int NC, int TM>
+int launch_search(tsp_engine* e, const SearchParams& p, int xw) {
+    return p.w_smem_floats > 0 ? launch_search_w<VARIANT, NC, TM, true>(e, p, xw)
+                               : launch_search_w<VARIANT, NC, TM, false>(e, p, xw);
+}
+
+template <int VARIANT, int NC>
+int launch_search_tm(tsp_engine* e, const SearchParams& p, int TM, int xw) {
+    if (NC == 5 && TM == 16) return launch_search<VARIANT, NC, (NC == 5 ? 16 : 32)>(e, p, xw);
+    return launch_search<VARIANT, NC, 32>(e, p, xw);
+}
+
+int launch_search_any(tsp_engine* e, const SearchParams& p_in) {
+    SearchParams p = p_in;
+    // 32 trees per CTA measured best at every batch size (4,096 .. 65,536 roots, both network sizes):
+    // lane == row in the MLP phase wants a full warp of rows; 16 is the fallback when the activation
+    // strips of 32 rows do not fit next to the weights.
     int TM = 32;
-    // small batches: 16 trees per CTA spreads the work over more SMs
-    if ((p.B + 31) / 32 < 2 * e->sm_count) TM = 16;
     if (search_smem(p.sched_a, 32, p.S) > 110 * 1024) TM = 16;
     if (e->tm_override == 16 || e->tm_override == 32) TM = e->tm_override;
+    if (e->nc != 5) TM = 32;
+    // keep the search MLP weights in shared memory when two CTAs per SM still fit
+    p.w_smem_floats = 0;
+    if (p.fed == nullptr && !e->no_wsmem &&
+        search_smem(p.sched_a, TM, p.S, (size_t)e->search_floats) <= 112 * 1024)
+        p.w_smem_floats = (int)e->search_floats;
     const int v = e->cfg.variant;
+    int xw = 1;  // helper threads for the MLP phase (developer knob)
+    if (e->xw_override == 1 || e->xw_override == 2) xw = e->xw_override;
     if (e->nc == 5) {
-        if (v == 0) return launch_search_tm<0, 5>(e, p, TM);
-        if (v == 1) return launch_search_tm<1, 5>(e, p, TM);
-        return launch_search_tm<2, 5>(e, p, TM);
+        if (v == 0) return launch_search_tm<0, 5>(e, p, TM, xw);
+        if (v == 1) return launch_search_tm<1, 5>(e, p, TM, xw);
+        return launch_search_tm<2, 5>(e, p, TM, xw);
     }
-    if (v == 0) return launch_search_tm<0, 8>(e, p, TM);
-    if (v == 1) return launch_search_tm<1, 8>(e, p, TM);
-    return launch_search_tm<2, 8>(e, p, TM);
+    if (v == 0) return launch_search_tm<0, 8>(e, p, 32, 1);
+    if (v == 1) return launch_search_tm<1, 8>(e, p, 32, 1);
+    return launch_search_tm<2, 8>(e, p, 32, 1);
 }
 
 // copy-in helper: returns the device pointer to use for an input array
@@ -438,6 +505,25 @@ int copy_out(tsp_engine* e, int memory, T* dst, const T* dev, size_t count) {
     return TSP_OK;
 }
 
+// accumulate the device times of every completed run (waits for the pending ones)
+int drain_events(tsp_engine* e) {
+    while (e->ev_pending > 0) {
+        cudaEvent_t* ev = &e->ev[3 * e->ev_head];
+        CK(e, cudaEventSynchronize(ev[2]));
+        float r = 0.f, s = 0.f;
+        CK(e, cudaEventElapsedTime(&r, ev[0], ev[1]));
+        CK(e, cudaEventElapsedTime(&s, ev[1], ev[2]));
+        e->stats.last_root_ms = r;
+        e->stats.last_search_ms = s;
+        e->stats.sum_root_ms += r;
+        e->stats.sum_search_ms += s;
+        e->stats.timed_runs++;
+        e->ev_head = (e->ev_head + 1) % tsp_engine::EV_RING;
+        e->ev_pending--;
+    }
+    return TSP_OK;
+}
+
 }  // namespace
 
 // ================================================================== C ABI ====
@@ -480,6 +566,10 @@ int tsp_create(const tsp_config* cfg, tsp_handle* out) {
     e->sm_count = prop.multiProcessorCount;
     e->nc = (std::max(cfg->num_actions, e->cfg.n_futures) <= 5) ? 5 : 8;
     if (const char* t = getenv("TSP_TREES_PER_CTA")) e->tm_override = atoi(t);
+    if (const char* t = getenv("TSP_NO_WSMEM")) e->no_wsmem = atoi(t) != 0;
+    if (const char* t = getenv("TSP_THREAD_MULT")) e->xw_override = atoi(t);
+    if (const char* t = getenv("TSP_PHASE_TIMING")) e->phase_timing = atoi(t) != 0;
+    if (const char* t = getenv("TSP_COLS_PER_THREAD")) e->ct_override = atoi(t);
     auto bail = [&](int rc) {
         g_create_error = e->err;
         tsp_destroy(e);
@@ -488,6 +578,7 @@ int tsp_create(const tsp_config* cfg, tsp_handle* out) {
     if (cudaSetDevice(e->device) != cudaSuccess) return bail(fail(e, TSP_ECUDA, "cudaSetDevice failed"));
     if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess)
         return bail(fail(e, TSP_ECUDA, "cudaStreamCreate failed"));
+    e->ev.resize(3 * tsp_engine::EV_RING, nullptr);
     for (auto& ev : e->ev)
         if (cudaEventCreate(&ev) != cudaSuccess) return bail(fail(e, TSP_ECUDA, "cudaEventCreate failed"));
 
@@ -512,12 +603,20 @@ int tsp_create(const tsp_config* cfg, tsp_handle* out) {
     if ((rc = ensure(e, e->rootact, B * GW * sizeof(int)))) return bail(rc);
     // pb_c table: log((N + pb_c_base + 1) / pb_c_base) + pb_c_init with the host libm, the same
     // correctly-rounded log CPython's math.log calls (self_play.py:457-462)
-    std::vector<double> pb(S + 2);
-    for (int n = 0; n < S + 2; ++n)
+    // ... followed by sqrt(N) (IEEE-exact, same as math.sqrt) so that the kernel never runs a double sqrt.
+    // The tables are laid out for max_simulations; tsp_run passes S == max_simulations-independent offsets.
+    std::vector<double> pb(2 * (S + 2));
+    for (int n = 0; n < S + 2; ++n) {
         pb[n] = std::log(((double)n + cfg->pb_c_base + 1.0) / cfg->pb_c_base) + cfg->pb_c_init;
+        pb[S + 2 + n] = std::sqrt((double)n);
+    }
     if ((rc = ensure(e, e->pbtable, pb.size() * sizeof(double)))) return bail(rc);
     if (cudaMemcpy(e->pbtable.p, pb.data(), pb.size() * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess)
         return bail(fail(e, TSP_ECUDA, "pb table upload failed"));
+    if (e->phase_timing) {
+        if ((rc = ensure(e, e->phase, 64 * sizeof(unsigned long long)))) return bail(rc);
+        cudaMemset(e->phase.p, 0, 64 * sizeof(unsigned long long));
+    }
     e->stats.sm_count = e->sm_count;
     *out = e;
     return TSP_OK;
@@ -527,10 +626,10 @@ int tsp_destroy(tsp_handle e) {
     if (!e) return TSP_OK;
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
-    for (DevBuf* b : {&e->arena, &e->blocks, &e->hidden, &e->hdr, &e->rootprior, &e->rootact, &e->pbtable, &e->s_obs,
+    for (DevBuf* b : {&e->arena, &e->blocks, &e->hidden, &e->hdr, &e->rootprior, &e->rootact, &e->pbtable, &e->phase, &e->s_obs,
                       &e->s_legal, &e->s_nlegal, &e->s_noise, &e->s_tie, &e->s_chance, &e->s_fedroot, &e->s_fed,
                       &e->s_visits, &e->s_rootv, &e->s_cval, &e->s_cprior, &e->s_crew, &e->s_depth, &e->s_rpred,
-                      &e->s_rhid, &e->s_nrec, &e->s_troot, &e->s_trace, &e->n_in, &e->n_act})
+                      &e->s_rhid, &e->s_nrec, &e->s_troot, &e->s_trace, &e->s_tdepth, &e->n_in, &e->n_act})
         release(*b);
     for (auto& b : e->n_o) release(b);
     for (auto& ev : e->ev)
@@ -562,7 +661,11 @@ int tsp_finalize_weights(tsp_handle e) {
     // pack: per layer Wt[in_dim][npad] (transposed so that consecutive threads read consecutive
     // output columns), zero padded to a multiple of 4 columns, followed by the bias [npad]
     int64_t total = 0;
-    for (auto& v : e->mlp)
+    const int order[TSP_NUM_MLP] = {TSP_MLP_DYNAMICS, TSP_MLP_REWARD, TSP_MLP_TERMINAL, TSP_MLP_POLICY, TSP_MLP_VALUE,
+                                    TSP_MLP_PRIOR, TSP_MLP_REPRESENTATION};
+    for (int oi = 0; oi < TSP_NUM_MLP; ++oi) {
+        auto& v = e->mlp[order[oi]];
+        if (order[oi] == TSP_MLP_REPRESENTATION) e->search_floats = total;
         for (size_t l = 0; l < v.size(); ++l) {
             HostLayer& L = v[l];
             if (L.out_dim == 0) return fail(e, TSP_ESTATE, "a Linear layer is missing (set every layer index)");
@@ -573,6 +676,7 @@ int tsp_finalize_weights(tsp_handle e) {
             L.b_off = (int)total;
             total += L.npad;
         }
+    }
     if (total == 0) return fail(e, TSP_ESTATE, "no weights loaded");
     std::vector<float> host((size_t)total, 0.0f);
     for (auto& v : e->mlp)
@@ -675,12 +779,14 @@ int tsp_run(tsp_handle e, const tsp_run_args* a) {
     sp.max_iters = (c.variant == 0) ? S : S + (S + 1) * A + 1;
     sp.discount = c.discount;
     sp.pb_table = reinterpret_cast<const double*>(e->pbtable.p);
+    sp.pb_stride = c.max_simulations + 2;
     sp.blocks = e->blocks.p;
     sp.hidden_pool = reinterpret_cast<float*>(e->hidden.p);
     sp.hdr = reinterpret_cast<TreeHeader*>(e->hdr.p);
     sp.rootprior = reinterpret_cast<const double*>(e->rootprior.p);
     sp.rootact = reinterpret_cast<const int*>(e->rootact.p);
     sp.W = reinterpret_cast<const float*>(e->arena.p);
+    sp.phase_cycles = reinterpret_cast<unsigned long long*>(e->phase.p);
     if (c.variant == 0) {
         sp.sched_a = e->sch_recur;
     } else {
@@ -705,14 +811,17 @@ int tsp_run(tsp_handle e, const tsp_run_args* a) {
     if ((rc = stage_out(e, mem, a->child_reward, nb * A, e->s_crew, &sp.child_reward))) return rc;
     if ((rc = stage_out(e, mem, a->max_tree_depth, nb, e->s_depth, &sp.max_depth))) return rc;
     if ((rc = stage_out(e, mem, a->num_records, nb, e->s_nrec, &sp.num_records))) return rc;
+    if ((rc = stage_out(e, mem, a->total_select_depth, nb, e->s_tdepth, &sp.total_depth))) return rc;
     if (fed && a->fed_records == nullptr) sp.fed = reinterpret_cast<const float*>(e->hdr.p);  // S == 0: never read
 
-    CK(e, cudaEventRecord(e->ev[0], e->stream));
+    if (e->ev_pending == tsp_engine::EV_RING && (rc = drain_events(e))) return rc;
+    cudaEvent_t* ev = &e->ev[3 * ((e->ev_head + e->ev_pending) % tsp_engine::EV_RING)];
+    CK(e, cudaEventRecord(ev[0], e->stream));
     if ((rc = launch_net_any(e, np))) return rc;
-    CK(e, cudaEventRecord(e->ev[1], e->stream));
+    CK(e, cudaEventRecord(ev[1], e->stream));
     if ((rc = launch_search_any(e, sp))) return rc;
-    CK(e, cudaEventRecord(e->ev[2], e->stream));
-    e->ev_valid = true;
+    CK(e, cudaEventRecord(ev[2], e->stream));
+    e->ev_pending++;
 
     if ((rc = copy_out(e, mem, a->trace_root, np.trace_root, nb * REC))) return rc;
     if ((rc = copy_out(e, mem, a->root_predicted_value, np.root_pred, nb))) return rc;
@@ -725,6 +834,7 @@ int tsp_run(tsp_handle e, const tsp_run_args* a) {
     if ((rc = copy_out(e, mem, a->child_reward, sp.child_reward, nb * A))) return rc;
     if ((rc = copy_out(e, mem, a->max_tree_depth, sp.max_depth, nb))) return rc;
     if ((rc = copy_out(e, mem, a->num_records, sp.num_records, nb))) return rc;
+    if ((rc = copy_out(e, mem, a->total_select_depth, sp.total_depth, nb))) return rc;
     e->stats.searches++;
     return TSP_OK;
 }
@@ -809,13 +919,32 @@ int tsp_synchronize(tsp_handle e) {
 int tsp_get_stats(tsp_handle e, tsp_stats* out) {
     if (!e || !out) return TSP_EINVAL;
     CK(e, cudaSetDevice(e->device));
-    if (e->ev_valid) {
-        CK(e, cudaEventSynchronize(e->ev[2]));
-        CK(e, cudaEventElapsedTime(&e->stats.last_root_ms, e->ev[0], e->ev[1]));
-        CK(e, cudaEventElapsedTime(&e->stats.last_search_ms, e->ev[1], e->ev[2]));
-    }
+    int rc = drain_events(e);
+    if (rc) return rc;
     e->stats.pool_bytes = e->pool_bytes;
     *out = e->stats;
+    return TSP_OK;
+}
+
+int tsp_reset_timing(tsp_handle e) {
+    if (!e) return TSP_EINVAL;
+    CK(e, cudaSetDevice(e->device));
+    int rc = drain_events(e);
+    if (rc) return rc;
+    e->stats.sum_search_ms = 0.0;
+    e->stats.sum_root_ms = 0.0;
+    e->stats.timed_runs = 0;
+    return TSP_OK;
+}
+
+int tsp_debug_phase_cycles(tsp_handle e, uint64_t out[64], int32_t reset) {
+    if (!e || !out) return TSP_EINVAL;
+    for (int i = 0; i < 64; ++i) out[i] = 0;
+    if (!e->phase.p) return TSP_OK;
+    CK(e, cudaSetDevice(e->device));
+    CK(e, cudaStreamSynchronize(e->stream));
+    CK(e, cudaMemcpy(out, e->phase.p, 64 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    if (reset) CK(e, cudaMemset(e->phase.p, 0, 64 * sizeof(uint64_t)));
     return TSP_OK;
 }
 

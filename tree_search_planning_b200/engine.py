@@ -44,7 +44,7 @@ class _RunArgs(ctypes.Structure):
         ("tie_stream", _P), ("chance_stream", _P), ("fed_root", _P), ("fed_records", _P),
         ("visit_counts", _P), ("root_value", _P), ("child_value", _P), ("child_prior", _P),
         ("child_reward", _P), ("max_tree_depth", _P), ("root_predicted_value", _P), ("root_hidden", _P),
-        ("num_records", _P), ("trace_root", _P), ("trace_records", _P),
+        ("num_records", _P), ("total_select_depth", _P), ("trace_root", _P), ("trace_records", _P),
     ]
 
 
@@ -52,8 +52,10 @@ class Stats(ctypes.Structure):
     _fields_ = [
         ("kernel_launches", ctypes.c_int64), ("searches", ctypes.c_int64), ("bytes_h2d", ctypes.c_int64),
         ("bytes_d2h", ctypes.c_int64), ("pool_bytes", ctypes.c_int64), ("last_search_ms", ctypes.c_float),
-        ("last_root_ms", ctypes.c_float), ("sm_count", ctypes.c_int32), ("search_ctas", ctypes.c_int32),
+        ("last_root_ms", ctypes.c_float), ("sum_search_ms", ctypes.c_double), ("sum_root_ms", ctypes.c_double),
+        ("timed_runs", ctypes.c_int64), ("sm_count", ctypes.c_int32), ("search_ctas", ctypes.c_int32),
         ("search_smem_bytes", ctypes.c_int32), ("trees_per_cta", ctypes.c_int32),
+        ("threads_per_cta", ctypes.c_int32), ("reserved", ctypes.c_int32),
     ]
 
     def as_dict(self):
@@ -64,7 +66,7 @@ class Stats(ctypes.Structure):
 ABI_SYMBOLS = (
     "tsp_abi_version", "tsp_create", "tsp_destroy", "tsp_last_error", "tsp_set_layer", "tsp_finalize_weights",
     "tsp_weight_arena", "tsp_run", "tsp_initial_inference", "tsp_recurrent_inference", "tsp_stochastic_dynamics",
-    "tsp_prediction", "tsp_synchronize", "tsp_get_stats", "tsp_stream",
+    "tsp_prediction", "tsp_synchronize", "tsp_get_stats", "tsp_reset_timing", "tsp_debug_phase_cycles", "tsp_stream",
 )
 
 _lib = None
@@ -96,6 +98,8 @@ def load_library(path=None):
     lib.tsp_prediction.argtypes = [_P, ctypes.c_int32, ctypes.c_int32] + [_P] * 3
     lib.tsp_synchronize.argtypes = [_P]
     lib.tsp_get_stats.argtypes = [_P, ctypes.POINTER(Stats)]
+    lib.tsp_reset_timing.argtypes = [_P]
+    lib.tsp_debug_phase_cycles.argtypes = [_P, ctypes.POINTER(ctypes.c_uint64 * 64), ctypes.c_int32]
     lib.tsp_stream.argtypes = [_P, ctypes.POINTER(_P)]
     if path is None:
         _lib = lib
@@ -235,7 +239,8 @@ class Engine:
         shapes = dict(visit_counts=((B, A), numpy.int32), root_value=((B,), numpy.float64),
                       child_value=((B, A), numpy.float64), child_prior=((B, A), numpy.float64),
                       child_reward=((B, A), numpy.float64), max_tree_depth=((B,), numpy.int32),
-                      root_predicted_value=((B,), numpy.float32), num_records=((B,), numpy.int32))
+                      root_predicted_value=((B,), numpy.float32), num_records=((B,), numpy.int32),
+                      total_select_depth=((B,), numpy.int32))
         out = {k: numpy.zeros(*shapes[k]) for k in want}
         if want_root_hidden:
             out["root_hidden"] = numpy.zeros((B, self.H), numpy.float32)
@@ -249,7 +254,7 @@ class Engine:
                      _ptr(out.get("visit_counts")), _ptr(out.get("root_value")), _ptr(out.get("child_value")),
                      _ptr(out.get("child_prior")), _ptr(out.get("child_reward")), _ptr(out.get("max_tree_depth")),
                      _ptr(out.get("root_predicted_value")), _ptr(out.get("root_hidden")), _ptr(out.get("num_records")),
-                     _ptr(out.get("trace_root")), _ptr(out.get("trace_records")))
+                     _ptr(out.get("total_select_depth")), _ptr(out.get("trace_root")), _ptr(out.get("trace_records")))
         self.run_raw(a)
         if synchronize:
             self.synchronize()
@@ -313,6 +318,35 @@ class Engine:
         s = Stats()
         self._check(self.lib.tsp_get_stats(self.handle, ctypes.byref(s)))
         return s.as_dict()
+
+    def phase_cycles(self, reset=True):
+        """Developer instrumentation (needs TSP_PHASE_TIMING=1 in the environment at construction)."""
+        buf = (ctypes.c_uint64 * 64)()
+        self._check(self.lib.tsp_debug_phase_cycles(self.handle, ctypes.byref(buf), int(reset)))
+        v = list(buf)
+        n = max(1, v[4])
+        stages = [(round(v[8 + 2 * s] / n), round(v[9 + 2 * s] / n)) for s in range(14) if v[8 + 2 * s] or v[9 + 2 * s]]
+        return dict(select=v[0] / n, wait=v[1] / n, mlp=v[2] / n, backup=v[3] / n, samples=v[4],
+                    stages_work_wait=stages)
+
+    def reset_timing(self):
+        self._check(self.lib.tsp_reset_timing(self.handle))
+
+    def make_args(self, num_roots, num_simulations, memory, inputs, outputs, add_exploration_noise=True,
+                  uniform_policy=False, max_records=0, tie_len=0, chance_len=0):
+        """Build a tsp_run_args over caller-owned buffers (numpy arrays, or torch tensors for device /
+        pinned memory). `inputs` / `outputs` map the field names of tsp_run_args to buffers."""
+        a = _RunArgs()
+        a.num_roots, a.num_simulations, a.memory = int(num_roots), int(num_simulations), int(memory)
+        a.add_exploration_noise, a.uniform_policy = int(bool(add_exploration_noise)), int(bool(uniform_policy))
+        a.max_records, a.tie_len, a.chance_len = int(max_records), int(tie_len), int(chance_len)
+        names = {n for n, _ in _RunArgs._fields_}
+        for k, v in list(inputs.items()) + list(outputs.items()):
+            if k not in names:
+                raise KeyError(k)
+            setattr(a, k, _ptr(v))
+        a._keep = (inputs, outputs)
+        return a
 
     def stream(self):
         p = _P()
