@@ -66,8 +66,12 @@ struct LayerOp {
     short in_off, out_off;  // float offsets inside a row's activation strip
     unsigned char act;      // 0 identity, 1 ELU
     unsigned char extra;    // 0 none, 1 + Wt[K + action], 2 + Wt[K + action] + Wt[K + A + z]
-    unsigned char ct;       // output columns per thread (4, 8 or 16; divides Npad), set per launch
-    unsigned char pad;
+    unsigned char ct;       // SIMT path: output columns per thread (4, 8 or 16; divides Npad), set per launch
+    unsigned char ng;       // tensor-core path: adjacent 8-column tiles per warp unit (1..4), set per launch
+    short wld;              // leading dimension of Wt in floats (== 8 or 24 mod 32)
+    short units;            // tensor-core path: warp units of this op = (TM / 16) * groups, set per launch
+    short groups;           // ceil((Npad / 8) / ng)
+    short pad2;
 };
 struct Stage {
     unsigned char n_ops;
@@ -108,10 +112,10 @@ __device__ __forceinline__ float4 ldw4(const float4* p) {
 template <bool WSMEM, int CT>
 __device__ __forceinline__ void dense_unit(const LayerOp& op, const float* __restrict__ W, float* __restrict__ act,
                                            int rs, int row, int c0, int action, bool active, int A, int z) {
-    const int npad = op.Npad;
+    const int npad = op.wld;  // row stride of Wt
     const int K = op.K;
     const float* x = act + row * rs + op.in_off;
-    const float* wp = W + op.w_off + c0;  // row k of Wt starts at wp + k * npad
+    const float* wp = W + op.w_off + c0;  // row k of Wt starts at wp + k * wld
     float acc[CT];
 #pragma unroll
     for (int c = 0; c < CT; c += 4) {
@@ -181,8 +185,9 @@ template <int RT>
 __device__ __forceinline__ void dense_tile_g(const LayerOp& op, const float* __restrict__ W, float* __restrict__ act,
                                              int rs, int tt, const int* __restrict__ row_action,
                                              const unsigned char* __restrict__ row_active, int A, int z) {
-    const int ncg = op.Npad >> 2;
-    const int rg = tt / ncg, cg = tt - rg * ncg;
+    const int ncgs = op.Npad >> 2;   // column groups of the tile grid
+    const int ncg = op.wld >> 2;     // row stride of Wt in float4
+    const int rg = tt / ncgs, cg = tt - rg * ncgs;
     const int row0 = rg * RT;
     bool any = false;
 #pragma unroll
@@ -252,6 +257,158 @@ __device__ __forceinline__ void dense_tile_g(const LayerOp& op, const float* __r
     }
 }
 
+// ------------------------------------------------------------- tensor-core MLP tiles ----
+// One warp computes a 16 (trees) x 8 (outputs) tile of a Linear layer with mma.sync.m16n8k8 on TF32
+// operands, using the 3xTF32 split (x = hi + lo, hi = rna-tf32(x), lo = x - hi;
+// x*w ~= hi_x*hi_w + hi_x*lo_w + lo_x*hi_w) accumulated in fp32: the dropped lo*lo term is ~2^-22 relative,
+// i.e. float32-level accuracy, which keeps the 1e-5 network parity of the CUDA-core path.
+// Why not tcgen05 here: a CTA holds 32 trees, a tcgen05 tile needs M >= 64 rows and a TMEM -> register ->
+// swizzled-bf16 shared-memory epilogue after EVERY layer (~500 instructions per thread per stage), more than
+// the whole warp-level stage costs (~170). Activations stay float32 in shared memory between layers.
+// hi = x with the 13 low mantissa bits cleared (exactly representable in TF32), lo = x - hi (exact in
+// fp32, |lo| < 2^-10 |x|). cvt.rna.tf32 would halve |lo| but is emulated with ~6 integer instructions
+// on sm_100a (measured: 1.4k of 13.5k instructions per step); the dropped lo*lo term stays < 2^-20.
+__device__ __forceinline__ unsigned tf32_hi(float x) { return __float_as_uint(x) & 0xFFFFE000u; }
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const unsigned (&a)[4], const unsigned (&b)[2]) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+template <bool WSMEM>
+__device__ __forceinline__ float ldw1(const float* p) {
+    if (WSMEM) return *p;
+    return __ldg(p);
+}
+
+// Unit (mt, nt0 .. nt0 + NT - 1): rows [16 mt, 16 mt + 16) x NT adjacent 8-column tiles, one warp.
+// The A fragments (activations) are loaded and split once per k-step and reused by the NT tiles; every
+// tile has two independent accumulators (hi*hi, and the two correction products), so that consecutive
+// mma.sync instructions never wait on each other's ~35-cycle latency.
+template <bool WSMEM, int NT>
+__device__ __forceinline__ void mma_tiles(const LayerOp& op, const float* __restrict__ W, float* __restrict__ act,
+                                          int rs, int mt, int nt0, const int* __restrict__ row_action,
+                                          const unsigned char* __restrict__ row_active, int A, int z,
+                                          unsigned long long* dbg = nullptr) {
+    long long q0 = 0, q1 = 0, q2 = 0;
+    if (dbg && threadIdx.x == 0) q0 = clock64();
+    const int lane = threadIdx.x & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int r0 = mt * 16 + g, r1 = r0 + 8;
+    const int ntiles = op.Npad >> 3;
+    const int K = op.K, wld = op.wld;
+    const bool on0 = row_active[r0] != 0, on1 = row_active[r1] != 0;
+    const int ra0 = row_action[r0], ra1 = row_action[r1];
+    const float* x0 = act + r0 * rs + op.in_off;
+    const float* x1 = act + r1 * rs + op.in_off;
+    const float* wb = W + op.w_off + nt0 * 8;  // Wt[k][8 nt0 + n] at wb[k * wld + n]
+    float dm[NT][4], dc[NT][4];
+#pragma unroll
+    for (int i = 0; i < NT; ++i) {
+        dc[i][0] = dc[i][1] = dc[i][2] = dc[i][3] = 0.f;
+        dm[i][0] = dm[i][1] = dm[i][2] = dm[i][3] = 0.f;
+        if (nt0 + i < ntiles) {  // accumulator init: bias (+ the one-hot rows of the action / future)
+            const float* bp = W + op.b_off + (nt0 + i) * 8 + 2 * t;
+            const float b0 = ldw1<WSMEM>(bp), b1 = ldw1<WSMEM>(bp + 1);
+            dm[i][0] = b0; dm[i][1] = b1; dm[i][2] = b0; dm[i][3] = b1;
+            if (op.extra) {
+                const float* e0 = wb + (K + ra0) * wld + i * 8 + 2 * t;
+                const float* e1 = wb + (K + ra1) * wld + i * 8 + 2 * t;
+                dm[i][0] += ldw1<WSMEM>(e0); dm[i][1] += ldw1<WSMEM>(e0 + 1);
+                dm[i][2] += ldw1<WSMEM>(e1); dm[i][3] += ldw1<WSMEM>(e1 + 1);
+                if (op.extra == 2) {
+                    const float* f = wb + (K + A + z) * wld + i * 8 + 2 * t;
+                    const float f0 = ldw1<WSMEM>(f), f1 = ldw1<WSMEM>(f + 1);
+                    dm[i][0] += f0; dm[i][1] += f1; dm[i][2] += f0; dm[i][3] += f1;
+                }
+            }
+        }
+    }
+    if (dbg && threadIdx.x == 0) q1 = clock64();
+    const float* wk = wb + t * wld + g;  // B fragment: b0 = Wt[k0 + t][n + g], b1 = Wt[k0 + t + 4][n + g]
+    const int kfull = K & ~7;
+#pragma unroll 2
+    for (int k0 = 0; k0 < kfull; k0 += 8) {
+        const float a0f = x0[k0 + t], a1f = x1[k0 + t], a2f = x0[k0 + t + 4], a3f = x1[k0 + t + 4];
+        float bf[NT][2];
+#pragma unroll
+        for (int i = 0; i < NT; ++i) {
+            bf[i][0] = bf[i][1] = 0.f;
+            if (nt0 + i < ntiles) {
+                bf[i][0] = ldw1<WSMEM>(wk + i * 8);
+                bf[i][1] = ldw1<WSMEM>(wk + i * 8 + 4 * wld);
+            }
+        }
+        wk += 8 * wld;
+        unsigned ah[4], al[4];
+        ah[0] = tf32_hi(a0f); ah[1] = tf32_hi(a1f); ah[2] = tf32_hi(a2f); ah[3] = tf32_hi(a3f);
+        al[0] = __float_as_uint(a0f - __uint_as_float(ah[0]));
+        al[1] = __float_as_uint(a1f - __uint_as_float(ah[1]));
+        al[2] = __float_as_uint(a2f - __uint_as_float(ah[2]));
+        al[3] = __float_as_uint(a3f - __uint_as_float(ah[3]));
+#pragma unroll
+        for (int i = 0; i < NT; ++i) {
+            if (nt0 + i < ntiles) {
+                unsigned bh[2], bl[2];
+                bh[0] = tf32_hi(bf[i][0]); bh[1] = tf32_hi(bf[i][1]);
+                bl[0] = __float_as_uint(bf[i][0] - __uint_as_float(bh[0]));
+                bl[1] = __float_as_uint(bf[i][1] - __uint_as_float(bh[1]));
+                mma_tf32(dm[i], ah, bh);
+                mma_tf32(dc[i], al, bh);
+                mma_tf32(dc[i], ah, bl);
+            }
+        }
+    }
+    if (kfull < K) {  // K not a multiple of 8 (e.g. the 465-wide observation): zero the out-of-range operands
+        const int k0 = kfull;
+        const bool lo_ok = (k0 + t) < K, hi_ok = (k0 + t + 4) < K;
+        const float a0f = lo_ok ? x0[k0 + t] : 0.f, a1f = lo_ok ? x1[k0 + t] : 0.f;
+        const float a2f = hi_ok ? x0[k0 + t + 4] : 0.f, a3f = hi_ok ? x1[k0 + t + 4] : 0.f;
+        unsigned ah[4], al[4];
+        ah[0] = tf32_hi(a0f); ah[1] = tf32_hi(a1f); ah[2] = tf32_hi(a2f); ah[3] = tf32_hi(a3f);
+        al[0] = __float_as_uint(a0f - __uint_as_float(ah[0]));
+        al[1] = __float_as_uint(a1f - __uint_as_float(ah[1]));
+        al[2] = __float_as_uint(a2f - __uint_as_float(ah[2]));
+        al[3] = __float_as_uint(a3f - __uint_as_float(ah[3]));
+#pragma unroll
+        for (int i = 0; i < NT; ++i) {
+            if (nt0 + i < ntiles) {
+                const float b0f = lo_ok ? ldw1<WSMEM>(wk + i * 8) : 0.f;
+                const float b1f = hi_ok ? ldw1<WSMEM>(wk + i * 8 + 4 * wld) : 0.f;
+                unsigned bh[2], bl[2];
+                bh[0] = tf32_hi(b0f); bh[1] = tf32_hi(b1f);
+                bl[0] = __float_as_uint(b0f - __uint_as_float(bh[0]));
+                bl[1] = __float_as_uint(b1f - __uint_as_float(bh[1]));
+                mma_tf32(dm[i], ah, bh);
+                mma_tf32(dc[i], al, bh);
+                mma_tf32(dc[i], ah, bl);
+            }
+        }
+    }
+    if (dbg && threadIdx.x == 0) q2 = clock64();
+    // C fragment: d0,d1 = C[g][2t, 2t+1], d2,d3 = C[g+8][2t, 2t+1]
+#pragma unroll
+    for (int i = 0; i < NT; ++i) {
+        if (nt0 + i < ntiles) {
+            float d0 = dm[i][0] + dc[i][0], d1 = dm[i][1] + dc[i][1], d2 = dm[i][2] + dc[i][2], d3 = dm[i][3] + dc[i][3];
+            if (op.act) {
+                d0 = elu(d0); d1 = elu(d1); d2 = elu(d2); d3 = elu(d3);
+            }
+            float* y = act + op.out_off + (nt0 + i) * 8 + 2 * t;
+            if (on0) *reinterpret_cast<float2*>(y + r0 * rs) = make_float2(d0, d1);
+            if (on1) *reinterpret_cast<float2*>(y + r1 * rs) = make_float2(d2, d3);
+        }
+    }
+    if (dbg && threadIdx.x == 0) {
+        const long long q3 = clock64();
+        atomicAdd(dbg + 40, (unsigned long long)(q1 - q0));  // accumulator init (bias, one-hot rows)
+        atomicAdd(dbg + 41, (unsigned long long)(q2 - q1));  // k loop
+        atomicAdd(dbg + 42, (unsigned long long)(q3 - q2));  // ELU + store
+        atomicAdd(dbg + 43, 1ull);
+    }
+}
+
 // Runtime-indexed reads of kernel parameters compile to indexed constant loads (LDC) with a latency of
 // hundreds of cycles; the schedules are therefore copied to shared memory once per CTA.
 __device__ __forceinline__ void copy_schedule(Schedule* dst, const Schedule& src, int tid, int nthreads) {
@@ -261,7 +418,7 @@ __device__ __forceinline__ void copy_schedule(Schedule* dst, const Schedule& src
 }
 
 // Evaluate all stages for the TM rows of this CTA. Every thread of the CTA must call it.
-template <int TM, int THREADS, bool WSMEM>
+template <int TM, int THREADS, bool WSMEM, bool MMA = true>
 __device__ void run_schedule(const Schedule& sc, const float* __restrict__ W, float* __restrict__ act,
                              const int* __restrict__ row_action, const unsigned char* __restrict__ row_active,
                              int A, int z, unsigned long long* dbg = nullptr) {
@@ -271,7 +428,30 @@ __device__ void run_schedule(const Schedule& sc, const float* __restrict__ W, fl
         const Stage& st = sc.st[s];
         long long d0 = 0, d1 = 0;
         if (dbg && tid == 0) d0 = clock64();
-        if (!WSMEM) {
+        if (MMA) {
+            // tensor-core path: one warp per unit = 16 rows x ng adjacent 8-column tiles
+            // (unit counts are precomputed on the host: no integer divisions by runtime values here)
+            const int nops = st.n_ops;
+            int total = 0;
+            for (int o = 0; o < nops; ++o) total += st.ops[o].units;
+            for (int u = tid >> 5; u < total; u += THREADS / 32) {
+                int o = 0, uu = u;
+                while (uu >= st.ops[o].units) {
+                    uu -= st.ops[o].units;
+                    ++o;
+                }
+                const LayerOp& op = st.ops[o];
+                const int groups = op.groups;
+                const int mt = (TM == 16 || uu < groups) ? 0 : 1;  // TM / 16 <= 2 row tiles
+                const int nt0 = (uu - mt * groups) * op.ng;
+                switch (op.ng) {
+                    case 1: mma_tiles<WSMEM, 1>(op, W, act, rs, mt, nt0, row_action, row_active, A, z, dbg); break;
+                    case 2: mma_tiles<WSMEM, 2>(op, W, act, rs, mt, nt0, row_action, row_active, A, z, dbg); break;
+                    case 3: mma_tiles<WSMEM, 3>(op, W, act, rs, mt, nt0, row_action, row_active, A, z, dbg); break;
+                    default: mma_tiles<WSMEM, 4>(op, W, act, rs, mt, nt0, row_action, row_active, A, z, dbg); break;
+                }
+            }
+        } else if (!WSMEM) {
             // weights in global memory: 4 x 4 register tiles
             int total = 0;
             for (int o = 0; o < st.n_ops; ++o) total += (TM / 4) * (st.ops[o].Npad >> 2);
@@ -323,8 +503,11 @@ __device__ void run_schedule(const Schedule& sc, const float* __restrict__ W, fl
                 }
                 float scale = __fsub_rn(mx, mn);
                 if (scale < 1e-5f) scale = __fadd_rn(scale, 1e-5f);
+                // one IEEE reciprocal per row instead of one division per element (<= 1 ulp from torch's
+                // (x - min) / scale, far inside the 1e-5 network tolerance)
+                const float inv = __frcp_rn(scale);
                 float* y = act + row * rs + st.r_out;
-                for (int i = j; i < st.r_n; i += GW) y[i] = __fdiv_rn(__fsub_rn(x[i], mn), scale);
+                for (int i = j; i < st.r_n; i += GW) y[i] = __fmul_rn(__fsub_rn(x[i], mn), inv);
             }
         }
         if (dbg && tid == 0) d1 = clock64();
@@ -698,6 +881,9 @@ __global__ void __launch_bounds__(TM * GW * XW) search_kernel(const __grid_const
                         vs = blk->vsum[j];
                         rw = blk->reward[j];
                         prior = (node == 0) ? root_prior : (double)blk->prior[j];
+                        // pull every expanded child's block towards L1 while this level's float64 scores
+                        // are computed: the next level's five loads then hit instead of paying L2 latency
+                        if (ch >= 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(blocks + ch));
                     }
                     double score = -CUDART_INF;
                     if (on) score = ucb_score<VARIANT>(pb[Np], sq[Np], vis, vs, prior, rw, discount, mm);
@@ -905,21 +1091,22 @@ __global__ void __launch_bounds__(TM * GW * XW) search_kernel(const __grid_const
                 int cur = node, cs = slot;
                 if (VARIANT == 0) {
                     // self_play.py:485-490
+                    // The 8 lanes of the group execute this loop in lock step (identical control flow) and ALL
+                    // of them store the identical updated statistics: no lane ever needs another lane's view
+                    // of memory inside the loop, so no warp-level sync per level is required.
                     while (true) {
                         Block* bk = blocks + cur;
+                        const int ps = bk->aux, pc = bk->parent;  // issued with the statistics loads
                         const double vs = __dadd_rn(bk->vsum[cs], v);
                         const int vis = bk->visit[cs] + 1;
                         const double rw = (double)bk->reward[cs];
-                        __syncwarp(gmask);
-                        if (j == 0) {
-                            bk->vsum[cs] = vs;
-                            bk->visit[cs] = vis;
-                        }
+                        bk->vsum[cs] = vs;
+                        bk->visit[cs] = vis;
                         mm.update(__dadd_rn(rw, __dmul_rn(discount, __ddiv_rn(vs, (double)vis))));
                         v = __dadd_rn(rw, __dmul_rn(discount, v));
                         if (cur == 0) break;
-                        cs = bk->aux & 0xFF;
-                        cur = bk->parent;
+                        cs = ps & 0xFF;
+                        cur = pc;
                     }
                     root_vsum = __dadd_rn(root_vsum, v);
                     root_visit += 1;

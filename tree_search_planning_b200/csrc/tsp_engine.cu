@@ -22,7 +22,7 @@ thread_local std::string g_create_error;
 struct HostLayer {
     int out_dim = 0, in_dim = 0;
     std::vector<float> W, b;
-    int w_off = -1, b_off = -1, npad = 0;  // arena placement
+    int w_off = -1, b_off = -1, npad = 0, wld = 0;  // arena placement: Wt[in_dim][wld], bias[npad]
 };
 
 struct DevBuf {
@@ -45,7 +45,7 @@ struct HSched {
     int in_buf = -1, hidden = -1, pl = -1, vl = -1, rl = -1, tl = -1, tp = -1;
     int in_dim = 0;
     int new_buf(int w, int ready_stage) {
-        width.push_back((w + 3) & ~3);
+        width.push_back((w + 7) & ~7);  // layers are written in 8-column mma tiles
         ready.push_back(ready_stage);
         return (int)width.size() - 1;
     }
@@ -74,6 +74,7 @@ struct tsp_engine {
     bool no_wsmem = false;
     int xw_override = 0;
     int ct_override = 0;
+    int ng_override = 0;
 
     // device memory
     DevBuf arena;  // packed weights
@@ -245,6 +246,7 @@ int lower(tsp_engine* e, const HSched& hs, Schedule& sc, bool keep_input = false
             d.b_off = L.b_off;
             d.N = (short)L.out_dim;
             d.Npad = (short)L.npad;
+            d.wld = (short)L.wld;
             d.in_off = o16(op.in_buf);
             d.out_off = o16(op.out_buf);
             d.act = (unsigned char)op.act;
@@ -341,7 +343,6 @@ void set_chunks(Schedule& sc, int slots, int forced) {
         Stage& st = sc.st[s];
         int best = 4;
         for (int ct : {16, 8, 4}) {
-            bool ok = true;
             int units = 0;
             for (int o = 0; o < st.n_ops; ++o) {
                 int c = ct;
@@ -352,13 +353,36 @@ void set_chunks(Schedule& sc, int slots, int forced) {
                 best = ct;
                 break;
             }
-            (void)ok;
         }
         if (forced == 4 || forced == 8 || forced == 16) best = forced;
         for (int o = 0; o < st.n_ops; ++o) {
             int c = best;
             while (st.ops[o].Npad % c) c >>= 1;
             st.ops[o].ct = (unsigned char)c;
+        }
+    }
+}
+
+// Tensor-core path: 8-column tiles per warp unit. The smallest group size (most warps busy, shortest
+// serial stream per warp) for which all units of a stage fit in one pass over the CTA's warps.
+void set_tile_groups(Schedule& sc, int TM, int warps, int forced) {
+    for (int s = 0; s < sc.n_stages; ++s) {
+        Stage& st = sc.st[s];
+        int best = 4;
+        for (int ng = 1; ng <= 4; ++ng) {
+            int units = 0;
+            for (int o = 0; o < st.n_ops; ++o) units += (TM / 16) * (((st.ops[o].Npad >> 3) + ng - 1) / ng);
+            if (units <= warps) {
+                best = ng;
+                break;
+            }
+        }
+        if (forced >= 1 && forced <= 4) best = forced;
+        for (int o = 0; o < st.n_ops; ++o) {
+            LayerOp& op = st.ops[o];
+            op.ng = (unsigned char)best;
+            op.groups = (short)(((op.Npad >> 3) + best - 1) / best);
+            op.units = (short)((TM / 16) * op.groups);
         }
     }
 }
@@ -379,6 +403,7 @@ template <int NC, int TM>
 int launch_net(tsp_engine* e, const NetParams& p_in) {
     NetParams p = p_in;
     set_chunks(p.sched, GW, e->ct_override);
+    set_tile_groups(p.sched, TM, TM * GW / 32, e->ng_override);
     const size_t smem = net_smem(p.sched, TM);
     int rc = set_smem(e, net_kernel<NC, TM>, smem);
     if (rc) return rc;
@@ -401,6 +426,8 @@ int launch_search_x(tsp_engine* e, const SearchParams& p_in) {
     SearchParams p = p_in;
     set_chunks(p.sched_a, GW * XW, e->ct_override);
     set_chunks(p.sched_b, GW * XW, e->ct_override);
+    set_tile_groups(p.sched_a, TM, TM * GW * XW / 32, e->ng_override);
+    set_tile_groups(p.sched_b, TM, TM * GW * XW / 32, e->ng_override);
     const size_t smem = search_smem(p.sched_a, TM, p.S, WSMEM ? (size_t)p.w_smem_floats : 0);
     int rc = set_smem(e, search_kernel<VARIANT, NC, TM, WSMEM, XW>, smem);
     if (rc) return rc;
@@ -570,6 +597,7 @@ int tsp_create(const tsp_config* cfg, tsp_handle* out) {
     if (const char* t = getenv("TSP_THREAD_MULT")) e->xw_override = atoi(t);
     if (const char* t = getenv("TSP_PHASE_TIMING")) e->phase_timing = atoi(t) != 0;
     if (const char* t = getenv("TSP_COLS_PER_THREAD")) e->ct_override = atoi(t);
+    if (const char* t = getenv("TSP_TILES_PER_WARP")) e->ng_override = atoi(t);
     auto bail = [&](int rc) {
         g_create_error = e->err;
         tsp_destroy(e);
@@ -658,8 +686,10 @@ int tsp_set_layer(tsp_handle e, int32_t mlp, int32_t layer, const float* W, cons
 int tsp_finalize_weights(tsp_handle e) {
     if (!e) return TSP_EINVAL;
     CK(e, cudaSetDevice(e->device));
-    // pack: per layer Wt[in_dim][npad] (transposed so that consecutive threads read consecutive
-    // output columns), zero padded to a multiple of 4 columns, followed by the bias [npad]
+    // pack: per layer Wt[in_dim][wld] (transposed: row k holds the weights of input k for all outputs),
+    // zero padded to npad = a multiple of 8 columns (one mma n-tile), followed by the bias [npad].
+    // The leading dimension wld is == 8 (mod 32) words so that the B fragments of mma.m16n8k8
+    // (rows k0 + lane % 4, columns n0 + lane / 4) hit 32 distinct shared-memory banks.
     int64_t total = 0;
     const int order[TSP_NUM_MLP] = {TSP_MLP_DYNAMICS, TSP_MLP_REWARD, TSP_MLP_TERMINAL, TSP_MLP_POLICY, TSP_MLP_VALUE,
                                     TSP_MLP_PRIOR, TSP_MLP_REPRESENTATION};
@@ -670,9 +700,11 @@ int tsp_finalize_weights(tsp_handle e) {
             HostLayer& L = v[l];
             if (L.out_dim == 0) return fail(e, TSP_ESTATE, "a Linear layer is missing (set every layer index)");
             if (l > 0 && v[l - 1].out_dim != L.in_dim) return fail(e, TSP_EINVAL, "layer shapes do not chain");
-            L.npad = (L.out_dim + 3) & ~3;
+            L.npad = (L.out_dim + 7) & ~7;
+            L.wld = L.npad;
+            while (L.wld % 32 != 8 && L.wld % 32 != 24) L.wld += 8;
             L.w_off = (int)total;
-            total += (int64_t)L.in_dim * L.npad;
+            total += (int64_t)L.in_dim * L.wld;
             L.b_off = (int)total;
             total += L.npad;
         }
@@ -682,7 +714,7 @@ int tsp_finalize_weights(tsp_handle e) {
     for (auto& v : e->mlp)
         for (HostLayer& L : v) {
             for (int o = 0; o < L.out_dim; ++o)
-                for (int i = 0; i < L.in_dim; ++i) host[(size_t)L.w_off + (size_t)i * L.npad + o] = L.W[(size_t)o * L.in_dim + i];
+                for (int i = 0; i < L.in_dim; ++i) host[(size_t)L.w_off + (size_t)i * L.wld + o] = L.W[(size_t)o * L.in_dim + i];
             for (int o = 0; o < L.out_dim; ++o) host[(size_t)L.b_off + o] = L.b[o];
         }
     int rc = ensure(e, e->arena, (size_t)total * sizeof(float));

@@ -326,8 +326,10 @@ class Engine:
         v = list(buf)
         n = max(1, v[4])
         stages = [(round(v[8 + 2 * s] / n), round(v[9 + 2 * s] / n)) for s in range(14) if v[8 + 2 * s] or v[9 + 2 * s]]
+        nt = max(1, v[43])
         return dict(select=v[0] / n, wait=v[1] / n, mlp=v[2] / n, backup=v[3] / n, samples=v[4],
-                    stages_work_wait=stages)
+                    stages_work_wait=stages, tile_init_kloop_store=(round(v[40] / nt), round(v[41] / nt), round(v[42] / nt)),
+                    tiles_per_iter=v[43] / n)
 
     def reset_timing(self):
         self._check(self.lib.tsp_reset_timing(self.handle))
