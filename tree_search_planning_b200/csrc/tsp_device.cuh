@@ -303,10 +303,11 @@ __device__ __forceinline__ void mma_tiles(const LayerOp& op, const float* __rest
     const float* x0 = act + r0 * rs + op.in_off;
     const float* x1 = act + r1 * rs + op.in_off;
     const float* wb = W + op.w_off + nt0 * 8;  // Wt[k][8 nt0 + n] at wb[k * wld + n]
-    float dm[NT][4], dc[NT][4];
+    float dm[NT][4], dc[NT][4], de[NT][4];  // hi*hi, lo*hi, hi*lo: three independent mma chains per tile
 #pragma unroll
     for (int i = 0; i < NT; ++i) {
         dc[i][0] = dc[i][1] = dc[i][2] = dc[i][3] = 0.f;
+        de[i][0] = de[i][1] = de[i][2] = de[i][3] = 0.f;
         dm[i][0] = dm[i][1] = dm[i][2] = dm[i][3] = 0.f;
         if (nt0 + i < ntiles) {  // accumulator init: bias (+ the one-hot rows of the action / future)
             const float* bp = W + op.b_off + (nt0 + i) * 8 + 2 * t;
@@ -356,7 +357,7 @@ __device__ __forceinline__ void mma_tiles(const LayerOp& op, const float* __rest
                 bl[1] = __float_as_uint(bf[i][1] - __uint_as_float(bh[1]));
                 mma_tf32(dm[i], ah, bh);
                 mma_tf32(dc[i], al, bh);
-                mma_tf32(dc[i], ah, bl);
+                mma_tf32(de[i], ah, bl);
             }
         }
     }
@@ -382,7 +383,7 @@ __device__ __forceinline__ void mma_tiles(const LayerOp& op, const float* __rest
                 bl[1] = __float_as_uint(b1f - __uint_as_float(bh[1]));
                 mma_tf32(dm[i], ah, bh);
                 mma_tf32(dc[i], al, bh);
-                mma_tf32(dc[i], ah, bl);
+                mma_tf32(de[i], ah, bl);
             }
         }
     }
@@ -391,7 +392,8 @@ __device__ __forceinline__ void mma_tiles(const LayerOp& op, const float* __rest
 #pragma unroll
     for (int i = 0; i < NT; ++i) {
         if (nt0 + i < ntiles) {
-            float d0 = dm[i][0] + dc[i][0], d1 = dm[i][1] + dc[i][1], d2 = dm[i][2] + dc[i][2], d3 = dm[i][3] + dc[i][3];
+            float d0 = dm[i][0] + (dc[i][0] + de[i][0]), d1 = dm[i][1] + (dc[i][1] + de[i][1]);
+            float d2 = dm[i][2] + (dc[i][2] + de[i][2]), d3 = dm[i][3] + (dc[i][3] + de[i][3]);
             if (op.act) {
                 d0 = elu(d0); d1 = elu(d1); d2 = elu(d2); d3 = elu(d3);
             }
