@@ -296,7 +296,6 @@ __device__ __forceinline__ void mma_tiles(const LayerOp& op, const float* __rest
     const int lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;
     const int r0 = mt * 16 + g, r1 = r0 + 8;
-    const int ntiles = op.Npad >> 3;
     const int K = op.K, wld = op.wld;
     const bool on0 = row_active[r0] != 0, on1 = row_active[r1] != 0;
     const int ra0 = row_action[r0], ra1 = row_action[r1];
@@ -309,7 +308,7 @@ __device__ __forceinline__ void mma_tiles(const LayerOp& op, const float* __rest
         dc[i][0] = dc[i][1] = dc[i][2] = dc[i][3] = 0.f;
         de[i][0] = de[i][1] = de[i][2] = de[i][3] = 0.f;
         dm[i][0] = dm[i][1] = dm[i][2] = dm[i][3] = 0.f;
-        if (nt0 + i < ntiles) {  // accumulator init: bias (+ the one-hot rows of the action / future)
+        {  // accumulator init: bias (+ the one-hot rows of the action / future)
             const float* bp = W + op.b_off + (nt0 + i) * 8 + 2 * t;
             const float b0 = ldw1<WSMEM>(bp), b1 = ldw1<WSMEM>(bp + 1);
             dm[i][0] = b0; dm[i][1] = b1; dm[i][2] = b0; dm[i][3] = b1;
@@ -335,11 +334,8 @@ __device__ __forceinline__ void mma_tiles(const LayerOp& op, const float* __rest
         float bf[NT][2];
 #pragma unroll
         for (int i = 0; i < NT; ++i) {
-            bf[i][0] = bf[i][1] = 0.f;
-            if (nt0 + i < ntiles) {
-                bf[i][0] = ldw1<WSMEM>(wk + i * 8);
-                bf[i][1] = ldw1<WSMEM>(wk + i * 8 + 4 * wld);
-            }
+            bf[i][0] = ldw1<WSMEM>(wk + i * 8);
+            bf[i][1] = ldw1<WSMEM>(wk + i * 8 + 4 * wld);
         }
         wk += 8 * wld;
         unsigned ah[4], al[4];
@@ -350,7 +346,7 @@ __device__ __forceinline__ void mma_tiles(const LayerOp& op, const float* __rest
         al[3] = __float_as_uint(a3f - __uint_as_float(ah[3]));
 #pragma unroll
         for (int i = 0; i < NT; ++i) {
-            if (nt0 + i < ntiles) {
+            {
                 unsigned bh[2], bl[2];
                 bh[0] = tf32_hi(bf[i][0]); bh[1] = tf32_hi(bf[i][1]);
                 bl[0] = __float_as_uint(bf[i][0] - __uint_as_float(bh[0]));
@@ -374,7 +370,7 @@ __device__ __forceinline__ void mma_tiles(const LayerOp& op, const float* __rest
         al[3] = __float_as_uint(a3f - __uint_as_float(ah[3]));
 #pragma unroll
         for (int i = 0; i < NT; ++i) {
-            if (nt0 + i < ntiles) {
+            {
                 const float b0f = lo_ok ? ldw1<WSMEM>(wk + i * 8) : 0.f;
                 const float b1f = hi_ok ? ldw1<WSMEM>(wk + i * 8 + 4 * wld) : 0.f;
                 unsigned bh[2], bl[2];
@@ -391,7 +387,7 @@ __device__ __forceinline__ void mma_tiles(const LayerOp& op, const float* __rest
     // C fragment: d0,d1 = C[g][2t, 2t+1], d2,d3 = C[g+8][2t, 2t+1]
 #pragma unroll
     for (int i = 0; i < NT; ++i) {
-        if (nt0 + i < ntiles) {
+        {
             float d0 = dm[i][0] + (dc[i][0] + de[i][0]), d1 = dm[i][1] + (dc[i][1] + de[i][1]);
             float d2 = dm[i][2] + (dc[i][2] + de[i][2]), d3 = dm[i][3] + (dc[i][3] + de[i][3]);
             if (op.act) {
@@ -408,6 +404,19 @@ __device__ __forceinline__ void mma_tiles(const LayerOp& op, const float* __rest
         atomicAdd(dbg + 41, (unsigned long long)(q2 - q1));  // k loop
         atomicAdd(dbg + 42, (unsigned long long)(q3 - q2));  // ELU + store
         atomicAdd(dbg + 43, 1ull);
+    }
+}
+
+template <bool WSMEM>
+__device__ __forceinline__ void mma_tiles_n(int n, const LayerOp& op, const float* __restrict__ W, float* __restrict__ act,
+                                            int rs, int mt, int nt0, const int* __restrict__ row_action,
+                                            const unsigned char* __restrict__ row_active, int A, int z,
+                                            unsigned long long* dbg = nullptr) {
+    switch (n) {
+        case 1: mma_tiles<WSMEM, 1>(op, W, act, rs, mt, nt0, row_action, row_active, A, z, dbg); break;
+        case 2: mma_tiles<WSMEM, 2>(op, W, act, rs, mt, nt0, row_action, row_active, A, z, dbg); break;
+        case 3: mma_tiles<WSMEM, 3>(op, W, act, rs, mt, nt0, row_action, row_active, A, z, dbg); break;
+        default: mma_tiles<WSMEM, 4>(op, W, act, rs, mt, nt0, row_action, row_active, A, z, dbg); break;
     }
 }
 
@@ -446,12 +455,8 @@ __device__ void run_schedule(const Schedule& sc, const float* __restrict__ W, fl
                 const int groups = op.groups;
                 const int mt = (TM == 16 || uu < groups) ? 0 : 1;  // TM / 16 <= 2 row tiles
                 const int nt0 = (uu - mt * groups) * op.ng;
-                switch (op.ng) {
-                    case 1: mma_tiles<WSMEM, 1>(op, W, act, rs, mt, nt0, row_action, row_active, A, z, dbg); break;
-                    case 2: mma_tiles<WSMEM, 2>(op, W, act, rs, mt, nt0, row_action, row_active, A, z, dbg); break;
-                    case 3: mma_tiles<WSMEM, 3>(op, W, act, rs, mt, nt0, row_action, row_active, A, z, dbg); break;
-                    default: mma_tiles<WSMEM, 4>(op, W, act, rs, mt, nt0, row_action, row_active, A, z, dbg); break;
-                }
+                const int rem = (op.Npad >> 3) - nt0;
+                mma_tiles_n<WSMEM>(rem < op.ng ? rem : op.ng, op, W, act, rs, mt, nt0, row_action, row_active, A, z, dbg);
             }
         } else if (!WSMEM) {
             // weights in global memory: 4 x 4 register tiles
@@ -519,6 +524,60 @@ __device__ void run_schedule(const Schedule& sc, const float* __restrict__ W, fl
             atomicAdd(dbg + 8 + 2 * s, (unsigned long long)(d1 - d0));      // thread 0's own work in stage s
             atomicAdd(dbg + 9 + 2 * s, (unsigned long long)(d2 - d1));      // its wait at the stage barrier
         }
+    }
+}
+
+// Warp-resident MLP: ONE warp evaluates every stage of the schedule for the 16 rows (trees) of row tile
+// `mt`. The A fragments of a layer are that same warp's C fragments of the previous layer (round-tripped
+// through its rows of the activation strip), so stages are separated by __syncwarp() only -- no CTA
+// barrier, no tile decode across warps -- and with 4 column tiles in flight (12 independent mma chains)
+// the warp issues HMMAs back to back. Measured against the CTA-wide stage-by-stage version in DESIGN.md.
+template <bool WSMEM>
+__device__ void run_schedule_warp(const Schedule& sc, const float* __restrict__ W, float* __restrict__ act,
+                                  const int* __restrict__ row_action, const unsigned char* __restrict__ row_active,
+                                  int A, int z, int mt, unsigned long long* dbg = nullptr) {
+    const int lane = threadIdx.x & 31;
+    const int rs = sc.row_stride;
+    for (int s = 0; s < sc.n_stages; ++s) {
+        const Stage& st = sc.st[s];
+        long long d0 = 0;
+        if (dbg && threadIdx.x == 0) d0 = clock64();
+        const int nops = st.n_ops;
+        for (int o = 0; o < nops; ++o) {
+            const LayerOp& op = st.ops[o];
+            const int ntiles = op.Npad >> 3;
+            for (int nt0 = 0; nt0 < ntiles; nt0 += 4)
+                mma_tiles_n<WSMEM>(ntiles - nt0, op, W, act, rs, mt, nt0, row_action, row_active, A, z, nullptr);
+        }
+        if (st.row_op == 1) {  // min-max scaling of the 16 rows of this tile, 8 lanes per row, 4 rows per pass
+            const int j = lane & 7;
+            const unsigned gmask = 0xFFu << (lane & 24);
+#pragma unroll 1
+            for (int r = 0; r < 16; r += 4) {
+                const int row = mt * 16 + r + (lane >> 3);
+                if (row_active[row]) {
+                    const float* x = act + row * rs + st.r_in;
+                    float mn = CUDART_INF_F, mx = -CUDART_INF_F;
+                    for (int i = j; i < st.r_n; i += GW) {
+                        const float v = x[i];
+                        mn = fminf(mn, v);
+                        mx = fmaxf(mx, v);
+                    }
+#pragma unroll
+                    for (int d = 1; d < GW; d <<= 1) {
+                        mn = fminf(mn, __shfl_xor_sync(gmask, mn, d));
+                        mx = fmaxf(mx, __shfl_xor_sync(gmask, mx, d));
+                    }
+                    float scale = __fsub_rn(mx, mn);
+                    if (scale < 1e-5f) scale = __fadd_rn(scale, 1e-5f);
+                    const float inv = __frcp_rn(scale);
+                    float* y = act + row * rs + st.r_out;
+                    for (int i = j; i < st.r_n; i += GW) y[i] = __fmul_rn(__fsub_rn(x[i], mn), inv);
+                }
+            }
+        }
+        __syncwarp();
+        if (dbg && threadIdx.x == 0) atomicAdd(dbg + 8 + 2 * s, (unsigned long long)(clock64() - d0));
     }
 }
 
@@ -643,7 +702,7 @@ struct NetParams {
 
 struct SearchParams {
     int B, S, A, H, nf, support, mask_absorbing, uniform_policy;
-    int blocks_per_tree, hidden_per_tree, max_rec, T, K, max_iters, w_smem_floats, pb_stride;
+    int blocks_per_tree, hidden_per_tree, max_rec, T, K, max_iters, w_smem_floats, pb_stride, warp_mlp;
     double discount;
     const double* pb_table;  // [2][S + 2]: log((N + base + 1) / base) + init, then sqrt(N); host libm (bit-equal to math.log / math.sqrt)
     void* blocks; float* hidden_pool; TreeHeader* hdr; const double* rootprior; const int* rootact;
@@ -960,7 +1019,13 @@ __global__ void __launch_bounds__(TM * GW * XW) search_kernel(const __grid_const
             __syncthreads();
             if (p.phase_cycles && tid == 0) tc2 = clock64();
             if (VARIANT == 0) {
-                run_schedule<TM, THREADS, WSMEM>(sched_a, Wp, act, row_action, row_active, A, 0, p.phase_cycles);
+                if (p.warp_mlp) {  // developer alternative: one warp per 16-row tile walks all stages
+                    if ((tid >> 5) < TM / 16)
+                        run_schedule_warp<WSMEM>(sched_a, Wp, act, row_action, row_active, A, 0, tid >> 5, p.phase_cycles);
+                    __syncthreads();
+                } else {
+                    run_schedule<TM, THREADS, WSMEM>(sched_a, Wp, act, row_action, row_active, A, 0, p.phase_cycles);
+                }
                 if (p.phase_cycles && tid == 0) tc3 = clock64();
                 if (active) {
                     const float* r = act + row * rs;

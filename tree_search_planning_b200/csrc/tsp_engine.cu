@@ -75,6 +75,7 @@ struct tsp_engine {
     int xw_override = 0;
     int ct_override = 0;
     int ng_override = 0;
+    bool warp_mlp = false;
 
     // device memory
     DevBuf arena;  // packed weights
@@ -480,6 +481,7 @@ int launch_search_any(tsp_engine* e, const SearchParams& p_in) {
     // helper warps for the MLP units pay off while there is at most one CTA per SM (they double the
     // registers of a CTA); measured: 4,096 roots 1.13 -> 0.99 ms, 65,536 roots slower
     int xw = ((p.B + TM - 1) / TM <= e->sm_count && TM == 32) ? 2 : 1;
+    p.warp_mlp = e->warp_mlp ? 1 : 0;
     if (e->xw_override == 1 || e->xw_override == 2) xw = e->xw_override;
     if (e->nc == 5) {
         if (v == 0) return launch_search_tm<0, 5>(e, p, TM, xw);
@@ -600,6 +602,7 @@ int tsp_create(const tsp_config* cfg, tsp_handle* out) {
     if (const char* t = getenv("TSP_PHASE_TIMING")) e->phase_timing = atoi(t) != 0;
     if (const char* t = getenv("TSP_COLS_PER_THREAD")) e->ct_override = atoi(t);
     if (const char* t = getenv("TSP_TILES_PER_WARP")) e->ng_override = atoi(t);
+    if (const char* t = getenv("TSP_WARP_MLP")) e->warp_mlp = atoi(t) != 0;
     auto bail = [&](int rc) {
         g_create_error = e->err;
         tsp_destroy(e);
