@@ -2,6 +2,7 @@
 // construction, pool management, kernel launches and the extern "C" ABI of include/tsp.h.
 // There is no CPU fallback in this file: every entry point either runs CUDA kernels or fails.
 #include "tsp_device.cuh"
+#include "tsp_fast.cuh"
 #include "../../include/tsp.h"
 
 #include <algorithm>
@@ -23,6 +24,8 @@ struct HostLayer {
     int out_dim = 0, in_dim = 0;
     std::vector<float> W, b;
     int w_off = -1, b_off = -1, npad = 0, wld = 0;  // arena placement: Wt[in_dim][wld], bias[npad]
+    // fragment-ordered arena of the fast search kernel (tsp_fast.cuh): tiles, bias[npad], one-hot rows
+    int f_off = -1, fb_off = -1, fe_off = -1, f_dense = 0;
 };
 
 struct DevBuf {
@@ -76,11 +79,17 @@ struct tsp_engine {
     int ct_override = 0;
     int ng_override = 0;
     bool warp_mlp = false;
+    bool no_fast = false;
+    int fast_groups = 0;  // TSP_FAST_GROUPS override (1, 2 or 4 groups of 16 trees per CTA)
 
     // device memory
     DevBuf arena;  // packed weights
     int64_t arena_floats = 0;
     int64_t search_floats = 0;  // leading part of the arena used by the search kernel (everything but the representation net)
+    DevBuf farena, fsched_dev;  // fast search kernel: fragment-ordered weights, FastSched
+    int64_t farena_floats = 0;
+    FastSched fsched{};
+    bool has_fast = false;
     DevBuf blocks, hidden, hdr, rootprior, rootact, pbtable, phase;
     bool phase_timing = false;
     int blocks_per_tree = 0, hidden_per_tree = 0, max_iters = 0;
@@ -171,12 +180,14 @@ int add_normalise(HSched& hs, int in_buf, int n) {
     return out;
 }
 
-int lower(tsp_engine* e, const HSched& hs, Schedule& sc, bool keep_input = false) {
+// Liveness-based first-fit placement of the activation buffers inside a row strip: two buffers may share
+// space iff their [first write, last read] stage ranges are disjoint. Returns the strip width in floats.
+int strip_offsets(const HSched& hs, const std::vector<int>& width, bool keep_input, std::vector<int>& off) {
     const int nb = (int)hs.width.size();
     const int ns = (int)hs.stages.size();
-    if (ns > MAX_STAGES) return fail(e, TSP_EINVAL, "network too deep: %d stages > %d", ns, MAX_STAGES);
     const int INF = 1 << 20;
-    std::vector<int> def(nb, INF), last(nb, -1), off(nb, -1);
+    std::vector<int> def(nb, INF), last(nb, -1);
+    off.assign(nb, -1);
     def[hs.in_buf] = -1;
     for (int s = 0; s < ns; ++s) {
         for (const HOp& op : hs.stages[s].ops) {
@@ -192,7 +203,6 @@ int lower(tsp_engine* e, const HSched& hs, Schedule& sc, bool keep_input = false
         if (o >= 0) last[o] = INF;
     last[hs.in_buf] = std::max(last[hs.in_buf], 0);
     if (keep_input) last[hs.in_buf] = INF;  // the schedule is evaluated once per future z on the same input
-    // first-fit with liveness: two buffers may share space iff their [def, last] ranges are disjoint
     std::vector<int> order(nb);
     for (int i = 0; i < nb; ++i) order[i] = i;
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return def[a] < def[b]; });
@@ -206,15 +216,23 @@ int lower(tsp_engine* e, const HSched& hs, Schedule& sc, bool keep_input = false
             for (int j = 0; j < idx; ++j) {
                 const int o = order[j];
                 const bool live_overlap = !(last[o] < def[b] || last[b] < def[o]);
-                if (live_overlap && pos < off[o] + hs.width[o] && off[o] < pos + hs.width[b]) {
-                    pos = off[o] + hs.width[o];
+                if (live_overlap && pos < off[o] + width[o] && off[o] < pos + width[b]) {
+                    pos = off[o] + width[o];
                     moved = true;
                 }
             }
         }
         off[b] = pos;
-        total = std::max(total, pos + hs.width[b]);
+        total = std::max(total, pos + width[b]);
     }
+    return total;
+}
+
+int lower(tsp_engine* e, const HSched& hs, Schedule& sc, bool keep_input = false) {
+    const int ns = (int)hs.stages.size();
+    if (ns > MAX_STAGES) return fail(e, TSP_EINVAL, "network too deep: %d stages > %d", ns, MAX_STAGES);
+    std::vector<int> off;
+    int total = strip_offsets(hs, hs.width, keep_input, off);
     total += ((4 - total % 32) + 32) % 32;  // row stride == 4 (mod 32)
     if (total > 32000) return fail(e, TSP_EINVAL, "activation strip too wide (%d floats)", total);
     memset(&sc, 0, sizeof(sc));
@@ -261,6 +279,153 @@ int lower(tsp_engine* e, const HSched& hs, Schedule& sc, bool keep_input = false
     return TSP_OK;
 }
 
+// Fast search kernel (tsp_fast.cuh): lower a schedule to per-stage, per-warp lists of 16 x 8 output tiles.
+// Returns TSP_OK with e->has_fast == false when the network does not fit the fast path's constraints
+// (the generic search kernel then runs it).
+int lower_fast(tsp_engine* e, const HSched& hs) {
+    e->has_fast = false;
+    const int ns = (int)hs.stages.size();
+    if (ns > FAST_MAX_STAGES) return TSP_OK;
+    std::vector<int> width(hs.width.size());
+    for (size_t i = 0; i < width.size(); ++i) width[i] = (hs.width[i] + 15) & ~15;  // A operands are read in chunks of 16
+    std::vector<int> off;
+    int total = strip_offsets(hs, width, false, off);
+    total += ((16 - total % 32) + 32) % 32;  // row stride == 16 (mod 32): conflict-free LDS.128 of rows g, g + 1
+    if (off[hs.in_buf] != 0 || total > 8000) return TSP_OK;
+    FastSched& fs = e->fsched;
+    memset(&fs, 0, sizeof(fs));
+    fs.n_stages = ns;
+    fs.row_stride = total;
+    auto o16 = [&](int b) { return (short)(b >= 0 ? off[b] : -1); };
+    fs.off_hidden = o16(hs.hidden);
+    fs.off_pl = o16(hs.pl);
+    fs.off_vl = o16(hs.vl);
+    fs.off_rl = o16(hs.rl);
+    fs.off_tl = o16(hs.tl);
+    int nt = 0;
+    for (int s = 0; s < ns; ++s) {
+        const HStage& h = hs.stages[s];
+        FStage& st = fs.st[s];
+        st.row_op = (short)h.rop;
+        if (h.rop) {
+            st.r_in = o16(h.r_in);
+            st.r_out = o16(h.r_out);
+            st.r_n = (short)h.r_n;
+        }
+        // tiles of the stage, ops reading the same buffer adjacent (their tiles can share A fragments)
+        std::vector<HOp> ops = h.ops;
+        std::stable_sort(ops.begin(), ops.end(), [](const HOp& a, const HOp& b) { return a.in_buf < b.in_buf; });
+        std::vector<FTile> tiles;
+        for (const HOp& op : ops) {
+            const HostLayer& L = e->mlp[op.mlp][op.layer];
+            if (L.f_off < 0 || L.f_dense % 16) return TSP_OK;
+            const int kc = L.f_dense / 16;
+            if (kc > 255) return TSP_OK;
+            for (int jt = 0; jt < L.npad / 8; ++jt) {
+                FTile t;
+                memset(&t, 0, sizeof(t));
+                t.wf_off = L.f_off + jt * kc * 128;
+                t.b_off = L.fb_off + 8 * jt;
+                t.e_off = op.extra ? L.fe_off + 8 * jt : -1;
+                t.e_ld = (short)L.npad;
+                t.in_off = o16(op.in_buf);
+                t.out_off = (short)(off[op.out_buf] + 8 * jt);
+                t.kc = (unsigned char)kc;
+                t.act = (unsigned char)op.act;
+                tiles.push_back(t);
+            }
+        }
+        if (nt + (int)tiles.size() > FAST_MAX_TILES) return TSP_OK;
+        // contiguous partition over the 4 warps of a group, balanced by k-chunks
+        int cost = 0;
+        for (const FTile& t : tiles) cost += t.kc;
+        int acc = 0, w = 0;
+        st.first[0] = (short)nt;
+        for (size_t i = 0; i < tiles.size(); ++i) {
+            // close warp w's range before tile i when its share is reached
+            while (w < GWARPS - 1 && acc * GWARPS >= (w + 1) * cost) st.first[++w] = (short)(nt + i);
+            acc += tiles[i].kc;
+        }
+        while (w < GWARPS) st.first[++w] = (short)(nt + tiles.size());
+        for (size_t i = 0; i < tiles.size(); ++i) fs.tiles[nt + i] = tiles[i];
+        // batches: consecutive tiles of one warp with the same input and depth, at most FAST_NT
+        for (int ww = 0; ww < GWARPS; ++ww) {
+            int i = st.first[ww];
+            while (i < st.first[ww + 1]) {
+                int n = 1;
+                while (n < FAST_NT && i + n < st.first[ww + 1] && fs.tiles[i + n].in_off == fs.tiles[i].in_off &&
+                       fs.tiles[i + n].kc == fs.tiles[i].kc)
+                    ++n;
+                fs.tiles[i].batch = (unsigned char)n;
+                i += n;
+            }
+        }
+        nt += (int)tiles.size();
+    }
+    fs.n_tiles = nt;
+    fs.w_floats = (int)e->farena_floats;
+    int rc = ensure(e, e->fsched_dev, sizeof(FastSched));
+    if (rc) return rc;
+    CK(e, cudaMemcpyAsync(e->fsched_dev.p, &fs, sizeof(FastSched), cudaMemcpyHostToDevice, e->stream));
+    CK(e, cudaStreamSynchronize(e->stream));
+    e->has_fast = true;
+    return TSP_OK;
+}
+
+// Pack the search MLPs (everything but the representation network) in fragment order for tsp_fast.cuh.
+int pack_fast_arena(tsp_engine* e) {
+    const tsp_config& c = e->cfg;
+    e->farena_floats = 0;
+    if (c.variant != TSP_VARIANT_MUZERO) return TSP_OK;
+    int64_t total = 0;
+    for (int m = 0; m < TSP_NUM_MLP; ++m) {
+        if (m == TSP_MLP_REPRESENTATION || m == TSP_MLP_PRIOR) continue;
+        if (m == TSP_MLP_TERMINAL && !c.mask_absorbing_states) continue;
+        auto& v = e->mlp[m];
+        for (size_t l = 0; l < v.size(); ++l) {
+            HostLayer& L = v[l];
+            const int n_extra = (m == TSP_MLP_DYNAMICS && l == 0) ? c.num_actions : 0;
+            L.f_dense = L.in_dim - n_extra;
+            L.f_off = -1;
+            if (L.f_dense <= 0 || L.f_dense % 16) continue;
+            L.f_off = (int)total;
+            total += (int64_t)(L.npad / 8) * (L.f_dense / 16) * 128;
+            L.fb_off = (int)total;
+            total += L.npad;
+            L.fe_off = (int)total;
+            total += (int64_t)n_extra * L.npad;
+        }
+    }
+    total = (total + 3) & ~(int64_t)3;
+    if (total == 0) return TSP_OK;
+    std::vector<float> host((size_t)total, 0.0f);
+    for (int m = 0; m < TSP_NUM_MLP; ++m)
+        for (HostLayer& L : e->mlp[m]) {
+            if (m == TSP_MLP_REPRESENTATION || m == TSP_MLP_PRIOR || L.f_off < 0) continue;
+            if (m == TSP_MLP_TERMINAL && !c.mask_absorbing_states) continue;
+            const int kc = L.f_dense / 16;
+            // tile jt, chunk ch, lane (g, t): W[8 jt + g][16 ch + 4 t .. + 3]
+            for (int jt = 0; jt < L.npad / 8; ++jt)
+                for (int ch = 0; ch < kc; ++ch)
+                    for (int lane = 0; lane < 32; ++lane) {
+                        const int g = lane >> 2, t = lane & 3, n = 8 * jt + g;
+                        float* dst = &host[(size_t)L.f_off + ((size_t)jt * kc + ch) * 128 + lane * 4];
+                        for (int q = 0; q < 4; ++q)
+                            dst[q] = n < L.out_dim ? L.W[(size_t)n * L.in_dim + 16 * ch + 4 * t + q] : 0.0f;
+                    }
+            for (int o = 0; o < L.out_dim; ++o) host[(size_t)L.fb_off + o] = L.b[o];
+            for (int a = 0; a < L.in_dim - L.f_dense; ++a)
+                for (int o = 0; o < L.out_dim; ++o)
+                    host[(size_t)L.fe_off + (size_t)a * L.npad + o] = L.W[(size_t)o * L.in_dim + L.f_dense + a];
+        }
+    int rc = ensure(e, e->farena, (size_t)total * sizeof(float));
+    if (rc) return rc;
+    CK(e, cudaMemcpyAsync(e->farena.p, host.data(), (size_t)total * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+    CK(e, cudaStreamSynchronize(e->stream));
+    e->farena_floats = total;
+    return TSP_OK;
+}
+
 int build_schedules(tsp_engine* e) {
     const tsp_config& c = e->cfg;
     const int H = c.encoding_size, A = c.num_actions;
@@ -304,19 +469,26 @@ int build_schedules(tsp_engine* e) {
         e->has_pred = true;
     }
     if (!stochastic) {  // recurrent inference: models.py:233-257, 283-287
-        HSched hs;
-        hs.in_dim = H;
-        hs.in_buf = hs.new_buf(H, 0);
-        const int raw = add_chain(e, hs, TSP_MLP_DYNAMICS, hs.in_buf, 1);
-        hs.rl = add_chain(e, hs, TSP_MLP_REWARD, raw, 0);  // reward / terminal read the UN-normalised state
-        if (have(TSP_MLP_TERMINAL) && e->mlp[TSP_MLP_TERMINAL].back().out_dim == 1 &&
-            e->mlp[TSP_MLP_TERMINAL].front().in_dim == H)
-            hs.tl = add_chain(e, hs, TSP_MLP_TERMINAL, raw, 0);
-        hs.hidden = add_normalise(hs, raw, H);
-        hs.pl = add_chain(e, hs, TSP_MLP_POLICY, hs.hidden, 0);
-        hs.vl = add_chain(e, hs, TSP_MLP_VALUE, hs.hidden, 0);
-        if ((rc = lower(e, hs, e->sch_recur))) return rc;
+        const bool have_terminal = have(TSP_MLP_TERMINAL) && e->mlp[TSP_MLP_TERMINAL].back().out_dim == 1 &&
+                                   e->mlp[TSP_MLP_TERMINAL].front().in_dim == H;
+        auto make = [&](bool with_terminal) {
+            HSched hs;
+            hs.in_dim = H;
+            hs.in_buf = hs.new_buf(H, 0);
+            const int raw = add_chain(e, hs, TSP_MLP_DYNAMICS, hs.in_buf, 1);
+            hs.rl = add_chain(e, hs, TSP_MLP_REWARD, raw, 0);  // reward / terminal read the UN-normalised state
+            if (with_terminal) hs.tl = add_chain(e, hs, TSP_MLP_TERMINAL, raw, 0);
+            hs.hidden = add_normalise(hs, raw, H);
+            hs.pl = add_chain(e, hs, TSP_MLP_POLICY, hs.hidden, 0);
+            hs.vl = add_chain(e, hs, TSP_MLP_VALUE, hs.hidden, 0);
+            return hs;
+        };
+        if ((rc = lower(e, make(have_terminal), e->sch_recur))) return rc;
         e->has_recur = true;
+        // the search evaluates the terminal head only under mask_absorbing_states (self_play.py:415)
+        if (e->nc == 5 && e->farena_floats > 0 && H % 16 == 0 && (!c.mask_absorbing_states || have_terminal) &&
+            (rc = lower_fast(e, make(c.mask_absorbing_states != 0))))
+            return rc;
     } else {  // one future of MuZeroStochasticConcat.dynamics: models.py:520-595
         HSched hs;
         hs.in_dim = H;
@@ -463,8 +635,61 @@ int launch_search_tm(tsp_engine* e, const SearchParams& p, int TM, int xw) {
     return launch_search<VARIANT, NC, 32>(e, p, xw);
 }
 
+size_t fast_smem(const FastSched& fs, int G, int S) {
+    const size_t pb_n = (size_t)((S + 3) & ~1);
+    return pb_n * 16 + ((pb_n + 3) & ~(size_t)3) * 4 + sizeof(FastSched) + (size_t)fs.w_floats * 4 +
+           (size_t)G * (GT * fs.row_stride + 2 * GT + GT * PATH_LEVELS) * 4;
+}
+
+template <int G>
+int launch_fast(tsp_engine* e, const FastParams& p) {
+    const size_t smem = fast_smem(e->fsched, G, p.S);
+    int rc = set_smem(e, search_fast_kernel<G>, smem);
+    if (rc) return rc;
+    const int grid = (p.B + G * GT - 1) / (G * GT);
+    search_fast_kernel<G><<<grid, G * GTHREADS, smem, e->stream>>>(p);
+    CK(e, cudaGetLastError());
+    e->stats.kernel_launches++;
+    e->stats.search_ctas = grid;
+    e->stats.search_smem_bytes = (int)smem;
+    e->stats.trees_per_cta = G * GT;
+    e->stats.threads_per_cta = G * GTHREADS;
+    return TSP_OK;
+}
+
+// Deterministic search on the fast kernel: groups of 16 trees, G groups per CTA sharing one weight copy.
+int launch_fast_any(tsp_engine* e, const SearchParams& sp) {
+    FastParams p;
+    memset(&p, 0, sizeof(p));
+    p.B = sp.B; p.S = sp.S; p.A = sp.A; p.H = sp.H; p.support = sp.support;
+    p.mask_absorbing = sp.mask_absorbing; p.uniform_policy = sp.uniform_policy;
+    p.blocks_per_tree = sp.blocks_per_tree; p.hidden_per_tree = sp.hidden_per_tree;
+    p.max_rec = sp.max_rec; p.T = sp.T; p.pb_stride = sp.pb_stride;
+    p.discount = sp.discount; p.pb_table = sp.pb_table;
+    p.blocks = sp.blocks; p.hidden_pool = sp.hidden_pool; p.hdr = sp.hdr; p.rootprior = sp.rootprior; p.rootact = sp.rootact;
+    p.tie = sp.tie; p.fed = sp.fed; p.trace = sp.trace;
+    p.sched = reinterpret_cast<const FastSched*>(e->fsched_dev.p);
+    p.wfrag = reinterpret_cast<const float*>(e->farena.p);
+    p.visit_counts = sp.visit_counts; p.root_value = sp.root_value; p.child_value = sp.child_value;
+    p.child_prior = sp.child_prior; p.child_reward = sp.child_reward;
+    p.max_depth = sp.max_depth; p.num_records = sp.num_records; p.total_depth = sp.total_depth;
+    p.phase_cycles = sp.phase_cycles;
+    // Few roots: one group per CTA spreads the groups over all SMs. Many roots: four groups per CTA share one
+    // weight copy (16 warps per SM either way: the register file, not shared memory, bounds residency).
+    const int groups = (p.B + GT - 1) / GT;
+    int G = groups <= 3 * e->sm_count ? 1 : 4;
+    if (e->fast_groups == 1 || e->fast_groups == 2 || e->fast_groups == 4) G = e->fast_groups;
+    while (G > 1 && fast_smem(e->fsched, G, p.S) > 227 * 1024) G >>= 1;
+    if (G == 4) return launch_fast<4>(e, p);
+    if (G == 2) return launch_fast<2>(e, p);
+    return launch_fast<1>(e, p);
+}
+
 int launch_search_any(tsp_engine* e, const SearchParams& p_in) {
     SearchParams p = p_in;
+    if (e->cfg.variant == 0 && e->nc == 5 && e->has_fast && !e->no_fast && e->finalized &&
+        fast_smem(e->fsched, 1, p.S) <= 227 * 1024)
+        return launch_fast_any(e, p);
     // 32 trees per CTA measured best at every batch size (4,096 .. 65,536 roots, both network sizes):
     // lane == row in the MLP phase wants a full warp of rows; 16 is the fallback when the activation
     // strips of 32 rows do not fit next to the weights.
@@ -603,6 +828,8 @@ int tsp_create(const tsp_config* cfg, tsp_handle* out) {
     if (const char* t = getenv("TSP_COLS_PER_THREAD")) e->ct_override = atoi(t);
     if (const char* t = getenv("TSP_TILES_PER_WARP")) e->ng_override = atoi(t);
     if (const char* t = getenv("TSP_WARP_MLP")) e->warp_mlp = atoi(t) != 0;
+    if (const char* t = getenv("TSP_NO_FAST")) e->no_fast = atoi(t) != 0;
+    if (const char* t = getenv("TSP_FAST_GROUPS")) e->fast_groups = atoi(t);
     auto bail = [&](int rc) {
         g_create_error = e->err;
         tsp_destroy(e);
@@ -659,7 +886,7 @@ int tsp_destroy(tsp_handle e) {
     if (!e) return TSP_OK;
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
-    for (DevBuf* b : {&e->arena, &e->blocks, &e->hidden, &e->hdr, &e->rootprior, &e->rootact, &e->pbtable, &e->phase, &e->s_obs,
+    for (DevBuf* b : {&e->arena, &e->farena, &e->fsched_dev, &e->blocks, &e->hidden, &e->hdr, &e->rootprior, &e->rootact, &e->pbtable, &e->phase, &e->s_obs,
                       &e->s_legal, &e->s_nlegal, &e->s_noise, &e->s_tie, &e->s_chance, &e->s_fedroot, &e->s_fed,
                       &e->s_visits, &e->s_rootv, &e->s_cval, &e->s_cprior, &e->s_crew, &e->s_depth, &e->s_rpred,
                       &e->s_rhid, &e->s_nrec, &e->s_troot, &e->s_trace, &e->s_tdepth, &e->n_in, &e->n_act})
@@ -727,6 +954,7 @@ int tsp_finalize_weights(tsp_handle e) {
     CK(e, cudaMemcpyAsync(e->arena.p, host.data(), (size_t)total * sizeof(float), cudaMemcpyHostToDevice, e->stream));
     CK(e, cudaStreamSynchronize(e->stream));
     e->arena_floats = total;
+    if ((rc = pack_fast_arena(e))) return rc;
     if ((rc = build_schedules(e))) return rc;
     e->finalized = true;
     return TSP_OK;

@@ -1,0 +1,631 @@
+// tsp_fast.cuh -- latency-engineered search kernel for the deterministic MuZero search
+// (self_play.py:378-427) with the network weights resident in shared memory.
+//
+// Organisation: a CTA holds G independent GROUPS of 16 trees; a group is 4 warps (8 lanes per tree),
+// owns one 16-row activation strip and synchronises only with itself (named barrier, 128 threads), so
+// the groups of an SM drift out of phase and one group's tensor-core MLP overlaps another group's
+// float64 selection / backup. All groups of a CTA share one shared-memory copy of the weights.
+//
+// MLP: every Linear layer is cut into 16 x 8 output tiles (mma.sync.m16n8k8, 3xTF32 split, fp32
+// accumulate -- float32-level accuracy, see tsp_device.cuh). The weights are packed on the host in
+// FRAGMENT ORDER: for an 8-column tile, chunk c of 16 inputs and lane (g, t) the four consecutive
+// weights W[8 j + g][16 c + 4 t .. 16 c + 4 t + 3] form one float4, so a warp fetches the B operands of
+// two k-steps with ONE conflict-free LDS.128. The same permutation of k inside a chunk is applied to
+// the A operand: lane (g, t) reads activations [16 c + 4 t .. + 3] of rows g and g + 8 with two LDS.128
+// (row stride == 16 mod 32 words). A host-built tile list per stage and warp replaces all index
+// arithmetic; tiles that share their input are batched so the A fragments are split once.
+#pragma once
+#include "tsp_device.cuh"
+
+namespace tsp {
+
+constexpr int GT = 16;              // trees per group (one mma row tile)
+constexpr int GTHREADS = GT * GW;   // 128 threads = 4 warps
+constexpr int GWARPS = GTHREADS / 32;
+constexpr int FAST_MAX_TILES = 200;
+constexpr int FAST_MAX_STAGES = 12;
+constexpr int FAST_NT = 4;          // tiles per batch (share one set of A fragments)
+
+struct alignas(16) FTile {
+    int wf_off;   // float offset of the fragment block [kc][32 lanes][4] of this 8-column tile
+    int b_off;    // float offset of the 8 bias values of this tile
+    int e_off;    // float offset of the one-hot rows (row a at e_off + a * e_ld), -1: none
+    short e_ld;
+    short in_off, out_off;  // float offsets inside a row strip (out_off: first of the 8 columns)
+    unsigned char kc;       // chunks of 16 inputs
+    unsigned char act;      // 1: ELU
+    unsigned char batch;    // on the first tile of a batch: tiles in the batch (same in_off / kc); else 0
+    unsigned char pad;
+    int pad2[2];
+};
+static_assert(sizeof(FTile) == 32, "FTile is two 16-byte words");
+
+struct FStage {
+    short first[GWARPS + 1];  // warp w of the group runs tiles [first[w], first[w + 1])
+    short row_op;             // 1: min-max normalise r_in -> r_out over r_n elements
+    short r_in, r_out, r_n;
+    short pad[3];
+};
+
+struct FastSched {
+    int n_stages, row_stride, n_tiles, w_floats;
+    short off_hidden, off_pl, off_vl, off_rl, off_tl, pad[3];
+    FStage st[FAST_MAX_STAGES];
+    FTile tiles[FAST_MAX_TILES];
+};
+
+struct FastParams {
+    int B, S, A, H, support, mask_absorbing, uniform_policy;
+    int blocks_per_tree, hidden_per_tree, max_rec, T, pb_stride;
+    double discount;
+    const double* pb_table;
+    void* blocks; float* hidden_pool; TreeHeader* hdr; const double* rootprior; const int* rootact;
+    const unsigned char* tie;
+    const float* fed; float* trace;
+    const FastSched* sched;  // device copy
+    const float* wfrag;      // fragment-ordered weight arena of the search MLPs
+    int* visit_counts; double* root_value; double* child_value; double* child_prior; double* child_reward;
+    int* max_depth; int* num_records; int* total_depth;
+    unsigned long long* phase_cycles;
+};
+
+__device__ __forceinline__ float rcp_approx(float x) {  // MUFU.RCP, <= 1 ulp
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ void group_barrier(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(GTHREADS) : "memory"); }
+
+// One batch: NT tiles x 16 rows, all K. KCT > 0: compile-time chunk count (fully unrolled).
+template <int KCT, int NT>
+__device__ __forceinline__ void mma_batch(const FTile* __restrict__ tl, const float* __restrict__ W,
+                                          float* __restrict__ act, int rs, const int* __restrict__ row_action,
+                                          const unsigned char* __restrict__ row_active) {
+    const int lane = threadIdx.x & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int kc = KCT ? KCT : tl[0].kc;
+    const float* x0 = act + g * rs + tl[0].in_off + 4 * t;
+    const float* x1 = x0 + 8 * rs;
+    float dm[NT][4], dc[NT][4], de[NT][4];  // hi*hi, lo*hi, hi*lo: three independent mma chains per tile
+    const float* wb[NT];
+#pragma unroll
+    for (int i = 0; i < NT; ++i) {
+        const FTile& ti = tl[i];
+        wb[i] = W + ti.wf_off + lane * 4;
+        const float2 b = *reinterpret_cast<const float2*>(W + ti.b_off + 2 * t);
+        dm[i][0] = b.x; dm[i][1] = b.y; dm[i][2] = b.x; dm[i][3] = b.y;
+        if (ti.e_off >= 0) {  // one-hot action input == one gathered weight row (models.py:236-243)
+            const float2 e0 = *reinterpret_cast<const float2*>(W + ti.e_off + row_action[g] * ti.e_ld + 2 * t);
+            const float2 e1 = *reinterpret_cast<const float2*>(W + ti.e_off + row_action[g + 8] * ti.e_ld + 2 * t);
+            dm[i][0] += e0.x; dm[i][1] += e0.y; dm[i][2] += e1.x; dm[i][3] += e1.y;
+        }
+        dc[i][0] = dc[i][1] = dc[i][2] = dc[i][3] = 0.f;
+        de[i][0] = de[i][1] = de[i][2] = de[i][3] = 0.f;
+    }
+#pragma unroll(KCT ? KCT : 2)
+    for (int c = 0; c < kc; ++c) {
+        const float4 A0 = *reinterpret_cast<const float4*>(x0 + 16 * c);
+        const float4 A1 = *reinterpret_cast<const float4*>(x1 + 16 * c);
+        // k-step 2c: slots (t, t+4) <-> inputs 16c+4t, 16c+4t+1; k-step 2c+1: inputs 16c+4t+2, 16c+4t+3
+        const float af[2][4] = {{A0.x, A1.x, A0.y, A1.y}, {A0.z, A1.z, A0.w, A1.w}};
+        unsigned ah[2][4], al[2][4];
+#pragma unroll
+        for (int s = 0; s < 2; ++s)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                ah[s][q] = tf32_hi(af[s][q]);
+                al[s][q] = __float_as_uint(af[s][q] - __uint_as_float(ah[s][q]));
+            }
+#pragma unroll
+        for (int i = 0; i < NT; ++i) {
+            const float4 Bv = *reinterpret_cast<const float4*>(wb[i] + c * 128);
+            const float bf[2][2] = {{Bv.x, Bv.y}, {Bv.z, Bv.w}};
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                unsigned bh[2], bl[2];
+                bh[0] = tf32_hi(bf[s][0]); bh[1] = tf32_hi(bf[s][1]);
+                bl[0] = __float_as_uint(bf[s][0] - __uint_as_float(bh[0]));
+                bl[1] = __float_as_uint(bf[s][1] - __uint_as_float(bh[1]));
+                mma_tf32(dm[i], ah[s], bh);
+                mma_tf32(dc[i], al[s], bh);
+                mma_tf32(de[i], ah[s], bl);
+            }
+        }
+    }
+    const bool on0 = row_active[g] != 0, on1 = row_active[g + 8] != 0;
+#pragma unroll
+    for (int i = 0; i < NT; ++i) {
+        const FTile& ti = tl[i];
+        float d0 = dm[i][0] + (dc[i][0] + de[i][0]), d1 = dm[i][1] + (dc[i][1] + de[i][1]);
+        float d2 = dm[i][2] + (dc[i][2] + de[i][2]), d3 = dm[i][3] + (dc[i][3] + de[i][3]);
+        if (ti.act) {
+            d0 = elu(d0); d1 = elu(d1); d2 = elu(d2); d3 = elu(d3);
+        }
+        float* y = act + ti.out_off + 2 * t;
+        if (on0) *reinterpret_cast<float2*>(y + g * rs) = make_float2(d0, d1);
+        if (on1) *reinterpret_cast<float2*>(y + (g + 8) * rs) = make_float2(d2, d3);
+    }
+}
+
+template <int NT>
+__device__ __forceinline__ void mma_batch_k(const FTile* tl, const float* W, float* act, int rs,
+                                            const int* row_action, const unsigned char* row_active) {
+    switch (tl[0].kc) {
+        case 2: mma_batch<2, NT>(tl, W, act, rs, row_action, row_active); break;
+        case 4: mma_batch<4, NT>(tl, W, act, rs, row_action, row_active); break;
+        default: mma_batch<0, NT>(tl, W, act, rs, row_action, row_active); break;
+    }
+}
+
+// All stages of the schedule for the 16 rows of one group; called by the 4 warps of the group.
+__device__ __forceinline__ void fast_mlp(const FastSched& fs, const float* __restrict__ W, float* __restrict__ act,
+                                         const int* __restrict__ row_action, const unsigned char* __restrict__ row_active,
+                                         int gt, int barid, unsigned long long* dbg) {
+    const int rs = fs.row_stride;
+    const int wg = gt >> 5;
+    for (int s = 0; s < fs.n_stages; ++s) {
+        const FStage& st = fs.st[s];
+        long long d0 = 0, d1 = 0;
+        if (dbg && threadIdx.x == 0) d0 = clock64();
+        int i = st.first[wg];
+        const int end = st.first[wg + 1];
+        while (i < end) {
+            const FTile* tl = fs.tiles + i;
+            const int nb = tl->batch;
+            switch (nb) {
+                case 1: mma_batch_k<1>(tl, W, act, rs, row_action, row_active); break;
+                case 2: mma_batch_k<2>(tl, W, act, rs, row_action, row_active); break;
+                case 3: mma_batch_k<3>(tl, W, act, rs, row_action, row_active); break;
+                default: mma_batch_k<4>(tl, W, act, rs, row_action, row_active); break;
+            }
+            i += nb;
+        }
+        if (st.row_op == 1) {
+            // models.py:223-231 / 248-255: (x - min) / scale, scale += 1e-5 only where scale < 1e-5
+            const int row = gt >> 3, j = gt & 7;
+            const unsigned gmask = 0xFFu << ((gt & 31) & 24);
+            if (row_active[row]) {
+                const float* x = act + row * rs + st.r_in;
+                float mn = CUDART_INF_F, mx = -CUDART_INF_F;
+                for (int q = j; q < st.r_n; q += GW) {
+                    const float v = x[q];
+                    mn = fminf(mn, v);
+                    mx = fmaxf(mx, v);
+                }
+#pragma unroll
+                for (int d = 1; d < GW; d <<= 1) {
+                    mn = fminf(mn, __shfl_xor_sync(gmask, mn, d));
+                    mx = fmaxf(mx, __shfl_xor_sync(gmask, mx, d));
+                }
+                float scale = __fsub_rn(mx, mn);
+                if (scale < 1e-5f) scale = __fadd_rn(scale, 1e-5f);
+                const float inv = __frcp_rn(scale);
+                float* y = act + row * rs + st.r_out;
+                for (int q = j; q < st.r_n; q += GW) y[q] = __fmul_rn(__fsub_rn(x[q], mn), inv);
+            }
+        }
+        if (dbg && threadIdx.x == 0) d1 = clock64();
+        group_barrier(barid);
+        if (dbg && threadIdx.x == 0) {
+            const long long d2 = clock64();
+            atomicAdd(dbg + 8 + 2 * s, (unsigned long long)(d1 - d0));
+            atomicAdd(dbg + 9 + 2 * s, (unsigned long long)(d2 - d1));
+        }
+    }
+}
+
+// value and reward decode (models.py:1180-1201) and the policy softmax (self_play.py:532-538) of one row
+// by its 8-lane group, with the three max-reductions and the five sum-reductions sharing their shuffle
+// rounds (3 + 3 dependent rounds instead of 24).
+__device__ __forceinline__ void decode_row(const float* __restrict__ vl, const float* __restrict__ rl,
+                                           const float* __restrict__ pl, int support, int A, bool uniform, int j,
+                                           unsigned gmask, float& value, float& reward, float& prior) {
+    const int n = 2 * support + 1;
+    float mv = -CUDART_INF_F, mr = -CUDART_INF_F;
+    for (int i = j; i < n; i += GW) {
+        mv = fmaxf(mv, vl[i]);
+        mr = fmaxf(mr, rl[i]);
+    }
+    const bool pon = j < A;
+    const float lg = (pon && !uniform) ? pl[j] : 0.0f;
+    float mp = pon ? lg : -CUDART_INF_F;
+#pragma unroll
+    for (int d = 1; d < GW; d <<= 1) {
+        mv = fmaxf(mv, __shfl_xor_sync(gmask, mv, d));
+        mr = fmaxf(mr, __shfl_xor_sync(gmask, mr, d));
+        mp = fmaxf(mp, __shfl_xor_sync(gmask, mp, d));
+    }
+    float sv = 0.f, xv = 0.f, sr = 0.f, xr = 0.f;
+    for (int i = j; i < n; i += GW) {
+        const float ev = expf(__fsub_rn(vl[i], mv));
+        const float er = expf(__fsub_rn(rl[i], mr));
+        sv = __fadd_rn(sv, ev);
+        xv = fmaf((float)(i - support), ev, xv);
+        sr = __fadd_rn(sr, er);
+        xr = fmaf((float)(i - support), er, xr);
+    }
+    const float ep = pon ? expf(__fsub_rn(lg, mp)) : 0.0f;
+    float sp = ep;
+#pragma unroll
+    for (int d = 1; d < GW; d <<= 1) {
+        sv = __fadd_rn(sv, __shfl_xor_sync(gmask, sv, d));
+        xv = __fadd_rn(xv, __shfl_xor_sync(gmask, xv, d));
+        sr = __fadd_rn(sr, __shfl_xor_sync(gmask, sr, d));
+        xr = __fadd_rn(xr, __shfl_xor_sync(gmask, xr, d));
+        sp = __fadd_rn(sp, __shfl_xor_sync(gmask, sp, d));
+    }
+    value = inverse_value_transform(__fdiv_rn(xv, sv));
+    reward = inverse_value_transform(__fdiv_rn(xr, sr));
+    prior = __fdiv_rn(ep, sp);
+}
+
+
+// ------------------------------------------------------------------ selection ----
+// Exact pUCT arg-max of one tree level in float64 (self_play.py:436-477), the reference's operation
+// order; out of line so that the float32 filter below stays small. Returns the chosen slot.
+__device__ __noinline__ int select_exact(double pbN, double sqN, int vis, double vs, double prior, float rw,
+                                         double discount, double mn, double mx, bool on, unsigned gmask, int gl0,
+                                         const unsigned char* tie_row, int T, int& k_tie) {
+    MinMax mm;
+    mm.mn = mn;
+    mm.mx = mx;
+    double score = -CUDART_INF;
+    if (on) score = ucb_score<0>(pbN, sqN, vis, vs, prior, rw, discount, mm);
+    double best = score;
+#pragma unroll
+    for (int d = 1; d < GW; d <<= 1) {
+        const double o = shfl_xor_d(gmask, best, d);
+        best = o > best ? o : best;
+    }
+    const unsigned tied = (__ballot_sync(gmask, on && score == best) >> gl0) & 0xFFu;
+    const int nt = __popc(tied);
+    if (nt == 1) return __ffs(tied) - 1;
+    int v = 0;  // self_play.py:444-450 with the external tie stream
+    if (tie_row) v = tie_row[k_tie % T];
+    k_tie++;
+    return __fns(tied, 0, (v % nt) + 1);
+}
+
+// Sequential backup for paths deeper than the lane-parallel version records (self_play.py:485-490).
+__device__ __noinline__ void backup_walk(NodeBlock<5>* blocks, int cur, int cs, double v, double discount, MinMax& mm,
+                                         double& root_vsum, int& root_visit) {
+    while (true) {
+        NodeBlock<5>* bk = blocks + cur;
+        const int ps = bk->aux, pc = bk->parent;
+        const double vs = __dadd_rn(bk->vsum[cs], v);
+        const int vis = bk->visit[cs] + 1;
+        const double rw = (double)bk->reward[cs];
+        bk->vsum[cs] = vs;
+        bk->visit[cs] = vis;
+        mm.update(__dadd_rn(rw, __dmul_rn(discount, __ddiv_rn(vs, (double)vis))));
+        v = __dadd_rn(rw, __dmul_rn(discount, v));
+        if (cur == 0) break;
+        cs = ps & 0xFF;
+        cur = pc;
+    }
+    root_vsum = __dadd_rn(root_vsum, v);
+    root_visit += 1;
+    mm.update(__dadd_rn(0.0, __dmul_rn(discount, __ddiv_rn(root_vsum, (double)root_visit))));
+}
+
+constexpr int PATH_LEVELS = 32;  // levels recorded per descent for the lane-parallel backup
+
+template <int G>
+__global__ void __launch_bounds__(G * GTHREADS, 4 / G) search_fast_kernel(const __grid_constant__ FastParams p) {
+    extern __shared__ __align__(16) float smem[];
+    constexpr int THREADS = G * GTHREADS;
+    constexpr int NC = 5;
+    using Block = NodeBlock<NC>;
+    // shared-memory carve-out (offsets only, so every pointer stays in the shared address space)
+    const int pb_n = (p.S + 2 + 1) & ~1;
+    const int pbf_n = (pb_n + 3) & ~3;
+    double* pb = reinterpret_cast<double*>(smem);  // pb[N] = log((N + base + 1) / base) + init
+    double* sq = pb + pb_n;                        // sq[N] = sqrt(N), correctly rounded (host libm)
+    float* pbf = smem + 4 * pb_n;                  // float32 pb[N] * sq[N] for the selection filter
+    FastSched* fsp = reinterpret_cast<FastSched*>(pbf + pbf_n);
+    float* wsm = pbf + pbf_n + sizeof(FastSched) / 4;
+    const int tid = threadIdx.x;
+    {
+        const int4* src = reinterpret_cast<const int4*>(p.sched);
+        int4* dst = reinterpret_cast<int4*>(fsp);
+        for (int i = tid; i < (int)(sizeof(FastSched) / 16); i += THREADS) dst[i] = src[i];
+    }
+    for (int i = tid; i < p.S + 2; i += THREADS) {
+        const double a = p.pb_table[i], c = p.pb_table[p.pb_stride + i];
+        pb[i] = a;
+        sq[i] = c;
+        pbf[i] = (float)(a * c);
+    }
+    const bool fed = p.fed != nullptr;
+    __syncthreads();
+    const FastSched& fs = *fsp;
+    const int rs = fs.row_stride;
+    if (!fed) {
+        const float4* src = reinterpret_cast<const float4*>(p.wfrag);
+        float4* dst = reinterpret_cast<float4*>(wsm);
+        for (int i = tid; i < (fs.w_floats >> 2); i += THREADS) dst[i] = __ldg(src + i);
+    }
+    const int grp = tid / GTHREADS, gt = tid % GTHREADS;
+    float* act = wsm + fs.w_floats + grp * (GT * rs + GT + GT + GT * PATH_LEVELS);
+    int* row_action = reinterpret_cast<int*>(act + GT * rs);
+    unsigned char* row_active = reinterpret_cast<unsigned char*>(row_action + GT);
+    int* path = row_action + 2 * GT + (gt >> 3) * PATH_LEVELS;  // (block << 8 | slot) per level of this tree's descent
+    const int barid = 1 + grp;
+
+    const int lane = tid & 31, j = tid & 7, row = gt >> 3;
+    const unsigned gmask = 0xFFu << (lane & 24);
+    const int gl0 = lane & 24;
+    const int b = (blockIdx.x * G + grp) * GT + row;
+    const bool valid = b < p.B;
+    const int A = p.A, H = p.H;
+    const double discount = p.discount;
+
+    Block* blocks = reinterpret_cast<Block*>(p.blocks) + (size_t)(valid ? b : 0) * p.blocks_per_tree;
+    float* hpool = p.hidden_pool + (size_t)(valid ? b : 0) * p.hidden_per_tree * H;
+    const float* fed_rec = fed ? p.fed + (size_t)(valid ? b : 0) * p.max_rec * REC : nullptr;
+    float* trace_rec = p.trace ? p.trace + (size_t)(valid ? b : 0) * p.max_rec * REC : nullptr;
+
+    MinMax mm;
+    mm.mn = CUDART_INF;
+    mm.mx = -CUDART_INF;
+    double root_vsum = 0.0, root_prior = 0.0;
+    int root_visit = 0, n_blocks = 1, max_depth = 0, n_sims = 0, k_tie = 0, n_rec = 0;
+    int n_root = 0, root_act = 0, depth_total = 0, n_exact = 0;
+    if (valid) {
+        const TreeHeader h = p.hdr[b];
+        n_root = h.n_root;
+        root_prior = p.rootprior[(size_t)b * GW + j];
+        root_act = p.rootact[(size_t)b * GW + j];
+    }
+    const float root_prior_f = (float)root_prior;
+    const float gammaf = (float)discount;
+    __syncthreads();
+
+    for (int it = 0; it < p.S; ++it) {
+        if (fed && n_rec >= p.max_rec) n_sims = p.S;  // fed records exhausted: stop this tree
+        const bool active = valid && n_sims < p.S;
+        long long tc0 = 0, tc1 = 0, tc2 = 0, tc3 = 0;
+        if (p.phase_cycles && tid == 0) tc0 = clock64();
+        // ================= selection (one 8-lane group per tree), self_play.py:388-397 =================
+        int node = 0, slot = 0, depth = 0, Np = root_visit;
+        if (active) {
+            // float32 image of MinMaxStats.normalize for the filter: (x - mnf) * idf, identity while max <= min
+            float mnf = 0.0f, idf = 1.0f;
+            if (mm.mx > mm.mn) {
+                mnf = (float)mm.mn;
+                idf = rcp_approx((float)__dsub_rn(mm.mx, mm.mn));
+            }
+            const float amnf = fabsf(mnf);
+            while (true) {
+                const Block* blk = blocks + node;
+                const int nch = (node == 0) ? n_root : A;
+                const bool on = j < nch;
+                int vis = 0, ch = -1;
+                double vs = 0.0;
+                float rw = 0.0f, prf = 0.0f;
+                if (on) {
+                    vis = blk->visit[j];
+                    ch = blk->child[j];
+                    vs = blk->vsum[j];
+                    rw = blk->reward[j];
+                    prf = (node == 0) ? root_prior_f : blk->prior[j];
+                    // pull every expanded child's block towards L1 while this level is scored
+                    if (ch >= 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(blocks + ch));
+                }
+                // ---- float32 filter: score_j +- E_j encloses the reference's float64 ucb_score; when one
+                // interval lies strictly above all others, the exact arg-max is that child and it is not tied.
+                float lo = -CUDART_INF_F, hi = -CUDART_INF_F;
+                if (on) {
+                    const float ps = pbf[Np] * rcp_approx((float)(vis + 1)) * prf;
+                    float V = 0.0f, aux = 0.0f;
+                    if (vis > 0) {
+                        const float gq = gammaf * ((float)vs * rcp_approx((float)vis));
+                        V = ((gq + rw) - mnf) * idf;
+                        aux = idf * (fabsf(gq) + fabsf(rw) + amnf);
+                    }
+                    const float sc = ps + V;
+                    const float E = fmaf(1.9073486e-6f, fabsf(ps) + fabsf(V) + aux, 1e-30f);  // 16 * 2^-23 * magnitudes
+                    lo = sc - E;
+                    hi = sc + E;
+                }
+                float m1 = lo;
+#pragma unroll
+                for (int d = 1; d < GW; d <<= 1) m1 = fmaxf(m1, __shfl_xor_sync(gmask, m1, d));
+                const unsigned cand = (__ballot_sync(gmask, on && hi >= m1) >> gl0) & 0xFFu;
+                if (__popc(cand) == 1) {
+                    slot = __ffs(cand) - 1;
+                } else {  // near-tie, exact tie or non-finite filter value: decide in float64
+                    slot = select_exact(pb[Np], sq[Np], vis, vs, (node == 0) ? root_prior : (double)prf, rw, discount, mm.mn,
+                                        mm.mx, on, gmask, gl0, p.tie ? p.tie + (size_t)b * p.T : nullptr, p.T, k_tie);
+                    n_exact++;
+                }
+                const int vis_sel = __shfl_sync(gmask, vis, gl0 + slot);
+                const int child_sel = __shfl_sync(gmask, ch, gl0 + slot);
+                if (j == 0 && depth < PATH_LEVELS) path[depth] = (node << 8) | slot;
+                depth++;
+                if (child_sel < 0) break;
+                node = child_sel;
+                Np = vis_sel;
+            }
+        }
+        int action = 0;
+        if (active) {
+            action = (node == 0) ? __shfl_sync(gmask, root_act, gl0 + slot) : slot;
+            if (depth > max_depth) max_depth = depth;
+            depth_total += depth;
+        }
+
+        // ================= network evaluation of the group's 16 leaves =================
+        float value = 0.0f, reward = 0.0f, terminal = -1.0f, prior = 0.0f;
+        if (!fed) {
+            if (j == 0) {
+                row_action[row] = action;
+                row_active[row] = active ? 1 : 0;
+            }
+            if (active) {  // gather the parent's hidden state (block id == hidden slot)
+                const float4* src = reinterpret_cast<const float4*>(hpool + (size_t)node * H);
+                float4* dst = reinterpret_cast<float4*>(act + row * rs);
+                for (int i = j; i < (H >> 2); i += GW) dst[i] = src[i];
+            }
+            if (p.phase_cycles && tid == 0) tc1 = clock64();
+            group_barrier(barid);
+            if (p.phase_cycles && tid == 0) tc2 = clock64();
+            fast_mlp(fs, wsm, act, row_action, row_active, gt, barid, p.phase_cycles);
+            if (p.phase_cycles && tid == 0) tc3 = clock64();
+            if (active) {
+                const float* r = act + row * rs;
+                decode_row(r + fs.off_vl, r + fs.off_rl, r + fs.off_pl, p.support, A, p.uniform_policy != 0, j, gmask,
+                           value, reward, prior);
+                if (p.mask_absorbing) terminal = r[fs.off_tl];
+            }
+        } else if (active) {
+            const float* fr = fed_rec + (size_t)n_rec * REC;
+            value = fr[1];
+            reward = fr[2];
+            terminal = fr[3];
+            prior = (j < A) ? fr[4 + j] : 0.0f;
+        }
+
+        // ================= expansion + backup (one group per tree) =================
+        if (active) {
+            if (trace_rec && n_rec < p.max_rec) {
+                float* tr = trace_rec + (size_t)n_rec * REC;
+                for (int i = j; i < REC; i += GW) tr[i] = 0.0f;
+                __syncwarp(gmask);
+                if (j == 0) {
+                    tr[0] = 1.0f;
+                    tr[1] = value;
+                    tr[2] = reward;
+                    tr[3] = terminal;
+                }
+                if (j < A) tr[4 + j] = prior;
+            }
+            n_rec++;
+            Block* pblk = blocks + node;
+            const bool masked = p.mask_absorbing && (terminal >= 0.0f);  // self_play.py:408-417
+            double v = masked ? 0.0 : (double)value;
+            if (!masked) {
+                // ---- Node.expand, self_play.py:524-538 ----
+                const int nb = n_blocks++;
+                Block* nblk = blocks + nb;
+                if (j < NC) {
+                    nblk->visit[j] = 0;
+                    nblk->child[j] = -1;
+                    nblk->prior[j] = prior;
+                    nblk->reward[j] = 0.0f;
+                    nblk->vsum[j] = 0.0;
+                }
+                if (j == 0) {
+                    nblk->parent = node;
+                    nblk->aux = slot | (nb << 8);
+                    pblk->child[slot] = nb;
+                    pblk->reward[slot] = reward;
+                }
+                if (!fed) {  // hidden state of the new node
+                    float4* dst = reinterpret_cast<float4*>(hpool + (size_t)nb * H);
+                    const float4* src = reinterpret_cast<const float4*>(act + row * rs + fs.off_hidden);
+                    for (int i = j; i < (H >> 2); i += GW) dst[i] = src[i];
+                }
+            }
+            __syncwarp(gmask);
+            // ---- backup, self_play.py:485-490, lane-parallel: entry e = 0 is the root, entry e >= 1 the child chosen
+            // at level e - 1 of the descent. The value chain v <- r + discount * v is replayed by every lane (one
+            // shuffle + 2 flops per level); the expensive per-node part (value_sum / visit_count for MinMaxStats)
+            // runs once, one entry per lane.
+            if (depth <= PATH_LEVELS) {
+                double pmn = CUDART_INF, pmx = -CUDART_INF;
+                for (int r = depth >> 3; r >= 0; --r) {
+                    const int e = 8 * r + j;
+                    const bool mine = e <= depth;
+                    Block* bk = blocks;
+                    int cs = 0, vis0 = root_visit;
+                    double vs0 = root_vsum;
+                    float rwf = 0.0f;
+                    if (mine && e >= 1) {
+                        const int ent = path[e - 1];
+                        bk = blocks + (ent >> 8);
+                        cs = ent & 0xFF;
+                        vs0 = bk->vsum[cs];
+                        vis0 = bk->visit[cs];
+                        rwf = bk->reward[cs];
+                    }
+                    double myv = 0.0;
+                    const int e_hi = min(depth, 8 * r + 7), e_lo = max(8 * r, 1);
+                    for (int ee = e_hi; ee >= e_lo; --ee) {
+                        const double rwe = (double)__shfl_sync(gmask, rwf, gl0 + (ee & 7));
+                        if (ee == e) myv = v;
+                        v = __dadd_rn(rwe, __dmul_rn(discount, v));
+                    }
+                    if (e == 0) myv = v;
+                    if (mine) {
+                        const double vs = __dadd_rn(vs0, myv);
+                        const int vis = vis0 + 1;
+                        const double x = __dadd_rn((double)rwf, __dmul_rn(discount, __ddiv_rn(vs, (double)vis)));
+                        if (e >= 1) {
+                            bk->vsum[cs] = vs;
+                            bk->visit[cs] = vis;
+                        }
+                        pmn = pmn < x ? pmn : x;
+                        pmx = pmx > x ? pmx : x;
+                    }
+                }
+                root_vsum = __dadd_rn(root_vsum, v);
+                root_visit += 1;
+#pragma unroll
+                for (int d = 1; d < GW; d <<= 1) {
+                    const double on_ = shfl_xor_d(gmask, pmn, d), ox_ = shfl_xor_d(gmask, pmx, d);
+                    pmn = on_ < pmn ? on_ : pmn;
+                    pmx = ox_ > pmx ? ox_ : pmx;
+                }
+                mm.mn = mm.mn < pmn ? mm.mn : pmn;
+                mm.mx = mm.mx > pmx ? mm.mx : pmx;
+            } else {
+                backup_walk(blocks, node, slot, v, discount, mm, root_vsum, root_visit);
+            }
+            n_sims++;
+        }
+        if (p.phase_cycles && tid == 0 && !fed) {
+            const long long tc4 = clock64();
+            atomicAdd(p.phase_cycles + 0, (unsigned long long)(tc1 - tc0));
+            atomicAdd(p.phase_cycles + 1, (unsigned long long)(tc2 - tc1));
+            atomicAdd(p.phase_cycles + 2, (unsigned long long)(tc3 - tc2));
+            atomicAdd(p.phase_cycles + 3, (unsigned long long)(tc4 - tc3));
+            atomicAdd(p.phase_cycles + 4, 1ull);
+        }
+        // a row's strip is re-filled by the group that read it; the last stage barrier ordered all tiles
+        __syncwarp(gmask);
+    }
+
+    // ================= outputs: what consumers read from `root` =================
+    if (valid) {
+        const Block* rb = blocks;
+        if (j == 0) {
+            if (p.root_value) p.root_value[b] = root_visit == 0 ? 0.0 : __ddiv_rn(root_vsum, (double)root_visit);
+            if (p.max_depth) p.max_depth[b] = max_depth;
+            if (p.num_records) p.num_records[b] = n_rec;
+            if (p.total_depth) p.total_depth[b] = depth_total;
+            if (p.phase_cycles) {  // how often the float32 filter had to defer to float64
+                atomicAdd(p.phase_cycles + 5, (unsigned long long)n_exact);
+                atomicAdd(p.phase_cycles + 6, (unsigned long long)depth_total);
+            }
+        }
+        if (j < A) {
+            if (p.visit_counts) p.visit_counts[(size_t)b * A + j] = 0;
+            if (p.child_value) p.child_value[(size_t)b * A + j] = 0.0;
+            if (p.child_prior) p.child_prior[(size_t)b * A + j] = 0.0;
+            if (p.child_reward) p.child_reward[(size_t)b * A + j] = 0.0;
+        }
+        __syncwarp(gmask);
+        if (j < n_root) {
+            const int a = root_act;
+            const int vis = rb->visit[j];
+            const double vs = rb->vsum[j];
+            if (p.visit_counts) p.visit_counts[(size_t)b * A + a] = vis;
+            if (p.child_value) p.child_value[(size_t)b * A + a] = vis == 0 ? 0.0 : __ddiv_rn(vs, (double)vis);
+            if (p.child_prior) p.child_prior[(size_t)b * A + a] = root_prior;
+            if (p.child_reward) p.child_reward[(size_t)b * A + a] = (double)rb->reward[j];
+        }
+    }
+}
+
+}  // namespace tsp

@@ -329,7 +329,7 @@ class Engine:
         nt = max(1, v[43])
         return dict(select=v[0] / n, wait=v[1] / n, mlp=v[2] / n, backup=v[3] / n, samples=v[4],
                     stages_work_wait=stages, tile_init_kloop_store=(round(v[40] / nt), round(v[41] / nt), round(v[42] / nt)),
-                    tiles_per_iter=v[43] / n)
+                    tiles_per_iter=v[43] / n, exact_selects=v[5], select_levels=v[6])
 
     def reset_timing(self):
         self._check(self.lib.tsp_reset_timing(self.handle))
