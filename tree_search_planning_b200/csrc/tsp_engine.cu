@@ -290,13 +290,19 @@ int lower_fast(tsp_engine* e, const HSched& hs) {
     for (size_t i = 0; i < width.size(); ++i) width[i] = (hs.width[i] + 15) & ~15;  // A operands are read in chunks of 16
     std::vector<int> off;
     int total = strip_offsets(hs, width, false, off);
-    total += ((16 - total % 32) + 32) % 32;  // row stride == 16 (mod 32): conflict-free LDS.128 of rows g, g + 1
-    if (off[hs.in_buf] != 0 || total > 8000) return TSP_OK;
+    // two rows are interleaved per strip line: line stride 2 * total == 16 (mod 32) words keeps the LDS.128 /
+    // STS.128 of lanes g, g + 1 conflict-free
+    total += ((8 - total % 16) + 16) % 16;
+    if (off[hs.in_buf] != 0 || total > 4000) return TSP_OK;
     FastSched& fs = e->fsched;
     memset(&fs, 0, sizeof(fs));
     fs.n_stages = ns;
-    fs.row_stride = total;
+    fs.row_stride = 2 * total;
     auto o16 = [&](int b) { return (short)(b >= 0 ? off[b] : -1); };
+    // buffers that a later layer reads as an mma operand get their lo parts stored by the producer
+    std::vector<char> is_operand(hs.width.size(), 0);
+    for (const HStage& h : hs.stages)
+        for (const HOp& op : h.ops) is_operand[op.in_buf] = 1;
     fs.off_hidden = o16(hs.hidden);
     fs.off_pl = o16(hs.pl);
     fs.off_vl = o16(hs.vl);
@@ -331,7 +337,7 @@ int lower_fast(tsp_engine* e, const HSched& hs) {
                 t.in_off = o16(op.in_buf);
                 t.out_off = (short)(off[op.out_buf] + 8 * jt);
                 t.kc = (unsigned char)kc;
-                t.act = (unsigned char)op.act;
+                t.act = (unsigned char)((op.act ? 1 : 0) | (is_operand[op.out_buf] ? 2 : 0));
                 tiles.push_back(t);
             }
         }
@@ -404,14 +410,15 @@ int pack_fast_arena(tsp_engine* e) {
             if (m == TSP_MLP_REPRESENTATION || m == TSP_MLP_PRIOR || L.f_off < 0) continue;
             if (m == TSP_MLP_TERMINAL && !c.mask_absorbing_states) continue;
             const int kc = L.f_dense / 16;
-            // tile jt, chunk ch, lane (g, t): W[8 jt + g][16 ch + 4 t .. + 3]
+            // tile jt, chunk ch, lane (g, t): W[8 jt + g][16 ch + {2 t, 2 t + 1, 8 + 2 t, 9 + 2 t}]
             for (int jt = 0; jt < L.npad / 8; ++jt)
                 for (int ch = 0; ch < kc; ++ch)
                     for (int lane = 0; lane < 32; ++lane) {
                         const int g = lane >> 2, t = lane & 3, n = 8 * jt + g;
                         float* dst = &host[(size_t)L.f_off + ((size_t)jt * kc + ch) * 128 + lane * 4];
+                        const int kk[4] = {2 * t, 2 * t + 1, 8 + 2 * t, 9 + 2 * t};
                         for (int q = 0; q < 4; ++q)
-                            dst[q] = n < L.out_dim ? L.W[(size_t)n * L.in_dim + 16 * ch + 4 * t + q] : 0.0f;
+                            dst[q] = n < L.out_dim ? L.W[(size_t)n * L.in_dim + 16 * ch + kk[q]] : 0.0f;
                     }
             for (int o = 0; o < L.out_dim; ++o) host[(size_t)L.fb_off + o] = L.b[o];
             for (int a = 0; a < L.in_dim - L.f_dense; ++a)
@@ -674,13 +681,11 @@ int launch_fast_any(tsp_engine* e, const SearchParams& sp) {
     p.child_prior = sp.child_prior; p.child_reward = sp.child_reward;
     p.max_depth = sp.max_depth; p.num_records = sp.num_records; p.total_depth = sp.total_depth;
     p.phase_cycles = sp.phase_cycles;
-    // Few roots: one group per CTA spreads the groups over all SMs. Many roots: four groups per CTA share one
-    // weight copy (16 warps per SM either way: the register file, not shared memory, bounds residency).
-    const int groups = (p.B + GT - 1) / GT;
-    int G = groups <= 3 * e->sm_count ? 1 : 4;
-    if (e->fast_groups == 1 || e->fast_groups == 2 || e->fast_groups == 4) G = e->fast_groups;
+    // 8 warps per group at <= 128 registers per thread: two groups per SM either way; two groups per CTA share
+    // one weight copy.
+    int G = 2;
+    if (e->fast_groups == 1 || e->fast_groups == 2) G = e->fast_groups;
     while (G > 1 && fast_smem(e->fsched, G, p.S) > 227 * 1024) G >>= 1;
-    if (G == 4) return launch_fast<4>(e, p);
     if (G == 2) return launch_fast<2>(e, p);
     return launch_fast<1>(e, p);
 }

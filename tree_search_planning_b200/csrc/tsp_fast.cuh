@@ -1,39 +1,53 @@
 // tsp_fast.cuh -- latency-engineered search kernel for the deterministic MuZero search
 // (self_play.py:378-427) with the network weights resident in shared memory.
 //
-// Organisation: a CTA holds G independent GROUPS of 16 trees; a group is 4 warps (8 lanes per tree),
-// owns one 16-row activation strip and synchronises only with itself (named barrier, 128 threads), so
-// the groups of an SM drift out of phase and one group's tensor-core MLP overlaps another group's
-// float64 selection / backup. All groups of a CTA share one shared-memory copy of the weights.
+// Organisation: a CTA holds G independent GROUPS of 16 trees; a group is 8 warps (16 lanes per tree, two
+// trees per warp), owns one 16-row activation strip and synchronises only with itself (named barrier,
+// 256 threads), so the groups of an SM drift out of phase and one group's tensor-core MLP overlaps another
+// group's selection / backup. All groups of a CTA share one shared-memory copy of the weights. The search
+// is bound by the serial instruction stream of a warp (ncu: ~8 cycles per issued instruction, issue slots
+// 25 % busy), so the design spreads a group's work over many warps: two trees per warp keep the number of
+// tree levels a warp walks close to one tree's depth, and the same 8 warps split the 16 x 8 MLP tiles.
 //
 // MLP: every Linear layer is cut into 16 x 8 output tiles (mma.sync.m16n8k8, 3xTF32 split, fp32
-// accumulate -- float32-level accuracy, see tsp_device.cuh). The weights are packed on the host in
-// FRAGMENT ORDER: for an 8-column tile, chunk c of 16 inputs and lane (g, t) the four consecutive
-// weights W[8 j + g][16 c + 4 t .. 16 c + 4 t + 3] form one float4, so a warp fetches the B operands of
-// two k-steps with ONE conflict-free LDS.128. The same permutation of k inside a chunk is applied to
-// the A operand: lane (g, t) reads activations [16 c + 4 t .. + 3] of rows g and g + 8 with two LDS.128
-// (row stride == 16 mod 32 words). A host-built tile list per stage and warp replaces all index
-// arithmetic; tiles that share their input are batched so the A fragments are split once.
+// accumulate -- float32-level accuracy, see tsp_device.cuh). Both operands live in shared memory in
+// FRAGMENT ORDER so that one LDS.128 yields the registers of an mma operand with no shuffling:
+//   * activations: rows g and g + 8 of the 16-row tile are interleaved, element (r, k) of a group's strip at
+//     (r & 7) * rs + (k >> 1) * 4 + (k & 1) * 2 + (r >> 3); lane (g, t) reads {X[g][k], X[g+8][k], X[g][k+1],
+//     X[g+8][k+1]}, k = 8 s + 2 t, == {a0, a1, a2, a3} of k-step s (k-slots t, t + 4 <-> inputs k, k + 1). The
+//     same float4 is what the accumulator fragment {c0, c2, c1, c3} of a lane is stored as. The producer also
+//     stores lo = x - trunc_tf32(x) in a twin strip, so consumers never split activations (the tensor core
+//     ignores the 13 low mantissa bits of a TF32 operand: the raw float32 IS the hi operand).
+//   * weights: per 8-column tile, chunk of 16 inputs and lane: {W[n][16c+2t], W[n][16c+2t+1], W[n][16c+8+2t],
+//     W[n][16c+9+2t]}, n = 8 j + g: the B operands of two k-steps in one LDS.128 (split in registers).
+// A host-built tile list per stage and warp replaces all index arithmetic; tiles that share their input are
+// batched so the A fragments are loaded once.
+//
+// Selection runs a float32 FILTER with a rigorous error bound in front of the float64 arithmetic of the
+// reference: the exact code path only decides near-ties and exact ties (about 0.6 % of the levels), so
+// the result is bit-identical to the float64 arg-max of self_play.py:436-477 at a fraction of its cost.
 #pragma once
 #include "tsp_device.cuh"
 
 namespace tsp {
 
-constexpr int GT = 16;              // trees per group (one mma row tile)
-constexpr int GTHREADS = GT * GW;   // 128 threads = 4 warps
+constexpr int GT = 16;               // trees per group (one mma row tile)
+constexpr int LPT = 16;              // lanes per tree: lanes 0..7 score the children, all 16 move data
+constexpr int GTHREADS = GT * LPT;   // 256 threads = 8 warps
 constexpr int GWARPS = GTHREADS / 32;
 constexpr int FAST_MAX_TILES = 200;
 constexpr int FAST_MAX_STAGES = 12;
-constexpr int FAST_NT = 4;          // tiles per batch (share one set of A fragments)
+constexpr int FAST_NT = 2;           // tiles per batch (share one set of A fragments)
+constexpr int PATH_LEVELS = 32;      // levels recorded per descent for the lane-parallel backup
 
 struct alignas(16) FTile {
     int wf_off;   // float offset of the fragment block [kc][32 lanes][4] of this 8-column tile
     int b_off;    // float offset of the 8 bias values of this tile
     int e_off;    // float offset of the one-hot rows (row a at e_off + a * e_ld), -1: none
     short e_ld;
-    short in_off, out_off;  // float offsets inside a row strip (out_off: first of the 8 columns)
+    short in_off, out_off;  // column offsets inside a row (out_off: first of the 8 columns)
     unsigned char kc;       // chunks of 16 inputs
-    unsigned char act;      // 1: ELU
+    unsigned char act;      // bit 0: ELU, bit 1: store the lo parts (a later layer reads the buffer as an operand)
     unsigned char batch;    // on the first tile of a batch: tiles in the batch (same in_off / kc); else 0
     unsigned char pad;
     int pad2[2];
@@ -46,6 +60,7 @@ struct FStage {
     short r_in, r_out, r_n;
     short pad[3];
 };
+static_assert(sizeof(FStage) == 32, "FStage is two 16-byte words");
 
 struct FastSched {
     int n_stages, row_stride, n_tiles, w_floats;
@@ -53,6 +68,7 @@ struct FastSched {
     FStage st[FAST_MAX_STAGES];
     FTile tiles[FAST_MAX_TILES];
 };
+static_assert(sizeof(FastSched) % 16 == 0, "FastSched is copied in 16-byte words");
 
 struct FastParams {
     int B, S, A, H, support, mask_absorbing, uniform_policy;
@@ -76,16 +92,25 @@ __device__ __forceinline__ float rcp_approx(float x) {  // MUFU.RCP, <= 1 ulp
 }
 __device__ __forceinline__ void group_barrier(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(GTHREADS) : "memory"); }
 
+// column k of a row inside the interleaved strip (see the header comment)
+__device__ __forceinline__ int kofs(int k) { return ((k >> 1) << 2) + ((k & 1) << 1); }
+__device__ __forceinline__ float tf32_lo(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+__device__ __forceinline__ void mma_tf32v(float (&d)[4], const uint4& a, unsigned b0, unsigned b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b0), "r"(b1));
+}
+
 // One batch: NT tiles x 16 rows, all K. KCT > 0: compile-time chunk count (fully unrolled).
 template <int KCT, int NT>
 __device__ __forceinline__ void mma_batch(const FTile* __restrict__ tl, const float* __restrict__ W,
-                                          float* __restrict__ act, int rs, const int* __restrict__ row_action,
-                                          const unsigned char* __restrict__ row_active) {
+                                          float* __restrict__ act, int rs, const int* __restrict__ row_action) {
     const int lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;
     const int kc = KCT ? KCT : tl[0].kc;
-    const float* x0 = act + g * rs + tl[0].in_off + 4 * t;
-    const float* x1 = x0 + 8 * rs;
+    const float* x = act + g * rs + 2 * tl[0].in_off + 4 * t;  // hi operand == the raw float32 activations
+    const float* xl = x + 8 * rs;                              // twin strip: lo parts
     float dm[NT][4], dc[NT][4], de[NT][4];  // hi*hi, lo*hi, hi*lo: three independent mma chains per tile
     const float* wb[NT];
 #pragma unroll
@@ -104,66 +129,59 @@ __device__ __forceinline__ void mma_batch(const FTile* __restrict__ tl, const fl
     }
 #pragma unroll(KCT ? KCT : 2)
     for (int c = 0; c < kc; ++c) {
-        const float4 A0 = *reinterpret_cast<const float4*>(x0 + 16 * c);
-        const float4 A1 = *reinterpret_cast<const float4*>(x1 + 16 * c);
-        // k-step 2c: slots (t, t+4) <-> inputs 16c+4t, 16c+4t+1; k-step 2c+1: inputs 16c+4t+2, 16c+4t+3
-        const float af[2][4] = {{A0.x, A1.x, A0.y, A1.y}, {A0.z, A1.z, A0.w, A1.w}};
-        unsigned ah[2][4], al[2][4];
+        uint4 ah[2], al[2];
 #pragma unroll
-        for (int s = 0; s < 2; ++s)
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                ah[s][q] = tf32_hi(af[s][q]);
-                al[s][q] = __float_as_uint(af[s][q] - __uint_as_float(ah[s][q]));
-            }
+        for (int s2 = 0; s2 < 2; ++s2) {
+            ah[s2] = *reinterpret_cast<const uint4*>(x + 32 * c + 16 * s2);
+            al[s2] = *reinterpret_cast<const uint4*>(xl + 32 * c + 16 * s2);
+        }
 #pragma unroll
         for (int i = 0; i < NT; ++i) {
             const float4 Bv = *reinterpret_cast<const float4*>(wb[i] + c * 128);
             const float bf[2][2] = {{Bv.x, Bv.y}, {Bv.z, Bv.w}};
 #pragma unroll
-            for (int s = 0; s < 2; ++s) {
-                unsigned bh[2], bl[2];
-                bh[0] = tf32_hi(bf[s][0]); bh[1] = tf32_hi(bf[s][1]);
-                bl[0] = __float_as_uint(bf[s][0] - __uint_as_float(bh[0]));
-                bl[1] = __float_as_uint(bf[s][1] - __uint_as_float(bh[1]));
-                mma_tf32(dm[i], ah[s], bh);
-                mma_tf32(dc[i], al[s], bh);
-                mma_tf32(de[i], ah[s], bl);
+            for (int s2 = 0; s2 < 2; ++s2) {
+                const unsigned bh0 = __float_as_uint(bf[s2][0]), bh1 = __float_as_uint(bf[s2][1]);
+                const unsigned bl0 = __float_as_uint(tf32_lo(bf[s2][0])), bl1 = __float_as_uint(tf32_lo(bf[s2][1]));
+                mma_tf32v(dm[i], ah[s2], bh0, bh1);
+                mma_tf32v(dc[i], al[s2], bh0, bh1);
+                mma_tf32v(de[i], ah[s2], bl0, bl1);
             }
         }
     }
-    const bool on0 = row_active[g] != 0, on1 = row_active[g + 8] != 0;
 #pragma unroll
     for (int i = 0; i < NT; ++i) {
         const FTile& ti = tl[i];
         float d0 = dm[i][0] + (dc[i][0] + de[i][0]), d1 = dm[i][1] + (dc[i][1] + de[i][1]);
         float d2 = dm[i][2] + (dc[i][2] + de[i][2]), d3 = dm[i][3] + (dc[i][3] + de[i][3]);
-        if (ti.act) {
+        if (ti.act & 1) {
             d0 = elu(d0); d1 = elu(d1); d2 = elu(d2); d3 = elu(d3);
         }
-        float* y = act + ti.out_off + 2 * t;
-        if (on0) *reinterpret_cast<float2*>(y + g * rs) = make_float2(d0, d1);
-        if (on1) *reinterpret_cast<float2*>(y + (g + 8) * rs) = make_float2(d2, d3);
+        // {c0, c2, c1, c3} = {X[g][n], X[g+8][n], X[g][n+1], X[g+8][n+1]}, n = out_off + 2 t
+        float* y = act + g * rs + 2 * ti.out_off + 4 * t;
+        *reinterpret_cast<float4*>(y) = make_float4(d0, d2, d1, d3);
+        if (ti.act & 2)
+            *reinterpret_cast<float4*>(y + 8 * rs) = make_float4(tf32_lo(d0), tf32_lo(d2), tf32_lo(d1), tf32_lo(d3));
     }
 }
 
 template <int NT>
-__device__ __forceinline__ void mma_batch_k(const FTile* tl, const float* W, float* act, int rs,
-                                            const int* row_action, const unsigned char* row_active) {
+__device__ __forceinline__ void mma_batch_k(const FTile* tl, const float* W, float* act, int rs, const int* row_action) {
     switch (tl[0].kc) {
-        case 2: mma_batch<2, NT>(tl, W, act, rs, row_action, row_active); break;
-        case 4: mma_batch<4, NT>(tl, W, act, rs, row_action, row_active); break;
-        default: mma_batch<0, NT>(tl, W, act, rs, row_action, row_active); break;
+        case 2: mma_batch<2, NT>(tl, W, act, rs, row_action); break;
+        case 4: mma_batch<4, NT>(tl, W, act, rs, row_action); break;
+        default: mma_batch<0, NT>(tl, W, act, rs, row_action); break;
     }
 }
 
-// All stages of the schedule for the 16 rows of one group; called by the 4 warps of the group.
+// All stages of the schedule for the 16 rows of one group; called by the 8 warps of the group.
 __device__ __forceinline__ void fast_mlp(const FastSched& fs, const float* __restrict__ W, float* __restrict__ act,
                                          const int* __restrict__ row_action, const unsigned char* __restrict__ row_active,
                                          int gt, int barid, unsigned long long* dbg) {
     const int rs = fs.row_stride;
     const int wg = gt >> 5;
-    for (int s = 0; s < fs.n_stages; ++s) {
+    const int n_stages = fs.n_stages;
+    for (int s = 0; s < n_stages; ++s) {
         const FStage& st = fs.st[s];
         long long d0 = 0, d1 = 0;
         if (dbg && threadIdx.x == 0) d0 = clock64();
@@ -172,36 +190,36 @@ __device__ __forceinline__ void fast_mlp(const FastSched& fs, const float* __res
         while (i < end) {
             const FTile* tl = fs.tiles + i;
             const int nb = tl->batch;
-            switch (nb) {
-                case 1: mma_batch_k<1>(tl, W, act, rs, row_action, row_active); break;
-                case 2: mma_batch_k<2>(tl, W, act, rs, row_action, row_active); break;
-                case 3: mma_batch_k<3>(tl, W, act, rs, row_action, row_active); break;
-                default: mma_batch_k<4>(tl, W, act, rs, row_action, row_active); break;
-            }
+            if (nb == 1) mma_batch_k<1>(tl, W, act, rs, row_action);
+            else mma_batch_k<2>(tl, W, act, rs, row_action);
             i += nb;
         }
         if (st.row_op == 1) {
             // models.py:223-231 / 248-255: (x - min) / scale, scale += 1e-5 only where scale < 1e-5
-            const int row = gt >> 3, j = gt & 7;
-            const unsigned gmask = 0xFFu << ((gt & 31) & 24);
+            const int row = gt >> 4, j = gt & 15;
+            const unsigned gmask = 0xFFFFu << (gt & 16);
             if (row_active[row]) {
-                const float* x = act + row * rs + st.r_in;
+                const float* x = act + (row & 7) * rs + (row >> 3) + 2 * st.r_in;
                 float mn = CUDART_INF_F, mx = -CUDART_INF_F;
-                for (int q = j; q < st.r_n; q += GW) {
-                    const float v = x[q];
+                for (int q = j; q < st.r_n; q += LPT) {
+                    const float v = x[kofs(q)];
                     mn = fminf(mn, v);
                     mx = fmaxf(mx, v);
                 }
 #pragma unroll
-                for (int d = 1; d < GW; d <<= 1) {
+                for (int d = 1; d < LPT; d <<= 1) {
                     mn = fminf(mn, __shfl_xor_sync(gmask, mn, d));
                     mx = fmaxf(mx, __shfl_xor_sync(gmask, mx, d));
                 }
                 float scale = __fsub_rn(mx, mn);
                 if (scale < 1e-5f) scale = __fadd_rn(scale, 1e-5f);
                 const float inv = __frcp_rn(scale);
-                float* y = act + row * rs + st.r_out;
-                for (int q = j; q < st.r_n; q += GW) y[q] = __fmul_rn(__fsub_rn(x[q], mn), inv);
+                float* y = act + (row & 7) * rs + (row >> 3) + 2 * st.r_out;
+                for (int q = j; q < st.r_n; q += LPT) {
+                    const float v = __fmul_rn(__fsub_rn(x[kofs(q)], mn), inv);
+                    y[kofs(q)] = v;
+                    y[kofs(q) + 8 * rs] = tf32_lo(v);
+                }
             }
         }
         if (dbg && threadIdx.x == 0) d1 = clock64();
@@ -215,30 +233,30 @@ __device__ __forceinline__ void fast_mlp(const FastSched& fs, const float* __res
 }
 
 // value and reward decode (models.py:1180-1201) and the policy softmax (self_play.py:532-538) of one row
-// by its 8-lane group, with the three max-reductions and the five sum-reductions sharing their shuffle
-// rounds (3 + 3 dependent rounds instead of 24).
+// by the 16 lanes of its tree, with the three max-reductions and the five sum-reductions sharing their
+// shuffle rounds. vl / rl / pl point at column 0 of the row inside the interleaved strip (column k at kofs(k)).
 __device__ __forceinline__ void decode_row(const float* __restrict__ vl, const float* __restrict__ rl,
                                            const float* __restrict__ pl, int support, int A, bool uniform, int j,
                                            unsigned gmask, float& value, float& reward, float& prior) {
     const int n = 2 * support + 1;
     float mv = -CUDART_INF_F, mr = -CUDART_INF_F;
-    for (int i = j; i < n; i += GW) {
-        mv = fmaxf(mv, vl[i]);
-        mr = fmaxf(mr, rl[i]);
+    for (int i = j; i < n; i += LPT) {
+        mv = fmaxf(mv, vl[kofs(i)]);
+        mr = fmaxf(mr, rl[kofs(i)]);
     }
     const bool pon = j < A;
-    const float lg = (pon && !uniform) ? pl[j] : 0.0f;
+    const float lg = (pon && !uniform) ? pl[kofs(j)] : 0.0f;
     float mp = pon ? lg : -CUDART_INF_F;
 #pragma unroll
-    for (int d = 1; d < GW; d <<= 1) {
+    for (int d = 1; d < LPT; d <<= 1) {
         mv = fmaxf(mv, __shfl_xor_sync(gmask, mv, d));
         mr = fmaxf(mr, __shfl_xor_sync(gmask, mr, d));
         mp = fmaxf(mp, __shfl_xor_sync(gmask, mp, d));
     }
     float sv = 0.f, xv = 0.f, sr = 0.f, xr = 0.f;
-    for (int i = j; i < n; i += GW) {
-        const float ev = expf(__fsub_rn(vl[i], mv));
-        const float er = expf(__fsub_rn(rl[i], mr));
+    for (int i = j; i < n; i += LPT) {
+        const float ev = expf(__fsub_rn(vl[kofs(i)], mv));
+        const float er = expf(__fsub_rn(rl[kofs(i)], mr));
         sv = __fadd_rn(sv, ev);
         xv = fmaf((float)(i - support), ev, xv);
         sr = __fadd_rn(sr, er);
@@ -247,7 +265,7 @@ __device__ __forceinline__ void decode_row(const float* __restrict__ vl, const f
     const float ep = pon ? expf(__fsub_rn(lg, mp)) : 0.0f;
     float sp = ep;
 #pragma unroll
-    for (int d = 1; d < GW; d <<= 1) {
+    for (int d = 1; d < LPT; d <<= 1) {
         sv = __fadd_rn(sv, __shfl_xor_sync(gmask, sv, d));
         xv = __fadd_rn(xv, __shfl_xor_sync(gmask, xv, d));
         sr = __fadd_rn(sr, __shfl_xor_sync(gmask, sr, d));
@@ -259,10 +277,9 @@ __device__ __forceinline__ void decode_row(const float* __restrict__ vl, const f
     prior = __fdiv_rn(ep, sp);
 }
 
-
 // ------------------------------------------------------------------ selection ----
 // Exact pUCT arg-max of one tree level in float64 (self_play.py:436-477), the reference's operation
-// order; out of line so that the float32 filter below stays small. Returns the chosen slot.
+// order; out of line so that the float32 filter stays small. Lanes 0..7 of the tree hold the children.
 __device__ __noinline__ int select_exact(double pbN, double sqN, int vis, double vs, double prior, float rw,
                                          double discount, double mn, double mx, bool on, unsigned gmask, int gl0,
                                          const unsigned char* tie_row, int T, int& k_tie) {
@@ -277,6 +294,7 @@ __device__ __noinline__ int select_exact(double pbN, double sqN, int vis, double
         const double o = shfl_xor_d(gmask, best, d);
         best = o > best ? o : best;
     }
+    best = shfl_d(gmask, best, gl0);  // lanes 8..15 hold no child: take the maximum of lanes 0..7
     const unsigned tied = (__ballot_sync(gmask, on && score == best) >> gl0) & 0xFFu;
     const int nt = __popc(tied);
     if (nt == 1) return __ffs(tied) - 1;
@@ -308,22 +326,20 @@ __device__ __noinline__ void backup_walk(NodeBlock<5>* blocks, int cur, int cs, 
     mm.update(__dadd_rn(0.0, __dmul_rn(discount, __ddiv_rn(root_vsum, (double)root_visit))));
 }
 
-constexpr int PATH_LEVELS = 32;  // levels recorded per descent for the lane-parallel backup
-
 template <int G>
-__global__ void __launch_bounds__(G * GTHREADS, 4 / G) search_fast_kernel(const __grid_constant__ FastParams p) {
+__global__ void __launch_bounds__(G * GTHREADS, 2 / G) search_fast_kernel(const __grid_constant__ FastParams p) {
     extern __shared__ __align__(16) float smem[];
     constexpr int THREADS = G * GTHREADS;
     constexpr int NC = 5;
     using Block = NodeBlock<NC>;
-    // shared-memory carve-out (offsets only, so every pointer stays in the shared address space)
+    // shared-memory carve-out: schedule (compile-time offset 0), tables, weights, per-group strips
+    FastSched* fsp = reinterpret_cast<FastSched*>(smem);
     const int pb_n = (p.S + 2 + 1) & ~1;
     const int pbf_n = (pb_n + 3) & ~3;
-    double* pb = reinterpret_cast<double*>(smem);  // pb[N] = log((N + base + 1) / base) + init
-    double* sq = pb + pb_n;                        // sq[N] = sqrt(N), correctly rounded (host libm)
-    float* pbf = smem + 4 * pb_n;                  // float32 pb[N] * sq[N] for the selection filter
-    FastSched* fsp = reinterpret_cast<FastSched*>(pbf + pbf_n);
-    float* wsm = pbf + pbf_n + sizeof(FastSched) / 4;
+    double* pb = reinterpret_cast<double*>(smem + sizeof(FastSched) / 4);  // pb[N] = log((N + base + 1) / base) + init
+    double* sq = pb + pb_n;                                                // sq[N] = sqrt(N), host libm
+    float* pbf = reinterpret_cast<float*>(sq + pb_n);                      // float32 pb[N] * sq[N] for the filter
+    float* wsm = pbf + pbf_n;
     const int tid = threadIdx.x;
     {
         const int4* src = reinterpret_cast<const int4*>(p.sched);
@@ -346,15 +362,18 @@ __global__ void __launch_bounds__(G * GTHREADS, 4 / G) search_fast_kernel(const 
         for (int i = tid; i < (fs.w_floats >> 2); i += THREADS) dst[i] = __ldg(src + i);
     }
     const int grp = tid / GTHREADS, gt = tid % GTHREADS;
+    // per group: strip of 8 interleaved row pairs (rs floats each) + its twin of lo parts, then the row tables
     float* act = wsm + fs.w_floats + grp * (GT * rs + GT + GT + GT * PATH_LEVELS);
     int* row_action = reinterpret_cast<int*>(act + GT * rs);
     unsigned char* row_active = reinterpret_cast<unsigned char*>(row_action + GT);
-    int* path = row_action + 2 * GT + (gt >> 3) * PATH_LEVELS;  // (block << 8 | slot) per level of this tree's descent
+    const int row = gt >> 4;                                 // tree of the group == row of the strip
+    int* path = row_action + 2 * GT + row * PATH_LEVELS;     // (block << 8 | slot) per level of this tree's descent
+    float* rowp = act + (row & 7) * rs + (row >> 3);         // column 0 of this tree's row in the interleaved strip
     const int barid = 1 + grp;
 
-    const int lane = tid & 31, j = tid & 7, row = gt >> 3;
-    const unsigned gmask = 0xFFu << (lane & 24);
-    const int gl0 = lane & 24;
+    const int lane = tid & 31, j = tid & 15;
+    const unsigned gmask = 0xFFFFu << (lane & 16);
+    const int gl0 = lane & 16;
     const int b = (blockIdx.x * G + grp) * GT + row;
     const bool valid = b < p.B;
     const int A = p.A, H = p.H;
@@ -374,8 +393,10 @@ __global__ void __launch_bounds__(G * GTHREADS, 4 / G) search_fast_kernel(const 
     if (valid) {
         const TreeHeader h = p.hdr[b];
         n_root = h.n_root;
-        root_prior = p.rootprior[(size_t)b * GW + j];
-        root_act = p.rootact[(size_t)b * GW + j];
+        if (j < GW) {
+            root_prior = p.rootprior[(size_t)b * GW + j];
+            root_act = p.rootact[(size_t)b * GW + j];
+        }
     }
     const float root_prior_f = (float)root_prior;
     const float gammaf = (float)discount;
@@ -386,7 +407,7 @@ __global__ void __launch_bounds__(G * GTHREADS, 4 / G) search_fast_kernel(const 
         const bool active = valid && n_sims < p.S;
         long long tc0 = 0, tc1 = 0, tc2 = 0, tc3 = 0;
         if (p.phase_cycles && tid == 0) tc0 = clock64();
-        // ================= selection (one 8-lane group per tree), self_play.py:388-397 =================
+        // ================= selection, self_play.py:388-397 =================
         int node = 0, slot = 0, depth = 0, Np = root_visit;
         if (active) {
             // float32 image of MinMaxStats.normalize for the filter: (x - mnf) * idf, identity while max <= min
@@ -411,6 +432,10 @@ __global__ void __launch_bounds__(G * GTHREADS, 4 / G) search_fast_kernel(const 
                     prf = (node == 0) ? root_prior_f : blk->prior[j];
                     // pull every expanded child's block towards L1 while this level is scored
                     if (ch >= 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(blocks + ch));
+                } else if (!fed && j >= GW) {
+                    // the idle lanes pull this node's hidden state in: it is the MLP input if the descent ends here
+                    const int line = j - GW;
+                    if (line * 32 < H) asm volatile("prefetch.global.L1 [%0];" ::"l"(hpool + (size_t)node * H + line * 32));
                 }
                 // ---- float32 filter: score_j +- E_j encloses the reference's float64 ucb_score; when one
                 // interval lies strictly above all others, the exact arg-max is that child and it is not tied.
@@ -431,6 +456,7 @@ __global__ void __launch_bounds__(G * GTHREADS, 4 / G) search_fast_kernel(const 
                 float m1 = lo;
 #pragma unroll
                 for (int d = 1; d < GW; d <<= 1) m1 = fmaxf(m1, __shfl_xor_sync(gmask, m1, d));
+                m1 = __shfl_sync(gmask, m1, gl0);
                 const unsigned cand = (__ballot_sync(gmask, on && hi >= m1) >> gl0) & 0xFFu;
                 if (__popc(cand) == 1) {
                     slot = __ffs(cand) - 1;
@@ -462,10 +488,15 @@ __global__ void __launch_bounds__(G * GTHREADS, 4 / G) search_fast_kernel(const 
                 row_action[row] = action;
                 row_active[row] = active ? 1 : 0;
             }
-            if (active) {  // gather the parent's hidden state (block id == hidden slot)
+            if (active) {  // gather the parent's hidden state (block id == hidden slot) into columns [0, H)
                 const float4* src = reinterpret_cast<const float4*>(hpool + (size_t)node * H);
-                float4* dst = reinterpret_cast<float4*>(act + row * rs);
-                for (int i = j; i < (H >> 2); i += GW) dst[i] = src[i];
+                for (int i = j; i < (H >> 2); i += LPT) {
+                    const float4 h4 = src[i];
+                    float* d = rowp + 8 * i;  // kofs(4 i)
+                    d[0] = h4.x; d[2] = h4.y; d[4] = h4.z; d[6] = h4.w;
+                    d += 8 * rs;
+                    d[0] = tf32_lo(h4.x); d[2] = tf32_lo(h4.y); d[4] = tf32_lo(h4.z); d[6] = tf32_lo(h4.w);
+                }
             }
             if (p.phase_cycles && tid == 0) tc1 = clock64();
             group_barrier(barid);
@@ -473,10 +504,10 @@ __global__ void __launch_bounds__(G * GTHREADS, 4 / G) search_fast_kernel(const 
             fast_mlp(fs, wsm, act, row_action, row_active, gt, barid, p.phase_cycles);
             if (p.phase_cycles && tid == 0) tc3 = clock64();
             if (active) {
-                const float* r = act + row * rs;
-                decode_row(r + fs.off_vl, r + fs.off_rl, r + fs.off_pl, p.support, A, p.uniform_policy != 0, j, gmask,
-                           value, reward, prior);
-                if (p.mask_absorbing) terminal = r[fs.off_tl];
+                const float* r = rowp;
+                decode_row(r + 2 * fs.off_vl, r + 2 * fs.off_rl, r + 2 * fs.off_pl, p.support, A, p.uniform_policy != 0, j,
+                           gmask, value, reward, prior);
+                if (p.mask_absorbing) terminal = r[2 * fs.off_tl];
             }
         } else if (active) {
             const float* fr = fed_rec + (size_t)n_rec * REC;
@@ -486,19 +517,18 @@ __global__ void __launch_bounds__(G * GTHREADS, 4 / G) search_fast_kernel(const 
             prior = (j < A) ? fr[4 + j] : 0.0f;
         }
 
-        // ================= expansion + backup (one group per tree) =================
+        // ================= expansion + backup =================
         if (active) {
             if (trace_rec && n_rec < p.max_rec) {
                 float* tr = trace_rec + (size_t)n_rec * REC;
-                for (int i = j; i < REC; i += GW) tr[i] = 0.0f;
-                __syncwarp(gmask);
-                if (j == 0) {
-                    tr[0] = 1.0f;
-                    tr[1] = value;
-                    tr[2] = reward;
-                    tr[3] = terminal;
-                }
-                if (j < A) tr[4 + j] = prior;
+                float tv = 0.0f;
+                if (j == 0) tv = 1.0f;
+                if (j == 1) tv = value;
+                if (j == 2) tv = reward;
+                if (j == 3) tv = terminal;
+                const float pj = __shfl_sync(gmask, prior, gl0 + ((j - 4) & 15));
+                if (j >= 4 && j < 4 + A) tv = pj;
+                tr[j] = tv;  // REC == LPT == 16
             }
             n_rec++;
             Block* pblk = blocks + node;
@@ -523,8 +553,11 @@ __global__ void __launch_bounds__(G * GTHREADS, 4 / G) search_fast_kernel(const 
                 }
                 if (!fed) {  // hidden state of the new node
                     float4* dst = reinterpret_cast<float4*>(hpool + (size_t)nb * H);
-                    const float4* src = reinterpret_cast<const float4*>(act + row * rs + fs.off_hidden);
-                    for (int i = j; i < (H >> 2); i += GW) dst[i] = src[i];
+                    const float* src = rowp + 2 * fs.off_hidden;
+                    for (int i = j; i < (H >> 2); i += LPT) {
+                        const float* q = src + 8 * i;
+                        dst[i] = make_float4(q[0], q[2], q[4], q[6]);
+                    }
                 }
             }
             __syncwarp(gmask);
@@ -534,8 +567,8 @@ __global__ void __launch_bounds__(G * GTHREADS, 4 / G) search_fast_kernel(const 
             // runs once, one entry per lane.
             if (depth <= PATH_LEVELS) {
                 double pmn = CUDART_INF, pmx = -CUDART_INF;
-                for (int r = depth >> 3; r >= 0; --r) {
-                    const int e = 8 * r + j;
+                for (int r = depth >> 4; r >= 0; --r) {
+                    const int e = LPT * r + j;
                     const bool mine = e <= depth;
                     Block* bk = blocks;
                     int cs = 0, vis0 = root_visit;
@@ -550,9 +583,9 @@ __global__ void __launch_bounds__(G * GTHREADS, 4 / G) search_fast_kernel(const 
                         rwf = bk->reward[cs];
                     }
                     double myv = 0.0;
-                    const int e_hi = min(depth, 8 * r + 7), e_lo = max(8 * r, 1);
+                    const int e_hi = min(depth, LPT * r + LPT - 1), e_lo = max(LPT * r, 1);
                     for (int ee = e_hi; ee >= e_lo; --ee) {
-                        const double rwe = (double)__shfl_sync(gmask, rwf, gl0 + (ee & 7));
+                        const double rwe = (double)__shfl_sync(gmask, rwf, gl0 + (ee & (LPT - 1)));
                         if (ee == e) myv = v;
                         v = __dadd_rn(rwe, __dmul_rn(discount, v));
                     }
@@ -572,7 +605,7 @@ __global__ void __launch_bounds__(G * GTHREADS, 4 / G) search_fast_kernel(const 
                 root_vsum = __dadd_rn(root_vsum, v);
                 root_visit += 1;
 #pragma unroll
-                for (int d = 1; d < GW; d <<= 1) {
+                for (int d = 1; d < LPT; d <<= 1) {
                     const double on_ = shfl_xor_d(gmask, pmn, d), ox_ = shfl_xor_d(gmask, pmx, d);
                     pmn = on_ < pmn ? on_ : pmn;
                     pmx = ox_ > pmx ? ox_ : pmx;
@@ -592,7 +625,7 @@ __global__ void __launch_bounds__(G * GTHREADS, 4 / G) search_fast_kernel(const 
             atomicAdd(p.phase_cycles + 3, (unsigned long long)(tc4 - tc3));
             atomicAdd(p.phase_cycles + 4, 1ull);
         }
-        // a row's strip is re-filled by the group that read it; the last stage barrier ordered all tiles
+        // a row's strip is re-filled by the lanes that read it; the last stage barrier ordered all tiles
         __syncwarp(gmask);
     }
 
