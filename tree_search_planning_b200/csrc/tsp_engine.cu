@@ -80,6 +80,7 @@ struct tsp_engine {
     int ng_override = 0;
     bool warp_mlp = false;
     bool no_fast = false;
+    bool no_wlo = false;
     int fast_groups = 0;  // TSP_FAST_GROUPS override (1, 2 or 4 groups of 16 trees per CTA)
 
     // device memory
@@ -308,67 +309,50 @@ int lower_fast(tsp_engine* e, const HSched& hs) {
     fs.off_vl = o16(hs.vl);
     fs.off_rl = o16(hs.rl);
     fs.off_tl = o16(hs.tl);
-    int nt = 0;
+    int nu = 0;
     for (int s = 0; s < ns; ++s) {
         const HStage& h = hs.stages[s];
-        FStage& st = fs.st[s];
-        st.row_op = (short)h.rop;
-        if (h.rop) {
-            st.r_in = o16(h.r_in);
-            st.r_out = o16(h.r_out);
-            st.r_n = (short)h.r_n;
-        }
-        // tiles of the stage, ops reading the same buffer adjacent (their tiles can share A fragments)
-        std::vector<HOp> ops = h.ops;
-        std::stable_sort(ops.begin(), ops.end(), [](const HOp& a, const HOp& b) { return a.in_buf < b.in_buf; });
-        std::vector<FTile> tiles;
-        for (const HOp& op : ops) {
+        fs.stage[s] = make_int4(h.rop, h.rop ? 2 * off[h.r_in] : 0, h.rop ? 2 * off[h.r_out] : 0, h.r_n);
+        std::vector<FUnit> units;
+        for (const HOp& op : h.ops) {
             const HostLayer& L = e->mlp[op.mlp][op.layer];
             if (L.f_off < 0 || L.f_dense % 16) return TSP_OK;
             const int kc = L.f_dense / 16;
             if (kc > 255) return TSP_OK;
             for (int jt = 0; jt < L.npad / 8; ++jt) {
-                FTile t;
-                memset(&t, 0, sizeof(t));
-                t.wf_off = L.f_off + jt * kc * 128;
-                t.b_off = L.fb_off + 8 * jt;
-                t.e_off = op.extra ? L.fe_off + 8 * jt : -1;
-                t.e_ld = (short)L.npad;
-                t.in_off = o16(op.in_buf);
-                t.out_off = (short)(off[op.out_buf] + 8 * jt);
-                t.kc = (unsigned char)kc;
-                t.act = (unsigned char)((op.act ? 1 : 0) | (is_operand[op.out_buf] ? 2 : 0));
-                tiles.push_back(t);
+                FUnit u;
+                memset(&u, 0, sizeof(u));
+                u.x_off = 2 * off[op.in_buf];
+                u.w_off = L.f_off + jt * kc * 128;
+                u.y_off = 2 * (off[op.out_buf] + 8 * jt);
+                u.flags = kc | (op.act ? 0x100 : 0) | (is_operand[op.out_buf] ? 0x200 : 0) | (op.extra ? 0x400 : 0);
+                u.b_off = L.fb_off + 8 * jt;
+                u.e_off = op.extra ? L.fe_off + 8 * jt : 0;
+                u.e_ld = L.npad;
+                units.push_back(u);
             }
         }
-        if (nt + (int)tiles.size() > FAST_MAX_TILES) return TSP_OK;
-        // contiguous partition over the 4 warps of a group, balanced by k-chunks
-        int cost = 0;
-        for (const FTile& t : tiles) cost += t.kc;
-        int acc = 0, w = 0;
-        st.first[0] = (short)nt;
-        for (size_t i = 0; i < tiles.size(); ++i) {
-            // close warp w's range before tile i when its share is reached
-            while (w < GWARPS - 1 && acc * GWARPS >= (w + 1) * cost) st.first[++w] = (short)(nt + i);
-            acc += tiles[i].kc;
+        if (nu + (int)units.size() > FAST_MAX_TILES) return TSP_OK;
+        // longest-processing-time assignment to the warps of a group: heaviest (deepest K) units first
+        std::vector<int> order(units.size());
+        for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
+        std::stable_sort(order.begin(), order.end(),
+                         [&](int a, int b) { return (units[a].flags & 0xFF) > (units[b].flags & 0xFF); });
+        std::vector<std::vector<int>> mine(GWARPS);
+        std::vector<int> load(GWARPS, 0);
+        for (int idx : order) {
+            int w = 0;
+            for (int k = 1; k < GWARPS; ++k)
+                if (load[k] < load[w]) w = k;
+            mine[w].push_back(idx);
+            load[w] += units[idx].flags & 0xFF;
         }
-        while (w < GWARPS) st.first[++w] = (short)(nt + tiles.size());
-        for (size_t i = 0; i < tiles.size(); ++i) fs.tiles[nt + i] = tiles[i];
-        // batches: consecutive tiles of one warp with the same input and depth, at most FAST_NT
-        for (int ww = 0; ww < GWARPS; ++ww) {
-            int i = st.first[ww];
-            while (i < st.first[ww + 1]) {
-                int n = 1;
-                while (n < FAST_NT && i + n < st.first[ww + 1] && fs.tiles[i + n].in_off == fs.tiles[i].in_off &&
-                       fs.tiles[i + n].kc == fs.tiles[i].kc)
-                    ++n;
-                fs.tiles[i].batch = (unsigned char)n;
-                i += n;
-            }
+        for (int w = 0; w < GWARPS; ++w) {
+            fs.ulist[s][w] = nu | ((int)mine[w].size() << 16);
+            for (int idx : mine[w]) fs.units[nu++] = units[idx];
         }
-        nt += (int)tiles.size();
     }
-    fs.n_tiles = nt;
+    fs.n_units = nu;
     fs.w_floats = (int)e->farena_floats;
     int rc = ensure(e, e->fsched_dev, sizeof(FastSched));
     if (rc) return rc;
@@ -425,9 +409,20 @@ int pack_fast_arena(tsp_engine* e) {
                 for (int o = 0; o < L.out_dim; ++o)
                     host[(size_t)L.fe_off + (size_t)a * L.npad + o] = L.W[(size_t)o * L.in_dim + L.f_dense + a];
         }
-    int rc = ensure(e, e->farena, (size_t)total * sizeof(float));
+    // second half: lo parts (x - trunc_tf32(x), the same float32 expression the kernel evaluates) of every value,
+    // same layout; only the weight fragments of it are read, and only when it fits in shared memory
+    host.resize((size_t)2 * total);
+    for (int64_t i = 0; i < total; ++i) {
+        uint32_t bits;
+        memcpy(&bits, &host[(size_t)i], 4);
+        bits &= 0xFFFFE000u;
+        float hi;
+        memcpy(&hi, &bits, 4);
+        host[(size_t)(total + i)] = host[(size_t)i] - hi;
+    }
+    int rc = ensure(e, e->farena, host.size() * sizeof(float));
     if (rc) return rc;
-    CK(e, cudaMemcpyAsync(e->farena.p, host.data(), (size_t)total * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+    CK(e, cudaMemcpyAsync(e->farena.p, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice, e->stream));
     CK(e, cudaStreamSynchronize(e->stream));
     e->farena_floats = total;
     return TSP_OK;
@@ -642,15 +637,15 @@ int launch_search_tm(tsp_engine* e, const SearchParams& p, int TM, int xw) {
     return launch_search<VARIANT, NC, 32>(e, p, xw);
 }
 
-size_t fast_smem(const FastSched& fs, int G, int S) {
+size_t fast_smem(const FastSched& fs, int G, int S, bool w_lo = false) {
     const size_t pb_n = (size_t)((S + 3) & ~1);
-    return pb_n * 16 + ((pb_n + 3) & ~(size_t)3) * 4 + sizeof(FastSched) + (size_t)fs.w_floats * 4 +
+    return pb_n * 16 + ((pb_n + 3) & ~(size_t)3) * 4 + sizeof(FastSched) + (size_t)fs.w_floats * (w_lo ? 8 : 4) +
            (size_t)G * (GT * fs.row_stride + 2 * GT + GT * PATH_LEVELS) * 4;
 }
 
 template <int G>
 int launch_fast(tsp_engine* e, const FastParams& p) {
-    const size_t smem = fast_smem(e->fsched, G, p.S);
+    const size_t smem = fast_smem(e->fsched, G, p.S, p.w_lo != 0);
     int rc = set_smem(e, search_fast_kernel<G>, smem);
     if (rc) return rc;
     const int grid = (p.B + G * GT - 1) / (G * GT);
@@ -672,7 +667,7 @@ int launch_fast_any(tsp_engine* e, const SearchParams& sp) {
     p.mask_absorbing = sp.mask_absorbing; p.uniform_policy = sp.uniform_policy;
     p.blocks_per_tree = sp.blocks_per_tree; p.hidden_per_tree = sp.hidden_per_tree;
     p.max_rec = sp.max_rec; p.T = sp.T; p.pb_stride = sp.pb_stride;
-    p.discount = sp.discount; p.pb_table = sp.pb_table;
+    p.discount = sp.discount; p.discount_f = (float)sp.discount; p.pb_table = sp.pb_table;
     p.blocks = sp.blocks; p.hidden_pool = sp.hidden_pool; p.hdr = sp.hdr; p.rootprior = sp.rootprior; p.rootact = sp.rootact;
     p.tie = sp.tie; p.fed = sp.fed; p.trace = sp.trace;
     p.sched = reinterpret_cast<const FastSched*>(e->fsched_dev.p);
@@ -686,6 +681,8 @@ int launch_fast_any(tsp_engine* e, const SearchParams& sp) {
     int G = 2;
     if (e->fast_groups == 1 || e->fast_groups == 2) G = e->fast_groups;
     while (G > 1 && fast_smem(e->fsched, G, p.S) > 227 * 1024) G >>= 1;
+    // host-split weights (no split arithmetic in the mma loop) when the doubled arena still fits
+    p.w_lo = (!e->no_wlo && fast_smem(e->fsched, G, p.S, true) <= 227 * 1024) ? 1 : 0;
     if (G == 2) return launch_fast<2>(e, p);
     return launch_fast<1>(e, p);
 }
@@ -834,6 +831,7 @@ int tsp_create(const tsp_config* cfg, tsp_handle* out) {
     if (const char* t = getenv("TSP_TILES_PER_WARP")) e->ng_override = atoi(t);
     if (const char* t = getenv("TSP_WARP_MLP")) e->warp_mlp = atoi(t) != 0;
     if (const char* t = getenv("TSP_NO_FAST")) e->no_fast = atoi(t) != 0;
+    if (const char* t = getenv("TSP_NO_WLO")) e->no_wlo = atoi(t) != 0;
     if (const char* t = getenv("TSP_FAST_GROUPS")) e->fast_groups = atoi(t);
     auto bail = [&](int rc) {
         g_create_error = e->err;

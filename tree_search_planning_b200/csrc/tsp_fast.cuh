@@ -37,42 +37,36 @@ constexpr int GTHREADS = GT * LPT;   // 256 threads = 8 warps
 constexpr int GWARPS = GTHREADS / 32;
 constexpr int FAST_MAX_TILES = 200;
 constexpr int FAST_MAX_STAGES = 12;
-constexpr int FAST_NT = 2;           // tiles per batch (share one set of A fragments)
 constexpr int PATH_LEVELS = 32;      // levels recorded per descent for the lane-parallel backup
+constexpr unsigned FULL = 0xffffffffu;  // the two trees of a warp run in lock step: every shuffle is full-mask
 
-struct alignas(16) FTile {
-    int wf_off;   // float offset of the fragment block [kc][32 lanes][4] of this 8-column tile
-    int b_off;    // float offset of the 8 bias values of this tile
-    int e_off;    // float offset of the one-hot rows (row a at e_off + a * e_ld), -1: none
-    short e_ld;
-    short in_off, out_off;  // column offsets inside a row (out_off: first of the 8 columns)
-    unsigned char kc;       // chunks of 16 inputs
-    unsigned char act;      // bit 0: ELU, bit 1: store the lo parts (a later layer reads the buffer as an operand)
-    unsigned char batch;    // on the first tile of a batch: tiles in the batch (same in_off / kc); else 0
-    unsigned char pad;
-    int pad2[2];
+// One 16 x 8 output tile of a Linear layer, all offsets in floats and final (no arithmetic left for the
+// device but adding the lane / group bases).
+struct alignas(16) FUnit {
+    int x_off;    // A operand: 2 * (column offset of the input buffer) inside the interleaved strip
+    int w_off;    // fragment block [kc][32 lanes][4] of this tile in the weight arena
+    int y_off;    // 2 * (column offset of the tile's 8 output columns)
+    int flags;    // bits 0..7: kc (chunks of 16 inputs), bit 8: ELU, bit 9: store lo parts, bit 10: one-hot rows
+    int b_off;    // 8 bias values of this tile
+    int e_off;    // one-hot rows: row a at e_off + a * e_ld
+    int e_ld;
+    int pad;
 };
-static_assert(sizeof(FTile) == 32, "FTile is two 16-byte words");
-
-struct FStage {
-    short first[GWARPS + 1];  // warp w of the group runs tiles [first[w], first[w + 1])
-    short row_op;             // 1: min-max normalise r_in -> r_out over r_n elements
-    short r_in, r_out, r_n;
-    short pad[3];
-};
-static_assert(sizeof(FStage) == 32, "FStage is two 16-byte words");
+static_assert(sizeof(FUnit) == 32, "FUnit is two 16-byte words");
 
 struct FastSched {
-    int n_stages, row_stride, n_tiles, w_floats;
+    int n_stages, row_stride, n_units, w_floats;
     short off_hidden, off_pl, off_vl, off_rl, off_tl, pad[3];
-    FStage st[FAST_MAX_STAGES];
-    FTile tiles[FAST_MAX_TILES];
+    int4 stage[FAST_MAX_STAGES];          // {row_op, 2 * r_in, 2 * r_out, r_n}; row_op 1: min-max normalise
+    int ulist[FAST_MAX_STAGES][GWARPS];   // units of warp w in stage s: first | count << 16
+    FUnit units[FAST_MAX_TILES];
 };
 static_assert(sizeof(FastSched) % 16 == 0, "FastSched is copied in 16-byte words");
 
 struct FastParams {
     int B, S, A, H, support, mask_absorbing, uniform_policy;
-    int blocks_per_tree, hidden_per_tree, max_rec, T, pb_stride;
+    int blocks_per_tree, hidden_per_tree, max_rec, T, pb_stride, w_lo;
+    float discount_f;  // (float)discount for the selection filter
     double discount;
     const double* pb_table;
     void* blocks; float* hidden_pool; TreeHeader* hdr; const double* rootprior; const int* rootact;
@@ -102,123 +96,134 @@ __device__ __forceinline__ void mma_tf32v(float (&d)[4], const uint4& a, unsigne
         : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b0), "r"(b1));
 }
 
-// One batch: NT tiles x 16 rows, all K. KCT > 0: compile-time chunk count (fully unrolled).
-template <int KCT, int NT>
-__device__ __forceinline__ void mma_batch(const FTile* __restrict__ tl, const float* __restrict__ W,
-                                          float* __restrict__ act, int rs, const int* __restrict__ row_action) {
-    const int lane = threadIdx.x & 31;
-    const int g = lane >> 2, t = lane & 3;
-    const int kc = KCT ? KCT : tl[0].kc;
-    const float* x = act + g * rs + 2 * tl[0].in_off + 4 * t;  // hi operand == the raw float32 activations
-    const float* xl = x + 8 * rs;                              // twin strip: lo parts
-    float dm[NT][4], dc[NT][4], de[NT][4];  // hi*hi, lo*hi, hi*lo: three independent mma chains per tile
-    const float* wb[NT];
-#pragma unroll
-    for (int i = 0; i < NT; ++i) {
-        const FTile& ti = tl[i];
-        wb[i] = W + ti.wf_off + lane * 4;
-        const float2 b = *reinterpret_cast<const float2*>(W + ti.b_off + 2 * t);
-        dm[i][0] = b.x; dm[i][1] = b.y; dm[i][2] = b.x; dm[i][3] = b.y;
-        if (ti.e_off >= 0) {  // one-hot action input == one gathered weight row (models.py:236-243)
-            const float2 e0 = *reinterpret_cast<const float2*>(W + ti.e_off + row_action[g] * ti.e_ld + 2 * t);
-            const float2 e1 = *reinterpret_cast<const float2*>(W + ti.e_off + row_action[g + 8] * ti.e_ld + 2 * t);
-            dm[i][0] += e0.x; dm[i][1] += e0.y; dm[i][2] += e1.x; dm[i][3] += e1.y;
+// ELU(alpha = 1) on the fast path: ex2.approx (2^-22 relative) keeps |error| < 5e-7 on (-inf, 0].
+__device__ __forceinline__ float elu_fast(float v) {
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fminf(v, 0.0f) * 1.4426950408889634f));
+    return v > 0.0f ? v : e - 1.0f;
+}
+
+// One unit: a 16 x 8 output tile over all K, by one warp. KCT > 0: compile-time chunk count, fully unrolled
+// (the compiler then batches every fragment load in front of the mma chain). wlo_off: float offset from a
+// weight fragment to its host-computed lo part (0: split the weights in registers).
+template <int KCT>
+__device__ __forceinline__ void mma_unit(const int4 ua, const int4 ub, const float* __restrict__ actL,
+                                         const float* __restrict__ wL, const float* __restrict__ wT, int lo_off,
+                                         int wlo_off, const int* __restrict__ row_action, int g) {
+    const int kc = KCT ? KCT : (ua.w & 0xFF);
+    const float* x = actL + ua.x;   // hi operand == the raw float32 activations; lo parts at + lo_off
+    const float* w = wL + ua.y;
+    float dm[4], dc[4] = {0.f, 0.f, 0.f, 0.f}, de[4] = {0.f, 0.f, 0.f, 0.f};  // hi*hi, lo*hi, hi*lo chains
+    {
+        const float2 b = *reinterpret_cast<const float2*>(wT + ub.x);
+        dm[0] = b.x; dm[1] = b.y; dm[2] = b.x; dm[3] = b.y;
+        if (ua.w & 0x400) {  // one-hot action input == one gathered weight row (models.py:236-243)
+            const float2 e0 = *reinterpret_cast<const float2*>(wT + ub.y + row_action[g] * ub.z);
+            const float2 e1 = *reinterpret_cast<const float2*>(wT + ub.y + row_action[g + 8] * ub.z);
+            dm[0] += e0.x; dm[1] += e0.y; dm[2] += e1.x; dm[3] += e1.y;
         }
-        dc[i][0] = dc[i][1] = dc[i][2] = dc[i][3] = 0.f;
-        de[i][0] = de[i][1] = de[i][2] = de[i][3] = 0.f;
     }
 #pragma unroll(KCT ? KCT : 2)
     for (int c = 0; c < kc; ++c) {
-        uint4 ah[2], al[2];
-#pragma unroll
-        for (int s2 = 0; s2 < 2; ++s2) {
-            ah[s2] = *reinterpret_cast<const uint4*>(x + 32 * c + 16 * s2);
-            al[s2] = *reinterpret_cast<const uint4*>(xl + 32 * c + 16 * s2);
+        const uint4 ah0 = *reinterpret_cast<const uint4*>(x + 32 * c), ah1 = *reinterpret_cast<const uint4*>(x + 32 * c + 16);
+        const uint4 al0 = *reinterpret_cast<const uint4*>(x + lo_off + 32 * c);
+        const uint4 al1 = *reinterpret_cast<const uint4*>(x + lo_off + 32 * c + 16);
+        const uint4 bh = *reinterpret_cast<const uint4*>(w + 128 * c);
+        uint4 bl;
+        if (wlo_off) {
+            bl = *reinterpret_cast<const uint4*>(w + wlo_off + 128 * c);
+        } else {
+            bl.x = __float_as_uint(tf32_lo(__uint_as_float(bh.x))); bl.y = __float_as_uint(tf32_lo(__uint_as_float(bh.y)));
+            bl.z = __float_as_uint(tf32_lo(__uint_as_float(bh.z))); bl.w = __float_as_uint(tf32_lo(__uint_as_float(bh.w)));
         }
-#pragma unroll
-        for (int i = 0; i < NT; ++i) {
-            const float4 Bv = *reinterpret_cast<const float4*>(wb[i] + c * 128);
-            const float bf[2][2] = {{Bv.x, Bv.y}, {Bv.z, Bv.w}};
-#pragma unroll
-            for (int s2 = 0; s2 < 2; ++s2) {
-                const unsigned bh0 = __float_as_uint(bf[s2][0]), bh1 = __float_as_uint(bf[s2][1]);
-                const unsigned bl0 = __float_as_uint(tf32_lo(bf[s2][0])), bl1 = __float_as_uint(tf32_lo(bf[s2][1]));
-                mma_tf32v(dm[i], ah[s2], bh0, bh1);
-                mma_tf32v(dc[i], al[s2], bh0, bh1);
-                mma_tf32v(de[i], ah[s2], bl0, bl1);
-            }
-        }
+        mma_tf32v(dm, ah0, bh.x, bh.y);
+        mma_tf32v(dc, al0, bh.x, bh.y);
+        mma_tf32v(de, ah0, bl.x, bl.y);
+        mma_tf32v(dm, ah1, bh.z, bh.w);
+        mma_tf32v(dc, al1, bh.z, bh.w);
+        mma_tf32v(de, ah1, bl.z, bl.w);
     }
-#pragma unroll
-    for (int i = 0; i < NT; ++i) {
-        const FTile& ti = tl[i];
-        float d0 = dm[i][0] + (dc[i][0] + de[i][0]), d1 = dm[i][1] + (dc[i][1] + de[i][1]);
-        float d2 = dm[i][2] + (dc[i][2] + de[i][2]), d3 = dm[i][3] + (dc[i][3] + de[i][3]);
-        if (ti.act & 1) {
-            d0 = elu(d0); d1 = elu(d1); d2 = elu(d2); d3 = elu(d3);
-        }
-        // {c0, c2, c1, c3} = {X[g][n], X[g+8][n], X[g][n+1], X[g+8][n+1]}, n = out_off + 2 t
-        float* y = act + g * rs + 2 * ti.out_off + 4 * t;
-        *reinterpret_cast<float4*>(y) = make_float4(d0, d2, d1, d3);
-        if (ti.act & 2)
-            *reinterpret_cast<float4*>(y + 8 * rs) = make_float4(tf32_lo(d0), tf32_lo(d2), tf32_lo(d1), tf32_lo(d3));
+    float d0 = dm[0] + (dc[0] + de[0]), d1 = dm[1] + (dc[1] + de[1]);
+    float d2 = dm[2] + (dc[2] + de[2]), d3 = dm[3] + (dc[3] + de[3]);
+    if (ua.w & 0x100) {
+        d0 = elu_fast(d0); d1 = elu_fast(d1); d2 = elu_fast(d2); d3 = elu_fast(d3);
     }
-}
-
-template <int NT>
-__device__ __forceinline__ void mma_batch_k(const FTile* tl, const float* W, float* act, int rs, const int* row_action) {
-    switch (tl[0].kc) {
-        case 2: mma_batch<2, NT>(tl, W, act, rs, row_action); break;
-        case 4: mma_batch<4, NT>(tl, W, act, rs, row_action); break;
-        default: mma_batch<0, NT>(tl, W, act, rs, row_action); break;
-    }
+    // {c0, c2, c1, c3} = {X[g][n], X[g+8][n], X[g][n+1], X[g+8][n+1]}, n = out column + 2 t
+    float* y = const_cast<float*>(actL) + ua.z;
+    *reinterpret_cast<float4*>(y) = make_float4(d0, d2, d1, d3);
+    if (ua.w & 0x200)  // a later layer reads this buffer as an mma operand
+        *reinterpret_cast<float4*>(y + lo_off) = make_float4(tf32_lo(d0), tf32_lo(d2), tf32_lo(d1), tf32_lo(d3));
 }
 
 // All stages of the schedule for the 16 rows of one group; called by the 8 warps of the group.
 __device__ __forceinline__ void fast_mlp(const FastSched& fs, const float* __restrict__ W, float* __restrict__ act,
                                          const int* __restrict__ row_action, const unsigned char* __restrict__ row_active,
-                                         int gt, int barid, unsigned long long* dbg) {
+                                         int gt, int barid, int wlo_off, unsigned long long* dbg) {
     const int rs = fs.row_stride;
-    const int wg = gt >> 5;
+    const int wg = gt >> 5, lane = gt & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const float* actL = act + g * rs + 4 * t;
+    const float* wL = W + lane * 4;
+    const float* wT = W + 2 * t;
+    const int lo_off = 8 * rs;
     const int n_stages = fs.n_stages;
+    // the descriptors of a stage are fetched before the barrier that ends the previous stage
+    int ul = fs.ulist[0][wg];
+    int4 ua = *reinterpret_cast<const int4*>(&fs.units[ul & 0xFFFF]);
+    int4 ub = *reinterpret_cast<const int4*>(&fs.units[ul & 0xFFFF].b_off);
     for (int s = 0; s < n_stages; ++s) {
-        const FStage& st = fs.st[s];
         long long d0 = 0, d1 = 0;
         if (dbg && threadIdx.x == 0) d0 = clock64();
-        int i = st.first[wg];
-        const int end = st.first[wg + 1];
-        while (i < end) {
-            const FTile* tl = fs.tiles + i;
-            const int nb = tl->batch;
-            if (nb == 1) mma_batch_k<1>(tl, W, act, rs, row_action);
-            else mma_batch_k<2>(tl, W, act, rs, row_action);
-            i += nb;
+        int u = ul & 0xFFFF;
+        const int uend = u + (ul >> 16);
+        long long q0 = 0, q1 = 0;
+        while (u < uend) {
+            const int kc = ua.w & 0xFF;
+            if (dbg && threadIdx.x == 0) q0 = clock64();
+            if (kc == 4) mma_unit<4>(ua, ub, actL, wL, wT, lo_off, wlo_off, row_action, g);
+            else if (kc == 2) mma_unit<2>(ua, ub, actL, wL, wT, lo_off, wlo_off, row_action, g);
+            else mma_unit<0>(ua, ub, actL, wL, wT, lo_off, wlo_off, row_action, g);
+            if (dbg && threadIdx.x == 0) {
+                q1 = clock64();
+                atomicAdd(dbg + 40, (unsigned long long)(q0 - d0));  // stage start -> unit start (dispatch)
+                atomicAdd(dbg + 41, (unsigned long long)(q1 - q0));  // the unit itself
+                atomicAdd(dbg + 43, 1ull);
+            }
+            if (++u < uend) {
+                ua = *reinterpret_cast<const int4*>(&fs.units[u]);
+                ub = *reinterpret_cast<const int4*>(&fs.units[u].b_off);
+            }
         }
-        if (st.row_op == 1) {
+        if (s + 1 < n_stages) {
+            ul = fs.ulist[s + 1][wg];
+            ua = *reinterpret_cast<const int4*>(&fs.units[ul & 0xFFFF]);
+            ub = *reinterpret_cast<const int4*>(&fs.units[ul & 0xFFFF].b_off);
+        }
+        const int4 sg = fs.stage[s];
+        if (sg.x == 1) {
             // models.py:223-231 / 248-255: (x - min) / scale, scale += 1e-5 only where scale < 1e-5
             const int row = gt >> 4, j = gt & 15;
-            const unsigned gmask = 0xFFFFu << (gt & 16);
-            if (row_active[row]) {
-                const float* x = act + (row & 7) * rs + (row >> 3) + 2 * st.r_in;
+            {   // both trees of a warp run this in lock step (full-mask shuffles); idle rows compute on stale data
+                const float* x = act + (row & 7) * rs + (row >> 3) + sg.y;
                 float mn = CUDART_INF_F, mx = -CUDART_INF_F;
-                for (int q = j; q < st.r_n; q += LPT) {
+                for (int q = j; q < sg.w; q += LPT) {
                     const float v = x[kofs(q)];
                     mn = fminf(mn, v);
                     mx = fmaxf(mx, v);
                 }
 #pragma unroll
                 for (int d = 1; d < LPT; d <<= 1) {
-                    mn = fminf(mn, __shfl_xor_sync(gmask, mn, d));
-                    mx = fmaxf(mx, __shfl_xor_sync(gmask, mx, d));
+                    mn = fminf(mn, __shfl_xor_sync(FULL, mn, d));
+                    mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, d));
                 }
                 float scale = __fsub_rn(mx, mn);
                 if (scale < 1e-5f) scale = __fadd_rn(scale, 1e-5f);
                 const float inv = __frcp_rn(scale);
-                float* y = act + (row & 7) * rs + (row >> 3) + 2 * st.r_out;
-                for (int q = j; q < st.r_n; q += LPT) {
+                float* y = act + (row & 7) * rs + (row >> 3) + sg.z;
+                for (int q = j; q < sg.w; q += LPT) {
                     const float v = __fmul_rn(__fsub_rn(x[kofs(q)], mn), inv);
                     y[kofs(q)] = v;
-                    y[kofs(q) + 8 * rs] = tf32_lo(v);
+                    y[kofs(q) + lo_off] = tf32_lo(v);
                 }
             }
         }
@@ -237,7 +242,7 @@ __device__ __forceinline__ void fast_mlp(const FastSched& fs, const float* __res
 // shuffle rounds. vl / rl / pl point at column 0 of the row inside the interleaved strip (column k at kofs(k)).
 __device__ __forceinline__ void decode_row(const float* __restrict__ vl, const float* __restrict__ rl,
                                            const float* __restrict__ pl, int support, int A, bool uniform, int j,
-                                           unsigned gmask, float& value, float& reward, float& prior) {
+                                           float& value, float& reward, float& prior) {
     const int n = 2 * support + 1;
     float mv = -CUDART_INF_F, mr = -CUDART_INF_F;
     for (int i = j; i < n; i += LPT) {
@@ -249,28 +254,28 @@ __device__ __forceinline__ void decode_row(const float* __restrict__ vl, const f
     float mp = pon ? lg : -CUDART_INF_F;
 #pragma unroll
     for (int d = 1; d < LPT; d <<= 1) {
-        mv = fmaxf(mv, __shfl_xor_sync(gmask, mv, d));
-        mr = fmaxf(mr, __shfl_xor_sync(gmask, mr, d));
-        mp = fmaxf(mp, __shfl_xor_sync(gmask, mp, d));
+        mv = fmaxf(mv, __shfl_xor_sync(FULL, mv, d));
+        mr = fmaxf(mr, __shfl_xor_sync(FULL, mr, d));
+        mp = fmaxf(mp, __shfl_xor_sync(FULL, mp, d));
     }
     float sv = 0.f, xv = 0.f, sr = 0.f, xr = 0.f;
     for (int i = j; i < n; i += LPT) {
-        const float ev = expf(__fsub_rn(vl[kofs(i)], mv));
-        const float er = expf(__fsub_rn(rl[kofs(i)], mr));
+        const float ev = __expf(__fsub_rn(vl[kofs(i)], mv));
+        const float er = __expf(__fsub_rn(rl[kofs(i)], mr));
         sv = __fadd_rn(sv, ev);
         xv = fmaf((float)(i - support), ev, xv);
         sr = __fadd_rn(sr, er);
         xr = fmaf((float)(i - support), er, xr);
     }
-    const float ep = pon ? expf(__fsub_rn(lg, mp)) : 0.0f;
+    const float ep = pon ? __expf(__fsub_rn(lg, mp)) : 0.0f;
     float sp = ep;
 #pragma unroll
     for (int d = 1; d < LPT; d <<= 1) {
-        sv = __fadd_rn(sv, __shfl_xor_sync(gmask, sv, d));
-        xv = __fadd_rn(xv, __shfl_xor_sync(gmask, xv, d));
-        sr = __fadd_rn(sr, __shfl_xor_sync(gmask, sr, d));
-        xr = __fadd_rn(xr, __shfl_xor_sync(gmask, xr, d));
-        sp = __fadd_rn(sp, __shfl_xor_sync(gmask, sp, d));
+        sv = __fadd_rn(sv, __shfl_xor_sync(FULL, sv, d));
+        xv = __fadd_rn(xv, __shfl_xor_sync(FULL, xv, d));
+        sr = __fadd_rn(sr, __shfl_xor_sync(FULL, sr, d));
+        xr = __fadd_rn(xr, __shfl_xor_sync(FULL, xr, d));
+        sp = __fadd_rn(sp, __shfl_xor_sync(FULL, sp, d));
     }
     value = inverse_value_transform(__fdiv_rn(xv, sv));
     reward = inverse_value_transform(__fdiv_rn(xr, sr));
@@ -281,7 +286,7 @@ __device__ __forceinline__ void decode_row(const float* __restrict__ vl, const f
 // Exact pUCT arg-max of one tree level in float64 (self_play.py:436-477), the reference's operation
 // order; out of line so that the float32 filter stays small. Lanes 0..7 of the tree hold the children.
 __device__ __noinline__ int select_exact(double pbN, double sqN, int vis, double vs, double prior, float rw,
-                                         double discount, double mn, double mx, bool on, unsigned gmask, int gl0,
+                                         double discount, double mn, double mx, bool on, int gl0,
                                          const unsigned char* tie_row, int T, int& k_tie) {
     MinMax mm;
     mm.mn = mn;
@@ -291,13 +296,13 @@ __device__ __noinline__ int select_exact(double pbN, double sqN, int vis, double
     double best = score;
 #pragma unroll
     for (int d = 1; d < GW; d <<= 1) {
-        const double o = shfl_xor_d(gmask, best, d);
+        const double o = shfl_xor_d(FULL, best, d);
         best = o > best ? o : best;
     }
-    best = shfl_d(gmask, best, gl0);  // lanes 8..15 hold no child: take the maximum of lanes 0..7
-    const unsigned tied = (__ballot_sync(gmask, on && score == best) >> gl0) & 0xFFu;
+    best = shfl_d(FULL, best, gl0);  // lanes 8..15 hold no child: take the maximum of lanes 0..7
+    const unsigned tied = (__ballot_sync(FULL, on && score == best) >> gl0) & 0xFFu;
     const int nt = __popc(tied);
-    if (nt == 1) return __ffs(tied) - 1;
+    if (nt <= 1) return __ffs(tied) - 1;
     int v = 0;  // self_play.py:444-450 with the external tie stream
     if (tie_row) v = tie_row[k_tie % T];
     k_tie++;
@@ -356,14 +361,17 @@ __global__ void __launch_bounds__(G * GTHREADS, 2 / G) search_fast_kernel(const 
     __syncthreads();
     const FastSched& fs = *fsp;
     const int rs = fs.row_stride;
+    // p.w_lo: the arena is followed by the lo parts of the weights (same fragment layout) -- shared memory permitting
+    const int wlo_off = p.w_lo ? fs.w_floats : 0;
+    const int w_total = fs.w_floats + wlo_off;
     if (!fed) {
         const float4* src = reinterpret_cast<const float4*>(p.wfrag);
         float4* dst = reinterpret_cast<float4*>(wsm);
-        for (int i = tid; i < (fs.w_floats >> 2); i += THREADS) dst[i] = __ldg(src + i);
+        for (int i = tid; i < (w_total >> 2); i += THREADS) dst[i] = __ldg(src + i);
     }
     const int grp = tid / GTHREADS, gt = tid % GTHREADS;
     // per group: strip of 8 interleaved row pairs (rs floats each) + its twin of lo parts, then the row tables
-    float* act = wsm + fs.w_floats + grp * (GT * rs + GT + GT + GT * PATH_LEVELS);
+    float* act = wsm + w_total + grp * (GT * rs + GT + GT + GT * PATH_LEVELS);
     int* row_action = reinterpret_cast<int*>(act + GT * rs);
     unsigned char* row_active = reinterpret_cast<unsigned char*>(row_action + GT);
     const int row = gt >> 4;                                 // tree of the group == row of the strip
@@ -372,7 +380,6 @@ __global__ void __launch_bounds__(G * GTHREADS, 2 / G) search_fast_kernel(const 
     const int barid = 1 + grp;
 
     const int lane = tid & 31, j = tid & 15;
-    const unsigned gmask = 0xFFFFu << (lane & 16);
     const int gl0 = lane & 16;
     const int b = (blockIdx.x * G + grp) * GT + row;
     const bool valid = b < p.B;
@@ -381,6 +388,11 @@ __global__ void __launch_bounds__(G * GTHREADS, 2 / G) search_fast_kernel(const 
 
     Block* blocks = reinterpret_cast<Block*>(p.blocks) + (size_t)(valid ? b : 0) * p.blocks_per_tree;
     float* hpool = p.hidden_pool + (size_t)(valid ? b : 0) * p.hidden_per_tree * H;
+    // Opaque to the compiler from here on: at the 128-register cap it would otherwise re-derive these bases
+    // (64-bit multiplies) inside every level of the selection loop instead of keeping them.
+    asm volatile("" : "+l"(blocks), "+l"(hpool));
+    __builtin_assume(__isGlobal(blocks));
+    __builtin_assume(__isGlobal(hpool));
     const float* fed_rec = fed ? p.fed + (size_t)(valid ? b : 0) * p.max_rec * REC : nullptr;
     float* trace_rec = p.trace ? p.trace + (size_t)(valid ? b : 0) * p.max_rec * REC : nullptr;
 
@@ -399,7 +411,6 @@ __global__ void __launch_bounds__(G * GTHREADS, 2 / G) search_fast_kernel(const 
         }
     }
     const float root_prior_f = (float)root_prior;
-    const float gammaf = (float)discount;
     __syncthreads();
 
     for (int it = 0; it < p.S; ++it) {
@@ -408,8 +419,9 @@ __global__ void __launch_bounds__(G * GTHREADS, 2 / G) search_fast_kernel(const 
         long long tc0 = 0, tc1 = 0, tc2 = 0, tc3 = 0;
         if (p.phase_cycles && tid == 0) tc0 = clock64();
         // ================= selection, self_play.py:388-397 =================
+        // The two trees of a warp descend in lock step (a finished tree idles), so every shuffle is full-mask.
         int node = 0, slot = 0, depth = 0, Np = root_visit;
-        if (active) {
+        {
             // float32 image of MinMaxStats.normalize for the filter: (x - mnf) * idf, identity while max <= min
             float mnf = 0.0f, idf = 1.0f;
             if (mm.mx > mm.mn) {
@@ -417,66 +429,69 @@ __global__ void __launch_bounds__(G * GTHREADS, 2 / G) search_fast_kernel(const 
                 idf = rcp_approx((float)__dsub_rn(mm.mx, mm.mn));
             }
             const float amnf = fabsf(mnf);
-            while (true) {
+            bool walking = active;
+            while (__any_sync(FULL, walking)) {
+                // straight-line level: every lane loads (lanes past the children re-read child 0), masks decide
                 const Block* blk = blocks + node;
                 const int nch = (node == 0) ? n_root : A;
-                const bool on = j < nch;
-                int vis = 0, ch = -1;
-                double vs = 0.0;
-                float rw = 0.0f, prf = 0.0f;
-                if (on) {
-                    vis = blk->visit[j];
-                    ch = blk->child[j];
-                    vs = blk->vsum[j];
-                    rw = blk->reward[j];
-                    prf = (node == 0) ? root_prior_f : blk->prior[j];
-                    // pull every expanded child's block towards L1 while this level is scored
-                    if (ch >= 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(blocks + ch));
-                } else if (!fed && j >= GW) {
-                    // the idle lanes pull this node's hidden state in: it is the MLP input if the descent ends here
-                    const int line = j - GW;
-                    if (line * 32 < H) asm volatile("prefetch.global.L1 [%0];" ::"l"(hpool + (size_t)node * H + line * 32));
-                }
+                const bool on = walking && j < nch;
+                const int jc = j < NC ? j : 0;
+                const int vis = blk->visit[jc];
+                const int ch = on ? blk->child[jc] : -1;
+                const double vs = blk->vsum[jc];
+                const float rw = blk->reward[jc];
+                const float prf = (node == 0) ? root_prior_f : blk->prior[jc];
+                // (prefetching the children's blocks / the node's hidden state towards L1 here was measured: no effect)
                 // ---- float32 filter: score_j +- E_j encloses the reference's float64 ucb_score; when one
                 // interval lies strictly above all others, the exact arg-max is that child and it is not tied.
-                float lo = -CUDART_INF_F, hi = -CUDART_INF_F;
-                if (on) {
-                    const float ps = pbf[Np] * rcp_approx((float)(vis + 1)) * prf;
-                    float V = 0.0f, aux = 0.0f;
-                    if (vis > 0) {
-                        const float gq = gammaf * ((float)vs * rcp_approx((float)vis));
-                        V = ((gq + rw) - mnf) * idf;
-                        aux = idf * (fabsf(gq) + fabsf(rw) + amnf);
-                    }
-                    const float sc = ps + V;
-                    const float E = fmaf(1.9073486e-6f, fabsf(ps) + fabsf(V) + aux, 1e-30f);  // 16 * 2^-23 * magnitudes
-                    lo = sc - E;
-                    hi = sc + E;
+                const float ps = pbf[Np] * rcp_approx((float)(vis + 1)) * prf;
+                const float gq = p.discount_f * ((float)vs * rcp_approx((float)vis));  // vis == 0: discarded below
+                float V = ((gq + rw) - mnf) * idf;
+                float aux = idf * (fabsf(gq) + fabsf(rw) + amnf);
+                if (vis <= 0) {
+                    V = 0.0f;
+                    aux = 0.0f;
                 }
+                const float sc = ps + V;
+                const float E = fmaf(1.9073486e-6f, fabsf(ps) + fabsf(V) + aux, 1e-30f);  // 16 * 2^-23 * magnitudes
+                const float lo = on ? sc - E : -CUDART_INF_F;
+                const float hi = on ? sc + E : -CUDART_INF_F;
                 float m1 = lo;
 #pragma unroll
-                for (int d = 1; d < GW; d <<= 1) m1 = fmaxf(m1, __shfl_xor_sync(gmask, m1, d));
-                m1 = __shfl_sync(gmask, m1, gl0);
-                const unsigned cand = (__ballot_sync(gmask, on && hi >= m1) >> gl0) & 0xFFu;
-                if (__popc(cand) == 1) {
-                    slot = __ffs(cand) - 1;
-                } else {  // near-tie, exact tie or non-finite filter value: decide in float64
-                    slot = select_exact(pb[Np], sq[Np], vis, vs, (node == 0) ? root_prior : (double)prf, rw, discount, mm.mn,
-                                        mm.mx, on, gmask, gl0, p.tie ? p.tie + (size_t)b * p.T : nullptr, p.T, k_tie);
-                    n_exact++;
+                for (int d = 1; d < GW; d <<= 1) m1 = fmaxf(m1, __shfl_xor_sync(FULL, m1, d));
+                m1 = __shfl_sync(FULL, m1, gl0);
+                const unsigned cand = (__ballot_sync(FULL, on && hi >= m1) >> gl0) & 0xFFu;
+                int sl = __ffs(cand) - 1;
+                const bool need = walking && __popc(cand) != 1;
+                if (__any_sync(FULL, need)) {  // near-tie, exact tie or non-finite filter value: decide in float64
+                    int k2 = k_tie;
+                    const int se = select_exact(pb[Np], sq[Np], vis, vs, (node == 0) ? root_prior : (double)prf, rw, discount,
+                                                mm.mn, mm.mx, on && need, gl0, p.tie ? p.tie + (size_t)b * p.T : nullptr, p.T, k2);
+                    if (need) {
+                        sl = se;
+                        k_tie = k2;
+                        n_exact++;
+                    }
                 }
-                const int vis_sel = __shfl_sync(gmask, vis, gl0 + slot);
-                const int child_sel = __shfl_sync(gmask, ch, gl0 + slot);
-                if (j == 0 && depth < PATH_LEVELS) path[depth] = (node << 8) | slot;
-                depth++;
-                if (child_sel < 0) break;
-                node = child_sel;
-                Np = vis_sel;
+                const int vis_sel = __shfl_sync(FULL, vis, (gl0 + sl) & 31);
+                const int child_sel = __shfl_sync(FULL, ch, (gl0 + sl) & 31);
+                if (walking) {
+                    slot = sl;
+                    if (j == 0 && depth < PATH_LEVELS) path[depth] = (node << 8) | slot;
+                    depth++;
+                    if (child_sel < 0) {
+                        walking = false;
+                    } else {
+                        node = child_sel;
+                        Np = vis_sel;
+                    }
+                }
             }
         }
+        const int ract = __shfl_sync(FULL, root_act, (gl0 + slot) & 31);
         int action = 0;
         if (active) {
-            action = (node == 0) ? __shfl_sync(gmask, root_act, gl0 + slot) : slot;
+            action = (node == 0) ? ract : slot;
             if (depth > max_depth) max_depth = depth;
             depth_total += depth;
         }
@@ -501,14 +516,11 @@ __global__ void __launch_bounds__(G * GTHREADS, 2 / G) search_fast_kernel(const 
             if (p.phase_cycles && tid == 0) tc1 = clock64();
             group_barrier(barid);
             if (p.phase_cycles && tid == 0) tc2 = clock64();
-            fast_mlp(fs, wsm, act, row_action, row_active, gt, barid, p.phase_cycles);
+            fast_mlp(fs, wsm, act, row_action, row_active, gt, barid, wlo_off, p.phase_cycles);
             if (p.phase_cycles && tid == 0) tc3 = clock64();
-            if (active) {
-                const float* r = rowp;
-                decode_row(r + 2 * fs.off_vl, r + 2 * fs.off_rl, r + 2 * fs.off_pl, p.support, A, p.uniform_policy != 0, j,
-                           gmask, value, reward, prior);
-                if (p.mask_absorbing) terminal = r[2 * fs.off_tl];
-            }
+            decode_row(rowp + 2 * fs.off_vl, rowp + 2 * fs.off_rl, rowp + 2 * fs.off_pl, p.support, A, p.uniform_policy != 0,
+                       j, value, reward, prior);
+            if (p.mask_absorbing) terminal = rowp[2 * fs.off_tl];
         } else if (active) {
             const float* fr = fed_rec + (size_t)n_rec * REC;
             value = fr[1];
@@ -518,23 +530,23 @@ __global__ void __launch_bounds__(G * GTHREADS, 2 / G) search_fast_kernel(const 
         }
 
         // ================= expansion + backup =================
-        if (active) {
-            if (trace_rec && n_rec < p.max_rec) {
+        {
+            const float pj = __shfl_sync(FULL, prior, (gl0 + ((j - 4) & 15)) & 31);
+            if (active && trace_rec && n_rec < p.max_rec) {
                 float* tr = trace_rec + (size_t)n_rec * REC;
                 float tv = 0.0f;
                 if (j == 0) tv = 1.0f;
                 if (j == 1) tv = value;
                 if (j == 2) tv = reward;
                 if (j == 3) tv = terminal;
-                const float pj = __shfl_sync(gmask, prior, gl0 + ((j - 4) & 15));
                 if (j >= 4 && j < 4 + A) tv = pj;
                 tr[j] = tv;  // REC == LPT == 16
             }
-            n_rec++;
+            if (active) n_rec++;
             Block* pblk = blocks + node;
             const bool masked = p.mask_absorbing && (terminal >= 0.0f);  // self_play.py:408-417
             double v = masked ? 0.0 : (double)value;
-            if (!masked) {
+            if (active && !masked) {
                 // ---- Node.expand, self_play.py:524-538 ----
                 const int nb = n_blocks++;
                 Block* nblk = blocks + nb;
@@ -560,16 +572,18 @@ __global__ void __launch_bounds__(G * GTHREADS, 2 / G) search_fast_kernel(const 
                     }
                 }
             }
-            __syncwarp(gmask);
+            __syncwarp();
             // ---- backup, self_play.py:485-490, lane-parallel: entry e = 0 is the root, entry e >= 1 the child chosen
             // at level e - 1 of the descent. The value chain v <- r + discount * v is replayed by every lane (one
             // shuffle + 2 flops per level); the expensive per-node part (value_sum / visit_count for MinMaxStats)
-            // runs once, one entry per lane.
-            if (depth <= PATH_LEVELS) {
+            // runs once, one entry per lane. Both trees of the warp run it together (warp-uniform trip counts).
+            const int dact = active ? depth : 0;
+            const int dmax = max(dact, __shfl_xor_sync(FULL, dact, 16));
+            if (dmax <= PATH_LEVELS) {
                 double pmn = CUDART_INF, pmx = -CUDART_INF;
-                for (int r = depth >> 4; r >= 0; --r) {
+                for (int r = dmax >> 4; r >= 0; --r) {
                     const int e = LPT * r + j;
-                    const bool mine = e <= depth;
+                    const bool mine = active && e <= depth;
                     Block* bk = blocks;
                     int cs = 0, vis0 = root_visit;
                     double vs0 = root_vsum;
@@ -583,11 +597,13 @@ __global__ void __launch_bounds__(G * GTHREADS, 2 / G) search_fast_kernel(const 
                         rwf = bk->reward[cs];
                     }
                     double myv = 0.0;
-                    const int e_hi = min(depth, LPT * r + LPT - 1), e_lo = max(LPT * r, 1);
+                    const int e_hi = min(dmax, LPT * r + LPT - 1), e_lo = max(LPT * r, 1);
                     for (int ee = e_hi; ee >= e_lo; --ee) {
-                        const double rwe = (double)__shfl_sync(gmask, rwf, gl0 + (ee & (LPT - 1)));
-                        if (ee == e) myv = v;
-                        v = __dadd_rn(rwe, __dmul_rn(discount, v));
+                        const double rwe = (double)__shfl_sync(FULL, rwf, gl0 + (ee & (LPT - 1)));
+                        if (ee <= depth) {
+                            if (ee == e) myv = v;
+                            v = __dadd_rn(rwe, __dmul_rn(discount, v));
+                        }
                     }
                     if (e == 0) myv = v;
                     if (mine) {
@@ -602,20 +618,22 @@ __global__ void __launch_bounds__(G * GTHREADS, 2 / G) search_fast_kernel(const 
                         pmx = pmx > x ? pmx : x;
                     }
                 }
-                root_vsum = __dadd_rn(root_vsum, v);
-                root_visit += 1;
 #pragma unroll
                 for (int d = 1; d < LPT; d <<= 1) {
-                    const double on_ = shfl_xor_d(gmask, pmn, d), ox_ = shfl_xor_d(gmask, pmx, d);
+                    const double on_ = shfl_xor_d(FULL, pmn, d), ox_ = shfl_xor_d(FULL, pmx, d);
                     pmn = on_ < pmn ? on_ : pmn;
                     pmx = ox_ > pmx ? ox_ : pmx;
                 }
-                mm.mn = mm.mn < pmn ? mm.mn : pmn;
-                mm.mx = mm.mx > pmx ? mm.mx : pmx;
-            } else {
+                if (active) {
+                    root_vsum = __dadd_rn(root_vsum, v);
+                    root_visit += 1;
+                    mm.mn = mm.mn < pmn ? mm.mn : pmn;
+                    mm.mx = mm.mx > pmx ? mm.mx : pmx;
+                }
+            } else if (active) {
                 backup_walk(blocks, node, slot, v, discount, mm, root_vsum, root_visit);
             }
-            n_sims++;
+            if (active) n_sims++;
         }
         if (p.phase_cycles && tid == 0 && !fed) {
             const long long tc4 = clock64();
@@ -626,7 +644,7 @@ __global__ void __launch_bounds__(G * GTHREADS, 2 / G) search_fast_kernel(const 
             atomicAdd(p.phase_cycles + 4, 1ull);
         }
         // a row's strip is re-filled by the lanes that read it; the last stage barrier ordered all tiles
-        __syncwarp(gmask);
+        __syncwarp();
     }
 
     // ================= outputs: what consumers read from `root` =================
@@ -648,7 +666,7 @@ __global__ void __launch_bounds__(G * GTHREADS, 2 / G) search_fast_kernel(const 
             if (p.child_prior) p.child_prior[(size_t)b * A + j] = 0.0;
             if (p.child_reward) p.child_reward[(size_t)b * A + j] = 0.0;
         }
-        __syncwarp(gmask);
+        __syncwarp();
         if (j < n_root) {
             const int a = root_act;
             const int vis = rb->visit[j];
