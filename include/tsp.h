@@ -40,7 +40,7 @@ enum {
     TSP_ENODEVICE = -2,   /* no CUDA device / wrong architecture */
     TSP_ECUDA = -3,       /* CUDA runtime error, text in tsp_last_error */
     TSP_ENOMEM = -4,
-    TSP_ENOTIMPL = -5,    /* e.g. > 1 player (self_play.py:503 raises NotImplementedError for > 2) */
+    TSP_ENOTIMPL = -5,    /* > 2 players (self_play.py:503 raises NotImplementedError) */
     TSP_ESTATE = -6       /* weights not loaded / not finalized */
 };
 
@@ -74,7 +74,8 @@ typedef struct {
     int32_t support_size;          /* config.support_size */
     int32_t n_futures;             /* config.n_futures (stochastic variants), else 1 */
     int32_t mask_absorbing_states; /* config.mask_absorbing_states, self_play.py:415 */
-    int32_t num_players;           /* len(config.players); only 1 is implemented */
+    int32_t num_players;           /* len(config.players): 1, or 2 for the deterministic search (self_play.py:469-472,
+                                      492-500); > 2 -> TSP_ENOTIMPL like the reference's NotImplementedError */
     double discount;               /* config.discount */
     double pb_c_base;              /* config.pb_c_base */
     double pb_c_init;              /* config.pb_c_init */

@@ -34,6 +34,9 @@ CASES = [
     ("risk_s25", "roundabout_env_ttc_flat_risk_sensitive", 25, 16, {}),
     ("risk_s25_legal", "roundabout_env_ttc_flat_risk_sensitive", 25, 8, {"legal": True}),
     ("cross_merge_s200", "cross_merge_env", 200, 4, {}),
+    # two-player backup / ucb branch (self_play.py:469-472, 492-500); to_play alternates over the roots
+    ("roundabout_s25_twoplayer", "roundabout_env_ttc_flat", 25, 12, {"players": [0, 1]}),
+    ("roundabout_s25_twoplayer_mask", "roundabout_env_ttc_flat", 25, 8, {"players": [0, 1], "mask": "adaptive", "legal": True}),
 ]
 
 
@@ -41,6 +44,8 @@ def make_case(name, game, S, N, opt, seed):
     cfg = get_config(game, num_simulations=S)
     if opt.get("mask"):
         cfg = cfg.replace(mask_absorbing_states=True)
+    if opt.get("players"):
+        cfg = cfg.replace(players=list(opt["players"]))
     ref = RL.load_reference()
     torch = ref.torch
     model = RL.build_model(cfg, seed)
@@ -49,7 +54,15 @@ def make_case(name, game, S, N, opt, seed):
         # branch (self_play.py:415-417) actually fires in some evaluations
         sd = model.state_dict()
         key = [k for k in sd if k.startswith("dynamics_terminal_network") and k.endswith("bias")][-1]
-        sd[key] = sd[key] + 0.07
+        lift = 0.07
+        if opt.get("mask") == "adaptive":  # shift so that about a third of the evaluations are terminal
+            with torch.no_grad():
+                o = torch.rand(512, cfg.stacked_observations * 2 + 1, 1, cfg.observation_shape[2])
+                hs = model.initial_inference(o)[5]
+                acts = torch.randint(0, len(cfg.action_space), (512, 1))
+                term = model.recurrent_inference(hs, acts)[2].reshape(-1)  # depth-1 evaluations
+            lift = -float(torch.quantile(term, 0.65))
+        sd[key] = sd[key] + lift
         model.load_state_dict(sd)
     A = len(cfg.action_space)
     variant = variant_of(cfg)
@@ -76,6 +89,7 @@ def make_case(name, game, S, N, opt, seed):
     )
     add_noise = not opt.get("no_noise", False)
     uniform = bool(opt.get("uniform_policy", False))
+    to_play = numpy.array([i % len(cfg.players) for i in range(N)], numpy.int32)
     for i in range(N):
         if opt.get("legal"):
             k = int(rng.integers(1, A + 1))
@@ -88,7 +102,7 @@ def make_case(name, game, S, N, opt, seed):
         noise[i, :len(la)] = nz
         r = RL.run_reference(cfg, model, obs[i].reshape(cfg.stacked_observations * 2 + 1, 1, -1), legal_actions=la,
                              noise=nz, tie=tie[i], chance=chance[i], add_exploration_noise=add_noise,
-                             uniform_policy=uniform)
+                             uniform_policy=uniform, to_play=int(to_play[i]))
         for k2 in ("visit_counts", "root_value", "child_value", "child_prior", "child_reward", "max_tree_depth",
                    "root_predicted_value", "n_nodes", "n_tie_draws", "n_chance_draws", "root_record",
                    "root_hidden"):
@@ -144,10 +158,10 @@ def make_case(name, game, S, N, opt, seed):
     weights = {"w:" + k: v for k, v in RL.state_dict_numpy(model).items()
                if not k.startswith("reconstruction_network") and not k.startswith("transition_posterior")}
     meta = dict(game=game, S=S, N=N, seed=seed, add_noise=add_noise, uniform_policy=uniform,
-                mask_absorbing_states=bool(opt.get("mask", False)))
+                mask_absorbing_states=bool(opt.get("mask", False)), players=list(cfg.players))
     path = os.path.join(OUT_DIR, name + ".npz")
     numpy.savez_compressed(
-        path, obs=obs, legal=legal, n_legal=n_legal, noise=noise, tie=tie, chance=chance,
+        path, obs=obs, legal=legal, n_legal=n_legal, noise=noise, tie=tie, chance=chance, to_play=to_play,
         meta=numpy.array(repr(meta)), **{"out:" + k: v for k, v in out.items()},
         **{"net:" + k: v for k, v in net.items()}, **weights)
     return path, out
@@ -155,7 +169,10 @@ def make_case(name, game, S, N, opt, seed):
 
 def main():
     os.makedirs(OUT_DIR, exist_ok=True)
+    only = set(sys.argv[1:])  # optional fixture names: the committed fixtures are not rewritten needlessly
     for i, (name, game, S, N, opt) in enumerate(CASES):
+        if only and name not in only:
+            continue
         path, out = make_case(name, game, S, N, opt, seed=i)
         print("%-26s %8.1f KB  visits[0]=%s depth<=%d records<=%d" % (
             name, os.path.getsize(path) / 1024.0, out["visit_counts"][0], out["max_tree_depth"].max(),

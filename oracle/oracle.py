@@ -46,7 +46,7 @@ class _RunArgs(ctypes.Structure):
         ("visit_counts", _P), ("root_value", _P), ("child_value", _P), ("child_prior", _P),
         ("child_reward", _P), ("max_depth", _P), ("root_pred_value", _P), ("root_hidden", _P),
         ("n_records", _P), ("n_nodes", _P), ("trace_root", _P), ("trace_records", _P),
-        ("n_threads", ctypes.c_int),
+        ("n_threads", ctypes.c_int), ("to_play", _P),
     ]
 
 
@@ -177,7 +177,7 @@ class Oracle:
     def run(self, num_simulations, observations=None, legal_actions=None, num_legal=None, noise=None,
             tie=None, chance=None, add_exploration_noise=True, uniform_policy=False,
             fed_root=None, fed_records=None, trace=False, max_records=None, n_threads=0, B=None,
-            want_root_hidden=False):
+            want_root_hidden=False, to_play=None):
         S = int(num_simulations)
         A = self.A
         keep = []
@@ -210,6 +210,7 @@ class Oracle:
         legal_actions = prep(legal_actions, numpy.int32, (B, A))
         num_legal = prep(num_legal, numpy.int32, (B,))
         noise = prep(noise, numpy.float64, (B, A))
+        to_play = prep(to_play, numpy.int32, (B,))
         tie = prep(tie, numpy.uint8)
         T = 0 if tie is None else tie.reshape(B, -1).shape[1]
         chance = prep(chance, numpy.uint8)
@@ -237,7 +238,7 @@ class Oracle:
                      _ptr(out["visit_counts"]), _ptr(out["root_value"]), _ptr(out["child_value"]),
                      _ptr(out["child_prior"]), _ptr(out["child_reward"]), _ptr(out["max_tree_depth"]),
                      _ptr(out["root_predicted_value"]), _ptr(root_hidden), _ptr(out["n_records"]),
-                     _ptr(out["n_nodes"]), _ptr(trace_root), _ptr(trace_records), int(n_threads))
+                     _ptr(out["n_nodes"]), _ptr(trace_root), _ptr(trace_records), int(n_threads), _ptr(to_play))
         rc = self.lib.orc_run(_P(self.net), ctypes.byref(a))
         if rc != 0:
             raise RuntimeError("oracle run failed with code %d" % rc)

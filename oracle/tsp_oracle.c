@@ -60,7 +60,7 @@ typedef struct {
     int support_size;  /* s; bins = 2s+1 */
     int n_futures;     /* nf (variants 1,2) */
     int mask_absorbing_states;
-    int num_players;   /* only 1 is restated */
+    int num_players;   /* 1 or 2 (deterministic MCTS only; the chance-node variants assert 1) */
     double discount;
     double pb_c_base;
     double pb_c_init;
@@ -304,7 +304,7 @@ typedef struct Node {
     int visit_count;
     int kind;
     int n_children; /* 0 = not expanded */
-    int depth_dummy;
+    int to_play;    /* Node.to_play: -1 until expanded (self_play.py:509, 529) */
     double prior;
     double value_sum; /* variants 0,1: sum; variant 2: the `.value` attribute */
     double reward;
@@ -336,6 +336,7 @@ static Node *node_new(Arena *a, int kind, double prior) {
     Node *n = (Node *)arena_alloc(a, sizeof(Node));
     n->kind = kind;
     n->prior = prior;
+    n->to_play = -1;
     return n;
 }
 
@@ -368,6 +369,8 @@ static double ucb_score(const orc_config *c, const Node *parent, const Node *chi
     if (child->visit_count > 0) {
         if (c->variant == 1)
             value_score = minmax_normalize(mm, node_value(child, 1));
+        else if (c->variant == 0 && c->num_players != 1) /* self_play.py:469-472: -child.value() for two players */
+            value_score = minmax_normalize(mm, child->reward + c->discount * -node_value(child, 0));
         else
             value_score = minmax_normalize(mm, child->reward + c->discount * node_value(child, c->variant));
     } else {
@@ -445,6 +448,7 @@ typedef struct {
     const float *fed_root;
     const float *fed_records;
     int max_records;
+    int to_play;          /* MCTS.run argument (root player) */
 } TreeJob;
 
 static void rec_clear(float *r) {
@@ -489,6 +493,7 @@ static int run_tree(const TreeJob *job, const float *obs, const int *legal, int 
     }
     if (job->root_hidden && root_h) memcpy(job->root_hidden, root_h, sizeof(float) * H);
     expand_state(ar, root, variant == 0 ? KIND_STATE : KIND_TRANSITION, legal, n_legal, 0.0, pri, root_h);
+    root->to_play = job->to_play;
     if (job->add_noise) { /* self_play.py:540-549 */
         const double frac = c->root_exploration_fraction;
         for (int i = 0; i < n_legal; ++i)
@@ -506,6 +511,7 @@ static int run_tree(const TreeJob *job, const float *obs, const int *legal, int 
     while (num_sims < job->S) {
         Node *node = root;
         int depth = 0, slot = 0, plen = 0;
+        int virtual_to_play = job->to_play;
         path[plen++] = node;
         while (node->n_children > 0) {
             depth++;
@@ -516,6 +522,11 @@ static int run_tree(const TreeJob *job, const float *obs, const int *legal, int 
             node = node->children[slot];
             if (plen >= path_cap) return -2;
             path[plen++] = node;
+            /* players play turn by turn, self_play.py:393-397 (config.players == [0, .., n-1]) */
+            if (virtual_to_play + 1 < c->num_players)
+                virtual_to_play = virtual_to_play + 1;
+            else
+                virtual_to_play = 0;
         }
         Node *parent = path[plen - 2];
         const int action = parent->child_action[slot];
@@ -556,16 +567,28 @@ static int run_tree(const TreeJob *job, const float *obs, const int *legal, int 
                 value = 0.0;
             } else {
                 expand_state(ar, node, KIND_STATE, NULL, A, (double)r, pri, h);
+                node->to_play = virtual_to_play; /* Node.expand, self_play.py:529 */
                 n_nodes += A;
                 value = (double)v;
             }
-            /* self_play.py:485-490 */
-            for (int i = plen - 1; i >= 0; --i) {
-                Node *x = path[i];
-                x->value_sum += value;
-                x->visit_count += 1;
-                minmax_update(&mm, x->reward + c->discount * node_value(x, 0));
-                value = x->reward + c->discount * value;
+            if (c->num_players == 1) {
+                /* self_play.py:485-490 */
+                for (int i = plen - 1; i >= 0; --i) {
+                    Node *x = path[i];
+                    x->value_sum += value;
+                    x->visit_count += 1;
+                    minmax_update(&mm, x->reward + c->discount * node_value(x, 0));
+                    value = x->reward + c->discount * value;
+                }
+            } else {
+                /* self_play.py:492-500 */
+                for (int i = plen - 1; i >= 0; --i) {
+                    Node *x = path[i];
+                    x->value_sum += (x->to_play == virtual_to_play) ? value : -value;
+                    x->visit_count += 1;
+                    minmax_update(&mm, x->reward + c->discount * -node_value(x, 0));
+                    value = ((x->to_play == virtual_to_play) ? -x->reward : x->reward) + c->discount * value;
+                }
             }
             num_sims++;
             (void)do_backprop;
@@ -735,6 +758,7 @@ typedef struct {
     float *trace_root;       /* [B][REC] or NULL */
     float *trace_records;    /* [B][max_records][REC] or NULL */
     int n_threads;           /* 0 = OpenMP default */
+    const int32_t *to_play;  /* [B] MCTS.run's to_play per root, or NULL = 0 */
 } orc_run_args;
 
 #include <pthread.h>
@@ -776,6 +800,7 @@ static void *worker_main(void *p) {
             memset(&job, 0, sizeof(job));
             job.net = net;
             job.S = a->S;
+            job.to_play = a->to_play ? a->to_play[b] : 0;
             job.add_noise = a->add_noise;
             job.uniform_policy = a->uniform_policy;
             job.visit_counts = a->visit_counts + (size_t)b * A;
@@ -818,7 +843,7 @@ static void *worker_main(void *p) {
 int orc_run(const orc_net *net, const orc_run_args *a) {
     const orc_config *c = &net->cfg;
     const int A = c->num_actions, H = c->encoding_size;
-    if (c->num_players != 1) return -10;
+    if (c->num_players != 1 && !(c->num_players == 2 && c->variant == 0)) return -10;
     if (A > ORC_MAX_ACTIONS) return -11;
     const int iters_cap = (c->variant == 0) ? a->S : a->S * (A + 2) + A + 2;
     const size_t node_bytes = sizeof(Node) + 64;

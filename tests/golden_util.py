@@ -25,17 +25,20 @@ class Golden:
         self.state_dict = {k[2:]: z[k] for k in z.files if k.startswith("w:")}
         for k in ("obs", "legal", "n_legal", "noise", "tie", "chance"):
             setattr(self, k, z[k])
+        self.to_play = z["to_play"] if "to_play" in z.files else None
         self.S = int(self.meta["S"])
         self.N = int(self.meta["N"])
         cfg = get_config(self.meta["game"], num_simulations=self.S)
         if self.meta.get("mask_absorbing_states"):
             cfg = cfg.replace(mask_absorbing_states=True)
+        if len(self.meta.get("players", [0])) != 1:
+            cfg = cfg.replace(players=list(self.meta["players"]))
         self.config = cfg
 
     def run_kwargs(self):
         return dict(legal_actions=self.legal, num_legal=self.n_legal, noise=self.noise, tie=self.tie,
                     chance=self.chance, add_exploration_noise=bool(self.meta["add_noise"]),
-                    uniform_policy=bool(self.meta["uniform_policy"]))
+                    uniform_policy=bool(self.meta["uniform_policy"]), to_play=self.to_play)
 
 
 TREE_KEYS_EXACT = ("visit_counts", "root_value", "child_value", "child_prior", "child_reward", "max_tree_depth")

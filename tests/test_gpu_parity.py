@@ -243,6 +243,37 @@ def test_mask_absorbing_states():
     check_against_oracle(cfg, 300, 25, seed=24, min_agree=0.9)
 
 
+def test_two_players():
+    """players == [0, 1]: -child.value() in ucb_score and the sign-alternating backup (self_play.py:469-472, 492-500)."""
+    cfg = tsp.get_config("roundabout_env_ttc_flat", players=[0, 1])
+    check_against_oracle(cfg, 512, 25, seed=26, min_agree=0.9)
+    cfg = tsp.get_config("roundabout_env_ttc_flat", players=[0, 1], mask_absorbing_states=True)
+    check_against_oracle(cfg, 300, 25, seed=27, legal=True, min_agree=0.9)
+    cfg = tsp.get_config("cross_merge_env", players=[0, 1], num_simulations=60)  # weights too large for the fast kernel
+    check_against_oracle(cfg, 64, 60, seed=28, min_agree=0.9)
+
+
+def test_two_players_rejected_by_the_chance_node_searches():
+    cfg = tsp.get_config("roundabout_env_ttc_flat_stochastic_concat", players=[0, 1])  # self_play_stochastic.py:407
+    with pytest.raises(tsp.TspError):
+        tsp.Engine(cfg, max_roots=1)
+
+
+@pytest.mark.parametrize("name", [n for n in NAMES if n.startswith(("highway", "roundabout"))])
+def test_generic_kernel_fallback_bit_exact(name, monkeypatch):
+    """The schedule-driven generic search kernel (what runs when a network does not fit the fast kernel's
+    shared-memory layout) against the reference fixtures, with the fast kernel switched off."""
+    monkeypatch.setenv("TSP_NO_FAST", "1")
+    g = Golden(name)
+    eng = tsp.Engine(g.config, max_roots=64, max_simulations=g.S, state_dict=g.state_dict)
+    got = eng.run(g.S, fed_root=g.out["root_record"], fed_records=g.out["records"], **g.run_kwargs())
+    assert_tree_outputs_bit_exact(got, g.out, what=name)
+    got = eng.run(g.S, observations=g.obs, trace=True, **g.run_kwargs())
+    replay = Oracle(g.config).run(g.S, fed_root=got["trace_root"], fed_records=got["trace_records"], B=g.N, **g.run_kwargs())
+    assert_tree_outputs_bit_exact(got, replay, what=name + " (own network, replayed)")
+    eng.close()
+
+
 def test_single_root_and_policy_only():
     cfg = tsp.get_config("highway_env_ttc_flat")
     check_against_oracle(cfg, 1, 25, seed=25, min_agree=1.0)

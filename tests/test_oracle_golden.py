@@ -16,7 +16,7 @@ NAMES = golden_names()
 
 
 def test_fixtures_present():
-    assert len(NAMES) >= 11
+    assert len(NAMES) >= 13
 
 
 @pytest.mark.parametrize("name", NAMES)

@@ -664,14 +664,16 @@ struct MinMax {
 // self_play.py:453-477 (VARIANT 0), self_play_stochastic.py:488-508 (1), self_play_risk_sensitive.py:496-520 (2)
 template <int VARIANT>
 __device__ __forceinline__ double ucb_score(double pb_log, double sqrt_parent_visits, int visits, double vsum,
-                                            double prior, float reward, double discount, const MinMax& mm) {
+                                            double prior, float reward, double discount, const MinMax& mm,
+                                            bool two_player = false) {
     double pb_c = __dmul_rn(pb_log, __ddiv_rn(sqrt_parent_visits, (double)(visits + 1)));
     const double prior_score = __dmul_rn(pb_c, prior);
     double value_score = 0.0;
     if (visits > 0) {
         if (VARIANT == 0) {
             const double q = __ddiv_rn(vsum, (double)visits);
-            value_score = mm.normalize(__dadd_rn((double)reward, __dmul_rn(discount, q)));
+            // two players: -child.value() (self_play.py:469-472)
+            value_score = mm.normalize(__dadd_rn((double)reward, __dmul_rn(discount, two_player ? -q : q)));
         } else if (VARIANT == 1) {
             value_score = mm.normalize(__ddiv_rn(vsum, (double)visits));
         } else {
@@ -702,7 +704,7 @@ struct NetParams {
 
 struct SearchParams {
     int B, S, A, H, nf, support, mask_absorbing, uniform_policy;
-    int blocks_per_tree, hidden_per_tree, max_rec, T, K, max_iters, w_smem_floats, pb_stride, warp_mlp;
+    int blocks_per_tree, hidden_per_tree, max_rec, T, K, max_iters, w_smem_floats, pb_stride, warp_mlp, two_player;
     double discount;
     const double* pb_table;  // [2][S + 2]: log((N + base + 1) / base) + init, then sqrt(N); host libm (bit-equal to math.log / math.sqrt)
     void* blocks; float* hidden_pool; TreeHeader* hdr; const double* rootprior; const int* rootact;
@@ -947,7 +949,7 @@ __global__ void __launch_bounds__(TM * GW * XW) search_kernel(const __grid_const
                         if (ch >= 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(blocks + ch));
                     }
                     double score = -CUDART_INF;
-                    if (on) score = ucb_score<VARIANT>(pb[Np], sq[Np], vis, vs, prior, rw, discount, mm);
+                    if (on) score = ucb_score<VARIANT>(pb[Np], sq[Np], vis, vs, prior, rw, discount, mm, VARIANT == 0 && p.two_player);
                     double best = score;
 #pragma unroll
                     for (int d = 1; d < GW; d <<= 1) {
@@ -1161,23 +1163,34 @@ __global__ void __launch_bounds__(TM * GW * XW) search_kernel(const __grid_const
                     // The 8 lanes of the group execute this loop in lock step (identical control flow) and ALL
                     // of them store the identical updated statistics: no lane ever needs another lane's view
                     // of memory inside the loop, so no warp-level sync per level is required.
+                    // two players (self_play.py:492-500): a node k plies above the leaf belongs to the leaf's player
+                    // iff k is even -- except the unexpanded (masked terminal) leaf, whose to_play is still -1
+                    const bool two = p.two_player != 0;
+                    int k = 0;
                     while (true) {
                         Block* bk = blocks + cur;
                         const int ps = bk->aux, pc = bk->parent;  // issued with the statistics loads
-                        const double vs = __dadd_rn(bk->vsum[cs], v);
+                        const bool same = two && ((k & 1) == 0) && !(masked && k == 0);
+                        const double vs = __dadd_rn(bk->vsum[cs], (two && !same) ? -v : v);
                         const int vis = bk->visit[cs] + 1;
                         const double rw = (double)bk->reward[cs];
                         bk->vsum[cs] = vs;
                         bk->visit[cs] = vis;
-                        mm.update(__dadd_rn(rw, __dmul_rn(discount, __ddiv_rn(vs, (double)vis))));
-                        v = __dadd_rn(rw, __dmul_rn(discount, v));
+                        const double q = __ddiv_rn(vs, (double)vis);
+                        mm.update(__dadd_rn(rw, __dmul_rn(discount, two ? -q : q)));
+                        v = __dadd_rn(same ? -rw : rw, __dmul_rn(discount, v));
+                        ++k;
                         if (cur == 0) break;
                         cs = ps & 0xFF;
                         cur = pc;
                     }
-                    root_vsum = __dadd_rn(root_vsum, v);
-                    root_visit += 1;
-                    mm.update(__dadd_rn(0.0, __dmul_rn(discount, __ddiv_rn(root_vsum, (double)root_visit))));
+                    {
+                        const bool same = two && ((k & 1) == 0);
+                        root_vsum = __dadd_rn(root_vsum, (two && !same) ? -v : v);
+                        root_visit += 1;
+                        const double q = __ddiv_rn(root_vsum, (double)root_visit);
+                        mm.update(__dadd_rn(0.0, __dmul_rn(discount, two ? -q : q)));
+                    }
                 } else if (VARIANT == 1) {
                     // self_play_stochastic.py:408-418; entries alternate State (leaf), Transition, State, ...
                     bool is_state = true;

@@ -667,7 +667,9 @@ int launch_fast_any(tsp_engine* e, const SearchParams& sp) {
     p.mask_absorbing = sp.mask_absorbing; p.uniform_policy = sp.uniform_policy;
     p.blocks_per_tree = sp.blocks_per_tree; p.hidden_per_tree = sp.hidden_per_tree;
     p.max_rec = sp.max_rec; p.T = sp.T; p.pb_stride = sp.pb_stride;
-    p.discount = sp.discount; p.discount_f = (float)sp.discount; p.pb_table = sp.pb_table;
+    p.discount = sp.discount; p.pb_table = sp.pb_table;
+    p.two_player = sp.two_player;
+    p.discount_f = sp.two_player ? -(float)sp.discount : (float)sp.discount;
     p.blocks = sp.blocks; p.hidden_pool = sp.hidden_pool; p.hdr = sp.hdr; p.rootprior = sp.rootprior; p.rootact = sp.rootact;
     p.tie = sp.tie; p.fed = sp.fed; p.trace = sp.trace;
     p.sched = reinterpret_cast<const FastSched*>(e->fsched_dev.p);
@@ -794,8 +796,10 @@ const char* tsp_last_error(tsp_handle h) { return h ? h->err.c_str() : g_create_
 int tsp_create(const tsp_config* cfg, tsp_handle* out) {
     if (!cfg || !out) return fail(nullptr, TSP_EINVAL, "tsp_create: null argument");
     *out = nullptr;
-    if (cfg->num_players != 1)
-        return fail(nullptr, TSP_ENOTIMPL, "only single-player search is implemented (len(players) == %d)", cfg->num_players);
+    if (cfg->num_players < 1 || cfg->num_players > 2)  // self_play.py:502-503 raises NotImplementedError
+        return fail(nullptr, TSP_ENOTIMPL, "more than two player mode not implemented (len(players) == %d)", cfg->num_players);
+    if (cfg->num_players == 2 && cfg->variant != TSP_VARIANT_MUZERO)  // self_play_stochastic.py:407 asserts one player
+        return fail(nullptr, TSP_EINVAL, "the chance-node searches require len(players) == 1");
     if (cfg->variant < 0 || cfg->variant > 2) return fail(nullptr, TSP_EINVAL, "unknown variant %d", cfg->variant);
     if (cfg->num_actions < 1 || cfg->num_actions > TSP_MAX_ACTIONS)
         return fail(nullptr, TSP_EINVAL, "num_actions must be in 1..%d", TSP_MAX_ACTIONS);
@@ -1046,6 +1050,7 @@ int tsp_run(tsp_handle e, const tsp_run_args* a) {
     sp.K = a->chance_stream ? a->chance_len : 0;
     sp.max_iters = (c.variant == 0) ? S : S + (S + 1) * A + 1;
     sp.discount = c.discount;
+    sp.two_player = c.num_players == 2 ? 1 : 0;
     sp.pb_table = reinterpret_cast<const double*>(e->pbtable.p);
     sp.pb_stride = c.max_simulations + 2;
     sp.blocks = e->blocks.p;

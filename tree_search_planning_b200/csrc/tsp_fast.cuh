@@ -65,8 +65,8 @@ static_assert(sizeof(FastSched) % 16 == 0, "FastSched is copied in 16-byte words
 
 struct FastParams {
     int B, S, A, H, support, mask_absorbing, uniform_policy;
-    int blocks_per_tree, hidden_per_tree, max_rec, T, pb_stride, w_lo;
-    float discount_f;  // (float)discount for the selection filter
+    int blocks_per_tree, hidden_per_tree, max_rec, T, pb_stride, w_lo, two_player;
+    float discount_f;  // (float)discount for the selection filter, negated for two players (-child.value())
     double discount;
     const double* pb_table;
     void* blocks; float* hidden_pool; TreeHeader* hdr; const double* rootprior; const int* rootact;
@@ -287,12 +287,12 @@ __device__ __forceinline__ void decode_row(const float* __restrict__ vl, const f
 // order; out of line so that the float32 filter stays small. Lanes 0..7 of the tree hold the children.
 __device__ __noinline__ int select_exact(double pbN, double sqN, int vis, double vs, double prior, float rw,
                                          double discount, double mn, double mx, bool on, int gl0,
-                                         const unsigned char* tie_row, int T, int& k_tie) {
+                                         const unsigned char* tie_row, int T, int& k_tie, bool two_player) {
     MinMax mm;
     mm.mn = mn;
     mm.mx = mx;
     double score = -CUDART_INF;
-    if (on) score = ucb_score<0>(pbN, sqN, vis, vs, prior, rw, discount, mm);
+    if (on) score = ucb_score<0>(pbN, sqN, vis, vs, prior, rw, discount, mm, two_player);
     double best = score;
 #pragma unroll
     for (int d = 1; d < GW; d <<= 1) {
@@ -309,26 +309,32 @@ __device__ __noinline__ int select_exact(double pbN, double sqN, int vis, double
     return __fns(tied, 0, (v % nt) + 1);
 }
 
-// Sequential backup for paths deeper than the lane-parallel version records (self_play.py:485-490).
+// Sequential backup for paths deeper than the lane-parallel version records (self_play.py:485-500).
 __device__ __noinline__ void backup_walk(NodeBlock<5>* blocks, int cur, int cs, double v, double discount, MinMax& mm,
-                                         double& root_vsum, int& root_visit) {
+                                         double& root_vsum, int& root_visit, bool two, bool masked) {
+    int k = 0;  // plies above the leaf
     while (true) {
         NodeBlock<5>* bk = blocks + cur;
         const int ps = bk->aux, pc = bk->parent;
-        const double vs = __dadd_rn(bk->vsum[cs], v);
+        const bool same = two && ((k & 1) == 0) && !(masked && k == 0);
+        const double vs = __dadd_rn(bk->vsum[cs], (two && !same) ? -v : v);
         const int vis = bk->visit[cs] + 1;
         const double rw = (double)bk->reward[cs];
         bk->vsum[cs] = vs;
         bk->visit[cs] = vis;
-        mm.update(__dadd_rn(rw, __dmul_rn(discount, __ddiv_rn(vs, (double)vis))));
-        v = __dadd_rn(rw, __dmul_rn(discount, v));
+        const double q = __ddiv_rn(vs, (double)vis);
+        mm.update(__dadd_rn(rw, __dmul_rn(discount, two ? -q : q)));
+        v = __dadd_rn(same ? -rw : rw, __dmul_rn(discount, v));
+        ++k;
         if (cur == 0) break;
         cs = ps & 0xFF;
         cur = pc;
     }
-    root_vsum = __dadd_rn(root_vsum, v);
+    const bool same = two && ((k & 1) == 0);
+    root_vsum = __dadd_rn(root_vsum, (two && !same) ? -v : v);
     root_visit += 1;
-    mm.update(__dadd_rn(0.0, __dmul_rn(discount, __ddiv_rn(root_vsum, (double)root_visit))));
+    const double q = __ddiv_rn(root_vsum, (double)root_visit);
+    mm.update(__dadd_rn(0.0, __dmul_rn(discount, two ? -q : q)));
 }
 
 template <int G>
@@ -466,7 +472,8 @@ __global__ void __launch_bounds__(G * GTHREADS, 2 / G) search_fast_kernel(const 
                 if (__any_sync(FULL, need)) {  // near-tie, exact tie or non-finite filter value: decide in float64
                     int k2 = k_tie;
                     const int se = select_exact(pb[Np], sq[Np], vis, vs, (node == 0) ? root_prior : (double)prf, rw, discount,
-                                                mm.mn, mm.mx, on && need, gl0, p.tie ? p.tie + (size_t)b * p.T : nullptr, p.T, k2);
+                                                mm.mn, mm.mx, on && need, gl0, p.tie ? p.tie + (size_t)b * p.T : nullptr, p.T, k2,
+                                                p.two_player != 0);
                     if (need) {
                         sl = se;
                         k_tie = k2;
@@ -577,6 +584,9 @@ __global__ void __launch_bounds__(G * GTHREADS, 2 / G) search_fast_kernel(const 
             // at level e - 1 of the descent. The value chain v <- r + discount * v is replayed by every lane (one
             // shuffle + 2 flops per level); the expensive per-node part (value_sum / visit_count for MinMaxStats)
             // runs once, one entry per lane. Both trees of the warp run it together (warp-uniform trip counts).
+            // two players (self_play.py:492-500): entry e is the leaf player's own node iff depth - e is even, except
+            // the unexpanded (masked terminal) leaf whose to_play is still -1
+            const bool two = p.two_player != 0;
             const int dact = active ? depth : 0;
             const int dmax = max(dact, __shfl_xor_sync(FULL, dact, 16));
             if (dmax <= PATH_LEVELS) {
@@ -602,14 +612,17 @@ __global__ void __launch_bounds__(G * GTHREADS, 2 / G) search_fast_kernel(const 
                         const double rwe = (double)__shfl_sync(FULL, rwf, gl0 + (ee & (LPT - 1)));
                         if (ee <= depth) {
                             if (ee == e) myv = v;
-                            v = __dadd_rn(rwe, __dmul_rn(discount, v));
+                            const bool same_ee = two && (((depth - ee) & 1) == 0) && !(masked && ee == depth);
+                            v = __dadd_rn(same_ee ? -rwe : rwe, __dmul_rn(discount, v));
                         }
                     }
                     if (e == 0) myv = v;
                     if (mine) {
-                        const double vs = __dadd_rn(vs0, myv);
+                        const bool same_e = two && (((depth - e) & 1) == 0) && !(masked && e == depth);
+                        const double vs = __dadd_rn(vs0, (two && !same_e) ? -myv : myv);
                         const int vis = vis0 + 1;
-                        const double x = __dadd_rn((double)rwf, __dmul_rn(discount, __ddiv_rn(vs, (double)vis)));
+                        const double q = __ddiv_rn(vs, (double)vis);
+                        const double x = __dadd_rn((double)rwf, __dmul_rn(discount, two ? -q : q));
                         if (e >= 1) {
                             bk->vsum[cs] = vs;
                             bk->visit[cs] = vis;
@@ -625,13 +638,13 @@ __global__ void __launch_bounds__(G * GTHREADS, 2 / G) search_fast_kernel(const 
                     pmx = ox_ > pmx ? ox_ : pmx;
                 }
                 if (active) {
-                    root_vsum = __dadd_rn(root_vsum, v);
+                    root_vsum = __dadd_rn(root_vsum, (two && (depth & 1)) ? -v : v);
                     root_visit += 1;
                     mm.mn = mm.mn < pmn ? mm.mn : pmn;
                     mm.mx = mm.mx > pmx ? mm.mx : pmx;
                 }
             } else if (active) {
-                backup_walk(blocks, node, slot, v, discount, mm, root_vsum, root_visit);
+                backup_walk(blocks, node, slot, v, discount, mm, root_vsum, root_visit, two, masked);
             }
             if (active) n_sims++;
         }

@@ -201,8 +201,12 @@ class Engine:
             fed_records=None, trace=False, max_records=None, want=("visit_counts", "root_value", "child_value",
                                                                    "child_prior", "child_reward", "max_tree_depth",
                                                                    "root_predicted_value", "num_records"),
-            want_root_hidden=False, synchronize=True):
-        """Batched MCTS.run over HOST numpy arrays; returns a dict of numpy arrays."""
+            want_root_hidden=False, synchronize=True, to_play=None):
+        """Batched MCTS.run over HOST numpy arrays; returns a dict of numpy arrays.
+
+        `to_play` ([B], MCTS.run's argument) is accepted for interface parity only: with players == [0, 1] the
+        reference's arithmetic depends on whether a node and the leaf are an even number of plies apart
+        (self_play.py:492-500), never on which player the root belongs to."""
         S = self.max_simulations if num_simulations is None else int(num_simulations)
         A = self.A
         keep = []
