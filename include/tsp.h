@@ -103,6 +103,14 @@ typedef struct {
     int32_t max_records;           /* rows per root in fed_records / trace_records */
     int32_t tie_len;               /* T */
     int32_t chance_len;            /* K */
+    int32_t resume;                /* != 0: MCTS.run(..., override_root_with=root) (self_play.py:331-333, 372-378) for every
+                                      root of the previous tsp_run on this handle: the trees are kept, no root inference,
+                                      a fresh MinMaxStats / max_tree_depth, the exploration noise mixed into the root
+                                      priors AGAIN, then num_simulations more simulations (the total must stay within
+                                      max_simulations). observations are ignored, root_predicted_value is not written
+                                      (the reference returns None). Deterministic and risk-sensitive search only: the
+                                      stochastic reference fails its own assert (self_play_stochastic.py:333). */
+    int32_t reserved0;
     /* inputs */
     const float *observations;     /* [B][obs_dim]; torch.tensor(observation).float() of self_play.py:336-341 */
     const int32_t *legal_actions;  /* [B][A] ordered legal-action lists (dict insertion order matters,
@@ -147,7 +155,7 @@ typedef struct {
     int32_t search_smem_bytes;
     int32_t trees_per_cta;
     int32_t threads_per_cta;
-    int32_t reserved;
+    int32_t search_kernel;         /* last search: 1 = tsp::search_fast_kernel (weights in shared memory), 0 = tsp::search_kernel */
 } tsp_stats;
 
 int tsp_abi_version(void);

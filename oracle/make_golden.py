@@ -36,6 +36,12 @@ CASES = [
     ("cross_merge_s200", "cross_merge_env", 200, 4, {}),
     # two-player backup / ucb branch (self_play.py:469-472, 492-500); to_play alternates over the roots
     ("roundabout_s25_twoplayer", "roundabout_env_ttc_flat", 25, 12, {"players": [0, 1]}),
+    # the search continued twice with override_root_with=root (self_play.py:331-333): 3 x S simulations
+    ("roundabout_s25_override", "roundabout_env_ttc_flat", 25, 8, {"phases": 3}),
+    # (the stochastic search cannot be continued: its assert at self_play_stochastic.py:333 fails on a root
+    #  that already has visits; the risk-sensitive one has no such assert)
+    ("roundabout_s25_override_legal", "roundabout_env_ttc_flat", 25, 6, {"phases": 2, "legal": True, "mask": "adaptive"}),
+    ("risk_s25_override", "roundabout_env_ttc_flat_risk_sensitive", 25, 6, {"phases": 2, "legal": True}),
     ("roundabout_s25_twoplayer_mask", "roundabout_env_ttc_flat", 25, 8, {"players": [0, 1], "mask": "adaptive", "legal": True}),
 ]
 
@@ -71,12 +77,17 @@ def make_case(name, game, S, N, opt, seed):
     max_rec = S if variant == 0 else S * (A + 2) + A + 2
     K = 8 * S
     T = 64
+    P = int(opt.get("phases", 1))
     obs = rng.random((N, D), dtype=numpy.float32)
     legal = numpy.zeros((N, A), numpy.int32)
     n_legal = numpy.zeros(N, numpy.int32)
     noise = numpy.zeros((N, A), numpy.float64)
     tie = rng.integers(0, 256, size=(N, T)).astype(numpy.uint8)
     chance = rng.integers(0, 256, size=(N, K)).astype(numpy.uint8)
+    if P > 1:  # per-phase streams [P][N][...]; phase 0 keeps the arrays above
+        noise = numpy.zeros((P, N, A), numpy.float64)
+        tie = numpy.concatenate([tie[None], rng.integers(0, 256, size=(P - 1, N, T)).astype(numpy.uint8)])
+        chance = numpy.concatenate([chance[None], rng.integers(0, 256, size=(P - 1, N, K)).astype(numpy.uint8)])
     out = dict(
         visit_counts=numpy.zeros((N, A), numpy.int32), root_value=numpy.zeros(N),
         child_value=numpy.zeros((N, A)), child_prior=numpy.zeros((N, A)), child_reward=numpy.zeros((N, A)),
@@ -84,7 +95,8 @@ def make_case(name, game, S, N, opt, seed):
         n_nodes=numpy.zeros(N, numpy.int32), n_records=numpy.zeros(N, numpy.int32),
         n_tie_draws=numpy.zeros(N, numpy.int32), n_chance_draws=numpy.zeros(N, numpy.int32),
         root_record=numpy.zeros((N, RL.REC_WIDTH), numpy.float32),
-        records=numpy.zeros((N, max_rec, RL.REC_WIDTH), numpy.float32),
+        records=numpy.zeros((N, max_rec, RL.REC_WIDTH), numpy.float32) if int(opt.get("phases", 1)) == 1
+        else numpy.zeros((int(opt["phases"]), N, max_rec, RL.REC_WIDTH), numpy.float32),
         root_hidden=numpy.zeros((N, cfg.encoding_size), numpy.float32),
     )
     add_noise = not opt.get("no_noise", False)
@@ -99,19 +111,36 @@ def make_case(name, game, S, N, opt, seed):
         n_legal[i] = len(la)
         legal[i, :len(la)] = la
         nz = rng.dirichlet([cfg.root_dirichlet_alpha] * len(la)) if len(la) > 1 else numpy.ones(1)
-        noise[i, :len(la)] = nz
+        conts = []
+        if P == 1:
+            noise[i, :len(la)] = nz
+            tie_i, chance_i = tie[i], chance[i]
+        else:
+            noise[0, i, :len(la)] = nz
+            tie_i, chance_i = tie[0, i], chance[0, i]
+            for ph in range(1, P):
+                nz2 = rng.dirichlet([cfg.root_dirichlet_alpha] * len(la)) if len(la) > 1 else numpy.ones(1)
+                noise[ph, i, :len(la)] = nz2
+                conts.append(dict(noise=nz2, tie=tie[ph, i], chance=chance[ph, i]))
         r = RL.run_reference(cfg, model, obs[i].reshape(cfg.stacked_observations * 2 + 1, 1, -1), legal_actions=la,
-                             noise=nz, tie=tie[i], chance=chance[i], add_exploration_noise=add_noise,
-                             uniform_policy=uniform, to_play=int(to_play[i]))
+                             noise=nz, tie=tie_i, chance=chance_i, add_exploration_noise=add_noise,
+                             uniform_policy=uniform, to_play=int(to_play[i]), continuations=conts)
         for k2 in ("visit_counts", "root_value", "child_value", "child_prior", "child_reward", "max_tree_depth",
                    "root_predicted_value", "n_nodes", "n_tie_draws", "n_chance_draws", "root_record",
                    "root_hidden"):
             out[k2][i] = r[k2]
-        nr = len(r["records"])
-        assert nr <= max_rec
-        out["n_records"][i] = nr
-        out["records"][i, :nr] = r["records"]
-        assert int(r["visit_counts"].sum()) == S and r["root_visit_count"] == S
+        if P == 1:
+            nr = len(r["records"])
+            assert nr <= max_rec
+            out["n_records"][i] = nr
+            out["records"][i, :nr] = r["records"]
+        else:
+            for ph in range(P):
+                nr = len(r["records"][ph])
+                assert nr <= max_rec
+                out["records"][ph, i, :nr] = r["records"][ph]
+            out["n_records"][i] = nr  # of the last search
+        assert int(r["visit_counts"].sum()) == S * P and r["root_visit_count"] == S * P
 
     # ---- batched network goldens (torch fp32, batch M) ----
     M = 48
@@ -158,7 +187,7 @@ def make_case(name, game, S, N, opt, seed):
     weights = {"w:" + k: v for k, v in RL.state_dict_numpy(model).items()
                if not k.startswith("reconstruction_network") and not k.startswith("transition_posterior")}
     meta = dict(game=game, S=S, N=N, seed=seed, add_noise=add_noise, uniform_policy=uniform,
-                mask_absorbing_states=bool(opt.get("mask", False)), players=list(cfg.players))
+                mask_absorbing_states=bool(opt.get("mask", False)), players=list(cfg.players), phases=P)
     path = os.path.join(OUT_DIR, name + ".npz")
     numpy.savez_compressed(
         path, obs=obs, legal=legal, n_legal=n_legal, noise=noise, tie=tie, chance=chance, to_play=to_play,

@@ -46,7 +46,7 @@ class _RunArgs(ctypes.Structure):
         ("visit_counts", _P), ("root_value", _P), ("child_value", _P), ("child_prior", _P),
         ("child_reward", _P), ("max_depth", _P), ("root_pred_value", _P), ("root_hidden", _P),
         ("n_records", _P), ("n_nodes", _P), ("trace_root", _P), ("trace_records", _P),
-        ("n_threads", ctypes.c_int), ("to_play", _P),
+        ("n_threads", ctypes.c_int), ("to_play", _P), ("n_phases", ctypes.c_int),
     ]
 
 
@@ -177,8 +177,12 @@ class Oracle:
     def run(self, num_simulations, observations=None, legal_actions=None, num_legal=None, noise=None,
             tie=None, chance=None, add_exploration_noise=True, uniform_policy=False,
             fed_root=None, fed_records=None, trace=False, max_records=None, n_threads=0, B=None,
-            want_root_hidden=False, to_play=None):
+            want_root_hidden=False, to_play=None, n_phases=1):
+        """n_phases > 1: the search is continued with override_root_with=root (self_play.py:331-333) n_phases - 1
+        times, S simulations each; noise / tie / chance / fed_records then have a leading [n_phases] dimension and
+        the trace records come back as [n_phases, B, max_records, REC]."""
         S = int(num_simulations)
+        P = int(n_phases)
         A = self.A
         keep = []
 
@@ -201,7 +205,7 @@ class Oracle:
         fed_root = prep(fed_root, numpy.float32, (B, REC_WIDTH))
         if fed_records is not None:
             fed_records = prep(fed_records, numpy.float32)
-            mr = fed_records.reshape(B, -1, REC_WIDTH).shape[1]
+            mr = fed_records.reshape(P * B, -1, REC_WIDTH).shape[1]
             if max_records is None:
                 max_records = mr
             assert mr == max_records
@@ -209,12 +213,12 @@ class Oracle:
             max_records = self.max_records(S) if trace else (self.max_records(S))
         legal_actions = prep(legal_actions, numpy.int32, (B, A))
         num_legal = prep(num_legal, numpy.int32, (B,))
-        noise = prep(noise, numpy.float64, (B, A))
+        noise = prep(noise, numpy.float64, (P * B, A))
         to_play = prep(to_play, numpy.int32, (B,))
         tie = prep(tie, numpy.uint8)
-        T = 0 if tie is None else tie.reshape(B, -1).shape[1]
+        T = 0 if tie is None else tie.reshape(P * B, -1).shape[1]
         chance = prep(chance, numpy.uint8)
-        K = 0 if chance is None else chance.reshape(B, -1).shape[1]
+        K = 0 if chance is None else chance.reshape(P * B, -1).shape[1]
         if add_exploration_noise:
             assert noise is not None, "exploration noise requested but no noise supplied"
         out = dict(
@@ -230,7 +234,7 @@ class Oracle:
         )
         root_hidden = numpy.zeros((B, self.H), numpy.float32) if want_root_hidden else None
         trace_root = numpy.zeros((B, REC_WIDTH), numpy.float32) if trace else None
-        trace_records = numpy.zeros((B, max_records, REC_WIDTH), numpy.float32) if trace else None
+        trace_records = numpy.zeros((P * B, max_records, REC_WIDTH), numpy.float32) if trace else None
         a = _RunArgs(B, S, int(bool(add_exploration_noise)), int(bool(uniform_policy)),
                      _ptr(observations), _ptr(legal_actions), _ptr(num_legal), _ptr(noise),
                      _ptr(tie), T, _ptr(chance), K,
@@ -238,13 +242,13 @@ class Oracle:
                      _ptr(out["visit_counts"]), _ptr(out["root_value"]), _ptr(out["child_value"]),
                      _ptr(out["child_prior"]), _ptr(out["child_reward"]), _ptr(out["max_tree_depth"]),
                      _ptr(out["root_predicted_value"]), _ptr(root_hidden), _ptr(out["n_records"]),
-                     _ptr(out["n_nodes"]), _ptr(trace_root), _ptr(trace_records), int(n_threads), _ptr(to_play))
+                     _ptr(out["n_nodes"]), _ptr(trace_root), _ptr(trace_records), int(n_threads), _ptr(to_play), P)
         rc = self.lib.orc_run(_P(self.net), ctypes.byref(a))
         if rc != 0:
             raise RuntimeError("oracle run failed with code %d" % rc)
         if trace:
             out["trace_root"] = trace_root
-            out["trace_records"] = trace_records
+            out["trace_records"] = trace_records if P == 1 else trace_records.reshape(P, B, max_records, REC_WIDTH)
         if want_root_hidden:
             out["root_hidden"] = root_hidden
         return out

@@ -271,9 +271,13 @@ def _tree_size(node):
 
 def run_reference(config, model, observation, legal_actions=None, noise=None, tie=None,
                   chance=None, add_exploration_noise=True, to_play=0, uniform_policy=False,
-                  policy_only=False, record=True):
+                  policy_only=False, record=True, continuations=()):
     """Run the reference MCTS.run once; returns a dict of everything a consumer reads
-    from `root` / `extra_info` plus the evaluation records."""
+    from `root` / `extra_info` plus the evaluation records.
+
+    `continuations`: sequence of dict(noise=, tie=, chance=); after the first search the reference is called
+    again with override_root_with=root (self_play.py:331-333) once per entry, with those random streams. The
+    returned statistics are those of the final tree, `records` is then a list with one array per search."""
     from tree_search_planning_b200.configs import variant_of
 
     ref = load_reference()
@@ -297,6 +301,17 @@ def run_reference(config, model, observation, legal_actions=None, noise=None, ti
             root, extra = module.MCTS(config).run(
                 model, numpy.asarray(observation), legal_actions, to_play,
                 add_exploration_noise, **kwargs)
+        phase_records = [list(rec.records)]
+        for cont in continuations:
+            rec.records = []
+            streams = ExternalStreams(noise=cont.get("noise"), tie=cont.get("tie"), chance=cont.get("chance"))
+            with torch.no_grad(), patched_rng(streams):
+                root, extra = module.MCTS(config).run(
+                    model, numpy.asarray(observation), legal_actions, to_play,
+                    add_exploration_noise, override_root_with=root, **kwargs)
+            assert extra["root_predicted_value"] is None
+            extra = dict(extra, root_predicted_value=float("nan"))
+            phase_records.append(list(rec.records))
     finally:
         if record:
             rec.uninstall()
@@ -327,6 +342,8 @@ def run_reference(config, model, observation, legal_actions=None, noise=None, ti
         out["root_record"] = rec.root_record
         out["records"] = (numpy.stack(rec.records) if rec.records
                           else numpy.zeros((0, REC_WIDTH), numpy.float32))
+        if continuations:
+            out["records"] = [numpy.stack(r) if r else numpy.zeros((0, REC_WIDTH), numpy.float32) for r in phase_records]
         out["root_hidden"] = rec.root_hidden
         out["root_logits"] = rec.root_logits
     return out

@@ -449,6 +449,12 @@ typedef struct {
     const float *fed_records;
     int max_records;
     int to_play;          /* MCTS.run argument (root player) */
+    /* n_phases > 1: the search is continued n_phases - 1 times with override_root_with=root
+     * (self_play.py:331-333): the tree is kept, MinMaxStats / max_tree_depth / the random streams start
+     * afresh and the exploration noise is mixed into the root priors again. Per-phase inputs and
+     * records are `stride` elements apart. */
+    int n_phases;
+    size_t noise_stride, tie_stride, chance_stride, rec_stride;
 } TreeJob;
 
 static void rec_clear(float *r) {
@@ -500,12 +506,32 @@ static int run_tree(const TreeJob *job, const float *obs, const int *legal, int 
             root->children[i]->prior = root->children[i]->prior * (1 - frac) + noise[i] * frac;
     }
 
+    const int n_phases = job->n_phases > 1 ? job->n_phases : 1;
+    Node **path = (Node **)arena_alloc(ar, sizeof(Node *) * (size_t)(2 * job->S * n_phases + 4) * 2);
+    int path_cap = (2 * job->S * n_phases + 4) * 2;
+    int max_tree_depth = 0;
+    const uint8_t *tie0 = st->tie, *chance0 = st->chance;
+    for (int phase = 0; phase < n_phases; ++phase) {
+    const float *fed_records = job->fed_records ? job->fed_records + phase * job->rec_stride : NULL;
+    float *trace_records = job->trace_records ? job->trace_records + phase * job->rec_stride : NULL;
+    if (phase > 0) {
+        /* MCTS.run(..., override_root_with=root): self_play.py:331-333, 372-378 */
+        if (job->add_noise) {
+            const double frac = c->root_exploration_fraction;
+            const double *nz = noise + phase * job->noise_stride;
+            for (int i = 0; i < n_legal; ++i)
+                root->children[i]->prior = root->children[i]->prior * (1 - frac) + nz[i] * frac;
+        }
+        st->tie = tie0 ? tie0 + phase * job->tie_stride : NULL;
+        st->chance = chance0 ? chance0 + phase * job->chance_stride : NULL;
+        st->k_tie = 0;
+        st->k_chance = 0;
+        n_rec = 0;
+    }
     MinMax mm;
     mm.maximum = -INFINITY;
     mm.minimum = INFINITY;
-    int max_tree_depth = 0;
-    Node **path = (Node **)arena_alloc(ar, sizeof(Node *) * (size_t)(2 * job->S + 4) * 2);
-    int path_cap = (2 * job->S + 4) * 2;
+    max_tree_depth = 0;
 
     int num_sims = 0;
     while (num_sims < job->S) {
@@ -539,7 +565,7 @@ static int run_tree(const TreeJob *job, const float *obs, const int *legal, int 
             float *h = NULL;
             if (fed) {
                 if (n_rec >= job->max_records) return -3;
-                const float *fr = job->fed_records + (size_t)n_rec * ORC_REC_WIDTH;
+                const float *fr = fed_records + (size_t)n_rec * ORC_REC_WIDTH;
                 v = fr[1];
                 r = fr[2];
                 term = fr[3];
@@ -552,8 +578,8 @@ static int run_tree(const TreeJob *job, const float *obs, const int *legal, int 
                     for (int i = 0; i < A; ++i) logits[i] = 0.0f;
                 orc_softmax(logits, pri, A);
             }
-            if (job->trace_records && n_rec < job->max_records) {
-                float *tr = job->trace_records + (size_t)n_rec * ORC_REC_WIDTH;
+            if (trace_records && n_rec < job->max_records) {
+                float *tr = trace_records + (size_t)n_rec * ORC_REC_WIDTH;
                 rec_clear(tr);
                 tr[0] = 1.0f;
                 tr[1] = v;
@@ -599,7 +625,7 @@ static int run_tree(const TreeJob *job, const float *obs, const int *legal, int 
             const double r = (double)parent->child_reward[slot];
             if (fed) {
                 if (n_rec >= job->max_records) return -3;
-                const float *fr = job->fed_records + (size_t)n_rec * ORC_REC_WIDTH;
+                const float *fr = fed_records + (size_t)n_rec * ORC_REC_WIDTH;
                 if (fr[0] != 1.0f) return -4;
                 v = fr[1];
                 for (int i = 0; i < A; ++i) pri[i] = fr[4 + i];
@@ -608,8 +634,8 @@ static int run_tree(const TreeJob *job, const float *obs, const int *legal, int 
                 net_prediction(net, h, logits, &v, NULL, sc);
                 orc_softmax(logits, pri, A);
             }
-            if (job->trace_records && n_rec < job->max_records) {
-                float *tr = job->trace_records + (size_t)n_rec * ORC_REC_WIDTH;
+            if (trace_records && n_rec < job->max_records) {
+                float *tr = trace_records + (size_t)n_rec * ORC_REC_WIDTH;
                 rec_clear(tr);
                 tr[0] = 1.0f;
                 tr[1] = v;
@@ -669,7 +695,7 @@ static int run_tree(const TreeJob *job, const float *obs, const int *legal, int 
             node->child_reward = (float *)arena_alloc(ar, sizeof(float) * nf);
             if (fed) {
                 if (n_rec >= job->max_records) return -3;
-                const float *fr = job->fed_records + (size_t)n_rec * ORC_REC_WIDTH;
+                const float *fr = fed_records + (size_t)n_rec * ORC_REC_WIDTH;
                 if (fr[0] != 2.0f) return -4;
                 for (int z = 0; z < nf; ++z) {
                     tp[z] = fr[1 + z];
@@ -683,8 +709,8 @@ static int run_tree(const TreeJob *job, const float *obs, const int *legal, int 
                 mlp_forward(&net->mlp[ORC_PRIOR], parent->hidden, tl, sc->a, sc->b);
                 orc_softmax(tl, tp, nf);
             }
-            if (job->trace_records && n_rec < job->max_records) {
-                float *tr = job->trace_records + (size_t)n_rec * ORC_REC_WIDTH;
+            if (trace_records && n_rec < job->max_records) {
+                float *tr = trace_records + (size_t)n_rec * ORC_REC_WIDTH;
                 rec_clear(tr);
                 tr[0] = 2.0f;
                 for (int z = 0; z < nf; ++z) {
@@ -706,6 +732,7 @@ static int run_tree(const TreeJob *job, const float *obs, const int *legal, int 
         }
         if (depth > max_tree_depth) max_tree_depth = depth;
     }
+    } /* phases */
 
     /* ---- what consumers read from root ---- */
     for (int a = 0; a < A; ++a) {
@@ -759,6 +786,8 @@ typedef struct {
     float *trace_records;    /* [B][max_records][REC] or NULL */
     int n_threads;           /* 0 = OpenMP default */
     const int32_t *to_play;  /* [B] MCTS.run's to_play per root, or NULL = 0 */
+    int n_phases;            /* > 1: continue the search n_phases - 1 times (override_root_with); noise / tie /
+                                chance / fed_records / trace_records then carry a leading [n_phases] dimension */
 } orc_run_args;
 
 #include <pthread.h>
@@ -818,6 +847,11 @@ static void *worker_main(void *p) {
             job.fed_root = a->fed_root ? a->fed_root + (size_t)b * ORC_REC_WIDTH : NULL;
             job.fed_records = a->fed_records ? a->fed_records + (size_t)b * a->max_records * ORC_REC_WIDTH : NULL;
             job.max_records = a->max_records;
+            job.n_phases = a->n_phases;
+            job.noise_stride = (size_t)a->B * A;
+            job.tie_stride = (size_t)a->B * a->T;
+            job.chance_stride = (size_t)a->B * a->K;
+            job.rec_stride = (size_t)a->B * a->max_records * ORC_REC_WIDTH;
             Streams st;
             st.tie = a->tie ? a->tie + (size_t)b * a->T : NULL;
             st.T = a->T;
@@ -845,10 +879,11 @@ int orc_run(const orc_net *net, const orc_run_args *a) {
     const int A = c->num_actions, H = c->encoding_size;
     if (c->num_players != 1 && !(c->num_players == 2 && c->variant == 0)) return -10;
     if (A > ORC_MAX_ACTIONS) return -11;
-    const int iters_cap = (c->variant == 0) ? a->S : a->S * (A + 2) + A + 2;
+    const int S_all = a->S * (a->n_phases > 1 ? a->n_phases : 1);
+    const int iters_cap = (c->variant == 0) ? S_all : S_all * (A + 2) + A + 2;
     const size_t node_bytes = sizeof(Node) + 64;
     const size_t per_iter = (size_t)(A + 2) * (node_bytes + 16) + sizeof(float) * (size_t)(c->n_futures + 1) * (H + 8) + 256;
-    const size_t arena_cap = (size_t)(iters_cap + 4) * per_iter + sizeof(Node *) * (size_t)(4 * a->S + 16) * 2 + (1 << 16);
+    const size_t arena_cap = (size_t)(iters_cap + 4) * per_iter + sizeof(Node *) * (size_t)(4 * S_all + 16) * 2 + (1 << 16);
     int nthreads = a->n_threads > 0 ? a->n_threads : orc_max_threads();
     if (nthreads > (a->B + ORC_CHUNK - 1) / ORC_CHUNK) nthreads = (a->B + ORC_CHUNK - 1) / ORC_CHUNK;
     if (nthreads < 1) nthreads = 1;

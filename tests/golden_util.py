@@ -26,8 +26,11 @@ class Golden:
         for k in ("obs", "legal", "n_legal", "noise", "tie", "chance"):
             setattr(self, k, z[k])
         self.to_play = z["to_play"] if "to_play" in z.files else None
-        self.S = int(self.meta["S"])
+        self.S = int(self.meta["S"])   # simulations per search
         self.N = int(self.meta["N"])
+        # > 1: the search was continued P - 1 times with override_root_with=root; noise / tie / chance / records
+        # then carry a leading [P] dimension and the statistics are those of the final tree
+        self.P = int(self.meta.get("phases", 1))
         cfg = get_config(self.meta["game"], num_simulations=self.S)
         if self.meta.get("mask_absorbing_states"):
             cfg = cfg.replace(mask_absorbing_states=True)
@@ -35,10 +38,20 @@ class Golden:
             cfg = cfg.replace(players=list(self.meta["players"]))
         self.config = cfg
 
-    def run_kwargs(self):
-        return dict(legal_actions=self.legal, num_legal=self.n_legal, noise=self.noise, tie=self.tie,
-                    chance=self.chance, add_exploration_noise=bool(self.meta["add_noise"]),
+    def run_kwargs(self, phase=None):
+        """Keyword arguments of Oracle.run / Engine.run; `phase` selects one search of a continued fixture."""
+        noise, tie, chance = self.noise, self.tie, self.chance
+        if self.P > 1 and phase is not None:
+            noise, tie, chance = noise[phase], tie[phase], chance[phase]
+        return dict(legal_actions=self.legal, num_legal=self.n_legal, noise=noise, tie=tie,
+                    chance=chance, add_exploration_noise=bool(self.meta["add_noise"]),
                     uniform_policy=bool(self.meta["uniform_policy"]), to_play=self.to_play)
+
+    def oracle_kwargs(self):
+        kw = self.run_kwargs()
+        if self.P > 1:
+            kw["n_phases"] = self.P
+        return kw
 
 
 TREE_KEYS_EXACT = ("visit_counts", "root_value", "child_value", "child_prior", "child_reward", "max_tree_depth")

@@ -24,8 +24,31 @@ _engines = {}
 def engine_for(g, max_roots=64):
     key = (g.name, max_roots)
     if key not in _engines:
-        _engines[key] = tsp.Engine(g.config, max_roots=max_roots, max_simulations=g.S, state_dict=g.state_dict)
+        _engines[key] = tsp.Engine(g.config, max_roots=max_roots, max_simulations=g.S * g.P, state_dict=g.state_dict)
     return _engines[key]
+
+
+def engine_run(eng, g, fed, **opts):
+    """One search per phase of the fixture: phase 0 from scratch, the others continue the device-resident
+    trees (tsp_run_args.resume == MCTS.run's override_root_with). Returns the last run's outputs and the
+    per-phase trace records."""
+    traces = []
+    for ph in range(g.P):
+        kw = dict(g.run_kwargs(ph if g.P > 1 else None), **opts)
+        recs = g.out["records"] if g.P == 1 else g.out["records"][ph]
+        if ph == 0:
+            src = dict(fed_root=g.out["root_record"], fed_records=recs) if fed else dict(observations=g.obs)
+            got = eng.run(g.S, **src, **kw)
+            first = got
+        else:
+            src = dict(fed_records=recs) if fed else {}
+            got = eng.run(g.S, resume=True, num_roots=g.N, **src, **kw)
+        if "trace_records" in got:
+            traces.append(got["trace_records"])
+    for k in ("trace_root", "root_hidden", "root_predicted_value"):  # written by the first search only
+        if k in first:
+            got[k] = first[k]
+    return got, traces
 
 
 def drop_terminal(records, cfg):
@@ -49,10 +72,10 @@ def test_tree_arithmetic_bit_exact_with_reference_outputs_fed(name):
     the reference, when the reference's own network outputs are fed in call order."""
     g = Golden(name)
     eng = engine_for(g)
-    got = eng.run(g.S, fed_root=g.out["root_record"], fed_records=g.out["records"], **g.run_kwargs())
+    got, _ = engine_run(eng, g, fed=True)
     assert_tree_outputs_bit_exact(got, g.out, what=name)
     assert (got["num_records"] == g.out["n_records"]).all()
-    assert (got["visit_counts"].sum(1) == g.S).all()
+    assert (got["visit_counts"].sum(1) == g.S * g.P).all()
 
 
 @pytest.mark.parametrize("name", NAMES)
@@ -60,7 +83,8 @@ def test_end_to_end_against_reference_golden(name):
     """Own float32 network + own tree: visit counts equal the reference's on the fixture roots."""
     g = Golden(name)
     eng = engine_for(g)
-    got = eng.run(g.S, observations=g.obs, trace=True, want_root_hidden=True, **g.run_kwargs())
+    got, traces = engine_run(eng, g, fed=False, trace=True, want_root_hidden=True)
+    got["trace_records"] = traces[-1]
     same = (got["visit_counts"] == g.out["visit_counts"]).all(axis=1)
     assert same.mean() >= 0.9, "visit counts differ on %d of %d roots" % ((~same).sum(), g.N)
     assert close(got["root_hidden"], g.out["root_hidden"]).all()
@@ -71,8 +95,9 @@ def test_end_to_end_against_reference_golden(name):
     for b in numpy.nonzero(same)[0]:
         n = g.out["n_records"][b]
         assert got["num_records"][b] == n
+        ref_rec = g.out["records"] if g.P == 1 else g.out["records"][-1]
         assert_close_quantised(drop_terminal(got["trace_records"][b, :n], g.config),
-                               drop_terminal(g.out["records"][b, :n], g.config), min_fraction=0.97, what="records")
+                               drop_terminal(ref_rec[b, :n], g.config), min_fraction=0.97, what="records")
 
 
 @pytest.mark.parametrize("name", ["highway_s25", "cross_merge_s200", "stochastic_s25"])
@@ -265,12 +290,48 @@ def test_generic_kernel_fallback_bit_exact(name, monkeypatch):
     shared-memory layout) against the reference fixtures, with the fast kernel switched off."""
     monkeypatch.setenv("TSP_NO_FAST", "1")
     g = Golden(name)
-    eng = tsp.Engine(g.config, max_roots=64, max_simulations=g.S, state_dict=g.state_dict)
-    got = eng.run(g.S, fed_root=g.out["root_record"], fed_records=g.out["records"], **g.run_kwargs())
+    eng = tsp.Engine(g.config, max_roots=64, max_simulations=g.S * g.P, state_dict=g.state_dict)
+    got, _ = engine_run(eng, g, fed=True)
     assert_tree_outputs_bit_exact(got, g.out, what=name)
-    got = eng.run(g.S, observations=g.obs, trace=True, **g.run_kwargs())
-    replay = Oracle(g.config).run(g.S, fed_root=got["trace_root"], fed_records=got["trace_records"], B=g.N, **g.run_kwargs())
+    got, traces = engine_run(eng, g, fed=False, trace=True)
+    replay = Oracle(g.config).run(g.S, fed_root=got["trace_root"], fed_records=numpy.stack(traces) if g.P > 1 else traces[0],
+                                  B=g.N, **g.oracle_kwargs())
     assert_tree_outputs_bit_exact(got, replay, what=name + " (own network, replayed)")
+    eng.close()
+
+
+def test_continued_search_large_batch_vs_oracle():
+    """resume (override_root_with) at batch scale: 3 x 20 simulations on 2,048 roots, every phase with fresh noise
+    and streams; the engine's traces replayed through the oracle must give bit-identical root statistics."""
+    cfg = tsp.get_config("roundabout_env_ttc_flat", num_simulations=20)
+    sd = random_state_dict(cfg, 41)
+    B, S, P = 2048, 20, 3
+    eng = tsp.Engine(cfg, max_roots=B, max_simulations=S * P, state_dict=sd)
+    obs, kw0 = seeded_inputs(cfg, B, S, 42)
+    phases = [kw0] + [seeded_inputs(cfg, B, S, 43 + i)[1] for i in range(P - 1)]
+    traces = []
+    for ph, kw in enumerate(phases):
+        got = eng.run(S, observations=obs, trace=True, **kw) if ph == 0 else \
+            eng.run(S, resume=True, num_roots=B, trace=True, **kw)
+        traces.append(got["trace_records"])
+        if ph == 0:
+            troot = got["trace_root"]
+    assert (got["visit_counts"].sum(1) == S * P).all()
+    stack = lambda k: numpy.stack([kw[k] for kw in phases])
+    replay = Oracle(cfg, sd).run(S, fed_root=troot, fed_records=numpy.stack(traces), B=B, n_phases=P,
+                                 noise=stack("noise"), tie=stack("tie"))
+    assert_tree_outputs_bit_exact(got, replay, what="continued search replayed through the oracle")
+    with pytest.raises(tsp.TspError, match="exceed max_simulations"):
+        eng.run(S, resume=True, num_roots=B, **phases[0])
+    with pytest.raises(tsp.TspError, match="held"):
+        eng.run(S, resume=True, num_roots=B - 1, **{k: v[:B - 1] for k, v in phases[0].items()})
+    eng.close()
+    cfg = tsp.get_config("roundabout_env_ttc_flat_stochastic_concat")
+    eng = tsp.Engine(cfg, max_roots=4, max_simulations=50, state_dict=random_state_dict(cfg, 1))
+    obs, kw = seeded_inputs(cfg, 4, 25, 1)
+    eng.run(25, observations=obs, **kw)
+    with pytest.raises(tsp.TspError, match="cannot be continued"):  # self_play_stochastic.py:333
+        eng.run(25, resume=True, num_roots=4, **kw)
     eng.close()
 
 
@@ -339,3 +400,19 @@ def test_mcts_run_surface(game):
         tsp.MCTS(cfg).run(model, obs, [], 0, True)
     with pytest.raises(AssertionError):
         tsp.MCTS(cfg).run(model, obs, [0, 9], 0, True)
+    # override_root_with (self_play.py:331-333): the same root searched further
+    mcts = tsp.MCTS(cfg, max_search_multiple=2)
+    root, _ = mcts.run(model, obs, [3, 1, 4], 0, True)
+    if tsp.variant_of(cfg) == 1:
+        with pytest.raises(AssertionError):  # the reference's own assert, self_play_stochastic.py:333
+            mcts.run(model, obs, [3, 1, 4], 0, True, override_root_with=root)
+    else:
+        before = {a: c.visit_count for a, c in root.children.items()}
+        root2, extra2 = mcts.run(model, obs, [3, 1, 4], 0, True, override_root_with=root)
+        assert extra2["root_predicted_value"] is None
+        assert root2.visit_count == 2 * cfg.num_simulations
+        assert all(root2.children[a].visit_count >= before[a] for a in before)
+        assert root2.hidden_state is not None
+        stale = root  # a root whose tree has been searched over since
+        with pytest.raises(ValueError):
+            mcts.run(model, obs, [3, 1, 4], 0, True, override_root_with=stale)

@@ -705,9 +705,13 @@ struct NetParams {
 struct SearchParams {
     int B, S, A, H, nf, support, mask_absorbing, uniform_policy;
     int blocks_per_tree, hidden_per_tree, max_rec, T, K, max_iters, w_smem_floats, pb_stride, warp_mlp, two_player;
+    int S_tab;                 // simulations the trees hold after this run (size of the visit-count tables)
+    int resume, add_noise;     // resume: continue the trees of the previous run (override_root_with, self_play.py:331-333)
+    double one_minus_frac, frac;
+    const double* noise;      // [B][A], mixed into the root priors again on resume (self_play.py:372-376)
     double discount;
     const double* pb_table;  // [2][S + 2]: log((N + base + 1) / base) + init, then sqrt(N); host libm (bit-equal to math.log / math.sqrt)
-    void* blocks; float* hidden_pool; TreeHeader* hdr; const double* rootprior; const int* rootact;
+    void* blocks; float* hidden_pool; TreeHeader* hdr; double* rootprior; const int* rootact;
     const unsigned char* tie; const unsigned char* chance;
     const float* fed; float* trace;
     const float* W;
@@ -865,7 +869,7 @@ __global__ void __launch_bounds__(TM * GW * XW) search_kernel(const __grid_const
     const int rs = p.sched_a.row_stride;  // the host gives sched_a and sched_b the same row stride
     // shared-memory carve-out (offsets only -- no integer round trips, so every pointer stays "shared")
     double* pb = reinterpret_cast<double*>(smem);  // pb[N] = log((N + base + 1) / base) + init
-    const int pb_n = (p.S + 2 + 1) & ~1;
+    const int pb_n = (p.S_tab + 2 + 1) & ~1;  // S_tab: largest parent visit count (sums over continued searches)
     double* sq = pb + pb_n;                        // sq[N] = sqrt(N), correctly rounded (host libm)
     float* wsm = smem + 4 * pb_n;                  // optional copy of the search MLP weights
     float* act = wsm + (WSMEM ? p.w_smem_floats : 0);
@@ -884,7 +888,7 @@ __global__ void __launch_bounds__(TM * GW * XW) search_kernel(const __grid_const
     const int A = p.A, H = p.H, nf = p.nf;
     const double discount = p.discount;
 
-    for (int i = tid; i < p.S + 2; i += THREADS) {
+    for (int i = tid; i < p.S_tab + 2; i += THREADS) {
         pb[i] = p.pb_table[i];
         sq[i] = p.pb_table[p.pb_stride + i];
     }
@@ -911,6 +915,16 @@ __global__ void __launch_bounds__(TM * GW * XW) search_kernel(const __grid_const
         n_root = h.n_root;
         root_prior = p.rootprior[(size_t)b * GW + j];
         root_act = p.rootact[(size_t)b * GW + j];
+        if (p.resume) {  // MCTS.run(..., override_root_with=root): keep the tree, fresh MinMaxStats / depth / streams
+            root_vsum = h.root_vsum;
+            root_visit = h.root_visit;
+            n_blocks = h.n_blocks;
+            n_tgroups = h.n_tgroups;
+            if (p.add_noise && j < n_root) {  // add_exploration_noise once more, self_play.py:372-376, 540-549
+                root_prior = __dadd_rn(__dmul_rn(root_prior, p.one_minus_frac), __dmul_rn(p.noise[(size_t)b * A + j], p.frac));
+                p.rootprior[(size_t)b * GW + j] = root_prior;
+            }
+        }
     }
     __syncthreads();
 
@@ -1297,6 +1311,11 @@ __global__ void __launch_bounds__(TM * GW * XW) search_kernel(const __grid_const
             if (p.max_depth) p.max_depth[b] = max_depth;
             if (p.num_records) p.num_records[b] = n_rec;
             if (p.total_depth) p.total_depth[b] = depth_total;
+            // what a continued search (resume) needs besides the pools
+            p.hdr[b].root_vsum = root_vsum;
+            p.hdr[b].root_visit = root_visit;
+            p.hdr[b].n_blocks = n_blocks;
+            p.hdr[b].n_tgroups = n_tgroups;
         }
         if (j < A) {  // zero-fill, then scatter the legal children to their action index
             if (p.visit_counts) p.visit_counts[(size_t)b * A + j] = 0;

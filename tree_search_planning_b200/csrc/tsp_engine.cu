@@ -79,6 +79,9 @@ struct tsp_engine {
     int ct_override = 0;
     int ng_override = 0;
     bool warp_mlp = false;
+    // trees currently held by the pools (for tsp_run_args.resume)
+    int tree_roots = 0, tree_sims = 0;
+    bool tree_fed = false;
     bool no_fast = false;
     bool no_wlo = false;
     int fast_groups = 0;  // TSP_FAST_GROUPS override (1, 2 or 4 groups of 16 trees per CTA)
@@ -603,7 +606,7 @@ int launch_search_x(tsp_engine* e, const SearchParams& p_in) {
     set_chunks(p.sched_b, GW * XW, e->ct_override);
     set_tile_groups(p.sched_a, TM, TM * GW * XW / 32, e->ng_override);
     set_tile_groups(p.sched_b, TM, TM * GW * XW / 32, e->ng_override);
-    const size_t smem = search_smem(p.sched_a, TM, p.S, WSMEM ? (size_t)p.w_smem_floats : 0);
+    const size_t smem = search_smem(p.sched_a, TM, p.S_tab, WSMEM ? (size_t)p.w_smem_floats : 0);
     int rc = set_smem(e, search_kernel<VARIANT, NC, TM, WSMEM, XW>, smem);
     if (rc) return rc;
     const int grid = (p.B + TM - 1) / TM;
@@ -614,6 +617,7 @@ int launch_search_x(tsp_engine* e, const SearchParams& p_in) {
     e->stats.search_smem_bytes = (int)smem;
     e->stats.trees_per_cta = TM;
     e->stats.threads_per_cta = TM * GW * XW;
+    e->stats.search_kernel = 0;
     return TSP_OK;
 }
 
@@ -645,7 +649,7 @@ size_t fast_smem(const FastSched& fs, int G, int S, bool w_lo = false) {
 
 template <int G>
 int launch_fast(tsp_engine* e, const FastParams& p) {
-    const size_t smem = fast_smem(e->fsched, G, p.S, p.w_lo != 0);
+    const size_t smem = fast_smem(e->fsched, G, p.S_tab, p.w_lo != 0);
     int rc = set_smem(e, search_fast_kernel<G>, smem);
     if (rc) return rc;
     const int grid = (p.B + G * GT - 1) / (G * GT);
@@ -656,6 +660,7 @@ int launch_fast(tsp_engine* e, const FastParams& p) {
     e->stats.search_smem_bytes = (int)smem;
     e->stats.trees_per_cta = G * GT;
     e->stats.threads_per_cta = G * GTHREADS;
+    e->stats.search_kernel = 1;
     return TSP_OK;
 }
 
@@ -669,6 +674,7 @@ int launch_fast_any(tsp_engine* e, const SearchParams& sp) {
     p.max_rec = sp.max_rec; p.T = sp.T; p.pb_stride = sp.pb_stride;
     p.discount = sp.discount; p.pb_table = sp.pb_table;
     p.two_player = sp.two_player;
+    p.S_tab = sp.S_tab; p.resume = sp.resume; p.add_noise = sp.add_noise; p.one_minus_frac = sp.one_minus_frac; p.frac = sp.frac; p.noise = sp.noise;
     p.discount_f = sp.two_player ? -(float)sp.discount : (float)sp.discount;
     p.blocks = sp.blocks; p.hidden_pool = sp.hidden_pool; p.hdr = sp.hdr; p.rootprior = sp.rootprior; p.rootact = sp.rootact;
     p.tie = sp.tie; p.fed = sp.fed; p.trace = sp.trace;
@@ -682,9 +688,9 @@ int launch_fast_any(tsp_engine* e, const SearchParams& sp) {
     // one weight copy.
     int G = 2;
     if (e->fast_groups == 1 || e->fast_groups == 2) G = e->fast_groups;
-    while (G > 1 && fast_smem(e->fsched, G, p.S) > 227 * 1024) G >>= 1;
+    while (G > 1 && fast_smem(e->fsched, G, p.S_tab) > 227 * 1024) G >>= 1;
     // host-split weights (no split arithmetic in the mma loop) when the doubled arena still fits
-    p.w_lo = (!e->no_wlo && fast_smem(e->fsched, G, p.S, true) <= 227 * 1024) ? 1 : 0;
+    p.w_lo = (!e->no_wlo && fast_smem(e->fsched, G, p.S_tab, true) <= 227 * 1024) ? 1 : 0;
     if (G == 2) return launch_fast<2>(e, p);
     return launch_fast<1>(e, p);
 }
@@ -692,19 +698,19 @@ int launch_fast_any(tsp_engine* e, const SearchParams& sp) {
 int launch_search_any(tsp_engine* e, const SearchParams& p_in) {
     SearchParams p = p_in;
     if (e->cfg.variant == 0 && e->nc == 5 && e->has_fast && !e->no_fast && e->finalized &&
-        fast_smem(e->fsched, 1, p.S) <= 227 * 1024)
+        fast_smem(e->fsched, 1, p.S_tab) <= 227 * 1024)
         return launch_fast_any(e, p);
     // 32 trees per CTA measured best at every batch size (4,096 .. 65,536 roots, both network sizes):
     // lane == row in the MLP phase wants a full warp of rows; 16 is the fallback when the activation
     // strips of 32 rows do not fit next to the weights.
     int TM = 32;
-    if (search_smem(p.sched_a, 32, p.S) > 110 * 1024) TM = 16;
+    if (search_smem(p.sched_a, 32, p.S_tab) > 110 * 1024) TM = 16;
     if (e->tm_override == 16 || e->tm_override == 32) TM = e->tm_override;
     if (e->nc != 5) TM = 32;
     // keep the search MLP weights in shared memory when two CTAs per SM still fit
     p.w_smem_floats = 0;
     if (p.fed == nullptr && !e->no_wsmem &&
-        search_smem(p.sched_a, TM, p.S, (size_t)e->search_floats) <= 112 * 1024)
+        search_smem(p.sched_a, TM, p.S_tab, (size_t)e->search_floats) <= 112 * 1024)
         p.w_smem_floats = (int)e->search_floats;
     const int v = e->cfg.variant;
     // helper warps for the MLP units pay off while there is at most one CTA per SM (they double the
@@ -982,8 +988,19 @@ int tsp_run(tsp_handle e, const tsp_run_args* a) {
     if (!fed && !e->finalized) return fail(e, TSP_ESTATE, "tsp_run before tsp_finalize_weights");
     if (B < 1 || B > c.max_roots) return fail(e, TSP_EINVAL, "num_roots %d outside 1..%d", B, c.max_roots);
     if (S < 0 || S > c.max_simulations) return fail(e, TSP_EINVAL, "num_simulations %d outside 0..%d", S, c.max_simulations);
-    if (fed && (!a->fed_root || (S > 0 && !a->fed_records))) return fail(e, TSP_EINVAL, "fed mode needs fed_root and fed_records");
-    if (!fed && !a->observations) return fail(e, TSP_EINVAL, "observations missing");
+    if (fed && ((!a->fed_root && !a->resume) || (S > 0 && !a->fed_records)))
+        return fail(e, TSP_EINVAL, "fed mode needs fed_root and fed_records");
+    const bool resume = a->resume != 0;
+    if (resume) {
+        if (c.variant == TSP_VARIANT_STOCHASTIC)  // its first assert fails on a visited root, self_play_stochastic.py:333
+            return fail(e, TSP_EINVAL, "resume: the stochastic search cannot be continued (the reference asserts "
+                                       "num_sims == sum of the root's child visits, self_play_stochastic.py:333)");
+        if (e->tree_roots != B) return fail(e, TSP_ESTATE, "resume: the previous tsp_run held %d roots, not %d", e->tree_roots, B);
+        if (e->tree_sims + S > c.max_simulations)
+            return fail(e, TSP_EINVAL, "resume: %d + %d simulations exceed max_simulations %d", e->tree_sims, S, c.max_simulations);
+        if (fed != e->tree_fed) return fail(e, TSP_EINVAL, "resume: fed / network mode must match the search being continued");
+    }
+    if (!fed && !resume && !a->observations) return fail(e, TSP_EINVAL, "observations missing");
     if (a->add_exploration_noise && !a->noise) return fail(e, TSP_EINVAL, "add_exploration_noise without a noise array");
     if ((a->legal_actions == nullptr) != (a->num_legal == nullptr))
         return fail(e, TSP_EINVAL, "legal_actions and num_legal must be given together");
@@ -1048,15 +1065,24 @@ int tsp_run(tsp_handle e, const tsp_run_args* a) {
     sp.max_rec = a->max_records;
     sp.T = a->tie_stream ? a->tie_len : 0;
     sp.K = a->chance_stream ? a->chance_len : 0;
-    sp.max_iters = (c.variant == 0) ? S : S + (S + 1) * A + 1;
+    // chance-node variants: every iteration either counts a simulation or expands one of the <= (states) * A
+    // transition nodes; a continued search may still find unexpanded transitions of the earlier searches
+    const int S_tree = (resume ? e->tree_sims : 0) + S;
+    sp.S_tab = S_tree;
+    sp.max_iters = (c.variant == 0) ? S : S + (S_tree + 1) * A + 1;
     sp.discount = c.discount;
     sp.two_player = c.num_players == 2 ? 1 : 0;
+    sp.resume = resume ? 1 : 0;
+    sp.add_noise = a->add_exploration_noise ? 1 : 0;
+    sp.frac = c.root_exploration_fraction;
+    sp.one_minus_frac = 1 - c.root_exploration_fraction;
+    sp.noise = np.noise;
     sp.pb_table = reinterpret_cast<const double*>(e->pbtable.p);
     sp.pb_stride = c.max_simulations + 2;
     sp.blocks = e->blocks.p;
     sp.hidden_pool = reinterpret_cast<float*>(e->hidden.p);
     sp.hdr = reinterpret_cast<TreeHeader*>(e->hdr.p);
-    sp.rootprior = reinterpret_cast<const double*>(e->rootprior.p);
+    sp.rootprior = reinterpret_cast<double*>(e->rootprior.p);
     sp.rootact = reinterpret_cast<const int*>(e->rootact.p);
     sp.W = reinterpret_cast<const float*>(e->arena.p);
     sp.phase_cycles = reinterpret_cast<unsigned long long*>(e->phase.p);
@@ -1090,15 +1116,17 @@ int tsp_run(tsp_handle e, const tsp_run_args* a) {
     if (e->ev_pending == tsp_engine::EV_RING && (rc = drain_events(e))) return rc;
     cudaEvent_t* ev = &e->ev[3 * ((e->ev_head + e->ev_pending) % tsp_engine::EV_RING)];
     CK(e, cudaEventRecord(ev[0], e->stream));
-    if ((rc = launch_net_any(e, np))) return rc;
+    if (!resume && (rc = launch_net_any(e, np))) return rc;
     CK(e, cudaEventRecord(ev[1], e->stream));
     if ((rc = launch_search_any(e, sp))) return rc;
     CK(e, cudaEventRecord(ev[2], e->stream));
     e->ev_pending++;
 
-    if ((rc = copy_out(e, mem, a->trace_root, np.trace_root, nb * REC))) return rc;
-    if ((rc = copy_out(e, mem, a->root_predicted_value, np.root_pred, nb))) return rc;
-    if ((rc = copy_out(e, mem, a->root_hidden, np.root_hidden, nb * H))) return rc;
+    if (!resume) {  // the root is not evaluated again on resume (root_predicted_value is None in the reference)
+        if ((rc = copy_out(e, mem, a->trace_root, np.trace_root, nb * REC))) return rc;
+        if ((rc = copy_out(e, mem, a->root_predicted_value, np.root_pred, nb))) return rc;
+        if ((rc = copy_out(e, mem, a->root_hidden, np.root_hidden, nb * H))) return rc;
+    }
     if ((rc = copy_out(e, mem, a->trace_records, sp.trace, nrec * REC))) return rc;
     if ((rc = copy_out(e, mem, a->visit_counts, sp.visit_counts, nb * A))) return rc;
     if ((rc = copy_out(e, mem, a->root_value, sp.root_value, nb))) return rc;
@@ -1109,6 +1137,9 @@ int tsp_run(tsp_handle e, const tsp_run_args* a) {
     if ((rc = copy_out(e, mem, a->num_records, sp.num_records, nb))) return rc;
     if ((rc = copy_out(e, mem, a->total_select_depth, sp.total_depth, nb))) return rc;
     e->stats.searches++;
+    e->tree_roots = B;
+    e->tree_sims = (resume ? e->tree_sims : 0) + S;
+    e->tree_fed = fed;
     return TSP_OK;
 }
 

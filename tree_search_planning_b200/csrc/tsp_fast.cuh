@@ -66,10 +66,14 @@ static_assert(sizeof(FastSched) % 16 == 0, "FastSched is copied in 16-byte words
 struct FastParams {
     int B, S, A, H, support, mask_absorbing, uniform_policy;
     int blocks_per_tree, hidden_per_tree, max_rec, T, pb_stride, w_lo, two_player;
+    int S_tab;                // simulations the trees hold after this run (size of the visit-count tables)
+    int resume, add_noise;    // resume: continue the trees of the previous run (override_root_with, self_play.py:331-333)
+    double one_minus_frac, frac;
+    const double* noise;      // [B][A], mixed into the root priors again on resume
     float discount_f;  // (float)discount for the selection filter, negated for two players (-child.value())
     double discount;
     const double* pb_table;
-    void* blocks; float* hidden_pool; TreeHeader* hdr; const double* rootprior; const int* rootact;
+    void* blocks; float* hidden_pool; TreeHeader* hdr; double* rootprior; const int* rootact;
     const unsigned char* tie;
     const float* fed; float* trace;
     const FastSched* sched;  // device copy
@@ -345,7 +349,7 @@ __global__ void __launch_bounds__(G * GTHREADS, 2 / G) search_fast_kernel(const 
     using Block = NodeBlock<NC>;
     // shared-memory carve-out: schedule (compile-time offset 0), tables, weights, per-group strips
     FastSched* fsp = reinterpret_cast<FastSched*>(smem);
-    const int pb_n = (p.S + 2 + 1) & ~1;
+    const int pb_n = (p.S_tab + 2 + 1) & ~1;  // S_tab: largest parent visit count (sums over continued searches)
     const int pbf_n = (pb_n + 3) & ~3;
     double* pb = reinterpret_cast<double*>(smem + sizeof(FastSched) / 4);  // pb[N] = log((N + base + 1) / base) + init
     double* sq = pb + pb_n;                                                // sq[N] = sqrt(N), host libm
@@ -357,7 +361,7 @@ __global__ void __launch_bounds__(G * GTHREADS, 2 / G) search_fast_kernel(const 
         int4* dst = reinterpret_cast<int4*>(fsp);
         for (int i = tid; i < (int)(sizeof(FastSched) / 16); i += THREADS) dst[i] = src[i];
     }
-    for (int i = tid; i < p.S + 2; i += THREADS) {
+    for (int i = tid; i < p.S_tab + 2; i += THREADS) {
         const double a = p.pb_table[i], c = p.pb_table[p.pb_stride + i];
         pb[i] = a;
         sq[i] = c;
@@ -414,6 +418,15 @@ __global__ void __launch_bounds__(G * GTHREADS, 2 / G) search_fast_kernel(const 
         if (j < GW) {
             root_prior = p.rootprior[(size_t)b * GW + j];
             root_act = p.rootact[(size_t)b * GW + j];
+        }
+        if (p.resume) {  // MCTS.run(..., override_root_with=root): keep the tree, fresh MinMaxStats / depth / streams
+            root_vsum = h.root_vsum;
+            root_visit = h.root_visit;
+            n_blocks = h.n_blocks;
+            if (p.add_noise && j < n_root) {  // add_exploration_noise once more, self_play.py:372-376, 540-549
+                root_prior = __dadd_rn(__dmul_rn(root_prior, p.one_minus_frac), __dmul_rn(p.noise[(size_t)b * A + j], p.frac));
+                p.rootprior[(size_t)b * GW + j] = root_prior;
+            }
         }
     }
     const float root_prior_f = (float)root_prior;
@@ -668,6 +681,9 @@ __global__ void __launch_bounds__(G * GTHREADS, 2 / G) search_fast_kernel(const 
             if (p.max_depth) p.max_depth[b] = max_depth;
             if (p.num_records) p.num_records[b] = n_rec;
             if (p.total_depth) p.total_depth[b] = depth_total;
+            p.hdr[b].root_vsum = root_vsum;  // what a continued search (resume) needs besides the pools
+            p.hdr[b].root_visit = root_visit;
+            p.hdr[b].n_blocks = n_blocks;
             if (p.phase_cycles) {  // how often the float32 filter had to defer to float64
                 atomicAdd(p.phase_cycles + 5, (unsigned long long)n_exact);
                 atomicAdd(p.phase_cycles + 6, (unsigned long long)depth_total);

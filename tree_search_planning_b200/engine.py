@@ -40,6 +40,7 @@ class _RunArgs(ctypes.Structure):
         ("num_roots", ctypes.c_int32), ("num_simulations", ctypes.c_int32), ("memory", ctypes.c_int32),
         ("add_exploration_noise", ctypes.c_int32), ("uniform_policy", ctypes.c_int32),
         ("max_records", ctypes.c_int32), ("tie_len", ctypes.c_int32), ("chance_len", ctypes.c_int32),
+        ("resume", ctypes.c_int32), ("reserved0", ctypes.c_int32),
         ("observations", _P), ("legal_actions", _P), ("num_legal", _P), ("noise", _P),
         ("tie_stream", _P), ("chance_stream", _P), ("fed_root", _P), ("fed_records", _P),
         ("visit_counts", _P), ("root_value", _P), ("child_value", _P), ("child_prior", _P),
@@ -55,7 +56,7 @@ class Stats(ctypes.Structure):
         ("last_root_ms", ctypes.c_float), ("sum_search_ms", ctypes.c_double), ("sum_root_ms", ctypes.c_double),
         ("timed_runs", ctypes.c_int64), ("sm_count", ctypes.c_int32), ("search_ctas", ctypes.c_int32),
         ("search_smem_bytes", ctypes.c_int32), ("trees_per_cta", ctypes.c_int32),
-        ("threads_per_cta", ctypes.c_int32), ("reserved", ctypes.c_int32),
+        ("threads_per_cta", ctypes.c_int32), ("search_kernel", ctypes.c_int32),
     ]
 
     def as_dict(self):
@@ -135,6 +136,7 @@ class Engine:
         self.max_roots = int(max_roots)
         self.max_simulations = int(config.num_simulations if max_simulations is None else max_simulations)
         self.device = int(device)
+        self.generation = 0
         if len(config.players) > 2:
             raise NotImplementedError("More than two player mode not implemented.")  # self_play.py:503
         c = _Config(self.variant, self.A, self.obs_dim, self.H, int(config.support_size), self.nf,
@@ -194,6 +196,7 @@ class Engine:
         return S if self.variant == 0 else S * (self.A + 2) + self.A + 2
 
     def run_raw(self, args):
+        self.generation += 1  # the pools now hold the trees of this search
         self._check(self.lib.tsp_run(self.handle, ctypes.byref(args)))
 
     def run(self, num_simulations=None, observations=None, legal_actions=None, num_legal=None, noise=None,
@@ -201,12 +204,15 @@ class Engine:
             fed_records=None, trace=False, max_records=None, want=("visit_counts", "root_value", "child_value",
                                                                    "child_prior", "child_reward", "max_tree_depth",
                                                                    "root_predicted_value", "num_records"),
-            want_root_hidden=False, synchronize=True, to_play=None):
+            want_root_hidden=False, synchronize=True, to_play=None, resume=False, num_roots=None):
         """Batched MCTS.run over HOST numpy arrays; returns a dict of numpy arrays.
 
         `to_play` ([B], MCTS.run's argument) is accepted for interface parity only: with players == [0, 1] the
         reference's arithmetic depends on whether a node and the leaf are an even number of plies apart
-        (self_play.py:492-500), never on which player the root belongs to."""
+        (self_play.py:492-500), never on which player the root belongs to.
+
+        `resume=True` continues the previous run's searches (MCTS.run's override_root_with, self_play.py:331-333):
+        no observations, `num_roots` roots, fresh MinMaxStats, noise mixed into the root priors again."""
         S = self.max_simulations if num_simulations is None else int(num_simulations)
         A = self.A
         keep = []
@@ -225,8 +231,10 @@ class Engine:
             B = observations.shape[0]
         elif fed_root is not None:
             B = numpy.asarray(fed_root).reshape(-1, REC_WIDTH).shape[0]
+        elif resume and num_roots is not None:
+            B = int(num_roots)
         else:
-            raise ValueError("observations (or fed_root) required")
+            raise ValueError("observations (or fed_root, or resume=True with num_roots) required")
         fed_root = prep(fed_root, numpy.float32, (B, REC_WIDTH))
         if fed_records is not None:
             fed_records = prep(fed_records, numpy.float32).reshape(B, -1, REC_WIDTH)
@@ -252,7 +260,7 @@ class Engine:
             out["trace_root"] = numpy.zeros((B, REC_WIDTH), numpy.float32)
             out["trace_records"] = numpy.zeros((B, max(max_records, 1), REC_WIDTH), numpy.float32)
         a = _RunArgs(B, S, MEM_HOST, int(bool(add_exploration_noise)), int(bool(uniform_policy)),
-                     int(max_records), T, K,
+                     int(max_records), T, K, int(bool(resume)), 0,
                      _ptr(observations), _ptr(legal_actions), _ptr(num_legal), _ptr(noise), _ptr(tie), _ptr(chance),
                      _ptr(fed_root), _ptr(fed_records),
                      _ptr(out.get("visit_counts")), _ptr(out.get("root_value")), _ptr(out.get("child_value")),
@@ -339,13 +347,14 @@ class Engine:
         self._check(self.lib.tsp_reset_timing(self.handle))
 
     def make_args(self, num_roots, num_simulations, memory, inputs, outputs, add_exploration_noise=True,
-                  uniform_policy=False, max_records=0, tie_len=0, chance_len=0):
+                  uniform_policy=False, max_records=0, tie_len=0, chance_len=0, resume=False):
         """Build a tsp_run_args over caller-owned buffers (numpy arrays, or torch tensors for device /
         pinned memory). `inputs` / `outputs` map the field names of tsp_run_args to buffers."""
         a = _RunArgs()
         a.num_roots, a.num_simulations, a.memory = int(num_roots), int(num_simulations), int(memory)
         a.add_exploration_noise, a.uniform_policy = int(bool(add_exploration_noise)), int(bool(uniform_policy))
         a.max_records, a.tie_len, a.chance_len = int(max_records), int(tie_len), int(chance_len)
+        a.resume = int(bool(resume))
         names = {n for n, _ in _RunArgs._fields_}
         for k, v in list(inputs.items()) + list(outputs.items()):
             if k not in names:

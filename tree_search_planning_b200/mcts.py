@@ -73,18 +73,27 @@ class RootView(ChildView):
 class BatchResult(dict):
     """Arrays of one batched search + per-root `root` views."""
 
-    def __init__(self, res, legal_lists, variant):
+    def __init__(self, res, legal_lists, variant, engine=None, resumed=False, hidden=None):
         super().__init__(res)
         self._legal = legal_lists
         self._variant = variant
+        self._engine = engine
+        self._generation = engine.generation if engine is not None else None
+        self._resumed = resumed
+        self._hidden = hidden  # root hidden states carried over a continued search
 
     def root(self, i):
         hid = self["root_hidden"][i][None] if "root_hidden" in self else None
-        return RootView(self, i, self._legal[i], self._variant, hid)
+        if hid is None and self._hidden is not None:
+            hid = self._hidden[i][None]
+        r = RootView(self, i, self._legal[i], self._variant, hid)
+        r._batch, r._index = self, i  # lets MCTS.run(..., override_root_with=root) find the device-resident tree
+        return r
 
     def extra_info(self, i):
         info = {"max_tree_depth": int(self["max_tree_depth"][i]),
-                "root_predicted_value": float(self["root_predicted_value"][i])}
+                # None when the search continued an existing root (self_play.py:331-333)
+                "root_predicted_value": None if self._resumed else float(self["root_predicted_value"][i])}
         if self._variant == 0:
             info["n_env_interactions"] = 0  # self_play.py:432
         return info
@@ -93,10 +102,13 @@ class BatchResult(dict):
 class MCTS:
     """Drop-in for self_play.MCTS / self_play_stochastic.MCTS / self_play_risk_sensitive.MCTS."""
 
-    def __init__(self, config, device=0, max_roots=1):
+    def __init__(self, config, device=0, max_roots=1, max_search_multiple=1):
+        """`max_search_multiple`: how many searches of config.num_simulations a tree may accumulate through
+        override_root_with / run_batch(resume=...) (sizes the device node pools)."""
         self.config = config
         self.device = device
         self.max_roots = max_roots
+        self.max_search_multiple = int(max_search_multiple)
         self.variant = variant_of(config)
 
     # -- engine management ---------------------------------------------------------------
@@ -120,10 +132,20 @@ class MCTS:
     # -- the reference surface ---------------------------------------------------------------
     def run(self, model, observation, legal_actions, to_play, add_exploration_noise, override_root_with=None,
             policy_only=False, uniform_policy=False):
-        if override_root_with is not None:
-            raise NotImplementedError("override_root_with: trees live on the device and are rebuilt per search")
         if self.variant != 0 and (policy_only or uniform_policy):
             raise TypeError("policy_only / uniform_policy exist only in self_play.MCTS.run")
+        if override_root_with is not None:
+            # self_play.py:331-333: continue the search of an existing root. The tree lives in the engine's pools,
+            # so the root must come from the latest search of this engine (no other search in between).
+            batch = getattr(override_root_with, "_batch", None)
+            if batch is None or batch._engine is None or batch._generation != batch._engine.generation:
+                raise ValueError("override_root_with must be the root returned by the latest MCTS.run / run_batch of "
+                                 "this engine: its tree is device-resident and the next search reuses the pools")
+            if len(batch._legal) != 1:
+                raise ValueError("override_root_with continues a whole batch: use run_batch(resume=batch)")
+            res = self.run_batch(model, None, add_exploration_noise=add_exploration_noise, policy_only=policy_only,
+                                 uniform_policy=uniform_policy, resume=batch)
+            return res.root(0), res.extra_info(0)
         assert legal_actions, f"Legal actions should not be an empty array. Got {legal_actions}."
         assert set(legal_actions).issubset(set(self.config.action_space)), \
             "Legal actions should be a subset of the action space."
@@ -134,16 +156,27 @@ class MCTS:
 
     def run_batch(self, model, observations, legal_actions=None, add_exploration_noise=True, noise=None, tie=None,
                   chance=None, policy_only=False, uniform_policy=False, num_simulations=None,
-                  want_root_hidden=False):
+                  want_root_hidden=False, resume=None):
         """B independent searches at once. `legal_actions`: list of B ordered lists (None = all).
         Random sources default to numpy.random like the reference (Dirichlet noise is drawn with the
-        very call of self_play.py:546); pass `noise` / `tie` / `chance` for reproducible searches."""
+        very call of self_play.py:546); pass `noise` / `tie` / `chance` for reproducible searches.
+        `resume`: the BatchResult of the latest search of this engine -- every one of its roots is searched
+        further (what MCTS.run does with override_root_with, self_play.py:331-333)."""
         cfg = self.config
         A = len(cfg.action_space)
-        observations = numpy.ascontiguousarray(observations, numpy.float32).reshape(-1, observation_dim(cfg))
-        B = observations.shape[0]
         S = 0 if policy_only else int(cfg.num_simulations if num_simulations is None else num_simulations)
-        legal_lists = [list(cfg.action_space)] * B if legal_actions is None else [list(l) for l in legal_actions]
+        if resume is not None:
+            if self.variant == 1:  # self_play_stochastic.py:333 fails on a root that already has visits
+                raise AssertionError("the stochastic search cannot be continued: the reference asserts "
+                                     "num_sims == sum(child.visit_count) (self_play_stochastic.py:333)")
+            legal_lists = resume._legal
+            B = len(legal_lists)
+            legal_actions = None  # the root's children are already in place
+            observations = None
+        else:
+            observations = numpy.ascontiguousarray(observations, numpy.float32).reshape(-1, observation_dim(cfg))
+            B = observations.shape[0]
+            legal_lists = [list(cfg.action_space)] * B if legal_actions is None else [list(l) for l in legal_actions]
         la = nl = None
         if legal_actions is not None:
             la = numpy.zeros((B, A), numpy.int32)
@@ -161,8 +194,17 @@ class MCTS:
             tie = numpy.random.randint(0, _STREAM_MOD, size=(B, 64)).astype(numpy.uint8)
         if chance is None and self.variant != 0:
             chance = numpy.random.randint(0, _STREAM_MOD, size=(B, max(64, 8 * S))).astype(numpy.uint8)
-        eng = self._engine(model, B, S)
+        if resume is not None:
+            eng = resume._engine
+            if resume._generation != eng.generation:
+                raise ValueError("resume: another search has run on this engine since; its trees are gone")
+            res = eng.run(S, noise=noise, tie=tie, chance=chance, add_exploration_noise=add_exploration_noise,
+                          uniform_policy=uniform_policy, resume=True, num_roots=B)
+            hidden = resume["root_hidden"] if "root_hidden" in resume else resume._hidden
+            return BatchResult(res, legal_lists, self.variant, engine=eng, resumed=True, hidden=hidden)
+        # room for continued searches: pools sized for a multiple of the configured simulations
+        eng = self._engine(model, B, S * self.max_search_multiple)
         res = eng.run(S, observations=observations, legal_actions=la, num_legal=nl, noise=noise, tie=tie,
                       chance=chance, add_exploration_noise=add_exploration_noise, uniform_policy=uniform_policy,
                       want_root_hidden=want_root_hidden)
-        return BatchResult(res, legal_lists, self.variant)
+        return BatchResult(res, legal_lists, self.variant, engine=eng)
