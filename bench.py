@@ -173,7 +173,7 @@ def run_reference_arm(args, rank):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------- GPU arm ----
@@ -278,8 +278,32 @@ def time_config(torch, dist, eng, cfg, B, S, steps, warmup, device, world, rank,
     return float(t.item()) / 1e3, extras
 
 
+_JSON_FD = None
+
+
+def guard_stdout():
+    """Libraries (NCCL prints its version banner) write to stdout; the driver wants exactly ONE JSON line there.
+    Everything but that line goes to stderr: fd 1 is pointed at fd 2 and the line is written to the saved fd."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_JSON_FD, data)
+
+
 def main():
     args = parse_args()
+    guard_stdout()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -349,7 +373,7 @@ def main():
     if args.sweep and world == 1:
         sweep(torch, dist, tsp, device, local_rank, flush, line)
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -197,6 +197,28 @@ int tsp_stochastic_dynamics(tsp_handle h, int32_t memory, int32_t B, const float
 int tsp_prediction(tsp_handle h, int32_t memory, int32_t B, const float *hidden, float *value,
                    float *policy_logits);
 
+/* ---- the data formats on either side of the search, on the device (batched self-play) ---- */
+
+/* replaces GameHistory.get_stacked_observations (self_play.py:587-624) for B rows at once.
+ *   frame_pool   [N][frame_size] float32 observation frames (frame_size = C*H*W of config.observation_shape)
+ *   frame_index  [B][so + 1] rows of frame_pool: the frame at `index`, then index-1, index-2, ...; -1 = before the
+ *                start of the game (the reference pads with zeros)
+ *   action_value [B][so] value of the action plane that follows past frame i (action_history[past + 1]; 0 when padded)
+ *   out          [B][obs_dim], obs_dim = frame_size*(so+1) + so*plane_size (plane_size = H*W) -- the layout
+ *                tsp_run / tsp_initial_inference take as `observations` */
+int tsp_stack_observations(tsp_handle h, int32_t memory, int32_t B, int32_t stacked_observations, int32_t frame_size,
+                           int32_t plane_size, const float *frame_pool, const int32_t *frame_index,
+                           const float *action_value, float *out);
+/* replaces SelfPlay.select_action (self_play.py:277-299) for B roots: temperature 0 = first arg-max of the visit
+ * counts over the ordered legal list, +inf = uniform, else numpy.random.choice(actions, p = visits^(1/T) / sum)
+ * with the caller's uniform samples u[B] in [0, 1) (inverse CDF, exactly numpy's algorithm).
+ * legal_actions / num_legal as in tsp_run (NULL = all actions). */
+int tsp_select_action(tsp_handle h, int32_t memory, int32_t B, const int32_t *visit_counts, const int32_t *legal_actions,
+                      const int32_t *num_legal, double temperature, const double *uniform, int32_t *action);
+/* replaces the policy target of GameHistory.store_search_statistics (self_play.py:570-585):
+ * child_visits[B][A] = visit_count / max(sum of the root's visit counts, 1) in float64 */
+int tsp_search_statistics(tsp_handle h, int32_t memory, int32_t B, const int32_t *visit_counts, double *child_visits);
+
 int tsp_synchronize(tsp_handle h);
 int tsp_get_stats(tsp_handle h, tsp_stats *out);
 /* zero sum_search_ms / sum_root_ms / timed_runs (synchronizes the stream) */

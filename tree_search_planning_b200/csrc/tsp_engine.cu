@@ -3,6 +3,7 @@
 // There is no CPU fallback in this file: every entry point either runs CUDA kernels or fails.
 #include "tsp_device.cuh"
 #include "tsp_fast.cuh"
+#include "tsp_rootio.cuh"
 #include "../../include/tsp.h"
 
 #include <algorithm>
@@ -1211,6 +1212,64 @@ int tsp_prediction(tsp_handle e, int32_t memory, int32_t B, const float* hidden,
     float* outs[8] = {value, nullptr, nullptr, policy_logits, nullptr, nullptr, nullptr, nullptr};
     const size_t cnt[8] = {n, 0, 0, n * c.num_actions, 0, 0, 0, 0};
     return net_call(e, 3, e->sch_pred, memory, B, hidden, c.encoding_size, nullptr, outs, cnt);
+}
+
+int tsp_stack_observations(tsp_handle e, int32_t memory, int32_t B, int32_t so, int32_t F, int32_t HW, const float* frame_pool,
+                           const int32_t* frame_index, const float* action_value, float* out) {
+    if (!e) return TSP_EINVAL;
+    if (B < 1 || so < 0 || F < 1 || HW < 0 || !frame_pool || !frame_index || !out || (so > 0 && !action_value))
+        return fail(e, TSP_EINVAL, "tsp_stack_observations: bad argument");
+    if (F * (so + 1) + so * HW != e->cfg.obs_dim)
+        return fail(e, TSP_EINVAL, "tsp_stack_observations: frame_size * (so + 1) + so * plane_size = %d, obs_dim is %d",
+                    F * (so + 1) + so * HW, e->cfg.obs_dim);
+    if (memory != TSP_MEM_DEVICE)
+        return fail(e, TSP_EINVAL, "tsp_stack_observations takes DEVICE buffers (the frame pool stays on the device)");
+    CK(e, cudaSetDevice(e->device));
+    stack_observations_kernel<<<B, 128, 0, e->stream>>>(B, so, F, HW, frame_pool, frame_index, action_value, out);
+    CK(e, cudaGetLastError());
+    e->stats.kernel_launches++;
+    return TSP_OK;
+}
+
+int tsp_select_action(tsp_handle e, int32_t memory, int32_t B, const int32_t* visit_counts, const int32_t* legal_actions,
+                      const int32_t* num_legal, double temperature, const double* uniform, int32_t* action) {
+    if (!e) return TSP_EINVAL;
+    const int A = e->cfg.num_actions;
+    if (B < 1 || !visit_counts || !action || (legal_actions == nullptr) != (num_legal == nullptr) || temperature < 0)
+        return fail(e, TSP_EINVAL, "tsp_select_action: bad argument");
+    if (temperature != 0.0 && !uniform) return fail(e, TSP_EINVAL, "tsp_select_action: uniform samples required for temperature > 0");
+    CK(e, cudaSetDevice(e->device));
+    const size_t nb = (size_t)B;
+    const int32_t *d_v, *d_l, *d_n;
+    const double* d_u;
+    int32_t* d_a;
+    int rc;
+    if ((rc = stage_in(e, memory, visit_counts, nb * A, e->s_visits, &d_v))) return rc;
+    if ((rc = stage_in(e, memory, legal_actions, nb * A, e->s_legal, &d_l))) return rc;
+    if ((rc = stage_in(e, memory, num_legal, nb, e->s_nlegal, &d_n))) return rc;
+    if ((rc = stage_in(e, memory, uniform, nb, e->s_noise, &d_u))) return rc;
+    if ((rc = stage_out(e, memory, action, nb, e->s_depth, &d_a))) return rc;
+    select_action_kernel<<<(B + 127) / 128, 128, 0, e->stream>>>(B, A, d_v, d_l, d_n, temperature, d_u, d_a);
+    CK(e, cudaGetLastError());
+    e->stats.kernel_launches++;
+    return copy_out(e, memory, action, d_a, nb);
+}
+
+int tsp_search_statistics(tsp_handle e, int32_t memory, int32_t B, const int32_t* visit_counts, double* child_visits) {
+    if (!e) return TSP_EINVAL;
+    const int A = e->cfg.num_actions;
+    if (B < 1 || !visit_counts || !child_visits) return fail(e, TSP_EINVAL, "tsp_search_statistics: bad argument");
+    CK(e, cudaSetDevice(e->device));
+    const size_t nb = (size_t)B;
+    const int32_t* d_v;
+    double* d_c;
+    int rc;
+    if ((rc = stage_in(e, memory, visit_counts, nb * A, e->s_visits, &d_v))) return rc;
+    if ((rc = stage_out(e, memory, child_visits, nb * A, e->s_cval, &d_c))) return rc;
+    search_statistics_kernel<<<(B + 127) / 128, 128, 0, e->stream>>>(B, A, d_v, d_c);
+    CK(e, cudaGetLastError());
+    e->stats.kernel_launches++;
+    return copy_out(e, memory, child_visits, d_c, nb * A);
 }
 
 int tsp_synchronize(tsp_handle e) {

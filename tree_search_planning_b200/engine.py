@@ -68,6 +68,7 @@ ABI_SYMBOLS = (
     "tsp_abi_version", "tsp_create", "tsp_destroy", "tsp_last_error", "tsp_set_layer", "tsp_finalize_weights",
     "tsp_weight_arena", "tsp_run", "tsp_initial_inference", "tsp_recurrent_inference", "tsp_stochastic_dynamics",
     "tsp_prediction", "tsp_synchronize", "tsp_get_stats", "tsp_reset_timing", "tsp_debug_phase_cycles", "tsp_stream",
+    "tsp_stack_observations", "tsp_select_action", "tsp_search_statistics",
 )
 
 _lib = None
@@ -102,6 +103,9 @@ def load_library(path=None):
     lib.tsp_reset_timing.argtypes = [_P]
     lib.tsp_debug_phase_cycles.argtypes = [_P, ctypes.POINTER(ctypes.c_uint64 * 64), ctypes.c_int32]
     lib.tsp_stream.argtypes = [_P, ctypes.POINTER(_P)]
+    lib.tsp_stack_observations.argtypes = [_P] + [ctypes.c_int32] * 5 + [_P] * 4
+    lib.tsp_select_action.argtypes = [_P, ctypes.c_int32, ctypes.c_int32, _P, _P, _P, ctypes.c_double, _P, _P]
+    lib.tsp_search_statistics.argtypes = [_P, ctypes.c_int32, ctypes.c_int32, _P, _P]
     if path is None:
         _lib = lib
     return lib
@@ -274,6 +278,46 @@ class Engine:
             self._keep = keep  # keep host inputs alive until the caller synchronizes
         return out
 
+    # -- root I/O formats on the device ---------------------------------------------
+    def stack_observations(self, frame_pool, frame_index, action_value, out, stacked_observations, frame_size,
+                           plane_size):
+        """GameHistory.get_stacked_observations for B rows; DEVICE buffers (torch tensors), asynchronous."""
+        B = int(frame_index.shape[0])
+        self._check(self.lib.tsp_stack_observations(self.handle, MEM_DEVICE, B, int(stacked_observations),
+                                                    int(frame_size), int(plane_size), _ptr(frame_pool),
+                                                    _ptr(frame_index), _ptr(action_value), _ptr(out)))
+
+    def select_action(self, visit_counts, temperature, uniform=None, legal_actions=None, num_legal=None, out=None,
+                      memory=None):
+        """SelfPlay.select_action for B roots. numpy arrays (HOST, synchronous) or torch CUDA tensors (DEVICE)."""
+        dev = _is_torch_tensor(visit_counts)
+        mem = (MEM_DEVICE if dev else MEM_HOST) if memory is None else memory
+        B = int(visit_counts.shape[0])
+        if not dev:
+            visit_counts = numpy.ascontiguousarray(visit_counts, numpy.int32)
+            uniform = None if uniform is None else numpy.ascontiguousarray(uniform, numpy.float64)
+            legal_actions = None if legal_actions is None else numpy.ascontiguousarray(legal_actions, numpy.int32)
+            num_legal = None if num_legal is None else numpy.ascontiguousarray(num_legal, numpy.int32)
+            out = numpy.zeros(B, numpy.int32) if out is None else out
+        self._check(self.lib.tsp_select_action(self.handle, mem, B, _ptr(visit_counts), _ptr(legal_actions),
+                                               _ptr(num_legal), float(temperature), _ptr(uniform), _ptr(out)))
+        if not dev:
+            self.synchronize()
+        return out
+
+    def search_statistics(self, visit_counts, out=None, memory=None):
+        """The policy target of GameHistory.store_search_statistics for B roots: visits / max(sum, 1), float64."""
+        dev = _is_torch_tensor(visit_counts)
+        mem = (MEM_DEVICE if dev else MEM_HOST) if memory is None else memory
+        B = int(visit_counts.shape[0])
+        if not dev:
+            visit_counts = numpy.ascontiguousarray(visit_counts, numpy.int32)
+            out = numpy.zeros((B, self.A), numpy.float64) if out is None else out
+        self._check(self.lib.tsp_search_statistics(self.handle, mem, B, _ptr(visit_counts), _ptr(out)))
+        if not dev:
+            self.synchronize()
+        return out
+
     # -- network entry points --------------------------------------------------------------
     def initial_inference(self, observations):
         obs = numpy.ascontiguousarray(observations, numpy.float32).reshape(-1, self.obs_dim)
@@ -285,6 +329,12 @@ class Engine:
                                                    _ptr(out["value_logits"])))
         self.synchronize()
         return out
+
+    def initial_inference_device(self, observations, value=None, policy_logits=None, hidden=None, value_logits=None):
+        """tsp_initial_inference over DEVICE buffers (torch CUDA tensors), asynchronous on the engine's stream."""
+        B = int(observations.shape[0])
+        self._check(self.lib.tsp_initial_inference(self.handle, MEM_DEVICE, B, _ptr(observations), _ptr(value),
+                                                   _ptr(policy_logits), _ptr(hidden), _ptr(value_logits)))
 
     def recurrent_inference(self, hidden, action):
         h = numpy.ascontiguousarray(hidden, numpy.float32).reshape(-1, self.H)
