@@ -91,10 +91,13 @@ struct tsp_engine {
     DevBuf arena;  // packed weights
     int64_t arena_floats = 0;
     int64_t search_floats = 0;  // leading part of the arena used by the search kernel (everything but the representation net)
-    DevBuf farena, fsched_dev;  // fast search kernel: fragment-ordered weights, FastSched
+    // fast search kernel: fragment-ordered weights; one FastSched per group shape ([0]: 8 warps / 16 lanes per tree,
+    // [1]: 4 warps / 8 lanes per tree)
+    DevBuf farena, fsched_dev[2];
     int64_t farena_floats = 0;
-    FastSched fsched{};
+    FastSched fsched[2]{};
     bool has_fast = false;
+    int fast_lpt = 0;     // TSP_FAST_LPT override (8 or 16 lanes per tree)
     DevBuf blocks, hidden, hdr, rootprior, rootact, pbtable, phase;
     bool phase_timing = false;
     int blocks_per_tree = 0, hidden_per_tree = 0, max_iters = 0;
@@ -287,7 +290,7 @@ int lower(tsp_engine* e, const HSched& hs, Schedule& sc, bool keep_input = false
 // Fast search kernel (tsp_fast.cuh): lower a schedule to per-stage, per-warp lists of 16 x 8 output tiles.
 // Returns TSP_OK with e->has_fast == false when the network does not fit the fast path's constraints
 // (the generic search kernel then runs it).
-int lower_fast(tsp_engine* e, const HSched& hs) {
+int lower_fast(tsp_engine* e, const HSched& hs, int which, int GWARPS) {
     e->has_fast = false;
     const int ns = (int)hs.stages.size();
     if (ns > FAST_MAX_STAGES) return TSP_OK;
@@ -299,7 +302,7 @@ int lower_fast(tsp_engine* e, const HSched& hs) {
     // STS.128 of lanes g, g + 1 conflict-free
     total += ((8 - total % 16) + 16) % 16;
     if (off[hs.in_buf] != 0 || total > 4000) return TSP_OK;
-    FastSched& fs = e->fsched;
+    FastSched& fs = e->fsched[which];
     memset(&fs, 0, sizeof(fs));
     fs.n_stages = ns;
     fs.row_stride = 2 * total;
@@ -358,9 +361,9 @@ int lower_fast(tsp_engine* e, const HSched& hs) {
     }
     fs.n_units = nu;
     fs.w_floats = (int)e->farena_floats;
-    int rc = ensure(e, e->fsched_dev, sizeof(FastSched));
+    int rc = ensure(e, e->fsched_dev[which], sizeof(FastSched));
     if (rc) return rc;
-    CK(e, cudaMemcpyAsync(e->fsched_dev.p, &fs, sizeof(FastSched), cudaMemcpyHostToDevice, e->stream));
+    CK(e, cudaMemcpyAsync(e->fsched_dev[which].p, &fs, sizeof(FastSched), cudaMemcpyHostToDevice, e->stream));
     CK(e, cudaStreamSynchronize(e->stream));
     e->has_fast = true;
     return TSP_OK;
@@ -492,9 +495,11 @@ int build_schedules(tsp_engine* e) {
         if ((rc = lower(e, make(have_terminal), e->sch_recur))) return rc;
         e->has_recur = true;
         // the search evaluates the terminal head only under mask_absorbing_states (self_play.py:415)
-        if (e->nc == 5 && e->farena_floats > 0 && H % 16 == 0 && (!c.mask_absorbing_states || have_terminal) &&
-            (rc = lower_fast(e, make(c.mask_absorbing_states != 0))))
-            return rc;
+        if (e->nc == 5 && e->farena_floats > 0 && H % 16 == 0 && (!c.mask_absorbing_states || have_terminal)) {
+            const HSched fh = make(c.mask_absorbing_states != 0);
+            if ((rc = lower_fast(e, fh, 0, 8))) return rc;
+            if (e->has_fast && (rc = lower_fast(e, fh, 1, 4))) return rc;
+        }
     } else {  // one future of MuZeroStochasticConcat.dynamics: models.py:520-595
         HSched hs;
         hs.in_dim = H;
@@ -648,13 +653,14 @@ size_t fast_smem(const FastSched& fs, int G, int S, bool w_lo = false) {
            (size_t)G * (GT * fs.row_stride + 2 * GT + GT * PATH_LEVELS) * 4;
 }
 
-template <int G>
+template <int G, int LPT>
 int launch_fast(tsp_engine* e, const FastParams& p) {
-    const size_t smem = fast_smem(e->fsched, G, p.S_tab, p.w_lo != 0);
-    int rc = set_smem(e, search_fast_kernel<G>, smem);
+    const size_t smem = fast_smem(e->fsched[LPT == 16 ? 0 : 1], G, p.S_tab, p.w_lo != 0);
+    int rc = set_smem(e, search_fast_kernel<G, LPT>, smem);
     if (rc) return rc;
     const int grid = (p.B + G * GT - 1) / (G * GT);
-    search_fast_kernel<G><<<grid, G * GTHREADS, smem, e->stream>>>(p);
+    constexpr int GTHREADS = GT * LPT;
+    search_fast_kernel<G, LPT><<<grid, G * GTHREADS, smem, e->stream>>>(p);
     CK(e, cudaGetLastError());
     e->stats.kernel_launches++;
     e->stats.search_ctas = grid;
@@ -679,27 +685,38 @@ int launch_fast_any(tsp_engine* e, const SearchParams& sp) {
     p.discount_f = sp.two_player ? -(float)sp.discount : (float)sp.discount;
     p.blocks = sp.blocks; p.hidden_pool = sp.hidden_pool; p.hdr = sp.hdr; p.rootprior = sp.rootprior; p.rootact = sp.rootact;
     p.tie = sp.tie; p.fed = sp.fed; p.trace = sp.trace;
-    p.sched = reinterpret_cast<const FastSched*>(e->fsched_dev.p);
     p.wfrag = reinterpret_cast<const float*>(e->farena.p);
     p.visit_counts = sp.visit_counts; p.root_value = sp.root_value; p.child_value = sp.child_value;
     p.child_prior = sp.child_prior; p.child_reward = sp.child_reward;
     p.max_depth = sp.max_depth; p.num_records = sp.num_records; p.total_depth = sp.total_depth;
     p.phase_cycles = sp.phase_cycles;
-    // 8 warps per group at <= 128 registers per thread: two groups per SM either way; two groups per CTA share
-    // one weight copy.
-    int G = 2;
-    if (e->fast_groups == 1 || e->fast_groups == 2) G = e->fast_groups;
-    while (G > 1 && fast_smem(e->fsched, G, p.S_tab) > 227 * 1024) G >>= 1;
+    // Group shape. Few roots (<= 2 groups of 16 trees per SM): the search is latency-bound -- 8 warps per group,
+    // two groups per CTA sharing one weight copy. Many roots: 4 warps per group (four trees per warp: fewer issued
+    // instructions per simulation) and four groups per CTA = 64 trees per SM at the same 16 warps.
+    const int groups = (p.B + GT - 1) / GT;
+    int lpt = groups <= 2 * e->sm_count ? 16 : 8;
+    if (e->fast_lpt == 8 || e->fast_lpt == 16) lpt = e->fast_lpt;
+    const int which = lpt == 16 ? 0 : 1;
+    p.sched = reinterpret_cast<const FastSched*>(e->fsched_dev[which].p);
+    int G = lpt == 16 ? 2 : 4;
+    if (e->fast_groups == 1 || e->fast_groups == 2 || (e->fast_groups == 4 && lpt == 8)) G = e->fast_groups;
+    while (G > 1 && fast_smem(e->fsched[which], G, p.S_tab) > 227 * 1024) G >>= 1;
     // host-split weights (no split arithmetic in the mma loop) when the doubled arena still fits
-    p.w_lo = (!e->no_wlo && fast_smem(e->fsched, G, p.S_tab, true) <= 227 * 1024) ? 1 : 0;
-    if (G == 2) return launch_fast<2>(e, p);
-    return launch_fast<1>(e, p);
+    p.w_lo = (!e->no_wlo && fast_smem(e->fsched[which], G, p.S_tab, true) <= 227 * 1024) ? 1 : 0;
+    if (lpt == 8) {
+        if (G == 4) return launch_fast<4, 8>(e, p);
+        if (G == 2) return launch_fast<2, 8>(e, p);
+        return launch_fast<1, 8>(e, p);
+    }
+    if (G == 2) return launch_fast<2, 16>(e, p);
+    return launch_fast<1, 16>(e, p);
 }
+
 
 int launch_search_any(tsp_engine* e, const SearchParams& p_in) {
     SearchParams p = p_in;
     if (e->cfg.variant == 0 && e->nc == 5 && e->has_fast && !e->no_fast && e->finalized &&
-        fast_smem(e->fsched, 1, p.S_tab) <= 227 * 1024)
+        fast_smem(e->fsched[0], 1, p.S_tab) <= 227 * 1024)
         return launch_fast_any(e, p);
     // 32 trees per CTA measured best at every batch size (4,096 .. 65,536 roots, both network sizes):
     // lane == row in the MLP phase wants a full warp of rows; 16 is the fallback when the activation
@@ -844,6 +861,7 @@ int tsp_create(const tsp_config* cfg, tsp_handle* out) {
     if (const char* t = getenv("TSP_NO_FAST")) e->no_fast = atoi(t) != 0;
     if (const char* t = getenv("TSP_NO_WLO")) e->no_wlo = atoi(t) != 0;
     if (const char* t = getenv("TSP_FAST_GROUPS")) e->fast_groups = atoi(t);
+    if (const char* t = getenv("TSP_FAST_LPT")) e->fast_lpt = atoi(t);
     auto bail = [&](int rc) {
         g_create_error = e->err;
         tsp_destroy(e);
@@ -900,7 +918,7 @@ int tsp_destroy(tsp_handle e) {
     if (!e) return TSP_OK;
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
-    for (DevBuf* b : {&e->arena, &e->farena, &e->fsched_dev, &e->blocks, &e->hidden, &e->hdr, &e->rootprior, &e->rootact, &e->pbtable, &e->phase, &e->s_obs,
+    for (DevBuf* b : {&e->arena, &e->farena, &e->fsched_dev[0], &e->fsched_dev[1], &e->blocks, &e->hidden, &e->hdr, &e->rootprior, &e->rootact, &e->pbtable, &e->phase, &e->s_obs,
                       &e->s_legal, &e->s_nlegal, &e->s_noise, &e->s_tie, &e->s_chance, &e->s_fedroot, &e->s_fed,
                       &e->s_visits, &e->s_rootv, &e->s_cval, &e->s_cprior, &e->s_crew, &e->s_depth, &e->s_rpred,
                       &e->s_rhid, &e->s_nrec, &e->s_troot, &e->s_trace, &e->s_tdepth, &e->n_in, &e->n_act})

@@ -32,9 +32,12 @@
 namespace tsp {
 
 constexpr int GT = 16;               // trees per group (one mma row tile)
-constexpr int LPT = 16;              // lanes per tree: lanes 0..7 score the children, all 16 move data
-constexpr int GTHREADS = GT * LPT;   // 256 threads = 8 warps
-constexpr int GWARPS = GTHREADS / 32;
+// Lanes per tree (template parameter LPT of the kernel): lanes 0..7 score the children, all LPT lanes move data.
+//   LPT = 16: 8 warps per group, two trees per warp  -- shortest warp programs, for batches that leave the GPU
+//             latency-bound (<= ~2 groups per SM, e.g. 4,096 roots);
+//   LPT =  8: 4 warps per group, four trees per warp -- fewer issued instructions per simulation and 64 trees per SM
+//             (four groups) at the same 16 warps, for large batches (throughput-bound).
+constexpr int MAX_GWARPS = 8;
 constexpr int FAST_MAX_TILES = 200;
 constexpr int FAST_MAX_STAGES = 12;
 constexpr int PATH_LEVELS = 32;      // levels recorded per descent for the lane-parallel backup
@@ -58,7 +61,7 @@ struct FastSched {
     int n_stages, row_stride, n_units, w_floats;
     short off_hidden, off_pl, off_vl, off_rl, off_tl, pad[3];
     int4 stage[FAST_MAX_STAGES];          // {row_op, 2 * r_in, 2 * r_out, r_n}; row_op 1: min-max normalise
-    int ulist[FAST_MAX_STAGES][GWARPS];   // units of warp w in stage s: first | count << 16
+    int ulist[FAST_MAX_STAGES][MAX_GWARPS];   // units of warp w in stage s: first | count << 16
     FUnit units[FAST_MAX_TILES];
 };
 static_assert(sizeof(FastSched) % 16 == 0, "FastSched is copied in 16-byte words");
@@ -88,6 +91,7 @@ __device__ __forceinline__ float rcp_approx(float x) {  // MUFU.RCP, <= 1 ulp
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
+template <int GTHREADS>
 __device__ __forceinline__ void group_barrier(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(GTHREADS) : "memory"); }
 
 // column k of a row inside the interleaved strip (see the header comment)
@@ -159,7 +163,8 @@ __device__ __forceinline__ void mma_unit(const int4 ua, const int4 ub, const flo
         *reinterpret_cast<float4*>(y + lo_off) = make_float4(tf32_lo(d0), tf32_lo(d2), tf32_lo(d1), tf32_lo(d3));
 }
 
-// All stages of the schedule for the 16 rows of one group; called by the 8 warps of the group.
+// All stages of the schedule for the 16 rows of one group; called by the warps of the group.
+template <int LPT>
 __device__ __forceinline__ void fast_mlp(const FastSched& fs, const float* __restrict__ W, float* __restrict__ act,
                                          const int* __restrict__ row_action, const unsigned char* __restrict__ row_active,
                                          int gt, int barid, int wlo_off, unsigned long long* dbg) {
@@ -206,7 +211,7 @@ __device__ __forceinline__ void fast_mlp(const FastSched& fs, const float* __res
         const int4 sg = fs.stage[s];
         if (sg.x == 1) {
             // models.py:223-231 / 248-255: (x - min) / scale, scale += 1e-5 only where scale < 1e-5
-            const int row = gt >> 4, j = gt & 15;
+            const int row = gt / LPT, j = gt % LPT;
             {   // both trees of a warp run this in lock step (full-mask shuffles); idle rows compute on stale data
                 const float* x = act + (row & 7) * rs + (row >> 3) + sg.y;
                 float mn = CUDART_INF_F, mx = -CUDART_INF_F;
@@ -232,7 +237,7 @@ __device__ __forceinline__ void fast_mlp(const FastSched& fs, const float* __res
             }
         }
         if (dbg && threadIdx.x == 0) d1 = clock64();
-        group_barrier(barid);
+        group_barrier<GT * LPT>(barid);
         if (dbg && threadIdx.x == 0) {
             const long long d2 = clock64();
             atomicAdd(dbg + 8 + 2 * s, (unsigned long long)(d1 - d0));
@@ -244,6 +249,7 @@ __device__ __forceinline__ void fast_mlp(const FastSched& fs, const float* __res
 // value and reward decode (models.py:1180-1201) and the policy softmax (self_play.py:532-538) of one row
 // by the 16 lanes of its tree, with the three max-reductions and the five sum-reductions sharing their
 // shuffle rounds. vl / rl / pl point at column 0 of the row inside the interleaved strip (column k at kofs(k)).
+template <int LPT>
 __device__ __forceinline__ void decode_row(const float* __restrict__ vl, const float* __restrict__ rl,
                                            const float* __restrict__ pl, int support, int A, bool uniform, int j,
                                            float& value, float& reward, float& prior) {
@@ -341,10 +347,13 @@ __device__ __noinline__ void backup_walk(NodeBlock<5>* blocks, int cur, int cs, 
     mm.update(__dadd_rn(0.0, __dmul_rn(discount, two ? -q : q)));
 }
 
-template <int G>
-__global__ void __launch_bounds__(G * GTHREADS, 2 / G) search_fast_kernel(const __grid_constant__ FastParams p) {
+template <int G, int LPT>
+__global__ void __launch_bounds__(G * GT * LPT, 512 / (G * GT * LPT)) search_fast_kernel(const __grid_constant__ FastParams p) {
     extern __shared__ __align__(16) float smem[];
+    constexpr int GTHREADS = GT * LPT;
     constexpr int THREADS = G * GTHREADS;
+    static_assert(LPT == 8 || LPT == 16, "8 or 16 lanes per tree");
+    static_assert(THREADS <= 512, "128 registers per thread");
     constexpr int NC = 5;
     using Block = NodeBlock<NC>;
     // shared-memory carve-out: schedule (compile-time offset 0), tables, weights, per-group strips
@@ -384,13 +393,13 @@ __global__ void __launch_bounds__(G * GTHREADS, 2 / G) search_fast_kernel(const 
     float* act = wsm + w_total + grp * (GT * rs + GT + GT + GT * PATH_LEVELS);
     int* row_action = reinterpret_cast<int*>(act + GT * rs);
     unsigned char* row_active = reinterpret_cast<unsigned char*>(row_action + GT);
-    const int row = gt >> 4;                                 // tree of the group == row of the strip
+    const int row = gt / LPT;                                // tree of the group == row of the strip
     int* path = row_action + 2 * GT + row * PATH_LEVELS;     // (block << 8 | slot) per level of this tree's descent
     float* rowp = act + (row & 7) * rs + (row >> 3);         // column 0 of this tree's row in the interleaved strip
     const int barid = 1 + grp;
 
-    const int lane = tid & 31, j = tid & 15;
-    const int gl0 = lane & 16;
+    const int lane = tid & 31, j = tid % LPT;
+    const int gl0 = lane & (32 - LPT);  // first lane of this tree inside the warp
     const int b = (blockIdx.x * G + grp) * GT + row;
     const bool valid = b < p.B;
     const int A = p.A, H = p.H;
@@ -534,11 +543,11 @@ __global__ void __launch_bounds__(G * GTHREADS, 2 / G) search_fast_kernel(const 
                 }
             }
             if (p.phase_cycles && tid == 0) tc1 = clock64();
-            group_barrier(barid);
+            group_barrier<GTHREADS>(barid);
             if (p.phase_cycles && tid == 0) tc2 = clock64();
-            fast_mlp(fs, wsm, act, row_action, row_active, gt, barid, wlo_off, p.phase_cycles);
+            fast_mlp<LPT>(fs, wsm, act, row_action, row_active, gt, barid, wlo_off, p.phase_cycles);
             if (p.phase_cycles && tid == 0) tc3 = clock64();
-            decode_row(rowp + 2 * fs.off_vl, rowp + 2 * fs.off_rl, rowp + 2 * fs.off_pl, p.support, A, p.uniform_policy != 0,
+            decode_row<LPT>(rowp + 2 * fs.off_vl, rowp + 2 * fs.off_rl, rowp + 2 * fs.off_pl, p.support, A, p.uniform_policy != 0,
                        j, value, reward, prior);
             if (p.mask_absorbing) terminal = rowp[2 * fs.off_tl];
         } else if (active) {
@@ -551,16 +560,20 @@ __global__ void __launch_bounds__(G * GTHREADS, 2 / G) search_fast_kernel(const 
 
         // ================= expansion + backup =================
         {
-            const float pj = __shfl_sync(FULL, prior, (gl0 + ((j - 4) & 15)) & 31);
-            if (active && trace_rec && n_rec < p.max_rec) {
-                float* tr = trace_rec + (size_t)n_rec * REC;
-                float tv = 0.0f;
-                if (j == 0) tv = 1.0f;
-                if (j == 1) tv = value;
-                if (j == 2) tv = reward;
-                if (j == 3) tv = terminal;
-                if (j >= 4 && j < 4 + A) tv = pj;
-                tr[j] = tv;  // REC == LPT == 16
+            // record: [0]=1 [1]=value [2]=reward [3]=terminal [4..4+A) priors; the LPT lanes write REC / LPT entries each
+#pragma unroll
+            for (int q = 0; q < REC / LPT; ++q) {
+                const int k = j + q * LPT;
+                const float pk = __shfl_sync(FULL, prior, (gl0 + ((k - 4) & (LPT - 1))) & 31);
+                if (active && trace_rec && n_rec < p.max_rec) {
+                    float tv = 0.0f;
+                    if (k == 0) tv = 1.0f;
+                    if (k == 1) tv = value;
+                    if (k == 2) tv = reward;
+                    if (k == 3) tv = terminal;
+                    if (k >= 4 && k < 4 + A) tv = pk;
+                    trace_rec[(size_t)n_rec * REC + k] = tv;
+                }
             }
             if (active) n_rec++;
             Block* pblk = blocks + node;
@@ -601,10 +614,12 @@ __global__ void __launch_bounds__(G * GTHREADS, 2 / G) search_fast_kernel(const 
             // the unexpanded (masked terminal) leaf whose to_play is still -1
             const bool two = p.two_player != 0;
             const int dact = active ? depth : 0;
-            const int dmax = max(dact, __shfl_xor_sync(FULL, dact, 16));
+            int dmax = dact;  // the deepest descent among the trees of this warp
+#pragma unroll
+            for (int d = LPT; d < 32; d <<= 1) dmax = max(dmax, __shfl_xor_sync(FULL, dmax, d));
             if (dmax <= PATH_LEVELS) {
                 double pmn = CUDART_INF, pmx = -CUDART_INF;
-                for (int r = dmax >> 4; r >= 0; --r) {
+                for (int r = dmax / LPT; r >= 0; --r) {
                     const int e = LPT * r + j;
                     const bool mine = active && e <= depth;
                     Block* bk = blocks;
