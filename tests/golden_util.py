@@ -84,4 +84,5 @@ def assert_close_quantised(got, want, tol=1e-5, min_fraction=0.98, hard_tol=2e-3
     err = numpy.abs(a - b) / numpy.maximum(1.0, numpy.abs(b))
     assert err.max() <= hard_tol, "%s: max error %g > %g" % (what, err.max(), hard_tol)
     frac = float((err <= tol).mean())
-    assert frac >= min_fraction, "%s: only %.4f of entries within %g" % (what, frac, tol)
+    # (a single quantisation step on a fixture with a handful of roots must not fail the fraction test)
+    assert frac >= min_fraction or int((err > tol).sum()) <= 1, "%s: only %.4f of entries within %g" % (what, frac, tol)

@@ -284,7 +284,7 @@ def test_two_players_rejected_by_the_chance_node_searches():
         tsp.Engine(cfg, max_roots=1)
 
 
-@pytest.mark.parametrize("name", [n for n in NAMES if n.startswith(("highway", "roundabout"))])
+@pytest.mark.parametrize("name", [n for n in NAMES if not n.startswith("cross_merge")])
 def test_generic_kernel_fallback_bit_exact(name, monkeypatch):
     """The schedule-driven generic search kernel (what runs when a network does not fit the fast kernel's
     shared-memory layout) against the reference fixtures, with the fast kernel switched off."""

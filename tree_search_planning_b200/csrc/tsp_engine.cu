@@ -93,9 +93,10 @@ struct tsp_engine {
     int64_t search_floats = 0;  // leading part of the arena used by the search kernel (everything but the representation net)
     // fast search kernel: fragment-ordered weights; one FastSched per group shape ([0]: 8 warps / 16 lanes per tree,
     // [1]: 4 warps / 8 lanes per tree)
-    DevBuf farena, fsched_dev[2];
+    // [shape][0]: recurrent inference (deterministic) or one future of a transition expansion; [shape][1]: prediction
+    DevBuf farena, fsched_dev[2][2];
     int64_t farena_floats = 0;
-    FastSched fsched[2]{};
+    FastSched fsched[2][2]{};
     bool has_fast = false;
     int fast_lpt = 0;     // TSP_FAST_LPT override (8 or 16 lanes per tree)
     DevBuf blocks, hidden, hdr, rootprior, rootact, pbtable, phase;
@@ -290,19 +291,19 @@ int lower(tsp_engine* e, const HSched& hs, Schedule& sc, bool keep_input = false
 // Fast search kernel (tsp_fast.cuh): lower a schedule to per-stage, per-warp lists of 16 x 8 output tiles.
 // Returns TSP_OK with e->has_fast == false when the network does not fit the fast path's constraints
 // (the generic search kernel then runs it).
-int lower_fast(tsp_engine* e, const HSched& hs, int which, int GWARPS) {
+int lower_fast(tsp_engine* e, const HSched& hs, int which, int GWARPS, int slot = 0, bool keep_input = false) {
     e->has_fast = false;
     const int ns = (int)hs.stages.size();
     if (ns > FAST_MAX_STAGES) return TSP_OK;
     std::vector<int> width(hs.width.size());
     for (size_t i = 0; i < width.size(); ++i) width[i] = (hs.width[i] + 15) & ~15;  // A operands are read in chunks of 16
     std::vector<int> off;
-    int total = strip_offsets(hs, width, false, off);
+    int total = strip_offsets(hs, width, keep_input, off);
     // two rows are interleaved per strip line: line stride 2 * total == 16 (mod 32) words keeps the LDS.128 /
     // STS.128 of lanes g, g + 1 conflict-free
     total += ((8 - total % 16) + 16) % 16;
     if (off[hs.in_buf] != 0 || total > 4000) return TSP_OK;
-    FastSched& fs = e->fsched[which];
+    FastSched& fs = e->fsched[which][slot];
     memset(&fs, 0, sizeof(fs));
     fs.n_stages = ns;
     fs.row_stride = 2 * total;
@@ -316,6 +317,7 @@ int lower_fast(tsp_engine* e, const HSched& hs, int which, int GWARPS) {
     fs.off_vl = o16(hs.vl);
     fs.off_rl = o16(hs.rl);
     fs.off_tl = o16(hs.tl);
+    fs.off_tp = o16(hs.tp);
     int nu = 0;
     for (int s = 0; s < ns; ++s) {
         const HStage& h = hs.stages[s];
@@ -332,10 +334,12 @@ int lower_fast(tsp_engine* e, const HSched& hs, int which, int GWARPS) {
                 u.x_off = 2 * off[op.in_buf];
                 u.w_off = L.f_off + jt * kc * 128;
                 u.y_off = 2 * (off[op.out_buf] + 8 * jt);
-                u.flags = kc | (op.act ? 0x100 : 0) | (is_operand[op.out_buf] ? 0x200 : 0) | (op.extra ? 0x400 : 0);
+                u.flags = kc | (op.act ? 0x100 : 0) | (is_operand[op.out_buf] ? 0x200 : 0) | (op.extra ? 0x400 : 0) |
+                          (op.extra == 2 ? 0x800 : 0);
                 u.b_off = L.fb_off + 8 * jt;
                 u.e_off = op.extra ? L.fe_off + 8 * jt : 0;
                 u.e_ld = L.npad;
+                u.e_fut = e->cfg.num_actions;
                 units.push_back(u);
             }
         }
@@ -361,9 +365,9 @@ int lower_fast(tsp_engine* e, const HSched& hs, int which, int GWARPS) {
     }
     fs.n_units = nu;
     fs.w_floats = (int)e->farena_floats;
-    int rc = ensure(e, e->fsched_dev[which], sizeof(FastSched));
+    int rc = ensure(e, e->fsched_dev[which][slot], sizeof(FastSched));
     if (rc) return rc;
-    CK(e, cudaMemcpyAsync(e->fsched_dev[which].p, &fs, sizeof(FastSched), cudaMemcpyHostToDevice, e->stream));
+    CK(e, cudaMemcpyAsync(e->fsched_dev[which][slot].p, &fs, sizeof(FastSched), cudaMemcpyHostToDevice, e->stream));
     CK(e, cudaStreamSynchronize(e->stream));
     e->has_fast = true;
     return TSP_OK;
@@ -373,15 +377,20 @@ int lower_fast(tsp_engine* e, const HSched& hs, int which, int GWARPS) {
 int pack_fast_arena(tsp_engine* e) {
     const tsp_config& c = e->cfg;
     e->farena_floats = 0;
-    if (c.variant != TSP_VARIANT_MUZERO) return TSP_OK;
+    const bool chance = c.variant != TSP_VARIANT_MUZERO;
+    auto skipped = [&](int m) {
+        if (m == TSP_MLP_REPRESENTATION) return true;
+        if (m == TSP_MLP_PRIOR) return !chance;
+        if (m == TSP_MLP_TERMINAL) return chance || !c.mask_absorbing_states;
+        return false;
+    };
     int64_t total = 0;
     for (int m = 0; m < TSP_NUM_MLP; ++m) {
-        if (m == TSP_MLP_REPRESENTATION || m == TSP_MLP_PRIOR) continue;
-        if (m == TSP_MLP_TERMINAL && !c.mask_absorbing_states) continue;
+        if (skipped(m)) continue;
         auto& v = e->mlp[m];
         for (size_t l = 0; l < v.size(); ++l) {
             HostLayer& L = v[l];
-            const int n_extra = (m == TSP_MLP_DYNAMICS && l == 0) ? c.num_actions : 0;
+            const int n_extra = (m == TSP_MLP_DYNAMICS && l == 0) ? c.num_actions + (chance ? c.n_futures : 0) : 0;
             L.f_dense = L.in_dim - n_extra;
             L.f_off = -1;
             if (L.f_dense <= 0 || L.f_dense % 16) continue;
@@ -398,8 +407,7 @@ int pack_fast_arena(tsp_engine* e) {
     std::vector<float> host((size_t)total, 0.0f);
     for (int m = 0; m < TSP_NUM_MLP; ++m)
         for (HostLayer& L : e->mlp[m]) {
-            if (m == TSP_MLP_REPRESENTATION || m == TSP_MLP_PRIOR || L.f_off < 0) continue;
-            if (m == TSP_MLP_TERMINAL && !c.mask_absorbing_states) continue;
+            if (skipped(m) || L.f_off < 0) continue;
             const int kc = L.f_dense / 16;
             // tile jt, chunk ch, lane (g, t): W[8 jt + g][16 ch + {2 t, 2 t + 1, 8 + 2 t, 9 + 2 t}]
             for (int jt = 0; jt < L.npad / 8; ++jt)
@@ -514,6 +522,31 @@ int build_schedules(tsp_engine* e) {
         const int rs = std::max(e->sch_trans.row_stride, e->sch_pred.row_stride);
         e->sch_trans.row_stride = rs;
         e->sch_pred.row_stride = rs;
+        if (e->nc == 5 && e->farena_floats > 0 && H % 16 == 0) {  // the chance-node searches on the fast kernel's structure
+            HSched hp;
+            hp.in_dim = H;
+            hp.in_buf = hp.new_buf(H, 0);
+            hp.pl = add_chain(e, hp, TSP_MLP_POLICY, hp.in_buf, 0);
+            hp.vl = add_chain(e, hp, TSP_MLP_VALUE, hp.in_buf, 0);
+            bool ok = true;
+            for (int shape = 0; shape < 2 && ok; ++shape) {
+                const int gw = shape == 0 ? 8 : 4;
+                if ((rc = lower_fast(e, hs, shape, gw, 0, true))) return rc;
+                ok = e->has_fast;
+                if (ok && (rc = lower_fast(e, hp, shape, gw, 1, true))) return rc;
+                ok = ok && e->has_fast;
+                if (ok) {  // one strip geometry for both schedules
+                    const int frs = std::max(e->fsched[shape][0].row_stride, e->fsched[shape][1].row_stride);
+                    for (int k = 0; k < 2; ++k) {
+                        e->fsched[shape][k].row_stride = frs;
+                        CK(e, cudaMemcpyAsync(e->fsched_dev[shape][k].p, &e->fsched[shape][k], sizeof(FastSched),
+                                              cudaMemcpyHostToDevice, e->stream));
+                    }
+                    CK(e, cudaStreamSynchronize(e->stream));
+                }
+            }
+            e->has_fast = ok;
+        }
     }
     for (Schedule* s : {&e->sch_root, &e->sch_pred, &e->sch_recur, &e->sch_trans})
         if (s->n_stages && s->off_in != 0) return fail(e, TSP_EINVAL, "internal: schedule input not at offset 0");
@@ -647,15 +680,15 @@ int launch_search_tm(tsp_engine* e, const SearchParams& p, int TM, int xw) {
     return launch_search<VARIANT, NC, 32>(e, p, xw);
 }
 
-size_t fast_smem(const FastSched& fs, int G, int S, bool w_lo = false) {
+size_t fast_smem(const FastSched& fs, int G, int S, bool w_lo = false, int n_sched = 1) {
     const size_t pb_n = (size_t)((S + 3) & ~1);
-    return pb_n * 16 + ((pb_n + 3) & ~(size_t)3) * 4 + sizeof(FastSched) + (size_t)fs.w_floats * (w_lo ? 8 : 4) +
+    return pb_n * 16 + ((pb_n + 3) & ~(size_t)3) * 4 + n_sched * sizeof(FastSched) + (size_t)fs.w_floats * (w_lo ? 8 : 4) +
            (size_t)G * (GT * fs.row_stride + 2 * GT + GT * PATH_LEVELS) * 4;
 }
 
 template <int G, int LPT>
 int launch_fast(tsp_engine* e, const FastParams& p) {
-    const size_t smem = fast_smem(e->fsched[LPT == 16 ? 0 : 1], G, p.S_tab, p.w_lo != 0);
+    const size_t smem = fast_smem(e->fsched[LPT == 16 ? 0 : 1][0], G, p.S_tab, p.w_lo != 0);
     int rc = set_smem(e, search_fast_kernel<G, LPT>, smem);
     if (rc) return rc;
     const int grid = (p.B + G * GT - 1) / (G * GT);
@@ -671,7 +704,25 @@ int launch_fast(tsp_engine* e, const FastParams& p) {
     return TSP_OK;
 }
 
-// Deterministic search on the fast kernel: groups of 16 trees, G groups per CTA sharing one weight copy.
+template <int G, int LPT, int VARIANT>
+int launch_fast_variant(tsp_engine* e, const FastParams& p) {
+    const size_t smem = fast_smem(e->fsched[LPT == 16 ? 0 : 1][0], G, p.S_tab, p.w_lo != 0, 2);
+    int rc = set_smem(e, search_fast_variant_kernel<G, LPT, VARIANT>, smem);
+    if (rc) return rc;
+    const int grid = (p.B + G * GT - 1) / (G * GT);
+    constexpr int GTHREADS = GT * LPT;
+    search_fast_variant_kernel<G, LPT, VARIANT><<<grid, G * GTHREADS, smem, e->stream>>>(p);
+    CK(e, cudaGetLastError());
+    e->stats.kernel_launches++;
+    e->stats.search_ctas = grid;
+    e->stats.search_smem_bytes = (int)smem;
+    e->stats.trees_per_cta = G * GT;
+    e->stats.threads_per_cta = G * GTHREADS;
+    e->stats.search_kernel = 1;
+    return TSP_OK;
+}
+
+// Search on the fast kernels: groups of 16 trees, G groups per CTA sharing one weight copy.
 int launch_fast_any(tsp_engine* e, const SearchParams& sp) {
     FastParams p;
     memset(&p, 0, sizeof(p));
@@ -697,12 +748,21 @@ int launch_fast_any(tsp_engine* e, const SearchParams& sp) {
     int lpt = groups <= 2 * e->sm_count ? 16 : 8;
     if (e->fast_lpt == 8 || e->fast_lpt == 16) lpt = e->fast_lpt;
     const int which = lpt == 16 ? 0 : 1;
-    p.sched = reinterpret_cast<const FastSched*>(e->fsched_dev[which].p);
+    p.sched = reinterpret_cast<const FastSched*>(e->fsched_dev[which][0].p);
+    p.sched_b = reinterpret_cast<const FastSched*>(e->fsched_dev[which][1].p);
+    p.nf = sp.nf; p.K = sp.K; p.max_iters = sp.max_iters; p.chance = sp.chance;
+    const int variant = e->cfg.variant, n_sched = variant == 0 ? 1 : 2;
     int G = lpt == 16 ? 2 : 4;
     if (e->fast_groups == 1 || e->fast_groups == 2 || (e->fast_groups == 4 && lpt == 8)) G = e->fast_groups;
-    while (G > 1 && fast_smem(e->fsched[which], G, p.S_tab) > 227 * 1024) G >>= 1;
+    while (G > 1 && fast_smem(e->fsched[which][0], G, p.S_tab, false, n_sched) > 227 * 1024) G >>= 1;
     // host-split weights (no split arithmetic in the mma loop) when the doubled arena still fits
-    p.w_lo = (!e->no_wlo && fast_smem(e->fsched[which], G, p.S_tab, true) <= 227 * 1024) ? 1 : 0;
+    p.w_lo = (!e->no_wlo && fast_smem(e->fsched[which][0], G, p.S_tab, true, n_sched) <= 227 * 1024) ? 1 : 0;
+    if (variant != 0) {
+#define TSP_LAUNCH_V(GG, LL) (variant == 1 ? launch_fast_variant<GG, LL, 1>(e, p) : launch_fast_variant<GG, LL, 2>(e, p))
+        if (lpt == 8) return G == 4 ? TSP_LAUNCH_V(4, 8) : (G == 2 ? TSP_LAUNCH_V(2, 8) : TSP_LAUNCH_V(1, 8));
+        return G == 2 ? TSP_LAUNCH_V(2, 16) : TSP_LAUNCH_V(1, 16);
+#undef TSP_LAUNCH_V
+    }
     if (lpt == 8) {
         if (G == 4) return launch_fast<4, 8>(e, p);
         if (G == 2) return launch_fast<2, 8>(e, p);
@@ -715,8 +775,8 @@ int launch_fast_any(tsp_engine* e, const SearchParams& sp) {
 
 int launch_search_any(tsp_engine* e, const SearchParams& p_in) {
     SearchParams p = p_in;
-    if (e->cfg.variant == 0 && e->nc == 5 && e->has_fast && !e->no_fast && e->finalized &&
-        fast_smem(e->fsched[0], 1, p.S_tab) <= 227 * 1024)
+    if (e->nc == 5 && e->has_fast && !e->no_fast && e->finalized &&
+        fast_smem(e->fsched[0][0], 1, p.S_tab, false, e->cfg.variant == 0 ? 1 : 2) <= 227 * 1024)
         return launch_fast_any(e, p);
     // 32 trees per CTA measured best at every batch size (4,096 .. 65,536 roots, both network sizes):
     // lane == row in the MLP phase wants a full warp of rows; 16 is the fallback when the activation
@@ -918,7 +978,8 @@ int tsp_destroy(tsp_handle e) {
     if (!e) return TSP_OK;
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
-    for (DevBuf* b : {&e->arena, &e->farena, &e->fsched_dev[0], &e->fsched_dev[1], &e->blocks, &e->hidden, &e->hdr, &e->rootprior, &e->rootact, &e->pbtable, &e->phase, &e->s_obs,
+    for (DevBuf* b : {&e->arena, &e->farena, &e->fsched_dev[0][0], &e->fsched_dev[0][1], &e->fsched_dev[1][0],
+                      &e->fsched_dev[1][1], &e->blocks, &e->hidden, &e->hdr, &e->rootprior, &e->rootact, &e->pbtable, &e->phase, &e->s_obs,
                       &e->s_legal, &e->s_nlegal, &e->s_noise, &e->s_tie, &e->s_chance, &e->s_fedroot, &e->s_fed,
                       &e->s_visits, &e->s_rootv, &e->s_cval, &e->s_cprior, &e->s_crew, &e->s_depth, &e->s_rpred,
                       &e->s_rhid, &e->s_nrec, &e->s_troot, &e->s_trace, &e->s_tdepth, &e->n_in, &e->n_act})

@@ -49,17 +49,18 @@ struct alignas(16) FUnit {
     int x_off;    // A operand: 2 * (column offset of the input buffer) inside the interleaved strip
     int w_off;    // fragment block [kc][32 lanes][4] of this tile in the weight arena
     int y_off;    // 2 * (column offset of the tile's 8 output columns)
-    int flags;    // bits 0..7: kc (chunks of 16 inputs), bit 8: ELU, bit 9: store lo parts, bit 10: one-hot rows
+    int flags;    // bits 0..7: kc (chunks of 16 inputs), bit 8: ELU, bit 9: store lo parts, bit 10: one-hot action
+                  // rows, bit 11: one-hot future rows (MuZeroStochasticConcat, models.py:568-580)
     int b_off;    // 8 bias values of this tile
-    int e_off;    // one-hot rows: row a at e_off + a * e_ld
+    int e_off;    // one-hot rows: action a at e_off + a * e_ld, future z at e_off + (e_fut + z) * e_ld
     int e_ld;
-    int pad;
+    int e_fut;    // number of action rows in front of the future rows
 };
 static_assert(sizeof(FUnit) == 32, "FUnit is two 16-byte words");
 
 struct FastSched {
     int n_stages, row_stride, n_units, w_floats;
-    short off_hidden, off_pl, off_vl, off_rl, off_tl, pad[3];
+    short off_hidden, off_pl, off_vl, off_rl, off_tl, off_tp, pad[2];
     int4 stage[FAST_MAX_STAGES];          // {row_op, 2 * r_in, 2 * r_out, r_n}; row_op 1: min-max normalise
     int ulist[FAST_MAX_STAGES][MAX_GWARPS];   // units of warp w in stage s: first | count << 16
     FUnit units[FAST_MAX_TILES];
@@ -79,7 +80,11 @@ struct FastParams {
     void* blocks; float* hidden_pool; TreeHeader* hdr; double* rootprior; const int* rootact;
     const unsigned char* tie;
     const float* fed; float* trace;
-    const FastSched* sched;  // device copy
+    const FastSched* sched;  // device copy (deterministic: recurrent inference; chance-node searches: one future of the
+                             // transition expansion)
+    const FastSched* sched_b;  // chance-node searches: prediction
+    int nf, K, max_iters;      // chance-node searches: futures, chance stream length, loop bound
+    const unsigned char* chance;
     const float* wfrag;      // fragment-ordered weight arena of the search MLPs
     int* visit_counts; double* root_value; double* child_value; double* child_prior; double* child_reward;
     int* max_depth; int* num_records; int* total_depth;
@@ -117,7 +122,7 @@ __device__ __forceinline__ float elu_fast(float v) {
 template <int KCT>
 __device__ __forceinline__ void mma_unit(const int4 ua, const int4 ub, const float* __restrict__ actL,
                                          const float* __restrict__ wL, const float* __restrict__ wT, int lo_off,
-                                         int wlo_off, const int* __restrict__ row_action, int g) {
+                                         int wlo_off, const int* __restrict__ row_action, int g, int z = 0) {
     const int kc = KCT ? KCT : (ua.w & 0xFF);
     const float* x = actL + ua.x;   // hi operand == the raw float32 activations; lo parts at + lo_off
     const float* w = wL + ua.y;
@@ -129,6 +134,10 @@ __device__ __forceinline__ void mma_unit(const int4 ua, const int4 ub, const flo
             const float2 e0 = *reinterpret_cast<const float2*>(wT + ub.y + row_action[g] * ub.z);
             const float2 e1 = *reinterpret_cast<const float2*>(wT + ub.y + row_action[g + 8] * ub.z);
             dm[0] += e0.x; dm[1] += e0.y; dm[2] += e1.x; dm[3] += e1.y;
+        }
+        if (ua.w & 0x800) {  // one-hot future z: the same row for every tree of the pass
+            const float2 f = *reinterpret_cast<const float2*>(wT + ub.y + (ub.w + z) * ub.z);
+            dm[0] += f.x; dm[1] += f.y; dm[2] += f.x; dm[3] += f.y;
         }
     }
 #pragma unroll(KCT ? KCT : 2)
@@ -167,7 +176,7 @@ __device__ __forceinline__ void mma_unit(const int4 ua, const int4 ub, const flo
 template <int LPT>
 __device__ __forceinline__ void fast_mlp(const FastSched& fs, const float* __restrict__ W, float* __restrict__ act,
                                          const int* __restrict__ row_action, const unsigned char* __restrict__ row_active,
-                                         int gt, int barid, int wlo_off, unsigned long long* dbg) {
+                                         int gt, int barid, int wlo_off, unsigned long long* dbg, int z = 0) {
     const int rs = fs.row_stride;
     const int wg = gt >> 5, lane = gt & 31;
     const int g = lane >> 2, t = lane & 3;
@@ -189,9 +198,9 @@ __device__ __forceinline__ void fast_mlp(const FastSched& fs, const float* __res
         while (u < uend) {
             const int kc = ua.w & 0xFF;
             if (dbg && threadIdx.x == 0) q0 = clock64();
-            if (kc == 4) mma_unit<4>(ua, ub, actL, wL, wT, lo_off, wlo_off, row_action, g);
-            else if (kc == 2) mma_unit<2>(ua, ub, actL, wL, wT, lo_off, wlo_off, row_action, g);
-            else mma_unit<0>(ua, ub, actL, wL, wT, lo_off, wlo_off, row_action, g);
+            if (kc == 4) mma_unit<4>(ua, ub, actL, wL, wT, lo_off, wlo_off, row_action, g, z);
+            else if (kc == 2) mma_unit<2>(ua, ub, actL, wL, wT, lo_off, wlo_off, row_action, g, z);
+            else mma_unit<0>(ua, ub, actL, wL, wT, lo_off, wlo_off, row_action, g, z);
             if (dbg && threadIdx.x == 0) {
                 q1 = clock64();
                 atomicAdd(dbg + 40, (unsigned long long)(q0 - d0));  // stage start -> unit start (dispatch)
@@ -717,6 +726,485 @@ __global__ void __launch_bounds__(G * GT * LPT, 512 / (G * GT * LPT)) search_fas
             const double vs = rb->vsum[j];
             if (p.visit_counts) p.visit_counts[(size_t)b * A + a] = vis;
             if (p.child_value) p.child_value[(size_t)b * A + a] = vis == 0 ? 0.0 : __ddiv_rn(vs, (double)vis);
+            if (p.child_prior) p.child_prior[(size_t)b * A + a] = root_prior;
+            if (p.child_reward) p.child_reward[(size_t)b * A + a] = (double)rb->reward[j];
+        }
+    }
+}
+
+// ------------------------------------------------------- chance-node searches ----
+// OR of a predicate over the threads of a group (named barrier reduction)
+template <int GTHREADS>
+__device__ __forceinline__ bool group_any(int id, bool pred) {
+    int out;
+    asm volatile(
+        "{ .reg .pred q, r; setp.ne.s32 q, %2, 0; barrier.red.or.pred r, %1, %3, q; selp.s32 %0, 1, 0, r; }"
+        : "=r"(out) : "r"(id), "r"((int)pred), "n"(GTHREADS) : "memory");
+    return out != 0;
+}
+
+// Exact pUCT arg-max of a StateNode level of the chance-node searches (self_play_stochastic.py:471-508,
+// self_play_risk_sensitive.py:479-520) in float64; same contract as select_exact.
+template <int VARIANT>
+__device__ __noinline__ int select_exact_v(double pbN, double sqN, int vis, double vs, double prior, float rw,
+                                           double discount, double mn, double mx, bool on, int gl0,
+                                           const unsigned char* tie_row, int T, int& k_tie) {
+    MinMax mm;
+    mm.mn = mn;
+    mm.mx = mx;
+    double score = -CUDART_INF;
+    if (on) score = ucb_score<VARIANT>(pbN, sqN, vis, vs, prior, rw, discount, mm);
+    double best = score;
+#pragma unroll
+    for (int d = 1; d < GW; d <<= 1) {
+        const double o = shfl_xor_d(FULL, best, d);
+        best = o > best ? o : best;
+    }
+    best = shfl_d(FULL, best, gl0);
+    const unsigned tied = (__ballot_sync(FULL, on && score == best) >> gl0) & 0xFFu;
+    const int nt = __popc(tied);
+    if (nt <= 1) return __ffs(tied) - 1;
+    int v = 0;
+    if (tie_row) v = tie_row[k_tie % T];
+    k_tie++;
+    return __fns(tied, 0, (v % nt) + 1);
+}
+
+// Stochastic (VARIANT 1, self_play_stochastic.py:329-418) and risk-sensitive (VARIANT 2,
+// self_play_risk_sensitive.py:329-537) searches on the group / unit structure of search_fast_kernel:
+// the same float32-filtered selection at StateNode levels, chance outcomes from the external stream at
+// TransitionNode levels, two unit schedules (one future of a transition expansion, evaluated once per future;
+// the prediction of a state expansion), the reference's backups walked by one lane per tree.
+template <int G, int LPT, int VARIANT>
+__global__ void __launch_bounds__(G * GT * LPT, 512 / (G * GT * LPT)) search_fast_variant_kernel(const __grid_constant__ FastParams p) {
+    extern __shared__ __align__(16) float smem[];
+    constexpr int GTHREADS = GT * LPT;
+    constexpr int THREADS = G * GTHREADS;
+    constexpr int NC = 5;
+    using Block = NodeBlock<NC>;
+    static_assert(VARIANT == 1 || VARIANT == 2, "chance-node searches");
+    FastSched* fsa = reinterpret_cast<FastSched*>(smem);
+    FastSched* fsb = fsa + 1;
+    const int pb_n = (p.S_tab + 2 + 1) & ~1;
+    const int pbf_n = (pb_n + 3) & ~3;
+    double* pb = reinterpret_cast<double*>(smem + 2 * sizeof(FastSched) / 4);
+    double* sq = pb + pb_n;
+    float* pbf = reinterpret_cast<float*>(sq + pb_n);
+    float* wsm = pbf + pbf_n;
+    const int tid = threadIdx.x;
+    {
+        const int4* sa = reinterpret_cast<const int4*>(p.sched);
+        const int4* sb = reinterpret_cast<const int4*>(p.sched_b);
+        int4* da = reinterpret_cast<int4*>(fsa);
+        int4* db = reinterpret_cast<int4*>(fsb);
+        for (int i = tid; i < (int)(sizeof(FastSched) / 16); i += THREADS) {
+            da[i] = sa[i];
+            db[i] = sb[i];
+        }
+    }
+    for (int i = tid; i < p.S_tab + 2; i += THREADS) {
+        const double a = p.pb_table[i], c = p.pb_table[p.pb_stride + i];
+        pb[i] = a;
+        sq[i] = c;
+        pbf[i] = (float)(a * c);
+    }
+    const bool fed = p.fed != nullptr;
+    __syncthreads();
+    const FastSched& fA = *fsa;
+    const FastSched& fB = *fsb;
+    const int rs = fA.row_stride;  // the host gives both schedules the same strip geometry
+    const int wlo_off = p.w_lo ? fA.w_floats : 0;
+    const int w_total = fA.w_floats + wlo_off;
+    if (!fed) {
+        const float4* src = reinterpret_cast<const float4*>(p.wfrag);
+        float4* dst = reinterpret_cast<float4*>(wsm);
+        for (int i = tid; i < (w_total >> 2); i += THREADS) dst[i] = __ldg(src + i);
+    }
+    const int grp = tid / GTHREADS, gt = tid % GTHREADS;
+    float* act = wsm + w_total + grp * (GT * rs + GT + GT + GT * PATH_LEVELS);
+    int* row_action = reinterpret_cast<int*>(act + GT * rs);
+    unsigned char* row_active = reinterpret_cast<unsigned char*>(row_action + GT);
+    const int row = gt / LPT;
+    float* rowp = act + (row & 7) * rs + (row >> 3);
+    const int barid = 1 + grp;
+
+    const int lane = tid & 31, j = tid % LPT;
+    const int gl0 = lane & (32 - LPT);
+    const int b = (blockIdx.x * G + grp) * GT + row;
+    const bool valid = b < p.B;
+    const int A = p.A, H = p.H, nf = p.nf;
+    const double discount = p.discount;
+
+    Block* blocks = reinterpret_cast<Block*>(p.blocks) + (size_t)(valid ? b : 0) * p.blocks_per_tree;
+    float* hpool = p.hidden_pool + (size_t)(valid ? b : 0) * p.hidden_per_tree * H;
+    asm volatile("" : "+l"(blocks), "+l"(hpool));
+    __builtin_assume(__isGlobal(blocks));
+    __builtin_assume(__isGlobal(hpool));
+    const float* fed_rec = fed ? p.fed + (size_t)(valid ? b : 0) * p.max_rec * REC : nullptr;
+    float* trace_rec = p.trace ? p.trace + (size_t)(valid ? b : 0) * p.max_rec * REC : nullptr;
+    const unsigned char* chance_row = p.chance ? p.chance + (size_t)(valid ? b : 0) * p.K : nullptr;
+
+    MinMax mm;
+    mm.mn = CUDART_INF;
+    mm.mx = -CUDART_INF;
+    double root_vsum = 0.0, root_prior = 0.0;
+    int root_visit = 0, n_blocks = 1, n_tgroups = 0, max_depth = 0, n_sims = 0, k_tie = 0, k_chance = 0, n_rec = 0;
+    int n_root = 0, root_act = 0, depth_total = 0, n_exact = 0;
+    if (valid) {
+        const TreeHeader h = p.hdr[b];
+        n_root = h.n_root;
+        if (j < GW) {
+            root_prior = p.rootprior[(size_t)b * GW + j];
+            root_act = p.rootact[(size_t)b * GW + j];
+        }
+        if (p.resume) {
+            root_vsum = h.root_vsum;
+            root_visit = h.root_visit;
+            n_blocks = h.n_blocks;
+            n_tgroups = h.n_tgroups;
+            if (p.add_noise && j < n_root) {
+                root_prior = __dadd_rn(__dmul_rn(root_prior, p.one_minus_frac), __dmul_rn(p.noise[(size_t)b * A + j], p.frac));
+                p.rootprior[(size_t)b * GW + j] = root_prior;
+            }
+        }
+    }
+    const float root_prior_f = (float)root_prior;
+    __syncthreads();
+
+    for (int it = 0; it < p.max_iters; ++it) {
+        if (fed && n_rec >= p.max_rec) n_sims = p.S;
+        const bool active = valid && n_sims < p.S;
+        if (!group_any<GTHREADS>(barid, active)) break;
+
+        // ================= selection: StateNode levels pUCT, TransitionNode levels chance =================
+        int node = 0, slot = 0, depth = 0, Np = root_visit;
+        bool parent_is_state = true;  // kind of the node that owns block `node`
+        {
+            float mnf = 0.0f, idf = 1.0f;
+            if (mm.mx > mm.mn) {
+                mnf = (float)mm.mn;
+                idf = rcp_approx((float)__dsub_rn(mm.mx, mm.mn));
+            }
+            const float amnf = fabsf(mnf);
+            bool walking = active;
+            while (__any_sync(FULL, walking)) {
+                const Block* blk = blocks + node;
+                const int nch = (node == 0) ? n_root : A;
+                const bool state_lvl = walking && parent_is_state;
+                const bool on = state_lvl && j < nch;
+                const int jc = j < NC ? j : 0;
+                const int vis = blk->visit[jc];
+                const int ch = blk->child[jc];
+                const double vs = blk->vsum[jc];
+                const float rw = blk->reward[jc];
+                const float prf = (node == 0) ? root_prior_f : blk->prior[jc];
+                const float ps = pbf[Np] * rcp_approx((float)(vis + 1)) * prf;
+                float V, aux;
+                if (VARIANT == 1) {  // normalize(child.value()), self_play_stochastic.py:500-503
+                    const float q = (float)vs * rcp_approx((float)vis);
+                    V = (q - mnf) * idf;
+                    aux = idf * (fabsf(q) + amnf);
+                } else {  // normalize(child.reward + discount * child.value), self_play_risk_sensitive.py:511-516
+                    const float gq = p.discount_f * (float)vs;
+                    V = ((gq + rw) - mnf) * idf;
+                    aux = idf * (fabsf(gq) + fabsf(rw) + amnf);
+                }
+                if (vis <= 0) {
+                    V = 0.0f;
+                    aux = 0.0f;
+                }
+                const float sc = ps + V;
+                const float E = fmaf(1.9073486e-6f, fabsf(ps) + fabsf(V) + aux, 1e-30f);
+                const float lo = on ? sc - E : -CUDART_INF_F;
+                const float hi = on ? sc + E : -CUDART_INF_F;
+                float m1 = lo;
+#pragma unroll
+                for (int d = 1; d < GW; d <<= 1) m1 = fmaxf(m1, __shfl_xor_sync(FULL, m1, d));
+                m1 = __shfl_sync(FULL, m1, gl0);
+                const unsigned cand = (__ballot_sync(FULL, on && hi >= m1) >> gl0) & 0xFFu;
+                int sl = __ffs(cand) - 1;
+                const bool need = state_lvl && __popc(cand) != 1;
+                if (__any_sync(FULL, need)) {
+                    int k2 = k_tie;
+                    const int se = select_exact_v<VARIANT>(pb[Np], sq[Np], vis, vs, (node == 0) ? root_prior : (double)prf, rw,
+                                                           discount, mm.mn, mm.mx, on && need, gl0,
+                                                           p.tie ? p.tie + (size_t)b * p.T : nullptr, p.T, k2);
+                    if (need) {
+                        sl = se;
+                        k_tie = k2;
+                        n_exact++;
+                    }
+                }
+                if (walking && !parent_is_state) {  // TransitionNode.select_child, self_play_stochastic.py:517-533
+                    sl = 0;
+                    if (nf > 1) {
+                        const int v = chance_row ? chance_row[k_chance % p.K] : 0;
+                        k_chance++;
+                        sl = v % nf;
+                    }
+                }
+                const int vis_sel = __shfl_sync(FULL, vis, (gl0 + sl) & 31);
+                const int child_sel = __shfl_sync(FULL, ch, (gl0 + sl) & 31);
+                if (walking) {
+                    slot = sl;
+                    depth++;
+                    if (child_sel < 0) {
+                        walking = false;
+                    } else {
+                        node = child_sel;
+                        Np = vis_sel;
+                        parent_is_state = !parent_is_state;
+                    }
+                }
+            }
+        }
+        // leaf = child `slot` of block `node`
+        const bool leaf_is_state = !parent_is_state;
+        const int kind = !active ? 0 : (leaf_is_state ? 1 : 2);
+        const int ract = __shfl_sync(FULL, root_act, (gl0 + slot) & 31);
+        int action = 0, hslot = 0;
+        if (active) {
+            const int aux_node = blocks[node].aux >> 8;
+            if (!leaf_is_state) {
+                action = (node == 0) ? ract : slot;
+                hslot = (node == 0) ? 0 : aux_node;
+            } else {
+                hslot = 1 + aux_node * nf + slot;
+            }
+            if (depth > max_depth) max_depth = depth;
+            depth_total += depth;
+        }
+
+        // ================= network evaluation =================
+        float value = 0.0f, prior = 0.0f;    // state-leaf results
+        float tprior = 0.0f, treward = 0.0f;  // transition-leaf results (lane z)
+        if (!fed) {
+            if (j == 0) {
+                row_action[row] = action;
+                row_active[row] = active ? 1 : 0;
+            }
+            if (active) {
+                const float4* src = reinterpret_cast<const float4*>(hpool + (size_t)hslot * H);
+                for (int i = j; i < (H >> 2); i += LPT) {
+                    const float4 h4 = src[i];
+                    float* d = rowp + 8 * i;
+                    d[0] = h4.x; d[2] = h4.y; d[4] = h4.z; d[6] = h4.w;
+                    d += 8 * rs;
+                    d[0] = tf32_lo(h4.x); d[2] = tf32_lo(h4.y); d[4] = tf32_lo(h4.z); d[6] = tf32_lo(h4.w);
+                }
+            }
+            const bool any_t = group_any<GTHREADS>(barid, kind == 2);  // (also orders the gather before the tiles)
+            const bool any_s = group_any<GTHREADS>(barid, kind == 1);
+            if (any_t) {
+                for (int z = 0; z < nf; ++z) {
+                    fast_mlp<LPT>(fA, wsm, act, row_action, row_active, gt, barid, wlo_off, nullptr, z);
+                    float dv, rwz, tp;
+                    decode_row<LPT>(rowp + 2 * fA.off_rl, rowp + 2 * fA.off_rl, rowp + 2 * fA.off_tp, p.support, nf, false, j,
+                                    dv, rwz, tp);
+                    if (kind == 2) {
+                        if (j == z) treward = rwz;
+                        if (z == 0) tprior = tp;  // softmax of the prior logits, self_play_stochastic.py:553-554
+                        float4* dst = reinterpret_cast<float4*>(hpool + (size_t)(1 + n_tgroups * nf + z) * H);
+                        const float* src = rowp + 2 * fA.off_hidden;
+                        for (int i = j; i < (H >> 2); i += LPT) {
+                            const float* q = src + 8 * i;
+                            dst[i] = make_float4(q[0], q[2], q[4], q[6]);
+                        }
+                    }
+                    group_barrier<GTHREADS>(barid);  // the strip is read above and rewritten by the next pass
+                }
+            }
+            if (any_s) {
+                fast_mlp<LPT>(fB, wsm, act, row_action, row_active, gt, barid, wlo_off, nullptr, 0);
+                float dr, v1, p1;
+                decode_row<LPT>(rowp + 2 * fB.off_vl, rowp + 2 * fB.off_vl, rowp + 2 * fB.off_pl, p.support, A, false, j, v1, dr, p1);
+                if (kind == 1) {
+                    value = v1;
+                    prior = p1;
+                }
+            }
+        } else if (active) {
+            const float* fr = fed_rec + (size_t)n_rec * REC;
+            if (kind == 1) {
+                value = fr[1];
+                prior = (j < A) ? fr[4 + j] : 0.0f;
+            } else {
+                tprior = (j < nf) ? fr[1 + j] : 0.0f;
+                treward = (j < nf) ? fr[1 + nf + j] : 0.0f;
+            }
+        }
+
+        // ================= expansion + backup =================
+        {
+#pragma unroll
+            for (int q = 0; q < REC / LPT; ++q) {  // evaluation record (tsp.h)
+                const int k = j + q * LPT;
+                const float pk = __shfl_sync(FULL, prior, (gl0 + ((k - 4) & (LPT - 1))) & 31);
+                const float tpk = __shfl_sync(FULL, tprior, (gl0 + ((k - 1) & (LPT - 1))) & 31);
+                const float trk = __shfl_sync(FULL, treward, (gl0 + ((k - 1 - nf) & (LPT - 1))) & 31);
+                if (active && trace_rec && n_rec < p.max_rec) {
+                    float tv = 0.0f;
+                    if (kind == 1) {
+                        if (k == 0) tv = 1.0f;
+                        if (k == 1) tv = value;
+                        if (k >= 4 && k < 4 + A) tv = pk;
+                    } else {
+                        if (k == 0) tv = 2.0f;
+                        if (k >= 1 && k < 1 + nf) tv = tpk;
+                        if (k >= 1 + nf && k < 1 + 2 * nf) tv = trk;
+                    }
+                    trace_rec[(size_t)n_rec * REC + k] = tv;
+                }
+            }
+            if (active) n_rec++;
+            Block* pblk = blocks + node;
+            if (kind == 2) {
+                // ---- TransitionNode.expand, self_play_stochastic.py:535-557 (no backup, no sim count) ----
+                const int nb = n_blocks++;
+                Block* nblk = blocks + nb;
+                if (j < NC) {
+                    nblk->visit[j] = 0;
+                    nblk->child[j] = -1;
+                    nblk->prior[j] = tprior;
+                    nblk->reward[j] = (j < nf) ? treward : 0.0f;
+                    nblk->vsum[j] = 0.0;
+                }
+                if (j == 0) {
+                    nblk->parent = node;
+                    nblk->aux = slot | (n_tgroups << 8);
+                    pblk->child[slot] = nb;
+                }
+                n_tgroups++;
+            } else if (kind == 1) {
+                // ---- StateNode.expand (self_play_stochastic.py:455-469) ----
+                const int nb = n_blocks++;
+                Block* nblk = blocks + nb;
+                if (j < NC) {
+                    nblk->visit[j] = 0;
+                    nblk->child[j] = -1;
+                    nblk->prior[j] = prior;
+                    nblk->reward[j] = 0.0f;
+                    nblk->vsum[j] = 0.0;
+                }
+                if (j == 0) {
+                    nblk->parent = node;
+                    nblk->aux = slot | (hslot << 8);
+                    pblk->child[slot] = nb;
+                }
+            }
+            __syncwarp();
+            // ---- backup by one lane per tree (the walk is a dependent chain; no lane needs another's view) ----
+            if (kind == 1 && j == 0) {
+                double v = (double)value;
+                int cur = node, cs = slot;
+                if (VARIANT == 1) {
+                    // self_play_stochastic.py:408-418; entries alternate State (leaf), Transition, State, ...
+                    bool is_state = true;
+                    while (true) {
+                        Block* bk = blocks + cur;
+                        const double vs = __dadd_rn(bk->vsum[cs], v);
+                        const int vis = bk->visit[cs] + 1;
+                        const double rw = (double)bk->reward[cs];
+                        bk->vsum[cs] = vs;
+                        bk->visit[cs] = vis;
+                        if (is_state) {
+                            v = __dadd_rn(rw, __dmul_rn(discount, v));
+                            mm.update(__dadd_rn(rw, __dmul_rn(discount, __ddiv_rn(vs, (double)vis))));
+                        }
+                        is_state = !is_state;
+                        if (cur == 0) break;
+                        cs = bk->aux & 0xFF;
+                        cur = bk->parent;
+                    }
+                    root_vsum = __dadd_rn(root_vsum, v);
+                    root_visit += 1;
+                    mm.update(__dadd_rn(0.0, __dmul_rn(discount, __ddiv_rn(root_vsum, (double)root_visit))));
+                } else {
+                    // self_play_risk_sensitive.py:408-420, 452-461, 529-537
+                    pblk->vsum[slot] = v;  // search_path[-1].value = value
+                    pblk->visit[slot] = pblk->visit[slot] + 1;
+                    bool is_transition = true;  // kind of the node that OWNS block `cur`
+                    while (true) {
+                        Block* bk = blocks + cur;
+                        double nv;
+                        if (is_transition) {
+                            double best = 0.0;
+                            bool have = false;
+                            for (int k = 0; k < nf; ++k) {
+                                if (bk->visit[k] > 0) {
+                                    const double t = __dadd_rn((double)bk->reward[k], __dmul_rn(discount, bk->vsum[k]));
+                                    if (!have || t < best) best = t;
+                                    have = true;
+                                }
+                            }
+                            nv = best;
+                        } else {
+                            const int nch = (cur == 0) ? n_root : A;
+                            double sum = 0.0;
+                            int counts = 0;
+                            for (int k = 0; k < nch; ++k) {
+                                const int c = bk->visit[k];
+                                sum = __dadd_rn(sum, __dmul_rn((double)c, bk->vsum[k]));
+                                counts += c;
+                            }
+                            nv = __ddiv_rn(sum, (double)counts);
+                        }
+                        if (cur == 0) {
+                            root_vsum = nv;
+                            root_visit += 1;
+                            mm.update(__dadd_rn(0.0, __dmul_rn(discount, nv)));
+                            break;
+                        }
+                        const int ps = bk->aux & 0xFF, pc = bk->parent;
+                        Block* pb2 = blocks + pc;
+                        const int vis = pb2->visit[ps] + 1;
+                        const double rw = (double)pb2->reward[ps];
+                        pb2->vsum[ps] = nv;
+                        pb2->visit[ps] = vis;
+                        if (!is_transition) mm.update(__dadd_rn(rw, __dmul_rn(discount, nv)));
+                        is_transition = !is_transition;
+                        cur = pc;
+                    }
+                }
+            }
+            __syncwarp();
+            // lane 0 of the tree carries the updated statistics: hand them to the other lanes
+            mm.mn = shfl_d(FULL, mm.mn, gl0);
+            mm.mx = shfl_d(FULL, mm.mx, gl0);
+            root_vsum = shfl_d(FULL, root_vsum, gl0);
+            root_visit = __shfl_sync(FULL, root_visit, gl0);
+            if (kind == 1) n_sims++;
+        }
+        __syncwarp();
+    }
+
+    if (valid) {
+        const Block* rb = blocks;
+        if (j == 0) {
+            if (p.root_value)
+                p.root_value[b] = (VARIANT == 2) ? root_vsum : (root_visit == 0 ? 0.0 : __ddiv_rn(root_vsum, (double)root_visit));
+            if (p.max_depth) p.max_depth[b] = max_depth;
+            if (p.num_records) p.num_records[b] = n_rec;
+            if (p.total_depth) p.total_depth[b] = depth_total;
+            p.hdr[b].root_vsum = root_vsum;
+            p.hdr[b].root_visit = root_visit;
+            p.hdr[b].n_blocks = n_blocks;
+            p.hdr[b].n_tgroups = n_tgroups;
+        }
+        if (j < A) {
+            if (p.visit_counts) p.visit_counts[(size_t)b * A + j] = 0;
+            if (p.child_value) p.child_value[(size_t)b * A + j] = 0.0;
+            if (p.child_prior) p.child_prior[(size_t)b * A + j] = 0.0;
+            if (p.child_reward) p.child_reward[(size_t)b * A + j] = 0.0;
+        }
+        __syncwarp();
+        if (j < n_root) {
+            const int a = root_act;
+            const int vis = rb->visit[j];
+            const double vs = rb->vsum[j];
+            if (p.visit_counts) p.visit_counts[(size_t)b * A + a] = vis;
+            if (p.child_value)
+                p.child_value[(size_t)b * A + a] = (VARIANT == 2) ? vs : (vis == 0 ? 0.0 : __ddiv_rn(vs, (double)vis));
             if (p.child_prior) p.child_prior[(size_t)b * A + a] = root_prior;
             if (p.child_reward) p.child_reward[(size_t)b * A + a] = (double)rb->reward[j];
         }
