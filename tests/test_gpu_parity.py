@@ -278,6 +278,16 @@ def test_two_players():
     check_against_oracle(cfg, 64, 60, seed=28, min_agree=0.9)
 
 
+def test_streamed_weights_fast_kernel_large_network(monkeypatch):
+    """cross-merge (365 KB of search weights) on the fast kernel with the weights streamed from L2, both group
+    shapes, forced also at a batch size where the dispatcher would pick the generic kernel."""
+    monkeypatch.setenv("TSP_FORCE_WGLOBAL", "1")
+    cfg = tsp.get_config("cross_merge_env", num_simulations=40)
+    for lpt in ("16", "8"):
+        monkeypatch.setenv("TSP_FAST_LPT", lpt)
+        check_against_oracle(cfg, 700, 40, seed=29, min_agree=0.9)
+
+
 def test_two_players_rejected_by_the_chance_node_searches():
     cfg = tsp.get_config("roundabout_env_ttc_flat_stochastic_concat", players=[0, 1])  # self_play_stochastic.py:407
     with pytest.raises(tsp.TspError):

@@ -85,6 +85,7 @@ struct tsp_engine {
     bool tree_fed = false;
     bool no_fast = false;
     bool no_wlo = false;
+    bool no_wglobal = false, force_wglobal = false;
     int fast_groups = 0;  // TSP_FAST_GROUPS override (1, 2 or 4 groups of 16 trees per CTA)
 
     // device memory
@@ -680,20 +681,21 @@ int launch_search_tm(tsp_engine* e, const SearchParams& p, int TM, int xw) {
     return launch_search<VARIANT, NC, 32>(e, p, xw);
 }
 
-size_t fast_smem(const FastSched& fs, int G, int S, bool w_lo = false, int n_sched = 1) {
+size_t fast_smem(const FastSched& fs, int G, int S, bool w_lo = false, int n_sched = 1, bool w_global = false) {
     const size_t pb_n = (size_t)((S + 3) & ~1);
-    return pb_n * 16 + ((pb_n + 3) & ~(size_t)3) * 4 + n_sched * sizeof(FastSched) + (size_t)fs.w_floats * (w_lo ? 8 : 4) +
-           (size_t)G * (GT * fs.row_stride + 2 * GT + GT * PATH_LEVELS) * 4;
+    return pb_n * 16 + ((pb_n + 3) & ~(size_t)3) * 4 + n_sched * sizeof(FastSched) +
+           (w_global ? 0 : (size_t)fs.w_floats * (w_lo ? 8 : 4)) +
+           (size_t)G * ((w_global ? GT / 2 : GT) * fs.row_stride + 2 * GT + GT * PATH_LEVELS) * 4;
 }
 
-template <int G, int LPT>
+template <int G, int LPT, bool WG = false>
 int launch_fast(tsp_engine* e, const FastParams& p) {
-    const size_t smem = fast_smem(e->fsched[LPT == 16 ? 0 : 1][0], G, p.S_tab, p.w_lo != 0);
-    int rc = set_smem(e, search_fast_kernel<G, LPT>, smem);
+    const size_t smem = fast_smem(e->fsched[LPT == 16 ? 0 : 1][0], G, p.S_tab, p.w_lo != 0, 1, WG);
+    int rc = set_smem(e, search_fast_kernel<G, LPT, WG>, smem);
     if (rc) return rc;
     const int grid = (p.B + G * GT - 1) / (G * GT);
     constexpr int GTHREADS = GT * LPT;
-    search_fast_kernel<G, LPT><<<grid, G * GTHREADS, smem, e->stream>>>(p);
+    search_fast_kernel<G, LPT, WG><<<grid, G * GTHREADS, smem, e->stream>>>(p);
     CK(e, cudaGetLastError());
     e->stats.kernel_launches++;
     e->stats.search_ctas = grid;
@@ -752,6 +754,20 @@ int launch_fast_any(tsp_engine* e, const SearchParams& sp) {
     p.sched_b = reinterpret_cast<const FastSched*>(e->fsched_dev[which][1].p);
     p.nf = sp.nf; p.K = sp.K; p.max_iters = sp.max_iters; p.chance = sp.chance;
     const int variant = e->cfg.variant, n_sched = variant == 0 ? 1 : 2;
+    if (variant == 0 && fast_smem(e->fsched[which][0], 1, p.S_tab, false, 1) > 227 * 1024) {
+        // the weights do not fit shared memory (cross-merge): stream them from L2, strips only in shared memory
+        int G = lpt == 16 ? 2 : 4;
+        if (e->fast_groups == 1 || e->fast_groups == 2 || (e->fast_groups == 4 && lpt == 8)) G = e->fast_groups;
+        while (G > 1 && fast_smem(e->fsched[which][0], G, p.S_tab, false, 1, true) > 227 * 1024) G >>= 1;
+        p.w_lo = 0;
+        if (lpt == 8) {
+            if (G == 4) return launch_fast<4, 8, true>(e, p);
+            if (G == 2) return launch_fast<2, 8, true>(e, p);
+            return launch_fast<1, 8, true>(e, p);
+        }
+        if (G == 2) return launch_fast<2, 16, true>(e, p);
+        return launch_fast<1, 16, true>(e, p);
+    }
     int G = lpt == 16 ? 2 : 4;
     if (e->fast_groups == 1 || e->fast_groups == 2 || (e->fast_groups == 4 && lpt == 8)) G = e->fast_groups;
     while (G > 1 && fast_smem(e->fsched[which][0], G, p.S_tab, false, n_sched) > 227 * 1024) G >>= 1;
@@ -775,8 +791,13 @@ int launch_fast_any(tsp_engine* e, const SearchParams& sp) {
 
 int launch_search_any(tsp_engine* e, const SearchParams& p_in) {
     SearchParams p = p_in;
+    // Networks whose weights do not fit shared memory (cross-merge) run on the fast kernel with the weights streamed
+    // from L2 only while the batch is latency-bound (<= 2 groups per SM: 1.94 vs 2.19 ms at 4,096 x 50); for large
+    // batches the generic kernel's 32-row tiles reuse every streamed weight twice as often (12.2 vs 13.5 ms at 8,192 x 200).
+    const bool small_batch = (p.B + GT - 1) / GT <= 2 * e->sm_count;
+    const bool stream_ok = e->cfg.variant == 0 && !e->no_wglobal && (small_batch || e->force_wglobal);
     if (e->nc == 5 && e->has_fast && !e->no_fast && e->finalized &&
-        fast_smem(e->fsched[0][0], 1, p.S_tab, false, e->cfg.variant == 0 ? 1 : 2) <= 227 * 1024)
+        fast_smem(e->fsched[0][0], 1, p.S_tab, false, e->cfg.variant == 0 ? 1 : 2, stream_ok) <= 227 * 1024)
         return launch_fast_any(e, p);
     // 32 trees per CTA measured best at every batch size (4,096 .. 65,536 roots, both network sizes):
     // lane == row in the MLP phase wants a full warp of rows; 16 is the fallback when the activation
@@ -920,6 +941,8 @@ int tsp_create(const tsp_config* cfg, tsp_handle* out) {
     if (const char* t = getenv("TSP_WARP_MLP")) e->warp_mlp = atoi(t) != 0;
     if (const char* t = getenv("TSP_NO_FAST")) e->no_fast = atoi(t) != 0;
     if (const char* t = getenv("TSP_NO_WLO")) e->no_wlo = atoi(t) != 0;
+    if (const char* t = getenv("TSP_NO_WGLOBAL")) e->no_wglobal = atoi(t) != 0;
+    if (const char* t = getenv("TSP_FORCE_WGLOBAL")) e->force_wglobal = atoi(t) != 0;
     if (const char* t = getenv("TSP_FAST_GROUPS")) e->fast_groups = atoi(t);
     if (const char* t = getenv("TSP_FAST_LPT")) e->fast_lpt = atoi(t);
     auto bail = [&](int rc) {

@@ -172,8 +172,72 @@ __device__ __forceinline__ void mma_unit(const int4 ua, const int4 ub, const flo
         *reinterpret_cast<float4*>(y + lo_off) = make_float4(tf32_lo(d0), tf32_lo(d2), tf32_lo(d1), tf32_lo(d3));
 }
 
+
+// The same unit with the weights streamed from global memory / L2 (networks whose search MLPs do not fit shared
+// memory, e.g. cross-merge: 365 KB): fragment-ordered weights make every warp load a contiguous 512-byte line;
+// a 4-deep register ring keeps four of them in flight ahead of the mma chain (L2 latency ~300 cycles).
+__device__ __forceinline__ void mma_unit_g(const int4 ua, const int4 ub, const float* __restrict__ actL,
+                                           const float* __restrict__ wG, const int* __restrict__ row_action,
+                                           int g, int lane, int z = 0) {
+    const int kc = ua.w & 0xFF;
+    const int t = lane & 3;
+    const float* x = actL + ua.x;
+    const float4* w = reinterpret_cast<const float4*>(wG + ua.y) + lane;  // chunk c at w + 32 * c
+    float4 ring[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) ring[q] = __ldg(w + 32 * (q < kc ? q : 0));
+    float dm[4], dc[4] = {0.f, 0.f, 0.f, 0.f}, de[4] = {0.f, 0.f, 0.f, 0.f};
+    {
+        const float2 b = __ldg(reinterpret_cast<const float2*>(wG + ub.x + 2 * t));
+        dm[0] = b.x; dm[1] = b.y; dm[2] = b.x; dm[3] = b.y;
+        if (ua.w & 0x400) {
+            const float2 e0 = __ldg(reinterpret_cast<const float2*>(wG + ub.y + row_action[g] * ub.z + 2 * t));
+            const float2 e1 = __ldg(reinterpret_cast<const float2*>(wG + ub.y + row_action[g + 8] * ub.z + 2 * t));
+            dm[0] += e0.x; dm[1] += e0.y; dm[2] += e1.x; dm[3] += e1.y;
+        }
+        if (ua.w & 0x800) {
+            const float2 f = __ldg(reinterpret_cast<const float2*>(wG + ub.y + (ub.w + z) * ub.z + 2 * t));
+            dm[0] += f.x; dm[1] += f.y; dm[2] += f.x; dm[3] += f.y;
+        }
+    }
+    for (int c0 = 0; c0 < kc; c0 += 4) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int c = c0 + q;
+            if (c < kc) {
+                const float4 Bv = ring[q];
+                if (c + 4 < kc) ring[q] = __ldg(w + 32 * (c + 4));
+                // (this path is tensor-pipe bound: the split arithmetic hides behind the mma of the other warps, and
+                // without the twin strip of lo parts twice as many groups fit beside each other)
+                const uint4 ah0 = *reinterpret_cast<const uint4*>(x + 32 * c), ah1 = *reinterpret_cast<const uint4*>(x + 32 * c + 16);
+                uint4 al0, al1;
+                al0.x = __float_as_uint(tf32_lo(__uint_as_float(ah0.x))); al0.y = __float_as_uint(tf32_lo(__uint_as_float(ah0.y)));
+                al0.z = __float_as_uint(tf32_lo(__uint_as_float(ah0.z))); al0.w = __float_as_uint(tf32_lo(__uint_as_float(ah0.w)));
+                al1.x = __float_as_uint(tf32_lo(__uint_as_float(ah1.x))); al1.y = __float_as_uint(tf32_lo(__uint_as_float(ah1.y)));
+                al1.z = __float_as_uint(tf32_lo(__uint_as_float(ah1.z))); al1.w = __float_as_uint(tf32_lo(__uint_as_float(ah1.w)));
+                const unsigned bl0 = __float_as_uint(tf32_lo(Bv.x)), bl1 = __float_as_uint(tf32_lo(Bv.y));
+                const unsigned bl2 = __float_as_uint(tf32_lo(Bv.z)), bl3 = __float_as_uint(tf32_lo(Bv.w));
+                mma_tf32v(dm, ah0, __float_as_uint(Bv.x), __float_as_uint(Bv.y));
+                mma_tf32v(dc, al0, __float_as_uint(Bv.x), __float_as_uint(Bv.y));
+                mma_tf32v(de, ah0, bl0, bl1);
+                mma_tf32v(dm, ah1, __float_as_uint(Bv.z), __float_as_uint(Bv.w));
+                mma_tf32v(dc, al1, __float_as_uint(Bv.z), __float_as_uint(Bv.w));
+                mma_tf32v(de, ah1, bl2, bl3);
+            }
+        }
+    }
+    float d0 = dm[0] + (dc[0] + de[0]), d1 = dm[1] + (dc[1] + de[1]);
+    float d2 = dm[2] + (dc[2] + de[2]), d3 = dm[3] + (dc[3] + de[3]);
+    if (ua.w & 0x100) {
+        d0 = elu_fast(d0); d1 = elu_fast(d1); d2 = elu_fast(d2); d3 = elu_fast(d3);
+    }
+    float* y = const_cast<float*>(actL) + ua.z;
+    *reinterpret_cast<float4*>(y) = make_float4(d0, d2, d1, d3);
+}
+
 // All stages of the schedule for the 16 rows of one group; called by the warps of the group.
-template <int LPT>
+// WG: the weights stay in global memory (W is then the device arena).
+template <int LPT, bool WG = false>
 __device__ __forceinline__ void fast_mlp(const FastSched& fs, const float* __restrict__ W, float* __restrict__ act,
                                          const int* __restrict__ row_action, const unsigned char* __restrict__ row_active,
                                          int gt, int barid, int wlo_off, unsigned long long* dbg, int z = 0) {
@@ -198,7 +262,8 @@ __device__ __forceinline__ void fast_mlp(const FastSched& fs, const float* __res
         while (u < uend) {
             const int kc = ua.w & 0xFF;
             if (dbg && threadIdx.x == 0) q0 = clock64();
-            if (kc == 4) mma_unit<4>(ua, ub, actL, wL, wT, lo_off, wlo_off, row_action, g, z);
+            if (WG) mma_unit_g(ua, ub, actL, W, row_action, g, lane, z);
+            else if (kc == 4) mma_unit<4>(ua, ub, actL, wL, wT, lo_off, wlo_off, row_action, g, z);
             else if (kc == 2) mma_unit<2>(ua, ub, actL, wL, wT, lo_off, wlo_off, row_action, g, z);
             else mma_unit<0>(ua, ub, actL, wL, wT, lo_off, wlo_off, row_action, g, z);
             if (dbg && threadIdx.x == 0) {
@@ -241,7 +306,7 @@ __device__ __forceinline__ void fast_mlp(const FastSched& fs, const float* __res
                 for (int q = j; q < sg.w; q += LPT) {
                     const float v = __fmul_rn(__fsub_rn(x[kofs(q)], mn), inv);
                     y[kofs(q)] = v;
-                    y[kofs(q) + lo_off] = tf32_lo(v);
+                    if (!WG) y[kofs(q) + lo_off] = tf32_lo(v);
                 }
             }
         }
@@ -356,7 +421,7 @@ __device__ __noinline__ void backup_walk(NodeBlock<5>* blocks, int cur, int cs, 
     mm.update(__dadd_rn(0.0, __dmul_rn(discount, two ? -q : q)));
 }
 
-template <int G, int LPT>
+template <int G, int LPT, bool WG = false>
 __global__ void __launch_bounds__(G * GT * LPT, 512 / (G * GT * LPT)) search_fast_kernel(const __grid_constant__ FastParams p) {
     extern __shared__ __align__(16) float smem[];
     constexpr int GTHREADS = GT * LPT;
@@ -390,17 +455,19 @@ __global__ void __launch_bounds__(G * GT * LPT, 512 / (G * GT * LPT)) search_fas
     const FastSched& fs = *fsp;
     const int rs = fs.row_stride;
     // p.w_lo: the arena is followed by the lo parts of the weights (same fragment layout) -- shared memory permitting
-    const int wlo_off = p.w_lo ? fs.w_floats : 0;
-    const int w_total = fs.w_floats + wlo_off;
-    if (!fed) {
+    const int wlo_off = (p.w_lo && !WG) ? fs.w_floats : 0;
+    const int w_total = WG ? 0 : fs.w_floats + wlo_off;  // WG: the weights are streamed from global memory
+    if (!fed && !WG) {
         const float4* src = reinterpret_cast<const float4*>(p.wfrag);
         float4* dst = reinterpret_cast<float4*>(wsm);
         for (int i = tid; i < (w_total >> 2); i += THREADS) dst[i] = __ldg(src + i);
     }
     const int grp = tid / GTHREADS, gt = tid % GTHREADS;
-    // per group: strip of 8 interleaved row pairs (rs floats each) + its twin of lo parts, then the row tables
-    float* act = wsm + w_total + grp * (GT * rs + GT + GT + GT * PATH_LEVELS);
-    int* row_action = reinterpret_cast<int*>(act + GT * rs);
+    // per group: strip of 8 interleaved row pairs (rs floats each) + its twin of lo parts (not with streamed
+    // weights), then the row tables
+    constexpr int STRIP_LINES = WG ? GT / 2 : GT;
+    float* act = wsm + w_total + grp * (STRIP_LINES * rs + GT + GT + GT * PATH_LEVELS);
+    int* row_action = reinterpret_cast<int*>(act + STRIP_LINES * rs);
     unsigned char* row_active = reinterpret_cast<unsigned char*>(row_action + GT);
     const int row = gt / LPT;                                // tree of the group == row of the strip
     int* path = row_action + 2 * GT + row * PATH_LEVELS;     // (block << 8 | slot) per level of this tree's descent
@@ -547,14 +614,16 @@ __global__ void __launch_bounds__(G * GT * LPT, 512 / (G * GT * LPT)) search_fas
                     const float4 h4 = src[i];
                     float* d = rowp + 8 * i;  // kofs(4 i)
                     d[0] = h4.x; d[2] = h4.y; d[4] = h4.z; d[6] = h4.w;
-                    d += 8 * rs;
-                    d[0] = tf32_lo(h4.x); d[2] = tf32_lo(h4.y); d[4] = tf32_lo(h4.z); d[6] = tf32_lo(h4.w);
+                    if (!WG) {
+                        d += 8 * rs;
+                        d[0] = tf32_lo(h4.x); d[2] = tf32_lo(h4.y); d[4] = tf32_lo(h4.z); d[6] = tf32_lo(h4.w);
+                    }
                 }
             }
             if (p.phase_cycles && tid == 0) tc1 = clock64();
             group_barrier<GTHREADS>(barid);
             if (p.phase_cycles && tid == 0) tc2 = clock64();
-            fast_mlp<LPT>(fs, wsm, act, row_action, row_active, gt, barid, wlo_off, p.phase_cycles);
+            fast_mlp<LPT, WG>(fs, WG ? p.wfrag : wsm, act, row_action, row_active, gt, barid, wlo_off, p.phase_cycles);
             if (p.phase_cycles && tid == 0) tc3 = clock64();
             decode_row<LPT>(rowp + 2 * fs.off_vl, rowp + 2 * fs.off_rl, rowp + 2 * fs.off_pl, p.support, A, p.uniform_policy != 0,
                        j, value, reward, prior);
