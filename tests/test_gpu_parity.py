@@ -241,6 +241,49 @@ def test_config5_cross_merge_200_sims_slice():
     check_against_oracle(cfg, 1024, 200, seed=14, min_agree=0.9)
 
 
+def _full_size_properties(game, B, S, seed, monkeypatch, slice_roots=192):
+    """BASELINE.json's full batch sizes, through size-independent properties: every root completes (sum of the
+    root's child visits == S, self_play_stochastic.py:333), depths are in range, the search is deterministic
+    (bit-identical on a second run), and a root's result does not depend on the batch it is in -- a slice of the
+    roots searched on its own, with its own trace replayed through the oracle, reproduces the big batch bit for bit."""
+    cfg = tsp.get_config(game, num_simulations=S)
+    sd = random_state_dict(cfg, seed)
+    eng = tsp.Engine(cfg, max_roots=B, max_simulations=S, state_dict=sd)
+    obs, kw = seeded_inputs(cfg, B, S, seed)
+    big = eng.run(S, observations=obs, **kw)
+    assert (big["visit_counts"].sum(1) == S).all()
+    assert (big["max_tree_depth"] >= 1).all() and (big["max_tree_depth"] <= S).all()
+    assert numpy.isfinite(big["root_value"]).all() and numpy.isfinite(big["child_value"]).all()
+    again = eng.run(S, observations=obs, **kw)
+    assert_tree_outputs_bit_exact(again, big, what="second run")
+    rng = numpy.random.default_rng(seed)
+    pick = numpy.sort(rng.choice(B, size=slice_roots, replace=False))
+    sub_kw = {k: (v[pick] if isinstance(v, numpy.ndarray) and v.shape[:1] == (B,) else v) for k, v in kw.items()}
+    # the dispatcher picks the kernel shape from the batch size, and float32 reductions of different shapes round
+    # differently: the slice is searched by the kernel shape the big batch used
+    st = eng.stats()
+    eng.close()
+    if st["search_kernel"]:
+        monkeypatch.setenv("TSP_FAST_LPT", str(st["threads_per_cta"] // st["trees_per_cta"]))
+    else:
+        monkeypatch.setenv("TSP_NO_WGLOBAL", "1")
+    eng = tsp.Engine(cfg, max_roots=slice_roots, max_simulations=S, state_dict=sd)
+    small = eng.run(S, observations=obs[pick], trace=True, **sub_kw)
+    assert_tree_outputs_bit_exact(small, {k: big[k][pick] for k in big if k in small and k.startswith(("visit", "root_value", "child", "max"))},
+                                  what="slice searched on its own")
+    replay = Oracle(cfg, sd).run(S, fed_root=small["trace_root"], fed_records=small["trace_records"], B=slice_roots, **sub_kw)
+    assert_tree_outputs_bit_exact(small, replay, what="slice replayed through the oracle")
+    eng.close()
+
+
+def test_config5_cross_merge_65536_roots_200_sims_full_size(monkeypatch):
+    _full_size_properties("cross_merge_env", 65536, 200, seed=31, monkeypatch=monkeypatch)
+
+
+def test_north_star_highway_65536_roots_full_size(monkeypatch):
+    _full_size_properties("highway_env_ttc_flat", 65536, 50, seed=32, monkeypatch=monkeypatch)
+
+
 def test_highway_200_sims():
     cfg = tsp.get_config("highway_env_ttc_flat", num_simulations=200)
     check_against_oracle(cfg, 1024, 200, seed=15, min_agree=0.9)
