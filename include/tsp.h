@@ -155,7 +155,7 @@ typedef struct {
     int32_t search_smem_bytes;
     int32_t trees_per_cta;
     int32_t threads_per_cta;
-    int32_t search_kernel;         /* last search: 1 = tsp::search_fast_kernel (weights in shared memory), 0 = tsp::search_kernel */
+    int32_t search_kernel;         /* last search: 2 = tsp::search_tc_kernel (tcgen05, weights in tensor memory), 1 = tsp::search_fast_kernel (weights in shared memory), 0 = tsp::search_kernel */
 } tsp_stats;
 
 int tsp_abi_version(void);

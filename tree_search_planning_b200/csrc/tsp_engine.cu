@@ -100,6 +100,12 @@ struct tsp_engine {
     FastSched fsched[2][2]{};
     bool has_fast = false;
     int fast_lpt = 0;     // TSP_FAST_LPT override (8 or 16 lanes per tree)
+    // tcgen05 search MLP (tsp_tc.cuh): [0] latency shape (2 groups x 8 warps, replicated weights), [1] throughput
+    // shape (4 groups x 4 warps); TMEM image of the weights and the bias / one-hot table per shape
+    TcSched tcs[2]{};
+    DevBuf tc_img[2], tc_ctab[2], tc_status;
+    bool has_tc = false;
+    bool no_tc = false;   // TSP_NO_TC: keep the mma.sync kernels
     DevBuf blocks, hidden, hdr, rootprior, rootact, pbtable, phase;
     bool phase_timing = false;
     int blocks_per_tree = 0, hidden_per_tree = 0, max_iters = 0;
@@ -444,6 +450,180 @@ int pack_fast_arena(tsp_engine* e) {
     return TSP_OK;
 }
 
+// tcgen05 search MLP (tsp_tc.cuh): place the weights of the recurrent inference in tensor memory and lower the
+// network to MMA / epilogue tables. Supported: the fully-connected MuZero network with one hidden layer in the
+// dynamics and in every head (all game files of the reference: fc_*_layers = [n]), widths that are multiples of 8,
+// H <= 64, head widths <= 32, no terminal head. Anything else keeps the mma.sync kernels (e->has_tc == false).
+int build_tc(tsp_engine* e) {
+    e->has_tc = false;
+    const tsp_config& c = e->cfg;
+    if (c.variant != TSP_VARIANT_MUZERO || e->nc != 5 || c.mask_absorbing_states) return TSP_OK;
+    for (int m : {TSP_MLP_DYNAMICS, TSP_MLP_REWARD, TSP_MLP_POLICY, TSP_MLP_VALUE})
+        if (e->mlp[m].size() != 2) return TSP_OK;
+    const HostLayer &D1 = e->mlp[TSP_MLP_DYNAMICS][0], &D2 = e->mlp[TSP_MLP_DYNAMICS][1];
+    const HostLayer &R1 = e->mlp[TSP_MLP_REWARD][0], &R2 = e->mlp[TSP_MLP_REWARD][1];
+    const HostLayer &P1 = e->mlp[TSP_MLP_POLICY][0], &P2 = e->mlp[TSP_MLP_POLICY][1];
+    const HostLayer &V1 = e->mlp[TSP_MLP_VALUE][0], &V2 = e->mlp[TSP_MLP_VALUE][1];
+    const int H = c.encoding_size, A = c.num_actions;
+    const int DH = D1.out_dim, RH = R1.out_dim, PH = P1.out_dim, VH = V1.out_dim;
+    const int NR = R2.out_dim, NV = V2.out_dim;
+    if (H % 8 || H > 64 || H < 8 || DH % 8 || DH > 32 || RH % 8 || PH % 8 || VH % 8 || RH > 32 || PH > 32 || VH > 32) return TSP_OK;
+    if (NR > 32 || NV > 32 || A > 32 || D1.in_dim != H + A || D2.out_dim != H) return TSP_OK;
+    const int HK = std::max(RH, std::max(PH, VH));
+    auto bufsz = [](int K) { return 2 * (K / 4) * TC_LBO; };
+    auto sbo = [](int K) { return (K / 4) * TC_LBO; };
+    for (int shape = 0; shape < 2; ++shape) {
+        TcSched& ts = e->tcs[shape];
+        memset(&ts, 0, sizeof(ts));
+        const bool rep = shape == 0;  // replicate small layers over the lane quarters (latency shape)
+        const int G = shape == 0 ? 2 : 4;
+        // ---- TMEM columns ----
+        const int c1 = 0, c2 = c1 + H, c3 = rep ? c2 + DH : c1, c4 = (rep ? c3 + H : c2 + DH);
+        const int hi_cols = c4 + HK;
+        ts.a_lo = hi_cols;
+        ts.n_cols = 2 * hi_cols;
+        ts.d_col0 = ts.n_cols;
+        ts.d_cols_group = 48;
+        if (ts.n_cols % 8 || ts.d_col0 + G * ts.d_cols_group > TC_TMEM_COLS) return TSP_OK;
+        // ---- B arena of a group ----
+        int o = 0;
+        const int xh = o; o += bufsz(H);
+        const int xd = o; o += bufsz(DH);
+        const int xs = o; o += bufsz(H);
+        const int xn = o; o += bufsz(H);
+        const int xr = o; o += bufsz(RH);
+        const int xp = o; o += bufsz(PH);
+        const int xv = o; o += bufsz(VH);
+        ts.b_lo = o;
+        ts.arena_bytes = (2 * o + 127) & ~127;
+        ts.xh_off = xh; ts.xh_sbo = sbo(H);
+        ts.xs_off = xs; ts.xs_sbo = sbo(H);
+        ts.xn_off = xn; ts.xn_sbo = sbo(H);
+        ts.H = H;
+        // ---- out strip ----
+        ts.off_vl = 0;
+        ts.off_rl = NV;
+        ts.off_pl = NV + NR;
+        int pitch = NV + NR + A;
+        if (shape == 0) while (pitch % 32 != 16) ++pitch;
+        else while (pitch % 32 != 8 && pitch % 32 != 24) ++pitch;
+        ts.out_pitch = pitch;
+        // ---- constant table ----
+        std::vector<float> ctab;
+        auto put = [&](const std::vector<float>& v, int n) {
+            const int at = (int)ctab.size();
+            for (int i = 0; i < n; ++i) ctab.push_back(v[(size_t)i]);
+            while (ctab.size() % 32) ctab.push_back(0.0f);  // lanes past `rows` still form an address
+            return at;
+        };
+        const int t_b1 = put(D1.b, DH);
+        std::vector<float> e1((size_t)A * 32, 0.0f);
+        for (int a = 0; a < A; ++a)
+            for (int r = 0; r < DH; ++r) e1[(size_t)a * 32 + r] = D1.W[(size_t)r * D1.in_dim + H + a];
+        const int t_e1 = put(e1, A * 32);
+        const int t_b2 = put(D2.b, H);
+        const int t_b3r = put(R1.b, RH), t_b3p = put(P1.b, PH), t_b3v = put(V1.b, VH);
+        const int t_b4r = put(R2.b, NR), t_b4v = put(V2.b, NV), t_b4p = put(P2.b, A);
+        for (int i = 0; i < 64; ++i) ctab.push_back(0.0f);
+        if ((int)ctab.size() > TC_MAX_CTAB) return TSP_OK;
+        ts.ctab_floats = (int)ctab.size();
+        // ---- TMEM image [column][lane] ----
+        std::vector<float> img((size_t)ts.n_cols * 128, 0.0f);
+        auto place = [&](const HostLayer& L, int col0, int lane0, int K) {  // rows of L at lanes lane0.., k < K at columns col0..
+            for (int r = 0; r < L.out_dim; ++r)
+                for (int k = 0; k < K; ++k) img[(size_t)(col0 + k) * 128 + lane0 + r] = L.W[(size_t)r * L.in_dim + k];
+        };
+        if (rep) {
+            for (int q = 0; q < 4; ++q) place(D1, c1, 32 * q, H);
+            const int r2 = H <= 32 ? 4 : 2;
+            for (int q = 0; q < r2; ++q) place(D2, c2, (128 / r2) * q, DH);
+            place(R1, c3, 0, H); place(P1, c3, 32, H); place(V1, c3, 64, H);
+        } else {
+            place(D1, c1, 0, H); place(R1, c1, 32, H); place(P1, c1, 64, H); place(V1, c1, 96, H);
+            place(D2, c2, 0, DH);
+        }
+        place(R2, c4, 0, RH); place(V2, c4, 32, VH); place(P2, c4, 64, PH);
+        for (int col = 0; col < hi_cols; ++col)
+            for (int l = 0; l < 128; ++l) {
+                const float w = img[(size_t)col * 128 + l];
+                uint32_t bits;
+                memcpy(&bits, &w, 4);
+                bits &= 0xFFFFE000u;
+                float hi;
+                memcpy(&hi, &bits, 4);
+                img[(size_t)(hi_cols + col) * 128 + l] = w - hi;
+            }
+        // ---- MMAs ----
+        auto mma = [&](int i, int a_col, int b_off, int K, int d_col) {
+            ts.mma[i].a_col = a_col; ts.mma[i].b_off = b_off; ts.mma[i].ksteps = K / 8; ts.mma[i].sbo = sbo(K); ts.mma[i].d_col = d_col;
+        };
+        const int DA = 0, DB = 16, DC = 32;
+        mma(0, c1, xh, H, DA);
+        mma(1, c2, xd, DH, DB);
+        mma(2, c3, xs, H, DA);
+        mma(3, c3, xn, H, DC);
+        mma(4, c4, xr, RH, DA);
+        mma(5, c4, xv, VH, DB);
+        mma(6, c4, xp, PH, DC);
+        // ---- epilogue passes ----
+        // a pass is described per TMEM lane quarter q; with 8 warps per group (latency shape) warps q and q + 4 split
+        // the quarter's trees
+        auto epi = [&](int pass, int q, int d_col, int n0, int ncnt, int rows, int dst, int dst_sbo, int feat0, int cidx, int eidx,
+                       int flags) {
+            const int parts = rep ? 2 : 1;
+            for (int h = 0; h < parts; ++h) {
+                TcEpi& x = ts.epi[pass][q + 4 * h];
+                x.d_col = (short)d_col; x.n0 = (short)(n0 + h * (ncnt / parts)); x.ncnt = (short)(ncnt / parts); x.rows = (short)rows;
+                x.dst = dst; x.dst_sbo = dst_sbo; x.feat0 = feat0; x.cidx = cidx; x.eidx = eidx; x.e_ld = 32; x.flags = flags;
+            }
+        };
+        if (rep) {
+            for (int q = 0; q < 4; ++q) epi(0, q, DA, 4 * q, 4, DH, xd, sbo(DH), 0, t_b1, t_e1, 1);
+            if (H <= 32) {
+                for (int q = 0; q < 4; ++q) epi(1, q, DB, 4 * q, 4, H, xs, sbo(H), 0, t_b2, -1, 0);
+            } else {
+                for (int q = 0; q < 4; ++q)
+                    epi(1, q, DB, 8 * (q >> 1), 8, std::min(32, H - 32 * (q & 1)), xs, sbo(H), 32 * (q & 1), t_b2 + 32 * (q & 1), -1, 0);
+            }
+            epi(2, 0, DA, 0, 16, RH, xr, sbo(RH), 0, t_b3r, -1, 1);
+            epi(2, 1, DC, 0, 16, PH, xp, sbo(PH), 0, t_b3p, -1, 1);
+            epi(2, 2, DC, 0, 16, VH, xv, sbo(VH), 0, t_b3v, -1, 1);
+        } else {
+            epi(0, 0, DA, 0, 16, DH, xd, sbo(DH), 0, t_b1, t_e1, 1);
+            epi(1, 0, DB, 0, 16, std::min(32, H), xs, sbo(H), 0, t_b2, -1, 0);
+            if (H > 32) epi(1, 1, DB, 0, 16, H - 32, xs, sbo(H), 32, t_b2 + 32, -1, 0);
+            epi(2, 1, DA, 0, 16, RH, xr, sbo(RH), 0, t_b3r, -1, 1);
+            epi(2, 2, DC, 0, 16, PH, xp, sbo(PH), 0, t_b3p, -1, 1);
+            epi(2, 3, DC, 0, 16, VH, xv, sbo(VH), 0, t_b3v, -1, 1);
+        }
+        epi(3, 0, DA, 0, 16, NR, ts.off_rl, 0, 0, t_b4r, -1, 2);
+        epi(3, 1, DB, 0, 16, NV, ts.off_vl, 0, 0, t_b4v, -1, 2);
+        epi(3, 2, DC, 0, 16, A, ts.off_pl, 0, 0, t_b4p, -1, 2);
+        // ---- stages ----
+        auto stage = [&](int s, int mma0, int n_mma, int commit, int row_op, int epi0, int n_epi) {
+            ts.stage[s].mma0 = mma0; ts.stage[s].n_mma = n_mma; ts.stage[s].commit = commit; ts.stage[s].row_op = row_op;
+            ts.stage[s].epi0 = epi0; ts.stage[s].n_epi = n_epi;
+        };
+        ts.n_stages = 5;
+        stage(0, 0, 1, 1, 0, 0, 1);   // dynamics layer 1
+        stage(1, 1, 1, 1, 0, 1, 1);   // dynamics layer 2 -> un-normalised next state
+        stage(2, 2, 1, 0, 1, 0, 0);   // reward layer 1 in flight while the state is normalised
+        stage(3, 3, 1, 1, 0, 2, 1);   // policy / value layer 1; epilogue of the three hidden layers
+        stage(4, 4, 3, 1, 0, 3, 1);   // output layers -> logits
+        int rc;
+        if ((rc = ensure(e, e->tc_img[shape], img.size() * sizeof(float)))) return rc;
+        if ((rc = ensure(e, e->tc_ctab[shape], ctab.size() * sizeof(float)))) return rc;
+        CK(e, cudaMemcpyAsync(e->tc_img[shape].p, img.data(), img.size() * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+        CK(e, cudaMemcpyAsync(e->tc_ctab[shape].p, ctab.data(), ctab.size() * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+        CK(e, cudaStreamSynchronize(e->stream));
+    }
+    int rc;
+    if ((rc = ensure(e, e->tc_status, sizeof(int)))) return rc;
+    CK(e, cudaMemset(e->tc_status.p, 0, sizeof(int)));
+    e->has_tc = true;
+    return TSP_OK;
+}
+
 int build_schedules(tsp_engine* e) {
     const tsp_config& c = e->cfg;
     const int H = c.encoding_size, A = c.num_actions;
@@ -508,6 +688,7 @@ int build_schedules(tsp_engine* e) {
             const HSched fh = make(c.mask_absorbing_states != 0);
             if ((rc = lower_fast(e, fh, 0, 8))) return rc;
             if (e->has_fast && (rc = lower_fast(e, fh, 1, 4))) return rc;
+            if (e->has_fast && (rc = build_tc(e))) return rc;
         }
     } else {  // one future of MuZeroStochasticConcat.dynamics: models.py:520-595
         HSched hs;
@@ -706,6 +887,31 @@ int launch_fast(tsp_engine* e, const FastParams& p) {
     return TSP_OK;
 }
 
+size_t tc_smem(const TcSched& ts, int G, int S) {
+    const size_t pb_n = (size_t)((S + 3) & ~1);
+    return pb_n * 16 + ((pb_n + 3) & ~(size_t)3) * 4 + sizeof(FastSched) + (size_t)((ts.ctab_floats + 3) & ~3) * 4 + 64 + 256 +
+           (size_t)G * (ts.arena_bytes + (GT * ts.out_pitch + GT + GT / 4 + GT * PATH_LEVELS) * 4);
+}
+
+template <int G, int LPT>
+int launch_tc(tsp_engine* e, const FastParams& p, const TcSched& ts) {
+    // at least half of an SM's shared memory: one CTA per SM, which owns all of the SM's tensor memory
+    const size_t smem = std::max(tc_smem(ts, G, p.S_tab), (size_t)120 * 1024);
+    int rc = set_smem(e, search_tc_kernel<G, LPT>, smem);
+    if (rc) return rc;
+    const int grid = (p.B + G * GT - 1) / (G * GT);
+    constexpr int GTHREADS = GT * LPT;
+    search_tc_kernel<G, LPT><<<grid, G * GTHREADS, smem, e->stream>>>(p, ts);
+    CK(e, cudaGetLastError());
+    e->stats.kernel_launches++;
+    e->stats.search_ctas = grid;
+    e->stats.search_smem_bytes = (int)smem;
+    e->stats.trees_per_cta = G * GT;
+    e->stats.threads_per_cta = G * GTHREADS;
+    e->stats.search_kernel = 2;
+    return TSP_OK;
+}
+
 template <int G, int LPT, int VARIANT>
 int launch_fast_variant(tsp_engine* e, const FastParams& p) {
     const size_t smem = fast_smem(e->fsched[LPT == 16 ? 0 : 1][0], G, p.S_tab, p.w_lo != 0, 2);
@@ -754,6 +960,15 @@ int launch_fast_any(tsp_engine* e, const SearchParams& sp) {
     p.sched_b = reinterpret_cast<const FastSched*>(e->fsched_dev[which][1].p);
     p.nf = sp.nf; p.K = sp.K; p.max_iters = sp.max_iters; p.chance = sp.chance;
     const int variant = e->cfg.variant, n_sched = variant == 0 ? 1 : 2;
+    if (variant == 0 && e->has_tc && !e->no_tc && !p.fed && !p.mask_absorbing) {
+        // the MLP on tcgen05 with the weights resident in tensor memory (tsp_tc.cuh)
+        const TcSched& ts = e->tcs[which];
+        p.tc_img = reinterpret_cast<const float*>(e->tc_img[which].p);
+        p.tc_ctab = reinterpret_cast<const float*>(e->tc_ctab[which].p);
+        p.tc_status = reinterpret_cast<int*>(e->tc_status.p);
+        if (lpt == 16 && tc_smem(ts, 2, p.S_tab) <= 227 * 1024) return launch_tc<2, 16>(e, p, ts);
+        if (lpt == 8 && tc_smem(ts, 4, p.S_tab) <= 227 * 1024) return launch_tc<4, 8>(e, p, ts);
+    }
     if (variant == 0 && fast_smem(e->fsched[which][0], 1, p.S_tab, false, 1) > 227 * 1024) {
         // the weights do not fit shared memory (cross-merge): stream them from L2, strips only in shared memory
         int G = lpt == 16 ? 2 : 4;
@@ -941,6 +1156,7 @@ int tsp_create(const tsp_config* cfg, tsp_handle* out) {
     if (const char* t = getenv("TSP_WARP_MLP")) e->warp_mlp = atoi(t) != 0;
     if (const char* t = getenv("TSP_NO_FAST")) e->no_fast = atoi(t) != 0;
     if (const char* t = getenv("TSP_NO_WLO")) e->no_wlo = atoi(t) != 0;
+    if (const char* t = getenv("TSP_NO_TC")) e->no_tc = atoi(t) != 0;
     if (const char* t = getenv("TSP_NO_WGLOBAL")) e->no_wglobal = atoi(t) != 0;
     if (const char* t = getenv("TSP_FORCE_WGLOBAL")) e->force_wglobal = atoi(t) != 0;
     if (const char* t = getenv("TSP_FAST_GROUPS")) e->fast_groups = atoi(t);
@@ -1005,7 +1221,8 @@ int tsp_destroy(tsp_handle e) {
                       &e->fsched_dev[1][1], &e->blocks, &e->hidden, &e->hdr, &e->rootprior, &e->rootact, &e->pbtable, &e->phase, &e->s_obs,
                       &e->s_legal, &e->s_nlegal, &e->s_noise, &e->s_tie, &e->s_chance, &e->s_fedroot, &e->s_fed,
                       &e->s_visits, &e->s_rootv, &e->s_cval, &e->s_cprior, &e->s_crew, &e->s_depth, &e->s_rpred,
-                      &e->s_rhid, &e->s_nrec, &e->s_troot, &e->s_trace, &e->s_tdepth, &e->n_in, &e->n_act})
+                      &e->s_rhid, &e->s_nrec, &e->s_troot, &e->s_trace, &e->s_tdepth, &e->n_in, &e->n_act, &e->tc_img[0],
+                      &e->tc_img[1], &e->tc_ctab[0], &e->tc_ctab[1], &e->tc_status})
         release(*b);
     for (auto& b : e->n_o) release(b);
     for (auto& ev : e->ev)
@@ -1374,11 +1591,20 @@ int tsp_search_statistics(tsp_handle e, int32_t memory, int32_t B, const int32_t
     return copy_out(e, memory, child_visits, d_c, nb * A);
 }
 
+// tcgen05 path: a bounded mbarrier wait timed out (an MMA commit never arrived) -- the results are invalid
+static int check_tc_status(tsp_engine* e) {
+    if (!e->has_tc || !e->tc_status.p) return TSP_OK;
+    int st = 0;
+    CK(e, cudaMemcpy(&st, e->tc_status.p, sizeof(int), cudaMemcpyDeviceToHost));
+    if (st) return fail(e, TSP_ECUDA, "tcgen05 search kernel: mbarrier wait timed out");
+    return TSP_OK;
+}
+
 int tsp_synchronize(tsp_handle e) {
     if (!e) return TSP_EINVAL;
     CK(e, cudaSetDevice(e->device));
     CK(e, cudaStreamSynchronize(e->stream));
-    return TSP_OK;
+    return check_tc_status(e);
 }
 
 int tsp_get_stats(tsp_handle e, tsp_stats* out) {
@@ -1386,6 +1612,7 @@ int tsp_get_stats(tsp_handle e, tsp_stats* out) {
     CK(e, cudaSetDevice(e->device));
     int rc = drain_events(e);
     if (rc) return rc;
+    if ((rc = check_tc_status(e))) return rc;
     e->stats.pool_bytes = e->pool_bytes;
     *out = e->stats;
     return TSP_OK;

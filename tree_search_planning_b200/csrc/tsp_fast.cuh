@@ -86,6 +86,9 @@ struct FastParams {
     int nf, K, max_iters;      // chance-node searches: futures, chance stream length, loop bound
     const unsigned char* chance;
     const float* wfrag;      // fragment-ordered weight arena of the search MLPs
+    const float* tc_img;     // tcgen05 path: TMEM image of the weights [column][128 lanes], hi columns then lo columns
+    const float* tc_ctab;    // tcgen05 path: biases and one-hot rows
+    int* tc_status;          // tcgen05 path: set to 1 if an mbarrier wait timed out
     int* visit_counts; double* root_value; double* child_value; double* child_prior; double* child_reward;
     int* max_depth; int* num_records; int* total_depth;
     unsigned long long* phase_cycles;
@@ -323,10 +326,12 @@ __device__ __forceinline__ void fast_mlp(const FastSched& fs, const float* __res
 // value and reward decode (models.py:1180-1201) and the policy softmax (self_play.py:532-538) of one row
 // by the 16 lanes of its tree, with the three max-reductions and the five sum-reductions sharing their
 // shuffle rounds. vl / rl / pl point at column 0 of the row inside the interleaved strip (column k at kofs(k)).
-template <int LPT>
+// LIN: the logits are plain arrays (tcgen05 path) instead of columns of the interleaved strip.
+template <int LPT, bool LIN = false>
 __device__ __forceinline__ void decode_row(const float* __restrict__ vl, const float* __restrict__ rl,
                                            const float* __restrict__ pl, int support, int A, bool uniform, int j,
                                            float& value, float& reward, float& prior) {
+    auto kofs = [](int k) { return LIN ? k : ((k >> 1) << 2) + ((k & 1) << 1); };
     const int n = 2 * support + 1;
     float mv = -CUDART_INF_F, mr = -CUDART_INF_F;
     for (int i = j; i < n; i += LPT) {
@@ -421,8 +426,14 @@ __device__ __noinline__ void backup_walk(NodeBlock<5>* blocks, int cur, int cs, 
     mm.update(__dadd_rn(0.0, __dmul_rn(discount, two ? -q : q)));
 }
 
-template <int G, int LPT, bool WG = false>
-__global__ void __launch_bounds__(G * GT * LPT, 512 / (G * GT * LPT)) search_fast_kernel(const __grid_constant__ FastParams p) {
+}  // namespace tsp
+#include "tsp_tc.cuh"
+namespace tsp {
+
+// TC: the MLP runs on tcgen05 with the weights resident in tensor memory (tsp_tc.cuh); ts then points at the
+// kernel's TcSched parameter (constant bank).
+template <int G, int LPT, bool WG, bool TC>
+__device__ __forceinline__ void search_fast_body(const FastParams& p, const TcSched* __restrict__ tsp_) {
     extern __shared__ __align__(16) float smem[];
     constexpr int GTHREADS = GT * LPT;
     constexpr int THREADS = G * GTHREADS;
@@ -450,29 +461,89 @@ __global__ void __launch_bounds__(G * GT * LPT, 512 / (G * GT * LPT)) search_fas
         sq[i] = c;
         pbf[i] = (float)(a * c);
     }
-    const bool fed = p.fed != nullptr;
+    const bool fed = !TC && p.fed != nullptr;
     __syncthreads();
     const FastSched& fs = *fsp;
     const int rs = fs.row_stride;
     // p.w_lo: the arena is followed by the lo parts of the weights (same fragment layout) -- shared memory permitting
-    const int wlo_off = (p.w_lo && !WG) ? fs.w_floats : 0;
-    const int w_total = WG ? 0 : fs.w_floats + wlo_off;  // WG: the weights are streamed from global memory
-    if (!fed && !WG) {
+    const int wlo_off = (p.w_lo && !WG && !TC) ? fs.w_floats : 0;
+    const int w_total = (WG || TC) ? 0 : fs.w_floats + wlo_off;  // WG: the weights are streamed from global memory
+    if (!fed && !WG && !TC) {
         const float4* src = reinterpret_cast<const float4*>(p.wfrag);
         float4* dst = reinterpret_cast<float4*>(wsm);
         for (int i = tid; i < (w_total >> 2); i += THREADS) dst[i] = __ldg(src + i);
     }
     const int grp = tid / GTHREADS, gt = tid % GTHREADS;
-    // per group: strip of 8 interleaved row pairs (rs floats each) + its twin of lo parts (not with streamed
-    // weights), then the row tables
-    constexpr int STRIP_LINES = WG ? GT / 2 : GT;
-    float* act = wsm + w_total + grp * (STRIP_LINES * rs + GT + GT + GT * PATH_LEVELS);
-    int* row_action = reinterpret_cast<int*>(act + STRIP_LINES * rs);
-    unsigned char* row_active = reinterpret_cast<unsigned char*>(row_action + GT);
     const int row = gt / LPT;                                // tree of the group == row of the strip
-    int* path = row_action + 2 * GT + row * PATH_LEVELS;     // (block << 8 | slot) per level of this tree's descent
-    float* rowp = act + (row & 7) * rs + (row >> 3);         // column 0 of this tree's row in the interleaved strip
     const int barid = 1 + grp;
+    float* act = nullptr;
+    float* rowp = nullptr;
+    int* row_action;
+    unsigned char* row_active;
+    int* path;
+    // ---- TC: constant table, mbarriers and per group {B-operand arena, out strip, row tables}; weights -> TMEM ----
+    const TcSched& ts = *tsp_;
+    [[maybe_unused]] unsigned char* tc_arena = nullptr;
+    [[maybe_unused]] float* tc_outs = nullptr;
+    [[maybe_unused]] const float* ctab = wsm;
+    [[maybe_unused]] uint32_t tmem_base = 0, d_group = 0, tc_mbar = 0, tc_parity = 0;
+    [[maybe_unused]] int gw_u = 0;
+    [[maybe_unused]] float4 hq[2];
+    [[maybe_unused]] bool tc_ok = true;
+    if constexpr (TC) {
+        const int ctab_n = (ts.ctab_floats + 3) & ~3;
+        unsigned long long* mbars = reinterpret_cast<unsigned long long*>(wsm + ctab_n);  // 8-byte aligned: ctab_n % 4 == 0
+        uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbars + 4);
+        unsigned char* gbase = reinterpret_cast<unsigned char*>(
+            (reinterpret_cast<uintptr_t>(tmem_slot + 4) + 127) & ~(uintptr_t)127);
+        const int gstride = ts.arena_bytes + (GT * ts.out_pitch + GT + GT / 4 + GT * PATH_LEVELS) * 4;
+        tc_arena = gbase + (size_t)grp * gstride;
+        tc_outs = reinterpret_cast<float*>(tc_arena + ts.arena_bytes);
+        row_action = reinterpret_cast<int*>(tc_outs + GT * ts.out_pitch);
+        row_active = reinterpret_cast<unsigned char*>(row_action + GT);
+        path = row_action + GT + GT / 4 + row * PATH_LEVELS;
+        const int warp_u = __shfl_sync(FULL, tid >> 5, 0);  // provably warp-uniform: keeps the MMA issue on the uniform datapath
+        const int grp_u = warp_u / (GTHREADS / 32);
+        gw_u = warp_u % (GTHREADS / 32);
+        for (int i = tid; i < ts.ctab_floats; i += THREADS) wsm[i] = p.tc_ctab[i];
+        if (tid < G) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbars + tid)));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        if (warp_u == 0) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TC_TMEM_COLS));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        }
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        tmem_base = *tmem_slot;
+        tc_mbar = smem_u32(mbars + grp_u);
+        d_group = tmem_base + ts.d_col0 + grp_u * ts.d_cols_group;
+        {   // weight image [column][128 lanes] -> TMEM: warp w writes lane quarter w % 4, 8 columns per store
+            const uint32_t q = (uint32_t)(warp_u & 3);
+            const float* img = p.tc_img + 32 * q + (tid & 31);
+            for (int c0 = 8 * (warp_u >> 2); c0 < ts.n_cols; c0 += 8 * (THREADS / 128)) {
+                uint32_t r[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) r[i] = __float_as_uint(__ldg(img + (size_t)(c0 + i) * 128));
+                asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(tmem_base + ((32u * q) << 16) + c0),
+                             "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                             : "memory");
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        }
+        tc_fence_before();
+    } else {
+        // per group: strip of 8 interleaved row pairs (rs floats each) + its twin of lo parts (not with streamed
+        // weights), then the row tables
+        constexpr int STRIP_LINES = WG ? GT / 2 : GT;
+        act = wsm + w_total + grp * (STRIP_LINES * rs + GT + GT + GT * PATH_LEVELS);
+        row_action = reinterpret_cast<int*>(act + STRIP_LINES * rs);
+        row_active = reinterpret_cast<unsigned char*>(row_action + GT);
+        path = row_action + 2 * GT + row * PATH_LEVELS;     // (block << 8 | slot) per level of this tree's descent
+        rowp = act + (row & 7) * rs + (row >> 3);           // column 0 of this tree's row in the interleaved strip
+    }
 
     const int lane = tid & 31, j = tid % LPT;
     const int gl0 = lane & (32 - LPT);  // first lane of this tree inside the warp
@@ -516,6 +587,7 @@ __global__ void __launch_bounds__(G * GT * LPT, 512 / (G * GT * LPT)) search_fas
     }
     const float root_prior_f = (float)root_prior;
     __syncthreads();
+    if constexpr (TC) tc_fence_after();
 
     for (int it = 0; it < p.S; ++it) {
         if (fed && n_rec >= p.max_rec) n_sims = p.S;  // fed records exhausted: stop this tree
@@ -603,7 +675,32 @@ __global__ void __launch_bounds__(G * GT * LPT, 512 / (G * GT * LPT)) search_fas
 
         // ================= network evaluation of the group's 16 leaves =================
         float value = 0.0f, reward = 0.0f, terminal = -1.0f, prior = 0.0f;
-        if (!fed) {
+        if constexpr (TC) {
+            if (j == 0) {
+                row_action[row] = action;
+                row_active[row] = active ? 1 : 0;
+            }
+            if (active) {  // gather the parent's hidden state as the B operand of the first dynamics layer
+                const float4* src = reinterpret_cast<const float4*>(hpool + (size_t)node * H);
+                unsigned char* d = tc_arena + ts.xh_off + (row >> 3) * ts.xh_sbo + (row & 7) * 16;
+                for (int i = j; i < (H >> 2); i += LPT) {
+                    const float4 h4 = src[i];
+                    *reinterpret_cast<float4*>(d + i * TC_LBO) = h4;
+                    *reinterpret_cast<float4*>(d + i * TC_LBO + ts.b_lo) =
+                        make_float4(tf32_lo(h4.x), tf32_lo(h4.y), tf32_lo(h4.z), tf32_lo(h4.w));
+                }
+            }
+            fence_async_smem();
+            if (p.phase_cycles && tid == 0) tc1 = clock64();
+            group_barrier<GTHREADS>(barid);
+            if (p.phase_cycles && tid == 0) tc2 = clock64();
+            tc_ok = tc_mlp<LPT>(ts, tmem_base, d_group, tc_arena, tc_outs, ctab, row_action, tc_mbar, tc_parity, gw_u, lane, row, j,
+                                barid, hq, p.phase_cycles) && tc_ok;
+            if (p.phase_cycles && tid == 0) tc3 = clock64();
+            const float* o = tc_outs + row * ts.out_pitch;
+            decode_row<LPT, true>(o + ts.off_vl, o + ts.off_rl, o + ts.off_pl, p.support, A, p.uniform_policy != 0, j, value, reward,
+                                  prior);
+        } else if (!fed) {
             if (j == 0) {
                 row_action[row] = action;
                 row_active[row] = active ? 1 : 0;
@@ -674,7 +771,12 @@ __global__ void __launch_bounds__(G * GT * LPT, 512 / (G * GT * LPT)) search_fas
                     pblk->child[slot] = nb;
                     pblk->reward[slot] = reward;
                 }
-                if (!fed) {  // hidden state of the new node
+                if constexpr (TC) {  // hidden state of the new node: the normalised quads this lane produced
+                    float4* dst = reinterpret_cast<float4*>(hpool + (size_t)nb * H);
+#pragma unroll
+                    for (int q = 0; q < 2; ++q)
+                        if (j + q * LPT < (H >> 2)) dst[j + q * LPT] = hq[q];
+                } else if (!fed) {  // hidden state of the new node
                     float4* dst = reinterpret_cast<float4*>(hpool + (size_t)nb * H);
                     const float* src = rowp + 2 * fs.off_hidden;
                     for (int i = j; i < (H >> 2); i += LPT) {
@@ -799,6 +901,25 @@ __global__ void __launch_bounds__(G * GT * LPT, 512 / (G * GT * LPT)) search_fas
             if (p.child_reward) p.child_reward[(size_t)b * A + a] = (double)rb->reward[j];
         }
     }
+    if constexpr (TC) {
+        if (!tc_ok && p.tc_status) atomicExch(p.tc_status, 1);  // an MMA commit never arrived (bounded mbarrier wait)
+        tc_fence_before();
+        __syncthreads();
+        if (__shfl_sync(FULL, tid >> 5, 0) == 0)
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TC_TMEM_COLS));
+    }
+}
+
+template <int G, int LPT, bool WG = false>
+__global__ void __launch_bounds__(G * GT * LPT, 512 / (G * GT * LPT)) search_fast_kernel(const __grid_constant__ FastParams p) {
+    search_fast_body<G, LPT, WG, false>(p, nullptr);
+}
+
+// The same search with the MLP on tcgen05 / TMEM (tsp_tc.cuh). One CTA per SM: it owns all 512 TMEM columns.
+template <int G, int LPT>
+__global__ void __launch_bounds__(G * GT * LPT, 1) search_tc_kernel(const __grid_constant__ FastParams p,
+                                                                    const __grid_constant__ TcSched ts) {
+    search_fast_body<G, LPT, false, true>(p, &ts);
 }
 
 // ------------------------------------------------------- chance-node searches ----

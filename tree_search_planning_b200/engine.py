@@ -391,7 +391,9 @@ class Engine:
         nt = max(1, v[43])
         return dict(select=v[0] / n, wait=v[1] / n, mlp=v[2] / n, backup=v[3] / n, samples=v[4],
                     stages_work_wait=stages, tile_init_kloop_store=(round(v[40] / nt), round(v[41] / nt), round(v[42] / nt)),
-                    tiles_per_iter=v[43] / n, exact_selects=v[5], select_levels=v[6])
+                    tiles_per_iter=v[43] / n, exact_selects=v[5], select_levels=v[6],
+                    tc_issue_wait_epilogue=[tuple(round(v[44 + 4 * s + i] / n) for i in range(3)) for s in range(5)
+                                            if any(v[44 + 4 * s: 47 + 4 * s])])
 
     def reset_timing(self):
         self._check(self.lib.tsp_reset_timing(self.handle))
