@@ -14,8 +14,8 @@ GPU (configs[1]); weak scaling: every rank searches its own 4,096 roots.
   e2e     the same metric through the C ABI call with HOST (pinned) buffers: the host->device copy
           of observations / noise / tie stream and the device->host read of the root statistics are
           inside the timed region.
-  roofline  dominant kernel = tsp::search_fast_kernel (tsp::search_kernel for networks that do not fit
-          shared memory); achieved = algorithmic bytes per launch
+  roofline  dominant kernel = tsp::search_tc_kernel (MLP on tcgen05, weights in tensor memory; tsp::search_fast_kernel /
+          tsp::search_kernel for networks outside its envelope); achieved = algorithmic bytes per launch
           ((108*D + 8*H + 112) B per simulation, SURVEY 8d, D = measured mean selection depth)
           / its mean launch duration (CUDA events recorded by the engine around every launch).
   cpu_baseline  the CPU oracle (C restatement of the reference algorithm, oracle/) timed on the
@@ -348,7 +348,8 @@ def main():
     tag = "%s_B%d_S%d" % (args.game, B, S)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": profiled_traffic(tag),
-                "kernel": "tsp::search_fast_kernel" if ex_dev["stats"].get("search_kernel") else "tsp::search_kernel",
+                "kernel": {2: "tsp::search_tc_kernel", 1: "tsp::search_fast_kernel"}.get(ex_dev["stats"].get("search_kernel"),
+                                                                                         "tsp::search_kernel"),
                 "kernel_ms": ex_dev["search_ms"], "algorithmic_bytes_per_sim": bytes_per_sim, "mean_select_depth": D,
                 "peak_source": peak_src,
                 "kernel_share_of_step": ex_dev["search_ms"] / (ex_dev["search_ms"] + ex_dev["root_ms"])}

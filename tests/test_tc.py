@@ -1,0 +1,98 @@
+"""GPU (-m gpu): the tcgen05 / tensor-memory search kernel (tsp::search_tc_kernel, csrc/tsp_tc.cuh).
+
+The kernel replaces only the MLP of tsp::search_fast_kernel; selection / expansion / backup are the same code.
+Checked here, through the C ABI:
+  * the dispatcher really runs it (stats.search_kernel == 2) for the fully-connected MuZero nets of the
+    highway / roundabout game files in both group shapes, and keeps the mma.sync kernels where the network is
+    outside its envelope (terminal head, chance-node searches, cross-merge);
+  * the engine's own network outputs replayed through the oracle's tree code give bit-identical root statistics,
+    and the traced network outputs agree with the oracle's float32 network within 1e-5 (check_against_oracle);
+  * it agrees with the mma.sync kernel on the same inputs (both are 3xTF32 float32-accurate networks);
+  * other layer widths (tables for replication / lane packing are built per network).
+"""
+import numpy
+import pytest
+
+torch = pytest.importorskip("torch")
+
+import tree_search_planning_b200 as tsp  # noqa: E402
+from tree_search_planning_b200.synthetic import random_state_dict, synthetic_inputs  # noqa: E402
+from test_gpu_parity import check_against_oracle  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+def search_kernel_of(cfg, B, S, monkeypatch=None, **env):
+    if monkeypatch:
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+    eng = tsp.Engine(cfg, max_roots=B, max_simulations=S, state_dict=random_state_dict(cfg, 3))
+    obs, kw = synthetic_inputs(cfg, B, S, seed=3)
+    out = eng.run(S, observations=obs, trace=True, **kw)
+    st = eng.stats()
+    eng.close()
+    return st, out
+
+
+@pytest.mark.parametrize("B,shape", [(4096, (32, 512)), (300, (32, 512)), (16384, (64, 512))])
+def test_dispatch_runs_the_tcgen05_kernel(B, shape):
+    cfg = tsp.get_config("roundabout_env_ttc_flat", num_simulations=20)
+    st, out = search_kernel_of(cfg, B, 20)
+    assert st["search_kernel"] == 2
+    assert (st["trees_per_cta"], st["threads_per_cta"]) == shape
+    assert (out["visit_counts"].sum(1) == 20).all()
+
+
+def test_outside_the_envelope_keeps_the_mma_sync_kernels(monkeypatch):
+    for name, opts in (("roundabout_env_ttc_flat", dict(mask_absorbing_states=True)),
+                       ("roundabout_env_ttc_flat_stochastic_concat", {}), ("cross_merge_env", {})):
+        cfg = tsp.get_config(name, num_simulations=10, **opts)
+        st, _ = search_kernel_of(cfg, 256, 10)
+        assert st["search_kernel"] in (0, 1), name
+    cfg = tsp.get_config("roundabout_env_ttc_flat", num_simulations=10)
+    st, _ = search_kernel_of(cfg, 256, 10, monkeypatch, TSP_NO_TC="1")
+    assert st["search_kernel"] == 1
+
+
+@pytest.mark.parametrize("B,S", [(4096, 50), (8192, 25)])
+def test_agrees_with_the_mma_sync_kernel(B, S, monkeypatch):
+    cfg = tsp.get_config("highway_env_ttc_flat", num_simulations=S)
+    st_tc, tc = search_kernel_of(cfg, B, S)
+    st_mm, mm = search_kernel_of(cfg, B, S, monkeypatch, TSP_NO_TC="1")
+    assert st_tc["search_kernel"] == 2 and st_mm["search_kernel"] == 1
+    same = (tc["visit_counts"] == mm["visit_counts"]).all(axis=1)
+    assert same.mean() >= 0.985, same.mean()
+    a = tc["trace_records"][same].astype(numpy.float64)
+    b = mm["trace_records"][same].astype(numpy.float64)
+    err = numpy.abs(a - b) / numpy.maximum(1.0, numpy.abs(b))
+    assert (err <= 1e-5).mean() >= 0.97 and numpy.median(err) <= 1e-6
+
+
+@pytest.mark.parametrize("B", [2048, 8192])
+def test_trace_replays_bit_exactly_and_network_matches_oracle(B):
+    cfg = tsp.get_config("highway_env_ttc_flat", num_simulations=30)
+    check_against_oracle(cfg, B, 30, seed=21)
+
+
+@pytest.mark.parametrize("widths", [dict(encoding_size=32, fc_dynamics_layers=[16], fc_reward_layers=[16], fc_value_layers=[24],
+                                         fc_policy_layers=[8], support_size=5),
+                                    dict(encoding_size=48, fc_dynamics_layers=[24], fc_reward_layers=[32], fc_value_layers=[16],
+                                         fc_policy_layers=[32], support_size=15),
+                                    dict(encoding_size=64, fc_dynamics_layers=[32], fc_reward_layers=[8], fc_value_layers=[8],
+                                         fc_policy_layers=[8], support_size=1)])
+@pytest.mark.parametrize("B", [700, 9000])
+def test_other_layer_widths(widths, B):
+    cfg = tsp.get_config("roundabout_env_ttc_flat", num_simulations=20, **widths)
+    eng = tsp.Engine(cfg, max_roots=B, max_simulations=20, state_dict=random_state_dict(cfg, 5))
+    obs, kw = synthetic_inputs(cfg, 16, 20, seed=5)
+    eng.run(20, observations=obs, **kw)
+    assert eng.stats()["search_kernel"] == 2
+    eng.close()
+    check_against_oracle(cfg, B, 20, seed=22, legal=True)
+
+
+def test_ragged_uniform_and_two_players_on_tcgen05():
+    cfg = tsp.get_config("roundabout_env_ttc_flat", num_simulations=25)
+    check_against_oracle(cfg, 1000, 25, seed=23, legal=True)
+    check_against_oracle(cfg, 1000, 25, seed=24, uniform_policy=True, min_agree=0.9)
+    check_against_oracle(cfg.replace(players=[0, 1]), 1000, 25, seed=25, min_agree=0.9)

@@ -21,7 +21,7 @@ constexpr int LBO = 144;      // bytes between core matrices along K (128 data +
 constexpr int NSTAGE = 5;
 constexpr int WCOLS = 64;     // K columns of one weight set (hi), followed by 64 lo columns
 constexpr int NSETS = 3;
-constexpr int D_COL = NSETS * 2 * WCOLS;  // accumulators behind the weight sets: 2 x 16 columns
+constexpr int D_COL = NSETS * 2 * WCOLS;  // accumulators behind the weight sets
 
 __host__ __device__ inline int b_off(int n, int k, int K) {  // byte offset of X[n][k] inside a B buffer
     return (n >> 3) * ((K >> 2) * LBO) + (k >> 2) * LBO + (n & 7) * 16 + (k & 3) * 4;
@@ -58,10 +58,10 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 
-template <int REP, int K>
+template <int REP, int K, int SPLIT>
 __global__ void __launch_bounds__(128) stage_chain(const float* __restrict__ timg, const float* __restrict__ X0,
                                                    const float* __restrict__ bias, float* __restrict__ out,
-                                                   int iters, long long* cycles, int* status) {
+                                                   int iters, long long* cycles, int* status, int n_mma = NT) {
     __shared__ __align__(128) unsigned char bufs[2][2][BUF_BYTES];  // [buffer][hi / lo]
     __shared__ __align__(8) unsigned long long mbar;
     __shared__ uint32_t tmem_base_sh;
@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(128) stage_chain(const float* __restrict__ tim
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform: the MMA issue stays on the uniform datapath
     long long ph[4] = {0, 0, 0, 0};
     if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&mbar)), "n"(SPLIT));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -103,25 +103,27 @@ __global__ void __launch_bounds__(128) stage_chain(const float* __restrict__ tim
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n_mma >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);  // n_mma > 16: timing only
     const uint32_t sbo = (uint32_t)(K >> 2) * LBO;
     uint32_t parity = 0;
     long long t0 = clock64();
     for (int it = 0; it < iters; ++it) {
         for (int s = 0; s < NSTAGE; ++s) {
             const int cur = s & 1, nxt = cur ^ 1;
-            const uint32_t d_tmem = tmem_base + D_COL + 16 * (s & 1);
+            const uint32_t d_tmem = tmem_base + D_COL + 16 * (s & 1);  // split accumulators at + 32 * warp
             const long long q0 = clock64();
-            if (warp == 0) {
+            if (warp < SPLIT) {  // SPLIT issuing warps: each takes a share of the K steps into its own accumulator
                 const uint32_t a_hi = tmem_base + (s % NSETS) * 2 * WCOLS, a_lo = a_hi + WCOLS;
                 const uint32_t bh = smem_u32(&bufs[cur][0][0]), bl = smem_u32(&bufs[cur][1][0]);
+                const uint32_t dd = d_tmem + 32 * warp;
                 if (elect_one()) {
 #pragma unroll
-                    for (int ks = 0; ks < K / 8; ++ks) {
+                    for (int q = 0; q < K / 8 / SPLIT; ++q) {
+                        const int ks = warp * (K / 8 / SPLIT) + q;
                         const uint64_t dh = make_desc(bh + ks * 2 * LBO, LBO, sbo), dl = make_desc(bl + ks * 2 * LBO, LBO, sbo);
-                        mma_ts(d_tmem, a_hi + 8 * ks, dh, idesc, ks > 0 ? 1u : 0u);
-                        mma_ts(d_tmem, a_lo + 8 * ks, dh, idesc, 1u);
-                        mma_ts(d_tmem, a_hi + 8 * ks, dl, idesc, 1u);
+                        mma_ts(dd, a_hi + 8 * ks, dh, idesc, q > 0 ? 1u : 0u);
+                        mma_ts(dd, a_lo + 8 * ks, dh, idesc, 1u);
+                        mma_ts(dd, a_hi + 8 * ks, dl, idesc, 1u);
                     }
                     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mbar)) : "memory");
                 }
@@ -149,6 +151,13 @@ __global__ void __launch_bounds__(128) stage_chain(const float* __restrict__ tim
                 asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
                              : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(d_tmem + lane_base + 4 * warp));
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                for (int sp = 1; sp < SPLIT; ++sp) {
+                    uint32_t w[4];
+                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                                 : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(d_tmem + 32 * sp + lane_base + 4 * warp));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    for (int i = 0; i < 4; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(w[i]));
+                }
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const int n = 4 * warp + i;
@@ -210,9 +219,11 @@ static float tf32_lo_h(float x) {
     return x - t;
 }
 
-int main() {
+int main(int argc, char** argv) {
+    const int n_mma = argc > 1 ? atoi(argv[1]) : NT;
+    printf("MMA N = %d%s\n", n_mma, n_mma != NT ? " (timing only: results are not meaningful)" : "");
     for (int K : {64, 32}) {
-        for (int rep : {4, 1}) {
+        for (int rep : {4, 2, 3, 1}) {  // 2 / 3: rep 4 with the issue split over 2 / 4 warps
             // weights W[s][32][K]; stage s uses set s % NSETS, so stages 3, 4 reuse the weights of 0, 1
             std::vector<float> W(NSETS * 32 * K), X0(NT * K), bias(NSTAGE * 128), out(NT * 32);
             srand(7);
@@ -256,10 +267,14 @@ int main() {
             cudaMemcpy(dB, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice);
             cudaMemset(dO, 0, out.size() * 4); cudaMemset(dS, 0, 4);
             for (int iters : {1, 200}) {
-                if (rep == 4 && K == 64) stage_chain<4, 64><<<1, 128>>>(dT, dX, dB, dO, iters, dC, dS);
-                else if (rep == 4) stage_chain<4, 32><<<1, 128>>>(dT, dX, dB, dO, iters, dC, dS);
-                else if (K == 64) stage_chain<1, 64><<<1, 128>>>(dT, dX, dB, dO, iters, dC, dS);
-                else stage_chain<1, 32><<<1, 128>>>(dT, dX, dB, dO, iters, dC, dS);
+                if (rep == 4 && K == 64) stage_chain<4, 64, 1><<<1, 128>>>(dT, dX, dB, dO, iters, dC, dS, n_mma);
+                else if (rep == 4) stage_chain<4, 32, 1><<<1, 128>>>(dT, dX, dB, dO, iters, dC, dS, n_mma);
+                else if (rep == 2 && K == 64) stage_chain<4, 64, 2><<<1, 128>>>(dT, dX, dB, dO, iters, dC, dS, n_mma);
+                else if (rep == 2) stage_chain<4, 32, 2><<<1, 128>>>(dT, dX, dB, dO, iters, dC, dS, n_mma);
+                else if (rep == 3 && K == 64) stage_chain<4, 64, 4><<<1, 128>>>(dT, dX, dB, dO, iters, dC, dS, n_mma);
+                else if (rep == 3) stage_chain<4, 32, 4><<<1, 128>>>(dT, dX, dB, dO, iters, dC, dS, n_mma);
+                else if (K == 64) stage_chain<1, 64, 1><<<1, 128>>>(dT, dX, dB, dO, iters, dC, dS, n_mma);
+                else stage_chain<1, 32, 1><<<1, 128>>>(dT, dX, dB, dO, iters, dC, dS, n_mma);
                 cudaError_t e1 = cudaGetLastError();
                 cudaError_t e = cudaDeviceSynchronize();
                 long long cy[5] = {0, 0, 0, 0, 0};

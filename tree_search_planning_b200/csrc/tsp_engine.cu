@@ -106,6 +106,7 @@ struct tsp_engine {
     DevBuf tc_img[2], tc_ctab[2], tc_status;
     bool has_tc = false;
     bool no_tc = false;   // TSP_NO_TC: keep the mma.sync kernels
+    bool tc_nofold = false;  // TSP_TC_NOFOLD: evaluate the first reward layer as its own MMA on the un-normalised state
     DevBuf blocks, hidden, hdr, rootprior, rootact, pbtable, phase;
     bool phase_timing = false;
     int blocks_per_tree = 0, hidden_per_tree = 0, max_iters = 0;
@@ -477,6 +478,22 @@ int build_tc(tsp_engine* e) {
         memset(&ts, 0, sizeof(ts));
         const bool rep = shape == 0;  // replicate small layers over the lane quarters (latency shape)
         const int G = shape == 0 ? 2 : 4;
+        // The second dynamics layer has no activation (models.py:1150-1162: Identity at the output), so the first reward
+        // layer on the un-normalised state is a Linear layer of the dynamics hidden layer: Wr1 (W2 d + b2) + br1 =
+        // (Wr1 W2) d + (Wr1 b2 + br1). The product (float64 on the host, rounded once to float32) rides in the MMA of
+        // dynamics layer 2 as RH more rows -- one MMA sequence and one stage less per simulation.
+        const bool fold = !e->tc_nofold && H + RH <= 128;
+        std::vector<float> FW((size_t)RH * DH), Fb((size_t)RH);
+        for (int r = 0; r < RH; ++r) {
+            for (int k = 0; k < DH; ++k) {
+                double acc = 0.0;
+                for (int h = 0; h < H; ++h) acc += (double)R1.W[(size_t)r * H + h] * (double)D2.W[(size_t)h * DH + k];
+                FW[(size_t)r * DH + k] = (float)acc;
+            }
+            double acc = R1.b[(size_t)r];
+            for (int h = 0; h < H; ++h) acc += (double)R1.W[(size_t)r * H + h] * (double)D2.b[(size_t)h];
+            Fb[(size_t)r] = (float)acc;
+        }
         // ---- TMEM columns ----
         const int c1 = 0, c2 = c1 + H, c3 = rep ? c2 + DH : c1, c4 = (rep ? c3 + H : c2 + DH);
         const int hi_cols = c4 + HK;
@@ -522,7 +539,7 @@ int build_tc(tsp_engine* e) {
             for (int r = 0; r < DH; ++r) e1[(size_t)a * 32 + r] = D1.W[(size_t)r * D1.in_dim + H + a];
         const int t_e1 = put(e1, A * 32);
         const int t_b2 = put(D2.b, H);
-        const int t_b3r = put(R1.b, RH), t_b3p = put(P1.b, PH), t_b3v = put(V1.b, VH);
+        const int t_b3r = put(fold ? Fb : R1.b, RH), t_b3p = put(P1.b, PH), t_b3v = put(V1.b, VH);
         const int t_b4r = put(R2.b, NR), t_b4v = put(V2.b, NV), t_b4p = put(P2.b, A);
         for (int i = 0; i < 64; ++i) ctab.push_back(0.0f);
         if ((int)ctab.size() > TC_MAX_CTAB) return TSP_OK;
@@ -533,14 +550,27 @@ int build_tc(tsp_engine* e) {
             for (int r = 0; r < L.out_dim; ++r)
                 for (int k = 0; k < K; ++k) img[(size_t)(col0 + k) * 128 + lane0 + r] = L.W[(size_t)r * L.in_dim + k];
         };
+        const int h_q = (H + 31) / 32;  // lane quarters of the next state; the folded reward layer sits behind them
+        auto place_fold = [&](int col0, int lane0) {
+            for (int r = 0; r < RH; ++r)
+                for (int k = 0; k < DH; ++k) img[(size_t)(col0 + k) * 128 + lane0 + r] = FW[(size_t)r * DH + k];
+        };
         if (rep) {
             for (int q = 0; q < 4; ++q) place(D1, c1, 32 * q, H);
-            const int r2 = H <= 32 ? 4 : 2;
-            for (int q = 0; q < r2; ++q) place(D2, c2, (128 / r2) * q, DH);
-            place(R1, c3, 0, H); place(P1, c3, 32, H); place(V1, c3, 64, H);
+            if (fold) {
+                place(D2, c2, 0, DH);
+                place_fold(c2, 32 * h_q);
+                for (int q = 0; q < 2; ++q) { place(P1, c3, 64 * q, H); place(V1, c3, 64 * q + 32, H); }
+            } else {
+                const int r2 = H <= 32 ? 4 : 2;
+                for (int q = 0; q < r2; ++q) place(D2, c2, (128 / r2) * q, DH);
+                place(R1, c3, 0, H); place(P1, c3, 32, H); place(V1, c3, 64, H);
+            }
         } else {
-            place(D1, c1, 0, H); place(R1, c1, 32, H); place(P1, c1, 64, H); place(V1, c1, 96, H);
+            place(D1, c1, 0, H); place(P1, c1, 64, H); place(V1, c1, 96, H);
             place(D2, c2, 0, DH);
+            if (fold) place_fold(c2, 32 * h_q);
+            else place(R1, c1, 32, H);
         }
         place(R2, c4, 0, RH); place(V2, c4, 32, VH); place(P2, c4, 64, PH);
         for (int col = 0; col < hi_cols; ++col)
@@ -558,13 +588,16 @@ int build_tc(tsp_engine* e) {
             ts.mma[i].a_col = a_col; ts.mma[i].b_off = b_off; ts.mma[i].ksteps = K / 8; ts.mma[i].sbo = sbo(K); ts.mma[i].d_col = d_col;
         };
         const int DA = 0, DB = 16, DC = 32;
-        mma(0, c1, xh, H, DA);
-        mma(1, c2, xd, DH, DB);
-        mma(2, c3, xs, H, DA);
-        mma(3, c3, xn, H, DC);
-        mma(4, c4, xr, RH, DA);
-        mma(5, c4, xv, VH, DB);
-        mma(6, c4, xp, PH, DC);
+        int n_m = 0;
+        const int m_d1 = n_m++; mma(m_d1, c1, xh, H, DA);
+        const int m_d2 = n_m++; mma(m_d2, c2, xd, DH, DB);
+        int m_r1 = -1;
+        if (!fold) { m_r1 = n_m++; mma(m_r1, c3, xs, H, DA); }
+        const int m_pv = n_m++; mma(m_pv, c3, xn, H, DC);
+        const int m_out = n_m;
+        mma(n_m++, c4, xr, RH, DA);
+        mma(n_m++, c4, xv, VH, DB);
+        mma(n_m++, c4, xp, PH, DC);
         // ---- epilogue passes ----
         // a pass is described per TMEM lane quarter q; with 8 warps per group (latency shape) warps q and q + 4 split
         // the quarter's trees
@@ -579,20 +612,27 @@ int build_tc(tsp_engine* e) {
         };
         if (rep) {
             for (int q = 0; q < 4; ++q) epi(0, q, DA, 4 * q, 4, DH, xd, sbo(DH), 0, t_b1, t_e1, 1);
-            if (H <= 32) {
-                for (int q = 0; q < 4; ++q) epi(1, q, DB, 4 * q, 4, H, xs, sbo(H), 0, t_b2, -1, 0);
-            } else {
+            if (fold) {
+                for (int q = 0; q < h_q; ++q) epi(1, q, DB, 0, 16, std::min(32, H - 32 * q), xs, sbo(H), 32 * q, t_b2 + 32 * q, -1, 0);
+                epi(1, h_q, DB, 0, 16, RH, xr, sbo(RH), 0, t_b3r, -1, 1);
                 for (int q = 0; q < 4; ++q)
-                    epi(1, q, DB, 8 * (q >> 1), 8, std::min(32, H - 32 * (q & 1)), xs, sbo(H), 32 * (q & 1), t_b2 + 32 * (q & 1), -1, 0);
+                    epi(2, q, DC, 8 * (q >> 1), 8, (q & 1) ? VH : PH, (q & 1) ? xv : xp, sbo((q & 1) ? VH : PH), 0, (q & 1) ? t_b3v : t_b3p, -1, 1);
+            } else {
+                if (H <= 32) {
+                    for (int q = 0; q < 4; ++q) epi(1, q, DB, 4 * q, 4, H, xs, sbo(H), 0, t_b2, -1, 0);
+                } else {
+                    for (int q = 0; q < 4; ++q)
+                        epi(1, q, DB, 8 * (q >> 1), 8, std::min(32, H - 32 * (q & 1)), xs, sbo(H), 32 * (q & 1), t_b2 + 32 * (q & 1), -1, 0);
+                }
+                epi(2, 0, DA, 0, 16, RH, xr, sbo(RH), 0, t_b3r, -1, 1);
+                epi(2, 1, DC, 0, 16, PH, xp, sbo(PH), 0, t_b3p, -1, 1);
+                epi(2, 2, DC, 0, 16, VH, xv, sbo(VH), 0, t_b3v, -1, 1);
             }
-            epi(2, 0, DA, 0, 16, RH, xr, sbo(RH), 0, t_b3r, -1, 1);
-            epi(2, 1, DC, 0, 16, PH, xp, sbo(PH), 0, t_b3p, -1, 1);
-            epi(2, 2, DC, 0, 16, VH, xv, sbo(VH), 0, t_b3v, -1, 1);
         } else {
             epi(0, 0, DA, 0, 16, DH, xd, sbo(DH), 0, t_b1, t_e1, 1);
-            epi(1, 0, DB, 0, 16, std::min(32, H), xs, sbo(H), 0, t_b2, -1, 0);
-            if (H > 32) epi(1, 1, DB, 0, 16, H - 32, xs, sbo(H), 32, t_b2 + 32, -1, 0);
-            epi(2, 1, DA, 0, 16, RH, xr, sbo(RH), 0, t_b3r, -1, 1);
+            for (int q = 0; q < h_q; ++q) epi(1, q, DB, 0, 16, std::min(32, H - 32 * q), xs, sbo(H), 32 * q, t_b2 + 32 * q, -1, 0);
+            if (fold) epi(1, h_q, DB, 0, 16, RH, xr, sbo(RH), 0, t_b3r, -1, 1);
+            else epi(2, 1, DA, 0, 16, RH, xr, sbo(RH), 0, t_b3r, -1, 1);
             epi(2, 2, DC, 0, 16, PH, xp, sbo(PH), 0, t_b3p, -1, 1);
             epi(2, 3, DC, 0, 16, VH, xv, sbo(VH), 0, t_b3v, -1, 1);
         }
@@ -605,11 +645,12 @@ int build_tc(tsp_engine* e) {
             ts.stage[s].epi0 = epi0; ts.stage[s].n_epi = n_epi;
         };
         ts.n_stages = 5;
-        stage(0, 0, 1, 1, 0, 0, 1);   // dynamics layer 1
-        stage(1, 1, 1, 1, 0, 1, 1);   // dynamics layer 2 -> un-normalised next state
-        stage(2, 2, 1, 0, 1, 0, 0);   // reward layer 1 in flight while the state is normalised
-        stage(3, 3, 1, 1, 0, 2, 1);   // policy / value layer 1; epilogue of the three hidden layers
-        stage(4, 4, 3, 1, 0, 3, 1);   // output layers -> logits
+        stage(0, m_d1, 1, 1, 0, 0, 1);   // dynamics layer 1
+        stage(1, m_d2, 1, 1, 0, 1, 1);   // dynamics layer 2 -> un-normalised next state (+ folded reward layer 1)
+        if (fold) stage(2, 0, 0, 0, 1, 0, 0);     // the state is normalised
+        else stage(2, m_r1, 1, 0, 1, 0, 0);       // reward layer 1 in flight while the state is normalised
+        stage(3, m_pv, 1, 1, 0, 2, 1);   // policy / value layer 1; epilogue of the hidden layers
+        stage(4, m_out, 3, 1, 0, 3, 1);  // output layers -> logits
         int rc;
         if ((rc = ensure(e, e->tc_img[shape], img.size() * sizeof(float)))) return rc;
         if ((rc = ensure(e, e->tc_ctab[shape], ctab.size() * sizeof(float)))) return rc;
@@ -688,8 +729,8 @@ int build_schedules(tsp_engine* e) {
             const HSched fh = make(c.mask_absorbing_states != 0);
             if ((rc = lower_fast(e, fh, 0, 8))) return rc;
             if (e->has_fast && (rc = lower_fast(e, fh, 1, 4))) return rc;
-            if (e->has_fast && (rc = build_tc(e))) return rc;
         }
+        if ((rc = build_tc(e))) return rc;
     } else {  // one future of MuZeroStochasticConcat.dynamics: models.py:520-595
         HSched hs;
         hs.in_dim = H;
@@ -968,6 +1009,8 @@ int launch_fast_any(tsp_engine* e, const SearchParams& sp) {
         p.tc_status = reinterpret_cast<int*>(e->tc_status.p);
         if (lpt == 16 && tc_smem(ts, 2, p.S_tab) <= 227 * 1024) return launch_tc<2, 16>(e, p, ts);
         if (lpt == 8 && tc_smem(ts, 4, p.S_tab) <= 227 * 1024) return launch_tc<4, 8>(e, p, ts);
+        if (lpt == 8 && tc_smem(ts, 2, p.S_tab) <= 227 * 1024) return launch_tc<2, 8>(e, p, ts);
+        if (!e->has_fast) return fail(e, TSP_EINVAL, "internal: tcgen05 search kernel does not fit shared memory");
     }
     if (variant == 0 && fast_smem(e->fsched[which][0], 1, p.S_tab, false, 1) > 227 * 1024) {
         // the weights do not fit shared memory (cross-merge): stream them from L2, strips only in shared memory
@@ -1011,6 +1054,9 @@ int launch_search_any(tsp_engine* e, const SearchParams& p_in) {
     // batches the generic kernel's 32-row tiles reuse every streamed weight twice as often (12.2 vs 13.5 ms at 8,192 x 200).
     const bool small_batch = (p.B + GT - 1) / GT <= 2 * e->sm_count;
     const bool stream_ok = e->cfg.variant == 0 && !e->no_wglobal && (small_batch || e->force_wglobal);
+    if (e->nc == 5 && e->has_tc && !e->no_tc && !e->no_fast && e->finalized && e->cfg.variant == 0 && !p.fed && !p.mask_absorbing &&
+        tc_smem(e->tcs[0], 2, p.S_tab) <= 227 * 1024 && tc_smem(e->tcs[1], 2, p.S_tab) <= 227 * 1024)
+        return launch_fast_any(e, p);  // tcgen05 kernel (weights in tensor memory)
     if (e->nc == 5 && e->has_fast && !e->no_fast && e->finalized &&
         fast_smem(e->fsched[0][0], 1, p.S_tab, false, e->cfg.variant == 0 ? 1 : 2, stream_ok) <= 227 * 1024)
         return launch_fast_any(e, p);
@@ -1157,6 +1203,7 @@ int tsp_create(const tsp_config* cfg, tsp_handle* out) {
     if (const char* t = getenv("TSP_NO_FAST")) e->no_fast = atoi(t) != 0;
     if (const char* t = getenv("TSP_NO_WLO")) e->no_wlo = atoi(t) != 0;
     if (const char* t = getenv("TSP_NO_TC")) e->no_tc = atoi(t) != 0;
+    if (const char* t = getenv("TSP_TC_NOFOLD")) e->tc_nofold = atoi(t) != 0;
     if (const char* t = getenv("TSP_NO_WGLOBAL")) e->no_wglobal = atoi(t) != 0;
     if (const char* t = getenv("TSP_FORCE_WGLOBAL")) e->force_wglobal = atoi(t) != 0;
     if (const char* t = getenv("TSP_FAST_GROUPS")) e->fast_groups = atoi(t);

@@ -450,7 +450,7 @@ __device__ __forceinline__ void search_fast_body(const FastParams& p, const TcSc
     float* pbf = reinterpret_cast<float*>(sq + pb_n);                      // float32 pb[N] * sq[N] for the filter
     float* wsm = pbf + pbf_n;
     const int tid = threadIdx.x;
-    {
+    if (!TC) {
         const int4* src = reinterpret_cast<const int4*>(p.sched);
         int4* dst = reinterpret_cast<int4*>(fsp);
         for (int i = tid; i < (int)(sizeof(FastSched) / 16); i += THREADS) dst[i] = src[i];

@@ -58,7 +58,7 @@ struct TcStage {
     int mma0, n_mma;  // MMAs issued at the start of the stage
     int commit;       // commit them (and everything issued before) to the group's mbarrier
     int row_op;       // 1: min-max normalise xs -> xn (models.py:248-255) while the MMAs run
-    int epi0, n_epi;  // epilogue passes after the mbarrier wait
+    int epi0, n_epi;  // epilogue pass (n_epi <= 1) after the mbarrier wait
     int pad[2];
 };
 struct TcSched {
@@ -137,52 +137,66 @@ __device__ __forceinline__ void tmem_ld<16>(uint32_t taddr, uint32_t (&v)[16]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// One warp's share of an epilogue pass: NCNT trees (n0 a multiple of NCNT, or 0) of the lanes' features. All
-// per-tree addresses are the pass's base plus compile-time offsets.
+// One warp's share of an epilogue pass: NCNT trees (n0 a multiple of NCNT, or 0) of the lanes' features. Everything
+// that does not depend on the accumulator (bias, the trees' one-hot rows, addresses) is fetched BEFORE the wait on
+// the MMAs' mbarrier; all per-tree addresses are the pass's base plus compile-time offsets.
 template <int NCNT>
-__device__ __forceinline__ void tc_epi_warp(const TcEpi& ep, uint32_t d_tmem, unsigned char* __restrict__ arena, int b_lo,
+__device__ __forceinline__ bool tc_epi_warp(const TcEpi& ep, uint32_t d_tmem, unsigned char* __restrict__ arena, int b_lo,
                                             float* __restrict__ outs, int out_pitch, const float* __restrict__ ctab,
-                                            const int* __restrict__ row_action, int lane) {
-    uint32_t v[NCNT];
+                                            const int* __restrict__ row_action, int lane, uint32_t mbar, uint32_t parity) {
     const int n0 = ep.n0;
-    tmem_ld<NCNT>(d_tmem + (uint32_t)(ep.d_col + n0), v);
-    if (lane >= ep.rows) return;
-    const float bias = ctab[ep.cidx + lane];
-    if (ep.flags & 2) {  // raw logits for decode_row: out strip [tree][column]
-        float* o = outs + n0 * out_pitch + ep.dst + lane;
+    const bool on = lane < ep.rows;
+    const int flags = ep.flags;
+    float add[NCNT];
+    {
+        const float bias = on ? ctab[ep.cidx + lane] : 0.0f;
 #pragma unroll
-        for (int i = 0; i < NCNT; ++i) {
-            *o = __uint_as_float(v[i]) + bias;
-            o += out_pitch;
+        for (int i = 0; i < NCNT; ++i) add[i] = bias;
+        if (ep.eidx >= 0 && on) {  // one-hot action input == one gathered weight row per tree (models.py:236-243)
+            const float* erow = ctab + ep.eidx + lane;
+            const int e_ld = ep.e_ld;
+            int act[NCNT];
+            if constexpr (NCNT >= 4) {
+#pragma unroll
+                for (int i = 0; i < NCNT; i += 4) {
+                    const int4 a4 = *reinterpret_cast<const int4*>(row_action + n0 + i);
+                    act[i] = a4.x; act[i + 1] = a4.y; act[i + 2] = a4.z; act[i + 3] = a4.w;
+                }
+            } else {
+                const int2 a2 = *reinterpret_cast<const int2*>(row_action + n0);
+                act[0] = a2.x; act[1] = a2.y;
+            }
+#pragma unroll
+            for (int i = 0; i < NCNT; ++i) add[i] += erow[act[i] * e_ld];
         }
-        return;
     }
+    const int k = ep.feat0 + lane;
+    unsigned char* hi = (flags & 2) ? reinterpret_cast<unsigned char*>(outs + n0 * out_pitch + ep.dst + lane)
+                                    : arena + ep.dst + (k >> 2) * TC_LBO + (k & 3) * 4 + (n0 >> 3) * ep.dst_sbo + (n0 & 7) * 16;
+    const int sbo = ep.dst_sbo;
+    const uint32_t taddr = d_tmem + (uint32_t)(ep.d_col + n0);
+    // ---- the accumulator
+    const bool ok = mbar_wait(mbar, parity);
+    tc_fence_after();
+    uint32_t v[NCNT];
+    tmem_ld<NCNT>(taddr, v);
+    if (!on) return ok;
     float y[NCNT];
 #pragma unroll
-    for (int i = 0; i < NCNT; ++i) y[i] = __uint_as_float(v[i]) + bias;
-    if (ep.eidx >= 0) {  // one-hot action input == one gathered weight row per tree (models.py:236-243)
-        const float* erow = ctab + ep.eidx + lane;
-        const int e_ld = ep.e_ld;
-        int act[NCNT];
-        if constexpr (NCNT >= 4) {
+    for (int i = 0; i < NCNT; ++i) y[i] = __uint_as_float(v[i]) + add[i];
+    if (flags & 2) {  // raw logits for decode_row: out strip [tree][column]
+        float* o = reinterpret_cast<float*>(hi);
 #pragma unroll
-            for (int i = 0; i < NCNT; i += 4) {
-                const int4 a4 = *reinterpret_cast<const int4*>(row_action + n0 + i);
-                act[i] = a4.x; act[i + 1] = a4.y; act[i + 2] = a4.z; act[i + 3] = a4.w;
-            }
-        } else {
-            const int2 a2 = *reinterpret_cast<const int2*>(row_action + n0);
-            act[0] = a2.x; act[1] = a2.y;
+        for (int i = 0; i < NCNT; ++i) {
+            *o = y[i];
+            o += out_pitch;
         }
-#pragma unroll
-        for (int i = 0; i < NCNT; ++i) y[i] += erow[act[i] * e_ld];
+        return ok;
     }
-    if (ep.flags & 1) {
+    if (flags & 1) {
 #pragma unroll
         for (int i = 0; i < NCNT; ++i) y[i] = elu_fast(y[i]);
     }
-    const int k = ep.feat0 + lane;
-    unsigned char* hi = arena + ep.dst + (k >> 2) * TC_LBO + (k & 3) * 4 + (n0 >> 3) * ep.dst_sbo + (n0 & 7) * 16;
     unsigned char* lo = hi + b_lo;
 #pragma unroll
     for (int i = 0; i < (NCNT < 8 ? NCNT : 8); ++i) {
@@ -190,14 +204,15 @@ __device__ __forceinline__ void tc_epi_warp(const TcEpi& ep, uint32_t d_tmem, un
         *reinterpret_cast<float*>(lo + 16 * i) = tf32_lo(y[i]);
     }
     if constexpr (NCNT == 16) {
-        hi += ep.dst_sbo;
-        lo += ep.dst_sbo;
+        hi += sbo;
+        lo += sbo;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             *reinterpret_cast<float*>(hi + 16 * i) = y[8 + i];
             *reinterpret_cast<float*>(lo + 16 * i) = tf32_lo(y[8 + i]);
         }
     }
+    return ok;
 }
 
 // The 3 * KS MMAs of one layer (3xTF32), fully unrolled: one thread issues them.
@@ -295,19 +310,18 @@ __device__ __forceinline__ bool tc_mlp(const TcSched& ts, uint32_t tmem_base, ui
             }
             fence_async_smem();
         }
-        if (st.n_epi > 0) {
-            ok = mbar_wait(mbar, parity) && ok;
+        if (st.n_epi > 0) {  // one pass per stage: every warp of the group waits on the stage's commit
+            const TcEpi& ep = ts.epi[st.epi0][gw];
+            const uint32_t d_tmem = d_group + lane_q;
+            bool w;
+            if (ep.ncnt == 2) w = tc_epi_warp<2>(ep, d_tmem, arena, ts.b_lo, outs, ts.out_pitch, ctab, row_action, lane, mbar, parity);
+            else if (ep.ncnt == 4) w = tc_epi_warp<4>(ep, d_tmem, arena, ts.b_lo, outs, ts.out_pitch, ctab, row_action, lane, mbar, parity);
+            else if (ep.ncnt == 8) w = tc_epi_warp<8>(ep, d_tmem, arena, ts.b_lo, outs, ts.out_pitch, ctab, row_action, lane, mbar, parity);
+            else if (ep.ncnt == 16) w = tc_epi_warp<16>(ep, d_tmem, arena, ts.b_lo, outs, ts.out_pitch, ctab, row_action, lane, mbar, parity);
+            else w = mbar_wait(mbar, parity);
+            ok = ok && w;
             parity ^= 1u;
-            tc_fence_after();
             if (tm) q2 = clock64();
-            for (int e = st.epi0; e < st.epi0 + st.n_epi; ++e) {
-                const TcEpi& ep = ts.epi[e][gw];
-                const uint32_t d_tmem = d_group + lane_q;
-                if (ep.ncnt == 2) tc_epi_warp<2>(ep, d_tmem, arena, ts.b_lo, outs, ts.out_pitch, ctab, row_action, lane);
-                else if (ep.ncnt == 4) tc_epi_warp<4>(ep, d_tmem, arena, ts.b_lo, outs, ts.out_pitch, ctab, row_action, lane);
-                else if (ep.ncnt == 8) tc_epi_warp<8>(ep, d_tmem, arena, ts.b_lo, outs, ts.out_pitch, ctab, row_action, lane);
-                else if (ep.ncnt == 16) tc_epi_warp<16>(ep, d_tmem, arena, ts.b_lo, outs, ts.out_pitch, ctab, row_action, lane);
-            }
             fence_async_smem();
             tc_fence_before();
         }
