@@ -4,7 +4,8 @@ The kernel replaces only the MLP of tsp::search_fast_kernel; selection / expansi
 Checked here, through the C ABI:
   * the dispatcher really runs it (stats.search_kernel == 2) for the fully-connected MuZero nets of the
     highway / roundabout game files in both group shapes, and keeps the mma.sync kernels where the network is
-    outside its envelope (terminal head, chance-node searches, cross-merge);
+    outside its envelope (terminal head, cross-merge); the stochastic and risk-sensitive searches run their two
+    networks (one future of a transition expansion, prediction) on it as well;
   * the engine's own network outputs replayed through the oracle's tree code give bit-identical root statistics,
     and the traced network outputs agree with the oracle's float32 network within 1e-5 (check_against_oracle);
   * it agrees with the mma.sync kernel on the same inputs (both are 3xTF32 float32-accurate networks);
@@ -44,8 +45,7 @@ def test_dispatch_runs_the_tcgen05_kernel(B, shape):
 
 
 def test_outside_the_envelope_keeps_the_mma_sync_kernels(monkeypatch):
-    for name, opts in (("roundabout_env_ttc_flat", dict(mask_absorbing_states=True)),
-                       ("roundabout_env_ttc_flat_stochastic_concat", {}), ("cross_merge_env", {})):
+    for name, opts in (("roundabout_env_ttc_flat", dict(mask_absorbing_states=True)), ("cross_merge_env", {})):
         cfg = tsp.get_config(name, num_simulations=10, **opts)
         st, _ = search_kernel_of(cfg, 256, 10)
         assert st["search_kernel"] in (0, 1), name
@@ -96,3 +96,26 @@ def test_ragged_uniform_and_two_players_on_tcgen05():
     check_against_oracle(cfg, 1000, 25, seed=23, legal=True)
     check_against_oracle(cfg, 1000, 25, seed=24, uniform_policy=True, min_agree=0.9)
     check_against_oracle(cfg.replace(players=[0, 1]), 1000, 25, seed=25, min_agree=0.9)
+
+
+@pytest.mark.parametrize("game", ["roundabout_env_ttc_flat_stochastic_concat", "roundabout_env_ttc_flat_risk_sensitive"])
+@pytest.mark.parametrize("B", [1500, 9000])
+def test_chance_node_searches_on_tcgen05(game, B):
+    """Transition expansions (nf futures through dynamics + reward head + prior head) and state expansions
+    (prediction) on the tensor-memory path: trace replay bit-exact, network within 1e-5 of the oracle's."""
+    cfg = tsp.get_config(game)
+    st, out = search_kernel_of(cfg, B, 25)
+    assert st["search_kernel"] == 2
+    assert (st["trees_per_cta"], st["threads_per_cta"]) == ((32, 512) if B <= 16 * 2 * st["sm_count"] else (64, 512))
+    assert (out["visit_counts"].sum(1) == 25).all()
+    check_against_oracle(cfg, B, 25, seed=31, legal=(B == 1500))
+
+
+@pytest.mark.parametrize("game", ["roundabout_env_ttc_flat_stochastic_concat", "roundabout_env_ttc_flat_risk_sensitive"])
+def test_chance_node_searches_agree_with_the_mma_sync_kernel(game, monkeypatch):
+    cfg = tsp.get_config(game)
+    st_tc, tc = search_kernel_of(cfg, 4096, 25)
+    st_mm, mm = search_kernel_of(cfg, 4096, 25, monkeypatch, TSP_NO_TC="1")
+    assert st_tc["search_kernel"] == 2 and st_mm["search_kernel"] == 1
+    same = (tc["visit_counts"] == mm["visit_counts"]).all(axis=1)
+    assert same.mean() >= 0.97, same.mean()

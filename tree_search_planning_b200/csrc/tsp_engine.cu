@@ -607,7 +607,7 @@ int build_tc(tsp_engine* e) {
             for (int h = 0; h < parts; ++h) {
                 TcEpi& x = ts.epi[pass][q + 4 * h];
                 x.d_col = (short)d_col; x.n0 = (short)(n0 + h * (ncnt / parts)); x.ncnt = (short)(ncnt / parts); x.rows = (short)rows;
-                x.dst = dst; x.dst_sbo = dst_sbo; x.feat0 = feat0; x.cidx = cidx; x.eidx = eidx; x.e_ld = 32; x.flags = flags;
+                x.dst = dst; x.dst_sbo = dst_sbo; x.feat0 = feat0; x.cidx = cidx; x.eidx = eidx; x.e_ld = 32; x.zidx = -1; x.flags = flags;
             }
         };
         if (rep) {
@@ -651,6 +651,165 @@ int build_tc(tsp_engine* e) {
         else stage(2, m_r1, 1, 0, 1, 0, 0);       // reward layer 1 in flight while the state is normalised
         stage(3, m_pv, 1, 1, 0, 2, 1);   // policy / value layer 1; epilogue of the hidden layers
         stage(4, m_out, 3, 1, 0, 3, 1);  // output layers -> logits
+        int rc;
+        if ((rc = ensure(e, e->tc_img[shape], img.size() * sizeof(float)))) return rc;
+        if ((rc = ensure(e, e->tc_ctab[shape], ctab.size() * sizeof(float)))) return rc;
+        CK(e, cudaMemcpyAsync(e->tc_img[shape].p, img.data(), img.size() * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+        CK(e, cudaMemcpyAsync(e->tc_ctab[shape].p, ctab.data(), ctab.size() * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+        CK(e, cudaStreamSynchronize(e->stream));
+    }
+    int rc;
+    if ((rc = ensure(e, e->tc_status, sizeof(int)))) return rc;
+    CK(e, cudaMemset(e->tc_status.p, 0, sizeof(int)));
+    e->has_tc = true;
+    return TSP_OK;
+}
+
+// tcgen05 tables of the chance-node searches (MuZeroStochasticConcat, models.py:465-595): stages [0, 4) evaluate ONE future z
+// of a transition expansion (dynamics on [h | onehot(a) | onehot(z)] -> reward head on the un-normalised state (first
+// layer folded into the MMA of dynamics layer 2, see build_tc) -> min-max normalise; plus the transition prior head on h),
+// stages [4, 6) the prediction of a state expansion. One K = H weight set serves both (lanes: dynamics 1 | prior 1 |
+// policy 1 | value 1), one K = 32 set holds the four output layers (lanes: reward | prior | policy | value).
+int build_tc_variant(tsp_engine* e) {
+    e->has_tc = false;
+    const tsp_config& c = e->cfg;
+    if (c.variant == TSP_VARIANT_MUZERO || e->nc != 5) return TSP_OK;
+    for (int m : {TSP_MLP_DYNAMICS, TSP_MLP_REWARD, TSP_MLP_POLICY, TSP_MLP_VALUE, TSP_MLP_PRIOR})
+        if (e->mlp[m].size() != 2) return TSP_OK;
+    const HostLayer &D1 = e->mlp[TSP_MLP_DYNAMICS][0], &D2 = e->mlp[TSP_MLP_DYNAMICS][1];
+    const HostLayer &R1 = e->mlp[TSP_MLP_REWARD][0], &R2 = e->mlp[TSP_MLP_REWARD][1];
+    const HostLayer &P1 = e->mlp[TSP_MLP_POLICY][0], &P2 = e->mlp[TSP_MLP_POLICY][1];
+    const HostLayer &V1 = e->mlp[TSP_MLP_VALUE][0], &V2 = e->mlp[TSP_MLP_VALUE][1];
+    const HostLayer &Q1 = e->mlp[TSP_MLP_PRIOR][0], &Q2 = e->mlp[TSP_MLP_PRIOR][1];
+    const int H = c.encoding_size, A = c.num_actions, nf = c.n_futures;
+    const int DH = D1.out_dim, RH = R1.out_dim, PH = P1.out_dim, VH = V1.out_dim, QH = Q1.out_dim;
+    const int NR = R2.out_dim, NV = V2.out_dim;
+    for (int w : {H, DH, RH, PH, VH, QH})
+        if (w % 8 || w < 8) return TSP_OK;
+    if (H > 64 || DH > 32 || RH > 32 || PH > 32 || VH > 32 || QH > 32 || NR > 32 || NV > 32 || A > 32 || nf > 32) return TSP_OK;
+    if (D1.in_dim != H + A + nf || D2.out_dim != H || H + RH > 128) return TSP_OK;
+    const int HK = std::max(std::max(RH, QH), std::max(PH, VH));
+    auto bufsz = [](int K) { return 2 * (K / 4) * TC_LBO; };
+    auto sbo = [](int K) { return (K / 4) * TC_LBO; };
+    std::vector<float> FW((size_t)RH * DH), Fb((size_t)RH);
+    for (int r = 0; r < RH; ++r) {
+        for (int k = 0; k < DH; ++k) {
+            double acc = 0.0;
+            for (int h = 0; h < H; ++h) acc += (double)R1.W[(size_t)r * H + h] * (double)D2.W[(size_t)h * DH + k];
+            FW[(size_t)r * DH + k] = (float)acc;
+        }
+        double acc = R1.b[(size_t)r];
+        for (int h = 0; h < H; ++h) acc += (double)R1.W[(size_t)r * H + h] * (double)D2.b[(size_t)h];
+        Fb[(size_t)r] = (float)acc;
+    }
+    for (int shape = 0; shape < 2; ++shape) {
+        TcSched& ts = e->tcs[shape];
+        memset(&ts, 0, sizeof(ts));
+        const int G = shape == 0 ? 2 : 4;
+        const int parts = shape == 0 ? 2 : 1;  // 8 warps per group: warps q and q + 4 split the trees of lane quarter q
+        const int c1 = 0, c2 = c1 + H, c4 = c2 + DH, hi_cols = c4 + HK;
+        ts.a_lo = hi_cols;
+        ts.n_cols = 2 * hi_cols;
+        ts.d_col0 = ts.n_cols;
+        ts.d_cols_group = 48;
+        if (ts.n_cols % 8 || ts.d_col0 + G * ts.d_cols_group > TC_TMEM_COLS) return TSP_OK;
+        int o = 0;
+        const int xh = o; o += bufsz(H);
+        const int xd = o; o += bufsz(DH);
+        const int xq = o; o += bufsz(QH);
+        const int xs = o; o += bufsz(H);
+        const int xr = o; o += bufsz(RH);
+        const int xp = o; o += bufsz(PH);
+        const int xv = o; o += bufsz(VH);
+        ts.b_lo = o;
+        ts.arena_bytes = (2 * o + 127) & ~127;
+        ts.xh_off = xh; ts.xh_sbo = sbo(H);
+        ts.xs_off = xs; ts.xs_sbo = sbo(H);
+        ts.xn_off = -1; ts.xn_sbo = 0;  // no layer reads the normalised state of a future: it goes to the hidden-state pool only
+        ts.H = H;
+        ts.off_vl = 0; ts.off_rl = NV; ts.off_pl = NV + NR; ts.off_tp = NV + NR + A;
+        int pitch = NV + NR + A + nf;
+        if (shape == 0) while (pitch % 32 != 16) ++pitch;
+        else while (pitch % 32 != 8 && pitch % 32 != 24) ++pitch;
+        ts.out_pitch = pitch;
+        std::vector<float> ctab;
+        auto put = [&](const std::vector<float>& v, int n) {
+            const int at = (int)ctab.size();
+            for (int i = 0; i < n; ++i) ctab.push_back(v[(size_t)i]);
+            while (ctab.size() % 32) ctab.push_back(0.0f);
+            return at;
+        };
+        const int t_b1 = put(D1.b, DH);
+        std::vector<float> e1((size_t)(A + nf) * 32, 0.0f);  // one-hot action rows, then one-hot future rows
+        for (int a = 0; a < A + nf; ++a)
+            for (int r = 0; r < DH; ++r) e1[(size_t)a * 32 + r] = D1.W[(size_t)r * D1.in_dim + H + a];
+        const int t_e1 = put(e1, (A + nf) * 32);
+        const int t_bq1 = put(Q1.b, QH), t_b2 = put(D2.b, H), t_bf = put(Fb, RH);
+        const int t_bp1 = put(P1.b, PH), t_bv1 = put(V1.b, VH);
+        const int t_br2 = put(R2.b, NR), t_bq2 = put(Q2.b, nf), t_bp2 = put(P2.b, A), t_bv2 = put(V2.b, NV);
+        for (int i = 0; i < 64; ++i) ctab.push_back(0.0f);
+        if ((int)ctab.size() > TC_MAX_CTAB) return TSP_OK;
+        ts.ctab_floats = (int)ctab.size();
+        std::vector<float> img((size_t)ts.n_cols * 128, 0.0f);
+        auto place = [&](const HostLayer& L, int col0, int lane0, int K) {
+            for (int r = 0; r < L.out_dim; ++r)
+                for (int k = 0; k < K; ++k) img[(size_t)(col0 + k) * 128 + lane0 + r] = L.W[(size_t)r * L.in_dim + k];
+        };
+        const int h_q = (H + 31) / 32;
+        place(D1, c1, 0, H); place(Q1, c1, 32, H); place(P1, c1, 64, H); place(V1, c1, 96, H);
+        place(D2, c2, 0, DH);
+        for (int r = 0; r < RH; ++r)
+            for (int k = 0; k < DH; ++k) img[(size_t)(c2 + k) * 128 + 32 * h_q + r] = FW[(size_t)r * DH + k];
+        place(R2, c4, 0, RH); place(Q2, c4, 32, QH); place(P2, c4, 64, PH); place(V2, c4, 96, VH);
+        for (int col = 0; col < hi_cols; ++col)
+            for (int l = 0; l < 128; ++l) {
+                const float w = img[(size_t)col * 128 + l];
+                uint32_t bits;
+                memcpy(&bits, &w, 4);
+                bits &= 0xFFFFE000u;
+                float hi;
+                memcpy(&hi, &bits, 4);
+                img[(size_t)(hi_cols + col) * 128 + l] = w - hi;
+            }
+        auto mma = [&](int i, int a_col, int b_off, int K, int d_col) {
+            ts.mma[i].a_col = a_col; ts.mma[i].b_off = b_off; ts.mma[i].ksteps = K / 8; ts.mma[i].sbo = sbo(K); ts.mma[i].d_col = d_col;
+        };
+        const int DA = 0, DB = 16;
+        mma(0, c1, xh, H, DA);    // dynamics 1 | prior 1
+        mma(1, c2, xd, DH, DB);   // dynamics 2 | folded reward 1
+        mma(2, c4, xr, RH, DA);   // reward 2 (lanes 0..31)
+        mma(3, c4, xq, QH, DB);   // prior 2 (lanes 32..63)
+        mma(4, c1, xh, H, DA);    // policy 1 | value 1 (lanes 64..127)
+        mma(5, c4, xp, PH, DA);   // policy 2 (lanes 64..95)
+        mma(6, c4, xv, VH, DB);   // value 2 (lanes 96..127)
+        auto epi = [&](int pass, int q, int d_col, int rows, int dst, int dst_sbo, int feat0, int cidx, int eidx, int zidx, int flags) {
+            for (int h = 0; h < parts; ++h) {
+                TcEpi& x = ts.epi[pass][q + 4 * h];
+                x.d_col = (short)d_col; x.n0 = (short)(h * (16 / parts)); x.ncnt = (short)(16 / parts); x.rows = (short)rows;
+                x.dst = dst; x.dst_sbo = dst_sbo; x.feat0 = feat0; x.cidx = cidx; x.eidx = eidx; x.e_ld = 32; x.zidx = zidx; x.flags = flags;
+            }
+        };
+        epi(0, 0, DA, DH, xd, sbo(DH), 0, t_b1, t_e1, t_e1 + A * 32, 1);
+        epi(0, 1, DA, QH, xq, sbo(QH), 0, t_bq1, -1, -1, 1);
+        for (int q = 0; q < h_q; ++q) epi(1, q, DB, std::min(32, H - 32 * q), xs, sbo(H), 32 * q, t_b2 + 32 * q, -1, -1, 0);
+        epi(1, h_q, DB, RH, xr, sbo(RH), 0, t_bf, -1, -1, 1);
+        epi(2, 0, DA, NR, ts.off_rl, 0, 0, t_br2, -1, -1, 2);
+        epi(2, 1, DB, nf, ts.off_tp, 0, 0, t_bq2, -1, -1, 2);
+        epi(3, 2, DA, PH, xp, sbo(PH), 0, t_bp1, -1, -1, 1);
+        epi(3, 3, DA, VH, xv, sbo(VH), 0, t_bv1, -1, -1, 1);
+        epi(4, 2, DA, A, ts.off_pl, 0, 0, t_bp2, -1, -1, 2);
+        epi(4, 3, DB, NV, ts.off_vl, 0, 0, t_bv2, -1, -1, 2);
+        auto stage = [&](int s, int mma0, int n_mma, int commit, int row_op, int epi0, int n_epi) {
+            ts.stage[s].mma0 = mma0; ts.stage[s].n_mma = n_mma; ts.stage[s].commit = commit; ts.stage[s].row_op = row_op;
+            ts.stage[s].epi0 = epi0; ts.stage[s].n_epi = n_epi;
+        };
+        ts.n_stages = 6;
+        stage(0, 0, 1, 1, 0, 0, 1);
+        stage(1, 1, 1, 1, 0, 1, 1);
+        stage(2, 0, 0, 0, 1, 0, 0);
+        stage(3, 2, 2, 1, 0, 2, 1);
+        stage(4, 4, 1, 1, 0, 3, 1);
+        stage(5, 5, 2, 1, 0, 4, 1);
         int rc;
         if ((rc = ensure(e, e->tc_img[shape], img.size() * sizeof(float)))) return rc;
         if ((rc = ensure(e, e->tc_ctab[shape], ctab.size() * sizeof(float)))) return rc;
@@ -770,6 +929,7 @@ int build_schedules(tsp_engine* e) {
             }
             e->has_fast = ok;
         }
+        if ((rc = build_tc_variant(e))) return rc;
     }
     for (Schedule* s : {&e->sch_root, &e->sch_pred, &e->sch_recur, &e->sch_trans})
         if (s->n_stages && s->off_in != 0) return fail(e, TSP_EINVAL, "internal: schedule input not at offset 0");
@@ -953,6 +1113,30 @@ int launch_tc(tsp_engine* e, const FastParams& p, const TcSched& ts) {
     return TSP_OK;
 }
 
+size_t tc_variant_smem(const TcSched& ts, int G, int S) {
+    const size_t pb_n = (size_t)((S + 3) & ~1);
+    return pb_n * 16 + ((pb_n + 3) & ~(size_t)3) * 4 + (size_t)((ts.ctab_floats + 3) & ~3) * 4 + 64 + 256 +
+           (size_t)G * (ts.arena_bytes + (GT * ts.out_pitch + GT + GT / 4) * 4);
+}
+
+template <int G, int LPT, int VARIANT>
+int launch_tc_variant(tsp_engine* e, const FastParams& p, const TcSched& ts) {
+    const size_t smem = std::max(tc_variant_smem(ts, G, p.S_tab), (size_t)120 * 1024);  // one CTA per SM (it owns the SM's tensor memory)
+    int rc = set_smem(e, search_tc_variant_kernel<G, LPT, VARIANT>, smem);
+    if (rc) return rc;
+    const int grid = (p.B + G * GT - 1) / (G * GT);
+    constexpr int GTHREADS = GT * LPT;
+    search_tc_variant_kernel<G, LPT, VARIANT><<<grid, G * GTHREADS, smem, e->stream>>>(p, ts);
+    CK(e, cudaGetLastError());
+    e->stats.kernel_launches++;
+    e->stats.search_ctas = grid;
+    e->stats.search_smem_bytes = (int)smem;
+    e->stats.trees_per_cta = G * GT;
+    e->stats.threads_per_cta = G * GTHREADS;
+    e->stats.search_kernel = 2;
+    return TSP_OK;
+}
+
 template <int G, int LPT, int VARIANT>
 int launch_fast_variant(tsp_engine* e, const FastParams& p) {
     const size_t smem = fast_smem(e->fsched[LPT == 16 ? 0 : 1][0], G, p.S_tab, p.w_lo != 0, 2);
@@ -1012,6 +1196,18 @@ int launch_fast_any(tsp_engine* e, const SearchParams& sp) {
         if (lpt == 8 && tc_smem(ts, 2, p.S_tab) <= 227 * 1024) return launch_tc<2, 8>(e, p, ts);
         if (!e->has_fast) return fail(e, TSP_EINVAL, "internal: tcgen05 search kernel does not fit shared memory");
     }
+    if (variant != 0 && e->has_tc && !e->no_tc && !p.fed) {
+        const TcSched& ts = e->tcs[which];
+        p.tc_img = reinterpret_cast<const float*>(e->tc_img[which].p);
+        p.tc_ctab = reinterpret_cast<const float*>(e->tc_ctab[which].p);
+        p.tc_status = reinterpret_cast<int*>(e->tc_status.p);
+#define TSP_LAUNCH_TV(GG, LL) (variant == 1 ? launch_tc_variant<GG, LL, 1>(e, p, ts) : launch_tc_variant<GG, LL, 2>(e, p, ts))
+        if (lpt == 16 && tc_variant_smem(ts, 2, p.S_tab) <= 227 * 1024) return TSP_LAUNCH_TV(2, 16);
+        if (lpt == 8 && tc_variant_smem(ts, 4, p.S_tab) <= 227 * 1024) return TSP_LAUNCH_TV(4, 8);
+        if (lpt == 8 && tc_variant_smem(ts, 2, p.S_tab) <= 227 * 1024) return TSP_LAUNCH_TV(2, 8);
+#undef TSP_LAUNCH_TV
+        if (!e->has_fast) return fail(e, TSP_EINVAL, "internal: tcgen05 search kernel does not fit shared memory");
+    }
     if (variant == 0 && fast_smem(e->fsched[which][0], 1, p.S_tab, false, 1) > 227 * 1024) {
         // the weights do not fit shared memory (cross-merge): stream them from L2, strips only in shared memory
         int G = lpt == 16 ? 2 : 4;
@@ -1057,6 +1253,9 @@ int launch_search_any(tsp_engine* e, const SearchParams& p_in) {
     if (e->nc == 5 && e->has_tc && !e->no_tc && !e->no_fast && e->finalized && e->cfg.variant == 0 && !p.fed && !p.mask_absorbing &&
         tc_smem(e->tcs[0], 2, p.S_tab) <= 227 * 1024 && tc_smem(e->tcs[1], 2, p.S_tab) <= 227 * 1024)
         return launch_fast_any(e, p);  // tcgen05 kernel (weights in tensor memory)
+    if (e->nc == 5 && e->has_tc && !e->no_tc && !e->no_fast && e->finalized && e->cfg.variant != 0 && !p.fed &&
+        tc_variant_smem(e->tcs[0], 2, p.S_tab) <= 227 * 1024 && tc_variant_smem(e->tcs[1], 2, p.S_tab) <= 227 * 1024)
+        return launch_fast_any(e, p);
     if (e->nc == 5 && e->has_fast && !e->no_fast && e->finalized &&
         fast_smem(e->fsched[0][0], 1, p.S_tab, false, e->cfg.variant == 0 ? 1 : 2, stream_ok) <= 227 * 1024)
         return launch_fast_any(e, p);

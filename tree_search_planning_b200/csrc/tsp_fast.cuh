@@ -922,6 +922,76 @@ __global__ void __launch_bounds__(G * GT * LPT, 1) search_tc_kernel(const __grid
     search_fast_body<G, LPT, false, true>(p, &ts);
 }
 
+// Per-thread view of the tcgen05 path's state (tsp_tc.cuh) and its set-up: constant table, mbarriers, the group's
+// {B-operand arena, out strip, row tables} behind `base`, tensor-memory allocation and the weight image -> TMEM.
+// Must be followed by __syncthreads() and tc_fence_after().
+struct TcCtx {
+    unsigned char* arena;
+    float* outs;
+    const float* ctab;
+    int* row_action;
+    unsigned char* row_active;
+    int* path;
+    uint32_t tmem_base, d_group, mbar, parity;
+    int gw;
+};
+template <int G, int GTHREADS, int PATH>
+__device__ __forceinline__ void tc_setup(TcCtx& c, const FastParams& p, const TcSched& ts, float* base, int tid, int grp, int row) {
+    constexpr int THREADS = G * GTHREADS;
+    const int ctab_n = (ts.ctab_floats + 3) & ~3;
+    unsigned long long* mbars = reinterpret_cast<unsigned long long*>(base + ctab_n);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbars + 4);
+    unsigned char* gbase = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 127) & ~(uintptr_t)127);
+    const int gstride = ts.arena_bytes + (GT * ts.out_pitch + GT + GT / 4 + GT * PATH) * 4;
+    c.ctab = base;
+    c.arena = gbase + (size_t)grp * gstride;
+    c.outs = reinterpret_cast<float*>(c.arena + ts.arena_bytes);
+    c.row_action = reinterpret_cast<int*>(c.outs + GT * ts.out_pitch);
+    c.row_active = reinterpret_cast<unsigned char*>(c.row_action + GT);
+    c.path = c.row_action + GT + GT / 4 + row * PATH;
+    const int warp_u = __shfl_sync(FULL, tid >> 5, 0);  // provably warp-uniform
+    const int grp_u = warp_u / (GTHREADS / 32);
+    c.gw = warp_u % (GTHREADS / 32);
+    c.parity = 0;
+    for (int i = tid; i < ts.ctab_floats; i += THREADS) base[i] = p.tc_ctab[i];
+    if (tid < G) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbars + tid)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp_u == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TC_TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    c.tmem_base = *tmem_slot;
+    c.mbar = smem_u32(mbars + grp_u);
+    c.d_group = c.tmem_base + ts.d_col0 + grp_u * ts.d_cols_group;
+    const uint32_t q = (uint32_t)(warp_u & 3);
+    const float* img = p.tc_img + 32 * q + (tid & 31);
+    for (int c0 = 8 * (warp_u >> 2); c0 < ts.n_cols; c0 += 8 * (THREADS / 128)) {
+        uint32_t r[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r[i] = __float_as_uint(__ldg(img + (size_t)(c0 + i) * 128));
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(c.tmem_base + ((32u * q) << 16) + c0),
+                     "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                     : "memory");
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    tc_fence_before();
+}
+template <int LPT>
+__device__ __forceinline__ void tc_gather_hidden(const TcSched& ts, unsigned char* arena, const float* __restrict__ hsrc, int H, int row, int j) {
+    const float4* src = reinterpret_cast<const float4*>(hsrc);
+    unsigned char* d = arena + ts.xh_off + (row >> 3) * ts.xh_sbo + (row & 7) * 16;
+    for (int i = j; i < (H >> 2); i += LPT) {
+        const float4 h4 = src[i];
+        *reinterpret_cast<float4*>(d + i * TC_LBO) = h4;
+        *reinterpret_cast<float4*>(d + i * TC_LBO + ts.b_lo) = make_float4(tf32_lo(h4.x), tf32_lo(h4.y), tf32_lo(h4.z), tf32_lo(h4.w));
+    }
+}
+
 // ------------------------------------------------------- chance-node searches ----
 // OR of a predicate over the threads of a group (named barrier reduction)
 template <int GTHREADS>
@@ -965,8 +1035,10 @@ __device__ __noinline__ int select_exact_v(double pbN, double sqN, int vis, doub
 // the same float32-filtered selection at StateNode levels, chance outcomes from the external stream at
 // TransitionNode levels, two unit schedules (one future of a transition expansion, evaluated once per future;
 // the prediction of a state expansion), the reference's backups walked by one lane per tree.
-template <int G, int LPT, int VARIANT>
-__global__ void __launch_bounds__(G * GT * LPT, 512 / (G * GT * LPT)) search_fast_variant_kernel(const __grid_constant__ FastParams p) {
+// TC: both networks on tcgen05 with the weights resident in tensor memory (tsp_tc.cuh): stages [0, 4) of the TcSched are
+// one future of a transition expansion, stages [4, 6) the prediction of a state expansion.
+template <int G, int LPT, int VARIANT, bool TC>
+__device__ __forceinline__ void search_fast_variant_body(const FastParams& p, const TcSched* __restrict__ tsp_) {
     extern __shared__ __align__(16) float smem[];
     constexpr int GTHREADS = GT * LPT;
     constexpr int THREADS = G * GTHREADS;
@@ -977,12 +1049,12 @@ __global__ void __launch_bounds__(G * GT * LPT, 512 / (G * GT * LPT)) search_fas
     FastSched* fsb = fsa + 1;
     const int pb_n = (p.S_tab + 2 + 1) & ~1;
     const int pbf_n = (pb_n + 3) & ~3;
-    double* pb = reinterpret_cast<double*>(smem + 2 * sizeof(FastSched) / 4);
+    double* pb = reinterpret_cast<double*>(smem + (TC ? 0 : 2 * sizeof(FastSched) / 4));  // TC: no unit schedules in shared memory
     double* sq = pb + pb_n;
     float* pbf = reinterpret_cast<float*>(sq + pb_n);
     float* wsm = pbf + pbf_n;
     const int tid = threadIdx.x;
-    {
+    if (!TC) {
         const int4* sa = reinterpret_cast<const int4*>(p.sched);
         const int4* sb = reinterpret_cast<const int4*>(p.sched_b);
         int4* da = reinterpret_cast<int4*>(fsa);
@@ -998,25 +1070,39 @@ __global__ void __launch_bounds__(G * GT * LPT, 512 / (G * GT * LPT)) search_fas
         sq[i] = c;
         pbf[i] = (float)(a * c);
     }
-    const bool fed = p.fed != nullptr;
+    const bool fed = !TC && p.fed != nullptr;
     __syncthreads();
     const FastSched& fA = *fsa;
     const FastSched& fB = *fsb;
-    const int rs = fA.row_stride;  // the host gives both schedules the same strip geometry
-    const int wlo_off = p.w_lo ? fA.w_floats : 0;
-    const int w_total = fA.w_floats + wlo_off;
-    if (!fed) {
+    const int rs = TC ? 0 : fA.row_stride;  // the host gives both schedules the same strip geometry
+    const int wlo_off = (p.w_lo && !TC) ? fA.w_floats : 0;
+    const int w_total = TC ? 0 : fA.w_floats + wlo_off;
+    if (!fed && !TC) {
         const float4* src = reinterpret_cast<const float4*>(p.wfrag);
         float4* dst = reinterpret_cast<float4*>(wsm);
         for (int i = tid; i < (w_total >> 2); i += THREADS) dst[i] = __ldg(src + i);
     }
     const int grp = tid / GTHREADS, gt = tid % GTHREADS;
-    float* act = wsm + w_total + grp * (GT * rs + GT + GT + GT * PATH_LEVELS);
-    int* row_action = reinterpret_cast<int*>(act + GT * rs);
-    unsigned char* row_active = reinterpret_cast<unsigned char*>(row_action + GT);
     const int row = gt / LPT;
-    float* rowp = act + (row & 7) * rs + (row >> 3);
     const int barid = 1 + grp;
+    float* act = nullptr;
+    float* rowp = nullptr;
+    int* row_action;
+    unsigned char* row_active;
+    const TcSched& ts = *tsp_;
+    [[maybe_unused]] TcCtx tc;
+    [[maybe_unused]] float4 hq[2];
+    [[maybe_unused]] bool tc_ok = true;
+    if constexpr (TC) {
+        tc_setup<G, GTHREADS, 0>(tc, p, ts, wsm, tid, grp, row);  // (these searches record no path)
+        row_action = tc.row_action;
+        row_active = tc.row_active;
+    } else {
+        act = wsm + w_total + grp * (GT * rs + GT + GT + GT * PATH_LEVELS);
+        row_action = reinterpret_cast<int*>(act + GT * rs);
+        row_active = reinterpret_cast<unsigned char*>(row_action + GT);
+        rowp = act + (row & 7) * rs + (row >> 3);
+    }
 
     const int lane = tid & 31, j = tid % LPT;
     const int gl0 = lane & (32 - LPT);
@@ -1060,6 +1146,7 @@ __global__ void __launch_bounds__(G * GT * LPT, 512 / (G * GT * LPT)) search_fas
     }
     const float root_prior_f = (float)root_prior;
     __syncthreads();
+    if constexpr (TC) tc_fence_after();
 
     for (int it = 0; it < p.max_iters; ++it) {
         if (fed && n_rec >= p.max_rec) n_sims = p.S;
@@ -1168,7 +1255,44 @@ __global__ void __launch_bounds__(G * GT * LPT, 512 / (G * GT * LPT)) search_fas
         // ================= network evaluation =================
         float value = 0.0f, prior = 0.0f;    // state-leaf results
         float tprior = 0.0f, treward = 0.0f;  // transition-leaf results (lane z)
-        if (!fed) {
+        if constexpr (TC) {
+            if (j == 0) {
+                row_action[row] = action;
+                row_active[row] = active ? 1 : 0;
+            }
+            if (active) tc_gather_hidden<LPT>(ts, tc.arena, hpool + (size_t)hslot * H, H, row, j);
+            fence_async_smem();
+            const bool any_t = group_any<GTHREADS>(barid, kind == 2);  // (also orders the gather before the MMAs)
+            const bool any_s = group_any<GTHREADS>(barid, kind == 1);
+            const int lane_ = tid & 31;
+            const float* o = tc.outs + row * ts.out_pitch;
+            if (any_t) {
+                for (int z = 0; z < nf; ++z) {
+                    tc_ok = tc_mlp<LPT>(ts, tc.tmem_base, tc.d_group, tc.arena, tc.outs, tc.ctab, row_action, tc.mbar, tc.parity, tc.gw,
+                                        lane_, row, j, barid, hq, nullptr, 0, 4, z) && tc_ok;
+                    float dv, rwz, tp;
+                    decode_row<LPT, true>(o + ts.off_rl, o + ts.off_rl, o + ts.off_tp, p.support, nf, false, j, dv, rwz, tp);
+                    if (kind == 2) {
+                        if (j == z) treward = rwz;
+                        if (z == 0) tprior = tp;  // softmax of the prior logits, self_play_stochastic.py:553-554
+                        float4* dst = reinterpret_cast<float4*>(hpool + (size_t)(1 + n_tgroups * nf + z) * H);
+#pragma unroll
+                        for (int q = 0; q < 2; ++q)
+                            if (j + q * LPT < (H >> 2)) dst[j + q * LPT] = hq[q];
+                    }
+                }
+            }
+            if (any_s) {
+                tc_ok = tc_mlp<LPT>(ts, tc.tmem_base, tc.d_group, tc.arena, tc.outs, tc.ctab, row_action, tc.mbar, tc.parity, tc.gw,
+                                    lane_, row, j, barid, hq, nullptr, 4, 6, 0) && tc_ok;
+                float dr, v1, p1;
+                decode_row<LPT, true>(o + ts.off_vl, o + ts.off_vl, o + ts.off_pl, p.support, A, false, j, v1, dr, p1);
+                if (kind == 1) {
+                    value = v1;
+                    prior = p1;
+                }
+            }
+        } else if (!fed) {
             if (j == 0) {
                 row_action[row] = action;
                 row_active[row] = active ? 1 : 0;
@@ -1399,6 +1523,24 @@ __global__ void __launch_bounds__(G * GT * LPT, 512 / (G * GT * LPT)) search_fas
             if (p.child_reward) p.child_reward[(size_t)b * A + a] = (double)rb->reward[j];
         }
     }
+    if constexpr (TC) {
+        if (!tc_ok && p.tc_status) atomicExch(p.tc_status, 1);
+        tc_fence_before();
+        __syncthreads();
+        if (__shfl_sync(FULL, tid >> 5, 0) == 0)
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tc.tmem_base), "n"(TC_TMEM_COLS));
+    }
+}
+
+template <int G, int LPT, int VARIANT>
+__global__ void __launch_bounds__(G * GT * LPT, 512 / (G * GT * LPT)) search_fast_variant_kernel(const __grid_constant__ FastParams p) {
+    search_fast_variant_body<G, LPT, VARIANT, false>(p, nullptr);
+}
+
+template <int G, int LPT, int VARIANT>
+__global__ void __launch_bounds__(G * GT * LPT, 1) search_tc_variant_kernel(const __grid_constant__ FastParams p,
+                                                                            const __grid_constant__ TcSched ts) {
+    search_fast_variant_body<G, LPT, VARIANT, true>(p, &ts);
 }
 
 }  // namespace tsp

@@ -29,7 +29,7 @@ namespace tsp {
 constexpr int TC_LBO = 144;        // bytes between core matrices along K
 constexpr int TC_MAX_MMA = 8;
 constexpr int TC_MAX_STAGES = 6;
-constexpr int TC_MAX_PASS = 4;
+constexpr int TC_MAX_PASS = 6;
 constexpr int TC_MAX_CTAB = 1024;  // floats: biases and one-hot rows
 constexpr int TC_TMEM_COLS = 512;
 
@@ -51,9 +51,10 @@ struct TcEpi {        // one warp (TMEM lane quarter) of one epilogue pass
     int cidx;         // ctab offset of lane 0's bias
     int eidx;         // ctab offset of the one-hot rows (row a at eidx + a * e_ld), -1: none
     int e_ld;
+    int zidx;         // ctab offset of the one-hot FUTURE rows of MuZeroStochasticConcat (models.py:568-580; row z at zidx + z * e_ld), -1: none
     int flags;        // 1: ELU, 2: RAW (float32 logits to the out strip)
 };
-static_assert(sizeof(TcEpi) == 36, "TcEpi: four shorts and seven ints");
+static_assert(sizeof(TcEpi) == 40, "TcEpi: four shorts and eight ints");
 struct TcStage {
     int mma0, n_mma;  // MMAs issued at the start of the stage
     int commit;       // commit them (and everything issued before) to the group's mbarrier
@@ -66,12 +67,12 @@ struct TcSched {
     int d_col0, d_cols_group, arena_bytes, out_pitch;
     int off_vl, off_rl, off_pl, ctab_floats;
     int xh_off, xh_sbo, xs_off, xs_sbo;
-    int xn_off, xn_sbo, H, pad;
+    int xn_off, xn_sbo, H, off_tp;
     TcStage stage[TC_MAX_STAGES];
     TcMma mma[TC_MAX_MMA];
     TcEpi epi[TC_MAX_PASS][8];  // [pass][warp of the group]: warps w and w + 4 share TMEM lane quarter w % 4
 };
-static_assert(sizeof(TcSched) <= 3072, "TcSched travels as a kernel parameter (constant bank: uniform reads)");
+static_assert(sizeof(TcSched) <= 3200, "TcSched travels as a kernel parameter (constant bank: uniform reads)");
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ bool elect_one() {
@@ -143,13 +144,14 @@ __device__ __forceinline__ void tmem_ld<16>(uint32_t taddr, uint32_t (&v)[16]) {
 template <int NCNT>
 __device__ __forceinline__ bool tc_epi_warp(const TcEpi& ep, uint32_t d_tmem, unsigned char* __restrict__ arena, int b_lo,
                                             float* __restrict__ outs, int out_pitch, const float* __restrict__ ctab,
-                                            const int* __restrict__ row_action, int lane, uint32_t mbar, uint32_t parity) {
+                                            const int* __restrict__ row_action, int lane, uint32_t mbar, uint32_t parity, int z) {
     const int n0 = ep.n0;
     const bool on = lane < ep.rows;
     const int flags = ep.flags;
     float add[NCNT];
     {
-        const float bias = on ? ctab[ep.cidx + lane] : 0.0f;
+        float bias = on ? ctab[ep.cidx + lane] : 0.0f;
+        if (ep.zidx >= 0 && on) bias += ctab[ep.zidx + z * ep.e_ld + lane];  // the same future for every tree of the pass
 #pragma unroll
         for (int i = 0; i < NCNT; ++i) add[i] = bias;
         if (ep.eidx >= 0 && on) {  // one-hot action input == one gathered weight row per tree (models.py:236-243)
@@ -242,13 +244,14 @@ template <int LPT>
 __device__ __forceinline__ bool tc_mlp(const TcSched& ts, uint32_t tmem_base, uint32_t d_group, unsigned char* __restrict__ arena,
                                        float* __restrict__ outs, const float* __restrict__ ctab,
                                        const int* __restrict__ row_action, uint32_t mbar, uint32_t& parity, int gw, int lane,
-                                       int row, int j, int barid, float4 (&hq)[2], unsigned long long* dbg = nullptr) {
+                                       int row, int j, int barid, float4 (&hq)[2], unsigned long long* dbg = nullptr,
+                                       int s_begin = 0, int s_end = -1, int z = 0) {
     constexpr int GTHREADS = GT * LPT;
     const uint32_t arena_s = smem_u32(arena);
     const uint32_t lane_q = (uint32_t)(32 * (gw & 3)) << 16;
     bool ok = true;
-    const int n_stages = ts.n_stages;
-    for (int s = 0; s < n_stages; ++s) {
+    const int n_stages = s_end < 0 ? ts.n_stages : s_end;
+    for (int s = s_begin; s < n_stages; ++s) {
         const TcStage& st = ts.stage[s];
         const bool tm = dbg && threadIdx.x == 0;
         long long q0 = 0, q1 = 0, q2 = 0, q3 = 0, q4 = 0;
@@ -304,8 +307,10 @@ __device__ __forceinline__ bool tc_mlp(const TcSched& ts, uint32_t tmem_base, ui
                     v.x = __fmul_rn(__fsub_rn(v.x, mn), inv); v.y = __fmul_rn(__fsub_rn(v.y, mn), inv);
                     v.z = __fmul_rn(__fsub_rn(v.z, mn), inv); v.w = __fmul_rn(__fsub_rn(v.w, mn), inv);
                     hq[q] = v;
-                    *reinterpret_cast<float4*>(dst + i * TC_LBO) = v;
-                    *reinterpret_cast<float4*>(dst + i * TC_LBO + ts.b_lo) = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
+                    if (ts.xn_off >= 0) {  // (no layer of a transition expansion reads the normalised state)
+                        *reinterpret_cast<float4*>(dst + i * TC_LBO) = v;
+                        *reinterpret_cast<float4*>(dst + i * TC_LBO + ts.b_lo) = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
+                    }
                 }
             }
             fence_async_smem();
@@ -314,10 +319,10 @@ __device__ __forceinline__ bool tc_mlp(const TcSched& ts, uint32_t tmem_base, ui
             const TcEpi& ep = ts.epi[st.epi0][gw];
             const uint32_t d_tmem = d_group + lane_q;
             bool w;
-            if (ep.ncnt == 2) w = tc_epi_warp<2>(ep, d_tmem, arena, ts.b_lo, outs, ts.out_pitch, ctab, row_action, lane, mbar, parity);
-            else if (ep.ncnt == 4) w = tc_epi_warp<4>(ep, d_tmem, arena, ts.b_lo, outs, ts.out_pitch, ctab, row_action, lane, mbar, parity);
-            else if (ep.ncnt == 8) w = tc_epi_warp<8>(ep, d_tmem, arena, ts.b_lo, outs, ts.out_pitch, ctab, row_action, lane, mbar, parity);
-            else if (ep.ncnt == 16) w = tc_epi_warp<16>(ep, d_tmem, arena, ts.b_lo, outs, ts.out_pitch, ctab, row_action, lane, mbar, parity);
+            if (ep.ncnt == 2) w = tc_epi_warp<2>(ep, d_tmem, arena, ts.b_lo, outs, ts.out_pitch, ctab, row_action, lane, mbar, parity, z);
+            else if (ep.ncnt == 4) w = tc_epi_warp<4>(ep, d_tmem, arena, ts.b_lo, outs, ts.out_pitch, ctab, row_action, lane, mbar, parity, z);
+            else if (ep.ncnt == 8) w = tc_epi_warp<8>(ep, d_tmem, arena, ts.b_lo, outs, ts.out_pitch, ctab, row_action, lane, mbar, parity, z);
+            else if (ep.ncnt == 16) w = tc_epi_warp<16>(ep, d_tmem, arena, ts.b_lo, outs, ts.out_pitch, ctab, row_action, lane, mbar, parity, z);
             else w = mbar_wait(mbar, parity);
             ok = ok && w;
             parity ^= 1u;
