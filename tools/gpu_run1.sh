@@ -1,3 +1,2 @@
-timeout 1200 python -m pytest tests/test_tc.py -m gpu -x -q 2>&1 | tail -15 > gpurun_out/t6_pytest.log
-timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "stochastic or risk or golden or config3 or config4 or ragged or continued or mcts_run" 2>&1 | tail -15 >> gpurun_out/t6_pytest.log
-for g in roundabout_env_ttc_flat_stochastic_concat roundabout_env_ttc_flat_risk_sensitive; do for tc in 0 1; do TSP_NO_TC=$tc timeout 120 python tests/gpu_tune.py $g 16384 25; done; done > gpurun_out/t6_tune.log 2>&1
+for plan in "r:1:25:0" "r:37:25:1"; do echo "== $plan"; timeout 20 python tools/repro_hang.py "$plan"; echo "rc=$?"; done > gpurun_out/t12_repro.log 2>&1
+( time timeout 1000 python -m pytest tests/ -m gpu -x -q --durations=12 -o faulthandler_timeout=300 ) > gpurun_out/t12_pytest_full.log 2>&1

@@ -870,7 +870,6 @@ __device__ __forceinline__ void search_fast_body(const FastParams& p, const TcSc
 
     // ================= outputs: what consumers read from `root` =================
     if (valid) {
-        const Block* rb = blocks;
         if (j == 0) {
             if (p.root_value) p.root_value[b] = root_visit == 0 ? 0.0 : __ddiv_rn(root_vsum, (double)root_visit);
             if (p.max_depth) p.max_depth[b] = max_depth;
@@ -890,7 +889,12 @@ __device__ __forceinline__ void search_fast_body(const FastParams& p, const TcSc
             if (p.child_prior) p.child_prior[(size_t)b * A + j] = 0.0;
             if (p.child_reward) p.child_reward[(size_t)b * A + j] = 0.0;
         }
-        __syncwarp();
+    }
+    // (outside the branch: with an odd number of roots a warp holds one valid and one invalid tree, and the lanes of
+    // the invalid one do not exit here when the kernel still has to release its tensor memory)
+    __syncwarp();
+    if (valid) {
+        const Block* rb = blocks;
         if (j < n_root) {
             const int a = root_act;
             const int vis = rb->visit[j];
@@ -1493,7 +1497,6 @@ __device__ __forceinline__ void search_fast_variant_body(const FastParams& p, co
     }
 
     if (valid) {
-        const Block* rb = blocks;
         if (j == 0) {
             if (p.root_value)
                 p.root_value[b] = (VARIANT == 2) ? root_vsum : (root_visit == 0 ? 0.0 : __ddiv_rn(root_vsum, (double)root_visit));
@@ -1511,7 +1514,12 @@ __device__ __forceinline__ void search_fast_variant_body(const FastParams& p, co
             if (p.child_prior) p.child_prior[(size_t)b * A + j] = 0.0;
             if (p.child_reward) p.child_reward[(size_t)b * A + j] = 0.0;
         }
-        __syncwarp();
+    }
+    // (outside the branch: with an odd number of roots a warp holds one valid and one invalid tree, and the lanes of
+    // the invalid one do not exit here when the kernel still has to release its tensor memory)
+    __syncwarp();
+    if (valid) {
+        const Block* rb = blocks;
         if (j < n_root) {
             const int a = root_act;
             const int vis = rb->visit[j];
