@@ -1,2 +1,3 @@
-for plan in "r:1:25:0" "r:37:25:1"; do echo "== $plan"; timeout 20 python tools/repro_hang.py "$plan"; echo "rc=$?"; done > gpurun_out/t12_repro.log 2>&1
-( time timeout 1000 python -m pytest tests/ -m gpu -x -q --durations=12 -o faulthandler_timeout=300 ) > gpurun_out/t12_pytest_full.log 2>&1
+python bench.py --steps 300 --warmup 10 --no-cpu-baseline > gpurun_out/t13_bench_overlap.json 2> gpurun_out/t13_bench_overlap.err
+TSP_NO_OVERLAP=1 python bench.py --steps 300 --warmup 10 --no-cpu-baseline > gpurun_out/t13_bench_nooverlap.json 2>> gpurun_out/t13_bench_overlap.err
+( time timeout 600 python -m pytest tests/ -m gpu -x -q -o faulthandler_timeout=200 ) > gpurun_out/t13_pytest_full.log 2>&1

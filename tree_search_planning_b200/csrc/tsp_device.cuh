@@ -685,7 +685,8 @@ __device__ __forceinline__ double ucb_score(double pb_log, double sqrt_parent_vi
 
 // --------------------------------------------------------------------- params ----
 struct NetParams {
-    int B, A, H, nf, support;
+    int B, A, H, nf, support;  // B: one past the last row of this launch
+    int b0;                    // first row of this launch (tsp_run overlaps the root network with the upload of later rows)
     int mode;  // 0 initial_inference (+ optional tree init), 1 recurrent, 2 stochastic dynamics, 3 prediction
     const float* W;
     const float* in;      // observations [B][obs_dim] or hidden [B][H]
@@ -737,7 +738,7 @@ __global__ void __launch_bounds__(TM * GW) net_kernel(const __grid_constant__ Ne
     unsigned char* row_active = reinterpret_cast<unsigned char*>(row_action + TM);
     const int tid = threadIdx.x, j = tid & 7, row = tid >> 3;
     const unsigned gmask = 0xFFu << ((tid & 31) & 24);
-    const int b = blockIdx.x * TM + row;
+    const int b = p.b0 + blockIdx.x * TM + row;
     const bool valid = b < p.B;
     const bool fed = p.fed_root != nullptr;
 

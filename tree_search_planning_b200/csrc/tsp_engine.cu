@@ -67,6 +67,13 @@ struct tsp_engine {
     int device = 0;
     int sm_count = 0;
     cudaStream_t stream = nullptr;
+    // HOST-memory searches: the observations are uploaded in row chunks on a second stream and the root network of a
+    // chunk starts as soon as its rows have arrived (copy / compute overlap inside tsp_run)
+    cudaStream_t copy_stream = nullptr;
+    static constexpr int OBS_CHUNKS = 4;
+    cudaEvent_t ev_chunk[OBS_CHUNKS] = {};
+    cudaEvent_t ev_root_done = nullptr;
+    bool no_overlap = false;  // TSP_NO_OVERLAP
     // ring of event triples (before root kernel, between, after search kernel), drained lazily
     static constexpr int EV_RING = 1024;
     std::vector<cudaEvent_t> ev;
@@ -1007,7 +1014,7 @@ int launch_net(tsp_engine* e, const NetParams& p_in) {
     const size_t smem = net_smem(p.sched, TM);
     int rc = set_smem(e, net_kernel<NC, TM>, smem);
     if (rc) return rc;
-    const int grid = (p.B + TM - 1) / TM;
+    const int grid = (p.B - p.b0 + TM - 1) / TM;
     net_kernel<NC, TM><<<grid, TM * GW, smem, e->stream>>>(p);
     CK(e, cudaGetLastError());
     e->stats.kernel_launches++;
@@ -1402,6 +1409,7 @@ int tsp_create(const tsp_config* cfg, tsp_handle* out) {
     if (const char* t = getenv("TSP_NO_FAST")) e->no_fast = atoi(t) != 0;
     if (const char* t = getenv("TSP_NO_WLO")) e->no_wlo = atoi(t) != 0;
     if (const char* t = getenv("TSP_NO_TC")) e->no_tc = atoi(t) != 0;
+    if (const char* t = getenv("TSP_NO_OVERLAP")) e->no_overlap = atoi(t) != 0;
     if (const char* t = getenv("TSP_TC_NOFOLD")) e->tc_nofold = atoi(t) != 0;
     if (const char* t = getenv("TSP_NO_WGLOBAL")) e->no_wglobal = atoi(t) != 0;
     if (const char* t = getenv("TSP_FORCE_WGLOBAL")) e->force_wglobal = atoi(t) != 0;
@@ -1415,6 +1423,12 @@ int tsp_create(const tsp_config* cfg, tsp_handle* out) {
     if (cudaSetDevice(e->device) != cudaSuccess) return bail(fail(e, TSP_ECUDA, "cudaSetDevice failed"));
     if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess)
         return bail(fail(e, TSP_ECUDA, "cudaStreamCreate failed"));
+    if (cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking) != cudaSuccess)
+        return bail(fail(e, TSP_ECUDA, "cudaStreamCreate failed"));
+    for (auto& ce : e->ev_chunk)
+        if (cudaEventCreateWithFlags(&ce, cudaEventDisableTiming) != cudaSuccess) return bail(fail(e, TSP_ECUDA, "cudaEventCreate failed"));
+    if (cudaEventCreateWithFlags(&e->ev_root_done, cudaEventDisableTiming) != cudaSuccess)
+        return bail(fail(e, TSP_ECUDA, "cudaEventCreate failed"));
     e->ev.resize(3 * tsp_engine::EV_RING, nullptr);
     for (auto& ev : e->ev)
         if (cudaEventCreate(&ev) != cudaSuccess) return bail(fail(e, TSP_ECUDA, "cudaEventCreate failed"));
@@ -1473,6 +1487,10 @@ int tsp_destroy(tsp_handle e) {
     for (auto& b : e->n_o) release(b);
     for (auto& ev : e->ev)
         if (ev) cudaEventDestroy(ev);
+    for (auto& ce : e->ev_chunk)
+        if (ce) cudaEventDestroy(ce);
+    if (e->ev_root_done) cudaEventDestroy(e->ev_root_done);
+    if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
     return TSP_OK;
@@ -1612,7 +1630,14 @@ int tsp_run(tsp_handle e, const tsp_run_args* a) {
         memset(&np.sched, 0, sizeof(np.sched));
         np.sched.row_stride = 36;
     }
-    if ((rc = stage_in(e, mem, a->observations, nb * c.obs_dim, e->s_obs, &np.in))) return rc;
+    // large HOST batches: upload the observations in OBS_CHUNKS row chunks on the copy stream (below, next to the launches)
+    const bool overlap = mem == TSP_MEM_HOST && !resume && !fed && a->observations && B >= 1024 && !e->no_overlap && e->copy_stream;
+    if (overlap) {
+        if ((rc = ensure(e, e->s_obs, nb * c.obs_dim * sizeof(float)))) return rc;
+        np.in = reinterpret_cast<const float*>(e->s_obs.p);
+    } else if ((rc = stage_in(e, mem, a->observations, nb * c.obs_dim, e->s_obs, &np.in))) {
+        return rc;
+    }
     if ((rc = stage_in(e, mem, a->legal_actions, nb * A, e->s_legal, &np.legal))) return rc;
     if ((rc = stage_in(e, mem, a->num_legal, nb, e->s_nlegal, &np.num_legal))) return rc;
     if ((rc = stage_in(e, mem, a->noise, nb * A, e->s_noise, &np.noise))) return rc;
@@ -1682,7 +1707,30 @@ int tsp_run(tsp_handle e, const tsp_run_args* a) {
     if (e->ev_pending == tsp_engine::EV_RING && (rc = drain_events(e))) return rc;
     cudaEvent_t* ev = &e->ev[3 * ((e->ev_head + e->ev_pending) % tsp_engine::EV_RING)];
     CK(e, cudaEventRecord(ev[0], e->stream));
-    if (!resume && (rc = launch_net_any(e, np))) return rc;
+    if (overlap) {
+        // the staging buffer is free once the previous run's root kernels are done
+        CK(e, cudaStreamWaitEvent(e->copy_stream, e->ev_root_done, 0));
+        const int per = ((B + tsp_engine::OBS_CHUNKS - 1) / tsp_engine::OBS_CHUNKS + 31) & ~31;
+        int n_chunks = 0;
+        for (int r0 = 0; r0 < B; r0 += per, ++n_chunks) {
+            const size_t rows = (size_t)std::min(per, B - r0);
+            CK(e, cudaMemcpyAsync(reinterpret_cast<float*>(e->s_obs.p) + (size_t)r0 * c.obs_dim, a->observations + (size_t)r0 * c.obs_dim,
+                                  rows * c.obs_dim * sizeof(float), cudaMemcpyHostToDevice, e->copy_stream));
+            CK(e, cudaEventRecord(e->ev_chunk[n_chunks], e->copy_stream));
+        }
+        e->stats.bytes_h2d += (int64_t)(nb * c.obs_dim * sizeof(float));
+        n_chunks = 0;
+        for (int r0 = 0; r0 < B; r0 += per, ++n_chunks) {
+            CK(e, cudaStreamWaitEvent(e->stream, e->ev_chunk[n_chunks], 0));
+            NetParams part = np;
+            part.b0 = r0;
+            part.B = std::min(B, r0 + per);
+            if ((rc = launch_net_any(e, part))) return rc;
+        }
+    } else if (!resume && (rc = launch_net_any(e, np))) {
+        return rc;
+    }
+    if (e->ev_root_done) CK(e, cudaEventRecord(e->ev_root_done, e->stream));
     CK(e, cudaEventRecord(ev[1], e->stream));
     if ((rc = launch_search_any(e, sp))) return rc;
     CK(e, cudaEventRecord(ev[2], e->stream));
