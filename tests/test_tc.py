@@ -119,3 +119,17 @@ def test_chance_node_searches_agree_with_the_mma_sync_kernel(game, monkeypatch):
     assert st_tc["search_kernel"] == 2 and st_mm["search_kernel"] == 1
     same = (tc["visit_counts"] == mm["visit_counts"]).all(axis=1)
     assert same.mean() >= 0.97, same.mean()
+
+
+@pytest.mark.parametrize("game", ["roundabout_env_ttc_flat", "roundabout_env_ttc_flat_stochastic_concat",
+                                  "roundabout_env_ttc_flat_risk_sensitive"])
+@pytest.mark.parametrize("B", [1, 17, 33])
+def test_odd_number_of_roots(game, B):
+    """A warp holds two trees: with an odd batch one warp owns a valid and an invalid tree. The lanes of the invalid
+    tree must reach the CTA barrier in front of tcgen05.dealloc together with the others (regression: a __syncwarp
+    inside `if (valid)` deadlocked the kernel for every odd batch size)."""
+    cfg = tsp.get_config(game)
+    st, out = search_kernel_of(cfg, B, 25)
+    assert st["search_kernel"] == 2
+    assert (out["visit_counts"].sum(1) == 25).all()
+    check_against_oracle(cfg, B, 25, seed=40 + B, min_agree=0.9)
