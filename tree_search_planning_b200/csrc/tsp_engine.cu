@@ -1198,6 +1198,7 @@ int launch_fast_any(tsp_engine* e, const SearchParams& sp) {
         p.tc_img = reinterpret_cast<const float*>(e->tc_img[which].p);
         p.tc_ctab = reinterpret_cast<const float*>(e->tc_ctab[which].p);
         p.tc_status = reinterpret_cast<int*>(e->tc_status.p);
+        if (lpt == 16 && e->fast_groups == 1) return launch_tc<1, 16>(e, p, ts);  // (developer: one group alone on an SM)
         if (lpt == 16 && tc_smem(ts, 2, p.S_tab) <= 227 * 1024) return launch_tc<2, 16>(e, p, ts);
         if (lpt == 8 && tc_smem(ts, 4, p.S_tab) <= 227 * 1024) return launch_tc<4, 8>(e, p, ts);
         if (lpt == 8 && tc_smem(ts, 2, p.S_tab) <= 227 * 1024) return launch_tc<2, 8>(e, p, ts);

@@ -494,14 +494,21 @@ __device__ __forceinline__ void search_fast_body(const FastParams& p, const TcSc
         const int ctab_n = (ts.ctab_floats + 3) & ~3;
         unsigned long long* mbars = reinterpret_cast<unsigned long long*>(wsm + ctab_n);  // 8-byte aligned: ctab_n % 4 == 0
         uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbars + 4);
-        unsigned char* gbase = reinterpret_cast<unsigned char*>(
-            (reinterpret_cast<uintptr_t>(tmem_slot + 4) + 127) & ~(uintptr_t)127);
+        // (offsets from the shared-memory base, not integer-cast pointers: the compiler keeps the address space and emits
+        // STS / LDS with 32-bit addresses instead of generic ST.E / LD.E with 64-bit address arithmetic)
+        const int goff = ((int)(reinterpret_cast<unsigned char*>(tmem_slot + 4) - reinterpret_cast<unsigned char*>(smem)) + 127) & ~127;
+        unsigned char* gbase = reinterpret_cast<unsigned char*>(smem) + goff;
         const int gstride = ts.arena_bytes + (GT * ts.out_pitch + GT + GT / 4 + GT * PATH_LEVELS) * 4;
-        tc_arena = gbase + (size_t)grp * gstride;
+        tc_arena = gbase + grp * gstride;
         tc_outs = reinterpret_cast<float*>(tc_arena + ts.arena_bytes);
         row_action = reinterpret_cast<int*>(tc_outs + GT * ts.out_pitch);
         row_active = reinterpret_cast<unsigned char*>(row_action + GT);
         path = row_action + GT + GT / 4 + row * PATH_LEVELS;
+        __builtin_assume(__isShared(tc_arena));
+        __builtin_assume(__isShared(tc_outs));
+        __builtin_assume(__isShared(row_action));
+        __builtin_assume(__isShared(path));
+        __builtin_assume(__isShared(ctab));
         const int warp_u = __shfl_sync(FULL, tid >> 5, 0);  // provably warp-uniform: keeps the MMA issue on the uniform datapath
         const int grp_u = warp_u / (GTHREADS / 32);
         gw_u = warp_u % (GTHREADS / 32);
@@ -945,14 +952,20 @@ __device__ __forceinline__ void tc_setup(TcCtx& c, const FastParams& p, const Tc
     const int ctab_n = (ts.ctab_floats + 3) & ~3;
     unsigned long long* mbars = reinterpret_cast<unsigned long long*>(base + ctab_n);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbars + 4);
-    unsigned char* gbase = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 127) & ~(uintptr_t)127);
+    extern __shared__ __align__(16) float smem_base_[];
+    const int goff = ((int)(reinterpret_cast<unsigned char*>(tmem_slot + 4) - reinterpret_cast<unsigned char*>(smem_base_)) + 127) & ~127;
+    unsigned char* gbase = reinterpret_cast<unsigned char*>(smem_base_) + goff;
     const int gstride = ts.arena_bytes + (GT * ts.out_pitch + GT + GT / 4 + GT * PATH) * 4;
     c.ctab = base;
-    c.arena = gbase + (size_t)grp * gstride;
+    c.arena = gbase + grp * gstride;
     c.outs = reinterpret_cast<float*>(c.arena + ts.arena_bytes);
     c.row_action = reinterpret_cast<int*>(c.outs + GT * ts.out_pitch);
     c.row_active = reinterpret_cast<unsigned char*>(c.row_action + GT);
     c.path = c.row_action + GT + GT / 4 + row * PATH;
+    __builtin_assume(__isShared(c.arena));
+    __builtin_assume(__isShared(c.outs));
+    __builtin_assume(__isShared(c.row_action));
+    __builtin_assume(__isShared(c.ctab));
     const int warp_u = __shfl_sync(FULL, tid >> 5, 0);  // provably warp-uniform
     const int grp_u = warp_u / (GTHREADS / 32);
     c.gw = warp_u % (GTHREADS / 32);
