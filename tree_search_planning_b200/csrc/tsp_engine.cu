@@ -567,17 +567,21 @@ int build_tc(tsp_engine* e) {
             if (fold) {
                 place(D2, c2, 0, DH);
                 place_fold(c2, 32 * h_q);
-                for (int q = 0; q < 2; ++q) { place(P1, c3, 64 * q, H); place(V1, c3, 64 * q + 32, H); }
+                place(P1, c3, 0, H);
+                place(V1, c3, 32, H);
             } else {
                 const int r2 = H <= 32 ? 4 : 2;
                 for (int q = 0; q < r2; ++q) place(D2, c2, (128 / r2) * q, DH);
                 place(R1, c3, 0, H); place(P1, c3, 32, H); place(V1, c3, 64, H);
             }
+        } else if (fold) {  // lane quarter 3 stays free in every stage: its warp issues the MMAs
+            place(D1, c1, 0, H); place(P1, c1, 32, H); place(V1, c1, 64, H);
+            place(D2, c2, 0, DH);
+            place_fold(c2, 32 * h_q);
         } else {
             place(D1, c1, 0, H); place(P1, c1, 64, H); place(V1, c1, 96, H);
             place(D2, c2, 0, DH);
-            if (fold) place_fold(c2, 32 * h_q);
-            else place(R1, c1, 32, H);
+            place(R1, c1, 32, H);
         }
         place(R2, c4, 0, RH); place(V2, c4, 32, VH); place(P2, c4, 64, PH);
         for (int col = 0; col < hi_cols; ++col)
@@ -618,13 +622,15 @@ int build_tc(tsp_engine* e) {
             }
         };
         if (rep) {
-            for (int q = 0; q < 4; ++q) epi(0, q, DA, 4 * q, 4, DH, xd, sbo(DH), 0, t_b1, t_e1, 1);
             if (fold) {
+                // quarters 0 and 1 (two replicas of dynamics layer 1, 8 trees each, split over warps q and q + 4)
+                for (int q = 0; q < 2; ++q) epi(0, q, DA, 8 * q, 8, DH, xd, sbo(DH), 0, t_b1, t_e1, 1);
                 for (int q = 0; q < h_q; ++q) epi(1, q, DB, 0, 16, std::min(32, H - 32 * q), xs, sbo(H), 32 * q, t_b2 + 32 * q, -1, 0);
                 epi(1, h_q, DB, 0, 16, RH, xr, sbo(RH), 0, t_b3r, -1, 1);
-                for (int q = 0; q < 4; ++q)
-                    epi(2, q, DC, 8 * (q >> 1), 8, (q & 1) ? VH : PH, (q & 1) ? xv : xp, sbo((q & 1) ? VH : PH), 0, (q & 1) ? t_b3v : t_b3p, -1, 1);
+                epi(2, 0, DC, 0, 16, PH, xp, sbo(PH), 0, t_b3p, -1, 1);
+                epi(2, 1, DC, 0, 16, VH, xv, sbo(VH), 0, t_b3v, -1, 1);
             } else {
+                for (int q = 0; q < 4; ++q) epi(0, q, DA, 4 * q, 4, DH, xd, sbo(DH), 0, t_b1, t_e1, 1);
                 if (H <= 32) {
                     for (int q = 0; q < 4; ++q) epi(1, q, DB, 4 * q, 4, H, xs, sbo(H), 0, t_b2, -1, 0);
                 } else {
@@ -638,10 +644,15 @@ int build_tc(tsp_engine* e) {
         } else {
             epi(0, 0, DA, 0, 16, DH, xd, sbo(DH), 0, t_b1, t_e1, 1);
             for (int q = 0; q < h_q; ++q) epi(1, q, DB, 0, 16, std::min(32, H - 32 * q), xs, sbo(H), 32 * q, t_b2 + 32 * q, -1, 0);
-            if (fold) epi(1, h_q, DB, 0, 16, RH, xr, sbo(RH), 0, t_b3r, -1, 1);
-            else epi(2, 1, DA, 0, 16, RH, xr, sbo(RH), 0, t_b3r, -1, 1);
-            epi(2, 2, DC, 0, 16, PH, xp, sbo(PH), 0, t_b3p, -1, 1);
-            epi(2, 3, DC, 0, 16, VH, xv, sbo(VH), 0, t_b3v, -1, 1);
+            if (fold) {
+                epi(1, h_q, DB, 0, 16, RH, xr, sbo(RH), 0, t_b3r, -1, 1);
+                epi(2, 1, DC, 0, 16, PH, xp, sbo(PH), 0, t_b3p, -1, 1);
+                epi(2, 2, DC, 0, 16, VH, xv, sbo(VH), 0, t_b3v, -1, 1);
+            } else {
+                epi(2, 1, DA, 0, 16, RH, xr, sbo(RH), 0, t_b3r, -1, 1);
+                epi(2, 2, DC, 0, 16, PH, xp, sbo(PH), 0, t_b3p, -1, 1);
+                epi(2, 3, DC, 0, 16, VH, xv, sbo(VH), 0, t_b3v, -1, 1);
+            }
         }
         epi(3, 0, DA, 0, 16, NR, ts.off_rl, 0, 0, t_b4r, -1, 2);
         epi(3, 1, DB, 0, 16, NV, ts.off_vl, 0, 0, t_b4v, -1, 2);
@@ -652,6 +663,9 @@ int build_tc(tsp_engine* e) {
             ts.stage[s].epi0 = epi0; ts.stage[s].n_epi = n_epi;
         };
         ts.n_stages = 5;
+        // with the fold, lane quarter 3 has no epilogue share in any stage: the last warp of the group (quarter 3) issues
+        const int issuer = fold ? (rep ? 7 : 3) : 0;
+        for (int s2 = 0; s2 < TC_MAX_STAGES; ++s2) ts.stage[s2].issuer = issuer;
         stage(0, m_d1, 1, 1, 0, 0, 1);   // dynamics layer 1
         stage(1, m_d2, 1, 1, 0, 1, 1);   // dynamics layer 2 -> un-normalised next state (+ folded reward layer 1)
         if (fold) stage(2, 0, 0, 0, 1, 0, 0);     // the state is normalised
@@ -817,6 +831,10 @@ int build_tc_variant(tsp_engine* e) {
         stage(3, 2, 2, 1, 0, 2, 1);
         stage(4, 4, 1, 1, 0, 3, 1);
         stage(5, 5, 2, 1, 0, 4, 1);
+        // the MMAs of a stage are issued by a warp without a share of its epilogue: quarter 3 is idle in the stages of a
+        // future, quarter 0 in those of the prediction
+        for (int s2 = 0; s2 < 4; ++s2) ts.stage[s2].issuer = parts == 2 ? 7 : 3;
+        for (int s2 = 4; s2 < 6; ++s2) ts.stage[s2].issuer = parts == 2 ? 4 : 0;
         int rc;
         if ((rc = ensure(e, e->tc_img[shape], img.size() * sizeof(float)))) return rc;
         if ((rc = ensure(e, e->tc_ctab[shape], ctab.size() * sizeof(float)))) return rc;

@@ -14,8 +14,8 @@
 //   * fp32-level accuracy by the 3xTF32 split (hi*hi + lo*hi + hi*lo into one fp32 TMEM accumulator): the tensor
 //     core ignores the 13 low mantissa bits of a kind::tf32 operand, so the raw float32 word is the hi operand;
 //     lo = x - trunc(x) is stored next to it (weights: second half of the TMEM image; activations: twin buffer).
-//   * One elected thread of the group's first warp issues the MMAs of a stage and commits them to the group's
-//     mbarrier; all warps of the group run the epilogue (warp w reads TMEM lane quarter w % 4; with 8 warps per group
+//   * One elected thread of a warp that has no epilogue share in the stage issues the stage's MMAs and commits them
+//     to the group's mbarrier; all warps of the group run the epilogue (warp w reads TMEM lane quarter w % 4; with 8 warps per group
 //     two warps split the trees of a quarter): tcgen05.ld 32x32b
 //     (thread = feature, registers = trees), bias (+ the gathered one-hot action row of models.py:236-243), ELU,
 //     and the restaging of hi / lo as the next layer's B operand.
@@ -60,7 +60,9 @@ struct TcStage {
     int commit;       // commit them (and everything issued before) to the group's mbarrier
     int row_op;       // 1: min-max normalise xs -> xn (models.py:248-255) while the MMAs run
     int epi0, n_epi;  // epilogue pass (n_epi <= 1) after the mbarrier wait
-    int pad[2];
+    int issuer;       // warp of the group that issues the MMAs: one WITHOUT a share of this stage's epilogue, so that the
+                      // epilogue warps fetch their operands while the MMAs are issued instead of after
+    int pad;
 };
 struct TcSched {
     int n_stages, n_cols, a_lo, b_lo;
@@ -256,7 +258,7 @@ __device__ __forceinline__ bool tc_mlp(const TcSched& ts, uint32_t tmem_base, ui
         const bool tm = dbg && threadIdx.x == 0;
         long long q0 = 0, q1 = 0, q2 = 0, q3 = 0, q4 = 0;
         if (tm) q0 = clock64();
-        if (gw == 0) {
+        if (gw == st.issuer) {
             tc_fence_after();
             if (elect_one()) {
                 for (int m = st.mma0; m < st.mma0 + st.n_mma; ++m) {
