@@ -1,5 +1,4 @@
-TSP_PHASE_TIMING=1 timeout 120 python tests/gpu_tune.py roundabout_env_ttc_flat 4096 50 > gpurun_out/t18_tune.log 2>&1
-timeout 120 python tests/gpu_tune.py roundabout_env_ttc_flat 4096 50 >> gpurun_out/t18_tune.log 2>&1
-timeout 120 python tests/gpu_tune.py highway_env_ttc_flat 65536 50 >> gpurun_out/t18_tune.log 2>&1
-timeout 120 python tests/gpu_tune.py roundabout_env_ttc_flat_stochastic_concat 16384 25 >> gpurun_out/t18_tune.log 2>&1
-( time timeout 600 python -m pytest tests/ -m gpu -x -q -o faulthandler_timeout=200 ) > gpurun_out/t18_pytest_full.log 2>&1
+# developer scratch: what the last gpurun call of the session ran (search-kernel time per config + the GPU test suite)
+timeout 120 python tests/gpu_tune.py roundabout_env_ttc_flat 4096 50
+timeout 120 python tests/gpu_tune.py highway_env_ttc_flat 65536 50
+timeout 600 python -m pytest tests/ -m gpu -x -q -o faulthandler_timeout=200
