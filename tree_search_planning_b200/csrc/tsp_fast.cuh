@@ -99,6 +99,11 @@ __device__ __forceinline__ float rcp_approx(float x) {  // MUFU.RCP, <= 1 ulp
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
+// float -> int with the same ordering (finite values and infinities)
+__device__ __forceinline__ int ordered_key(float f) {
+    const int i = __float_as_int(f);
+    return i ^ ((i >> 31) & 0x7fffffff);
+}
 template <int GTHREADS>
 __device__ __forceinline__ void group_barrier(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(GTHREADS) : "memory"); }
 
@@ -639,11 +644,28 @@ __device__ __forceinline__ void search_fast_body(const FastParams& p, const TcSc
                 const float E = fmaf(1.9073486e-6f, fabsf(ps) + fabsf(V) + aux, 1e-30f);  // 16 * 2^-23 * magnitudes
                 const float lo = on ? sc - E : -CUDART_INF_F;
                 const float hi = on ? sc + E : -CUDART_INF_F;
-                float m1 = lo;
+                unsigned cand;
+                if constexpr (LPT == 16) {
+                    // two trees per warp: the maximum of the lower bounds by one REDUX.MAX per tree on order-preserving integer
+                    // keys instead of three shuffle rounds and a broadcast (-0.0 sorts below +0.0: only ever more conservative);
+                    // a non-finite bound sends the level to the float64 path like the float comparison did
+                    const int klo = ordered_key(lo), khi = ordered_key(hi);
+                    const bool upper = (lane & 16) != 0;
+                    const int ma = __reduce_max_sync(FULL, upper ? INT_MIN : klo);
+                    const int mb = __reduce_max_sync(FULL, upper ? klo : INT_MIN);
+                    const int m1k = upper ? mb : ma;
+                    const bool finite = fabsf(sc) <= 3.0e38f;
+                    const unsigned bal = __ballot_sync(FULL, on && khi >= m1k);
+                    const unsigned bad = __ballot_sync(FULL, on && !finite);
+                    cand = (bal >> gl0) & 0xFFu;
+                    if ((bad >> gl0) & 0xFFu) cand = 0;
+                } else {
+                    float m1 = lo;
 #pragma unroll
-                for (int d = 1; d < GW; d <<= 1) m1 = fmaxf(m1, __shfl_xor_sync(FULL, m1, d));
-                m1 = __shfl_sync(FULL, m1, gl0);
-                const unsigned cand = (__ballot_sync(FULL, on && hi >= m1) >> gl0) & 0xFFu;
+                    for (int d = 1; d < GW; d <<= 1) m1 = fmaxf(m1, __shfl_xor_sync(FULL, m1, d));
+                    m1 = __shfl_sync(FULL, m1, gl0);
+                    cand = (__ballot_sync(FULL, on && hi >= m1) >> gl0) & 0xFFu;
+                }
                 int sl = __ffs(cand) - 1;
                 const bool need = walking && __popc(cand) != 1;
                 if (__any_sync(FULL, need)) {  // near-tie, exact tie or non-finite filter value: decide in float64
