@@ -19,7 +19,13 @@ GPU (configs[1]); weak scaling: every rank searches its own 4,096 roots.
           ((108*D + 8*H + 112) B per simulation, SURVEY 8d, D = measured mean selection depth)
           / its mean launch duration (CUDA events recorded by the engine around every launch).
   cpu_baseline  the CPU oracle (C restatement of the reference algorithm, oracle/) timed on the
-          host cores of this box on a bounded sample of the same workload (rank 0, N = 1 only).
+          host cores of this box on a bounded sample of the same workload (rank 0, N = 1 only);
+          cpu_baseline.python_reference = the unmodified Python reference measured in the build container
+          (profiles/python_reference_rate.json; /root/reference does not exist on the GPU box).
+  configs   the other BASELINE.json configurations, same measurement, one row each (N = 1), and the
+          STRONG-scaling rows (every N): the north-star headline (highway net, 65,536 roots) and config 5
+          (cross-merge 65,536 roots x 200 sims) with the roots split B/N per rank (sharding.shard_bounds)
+          and the one all-gather of the root statistics inside the timed region.
 """
 import argparse
 import json
@@ -52,12 +58,35 @@ def parse_args():
     ap.add_argument("--sims", type=int, default=50)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU-baseline sample duration")
-    ap.add_argument("--sweep", action="store_true", help="also time the other BASELINE configs (stderr + gpurun_out/)")
+    ap.add_argument("--no-configs", action="store_true", help="only the headline workload (skip the other BASELINE configs)")
+    ap.add_argument("--only", default="", help="developer: comma-separated tags of the extra rows to run")
     return ap.parse_args()
 
 
 def workload_name(game, roots, sims):
     return "%s MuZero MCTS batched %s roots x %d sims per GPU" % (game, format(roots, ","), sims)
+
+
+def config_dict(game, roots, sims):
+    """The `config` object: identical in both arms (the driver compares them)."""
+    return {"workload": workload_name(game, roots, sims), "game": game, "roots_per_gpu": roots, "num_simulations": sims,
+            "network": "fullyconnected, random-init same shapes (repo checkpoints are Git-LFS stubs)",
+            "arithmetic": "float32 network, float64 tree statistics"}
+
+
+# The other BASELINE.json configurations (one GPU each; tag, game, roots, sims, timed steps).
+EXTRA_CONFIGS = [
+    ("config3_stochastic", "roundabout_env_ttc_flat_stochastic_concat", 16384, 25, 10),
+    ("config4_risk_sensitive", "roundabout_env_ttc_flat_risk_sensitive", 16384, 25, 10),
+    ("highway_65536x50", "highway_env_ttc_flat", 65536, 50, 5),
+    ("highway_8192x200", "highway_env_ttc_flat", 8192, 200, 5),
+    ("cross_merge_8192x200", "cross_merge_env", 8192, 200, 3),
+]
+# Strong scaling: the TOTAL number of roots is fixed and split over the ranks.
+STRONG_CONFIGS = [
+    ("headline_highway_65536x200", "highway_env_ttc_flat", 65536, 200, 3),
+    ("config5_cross_merge_65536x200", "cross_merge_env", 65536, 200, 2),
+]
 
 
 # ------------------------------------------------------------------ clocks ----
@@ -167,8 +196,8 @@ def run_reference_arm(args, rank):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32/f64", "data": "synthetic",
-        "config": {"workload": workload_name(args.game, args.roots, args.sims), "roots_per_step": roots,
-                   "num_simulations": args.sims, "weights": "random-init, same shapes (repo checkpoints are LFS stubs)"},
+        "config": config_dict(args.game, args.roots, args.sims),
+        "run": {"roots_per_step": roots},
         "cpu_baseline": cb,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -197,12 +226,16 @@ def profiled_traffic(tag):
         return None
 
 
-def time_config(torch, dist, eng, cfg, B, S, steps, warmup, device, world, rank, host_mode, flush, seed):
-    """Time `steps` searches; returns (seconds summed over steps [max over ranks], extras)."""
+def time_config(torch, dist, se, cfg, S, steps, warmup, device, world, rank, host_mode, flush, seed):
+    """Time `steps` searches of this rank's block of roots on the sharded engine `se`; returns
+    (seconds summed over the steps [max over ranks], extras). The one all-gather of the root statistics
+    (sharding.PackedGather) is inside the timed region when world > 1."""
     from tree_search_planning_b200.engine import MEM_DEVICE, MEM_HOST
     from tree_search_planning_b200.synthetic import synthetic_inputs
     from tree_search_planning_b200.configs import variant_of
 
+    eng = se.engine
+    B = se.n_local
     A = len(cfg.action_space)
     obs, kw = synthetic_inputs(cfg, B, S, seed=seed + rank)
     stochastic = variant_of(cfg) != 0
@@ -210,31 +243,39 @@ def time_config(torch, dist, eng, cfg, B, S, steps, warmup, device, world, rank,
                 tie_stream=torch.from_numpy(kw["tie"]))
     if stochastic:
         host["chance_stream"] = torch.from_numpy(kw["chance"])
-    out_shapes = dict(visit_counts=((B, A), torch.int32), root_value=((B,), torch.float64),
-                      max_tree_depth=((B,), torch.int32), root_predicted_value=((B,), torch.float32),
-                      total_select_depth=((B,), torch.int32))
+    extra_shapes = dict(max_tree_depth=((B,), torch.int32), root_predicted_value=((B,), torch.float32),
+                        total_select_depth=((B,), torch.int32))
+    packed = dict(visit_counts=((B, A), torch.int32), root_value=((B,), torch.float64))
+    gather = world > 1
+    host_all = None
     if host_mode:
         ins = {k: v.pin_memory() for k, v in host.items()}
-        outs = {k: torch.zeros(s, dtype=dt).pin_memory() for k, (s, dt) in out_shapes.items()}
+        if gather:
+            # N > 1: HOST inputs, the root statistics stay on the device for the all-gather, and the gathered
+            # buffer of all ranks is read back to pinned host memory (outputs_on_device, include/tsp.h)
+            outs = {k: torch.zeros(s, dtype=dt, device=device) for k, (s, dt) in extra_shapes.items()}
+            host_all = torch.zeros(se.pack.all_bytes.shape, dtype=torch.uint8).pin_memory()
+        else:
+            outs = {k: torch.zeros(s, dtype=dt).pin_memory() for k, (s, dt) in {**extra_shapes, **packed}.items()}
         mem = MEM_HOST
     else:
         ins = {k: v.to(device) for k, v in host.items()}
-        outs = {k: torch.zeros(s, dtype=dt, device=device) for k, (s, dt) in out_shapes.items()}
+        outs = {k: torch.zeros(s, dtype=dt, device=device) for k, (s, dt) in extra_shapes.items()}
         mem = MEM_DEVICE
-    a = eng.make_args(B, S, mem, ins, outs, add_exploration_noise=True, tie_len=kw["tie"].shape[1],
-                      chance_len=kw["chance"].shape[1] if stochastic else 0)
-    gathered = None
-    if world > 1 and not host_mode:
-        gathered = {k: torch.empty((world * B,) + tuple(outs[k].shape[1:]), dtype=outs[k].dtype, device=device)
-                    for k in ("visit_counts", "root_value")}
+    kwargs = dict(add_exploration_noise=True, tie_len=kw["tie"].shape[1], chance_len=kw["chance"].shape[1] if stochastic else 0)
+    if host_mode and not gather:
+        a = eng.make_args(B, S, mem, ins, outs, **kwargs)
+    else:
+        a = se.make_args(S, mem, ins, extra_outputs=outs, outputs_on_device=host_mode, **kwargs)
     stream = torch.cuda.ExternalStream(eng.stream(), device=device)
     torch.cuda.synchronize(device)
 
     def step():
         eng.run_raw(a)
-        if gathered is not None:  # gather of the root visit distributions over NCCL / NVLink
-            for k, g in gathered.items():
-                dist.all_gather_into_tensor(g, outs[k])
+        if gather:  # ONE collective: visit counts | root values of every rank over NCCL / NVLink
+            se.pack.gather()
+            if host_all is not None:
+                host_all.copy_(se.pack.all_bytes, non_blocking=True)
 
     with torch.cuda.stream(stream):
         for _ in range(warmup):
@@ -259,23 +300,100 @@ def time_config(torch, dist, eng, cfg, B, S, steps, warmup, device, world, rank,
     if world > 1:
         dist.barrier()
     ms = sum(e0.elapsed_time(e1) for e0, e1 in zip(ev0, ev1))
-    t = torch.tensor([ms], dtype=torch.float64, device=device)
+    t = torch.tensor([ms, wall * 1e3], dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     st = eng.stats()
-    outs_np = {k: v.cpu().numpy() for k, v in outs.items()}
-    assert (outs_np["visit_counts"].sum(1) == S).all(), "search did not complete"
+    if host_mode and not gather:
+        visits = outs["visit_counts"].numpy()
+    else:
+        visits = se.pack.local["visit_counts"][:B].cpu().numpy()
+    assert (visits.sum(1) == S).all(), "search did not complete"
+    if gather:  # every rank holds every root's statistics
+        allv = se.pack.unpack()["visit_counts"]
+        assert int(allv.shape[0]) == se.num_roots and bool((allv.sum(1) == S).all()), "gathered statistics incomplete"
+        if host_all is not None:
+            assert bool((host_all == se.pack.all_bytes.cpu()).all())
+    h2d = sum(v.numel() * v.element_size() for v in ins.values()) if host_mode else 0
+    if not host_mode:
+        d2h = 0
+    elif gather:
+        d2h = host_all.numel()
+    else:
+        d2h = sum(v.numel() * v.element_size() for v in outs.values())
     extras = dict(
         launches=int(st["kernel_launches"] - launches0),
         search_ms=st["sum_search_ms"] / max(1, st["timed_runs"]),
         root_ms=st["sum_root_ms"] / max(1, st["timed_runs"]),
-        mean_depth=float(outs_np["total_select_depth"].sum()) / (B * S),
-        wall_s=wall,
-        h2d=sum(v.numel() * v.element_size() for v in ins.values()) if host_mode else 0,
-        d2h=sum(v.numel() * v.element_size() for v in outs.values()) if host_mode else 0,
-        stats=st,
+        mean_depth=float(outs["total_select_depth"].sum().item()) / (B * S),
+        wall_ms=float(t[1].item()), h2d=h2d, d2h=d2h, stats=st,
     )
-    return float(t.item()) / 1e3, extras
+    return float(t[0].item()) / 1e3, extras
+
+
+KERNEL_NAMES = {3: "tsp::search_tcs_kernel", 2: "tsp::search_tc_kernel", 1: "tsp::search_fast_kernel", 0: "tsp::search_kernel"}
+
+
+def kernel_name(st, variant):
+    k = st.get("search_kernel")
+    if k == 2 and variant != 0:
+        return "tsp::search_tc_variant_kernel"
+    if k == 1 and variant != 0:
+        return "tsp::search_fast_variant_kernel"
+    return KERNEL_NAMES.get(k, "tsp::search_kernel")
+
+
+def roofline_of(cfg, B, S, ex, peak, peak_src, tag=None):
+    """HBM roofline of the search kernel: algorithmic bytes per simulation (108 D + 8 H + 112, D = the
+    measured mean selection depth) x the B x S simulations of one launch / its mean duration (CUDA events recorded by the
+    engine around every launch)."""
+    from tree_search_planning_b200.configs import variant_of
+    D = ex["mean_depth"]
+    bps = 108.0 * D + 8.0 * cfg.encoding_size + 112.0
+    achieved = bps * B * S / (ex["search_ms"] * 1e-3) / 1e9
+    return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": profiled_traffic(tag) if tag else None, "kernel": kernel_name(ex["stats"], variant_of(cfg)),
+            "kernel_ms": ex["search_ms"], "algorithmic_bytes_per_sim": bps, "mean_select_depth": D, "peak_source": peak_src,
+            "kernel_share_of_step": ex["search_ms"] / (ex["search_ms"] + ex["root_ms"])}
+
+
+def root_roofline(cfg, B, ex, peak):
+    """The root kernel (representation + prediction + tree init): 4 obs_dim + 4 H + 128 algorithmic bytes per root."""
+    from tree_search_planning_b200.configs import observation_dim
+    bpr = 4.0 * observation_dim(cfg) + 4.0 * cfg.encoding_size + 128.0
+    achieved = bpr * B / max(ex["root_ms"] * 1e-3, 1e-9) / 1e9
+    return {"bound": "hbm", "kernel": "tsp::net_kernel (root)", "kernel_ms": ex["root_ms"], "achieved": achieved, "peak": peak,
+            "unit": "GB/s", "frac": achieved / peak, "algorithmic_bytes_per_root": bpr}
+
+
+def measure_row(torch, dist, tsp, tag, game, B_total, S, steps, warmup, device, local_rank, world, rank, flush, peak, peak_src,
+                scaling, e2e=True):
+    """One extra row: the same measurement as the headline for another BASELINE configuration."""
+    from tree_search_planning_b200.synthetic import random_state_dict
+    from tree_search_planning_b200.sharding import ShardedEngine
+    cfg = tsp.get_config(game, num_simulations=S)
+    row = {"tag": tag, "game": game, "roots_total": B_total, "num_simulations": S, "scaling": scaling, "steps": steps}
+    se = None
+    try:
+        se = ShardedEngine(cfg, num_roots=B_total, max_simulations=S, device=device,
+                           state_dict=random_state_dict(cfg, 0) if rank == 0 else None)
+        t, ex = time_config(torch, dist, se, cfg, S, steps, warmup, device, world, rank, False, flush, 2000)
+        row.update(value=B_total * S * steps / t, unit=UNIT, ms_per_step=1e3 * t / steps, roots_per_gpu=se.n_local,
+                   kernel=kernel_name(ex["stats"], tsp.variant_of(cfg)), kernel_ms=ex["search_ms"], root_ms=ex["root_ms"],
+                   trees_per_cta=ex["stats"]["trees_per_cta"], search_ctas=ex["stats"]["search_ctas"],
+                   roofline=roofline_of(cfg, se.n_local, S, ex, peak, peak_src), root_roofline=root_roofline(cfg, se.n_local, ex, peak))
+        if e2e:
+            t2, ex2 = time_config(torch, dist, se, cfg, S, steps, warmup, device, world, rank, True, flush, 2000)
+            row["e2e"] = {"value": B_total * S * steps / t2, "unit": UNIT, "ms_per_step": 1e3 * t2 / steps,
+                          "wall_ms_per_step": ex2["wall_ms"] / steps, "h2d_bytes_per_step": ex2["h2d"],
+                          "d2h_bytes_per_step": ex2["d2h"]}
+    except Exception as e:  # pragma: no cover
+        row["error"] = "%s: %s" % (type(e).__name__, e)
+    finally:
+        if se is not None:
+            se.close()
+    log("row", json.dumps(row))
+    return row
 
 
 _JSON_FD = None
@@ -315,7 +433,6 @@ def main():
     import torch.distributed as dist
     import tree_search_planning_b200 as tsp
     from tree_search_planning_b200.synthetic import random_state_dict
-    from tree_search_planning_b200.sharding import broadcast_state_dict
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
@@ -324,85 +441,78 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=device)
+    from tree_search_planning_b200.sharding import ShardedEngine
     B, S = args.roots, args.sims
     cfg = tsp.get_config(args.game, num_simulations=S)
     sd = random_state_dict(cfg, 0) if rank == 0 else None
-    sd = broadcast_state_dict(sd, device)  # NCCL broadcast of the flattened weights from rank 0
-    eng = tsp.Engine(cfg, max_roots=B, max_simulations=S, device=local_rank, state_dict=sd)
+    # weak scaling: every rank searches its own B roots; weights broadcast from rank 0 over NCCL
+    se = ShardedEngine(cfg, num_roots=world * B, max_simulations=S, device=device, state_dict=sd)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
 
     sampler = ClockSampler(local_rank)
     sampler.start()
-    t_dev, ex_dev = time_config(torch, dist, eng, cfg, B, S, args.steps, args.warmup, device, world, rank, False, flush, 1000)
-    t_e2e, ex_e2e = time_config(torch, dist, eng, cfg, B, S, args.steps, args.warmup, device, world, rank, True, flush, 1000)
+    t_dev, ex_dev = time_config(torch, dist, se, cfg, S, args.steps, args.warmup, device, world, rank, False, flush, 1000)
+    t_e2e, ex_e2e = time_config(torch, dist, se, cfg, S, args.steps, args.warmup, device, world, rank, True, flush, 1000)
     clocks = sampler.stop()
+    se.close()
 
     units = float(world) * B * S * args.steps
     value = units / t_dev
     e2e = units / t_e2e
-    H = cfg.encoding_size
-    D = ex_dev["mean_depth"]
-    bytes_per_sim = 108.0 * D + 8.0 * H + 112.0
     peak, peak_src = measured_peaks()
-    achieved = bytes_per_sim * B * S / (ex_dev["search_ms"] * 1e-3) / 1e9
-    tag = "%s_B%d_S%d" % (args.game, B, S)
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": profiled_traffic(tag),
-                "kernel": {2: "tsp::search_tc_kernel", 1: "tsp::search_fast_kernel"}.get(ex_dev["stats"].get("search_kernel"),
-                                                                                         "tsp::search_kernel"),
-                "kernel_ms": ex_dev["search_ms"], "algorithmic_bytes_per_sim": bytes_per_sim, "mean_select_depth": D,
-                "peak_source": peak_src,
-                "kernel_share_of_step": ex_dev["search_ms"] / (ex_dev["search_ms"] + ex_dev["root_ms"])}
+    roofline = roofline_of(cfg, B, S, ex_dev, peak, peak_src, tag="%s_B%d_S%d" % (args.game, B, S))
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32/f64", "data": "synthetic",
-        "config": {"workload": workload_name(args.game, B, S), "roots_per_gpu": B, "num_simulations": S,
-                   "network": "fullyconnected, random-init same shapes (repo checkpoints are Git-LFS stubs)",
-                   "arithmetic": "float32 network, float64 tree statistics",
-                   "l2": "flushed between timed steps (256 MiB write, untimed)",
-                   "trees_per_cta": ex_dev["stats"]["trees_per_cta"], "search_ctas": ex_dev["stats"]["search_ctas"],
-                   "parallelism": "roots sharded, %d rank(s), no collective inside the search" % world},
+        "config": config_dict(args.game, B, S),
+        "run": {"l2": "flushed between timed steps (256 MiB write, untimed)",
+                "trees_per_cta": ex_dev["stats"]["trees_per_cta"], "search_ctas": ex_dev["stats"]["search_ctas"],
+                "parallelism": "roots sharded, %d rank(s), no collective inside the search; one all-gather of the packed "
+                               "root statistics per search" % world,
+                "wall_ms_per_step": ex_dev["wall_ms"] / args.steps},
         "clocks": clocks,
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": ex_e2e["h2d"], "d2h_bytes_per_step": ex_e2e["d2h"],
-                "ms_per_step": 1e3 * t_e2e / args.steps},
+                "ms_per_step": 1e3 * t_e2e / args.steps, "wall_ms_per_step": ex_e2e["wall_ms"] / args.steps,
+                "note": "sum of per-step CUDA-event intervals on the engine's stream; wall_ms_per_step is the host clock over the "
+                        "same steps (includes the untimed L2 flushes); the upload of step i + 1 overlaps the search of step i"},
         "gpu_launches": ex_dev["launches"],
         "roofline": roofline,
+        "kernels": [roofline, root_roofline(cfg, B, ex_dev, peak)],
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(cfg, sd, S, args.cpu_seconds)
-    if args.sweep and world == 1:
-        sweep(torch, dist, tsp, device, local_rank, flush, line)
+        pr = python_reference_rate()
+        if pr:
+            line["cpu_baseline"]["python_reference"] = pr
+    if not args.no_configs:
+        only = set(t for t in args.only.split(",") if t)
+        rows = []
+        common = (device, local_rank, world, rank, flush, peak, peak_src)
+        if world == 1:
+            for tag, game, Bx, Sx, steps in EXTRA_CONFIGS:
+                if only and tag not in only:
+                    continue
+                rows.append(measure_row(torch, dist, tsp, tag, game, Bx, Sx, steps, 2, *common, scaling="single-gpu"))
+        for tag, game, Bx, Sx, steps in STRONG_CONFIGS:
+            if only and tag not in only:
+                continue
+            rows.append(measure_row(torch, dist, tsp, tag, game, Bx, Sx, steps, 2, *common, scaling="strong"))
+        line["configs"] = rows
     if rank == 0:
         emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
-def sweep(torch, dist, tsp, device, local_rank, flush, line):
-    """Other BASELINE.json configs (not bench lines): absolute numbers for DESIGN.md / profiles."""
-    from tree_search_planning_b200.synthetic import random_state_dict
-    rows = []
-    for game, B, S, steps in [("highway_env_ttc_flat", 8192, 50, 50), ("highway_env_ttc_flat", 65536, 50, 10),
-                              ("highway_env_ttc_flat", 8192, 200, 10),
-                              ("roundabout_env_ttc_flat_stochastic_concat", 16384, 25, 20),
-                              ("roundabout_env_ttc_flat_risk_sensitive", 16384, 25, 20),
-                              ("cross_merge_env", 8192, 200, 5), ("cross_merge_env", 65536, 200, 2)]:
-        cfg = tsp.get_config(game, num_simulations=S)
-        try:
-            eng = tsp.Engine(cfg, max_roots=B, max_simulations=S, device=local_rank, state_dict=random_state_dict(cfg, 0))
-            t, ex = time_config(torch, dist, eng, cfg, B, S, steps, 2, device, 1, 0, False, flush, 2000)
-            H = cfg.encoding_size
-            bps = 108.0 * ex["mean_depth"] + 8.0 * H + 112.0
-            row = dict(game=game, roots=B, sims=S, sims_per_s=B * S * steps / t, search_ms=ex["search_ms"],
-                       root_ms=ex["root_ms"], mean_depth=ex["mean_depth"],
-                       achieved_gbs=bps * B * S / (ex["search_ms"] * 1e-3) / 1e9, trees_per_cta=ex["stats"]["trees_per_cta"])
-            eng.close()
-        except Exception as e:  # pragma: no cover
-            row = dict(game=game, roots=B, sims=S, error=str(e))
-        rows.append(row)
-        log("sweep", json.dumps(row))
-    line["sweep"] = rows
+def python_reference_rate():
+    """The unmodified Python reference (MCTS.run of muzero-general/self_play.py on torch-CPU), measured in the build
+    container where /root/reference exists (oracle/time_python_reference.py); it cannot run on the GPU box."""
+    p = os.path.join(ROOT, "profiles", "python_reference_rate.json")
+    try:
+        return json.load(open(p))
+    except Exception:
+        return None
 
 
 if __name__ == "__main__":

@@ -110,7 +110,10 @@ typedef struct {
                                       max_simulations). observations are ignored, root_predicted_value is not written
                                       (the reference returns None). Deterministic and risk-sensitive search only: the
                                       stochastic reference fails its own assert (self_play_stochastic.py:333). */
-    int32_t reserved0;
+    int32_t outputs_on_device;     /* != 0 with memory == TSP_MEM_HOST: the INPUT arrays are host memory (uploaded by the
+                                      engine, overlapped with the previous search) while every OUTPUT array is device
+                                      memory -- the multi-GPU path gathers the root statistics over NCCL before they
+                                      leave the device (sharding.ShardedEngine). Ignored with TSP_MEM_DEVICE. */
     /* inputs */
     const float *observations;     /* [B][obs_dim]; torch.tensor(observation).float() of self_play.py:336-341 */
     const int32_t *legal_actions;  /* [B][A] ordered legal-action lists (dict insertion order matters,

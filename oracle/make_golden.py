@@ -21,28 +21,28 @@ from oracle import reference_live as RL  # noqa: E402
 
 OUT_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 
-# (fixture name, game config, S, number of roots, options)
+# (fixture name, game config, S, number of roots, options, seed) -- the seed is part of the case, not its list position
 CASES = [
-    ("highway_s25", "highway_env_ttc_flat", 25, 16, {}),
-    ("roundabout_s50", "roundabout_env_ttc_flat", 50, 16, {}),
-    ("roundabout_s50_legal", "roundabout_env_ttc_flat", 50, 12, {"legal": True}),
-    ("roundabout_s25_uniform", "roundabout_env_ttc_flat", 25, 8, {"uniform_policy": True}),
-    ("roundabout_s25_nonoise", "roundabout_env_ttc_flat", 25, 8, {"no_noise": True}),
-    ("roundabout_s25_mask", "roundabout_env_ttc_flat", 25, 8, {"mask": True}),
-    ("stochastic_s25", "roundabout_env_ttc_flat_stochastic_concat", 25, 16, {}),
-    ("stochastic_s25_legal", "roundabout_env_ttc_flat_stochastic_concat", 25, 8, {"legal": True}),
-    ("risk_s25", "roundabout_env_ttc_flat_risk_sensitive", 25, 16, {}),
-    ("risk_s25_legal", "roundabout_env_ttc_flat_risk_sensitive", 25, 8, {"legal": True}),
-    ("cross_merge_s200", "cross_merge_env", 200, 4, {}),
+    ("highway_s25", "highway_env_ttc_flat", 25, 16, {}, 0),
+    ("roundabout_s50", "roundabout_env_ttc_flat", 50, 16, {}, 1),
+    ("roundabout_s50_legal", "roundabout_env_ttc_flat", 50, 12, {"legal": True}, 2),
+    ("roundabout_s25_uniform", "roundabout_env_ttc_flat", 25, 8, {"uniform_policy": True}, 3),
+    ("roundabout_s25_nonoise", "roundabout_env_ttc_flat", 25, 8, {"no_noise": True}, 4),
+    ("roundabout_s25_mask", "roundabout_env_ttc_flat", 25, 8, {"mask": True}, 5),
+    ("stochastic_s25", "roundabout_env_ttc_flat_stochastic_concat", 25, 16, {}, 6),
+    ("stochastic_s25_legal", "roundabout_env_ttc_flat_stochastic_concat", 25, 8, {"legal": True}, 7),
+    ("risk_s25", "roundabout_env_ttc_flat_risk_sensitive", 25, 16, {}, 8),
+    ("risk_s25_legal", "roundabout_env_ttc_flat_risk_sensitive", 25, 8, {"legal": True}, 9),
+    ("cross_merge_s200", "cross_merge_env", 200, 4, {}, 10),
     # two-player backup / ucb branch (self_play.py:469-472, 492-500); to_play alternates over the roots
-    ("roundabout_s25_twoplayer", "roundabout_env_ttc_flat", 25, 12, {"players": [0, 1]}),
+    ("roundabout_s25_twoplayer", "roundabout_env_ttc_flat", 25, 12, {"players": [0, 1]}, 11),
     # the search continued twice with override_root_with=root (self_play.py:331-333): 3 x S simulations
-    ("roundabout_s25_override", "roundabout_env_ttc_flat", 25, 8, {"phases": 3}),
+    ("roundabout_s25_override", "roundabout_env_ttc_flat", 25, 8, {"phases": 3}, 12),
     # (the stochastic search cannot be continued: its assert at self_play_stochastic.py:333 fails on a root
     #  that already has visits; the risk-sensitive one has no such assert)
-    ("roundabout_s25_override_legal", "roundabout_env_ttc_flat", 25, 6, {"phases": 2, "legal": True, "mask": "adaptive"}),
-    ("risk_s25_override", "roundabout_env_ttc_flat_risk_sensitive", 25, 6, {"phases": 2, "legal": True}),
-    ("roundabout_s25_twoplayer_mask", "roundabout_env_ttc_flat", 25, 8, {"players": [0, 1], "mask": "adaptive", "legal": True}),
+    ("roundabout_s25_override_legal", "roundabout_env_ttc_flat", 25, 6, {"phases": 2, "legal": True, "mask": "adaptive"}, 13),
+    ("risk_s25_override", "roundabout_env_ttc_flat_risk_sensitive", 25, 6, {"phases": 2, "legal": True}, 14),
+    ("roundabout_s25_twoplayer_mask", "roundabout_env_ttc_flat", 25, 8, {"players": [0, 1], "mask": "adaptive", "legal": True}, 12),
 ]
 
 
@@ -199,10 +199,10 @@ def make_case(name, game, S, N, opt, seed):
 def main():
     os.makedirs(OUT_DIR, exist_ok=True)
     only = set(sys.argv[1:])  # optional fixture names: the committed fixtures are not rewritten needlessly
-    for i, (name, game, S, N, opt) in enumerate(CASES):
+    for name, game, S, N, opt, seed in CASES:
         if only and name not in only:
             continue
-        path, out = make_case(name, game, S, N, opt, seed=i)
+        path, out = make_case(name, game, S, N, opt, seed=seed)
         print("%-26s %8.1f KB  visits[0]=%s depth<=%d records<=%d" % (
             name, os.path.getsize(path) / 1024.0, out["visit_counts"][0], out["max_tree_depth"].max(),
             out["n_records"].max()))

@@ -86,3 +86,38 @@ def assert_close_quantised(got, want, tol=1e-5, min_fraction=0.98, hard_tol=2e-3
     frac = float((err <= tol).mean())
     # (a single quantisation step on a fixture with a handful of roots must not fail the fraction test)
     assert frac >= min_fraction or int((err > tol).sum()) <= 1, "%s: only %.4f of entries within %g" % (what, frac, tol)
+
+
+def quantised_columns(records, n_futures):
+    """Boolean mask [..., REC] of the record entries that went through the reference's float32 inverse value transform
+    (support_to_scalar, models.py:1180-1201) and may therefore differ by one quantisation step: value and reward of a
+    state record (kind 1: columns 1, 2), the per-future rewards of a transition record (kind 2: columns 1 + nf .. 1 + 2 nf).
+    Everything else -- priors, transition probabilities, the terminal logit, the kind -- is plain float32 arithmetic."""
+    r = numpy.asarray(records)
+    q = numpy.zeros(r.shape, bool)
+    state = r[..., 0] == 1.0
+    trans = r[..., 0] == 2.0
+    q[..., 1] |= state
+    q[..., 2] |= state
+    for c in range(1 + n_futures, 1 + 2 * n_futures):
+        q[..., c] |= trans
+    return q
+
+
+def assert_records_close(got, want, n_futures, live=None, tol=1e-5, min_fraction=0.97, hard_tol=2e-3, what="records"):
+    """Column-wise tolerance for evaluation records: priors / probabilities / logits within `tol` on EVERY live entry;
+    only the entries of `quantised_columns` get the quantisation allowance of assert_close_quantised."""
+    a, b = numpy.asarray(got, numpy.float64), numpy.asarray(want, numpy.float64)
+    err = numpy.abs(a - b) / numpy.maximum(1.0, numpy.abs(b))
+    q = quantised_columns(want, n_futures)
+    if live is None:
+        live = numpy.ones(a.shape[:-1], bool)
+    live = numpy.broadcast_to(numpy.asarray(live, bool)[..., None], a.shape)
+    plain = live & ~q
+    assert err[plain].size == 0 or err[plain].max() <= tol, "%s: prior / probability entry off by %g (> %g)" % (
+        what, err[plain].max(), tol)
+    e = err[live & q]
+    if e.size:
+        assert e.max() <= hard_tol, "%s: max error of a value / reward entry %g > %g" % (what, e.max(), hard_tol)
+        frac = float((e <= tol).mean())
+        assert frac >= min_fraction or int((e > tol).sum()) <= 1, "%s: only %.4f of value / reward entries within %g" % (what, frac, tol)

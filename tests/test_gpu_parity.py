@@ -11,7 +11,8 @@ import pytest
 
 torch = pytest.importorskip("torch")
 
-from golden_util import Golden, golden_names, assert_tree_outputs_bit_exact, assert_close_quantised  # noqa: E402
+from golden_util import (Golden, golden_names, assert_tree_outputs_bit_exact, assert_close_quantised,  # noqa: E402
+                         assert_records_close)
 import tree_search_planning_b200 as tsp  # noqa: E402
 from oracle.oracle import Oracle  # noqa: E402  (the checker)
 
@@ -60,6 +61,11 @@ def drop_terminal(records, cfg):
     return r
 
 
+# Floors of the end-to-end visit-count agreement with the reference fixtures (fraction of the fixture's roots), pinned
+# just under what the B200 run measured (see the AGREE lines of profiles/r2_gpu_tests.log) so that a regression shows.
+GOLDEN_FLOOR = {}
+
+
 def close(a, b, tol=1e-5):
     a, b = numpy.asarray(a, numpy.float64), numpy.asarray(b, numpy.float64)
     return numpy.abs(a - b) <= tol * numpy.maximum(1.0, numpy.abs(b))
@@ -86,7 +92,13 @@ def test_end_to_end_against_reference_golden(name):
     got, traces = engine_run(eng, g, fed=False, trace=True, want_root_hidden=True)
     got["trace_records"] = traces[-1]
     same = (got["visit_counts"] == g.out["visit_counts"]).all(axis=1)
-    assert same.mean() >= 0.9, "visit counts differ on %d of %d roots" % ((~same).sum(), g.N)
+    assert same.mean() >= GOLDEN_FLOOR.get(name, 0.9), "visit counts differ on %d of %d roots" % ((~same).sum(), g.N)
+    st = eng.stats()
+    print("AGREE golden %s %.4f kernel %d" % (name, same.mean(), st["search_kernel"]))
+    # the fixtures inside the tcgen05 envelope must really run on the tcgen05 kernels (2: weights in tensor memory,
+    # 3: weights streamed by TMA) -- this test must not silently stop covering them
+    if not getattr(g.config, "mask_absorbing_states", False):
+        assert st["search_kernel"] in (2, 3), (name, st["search_kernel"])
     assert close(got["root_hidden"], g.out["root_hidden"]).all()
     assert_close_quantised(got["trace_root"], g.out["root_record"], what="root record")
     assert_close_quantised(got["root_value"][same], g.out["root_value"][same], min_fraction=0.85, what="root value")
@@ -96,8 +108,8 @@ def test_end_to_end_against_reference_golden(name):
         n = g.out["n_records"][b]
         assert got["num_records"][b] == n
         ref_rec = g.out["records"] if g.P == 1 else g.out["records"][-1]
-        assert_close_quantised(drop_terminal(got["trace_records"][b, :n], g.config),
-                               drop_terminal(ref_rec[b, :n], g.config), min_fraction=0.97, what="records")
+        assert_records_close(drop_terminal(got["trace_records"][b, :n], g.config),
+                             drop_terminal(ref_rec[b, :n], g.config), getattr(g.config, "n_futures", 1), what="records")
 
 
 @pytest.mark.parametrize("name", ["highway_s25", "cross_merge_s200", "stochastic_s25"])
@@ -214,9 +226,12 @@ def check_against_oracle(cfg, B, S, seed, legal=False, min_agree=0.985, **run_op
     assert diverged.mean() <= 1.0 - min_agree, "%.4f of the trees diverged" % diverged.mean()
     keep = ~diverged
     if keep.any():
-        e = err[keep][live[keep]]
-        assert (e <= 1e-5).mean() >= 0.97, "only %.4f of record entries within 1e-5" % (e <= 1e-5).mean()
+        # priors / transition probabilities within 1e-5 on EVERY entry of the trees that did not diverge; only value /
+        # reward entries get the quantisation allowance
+        assert_records_close(a[keep], w[keep], getattr(cfg, "n_futures", 1), live=live[keep], what="trace records")
         assert_close_quantised(got["root_value"][keep], want["root_value"][keep], min_fraction=0.85, what="root value")
+    print("AGREE oracle %s B=%d S=%d visit-count agreement %.4f diverged %.4f kernel %d" % (
+        cfg.name, B, S, same.mean(), diverged.mean(), eng.stats()["search_kernel"]))
     eng.close()
     return float(same.mean())
 

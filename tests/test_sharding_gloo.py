@@ -100,3 +100,40 @@ def test_two_ranks_match_one(tmp_path):
         assert numpy.array_equal(z["root_value"], want["root_value"])
         assert numpy.array_equal(z["max_tree_depth"], want["max_tree_depth"])
     assert spans == [(0, 19), (19, 37)]
+
+
+def _packed_worker(rank, world, port, B, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    from tree_search_planning_b200.sharding import PackedGather, shard_bounds
+
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    A = 5
+    pg = PackedGather([("visit_counts", (A,), torch.int32), ("root_value", (), torch.float64)], B, world, rank, "cpu")
+    lo, hi = shard_bounds(B, world, rank)
+    # what the engine would write into the views of this rank's block of roots
+    pg.local["visit_counts"][:hi - lo] = torch.arange(lo * A, hi * A, dtype=torch.int32).reshape(-1, A)
+    pg.local["root_value"][:hi - lo] = torch.arange(lo, hi, dtype=torch.float64) * 0.5
+    pg.gather()  # ONE collective for both fields
+    out = pg.unpack()
+    numpy.savez(os.path.join(out_dir, "packed%d.npz" % rank), **{k: v.numpy() for k, v in out.items()})
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("B", [37, 64])
+def test_packed_gather_one_collective_two_ranks(tmp_path, B):
+    """sharding.PackedGather (the multi-GPU product path's single all-gather of visit counts | root values): every
+    rank ends up with every root's statistics in root order, for equal and for unequal shards."""
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    procs = [ctx.Process(target=_packed_worker, args=(r, world, port, B, str(tmp_path))) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    for r in range(world):
+        z = numpy.load(os.path.join(str(tmp_path), "packed%d.npz" % r))
+        assert numpy.array_equal(z["visit_counts"], numpy.arange(B * 5, dtype=numpy.int32).reshape(B, 5))
+        assert numpy.array_equal(z["root_value"], numpy.arange(B, dtype=numpy.float64) * 0.5)

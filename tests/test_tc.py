@@ -19,6 +19,7 @@ torch = pytest.importorskip("torch")
 import tree_search_planning_b200 as tsp  # noqa: E402
 from tree_search_planning_b200.synthetic import random_state_dict, synthetic_inputs  # noqa: E402
 from test_gpu_parity import check_against_oracle  # noqa: E402
+from golden_util import assert_records_close  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 
@@ -65,7 +66,9 @@ def test_agrees_with_the_mma_sync_kernel(B, S, monkeypatch):
     a = tc["trace_records"][same].astype(numpy.float64)
     b = mm["trace_records"][same].astype(numpy.float64)
     err = numpy.abs(a - b) / numpy.maximum(1.0, numpy.abs(b))
-    assert (err <= 1e-5).mean() >= 0.97 and numpy.median(err) <= 1e-6
+    assert numpy.median(err) <= 1e-6
+    # priors within 1e-5 on every entry; only value / reward get the quantisation allowance
+    assert_records_close(a, b, 1, what="tcgen05 vs mma.sync records")
 
 
 @pytest.mark.parametrize("B", [2048, 8192])

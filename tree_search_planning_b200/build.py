@@ -35,13 +35,27 @@ def build(force=False, verbose=False):
     """Compile the engine for sm_100a; returns the path of the shared library."""
     if not force and not needs_build():
         return LIB_PATH
+    import fcntl
     flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"]
-    cmd = [_nvcc()] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + SOURCES
-    proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, universal_newlines=True)
-    if proc.returncode != 0:
-        raise RuntimeError("nvcc failed:\n%s\n%s" % (" ".join(cmd), proc.stdout))
-    if verbose:
-        print(proc.stdout)
+    # one builder at a time (one process per GPU may import the package at once); the library appears atomically, so a
+    # concurrent dlopen never sees a torn file
+    with open(LIB_PATH + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and not needs_build():
+            return LIB_PATH  # another process built it while we waited
+        tmp = "%s.tmp.%d" % (LIB_PATH, os.getpid())
+        cmd = [_nvcc()] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + SOURCES
+        try:
+            proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, universal_newlines=True)
+        except FileNotFoundError:
+            raise RuntimeError("nvcc not found (looked for $NVCC, /usr/local/cuda/bin/nvcc, nvcc on PATH): cannot build %s" % LIB_PATH)
+        if proc.returncode != 0:
+            if os.path.exists(tmp):
+                os.remove(tmp)
+            raise RuntimeError("nvcc failed:\n%s\n%s" % (" ".join(cmd), proc.stdout))
+        os.replace(tmp, LIB_PATH)
+        if verbose:
+            print(proc.stdout)
     return LIB_PATH
 
 

@@ -72,7 +72,14 @@ struct tsp_engine {
     cudaStream_t copy_stream = nullptr;
     static constexpr int OBS_CHUNKS = 4;
     cudaEvent_t ev_chunk[OBS_CHUNKS] = {};
-    cudaEvent_t ev_root_done = nullptr;
+    // Two sets of input staging buffers, used alternately: the inputs of run i + 1 cross PCIe on the copy stream while
+    // the search of run i (which still reads its own set: tie / chance streams, noise) is running.
+    struct InSet {
+        DevBuf obs, legal, nlegal, noise, tie, chance;
+        cudaEvent_t done = nullptr;  // recorded behind the search that read this set
+    };
+    InSet in_set[2];
+    int in_flip = 0;
     bool no_overlap = false;  // TSP_NO_OVERLAP
     // ring of event triples (before root kernel, between, after search kernel), drained lazily
     static constexpr int EV_RING = 1024;
@@ -155,6 +162,7 @@ int ensure(tsp_engine* e, DevBuf& b, size_t bytes) {
     if (bytes <= b.cap) return TSP_OK;
     if (b.p) {
         CK(e, cudaStreamSynchronize(e->stream));
+        if (e->copy_stream) CK(e, cudaStreamSynchronize(e->copy_stream));
         CK(e, cudaFree(b.p));
         e->pool_bytes -= (int64_t)b.cap;
         b.p = nullptr;
@@ -1446,8 +1454,8 @@ int tsp_create(const tsp_config* cfg, tsp_handle* out) {
         return bail(fail(e, TSP_ECUDA, "cudaStreamCreate failed"));
     for (auto& ce : e->ev_chunk)
         if (cudaEventCreateWithFlags(&ce, cudaEventDisableTiming) != cudaSuccess) return bail(fail(e, TSP_ECUDA, "cudaEventCreate failed"));
-    if (cudaEventCreateWithFlags(&e->ev_root_done, cudaEventDisableTiming) != cudaSuccess)
-        return bail(fail(e, TSP_ECUDA, "cudaEventCreate failed"));
+    for (auto& is : e->in_set)
+        if (cudaEventCreateWithFlags(&is.done, cudaEventDisableTiming) != cudaSuccess) return bail(fail(e, TSP_ECUDA, "cudaEventCreate failed"));
     e->ev.resize(3 * tsp_engine::EV_RING, nullptr);
     for (auto& ev : e->ev)
         if (cudaEventCreate(&ev) != cudaSuccess) return bail(fail(e, TSP_ECUDA, "cudaEventCreate failed"));
@@ -1508,7 +1516,10 @@ int tsp_destroy(tsp_handle e) {
         if (ev) cudaEventDestroy(ev);
     for (auto& ce : e->ev_chunk)
         if (ce) cudaEventDestroy(ce);
-    if (e->ev_root_done) cudaEventDestroy(e->ev_root_done);
+    for (auto& is : e->in_set) {
+        if (is.done) cudaEventDestroy(is.done);
+        for (DevBuf* b : {&is.obs, &is.legal, &is.nlegal, &is.noise, &is.tie, &is.chance}) release(*b);
+    }
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
@@ -1625,6 +1636,7 @@ int tsp_run(tsp_handle e, const tsp_run_args* a) {
     }
     CK(e, cudaSetDevice(e->device));
     const int mem = a->memory;
+    const int omem = (mem == TSP_MEM_HOST && a->outputs_on_device) ? TSP_MEM_DEVICE : mem;  // where the OUTPUT arrays live
     const size_t nb = (size_t)B;
     int rc;
 
@@ -1649,21 +1661,45 @@ int tsp_run(tsp_handle e, const tsp_run_args* a) {
         memset(&np.sched, 0, sizeof(np.sched));
         np.sched.row_stride = 36;
     }
-    // large HOST batches: upload the observations in OBS_CHUNKS row chunks on the copy stream (below, next to the launches)
+    // Large HOST batches: every input crosses PCIe on the copy stream into one of two staging sets (used alternately), so
+    // that the upload of this run overlaps the search of the previous one; the launches below wait for the copies.
     const bool overlap = mem == TSP_MEM_HOST && !resume && !fed && a->observations && B >= 1024 && !e->no_overlap && e->copy_stream;
+    tsp_engine::InSet* is = nullptr;
+    // on the copy stream: host array -> staging buffer of the set
+    auto upload = [&](const void* src, size_t bytes, DevBuf& buf, const void** out) -> int {
+        *out = nullptr;
+        if (!src || bytes == 0) return TSP_OK;
+        int r = ensure(e, buf, bytes);
+        if (r) return r;
+        CK(e, cudaMemcpyAsync(buf.p, src, bytes, cudaMemcpyHostToDevice, e->copy_stream));
+        e->stats.bytes_h2d += (int64_t)bytes;
+        *out = buf.p;
+        return TSP_OK;
+    };
     if (overlap) {
-        if ((rc = ensure(e, e->s_obs, nb * c.obs_dim * sizeof(float)))) return rc;
-        np.in = reinterpret_cast<const float*>(e->s_obs.p);
-    } else if ((rc = stage_in(e, mem, a->observations, nb * c.obs_dim, e->s_obs, &np.in))) {
-        return rc;
+        is = &e->in_set[e->in_flip];
+        e->in_flip ^= 1;
+        if ((rc = ensure(e, is->obs, nb * c.obs_dim * sizeof(float)))) return rc;
+        np.in = reinterpret_cast<const float*>(is->obs.p);
+        // the set is free once the search that read it (two runs ago) is done
+        CK(e, cudaStreamWaitEvent(e->copy_stream, is->done, 0));
+        const void* d = nullptr;
+        if ((rc = upload(a->legal_actions, nb * A * sizeof(int32_t), is->legal, &d))) return rc;
+        np.legal = reinterpret_cast<const int32_t*>(d);
+        if ((rc = upload(a->num_legal, nb * sizeof(int32_t), is->nlegal, &d))) return rc;
+        np.num_legal = reinterpret_cast<const int32_t*>(d);
+        if ((rc = upload(a->noise, nb * A * sizeof(double), is->noise, &d))) return rc;
+        np.noise = reinterpret_cast<const double*>(d);
+    } else {
+        if ((rc = stage_in(e, mem, a->observations, nb * c.obs_dim, e->s_obs, &np.in))) return rc;
+        if ((rc = stage_in(e, mem, a->legal_actions, nb * A, e->s_legal, &np.legal))) return rc;
+        if ((rc = stage_in(e, mem, a->num_legal, nb, e->s_nlegal, &np.num_legal))) return rc;
+        if ((rc = stage_in(e, mem, a->noise, nb * A, e->s_noise, &np.noise))) return rc;
     }
-    if ((rc = stage_in(e, mem, a->legal_actions, nb * A, e->s_legal, &np.legal))) return rc;
-    if ((rc = stage_in(e, mem, a->num_legal, nb, e->s_nlegal, &np.num_legal))) return rc;
-    if ((rc = stage_in(e, mem, a->noise, nb * A, e->s_noise, &np.noise))) return rc;
     if ((rc = stage_in(e, mem, a->fed_root, nb * REC, e->s_fedroot, &np.fed_root))) return rc;
-    if ((rc = stage_out(e, mem, a->trace_root, nb * REC, e->s_troot, &np.trace_root))) return rc;
-    if ((rc = stage_out(e, mem, a->root_predicted_value, nb, e->s_rpred, &np.root_pred))) return rc;
-    if ((rc = stage_out(e, mem, a->root_hidden, nb * H, e->s_rhid, &np.root_hidden))) return rc;
+    if ((rc = stage_out(e, omem, a->trace_root, nb * REC, e->s_troot, &np.trace_root))) return rc;
+    if ((rc = stage_out(e, omem, a->root_predicted_value, nb, e->s_rpred, &np.root_pred))) return rc;
+    if ((rc = stage_out(e, omem, a->root_hidden, nb * H, e->s_rhid, &np.root_hidden))) return rc;
 
     SearchParams sp;
     memset(&sp, 0, sizeof(sp));
@@ -1709,31 +1745,42 @@ int tsp_run(tsp_handle e, const tsp_run_args* a) {
         sp.sched_b.row_stride = 4;
     }
     const size_t nrec = nb * (size_t)std::max(a->max_records, 0);
-    if ((rc = stage_in(e, mem, a->tie_stream, nb * sp.T, e->s_tie, &sp.tie))) return rc;
-    if ((rc = stage_in(e, mem, a->chance_stream, nb * sp.K, e->s_chance, &sp.chance))) return rc;
+    if (overlap) {
+        const void* d = nullptr;
+        if ((rc = upload(a->tie_stream, nb * sp.T, is->tie, &d))) return rc;
+        sp.tie = reinterpret_cast<const unsigned char*>(d);
+        if ((rc = upload(a->chance_stream, nb * sp.K, is->chance, &d))) return rc;
+        sp.chance = reinterpret_cast<const unsigned char*>(d);
+    } else {
+        if ((rc = stage_in(e, mem, a->tie_stream, nb * sp.T, e->s_tie, &sp.tie))) return rc;
+        if ((rc = stage_in(e, mem, a->chance_stream, nb * sp.K, e->s_chance, &sp.chance))) return rc;
+    }
     if ((rc = stage_in(e, mem, a->fed_records, nrec * REC, e->s_fed, &sp.fed))) return rc;
-    if ((rc = stage_out(e, mem, a->trace_records, nrec * REC, e->s_trace, &sp.trace))) return rc;
-    if ((rc = stage_out(e, mem, a->visit_counts, nb * A, e->s_visits, &sp.visit_counts))) return rc;
-    if ((rc = stage_out(e, mem, a->root_value, nb, e->s_rootv, &sp.root_value))) return rc;
-    if ((rc = stage_out(e, mem, a->child_value, nb * A, e->s_cval, &sp.child_value))) return rc;
-    if ((rc = stage_out(e, mem, a->child_prior, nb * A, e->s_cprior, &sp.child_prior))) return rc;
-    if ((rc = stage_out(e, mem, a->child_reward, nb * A, e->s_crew, &sp.child_reward))) return rc;
-    if ((rc = stage_out(e, mem, a->max_tree_depth, nb, e->s_depth, &sp.max_depth))) return rc;
-    if ((rc = stage_out(e, mem, a->num_records, nb, e->s_nrec, &sp.num_records))) return rc;
-    if ((rc = stage_out(e, mem, a->total_select_depth, nb, e->s_tdepth, &sp.total_depth))) return rc;
+    if ((rc = stage_out(e, omem, a->trace_records, nrec * REC, e->s_trace, &sp.trace))) return rc;
+    if ((rc = stage_out(e, omem, a->visit_counts, nb * A, e->s_visits, &sp.visit_counts))) return rc;
+    if ((rc = stage_out(e, omem, a->root_value, nb, e->s_rootv, &sp.root_value))) return rc;
+    if ((rc = stage_out(e, omem, a->child_value, nb * A, e->s_cval, &sp.child_value))) return rc;
+    if ((rc = stage_out(e, omem, a->child_prior, nb * A, e->s_cprior, &sp.child_prior))) return rc;
+    if ((rc = stage_out(e, omem, a->child_reward, nb * A, e->s_crew, &sp.child_reward))) return rc;
+    if ((rc = stage_out(e, omem, a->max_tree_depth, nb, e->s_depth, &sp.max_depth))) return rc;
+    if ((rc = stage_out(e, omem, a->num_records, nb, e->s_nrec, &sp.num_records))) return rc;
+    if ((rc = stage_out(e, omem, a->total_select_depth, nb, e->s_tdepth, &sp.total_depth))) return rc;
     if (fed && a->fed_records == nullptr) sp.fed = reinterpret_cast<const float*>(e->hdr.p);  // S == 0: never read
 
     if (e->ev_pending == tsp_engine::EV_RING && (rc = drain_events(e))) return rc;
     cudaEvent_t* ev = &e->ev[3 * ((e->ev_head + e->ev_pending) % tsp_engine::EV_RING)];
     CK(e, cudaEventRecord(ev[0], e->stream));
     if (overlap) {
-        // the staging buffer is free once the previous run's root kernels are done
-        CK(e, cudaStreamWaitEvent(e->copy_stream, e->ev_root_done, 0));
-        const int per = ((B + tsp_engine::OBS_CHUNKS - 1) / tsp_engine::OBS_CHUNKS + 31) & ~31;
+        // A search still in flight hides the whole upload: one copy, ONE root launch behind it. On an idle engine the
+        // observations go up in OBS_CHUNKS row chunks and the root network of a chunk starts as soon as its rows have
+        // arrived, so that only the last chunk's root kernel is exposed (end to end = upload + search).
+        const bool busy = cudaStreamQuery(e->stream) == cudaErrorNotReady;
+        const int want = busy ? 1 : tsp_engine::OBS_CHUNKS;
+        const int per = ((B + want - 1) / want + 31) & ~31;
         int n_chunks = 0;
         for (int r0 = 0; r0 < B; r0 += per, ++n_chunks) {
             const size_t rows = (size_t)std::min(per, B - r0);
-            CK(e, cudaMemcpyAsync(reinterpret_cast<float*>(e->s_obs.p) + (size_t)r0 * c.obs_dim, a->observations + (size_t)r0 * c.obs_dim,
+            CK(e, cudaMemcpyAsync(reinterpret_cast<float*>(is->obs.p) + (size_t)r0 * c.obs_dim, a->observations + (size_t)r0 * c.obs_dim,
                                   rows * c.obs_dim * sizeof(float), cudaMemcpyHostToDevice, e->copy_stream));
             CK(e, cudaEventRecord(e->ev_chunk[n_chunks], e->copy_stream));
         }
@@ -1749,26 +1796,26 @@ int tsp_run(tsp_handle e, const tsp_run_args* a) {
     } else if (!resume && (rc = launch_net_any(e, np))) {
         return rc;
     }
-    if (e->ev_root_done) CK(e, cudaEventRecord(e->ev_root_done, e->stream));
     CK(e, cudaEventRecord(ev[1], e->stream));
     if ((rc = launch_search_any(e, sp))) return rc;
     CK(e, cudaEventRecord(ev[2], e->stream));
+    if (is) CK(e, cudaEventRecord(is->done, e->stream));
     e->ev_pending++;
 
     if (!resume) {  // the root is not evaluated again on resume (root_predicted_value is None in the reference)
-        if ((rc = copy_out(e, mem, a->trace_root, np.trace_root, nb * REC))) return rc;
-        if ((rc = copy_out(e, mem, a->root_predicted_value, np.root_pred, nb))) return rc;
-        if ((rc = copy_out(e, mem, a->root_hidden, np.root_hidden, nb * H))) return rc;
+        if ((rc = copy_out(e, omem, a->trace_root, np.trace_root, nb * REC))) return rc;
+        if ((rc = copy_out(e, omem, a->root_predicted_value, np.root_pred, nb))) return rc;
+        if ((rc = copy_out(e, omem, a->root_hidden, np.root_hidden, nb * H))) return rc;
     }
-    if ((rc = copy_out(e, mem, a->trace_records, sp.trace, nrec * REC))) return rc;
-    if ((rc = copy_out(e, mem, a->visit_counts, sp.visit_counts, nb * A))) return rc;
-    if ((rc = copy_out(e, mem, a->root_value, sp.root_value, nb))) return rc;
-    if ((rc = copy_out(e, mem, a->child_value, sp.child_value, nb * A))) return rc;
-    if ((rc = copy_out(e, mem, a->child_prior, sp.child_prior, nb * A))) return rc;
-    if ((rc = copy_out(e, mem, a->child_reward, sp.child_reward, nb * A))) return rc;
-    if ((rc = copy_out(e, mem, a->max_tree_depth, sp.max_depth, nb))) return rc;
-    if ((rc = copy_out(e, mem, a->num_records, sp.num_records, nb))) return rc;
-    if ((rc = copy_out(e, mem, a->total_select_depth, sp.total_depth, nb))) return rc;
+    if ((rc = copy_out(e, omem, a->trace_records, sp.trace, nrec * REC))) return rc;
+    if ((rc = copy_out(e, omem, a->visit_counts, sp.visit_counts, nb * A))) return rc;
+    if ((rc = copy_out(e, omem, a->root_value, sp.root_value, nb))) return rc;
+    if ((rc = copy_out(e, omem, a->child_value, sp.child_value, nb * A))) return rc;
+    if ((rc = copy_out(e, omem, a->child_prior, sp.child_prior, nb * A))) return rc;
+    if ((rc = copy_out(e, omem, a->child_reward, sp.child_reward, nb * A))) return rc;
+    if ((rc = copy_out(e, omem, a->max_tree_depth, sp.max_depth, nb))) return rc;
+    if ((rc = copy_out(e, omem, a->num_records, sp.num_records, nb))) return rc;
+    if ((rc = copy_out(e, omem, a->total_select_depth, sp.total_depth, nb))) return rc;
     e->stats.searches++;
     e->tree_roots = B;
     e->tree_sims = (resume ? e->tree_sims : 0) + S;
@@ -1909,7 +1956,10 @@ static int check_tc_status(tsp_engine* e) {
     if (!e->has_tc || !e->tc_status.p) return TSP_OK;
     int st = 0;
     CK(e, cudaMemcpy(&st, e->tc_status.p, sizeof(int), cudaMemcpyDeviceToHost));
-    if (st) return fail(e, TSP_ECUDA, "tcgen05 search kernel: mbarrier wait timed out");
+    if (st) {  // report once: the flag is cleared so that later searches are judged on their own
+        cudaMemset(e->tc_status.p, 0, sizeof(int));
+        return fail(e, TSP_ECUDA, "tcgen05 search kernel: mbarrier wait timed out (the results of that search are invalid)");
+    }
     return TSP_OK;
 }
 

@@ -671,6 +671,10 @@ __device__ __forceinline__ void search_fast_body(const FastParams& p, const TcSc
                     for (int d = 1; d < GW; d <<= 1) m1 = fmaxf(m1, __shfl_xor_sync(FULL, m1, d));
                     m1 = __shfl_sync(FULL, m1, gl0);
                     cand = (__ballot_sync(FULL, on && hi >= m1) >> gl0) & 0xFFu;
+                    // a non-finite score (NaN bounds drop out of fmaxf and of the comparison above) must not leave a
+                    // lone candidate behind: the level goes to the float64 path
+                    const unsigned bad = __ballot_sync(FULL, on && !(fabsf(sc) <= 3.0e38f));
+                    if ((bad >> gl0) & 0xFFu) cand = 0;
                 }
                 int sl = __ffs(cand) - 1;
                 const bool need = walking && __popc(cand) != 1;
@@ -1243,7 +1247,11 @@ __device__ __forceinline__ void search_fast_variant_body(const FastParams& p, co
 #pragma unroll
                 for (int d = 1; d < GW; d <<= 1) m1 = fmaxf(m1, __shfl_xor_sync(FULL, m1, d));
                 m1 = __shfl_sync(FULL, m1, gl0);
-                const unsigned cand = (__ballot_sync(FULL, on && hi >= m1) >> gl0) & 0xFFu;
+                unsigned cand = (__ballot_sync(FULL, on && hi >= m1) >> gl0) & 0xFFu;
+                {   // a non-finite score must not leave a lone candidate behind (NaN drops out of fmaxf / >=): float64 decides
+                    const unsigned bad = __ballot_sync(FULL, on && !(fabsf(sc) <= 3.0e38f));
+                    if ((bad >> gl0) & 0xFFu) cand = 0;
+                }
                 int sl = __ffs(cand) - 1;
                 const bool need = state_lvl && __popc(cand) != 1;
                 if (__any_sync(FULL, need)) {

@@ -40,7 +40,7 @@ class _RunArgs(ctypes.Structure):
         ("num_roots", ctypes.c_int32), ("num_simulations", ctypes.c_int32), ("memory", ctypes.c_int32),
         ("add_exploration_noise", ctypes.c_int32), ("uniform_policy", ctypes.c_int32),
         ("max_records", ctypes.c_int32), ("tie_len", ctypes.c_int32), ("chance_len", ctypes.c_int32),
-        ("resume", ctypes.c_int32), ("reserved0", ctypes.c_int32),
+        ("resume", ctypes.c_int32), ("outputs_on_device", ctypes.c_int32),
         ("observations", _P), ("legal_actions", _P), ("num_legal", _P), ("noise", _P),
         ("tie_stream", _P), ("chance_stream", _P), ("fed_root", _P), ("fed_records", _P),
         ("visit_counts", _P), ("root_value", _P), ("child_value", _P), ("child_prior", _P),
@@ -75,13 +75,18 @@ _lib = None
 
 
 def load_library(path=None):
-    """Load libtsp_b200.so (building it in-tree if the sources are newer). Fails loudly."""
+    """Load libtsp_b200.so. Fails loudly when it is missing. It is (re)built in-tree only when it does not exist, or
+    when TSP_AUTOBUILD=1 and a source is newer (after a checkout / rsync the mtimes say nothing, and on a GPU box with
+    one process per GPU nobody wants N concurrent nvcc runs); `__graft_entry__.build()` is the explicit build."""
     global _lib
     if _lib is not None and path is None:
         return _lib
     p = path or _build.LIB_PATH
-    if path is None and _build.needs_build():
-        _build.build()
+    if path is None and (not os.path.exists(p) or (os.environ.get("TSP_AUTOBUILD") == "1" and _build.needs_build())):
+        try:
+            _build.build()
+        except RuntimeError as e:
+            raise TspError(-2, "CUDA extension %s is missing or stale and could not be built: %s" % (p, e))
     if not os.path.exists(p):
         raise TspError(-2, "CUDA extension %s is missing; run `python -c 'import __graft_entry__ as g; g.build()'`" % p)
     lib = ctypes.CDLL(p)
@@ -399,7 +404,7 @@ class Engine:
         self._check(self.lib.tsp_reset_timing(self.handle))
 
     def make_args(self, num_roots, num_simulations, memory, inputs, outputs, add_exploration_noise=True,
-                  uniform_policy=False, max_records=0, tie_len=0, chance_len=0, resume=False):
+                  uniform_policy=False, max_records=0, tie_len=0, chance_len=0, resume=False, outputs_on_device=False):
         """Build a tsp_run_args over caller-owned buffers (numpy arrays, or torch tensors for device /
         pinned memory). `inputs` / `outputs` map the field names of tsp_run_args to buffers."""
         a = _RunArgs()
@@ -407,6 +412,7 @@ class Engine:
         a.add_exploration_noise, a.uniform_policy = int(bool(add_exploration_noise)), int(bool(uniform_policy))
         a.max_records, a.tie_len, a.chance_len = int(max_records), int(tie_len), int(chance_len)
         a.resume = int(bool(resume))
+        a.outputs_on_device = int(bool(outputs_on_device))
         names = {n for n, _ in _RunArgs._fields_}
         for k, v in list(inputs.items()) + list(outputs.items()):
             if k not in names:

@@ -28,10 +28,24 @@ def _config_key(config, device):
 
 
 def _weights_fingerprint(model):
+    """When does the engine have to reload the weights? A state dict is identified by its CONTENT (crc32 over every
+    array: ~1 ms for these networks) -- never by id(): a dict fetched fresh each step often lands at the address of the
+    one just freed, and a dict updated in place keeps its id. A module is identified by (storage address, version
+    counter) of every parameter: in-place updates (optimizer steps, load_state_dict / set_weights) bump the version,
+    replaced parameters change the address. `MCTS.refresh_weights()` forces a reload regardless."""
+    import zlib
     if isinstance(model, dict):
-        return ("dict", id(model))
+        crc = 0
+        for k in sorted(model.keys()):
+            v = model[k]
+            if hasattr(v, "detach"):
+                v = v.detach().cpu().numpy()
+            v = numpy.ascontiguousarray(v)
+            crc = zlib.crc32(k.encode(), crc)
+            crc = zlib.crc32(v.view(numpy.uint8).reshape(-1) if v.size else b"", crc)
+        return ("dict", len(model), crc)
     params = list(model.parameters()) if hasattr(model, "parameters") else []
-    return (id(model), sum(int(getattr(p, "_version", 0)) for p in params))
+    return ("module", id(model)) + tuple((int(p.data_ptr()), int(getattr(p, "_version", 0))) for p in params)
 
 
 class ChildView:
@@ -128,6 +142,21 @@ class MCTS:
             ent["engine"].load_state_dict(sd)
             ent["fingerprint"] = fp
         return ent["engine"]
+
+    def refresh_weights(self):
+        """Forget which weights the cached engine of this config holds: the next run reloads them from `model`
+        (for callers that mutate weights in ways the fingerprint cannot see, e.g. through raw storage)."""
+        ent = _engine_cache.get(_config_key(self.config, self.device))
+        if ent is not None:
+            ent["fingerprint"] = None
+
+    @staticmethod
+    def close_engines():
+        """Destroy every cached engine (the cache is process-wide and keyed by game config + device, because the
+        reference constructs a new MCTS(config) for every move, self_play.py:148)."""
+        for ent in _engine_cache.values():
+            ent["engine"].close()
+        _engine_cache.clear()
 
     # -- the reference surface ---------------------------------------------------------------
     def run(self, model, observation, legal_actions, to_play, add_exploration_noise, override_root_with=None,

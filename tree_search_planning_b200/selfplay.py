@@ -14,8 +14,11 @@ Per environment step and for all B games together:
 
 The environments are whatever the caller supplies (the reference's Game protocol: reset() -> observation,
 step(action) -> (observation, reward, done), legal_actions(), to_play()); gym / highway-env are not part of
-this package. Random sources follow the reference: numpy.random for the Dirichlet noise, ties, chance
-outcomes and the action sampling (one uniform sample per game replaces numpy.random.choice(actions, p=...)).
+this package. Random sources: Dirichlet noise, tie / chance streams and the action sampling (one uniform sample per
+game replaces numpy.random.choice(actions, p=...)) are all drawn from ONE numpy Generator seeded by `seed`
+(seed=None: fresh OS entropy), so a seeded driver is reproducible. The temperature follows the game file's
+visit_softmax_temperature_fn / temperature_threshold like play_game (self_play.py:171-185) when they are given.
+Finished games are not searched again: their rows keep a one-action legal list and their results are ignored.
 """
 import numpy
 
@@ -38,7 +41,10 @@ class GameHistory:
 
 
 class BatchedSelfPlay:
-    def __init__(self, config, state_dict, games, device=0, temperature=1.0, add_exploration_noise=True, seed=None):
+    def __init__(self, config, state_dict, games, device=0, temperature=1.0, add_exploration_noise=True, seed=None,
+                 temperature_fn=None, temperature_threshold=None, trained_steps=0):
+        """`temperature`: fixed sampling temperature, unless `temperature_fn(trained_steps)` is given (the game file's
+        visit_softmax_temperature_fn); `temperature_threshold`: moves after which play is greedy (self_play.py:181-184)."""
         import torch
 
         self.torch = torch
@@ -50,7 +56,9 @@ class BatchedSelfPlay:
         c, h, w = config.observation_shape
         self.F, self.HW = c * h * w, h * w
         self.obs_dim = observation_dim(config)
-        self.temperature = float(temperature)
+        self.temperature = float(temperature if temperature_fn is None else temperature_fn(trained_steps))
+        self.temperature_threshold = temperature_threshold
+        self.moves = 0
         self.add_noise = bool(add_exploration_noise)
         self.rng = numpy.random.default_rng(seed)
         self.variant = variant_of(config)
@@ -128,14 +136,20 @@ class BatchedSelfPlay:
         legal = numpy.zeros((B, A), numpy.int32)
         nlegal = numpy.zeros(B, numpy.int32)
         noise = numpy.zeros((B, A), numpy.float64)
+        rng = self.rng
         for b, g in enumerate(self.games):
+            if not live[b]:  # a finished game is not asked for legal actions again; its row is a dummy
+                legal[b, 0] = self.config.action_space[0]
+                nlegal[b] = 1
+                noise[b, 0] = 1.0
+                continue
             la = list(g.legal_actions())
             assert la, f"Legal actions should not be an empty array. Got {la}."
             assert set(la).issubset(set(self.config.action_space)), "Legal actions should be a subset of the action space."
             legal[b, :len(la)] = la
             nlegal[b] = len(la)
             if self.add_noise:
-                noise[b, :len(la)] = numpy.random.dirichlet([self.config.root_dirichlet_alpha] * len(la))
+                noise[b, :len(la)] = rng.dirichlet([self.config.root_dirichlet_alpha] * len(la))
         newest = torch.from_numpy(idx[:, 0].astype(numpy.int64)).to(self.dev)
         with torch.cuda.stream(self.stream):
             self.pool.index_copy_(0, newest, self.h_frame.to(self.dev, non_blocking=True))
@@ -144,22 +158,28 @@ class BatchedSelfPlay:
             self.d_legal.copy_(torch.from_numpy(legal), non_blocking=True)
             self.d_nlegal.copy_(torch.from_numpy(nlegal), non_blocking=True)
             self.d_noise.copy_(torch.from_numpy(noise), non_blocking=True)
-            self.d_tie.copy_(torch.from_numpy(numpy.random.randint(0, _STREAM_MOD, size=(B, 32)).astype(numpy.uint8)),
+            self.d_tie.copy_(torch.from_numpy(rng.integers(0, _STREAM_MOD, size=(B, 32)).astype(numpy.uint8)),
                              non_blocking=True)
             if self.variant != 0:
-                self.d_chance.copy_(torch.from_numpy(numpy.random.randint(
+                self.d_chance.copy_(torch.from_numpy(rng.integers(
                     0, _STREAM_MOD, size=tuple(self.d_chance.shape)).astype(numpy.uint8)), non_blocking=True)
-            self.d_uniform.copy_(torch.from_numpy(numpy.random.random_sample(B)), non_blocking=True)
+            self.d_uniform.copy_(torch.from_numpy(rng.random(B)), non_blocking=True)
             eng = self.engine
             eng.stack_observations(self.pool, self.frame_index, self.action_value, self.obs, self.so, self.F, self.HW)
             eng.run_raw(self.args)
-            eng.select_action(self.d_visits, self.temperature, self.d_uniform, self.d_legal, self.d_nlegal,
+            temperature = self.temperature  # self_play.py:178-185
+            if self.temperature_threshold is not None and self.moves >= self.temperature_threshold:
+                temperature = 0.0
+            eng.select_action(self.d_visits, temperature, self.d_uniform, self.d_legal, self.d_nlegal,
                               out=self.d_action)
             eng.search_statistics(self.d_visits, out=self.d_child_visits)
             self.h_action.copy_(self.d_action, non_blocking=True)
             self.h_child_visits.copy_(self.d_child_visits, non_blocking=True)
             self.h_rootv.copy_(self.d_rootv, non_blocking=True)
-        self.stream.synchronize()
+        # waits for the engine's stream AND reads the tcgen05 status flag: a search whose mbarrier wait timed out raises
+        # here instead of feeding invalid actions into the histories
+        self.engine.synchronize()
+        self.moves += 1
         actions = self.h_action.numpy().copy()
         for b, g in enumerate(self.games):
             if not live[b]:

@@ -111,3 +111,144 @@ def sharded_search(search_fn, observations, per_root_inputs, world_size, rank, g
             pieces.append(g[r].numpy()[:rhi - rlo])
         out[k] = numpy.concatenate(pieces, axis=0)
     return out, (lo, hi)
+
+
+class PackedGather:
+    """ONE collective per search for the root statistics of all ranks.
+
+    Every rank owns a contiguous block of roots (`shard_bounds`). The per-root result arrays of a rank
+    (e.g. visit counts int32 [n, A] and root values float64 [n]) live as VIEWS into one byte buffer
+    `[field 0 of max_local roots | field 1 of max_local roots | ...]` (8-byte aligned fields); the engine
+    writes its outputs straight into those views, a single `all_gather_into_tensor` of the byte buffers
+    moves everything, and `unpack` returns per-field arrays of all `num_roots` roots in root order.
+    Works on CUDA tensors over NCCL and on CPU tensors over gloo (the world-size-2 CPU test)."""
+
+    def __init__(self, fields, num_roots, world_size, rank, device):
+        import torch
+
+        self.torch = torch
+        self.B, self.world, self.rank = int(num_roots), int(world_size), int(rank)
+        self.lo, self.hi = shard_bounds(self.B, self.world, self.rank)
+        self.max_local = (self.B + self.world - 1) // self.world
+        self.fields = []
+        off = 0
+        for name, inner, dtype in fields:
+            inner = tuple(int(x) for x in inner)
+            n = self.max_local * int(numpy.prod(inner)) if inner else self.max_local
+            nbytes = n * torch.empty(0, dtype=dtype).element_size()
+            self.fields.append((name, inner, dtype, off, nbytes))
+            off += (nbytes + 7) & ~7
+        self.chunk = off
+        self.local_bytes = torch.zeros(self.chunk, dtype=torch.uint8, device=device)
+        self.all_bytes = torch.zeros(self.world * self.chunk, dtype=torch.uint8, device=device)
+        self.local = {name: self._view(self.local_bytes, o, nb, dt, inner) for name, inner, dt, o, nb in self.fields}
+
+    def _view(self, buf, off, nbytes, dtype, inner):
+        return buf[off:off + nbytes].view(dtype).reshape((self.max_local,) + inner)
+
+    def gather(self, group=None):
+        """The collective (asynchronous on the current CUDA stream for NCCL)."""
+        import torch.distributed as dist
+
+        if self.world == 1 or not (dist.is_available() and dist.is_initialized()):
+            self.all_bytes.copy_(self.local_bytes)
+        else:
+            dist.all_gather_into_tensor(self.all_bytes, self.local_bytes, group=group)
+        return self.all_bytes
+
+    def unpack(self, all_bytes=None):
+        """-> dict name -> tensor [num_roots, ...] in root order (views when the shards are equal)."""
+        torch = self.torch
+        buf = self.all_bytes if all_bytes is None else all_bytes
+        out = {}
+        for name, inner, dt, o, nb in self.fields:
+            parts = []
+            for r in range(self.world):
+                rlo, rhi = shard_bounds(self.B, self.world, r)
+                parts.append(self._view(buf[r * self.chunk:(r + 1) * self.chunk], o, nb, dt, inner)[:rhi - rlo])
+            out[name] = parts[0] if self.world == 1 else torch.cat(parts, 0)
+        return out
+
+
+class ShardedEngine:
+    """The multi-GPU product path: one process per GPU (torch.distributed, NCCL), each rank searches its
+    contiguous block of the `num_roots` roots on its own engine (own node pools, a full weight copy) and the
+    root statistics of all ranks are exchanged with ONE all-gather per search (PackedGather). Weights are
+    broadcast from rank `src`. There is no collective inside the simulation loop: roots are independent
+    (self_play.py:378).
+
+        se = ShardedEngine(cfg, num_roots=65536, max_simulations=200, device=torch.device("cuda", local_rank),
+                           state_dict=sd_on_rank0)
+        res = se.run_batch(200, observations=obs_local, noise=noise_local, tie_stream=tie_local)   # device tensors
+        res["visit_counts"]  # [65536, A] on every rank
+    """
+
+    def __init__(self, config, num_roots, max_simulations, device, state_dict=None, src=0, group=None, engine_cls=None):
+        import torch
+        import torch.distributed as dist
+        from .engine import Engine
+
+        self.torch, self.group = torch, group
+        on = dist.is_available() and dist.is_initialized()
+        self.world = dist.get_world_size(group) if on else 1
+        self.rank = dist.get_rank(group) if on else 0
+        self.device = torch.device(device)
+        self.config = config
+        self.num_roots = int(num_roots)
+        self.lo, self.hi = shard_bounds(self.num_roots, self.world, self.rank)
+        self.n_local = self.hi - self.lo
+        A = len(config.action_space)
+        self.A = A
+        sd = broadcast_state_dict(state_dict, self.device, src=src)
+        cls = Engine if engine_cls is None else engine_cls
+        self.engine = cls(config, max_roots=max(1, (self.num_roots + self.world - 1) // self.world),
+                          max_simulations=max_simulations, device=self.device.index or 0, state_dict=sd)
+        fields = [("visit_counts", (A,), torch.int32), ("root_value", (), torch.float64)]
+        self.pack = PackedGather(fields, self.num_roots, self.world, self.rank, self.device)
+        self._extra = {}
+
+    def refresh_weights(self, state_dict, src=0):
+        """Hot weight refresh on every rank: rank `src` passes the new state dict, the others None."""
+        self.engine.load_state_dict(broadcast_state_dict(state_dict, self.device, src=src))
+
+    def make_args(self, num_simulations, memory, inputs, extra_outputs=None, outputs_on_device=False, **kw):
+        """tsp_run_args whose visit_counts / root_value outputs are the packed gather buffer's views (DEVICE memory;
+        with HOST inputs pass outputs_on_device=True) -- or caller-given HOST outputs otherwise."""
+        outs = dict(extra_outputs or {})
+        from .engine import MEM_DEVICE
+        if memory == MEM_DEVICE or outputs_on_device:
+            outs["visit_counts"] = self.pack.local["visit_counts"]
+            outs["root_value"] = self.pack.local["root_value"]
+        return self.engine.make_args(self.n_local, num_simulations, memory, inputs, outs,
+                                     outputs_on_device=outputs_on_device, **kw)
+
+    def run_args(self, args, gather=True):
+        """Launch a prepared search on the engine's stream and (optionally) the one all-gather behind it."""
+        torch = self.torch
+        stream = torch.cuda.ExternalStream(self.engine.stream(), device=self.device)
+        with torch.cuda.stream(stream):
+            self.engine.run_raw(args)
+            if gather:
+                self.pack.gather(self.group)
+
+    def run_batch(self, num_simulations, observations, noise=None, tie_stream=None, chance_stream=None,
+                  legal_actions=None, num_legal=None, add_exploration_noise=True, gather=True):
+        """One sharded search over this rank's block of roots (DEVICE tensors [n_local, ...]); returns the
+        root statistics of ALL roots (device tensors) after synchronising the engine's stream."""
+        from .engine import MEM_DEVICE
+        ins = dict(observations=observations)
+        for k, v in (("noise", noise), ("tie_stream", tie_stream), ("chance_stream", chance_stream),
+                     ("legal_actions", legal_actions), ("num_legal", num_legal)):
+            if v is not None:
+                ins[k] = v
+        a = self.make_args(num_simulations, MEM_DEVICE, ins, add_exploration_noise=add_exploration_noise and noise is not None,
+                           tie_len=0 if tie_stream is None else int(tie_stream.shape[1]),
+                           chance_len=0 if chance_stream is None else int(chance_stream.shape[1]))
+        self.run_args(a, gather=gather)
+        self.engine.synchronize()
+        if not gather:
+            return {k: v[:self.n_local] for k, v in self.pack.local.items()}
+        return self.pack.unpack()
+
+    def close(self):
+        self.engine.close()
