@@ -158,7 +158,7 @@ typedef struct {
     int32_t search_smem_bytes;
     int32_t trees_per_cta;
     int32_t threads_per_cta;
-    int32_t search_kernel;         /* last search: 2 = tsp::search_tc_kernel (tcgen05, weights in tensor memory), 1 = tsp::search_fast_kernel (weights in shared memory), 0 = tsp::search_kernel */
+    int32_t search_kernel;         /* last search: 3 = tsp::search_tcs_kernel (tcgen05, weights streamed by TMA), 2 = tsp::search_tc_kernel (tcgen05, weights in tensor memory), 1 = tsp::search_fast_kernel (weights in shared memory), 0 = tsp::search_kernel */
 } tsp_stats;
 
 int tsp_abi_version(void);
@@ -221,6 +221,31 @@ int tsp_select_action(tsp_handle h, int32_t memory, int32_t B, const int32_t *vi
 /* replaces the policy target of GameHistory.store_search_statistics (self_play.py:570-585):
  * child_visits[B][A] = visit_count / max(sum of the root's visit counts, 1) in float64 */
 int tsp_search_statistics(tsp_handle h, int32_t memory, int32_t B, const int32_t *visit_counts, double *child_visits);
+
+/* The device-resident tree of one root of the latest tsp_run, for consumers that walk below the root's children
+ * (diagnose_model.py:156-185 recurses through node.children; SelfPlay itself only reads depth 1, which tsp_run returns).
+ * One fixed-size record per EXPANDED node ("block", id 0 = the root, ids in expansion order) holding the statistics of
+ * that node's children, i.e. exactly the fields of the reference's Node (self_play.py:506-522):
+ *   int32 visit[NC] | int32 child[NC] (block id of the expanded child, -1: not expanded) | float32 prior[NC] |
+ *   float32 reward[NC] | int32 parent | int32 aux (bits 0..7: slot in the parent; bits 8..: hidden-state slot of a state
+ *   node) | float64 value_sum[NC] (risk-sensitive: value),  NC = 5 (block_bytes 128) or 8 (256).
+ * Chance-node variants: node kinds alternate by depth (root = StateNode, its children = TransitionNodes whose slots
+ * are the futures z, ...). The root's own float64 priors and the action of each root slot come back in `info`.
+ * blocks: HOST [max_blocks][block_bytes] or NULL (query sizes only); hidden: HOST [max_hidden][H] hidden states by
+ * slot, or NULL (a search on fed network outputs keeps none: n_hidden == 0). Synchronises the engine's stream. */
+typedef struct tsp_tree_info {
+    int32_t n_blocks;        /* expanded nodes of this tree */
+    int32_t block_bytes;
+    int32_t num_children;    /* NC */
+    int32_t n_root;          /* children of the root (legal actions) */
+    int32_t root_visit;
+    int32_t n_hidden;        /* hidden-state slots in use */
+    double root_value_sum;   /* risk-sensitive: root.value */
+    double root_prior[8];
+    int32_t root_action[8];
+} tsp_tree_info;
+int tsp_export_tree(tsp_handle h, int32_t root_index, tsp_tree_info *info, void *blocks, int32_t max_blocks, float *hidden,
+                    int32_t max_hidden);
 
 int tsp_synchronize(tsp_handle h);
 int tsp_get_stats(tsp_handle h, tsp_stats *out);

@@ -271,7 +271,7 @@ def _tree_size(node):
 
 def run_reference(config, model, observation, legal_actions=None, noise=None, tie=None,
                   chance=None, add_exploration_noise=True, to_play=0, uniform_policy=False,
-                  policy_only=False, record=True, continuations=()):
+                  policy_only=False, record=True, continuations=(), keep_root=False):
     """Run the reference MCTS.run once; returns a dict of everything a consumer reads
     from `root` / `extra_info` plus the evaluation records.
 
@@ -346,4 +346,6 @@ def run_reference(config, model, observation, legal_actions=None, noise=None, ti
             out["records"] = [numpy.stack(r) if r else numpy.zeros((0, REC_WIDTH), numpy.float32) for r in phase_records]
         out["root_hidden"] = rec.root_hidden
         out["root_logits"] = rec.root_logits
+    if keep_root:
+        out["root"] = root  # the reference's own Node graph (oracle/make_golden_tree.py flattens it)
     return out

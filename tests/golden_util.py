@@ -12,9 +12,10 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
 def golden_names():
-    # (rootio.npz holds the root I/O format goldens of tests/test_rootio.py, not a search fixture)
+    # (rootio.npz holds the root I/O format goldens of tests/test_rootio.py, trees.npz the flattened Node graphs of
+    # tests/test_tree_export.py: not search fixtures)
     return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))
-                  if os.path.basename(p) != "rootio.npz")
+                  if os.path.basename(p) not in ("rootio.npz", "trees.npz"))
 
 
 class Golden:

@@ -340,6 +340,7 @@ def test_streamed_weights_fast_kernel_large_network(monkeypatch):
     """cross-merge (365 KB of search weights) on the fast kernel with the weights streamed from L2, both group
     shapes, forced also at a batch size where the dispatcher would pick the generic kernel."""
     monkeypatch.setenv("TSP_FORCE_WGLOBAL", "1")
+    monkeypatch.setenv("TSP_NO_TCS", "1")  # (the dispatcher's choice for this network is the streamed tcgen05 kernel)
     cfg = tsp.get_config("cross_merge_env", num_simulations=40)
     for lpt in ("16", "8"):
         monkeypatch.setenv("TSP_FAST_LPT", lpt)

@@ -8,7 +8,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libtsp_b200.so")
 SOURCES = [os.path.join(CSRC, "tsp_engine.cu")]
-HEADERS = [os.path.join(CSRC, h) for h in ("tsp_device.cuh", "tsp_fast.cuh", "tsp_tc.cuh", "tsp_rootio.cuh")] + [
+HEADERS = [os.path.join(CSRC, h) for h in ("tsp_device.cuh", "tsp_fast.cuh", "tsp_tc.cuh", "tsp_stream.cuh", "tsp_rootio.cuh")] + [
     os.path.join(os.path.dirname(_HERE), "include", "tsp.h")]
 
 NVCC_FLAGS = [

@@ -121,6 +121,13 @@ struct tsp_engine {
     bool has_tc = false;
     bool no_tc = false;   // TSP_NO_TC: keep the mma.sync kernels
     bool tc_nofold = false;  // TSP_TC_NOFOLD: evaluate the first reward layer as its own MMA on the un-normalised state
+    // streamed tcgen05 search MLP (tsp_stream.cuh): networks too large for tensor memory (cross-merge). fp16-split weight
+    // image in global memory (tiles in TMA order), bias / one-hot table, tile / epilogue tables, one tensor map per box height
+    TsSched tss{};
+    DevBuf ts_img, ts_ctab;
+    CUtensorMap ts_map[3]{};
+    bool has_tcs = false;
+    bool no_tcs = false;  // TSP_NO_TCS: keep the mma.sync kernels for these networks
     DevBuf blocks, hidden, hdr, rootprior, rootact, pbtable, phase;
     bool phase_timing = false;
     int blocks_per_tree = 0, hidden_per_tree = 0, max_iters = 0;
@@ -694,6 +701,201 @@ int build_tc(tsp_engine* e) {
     return TSP_OK;
 }
 
+// Streamed tcgen05 search MLP (tsp_stream.cuh): the weights of the recurrent inference as fp16-split tiles in TMA order
+// plus the tile / epilogue tables. Supported: the fully-connected MuZero network with one hidden layer in the dynamics
+// and in every head, 64 < H <= 256 (multiples of 64), dynamics hidden width <= 128 (multiples of 64), head widths
+// <= 32 (multiples of 16), no terminal head: the cross-merge network (games/cross_merge_env.py:112-118). Smaller
+// networks live in tensor memory (build_tc); anything else keeps the mma.sync kernels (e->has_tcs == false).
+typedef CUresult (*TspEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// v = v1 + v2 / 2048 (the same split the kernel applies to activations, tsp_stream.cuh)
+void ts_split_host(float v, __half& h1, __half& h2) {
+    h1 = __float2half_rn(v);
+    h2 = __float2half_rn((v - __half2float(h1)) * TS_SPLIT);
+}
+
+int build_tcs(tsp_engine* e) {
+    e->has_tcs = false;
+    const tsp_config& c = e->cfg;
+    if (c.variant != TSP_VARIANT_MUZERO || e->nc != 5 || c.mask_absorbing_states) return TSP_OK;
+    for (int m : {TSP_MLP_DYNAMICS, TSP_MLP_REWARD, TSP_MLP_POLICY, TSP_MLP_VALUE})
+        if (e->mlp[m].size() != 2) return TSP_OK;
+    const HostLayer &D1 = e->mlp[TSP_MLP_DYNAMICS][0], &D2 = e->mlp[TSP_MLP_DYNAMICS][1];
+    const HostLayer &R1 = e->mlp[TSP_MLP_REWARD][0], &R2 = e->mlp[TSP_MLP_REWARD][1];
+    const HostLayer &P1 = e->mlp[TSP_MLP_POLICY][0], &P2 = e->mlp[TSP_MLP_POLICY][1];
+    const HostLayer &V1 = e->mlp[TSP_MLP_VALUE][0], &V2 = e->mlp[TSP_MLP_VALUE][1];
+    const int H = c.encoding_size, A = c.num_actions;
+    const int DH = D1.out_dim, RH = R1.out_dim, PH = P1.out_dim, VH = V1.out_dim;
+    const int NR = R2.out_dim, NV = V2.out_dim;
+    if (H % 64 || H <= 64 || H > 256 || DH % 64 || DH > 128 || DH < 64) return TSP_OK;
+    if (RH % 16 || PH % 16 || VH % 16 || RH > 32 || PH > 32 || VH > 32 || RH < 16 || PH < 16 || VH < 16) return TSP_OK;
+    if (NR + NV + A > 32 || D1.in_dim != H + A || D2.out_dim != H || D2.in_dim != DH) return TSP_OK;
+    TsSched& ts = e->tss;
+    memset(&ts, 0, sizeof(ts));
+    // ---- B-operand arena: the gathered state X0 (K-major, LBO 144) shares its space with the normalised state XN (MN-major;
+    // X0 is dead once dynamics layer 1 has completed), then the dynamics hidden layer XD and the heads' hidden layers XH
+    // (policy at inputs [0, 32), value at [32, 64), reward at [64, 96)), all MN-major ----
+    auto mn_sbo = [](int K) { return (K / 8) * 128; };
+    const int x0_sbo = (H / 8) * 144, xn_sbo = mn_sbo(H);
+    int o = 0;
+    const int x0 = o; o += 16 * std::max(x0_sbo, xn_sbo);  // X1 image (8 groups of 8 trees) + X2 image
+    const int xd = o; o += 16 * mn_sbo(DH);
+    const int HK = 96;
+    const int xh = o; o += 16 * mn_sbo(HK);
+    ts.arena_bytes = (o + 127) & ~127;
+    ts.x0_off = x0; ts.x0_sbo = x0_sbo; ts.x0_lo = 8 * x0_sbo; ts.H = H;
+    // ---- out strip ----
+    ts.off_vl = 0; ts.off_rl = NV; ts.off_pl = NV + NR;
+    int pitch = NV + NR + A;
+    while (pitch % 32 != 8 && pitch % 32 != 24) ++pitch;
+    ts.out_pitch = pitch;
+    // ---- folded reward layer 1 (see build_tc): (Wr1 W2) d + (Wr1 b2 + br1), product in float64, rounded once ----
+    std::vector<float> FW((size_t)RH * DH), Fb((size_t)RH);
+    for (int r = 0; r < RH; ++r) {
+        for (int k = 0; k < DH; ++k) {
+            double acc = 0.0;
+            for (int h = 0; h < H; ++h) acc += (double)R1.W[(size_t)r * H + h] * (double)D2.W[(size_t)h * DH + k];
+            FW[(size_t)r * DH + k] = (float)acc;
+        }
+        double acc = R1.b[(size_t)r];
+        for (int h = 0; h < H; ++h) acc += (double)R1.W[(size_t)r * H + h] * (double)D2.b[(size_t)h];
+        Fb[(size_t)r] = (float)acc;
+    }
+    // ---- constant table ----
+    std::vector<float> ctab;
+    auto put = [&](const std::vector<float>& v, int n) {
+        const int at = (int)ctab.size();
+        for (int i = 0; i < n; ++i) ctab.push_back(v[(size_t)i]);
+        while (ctab.size() % 32) ctab.push_back(0.0f);
+        return at;
+    };
+    const int t_b1 = put(D1.b, DH);
+    std::vector<float> e1((size_t)A * 128, 0.0f);
+    for (int a = 0; a < A; ++a)
+        for (int r = 0; r < DH; ++r) e1[(size_t)a * 128 + r] = D1.W[(size_t)r * D1.in_dim + H + a];
+    const int t_e1 = put(e1, A * 128);
+    const int t_b2 = put(D2.b, H);
+    const int t_bf = put(Fb, RH);
+    std::vector<float> bpv(64, 0.0f);
+    for (int r = 0; r < PH; ++r) bpv[(size_t)r] = P1.b[(size_t)r];
+    for (int r = 0; r < VH; ++r) bpv[(size_t)(32 + r)] = V1.b[(size_t)r];
+    const int t_bpv = put(bpv, 64);
+    std::vector<float> bout(32, 0.0f);  // rows of the output tile: value | reward | policy == columns of the out strip
+    for (int r = 0; r < NV; ++r) bout[(size_t)(ts.off_vl + r)] = V2.b[(size_t)r];
+    for (int r = 0; r < NR; ++r) bout[(size_t)(ts.off_rl + r)] = R2.b[(size_t)r];
+    for (int r = 0; r < A; ++r) bout[(size_t)(ts.off_pl + r)] = P2.b[(size_t)r];
+    const int t_bo = put(bout, 32);
+    for (int i = 0; i < 128; ++i) ctab.push_back(0.0f);  // lanes past `rows` still form an address
+    if ((int)ctab.size() > TS_MAX_CTAB) return TSP_OK;
+    ts.ctab_floats = (int)ctab.size();
+    // ---- weight image: tiles of `rows` x 64 inputs, element (m, k) of a tile at ((m / 8) * 8 + k / 8) * 64 + (m % 8) * 8 + k % 8
+    // (K-major core matrices: LBO 128, SBO 1024); a tile is `rows` image rows of 128 bytes ----
+    std::vector<__half> img;
+    int n_tiles = 0, n_acc = 0;
+    bool overflow = false;
+    // W(m, k): weight of row m, input k of the layer group; rows x K
+    auto add_layer = [&](int rows_valid, int rows_box, int K, auto W, int b_off, int b_lo, int b_sbo, bool b_mn, int d_col) {
+        // one accumulator tile: K chunks of 64 inputs, per chunk the W1 tile then the W2 tile
+        for (int k0 = 0; k0 < K; k0 += 64) {
+            const int kw = std::min(64, K - k0);
+            for (int part = 0; part < 2; ++part) {
+                if (n_tiles >= TS_MAX_TILES) { overflow = true; return; }
+                TsTile& tl = ts.tile[n_tiles++];
+                tl.img_row = (int)(img.size() / 64);
+                tl.rows = (short)rows_box;
+                tl.ksteps = (short)(kw / 16);
+                const int lbo = b_mn ? 128 : 144;
+                tl.b_off = b_off + (k0 / 8) * lbo;
+                tl.b_lo = b_lo;
+                tl.b_sbo = b_sbo;
+                tl.b_lbo = (short)lbo;
+                tl.b_step = (short)((2 * lbo) >> 4);
+                tl.d_col = (short)d_col;
+                tl.kind = (char)part;
+                tl.first = (char)(k0 == 0 && part == 0);
+                tl.b_mn = (char)(b_mn ? 1 : 0);
+                tl.acc_done = (char)((k0 + 64 >= K && part == 1) ? n_acc + 1 : 0);
+                const size_t base = img.size();
+                img.resize(base + (size_t)rows_box * 64, __float2half_rn(0.0f));
+                for (int m = 0; m < rows_valid; ++m)
+                    for (int kk = 0; kk < kw; ++kk) {
+                        __half h1, h2;
+                        ts_split_host(W(m, k0 + kk), h1, h2);
+                        img[base + ((size_t)(m >> 3) * 8 + (kk >> 3)) * 64 + (m & 7) * 8 + (kk & 7)] = part == 0 ? h1 : h2;
+                    }
+            }
+        }
+    };
+    auto add_acc = [&](int d_col, int rows, int kind, int feat0, int dst, int dst_sbo, int cidx, int eidx, int e_ld) {
+        TsEpi& a = ts.acc[n_acc++];
+        a.d_col = (short)d_col; a.rows = (short)rows; a.kind = (short)kind; a.feat0 = (short)feat0;
+        a.dst = dst; a.dst_sbo = dst_sbo; a.dst_lo = 8 * dst_sbo; a.cidx = cidx; a.eidx = eidx; a.e_ld = e_ld;
+    };
+    auto box = [](int rows) { return rows > 64 ? 128 : (rows > 32 ? 64 : 32); };
+    // stage 0: dynamics layer 1 (the one-hot action input is a gathered row in the epilogue, models.py:236-243)
+    ts.stage_tile[0] = 0; ts.stage_acc[0] = 0;
+    add_layer(DH, box(DH), H, [&](int m, int k) { return D1.W[(size_t)m * D1.in_dim + k]; }, x0, ts.x0_lo, x0_sbo, false, 0);
+    add_acc(0, DH, 0, 0, xd, mn_sbo(DH), t_b1, t_e1, 128);
+    // stage 1: dynamics layer 2 -> the un-normalised next state in tiles of 128 features, then the folded reward layer 1
+    ts.stage_tile[1] = n_tiles; ts.stage_acc[1] = n_acc;
+    const int n_xs = (H + 127) / 128;
+    for (int t = 0; t < n_xs; ++t) {
+        const int rows = std::min(128, H - 128 * t);
+        add_layer(rows, box(rows), DH, [&](int m, int k) { return D2.W[(size_t)(128 * t + m) * DH + k]; }, xd, 8 * mn_sbo(DH), mn_sbo(DH),
+                  true, 128 * t);
+        add_acc(128 * t, rows, 1, 128 * t, x0, xn_sbo, t_b2 + 128 * t, -1, 0);
+    }
+    add_layer(RH, 32, DH, [&](int m, int k) { return FW[(size_t)m * DH + k]; }, xd, 8 * mn_sbo(DH), mn_sbo(DH), true, 256);
+    add_acc(256, RH, 0, 64, xh, mn_sbo(HK), t_bf, -1, 0);
+    // stage 2: policy layer 1 (rows 0..31) | value layer 1 (rows 32..63) on the normalised state
+    ts.stage_tile[2] = n_tiles; ts.stage_acc[2] = n_acc;
+    add_layer(64, 64, H, [&](int m, int k) {
+        if (m < 32) return m < PH ? P1.W[(size_t)m * H + k] : 0.0f;
+        return m - 32 < VH ? V1.W[(size_t)(m - 32) * H + k] : 0.0f;
+    }, x0, 8 * xn_sbo, xn_sbo, true, 384);
+    add_acc(384, 64, 0, 0, xh, mn_sbo(HK), t_bpv, -1, 0);
+    // stage 3: the three output layers as one block-diagonal layer over the 96 hidden inputs; rows == out-strip columns
+    ts.stage_tile[3] = n_tiles; ts.stage_acc[3] = n_acc;
+    add_layer(NV + NR + A, 32, HK, [&](int m, int k) {
+        if (m >= ts.off_pl) return (k < PH) ? P2.W[(size_t)(m - ts.off_pl) * PH + k] : 0.0f;
+        if (m >= ts.off_rl) return (k >= 64 && k - 64 < RH) ? R2.W[(size_t)(m - ts.off_rl) * RH + (k - 64)] : 0.0f;
+        return (k >= 32 && k - 32 < VH) ? V2.W[(size_t)m * VH + (k - 32)] : 0.0f;
+    }, xh, 8 * mn_sbo(HK), mn_sbo(HK), true, 256);
+    add_acc(256, NV + NR + A, 2, 0, 0, 0, t_bo, -1, 0);
+    ts.stage_tile[4] = n_tiles; ts.stage_acc[4] = n_acc;
+    if (overflow || n_acc > TS_MAX_ACC) return TSP_OK;
+    ts.n_tiles = n_tiles; ts.n_acc = n_acc;
+    ts.img_rows = (int)(img.size() / 64);
+    // ---- upload + tensor maps (cuTensorMapEncodeTiled through the runtime: no link against libcuda) ----
+    int rc;
+    if ((rc = ensure(e, e->ts_img, img.size() * sizeof(__half)))) return rc;
+    if ((rc = ensure(e, e->ts_ctab, ctab.size() * sizeof(float)))) return rc;
+    CK(e, cudaMemcpyAsync(e->ts_img.p, img.data(), img.size() * sizeof(__half), cudaMemcpyHostToDevice, e->stream));
+    CK(e, cudaMemcpyAsync(e->ts_ctab.p, ctab.data(), ctab.size() * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+    CK(e, cudaStreamSynchronize(e->stream));
+    TspEncodeTiled encode = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", (void**)&encode, cudaEnableDefault, &qres) != cudaSuccess || !encode)
+        return fail(e, TSP_ECUDA, "cuTensorMapEncodeTiled is not available from this driver (TMA weight streaming needs it)");
+    const cuuint64_t gdim[2] = {64, (cuuint64_t)ts.img_rows};
+    const cuuint64_t gstr[1] = {128};
+    const cuuint32_t estr[2] = {1, 1};
+    const int heights[3] = {128, 64, 32};
+    for (int i = 0; i < 3; ++i) {
+        const cuuint32_t bx[2] = {64, (cuuint32_t)heights[i]};
+        const CUresult cr = encode(&e->ts_map[i], CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, e->ts_img.p, gdim, gstr, bx, estr,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr != CUDA_SUCCESS) return fail(e, TSP_ECUDA, "cuTensorMapEncodeTiled failed (%d)", (int)cr);
+    }
+    if ((rc = ensure(e, e->tc_status, sizeof(int)))) return rc;
+    CK(e, cudaMemset(e->tc_status.p, 0, sizeof(int)));
+    e->has_tcs = true;
+    return TSP_OK;
+}
+
 // tcgen05 tables of the chance-node searches (MuZeroStochasticConcat, models.py:465-595): stages [0, 4) evaluate ONE future z
 // of a transition expansion (dynamics on [h | onehot(a) | onehot(z)] -> reward head on the un-normalised state (first
 // layer folded into the MMA of dynamics layer 2, see build_tc) -> min-max normalise; plus the transition prior head on h),
@@ -923,6 +1125,8 @@ int build_schedules(tsp_engine* e) {
             if (e->has_fast && (rc = lower_fast(e, fh, 1, 4))) return rc;
         }
         if ((rc = build_tc(e))) return rc;
+        e->has_tcs = false;
+        if (!e->has_tc && (rc = build_tcs(e))) return rc;
     } else {  // one future of MuZeroStochasticConcat.dynamics: models.py:520-595
         HSched hs;
         hs.in_dim = H;
@@ -1146,6 +1350,31 @@ int launch_tc(tsp_engine* e, const FastParams& p, const TcSched& ts) {
     return TSP_OK;
 }
 
+size_t tcs_smem(const TsSched& ts, int S) {
+    const size_t pb_n = (size_t)((S + 3) & ~1);
+    return pb_n * 16 + ((pb_n + 3) & ~(size_t)3) * 4 + (size_t)((ts.ctab_floats + 3) & ~3) * 4 + sizeof(TsCtl) + 256 +
+           (size_t)TS_NS * TS_SLOT + (size_t)ts.arena_bytes + (size_t)(TS_N * ts.out_pitch + TS_N + TS_N / 4 + TS_N * PATH_LEVELS) * 4;
+}
+
+// The search with the MLP on tcgen05 and the weights streamed by TMA (tsp_stream.cuh): 64 trees per CTA, one CTA per SM.
+int launch_tcs(tsp_engine* e, const FastParams& p) {
+    const TsSched& ts = e->tss;
+    const size_t smem = std::max(tcs_smem(ts, p.S_tab), (size_t)120 * 1024);
+    int rc = set_smem(e, search_tcs_kernel, smem);
+    if (rc) return rc;
+    const int grid = (p.B + TS_N - 1) / TS_N;
+    constexpr int THREADS = TS_N * 8 + TS_SERVICE_THREADS;
+    search_tcs_kernel<<<grid, THREADS, smem, e->stream>>>(p, ts, e->ts_map[0], e->ts_map[1], e->ts_map[2]);
+    CK(e, cudaGetLastError());
+    e->stats.kernel_launches++;
+    e->stats.search_ctas = grid;
+    e->stats.search_smem_bytes = (int)smem;
+    e->stats.trees_per_cta = TS_N;
+    e->stats.threads_per_cta = THREADS;
+    e->stats.search_kernel = 3;
+    return TSP_OK;
+}
+
 size_t tc_variant_smem(const TcSched& ts, int G, int S) {
     const size_t pb_n = (size_t)((S + 3) & ~1);
     return pb_n * 16 + ((pb_n + 3) & ~(size_t)3) * 4 + (size_t)((ts.ctab_floats + 3) & ~3) * 4 + 64 + 256 +
@@ -1218,6 +1447,12 @@ int launch_fast_any(tsp_engine* e, const SearchParams& sp) {
     p.sched_b = reinterpret_cast<const FastSched*>(e->fsched_dev[which][1].p);
     p.nf = sp.nf; p.K = sp.K; p.max_iters = sp.max_iters; p.chance = sp.chance;
     const int variant = e->cfg.variant, n_sched = variant == 0 ? 1 : 2;
+    if (variant == 0 && e->has_tcs && !e->no_tcs && !p.fed && !p.mask_absorbing && tcs_smem(e->tss, p.S_tab) <= 227 * 1024) {
+        // the MLP on tcgen05 with the weights streamed by TMA (tsp_stream.cuh)
+        p.tc_ctab = reinterpret_cast<const float*>(e->ts_ctab.p);
+        p.tc_status = reinterpret_cast<int*>(e->tc_status.p);
+        return launch_tcs(e, p);
+    }
     if (variant == 0 && e->has_tc && !e->no_tc && !p.fed && !p.mask_absorbing) {
         // the MLP on tcgen05 with the weights resident in tensor memory (tsp_tc.cuh)
         const TcSched& ts = e->tcs[which];
@@ -1287,6 +1522,9 @@ int launch_search_any(tsp_engine* e, const SearchParams& p_in) {
     if (e->nc == 5 && e->has_tc && !e->no_tc && !e->no_fast && e->finalized && e->cfg.variant == 0 && !p.fed && !p.mask_absorbing &&
         tc_smem(e->tcs[0], 2, p.S_tab) <= 227 * 1024 && tc_smem(e->tcs[1], 2, p.S_tab) <= 227 * 1024)
         return launch_fast_any(e, p);  // tcgen05 kernel (weights in tensor memory)
+    if (e->nc == 5 && e->has_tcs && !e->no_tcs && !e->no_fast && e->finalized && e->cfg.variant == 0 && !p.fed && !p.mask_absorbing &&
+        tcs_smem(e->tss, p.S_tab) <= 227 * 1024)
+        return launch_fast_any(e, p);  // tcgen05 kernel, weights streamed by TMA
     if (e->nc == 5 && e->has_tc && !e->no_tc && !e->no_fast && e->finalized && e->cfg.variant != 0 && !p.fed &&
         tc_variant_smem(e->tcs[0], 2, p.S_tab) <= 227 * 1024 && tc_variant_smem(e->tcs[1], 2, p.S_tab) <= 227 * 1024)
         return launch_fast_any(e, p);
@@ -1436,6 +1674,7 @@ int tsp_create(const tsp_config* cfg, tsp_handle* out) {
     if (const char* t = getenv("TSP_NO_FAST")) e->no_fast = atoi(t) != 0;
     if (const char* t = getenv("TSP_NO_WLO")) e->no_wlo = atoi(t) != 0;
     if (const char* t = getenv("TSP_NO_TC")) e->no_tc = atoi(t) != 0;
+    if (const char* t = getenv("TSP_NO_TCS")) e->no_tcs = atoi(t) != 0;
     if (const char* t = getenv("TSP_NO_OVERLAP")) e->no_overlap = atoi(t) != 0;
     if (const char* t = getenv("TSP_TC_NOFOLD")) e->tc_nofold = atoi(t) != 0;
     if (const char* t = getenv("TSP_NO_WGLOBAL")) e->no_wglobal = atoi(t) != 0;
@@ -1509,7 +1748,7 @@ int tsp_destroy(tsp_handle e) {
                       &e->s_legal, &e->s_nlegal, &e->s_noise, &e->s_tie, &e->s_chance, &e->s_fedroot, &e->s_fed,
                       &e->s_visits, &e->s_rootv, &e->s_cval, &e->s_cprior, &e->s_crew, &e->s_depth, &e->s_rpred,
                       &e->s_rhid, &e->s_nrec, &e->s_troot, &e->s_trace, &e->s_tdepth, &e->n_in, &e->n_act, &e->tc_img[0],
-                      &e->tc_img[1], &e->tc_ctab[0], &e->tc_ctab[1], &e->tc_status})
+                      &e->tc_img[1], &e->tc_ctab[0], &e->tc_ctab[1], &e->tc_status, &e->ts_img, &e->ts_ctab})
         release(*b);
     for (auto& b : e->n_o) release(b);
     for (auto& ev : e->ev)
@@ -1952,12 +2191,53 @@ int tsp_search_statistics(tsp_handle e, int32_t memory, int32_t B, const int32_t
 }
 
 // tcgen05 path: a bounded mbarrier wait timed out (an MMA commit never arrived) -- the results are invalid
+int tsp_export_tree(tsp_handle e, int32_t root_index, tsp_tree_info* info, void* blocks, int32_t max_blocks, float* hidden,
+                    int32_t max_hidden) {
+    if (!e || !info) return TSP_EINVAL;
+    if (root_index < 0 || root_index >= e->tree_roots)
+        return fail(e, TSP_EINVAL, "tsp_export_tree: root %d is not one of the %d trees of the latest search", root_index, e->tree_roots);
+    CK(e, cudaSetDevice(e->device));
+    CK(e, cudaStreamSynchronize(e->stream));
+    const size_t bb = e->nc == 5 ? sizeof(NodeBlock<5>) : sizeof(NodeBlock<8>);
+    TreeHeader h;
+    CK(e, cudaMemcpy(&h, reinterpret_cast<const TreeHeader*>(e->hdr.p) + root_index, sizeof(h), cudaMemcpyDeviceToHost));
+    memset(info, 0, sizeof(*info));
+    info->n_blocks = h.n_blocks;
+    info->block_bytes = (int32_t)bb;
+    info->num_children = e->nc;
+    info->n_root = h.n_root;
+    info->root_visit = h.root_visit;
+    info->root_value_sum = h.root_vsum;
+    // hidden-state slots: block id == slot (deterministic); one slot per future of every expanded transition + the root
+    // (a fed-network search keeps none: 0)
+    info->n_hidden = e->tree_fed ? 0 : (e->cfg.variant == 0 ? h.n_blocks : 1 + h.n_tgroups * e->cfg.n_futures);
+    CK(e, cudaMemcpy(info->root_prior, reinterpret_cast<const double*>(e->rootprior.p) + (size_t)root_index * GW, GW * sizeof(double),
+                     cudaMemcpyDeviceToHost));
+    CK(e, cudaMemcpy(info->root_action, reinterpret_cast<const int*>(e->rootact.p) + (size_t)root_index * GW, GW * sizeof(int),
+                     cudaMemcpyDeviceToHost));
+    if (blocks) {
+        if (max_blocks < h.n_blocks) return fail(e, TSP_EINVAL, "tsp_export_tree: %d blocks, room for %d", h.n_blocks, max_blocks);
+        CK(e, cudaMemcpy(blocks, reinterpret_cast<const unsigned char*>(e->blocks.p) + (size_t)root_index * e->blocks_per_tree * bb,
+                         (size_t)h.n_blocks * bb, cudaMemcpyDeviceToHost));
+    }
+    if (hidden && info->n_hidden > 0) {
+        if (max_hidden < info->n_hidden) return fail(e, TSP_EINVAL, "tsp_export_tree: %d hidden states, room for %d", info->n_hidden, max_hidden);
+        const size_t H = (size_t)e->cfg.encoding_size;
+        CK(e, cudaMemcpy(hidden, reinterpret_cast<const float*>(e->hidden.p) + (size_t)root_index * e->hidden_per_tree * H,
+                         (size_t)info->n_hidden * H * sizeof(float), cudaMemcpyDeviceToHost));
+    }
+    return TSP_OK;
+}
+
 static int check_tc_status(tsp_engine* e) {
-    if (!e->has_tc || !e->tc_status.p) return TSP_OK;
+    if ((!e->has_tc && !e->has_tcs) || !e->tc_status.p) return TSP_OK;
     int st = 0;
     CK(e, cudaMemcpy(&st, e->tc_status.p, sizeof(int), cudaMemcpyDeviceToHost));
     if (st) {  // report once: the flag is cleared so that later searches are judged on their own
         cudaMemset(e->tc_status.p, 0, sizeof(int));
+        if (st == 2)
+            return fail(e, TSP_ECUDA, "tcgen05 search kernel (streamed weights): an activation left the fp16-split range (|x| > 6e4); "
+                                      "the results of that search are invalid -- set TSP_NO_TCS=1 to search this network on the mma.sync kernels");
         return fail(e, TSP_ECUDA, "tcgen05 search kernel: mbarrier wait timed out (the results of that search are invalid)");
     }
     return TSP_OK;

@@ -436,24 +436,35 @@ __device__ __noinline__ void backup_walk(NodeBlock<5>* blocks, int cur, int cs, 
 
 }  // namespace tsp
 #include "tsp_tc.cuh"
+#include "tsp_stream.cuh"
 namespace tsp {
 
-// TC: the MLP runs on tcgen05 with the weights resident in tensor memory (tsp_tc.cuh); ts then points at the
-// kernel's TcSched parameter (constant bank).
-template <int G, int LPT, bool WG, bool TC>
-__device__ __forceinline__ void search_fast_body(const FastParams& p, const TcSched* __restrict__ tsp_) {
+// what the streamed tcgen05 path (TC == 2, tsp_stream.cuh) needs besides FastParams: all kernel parameters (constant bank)
+struct TsArgs {
+    const TsSched* ts;
+    const CUtensorMap *m128, *m64, *m32;  // weight image as boxes of 128 / 64 / 32 rows x 64 inputs
+};
+constexpr int TS_SERVICE_THREADS = 64;    // TC == 2: one TMA producer warp and one MMA issuer warp behind the tree threads
+
+// TC == 1: the MLP runs on tcgen05 with the weights resident in tensor memory (tsp_tc.cuh); ts then points at the
+// kernel's TcSched parameter (constant bank). TC == 2: tcgen05 with the weights streamed by TMA (tsp_stream.cuh): the
+// CTA's G * 16 = 64 trees evaluate the network in lock step, threads [THREADS, THREADS + 64) are the service warps.
+template <int G, int LPT, bool WG, int TC>
+__device__ __forceinline__ void search_fast_body(const FastParams& p, const TcSched* __restrict__ tsp_, const TsArgs* __restrict__ sx = nullptr) {
     extern __shared__ __align__(16) float smem[];
     constexpr int GTHREADS = GT * LPT;
     constexpr int THREADS = G * GTHREADS;
     static_assert(LPT == 8 || LPT == 16, "8 or 16 lanes per tree");
     static_assert(THREADS <= 512, "128 registers per thread");
+    static_assert(TC != 2 || (G * GT == TS_N && LPT == 8), "streamed path: 64 trees, 8 lanes per tree");
     constexpr int NC = 5;
     using Block = NodeBlock<NC>;
-    // shared-memory carve-out: schedule (compile-time offset 0), tables, weights, per-group strips
+    // shared-memory carve-out: schedule (compile-time offset 0; not on the streamed path), tables, weights, per-group strips
+    constexpr int SCHED_FLOATS = TC == 2 ? 0 : (int)(sizeof(FastSched) / 4);
     FastSched* fsp = reinterpret_cast<FastSched*>(smem);
     const int pb_n = (p.S_tab + 2 + 1) & ~1;  // S_tab: largest parent visit count (sums over continued searches)
     const int pbf_n = (pb_n + 3) & ~3;
-    double* pb = reinterpret_cast<double*>(smem + sizeof(FastSched) / 4);  // pb[N] = log((N + base + 1) / base) + init
+    double* pb = reinterpret_cast<double*>(smem + SCHED_FLOATS);  // pb[N] = log((N + base + 1) / base) + init
     double* sq = pb + pb_n;                                                // sq[N] = sqrt(N), host libm
     float* pbf = reinterpret_cast<float*>(sq + pb_n);                      // float32 pb[N] * sq[N] for the filter
     float* wsm = pbf + pbf_n;
@@ -498,7 +509,59 @@ __device__ __forceinline__ void search_fast_body(const FastParams& p, const TcSc
     [[maybe_unused]] int gw_u = 0;
     [[maybe_unused]] float4 hq[2];
     [[maybe_unused]] bool tc_ok = true;
-    if constexpr (TC) {
+    [[maybe_unused]] TsCtl* ts_ctl = nullptr;
+    [[maybe_unused]] bool ts_range_ok = true;
+    [[maybe_unused]] uint32_t ts_ring = 0;
+    if constexpr (TC == 2) {
+        // ---- streamed tcgen05 path: constant table, control block, weight ring, B-operand arena, out strip, row tables ----
+        const TsSched& tx = *sx->ts;
+        constexpr int ALL = THREADS + TS_SERVICE_THREADS;
+        const int ctab_n = (tx.ctab_floats + 3) & ~3;
+        ts_ctl = reinterpret_cast<TsCtl*>(wsm + ctab_n);  // 16-byte aligned: every table in front of it is a multiple of 16 bytes
+        const uint32_t base_s = smem_u32(smem);
+        const int goff = (int)(((base_s + (uint32_t)(reinterpret_cast<unsigned char*>(ts_ctl + 1) - reinterpret_cast<unsigned char*>(smem)) + 127u) & ~127u) - base_s);
+        unsigned char* gbase = reinterpret_cast<unsigned char*>(smem) + goff;  // TMA destinations: 128-byte aligned
+        ts_ring = base_s + (uint32_t)goff;
+        tc_arena = gbase + TS_NS * TS_SLOT;
+        tc_outs = reinterpret_cast<float*>(tc_arena + tx.arena_bytes);
+        row_action = reinterpret_cast<int*>(tc_outs + TS_N * tx.out_pitch);
+        row_active = reinterpret_cast<unsigned char*>(row_action + TS_N);
+        path = row_action + TS_N + TS_N / 4 + ((tid / LPT) & (TS_N - 1)) * PATH_LEVELS;
+        __builtin_assume(__isShared(tc_arena));
+        __builtin_assume(__isShared(tc_outs));
+        __builtin_assume(__isShared(row_action));
+        __builtin_assume(__isShared(path));
+        __builtin_assume(__isShared(ctab));
+        __builtin_assume(__isShared(ts_ctl));
+        gw_u = __shfl_sync(FULL, tid >> 5, 0);  // warp of the CTA, provably warp-uniform
+        for (int i = tid; i < tx.ctab_floats; i += ALL) wsm[i] = p.tc_ctab[i];
+        // zero arena: the padded inputs of an operand must be finite (their weights are zero)
+        for (int i = tid; i < (tx.arena_bytes >> 4); i += ALL) reinterpret_cast<uint4*>(tc_arena)[i] = make_uint4(0u, 0u, 0u, 0u);
+        if (tid == 0) {
+            for (int i = 0; i < TS_NS; ++i) {
+                asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&ts_ctl->full[i])));
+                asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&ts_ctl->empty[i])));
+            }
+            for (int i = 0; i < TS_MAX_ACC; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&ts_ctl->acc[i])));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&ts_ctl->bready)), "n"(THREADS / 32));
+            ts_ctl->abort = 0;
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        if (tid < TS_N) {
+            ts_ctl->mmk[0][tid][0] = INT_MAX; ts_ctl->mmk[0][tid][1] = INT_MIN;
+            ts_ctl->mmk[1][tid][0] = INT_MAX; ts_ctl->mmk[1][tid][1] = INT_MIN;
+            ts_ctl->hdst[tid] = 0ull;
+        }
+        if (gw_u == 0) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&ts_ctl->tmem_slot)), "n"(TS_TMEM_COLS));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        }
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        tmem_base = ts_ctl->tmem_slot;
+    } else if constexpr (TC == 1) {
         const int ctab_n = (ts.ctab_floats + 3) & ~3;
         unsigned long long* mbars = reinterpret_cast<unsigned long long*>(wsm + ctab_n);  // 8-byte aligned: ctab_n % 4 == 0
         uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbars + 4);
@@ -563,7 +626,7 @@ __device__ __forceinline__ void search_fast_body(const FastParams& p, const TcSc
     const int lane = tid & 31, j = tid % LPT;
     const int gl0 = lane & (32 - LPT);  // first lane of this tree inside the warp
     const int b = (blockIdx.x * G + grp) * GT + row;
-    const bool valid = b < p.B;
+    const bool valid = b < p.B && (TC != 2 || tid < THREADS);  // (the service warps of the streamed path own no tree)
     const int A = p.A, H = p.H;
     const double discount = p.discount;
 
@@ -604,7 +667,24 @@ __device__ __forceinline__ void search_fast_body(const FastParams& p, const TcSc
     __syncthreads();
     if constexpr (TC) tc_fence_after();
 
-    for (int it = 0; it < p.S; ++it) {
+    int n_it = p.S;
+    if constexpr (TC == 2) {
+        if (gw_u >= THREADS / 32) {  // service warps: the TMA producer and the MMA issuer of the whole search
+            n_it = 0;
+            bool ok = true;
+            if (elect_one()) {
+                const uint32_t full0 = smem_u32(&ts_ctl->full[0]), empty0 = smem_u32(&ts_ctl->empty[0]);
+                if (gw_u == THREADS / 32)
+                    ok = ts_producer(*sx->ts, sx->m128, sx->m64, sx->m32, ts_ring, full0, empty0, p.S, &ts_ctl->abort);
+                else
+                    ok = ts_issuer(*sx->ts, tmem_base, smem_u32(tc_arena), ts_ring, full0, empty0, smem_u32(&ts_ctl->acc[0]),
+                                   smem_u32(&ts_ctl->bready), p.S, &ts_ctl->abort);
+            }
+            __syncwarp();
+            tc_ok = ok;
+        }
+    }
+    for (int it = 0; it < n_it; ++it) {
         if (fed && n_rec >= p.max_rec) n_sims = p.S;  // fed records exhausted: stop this tree
         const bool active = valid && n_sims < p.S;
         long long tc0 = 0, tc1 = 0, tc2 = 0, tc3 = 0;
@@ -714,7 +794,35 @@ __device__ __forceinline__ void search_fast_body(const FastParams& p, const TcSc
 
         // ================= network evaluation of the group's 16 leaves =================
         float value = 0.0f, reward = 0.0f, terminal = -1.0f, prior = 0.0f;
-        if constexpr (TC) {
+        if constexpr (TC == 2) {
+            const TsSched& tx = *sx->ts;
+            const int n = tid / LPT;  // tree of the CTA == column of the MMAs
+            if (j == 0) {
+                row_action[n] = action;
+                row_active[n] = active ? 1 : 0;
+                // the new node's hidden state is written by the epilogue of the next-state tiles (no terminal head on this
+                // path: an active tree always expands, self_play.py:408-417)
+                ts_ctl->hdst[n] = active ? (unsigned long long)(hpool + (size_t)n_blocks * H) : 0ull;
+            }
+            if (active) {  // gather the parent's hidden state as the K-major B operand of the first dynamics layer
+                const float4* src = reinterpret_cast<const float4*>(hpool + (size_t)node * H);
+                unsigned char* d = tc_arena + tx.x0_off + (n >> 3) * tx.x0_sbo + (n & 7) * 16;
+                for (int c = j; c < (H >> 3); c += LPT) {
+                    const float4 u = src[2 * c], v = src[2 * c + 1];
+                    const float y[8] = {u.x, u.y, u.z, u.w, v.x, v.y, v.z, v.w};
+                    uint4 hi, lo;
+                    ts_split8(y, hi, lo);
+                    *reinterpret_cast<uint4*>(d + c * 144) = hi;
+                    *reinterpret_cast<uint4*>(d + c * 144 + tx.x0_lo) = lo;
+                }
+            }
+            if (p.phase_cycles && tid == 0) tc1 = tc2 = clock64();
+            tc_ok = ts_mlp<THREADS>(tx, ts_ctl, tmem_base, tc_arena, tc_outs, ctab, row_action, gw_u, lane, it, ts_range_ok, p.phase_cycles) && tc_ok;
+            if (p.phase_cycles && tid == 0) tc3 = clock64();
+            const float* o = tc_outs + n * tx.out_pitch;
+            decode_row<LPT, true>(o + tx.off_vl, o + tx.off_rl, o + tx.off_pl, p.support, A, p.uniform_policy != 0, j, value, reward,
+                                  prior);
+        } else if constexpr (TC == 1) {
             if (j == 0) {
                 row_action[row] = action;
                 row_active[row] = active ? 1 : 0;
@@ -810,7 +918,9 @@ __device__ __forceinline__ void search_fast_body(const FastParams& p, const TcSc
                     pblk->child[slot] = nb;
                     pblk->reward[slot] = reward;
                 }
-                if constexpr (TC) {  // hidden state of the new node: the normalised quads this lane produced
+                if constexpr (TC == 2) {
+                    // (the epilogue of the next-state tiles has written the hidden state of the new node, tsp_stream.cuh)
+                } else if constexpr (TC == 1) {  // hidden state of the new node: the normalised quads this lane produced
                     float4* dst = reinterpret_cast<float4*>(hpool + (size_t)nb * H);
 #pragma unroll
                     for (int q = 0; q < 2; ++q)
@@ -946,6 +1056,7 @@ __device__ __forceinline__ void search_fast_body(const FastParams& p, const TcSc
     }
     if constexpr (TC) {
         if (!tc_ok && p.tc_status) atomicExch(p.tc_status, 1);  // an MMA commit never arrived (bounded mbarrier wait)
+        if (!ts_range_ok && p.tc_status) atomicCAS(p.tc_status, 0, 2);  // an activation left the fp16 range of the streamed path
         tc_fence_before();
         __syncthreads();
         if (__shfl_sync(FULL, tid >> 5, 0) == 0)
@@ -955,14 +1066,23 @@ __device__ __forceinline__ void search_fast_body(const FastParams& p, const TcSc
 
 template <int G, int LPT, bool WG = false>
 __global__ void __launch_bounds__(G * GT * LPT, 512 / (G * GT * LPT)) search_fast_kernel(const __grid_constant__ FastParams p) {
-    search_fast_body<G, LPT, WG, false>(p, nullptr);
+    search_fast_body<G, LPT, WG, 0>(p, nullptr);
 }
 
 // The same search with the MLP on tcgen05 / TMEM (tsp_tc.cuh). One CTA per SM: it owns all 512 TMEM columns.
 template <int G, int LPT>
 __global__ void __launch_bounds__(G * GT * LPT, 1) search_tc_kernel(const __grid_constant__ FastParams p,
                                                                     const __grid_constant__ TcSched ts) {
-    search_fast_body<G, LPT, false, true>(p, &ts);
+    search_fast_body<G, LPT, false, 1>(p, &ts);
+}
+
+// The same search with the MLP on tcgen05 and the weights streamed by TMA (tsp_stream.cuh): 64 trees per CTA (8 lanes
+// per tree, 16 tree warps) + the TMA producer warp + the MMA issuer warp. One CTA per SM.
+__global__ void __launch_bounds__(TS_N * 8 + TS_SERVICE_THREADS, 1)
+search_tcs_kernel(const __grid_constant__ FastParams p, const __grid_constant__ TsSched ts, const __grid_constant__ CUtensorMap m128,
+                  const __grid_constant__ CUtensorMap m64, const __grid_constant__ CUtensorMap m32) {
+    const TsArgs sx{&ts, &m128, &m64, &m32};
+    search_fast_body<TS_N / GT, 8, false, 2>(p, nullptr, &sx);
 }
 
 // Per-thread view of the tcgen05 path's state (tsp_tc.cuh) and its set-up: constant table, mbarriers, the group's

@@ -1,0 +1,416 @@
+// tsp_stream.cuh -- the search MLP of 64 lock-stepped trees on tcgen05 with the weights STREAMED by TMA, used by
+// search_tcs_kernel for fully-connected MuZero networks whose search weights fit neither tensor memory nor shared
+// memory (cross-merge: games/cross_merge_env.py:112-118, H = 256, dynamics 261 -> 128 -> 256, heads 256 -> 32 -> n;
+// models.py:209-287).
+//
+// TRANSPOSED formulation like tsp_tc.cuh -- D^T[feature][tree] = W[feature][k] X^T[k][tree] -- with
+//   * N = 64: the 64 trees of the CTA are the MMA's N dimension and run the network evaluation in lock step;
+//   * A = weight tiles of <= 128 rows x 64 inputs (fp16, 16 KB), host-arranged in the K-major no-swizzle core-matrix
+//     order and streamed from global memory / L2 through a ring of TS_NS shared-memory slots by TMA
+//     (cp.async.bulk.tensor.2d + mbarrier complete_tx); one elected lane of a PRODUCER warp runs ahead of the MMAs by
+//     the depth of the ring, across layer and simulation boundaries;
+//   * B = the activations in shared memory: the gathered hidden state K-major (written by the trees' lanes, 16-byte
+//     chunks of 8 inputs, LBO = 144 against bank conflicts), every later operand MN-major (written by the epilogue,
+//     thread = feature, 16-byte chunks of 8 trees);
+//   * float32-level accuracy by the SCALED fp16 split on kind::f16 (K = 16 per MMA, half the MMAs of 3xTF32):
+//         v = v1 + v2 / 2048,  v1 = fp16(v),  v2 = fp16((v - v1) * 2048)          (22 significant bits)
+//         acc0 += W1 X1,  acc1 += W1 X2 + W2 X1,  D = acc0 + acc1 / 2048          (fp32 accumulators in TMEM)
+//     the dropped term W2 X2 / 2048^2 is 2^-22 relative (tools/tcs_gemm_test.cu: 5.8e-7 of max |D| at K = 256);
+//     activations beyond fp16's range (|x| > 6e4) raise the status flag instead of overflowing silently;
+//   * one elected lane of an ISSUER warp issues the MMAs of a tile when its slot is full (and, at a layer boundary, when
+//     all 16 tree warps have published the layer's B operand on an mbarrier), commits the slot back to the producer and
+//     the finished accumulator tile to the epilogue;
+//   * the 16 tree warps run the epilogues: warp w owns TMEM lane quarter w % 4 (32 features) and the trees
+//     16 (w / 4) .. + 15: tcgen05.ld, bias (+ the gathered one-hot action row of models.py:236-243), ELU, fp16 split,
+//     STS.128 of 8 trees. The next state is min-max normalised (models.py:248-255) in the accumulator's own layout:
+//     per-tree minimum / maximum by REDUX + shared-memory atomics on order-preserving integer keys, then a second pass
+//     over the accumulator writes the normalised state as the B operand of the prediction heads and straight into the
+//     hidden-state pool (thread = feature: a warp stores 128 contiguous bytes per tree).
+// Stages (cross-merge): dynamics 1 (8 tiles) -> dynamics 2 (+ the first reward layer folded in like tsp_tc.cuh: 12
+// tiles) -> policy 1 | value 1 (8 tiles) -> the three output layers as one block-diagonal K = 96 layer (4 tiles):
+// 32 tiles = 352 KB and 186 MMAs per simulation of 64 trees.
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cstdint>
+
+namespace tsp {
+
+constexpr int TS_N = 64;          // trees per CTA == N of every MMA
+constexpr int TS_NS = 4;          // ring slots
+constexpr int TS_SLOT = 16384;    // bytes per slot: 128 rows x 64 inputs fp16
+constexpr int TS_MAX_TILES = 40;
+constexpr int TS_MAX_ACC = 8;
+constexpr int TS_STAGES = 4;
+constexpr int TS_TMEM_COLS = 512;
+constexpr int TS_MAX_CTAB = 2048;  // floats: biases and one-hot rows
+constexpr float TS_SPLIT = 2048.0f, TS_INV_SPLIT = 1.0f / 2048.0f;
+constexpr float TS_FP16_MAX = 6.0e4f;
+
+struct TsTile {       // one weight tile: one ring slot fill and the MMAs that consume it
+    int img_row;      // first 128-byte row of the tile in the weight image (TMA coordinate)
+    short rows;       // 128 / 64 / 32 rows -> tensor map 0 / 1 / 2
+    short ksteps;     // K of the tile / 16, <= 4
+    int b_off;        // B operand (X1 image) at the tile's first input: byte offset in the arena
+    int b_lo;         // distance X1 -> X2 image of that operand
+    int b_sbo;        // bytes between 8-tree groups
+    short b_lbo;      // bytes between core matrices along K: 144 (K-major) or 128 (MN-major)
+    short b_step;     // descriptor units (16 bytes) per k-step
+    short d_col;      // accumulator: acc0 at d_col, acc1 at d_col + 64
+    char kind;        // 0: W1 tile (acc0 += W1 X1, acc1 += W1 X2), 1: W2 tile (acc1 += W2 X1)
+    char first;       // first tile of its accumulator: k-step 0 overwrites
+    char b_mn;        // B operand major: 0 K, 1 MN
+    char acc_done;    // 1 + index of the accumulator tile this tile completes, 0: none
+    short pad;
+};
+static_assert(sizeof(TsTile) == 32, "TsTile");
+struct TsEpi {        // one accumulator tile (128 TMEM lanes x {acc0, acc1} x 64 trees) and what its rows become
+    short d_col;
+    short rows;       // valid rows: lane quarter q holds rows 32 q .. 32 q + 31
+    short kind;       // 0: bias (+ one-hot action row) + ELU -> fp16 split -> B operand (MN-major)
+                      // 1: tile of the next state: bias, min-max normalised -> B operand + hidden-state pool
+                      // 2: raw float32 logits -> out strip [tree][column]
+    short feat0;      // input index k (kind 0, 1: of the destination operand) or out-strip column (kind 2) of row 0
+    int dst;          // destination operand (X1 image): byte offset in the arena; kind 2: unused
+    int dst_sbo;
+    int dst_lo;
+    int cidx;         // ctab offset of row 0's bias
+    int eidx;         // ctab offset of the one-hot action rows (row a at eidx + a * e_ld), -1: none
+    int e_ld;
+};
+static_assert(sizeof(TsEpi) == 32, "TsEpi");
+struct TsSched {
+    int n_tiles, n_acc, arena_bytes, out_pitch;
+    int off_vl, off_rl, off_pl, ctab_floats;
+    int x0_off, x0_sbo, x0_lo, H;       // gathered hidden state: K-major, LBO 144
+    int stage_tile[TS_STAGES + 1];      // tiles [stage_tile[s], stage_tile[s + 1]) read the B operand published before stage s
+    int stage_acc[TS_STAGES + 1];
+    int img_rows, pad;
+    TsTile tile[TS_MAX_TILES];
+    TsEpi acc[TS_MAX_ACC];
+};
+static_assert(sizeof(TsSched) <= 2048, "TsSched travels as a kernel parameter (constant bank: uniform reads)");
+
+// shared-memory control block of the streamed path
+struct TsCtl {
+    unsigned long long full[TS_NS], empty[TS_NS], acc[TS_MAX_ACC], bready;
+    uint32_t tmem_slot;
+    int abort;
+    int mmk[2][TS_N][2];                 // [simulation parity][tree]{min key, max key} of the next state
+    unsigned long long hdst[TS_N];       // where the hidden state of the tree's new node goes (0: nowhere)
+};
+
+__device__ __forceinline__ uint32_t ts_desc_lo(uint32_t saddr, uint32_t lbo) { return ((saddr & 0x3FFFF) >> 4) | ((lbo >> 4) << 16); }
+__device__ __forceinline__ uint32_t ts_desc_hi(uint32_t sbo) { return (sbo >> 4) | (1u << 14); }
+// D[tmem] (+)= A[smem descriptor] * B[smem descriptor], kind::f16 (fp16 operands, fp32 accumulate), M = 128, N = 64, K = 16
+__device__ __forceinline__ void ts_mma(uint32_t d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 ad, bd;\n\tsetp.ne.b32 p, %6, 0;\n\tmov.b64 ad, {%1, %2};\n\tmov.b64 bd, {%3, %4};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], ad, bd, %5, p;\n\t}\n" ::"r"(d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc)
+        : "memory");
+}
+constexpr uint32_t TS_IDESC = (1u << 4) | ((uint32_t)(TS_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);  // D f32, A / B f16, A K-major
+
+// Bounded wait that gives up at once when another thread of the CTA has already timed out (a lost TMA / commit must
+// neither hang the GPU nor stretch into minutes of serial time-outs).
+__device__ __forceinline__ bool ts_wait(uint32_t mbar, uint32_t parity, volatile int* abort) {
+    uint32_t done = 0;
+    for (int spin = 0; spin < (1 << 22); ++spin) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                     : "=r"(done) : "r"(mbar), "r"(parity) : "memory");
+        if (done) return true;
+        if ((spin & 255) == 255 && *abort) return false;
+    }
+    *abort = 1;
+    return false;
+}
+__device__ __forceinline__ void ts_arrive(uint32_t mbar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory"); }
+__device__ __forceinline__ void ts_commit(uint32_t mbar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
+}
+
+// TMA producer: one elected lane; the whole search (S simulations x n_tiles tiles) in ring order.
+__device__ __forceinline__ bool ts_producer(const TsSched& ts, const CUtensorMap* m128, const CUtensorMap* m64, const CUtensorMap* m32,
+                                            uint32_t ring, uint32_t full0, uint32_t empty0, int S, volatile int* abort) {
+    bool ok = true;
+    int g = 0;
+    for (int it = 0; it < S && ok; ++it)
+        for (int t = 0; t < ts.n_tiles; ++t, ++g) {
+            const int s = g & (TS_NS - 1);
+            if (g >= TS_NS) ok = ts_wait(empty0 + 8 * s, (uint32_t)(((g / TS_NS) - 1) & 1), abort) && ok;
+            const int rows = ts.tile[t].rows;
+            const CUtensorMap* mp = rows == 128 ? m128 : (rows == 64 ? m64 : m32);
+            const uint32_t dst = ring + s * TS_SLOT, mb = full0 + 8 * s;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(rows * 128) : "memory");
+            asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                         ::"r"(dst), "l"(mp), "r"(0), "r"(ts.tile[t].img_row), "r"(mb) : "memory");
+        }
+    return ok;
+}
+
+// MMA issuer: one elected lane.
+__device__ __forceinline__ bool ts_issuer(const TsSched& ts, uint32_t tmem, uint32_t arena_s, uint32_t ring, uint32_t full0,
+                                          uint32_t empty0, uint32_t acc0, uint32_t bready, int S, volatile int* abort) {
+    bool ok = true;
+    int g = 0;
+    uint32_t br = 0;
+    const uint32_t a_hi = ts_desc_hi(1024);  // A tile: core matrices of 8 rows x 8 inputs, 8 of them (64 inputs) per 8-row group
+    for (int it = 0; it < S && ok; ++it)
+        for (int st = 0; st < TS_STAGES; ++st) {
+            ok = ts_wait(bready, br, abort) && ok;  // all tree warps have published this stage's B operand
+            br ^= 1u;
+            tc_fence_after();
+            for (int t = ts.stage_tile[st]; t < ts.stage_tile[st + 1]; ++t, ++g) {
+                const TsTile& tl = ts.tile[t];
+                const int s = g & (TS_NS - 1);
+                ok = ts_wait(full0 + 8 * s, (uint32_t)((g / TS_NS) & 1), abort) && ok;
+                tc_fence_after();
+                const uint32_t a_lo = ts_desc_lo(ring + s * TS_SLOT, 128);
+                const uint32_t b1 = ts_desc_lo(arena_s + tl.b_off, (uint32_t)tl.b_lbo);
+                const uint32_t b2 = ts_desc_lo(arena_s + tl.b_off + tl.b_lo, (uint32_t)tl.b_lbo);
+                const uint32_t b_hi = ts_desc_hi((uint32_t)tl.b_sbo);
+                const uint32_t idesc = TS_IDESC | ((uint32_t)tl.b_mn << 16);
+                const uint32_t d = tmem + (uint32_t)tl.d_col, bstep = (uint32_t)tl.b_step;
+                const uint32_t fresh = tl.first ? 0u : 1u;
+                if (tl.kind == 0) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (j < tl.ksteps) {
+                            ts_mma(d, a_lo + 16 * j, a_hi, b1 + bstep * j, b_hi, idesc, j == 0 ? fresh : 1u);
+                            ts_mma(d + 64, a_lo + 16 * j, a_hi, b2 + bstep * j, b_hi, idesc, j == 0 ? fresh : 1u);
+                        }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (j < tl.ksteps) ts_mma(d + 64, a_lo + 16 * j, a_hi, b1 + bstep * j, b_hi, idesc, 1u);
+                }
+                ts_commit(empty0 + 8 * s);
+                if (tl.acc_done) ts_commit(acc0 + 8 * (tl.acc_done - 1));
+            }
+        }
+    return ok;
+}
+
+__device__ __forceinline__ void ts_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(taddr));
+}
+__device__ __forceinline__ void ts_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// v = v1 + v2 / 2048 for 8 trees of one feature -> two 16-byte chunks (MN-major core-matrix rows)
+__device__ __forceinline__ void ts_split8(const float (&y)[8], uint4& hi, uint4& lo) {
+    __half2 h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const __half a1 = __float2half_rn(y[2 * i]), b1 = __float2half_rn(y[2 * i + 1]);
+        const __half a2 = __float2half_rn((y[2 * i] - __half2float(a1)) * TS_SPLIT);
+        const __half b2 = __float2half_rn((y[2 * i + 1] - __half2float(b1)) * TS_SPLIT);
+        h[i] = __halves2half2(a1, b1);
+        l[i] = __halves2half2(a2, b2);
+    }
+    hi = make_uint4(*reinterpret_cast<uint32_t*>(&h[0]), *reinterpret_cast<uint32_t*>(&h[1]), *reinterpret_cast<uint32_t*>(&h[2]),
+                    *reinterpret_cast<uint32_t*>(&h[3]));
+    lo = make_uint4(*reinterpret_cast<uint32_t*>(&l[0]), *reinterpret_cast<uint32_t*>(&l[1]), *reinterpret_cast<uint32_t*>(&l[2]),
+                    *reinterpret_cast<uint32_t*>(&l[3]));
+}
+
+// Epilogue of one accumulator tile of kind 0 (hidden layer -> B operand) or 2 (logits -> out strip) by one tree warp:
+// lane quarter q, trees c0 .. c0 + 15, eight trees per round.
+__device__ __forceinline__ bool ts_epi_warp(const TsEpi& ep, uint32_t tmem_q, int q, int c0, int lane, unsigned char* __restrict__ arena,
+                                            float* __restrict__ outs, int out_pitch, const float* __restrict__ ctab,
+                                            const int* __restrict__ row_action, uint32_t accbar, uint32_t parity, volatile int* abort,
+                                            bool& range_ok) {
+    if (32 * q >= ep.rows) return true;  // this quarter holds no row of the tile (warp-uniform)
+    const int r = 32 * q + lane;
+    const bool on = r < ep.rows;
+    const float bias = on ? ctab[ep.cidx + r] : 0.0f;
+    const float* erow = ctab + ep.eidx + r;
+    const int e_ld = ep.e_ld;
+    const bool onehot = ep.eidx >= 0 && on;
+    const int k = ep.feat0 + r;
+    const bool ok = ts_wait(accbar, parity, abort);
+    tc_fence_after();
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int n0 = c0 + 8 * h;
+        uint32_t v0[8], v1[8];
+        ts_ld8(tmem_q + (uint32_t)(ep.d_col + n0), v0);
+        ts_ld8(tmem_q + (uint32_t)(ep.d_col + 64 + n0), v1);
+        float add[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) add[i] = bias;
+        if (onehot) {  // one-hot action input == one gathered weight row per tree (models.py:236-243)
+            const int4 a0 = *reinterpret_cast<const int4*>(row_action + n0), a1 = *reinterpret_cast<const int4*>(row_action + n0 + 4);
+            add[0] += erow[a0.x * e_ld]; add[1] += erow[a0.y * e_ld]; add[2] += erow[a0.z * e_ld]; add[3] += erow[a0.w * e_ld];
+            add[4] += erow[a1.x * e_ld]; add[5] += erow[a1.y * e_ld]; add[6] += erow[a1.z * e_ld]; add[7] += erow[a1.w * e_ld];
+        }
+        ts_ld_wait();
+        float y[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) y[i] = fmaf(__uint_as_float(v1[i]), TS_INV_SPLIT, __uint_as_float(v0[i])) + add[i];
+        if (!on) continue;
+        if (ep.kind == 2) {
+            float* o = outs + n0 * out_pitch + k;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i * out_pitch] = y[i];
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                y[i] = elu_fast(y[i]);
+                range_ok = range_ok && fabsf(y[i]) <= TS_FP16_MAX;
+            }
+            uint4 hi, lo;
+            ts_split8(y, hi, lo);
+            unsigned char* d = arena + ep.dst + (n0 >> 3) * ep.dst_sbo + k * 16;  // (k / 8) * 128 + (k % 8) * 16
+            *reinterpret_cast<uint4*>(d) = hi;
+            *reinterpret_cast<uint4*>(d + ep.dst_lo) = lo;
+        }
+    }
+    return ok;
+}
+
+// float <-> int with the same ordering (an involution)
+__device__ __forceinline__ int ts_key(float f) {
+    const int i = __float_as_int(f);
+    return i ^ ((i >> 31) & 0x7fffffff);
+}
+__device__ __forceinline__ float ts_unkey(int k) { return __int_as_float(k ^ ((k >> 31) & 0x7fffffff)); }
+
+// The network evaluation of the CTA's 64 leaves (models.py:233-257, 283-287); called by all 512 tree threads after
+// the hidden states have been gathered and ctl.hdst / row_action written. w: warp (provably uniform), it: simulation.
+template <int TREE_THREADS>
+__device__ __forceinline__ bool ts_mlp(const TsSched& ts, TsCtl* __restrict__ ctl, uint32_t tmem_base, unsigned char* __restrict__ arena,
+                                       float* __restrict__ outs, const float* __restrict__ ctab, const int* __restrict__ row_action, int w,
+                                       int lane, int it, bool& range_ok, unsigned long long* dbg) {
+    const int q = w & 3, c0 = 16 * (w >> 2);
+    const uint32_t tmem_q = tmem_base + ((uint32_t)(32 * q) << 16);
+    const uint32_t acc0 = smem_u32(&ctl->acc[0]), bready = smem_u32(&ctl->bready);
+    const uint32_t parity = (uint32_t)(it & 1);
+    volatile int* abort = &ctl->abort;
+    bool ok = true;
+    const bool tm = dbg && threadIdx.x == 0;
+    long long t0 = 0;
+    // the gathered hidden state is in place: publish it
+    fence_async_smem();
+    __syncwarp();
+    if (lane == 0) ts_arrive(bready);
+    for (int st = 0; st < TS_STAGES; ++st) {
+        if (tm) t0 = clock64();
+        const int a_begin = ts.stage_acc[st], a_end = ts.stage_acc[st + 1];
+        bool has_xs = false;
+        for (int a = a_begin; a < a_end; ++a) has_xs = has_xs || ts.acc[a].kind == 1;
+        if (has_xs) {  // (the next-state tiles are issued first: they are on the critical path)
+            // ---- pass 1: minimum / maximum of every tree's next state (models.py:248-250) ----
+            int kmn[16], kmx[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { kmn[i] = INT_MAX; kmx[i] = INT_MIN; }
+            for (int a = a_begin; a < a_end; ++a) {
+                const TsEpi& ep = ts.acc[a];
+                if (ep.kind != 1) continue;
+                ok = ts_wait(acc0 + 8 * a, parity, abort) && ok;
+                tc_fence_after();
+                if (32 * q >= ep.rows) continue;
+                const int r = 32 * q + lane;
+                const bool on = r < ep.rows;
+                const float bias = on ? ctab[ep.cidx + r] : 0.0f;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    uint32_t v0[8], v1[8];
+                    ts_ld8(tmem_q + (uint32_t)(ep.d_col + c0 + 8 * h), v0);
+                    ts_ld8(tmem_q + (uint32_t)(ep.d_col + 64 + c0 + 8 * h), v1);
+                    ts_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float y = fmaf(__uint_as_float(v1[i]), TS_INV_SPLIT, __uint_as_float(v0[i])) + bias;
+                        const int ky = ts_key(y);
+                        if (on) {
+                            kmn[8 * h + i] = min(kmn[8 * h + i], ky);
+                            kmx[8 * h + i] = max(kmx[8 * h + i], ky);
+                        }
+                    }
+                }
+            }
+            int mine = 0;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int rmn = __reduce_min_sync(FULL, kmn[i]), rmx = __reduce_max_sync(FULL, kmx[i]);
+                if (lane == i) mine = rmn;
+                if (lane == 16 + i) mine = rmx;
+            }
+            int (*mmk)[2] = ctl->mmk[it & 1];
+            if (lane < 16) atomicMin(&mmk[c0 + lane][0], mine);
+            else atomicMax(&mmk[c0 + lane - 16][1], mine);
+            asm volatile("bar.sync 1, %0;" ::"n"(TREE_THREADS) : "memory");
+            {   // the other parity's keys are free again: reset them for the next simulation
+                const int t = threadIdx.x;
+                if (t < TS_N) {
+                    ctl->mmk[(it + 1) & 1][t][0] = INT_MAX;
+                    ctl->mmk[(it + 1) & 1][t][1] = INT_MIN;
+                }
+            }
+            // ---- pass 2: normalise -> B operand of the prediction heads + hidden-state pool ----
+            for (int a = a_begin; a < a_end; ++a) {
+                const TsEpi& ep = ts.acc[a];
+                if (ep.kind != 1 || 32 * q >= ep.rows) continue;
+                const int r = 32 * q + lane;
+                const bool on = r < ep.rows;
+                const float bias = on ? ctab[ep.cidx + r] : 0.0f;
+                const int k = ep.feat0 + r;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int n0 = c0 + 8 * h;
+                    uint32_t v0[8], v1[8];
+                    ts_ld8(tmem_q + (uint32_t)(ep.d_col + n0), v0);
+                    ts_ld8(tmem_q + (uint32_t)(ep.d_col + 64 + n0), v1);
+                    float mn[8], inv[8];
+#pragma unroll
+                    for (int i = 0; i < 8; i += 2) {
+                        const int4 kk = *reinterpret_cast<const int4*>(&mmk[n0 + i][0]);
+                        mn[i] = ts_unkey(kk.x);
+                        mn[i + 1] = ts_unkey(kk.z);
+                        float s0 = __fsub_rn(ts_unkey(kk.y), mn[i]), s1 = __fsub_rn(ts_unkey(kk.w), mn[i + 1]);
+                        if (s0 < 1e-5f) s0 = __fadd_rn(s0, 1e-5f);  // scale += 1e-5 only where scale < 1e-5
+                        if (s1 < 1e-5f) s1 = __fadd_rn(s1, 1e-5f);
+                        inv[i] = __frcp_rn(s0);
+                        inv[i + 1] = __frcp_rn(s1);
+                    }
+                    ts_ld_wait();
+                    if (!on) continue;
+                    float y[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float x = fmaf(__uint_as_float(v1[i]), TS_INV_SPLIT, __uint_as_float(v0[i])) + bias;
+                        y[i] = __fmul_rn(__fsub_rn(x, mn[i]), inv[i]);
+                    }
+                    uint4 hi, lo;
+                    ts_split8(y, hi, lo);
+                    unsigned char* d = arena + ep.dst + (n0 >> 3) * ep.dst_sbo + k * 16;
+                    *reinterpret_cast<uint4*>(d) = hi;
+                    *reinterpret_cast<uint4*>(d + ep.dst_lo) = lo;
+#pragma unroll
+                    for (int i = 0; i < 8; i += 2) {
+                        const ulonglong2 hp = *reinterpret_cast<const ulonglong2*>(&ctl->hdst[n0 + i]);
+                        if (hp.x) reinterpret_cast<float*>(hp.x)[k] = y[i];
+                        if (hp.y) reinterpret_cast<float*>(hp.y)[k] = y[i + 1];
+                    }
+                }
+            }
+        }
+        for (int a = a_begin; a < a_end; ++a)
+            if (ts.acc[a].kind != 1)
+                ok = ts_epi_warp(ts.acc[a], tmem_q, q, c0, lane, arena, outs, ts.out_pitch, ctab, row_action, acc0 + 8 * a, parity, abort,
+                                 range_ok) && ok;
+        if (st + 1 < TS_STAGES) {  // this warp's share of the next stage's B operand is in place
+            fence_async_smem();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ts_arrive(bready);
+        }
+        if (tm) atomicAdd(dbg + 8 + 2 * st, (unsigned long long)(clock64() - t0));
+    }
+    tc_fence_before();
+    asm volatile("bar.sync 1, %0;" ::"n"(TREE_THREADS) : "memory");  // the logits of every tree are in the out strip
+    return ok;
+}
+
+}  // namespace tsp

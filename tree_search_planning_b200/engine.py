@@ -64,11 +64,28 @@ class Stats(ctypes.Structure):
 
 
 # every symbol include/tsp.h declares (tests check that the library exports each of them)
+class TreeInfo(ctypes.Structure):
+    """tsp_tree_info of include/tsp.h."""
+    _fields_ = [("n_blocks", ctypes.c_int32), ("block_bytes", ctypes.c_int32), ("num_children", ctypes.c_int32),
+                ("n_root", ctypes.c_int32), ("root_visit", ctypes.c_int32), ("n_hidden", ctypes.c_int32),
+                ("root_value_sum", ctypes.c_double), ("root_prior", ctypes.c_double * 8), ("root_action", ctypes.c_int32 * 8)]
+
+
+def tree_block_dtype(num_children):
+    """numpy view of one exported node block (tsp_export_tree; NodeBlock of csrc/tsp_device.cuh)."""
+    nc = int(num_children)
+    return numpy.dtype({"names": ["visit", "child", "prior", "reward", "parent", "aux", "value_sum"],
+                        "formats": [(numpy.int32, nc), (numpy.int32, nc), (numpy.float32, nc), (numpy.float32, nc),
+                                    numpy.int32, numpy.int32, (numpy.float64, nc)],
+                        "offsets": [0, 4 * nc, 8 * nc, 12 * nc, 16 * nc, 16 * nc + 4, 16 * nc + 8],
+                        "itemsize": 128 if nc == 5 else 256})
+
+
 ABI_SYMBOLS = (
     "tsp_abi_version", "tsp_create", "tsp_destroy", "tsp_last_error", "tsp_set_layer", "tsp_finalize_weights",
     "tsp_weight_arena", "tsp_run", "tsp_initial_inference", "tsp_recurrent_inference", "tsp_stochastic_dynamics",
     "tsp_prediction", "tsp_synchronize", "tsp_get_stats", "tsp_reset_timing", "tsp_debug_phase_cycles", "tsp_stream",
-    "tsp_stack_observations", "tsp_select_action", "tsp_search_statistics",
+    "tsp_stack_observations", "tsp_select_action", "tsp_search_statistics", "tsp_export_tree",
 )
 
 _lib = None
@@ -111,6 +128,7 @@ def load_library(path=None):
     lib.tsp_stack_observations.argtypes = [_P] + [ctypes.c_int32] * 5 + [_P] * 4
     lib.tsp_select_action.argtypes = [_P, ctypes.c_int32, ctypes.c_int32, _P, _P, _P, ctypes.c_double, _P, _P]
     lib.tsp_search_statistics.argtypes = [_P, ctypes.c_int32, ctypes.c_int32, _P, _P]
+    lib.tsp_export_tree.argtypes = [_P, ctypes.c_int32, ctypes.POINTER(TreeInfo), _P, ctypes.c_int32, _P, ctypes.c_int32]
     if path is None:
         _lib = lib
     return lib
@@ -377,6 +395,17 @@ class Engine:
         return out
 
     # -- misc ----------------------------------------------------------------------------------
+    def export_tree(self, root_index, want_hidden=True):
+        """The device-resident tree of one root of the latest search (tsp_export_tree): dict(info=TreeInfo,
+        blocks=structured array [n_blocks], hidden=[n_hidden, H] float32 or None)."""
+        info = TreeInfo()
+        self._check(self.lib.tsp_export_tree(self.handle, int(root_index), ctypes.byref(info), None, 0, None, 0))
+        blocks = numpy.zeros(info.n_blocks, tree_block_dtype(info.num_children))
+        hidden = numpy.zeros((info.n_hidden, self.H), numpy.float32) if want_hidden and info.n_hidden > 0 else None
+        self._check(self.lib.tsp_export_tree(self.handle, int(root_index), ctypes.byref(info), _ptr(blocks), info.n_blocks,
+                                             _ptr(hidden) if hidden is not None else None, info.n_hidden if hidden is not None else 0))
+        return dict(info=info, blocks=blocks, hidden=hidden)
+
     def synchronize(self):
         self._check(self.lib.tsp_synchronize(self.handle))
         self._keep = []

@@ -49,34 +49,105 @@ def _weights_fingerprint(model):
 
 
 class ChildView:
-    """What consumers read from `root.children[a]`: visit_count, prior, reward, value."""
+    """What consumers read from a node of the search tree: visit_count, prior, reward, value, children.
+    Depth 1 comes from the arrays tsp_run returns; `children` of deeper nodes (diagnose_model.py:156-185 recurses
+    through them) are built on first access from the device-resident tree (tsp_export_tree), which stays valid until
+    the next search on the same engine -- after that they read as {} like an unexpanded node."""
 
-    def __init__(self, visit_count, prior, reward, value, value_is_attribute):
+    def __init__(self, visit_count, prior, reward, value, value_is_attribute, tree=None, block=None, root_slot=None, depth=1):
         self.visit_count = int(visit_count)
         self.prior = float(prior)
         self.reward = float(reward)
-        self.children = {}  # deeper levels stay on the device
         self.hidden_state = None
         self.to_play = 0
         self._value = float(value)
+        # where this node's own children live: `tree` is a DeviceTree or a callable returning one (or None); `block` the
+        # node's block id (-1: not expanded), or None for a child of the root, whose block id the tree knows by `root_slot`
+        self._tree, self._block, self._root_slot, self._depth = tree, block, root_slot, depth
+        self._children = None
         if value_is_attribute:  # risk-sensitive nodes expose `.value` as an attribute
             self.value = self._value
 
+    def _resolve(self):
+        tree = self._tree() if callable(self._tree) else self._tree
+        if tree is None:
+            return None, -1
+        block = self._block
+        if block is None:
+            block = int(tree.blocks[0]["child"][self._root_slot])
+        return tree, block
+
+    @property
+    def children(self):
+        if self._children is None:
+            tree, block = self._resolve()
+            self._children = tree.children_of(block, self._depth) if tree is not None and block >= 0 else {}
+        return self._children
+
+    @children.setter
+    def children(self, value):
+        self._children = value
+
     def expanded(self):
-        return self.visit_count > 0
+        """self_play.py:516-517: a node is expanded once it has children -- a visited child that the search did not
+        expand (an absorbing state under mask_absorbing_states) stays unexpanded like in the reference."""
+        tree, block = self._resolve()
+        return block >= 0 if tree is not None else self.visit_count > 0
 
     def value(self):  # shadowed by the instance attribute in the risk-sensitive variant
         return self._value
 
 
+class DeviceTree:
+    """Host copy of one device-resident tree (Engine.export_tree) and the lazily built Node views below the root.
+    Block k holds the statistics of the children of expanded node k; in the chance-node variants node kinds alternate
+    by depth (even: StateNode, children keyed by action; odd: TransitionNode, children keyed by future z)."""
+
+    def __init__(self, exported, variant, num_actions, n_futures):
+        self.info, self.blocks, self.hidden = exported["info"], exported["blocks"], exported["hidden"]
+        self.variant, self.A, self.nf = variant, num_actions, max(int(n_futures), 1)
+
+    def children_of(self, block, depth):
+        """{action or future: ChildView} of the expanded node that owns `block`; `depth` is that node's depth."""
+        b = self.blocks[block]
+        transition = self.variant != 0 and (depth & 1) == 1  # a TransitionNode: its children are the futures z
+        if block == 0:
+            keys = [int(self.info.root_action[j]) for j in range(self.info.n_root)]
+        else:
+            keys = list(range(self.nf if transition else self.A))
+        out = {}
+        for slot, key in enumerate(keys):
+            visits, child = int(b["visit"][slot]), int(b["child"][slot])
+            vsum = float(b["value_sum"][slot])
+            prior = float(self.info.root_prior[slot]) if block == 0 else float(b["prior"][slot])
+            value = vsum if self.variant == 2 else (vsum / visits if visits > 0 else 0.0)
+            node = ChildView(visits, prior, float(b["reward"][slot]), value, self.variant == 2, tree=self, block=child,
+                             depth=depth + 1)
+            # hidden state: deterministic -- the expanded child's own block id is its slot; chance-node variants -- the
+            # StateNode children of a TransitionNode get theirs when the transition is expanded (slot 1 + ordinal * nf + z,
+            # self_play_stochastic.py:535-557), TransitionNodes carry none
+            hs = -1
+            if self.variant == 0:
+                hs = child
+            elif transition:
+                hs = 1 + (int(b["aux"]) >> 8) * self.nf + slot
+            if self.hidden is not None and 0 <= hs < len(self.hidden):
+                node.hidden_state = self.hidden[hs][None]
+            if child < 0:
+                node.to_play = -1  # self_play.py:508: set by expand
+            out[key] = node
+        return out
+
+
 class RootView(ChildView):
-    def __init__(self, res, i, legal_actions, variant, hidden_state=None):
+    def __init__(self, res, i, legal_actions, variant, hidden_state=None, tree=None):
         super().__init__(res["visit_counts"][i].sum() if "visit_counts" in res else 0, 0.0, 0.0,
-                         res["root_value"][i], variant == 2)
-        self.children = {
+                         res["root_value"][i], variant == 2, tree=tree, block=0, depth=0)
+        # depth 1 straight from the arrays of tsp_run (no export); deeper levels through `tree` on demand
+        self._children = {
             int(a): ChildView(res["visit_counts"][i][a], res["child_prior"][i][a], res["child_reward"][i][a],
-                              res["child_value"][i][a], variant == 2)
-            for a in legal_actions
+                              res["child_value"][i][a], variant == 2, tree=tree, block=None, root_slot=slot, depth=1)
+            for slot, a in enumerate(legal_actions)
         }
         self.hidden_state = hidden_state
 
@@ -95,12 +166,23 @@ class BatchResult(dict):
         self._generation = engine.generation if engine is not None else None
         self._resumed = resumed
         self._hidden = hidden  # root hidden states carried over a continued search
+        self._trees = {}       # root index -> DeviceTree (exported on demand)
+
+    def device_tree(self, i):
+        """Host copy of root i's whole tree (None once another search has run on the engine, or without an engine)."""
+        if self._engine is None or self._generation != self._engine.generation:
+            return self._trees.get(i)
+        if i not in self._trees:
+            cfg = self._engine.config
+            self._trees[i] = DeviceTree(self._engine.export_tree(i), self._variant, len(cfg.action_space),
+                                        getattr(cfg, "n_futures", 1) or 1)
+        return self._trees[i]
 
     def root(self, i):
         hid = self["root_hidden"][i][None] if "root_hidden" in self else None
         if hid is None and self._hidden is not None:
             hid = self._hidden[i][None]
-        r = RootView(self, i, self._legal[i], self._variant, hid)
+        r = RootView(self, i, self._legal[i], self._variant, hid, tree=(lambda: self.device_tree(i)) if self._engine is not None else None)
         r._batch, r._index = self, i  # lets MCTS.run(..., override_root_with=root) find the device-resident tree
         return r
 
