@@ -60,7 +60,13 @@ enum {
     TSP_MLP_POLICY = 4,         /* prediction_policy_network */
     TSP_MLP_VALUE = 5,          /* prediction_value_network */
     TSP_MLP_PRIOR = 6,          /* transition_prior_network (stochastic variants) */
-    TSP_NUM_MLP = 7
+    /* models.MuZeroStochastic (models.py:298-462): dynamics_encoded_state_network is a ModuleList with ONE MLP PER FUTURE,
+     * each on [h | onehot(a)]. Future 0 is TSP_MLP_DYNAMICS, futures 1..3 are the ids below; setting any of them selects
+     * the separate-heads network (n_futures of them must then be set, with equal shapes). */
+    TSP_MLP_DYNAMICS_F1 = 7,
+    TSP_MLP_DYNAMICS_F2 = 8,
+    TSP_MLP_DYNAMICS_F3 = 9,
+    TSP_NUM_MLP = 10
 };
 
 enum { TSP_MEM_HOST = 0, TSP_MEM_DEVICE = 1 };

@@ -43,6 +43,9 @@ CASES = [
     ("roundabout_s25_override_legal", "roundabout_env_ttc_flat", 25, 6, {"phases": 2, "legal": True, "mask": "adaptive"}, 13),
     ("risk_s25_override", "roundabout_env_ttc_flat_risk_sensitive", 25, 6, {"phases": 2, "legal": True}, 14),
     ("roundabout_s25_twoplayer_mask", "roundabout_env_ttc_flat", 25, 8, {"players": [0, 1], "mask": "adaptive", "legal": True}, 12),
+    # models.MuZeroStochastic: one dynamics MLP per future (models.py:298-462), 4 and 2 futures as in the game files
+    ("stochastic_sep_s25", "roundabout_env_ttc_flat_stochastic", 25, 8, {}, 15),
+    ("stochastic_sep_s25_legal", "highway_env_ttc_flat_stochastic", 25, 8, {"legal": True}, 16),
 ]
 
 

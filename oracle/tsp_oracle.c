@@ -14,6 +14,7 @@
  *   MuZeroFullyConnectedNetwork representation / dynamics /
  *     prediction / initial_inference / recurrent_inference   models.py:209-287
  *   MuZeroStochasticConcat dynamics / _dynamics              models.py:520-595
+ *   MuZeroStochastic (separate heads) dynamics / _dynamics    models.py:365-428
  *   mlp (Linear + ELU, identity output), support_to_scalar   models.py:1150-1162, 1180-1201
  *
  * Parity pinning: the reference has no tests or golden vectors for this path, so
@@ -42,7 +43,10 @@
 #define ORC_MAX_ACTIONS 32
 #define ORC_REC_WIDTH 16
 
-enum { ORC_REP = 0, ORC_DYN, ORC_REWARD, ORC_TERMINAL, ORC_POLICY, ORC_VALUE, ORC_PRIOR, ORC_NUM_MLP };
+/* ORC_DYN_F1.. : dynamics_encoded_state_network[z], z >= 1, of MuZeroStochastic (separate heads per future,
+ * models.py:334-345); z == 0 is ORC_DYN */
+enum { ORC_REP = 0, ORC_DYN, ORC_REWARD, ORC_TERMINAL, ORC_POLICY, ORC_VALUE, ORC_PRIOR, ORC_DYN_F1, ORC_DYN_F2, ORC_DYN_F3,
+       ORC_NUM_MLP };
 
 typedef struct {
     int n_layers;
@@ -224,14 +228,17 @@ static void net_initial(const orc_net *n, const float *obs, float *hidden, float
 static void net_dynamics(const orc_net *n, const float *h, int action, int future, float *next_hidden,
                          float *reward_scalar, float *terminal, float *reward_logits, orc_scratch *s) {
     const int H = n->cfg.encoding_size, A = n->cfg.num_actions;
-    const int nf = future >= 0 ? n->cfg.n_futures : 0;
+    /* MuZeroStochastic._dynamics (models.py:401-428): one dynamics MLP per future on [h | onehot(a)], no one-hot z */
+    const int separate = future >= 0 && n->mlp[ORC_DYN_F1].n_layers > 0;
+    const orc_mlp *dyn = (separate && future >= 1) ? &n->mlp[ORC_DYN_F1 + future - 1] : &n->mlp[ORC_DYN];
+    const int nf = (future >= 0 && !separate) ? n->cfg.n_futures : 0;
     float *x = (float *)malloc(sizeof(float) * (H + A + nf));
     float rl[2 * 64 + 1];
     memcpy(x, h, sizeof(float) * H);
     for (int i = 0; i < A + nf; ++i) x[H + i] = 0.0f;
     x[H + action] = 1.0f;
-    if (future >= 0) x[H + A + future] = 1.0f;
-    mlp_forward(&n->mlp[ORC_DYN], x, s->c, s->a, s->b);
+    if (nf > 0) x[H + A + future] = 1.0f;
+    mlp_forward(dyn, x, s->c, s->a, s->b);
     free(x);
     mlp_forward(&n->mlp[ORC_REWARD], s->c, rl, s->a, s->b);
     *reward_scalar = orc_support_to_scalar(rl, n->cfg.support_size);

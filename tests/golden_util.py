@@ -105,6 +105,24 @@ def quantised_columns(records, n_futures):
     return q
 
 
+def undisturbed_trees(got, want, n_futures, live=None, tol=1e-5, hard_tol=2e-3):
+    """[trees] bool: the two searches evaluated the same leaves in the same order. A flipped near-tie can swap the order of
+    two evaluations without changing a single visit count (sibling leaves with nearly equal outputs: two records then
+    differ by anything from 1e-5 to 1e-1 and the trees re-converge), so no threshold separates "same evaluation,
+    inaccurate network" from "other evaluation" record by record. What holds: entries that are not quantised sit at ~1e-7
+    on an undisturbed tree, so a tree counts as undisturbed iff ALL its prior / probability entries are within `tol` and
+    its value / reward entries within the quantisation step; callers bound the share of the others (a systematic network
+    error fails that bound), and tests/test_tree_export.py checks every expansion of the search kernels path-independently."""
+    a, b = numpy.asarray(got, numpy.float64), numpy.asarray(want, numpy.float64)
+    err = numpy.abs(a - b) / numpy.maximum(1.0, numpy.abs(b))
+    if live is not None:
+        err = err * numpy.broadcast_to(numpy.asarray(live, bool)[..., None], a.shape)
+    q = quantised_columns(want, n_futures)
+    plain = numpy.where(q, 0.0, err)
+    axes = tuple(range(1, a.ndim))
+    return (plain.max(axis=axes) <= tol) & (err.max(axis=axes) <= hard_tol)
+
+
 def assert_records_close(got, want, n_futures, live=None, tol=1e-5, min_fraction=0.97, hard_tol=2e-3, what="records"):
     """Column-wise tolerance for evaluation records: priors / probabilities / logits within `tol` on EVERY live entry;
     only the entries of `quantised_columns` get the quantisation allowance of assert_close_quantised."""

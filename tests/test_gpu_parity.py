@@ -12,7 +12,7 @@ import pytest
 torch = pytest.importorskip("torch")
 
 from golden_util import (Golden, golden_names, assert_tree_outputs_bit_exact, assert_close_quantised,  # noqa: E402
-                         assert_records_close)
+                         assert_records_close, undisturbed_trees)
 import tree_search_planning_b200 as tsp  # noqa: E402
 from oracle.oracle import Oracle  # noqa: E402  (the checker)
 
@@ -63,7 +63,9 @@ def drop_terminal(records, cfg):
 
 # Floors of the end-to-end visit-count agreement with the reference fixtures (fraction of the fixture's roots), pinned
 # just under what the B200 run measured (see the AGREE lines of profiles/r2_gpu_tests.log) so that a regression shows.
+# Measured: every fixture root agrees (1.0000 on all 18 fixtures); the kernels are deterministic, so the floor is "all".
 GOLDEN_FLOOR = {}
+GOLDEN_FLOOR_DEFAULT = 0.995
 
 
 def close(a, b, tol=1e-5):
@@ -92,27 +94,32 @@ def test_end_to_end_against_reference_golden(name):
     got, traces = engine_run(eng, g, fed=False, trace=True, want_root_hidden=True)
     got["trace_records"] = traces[-1]
     same = (got["visit_counts"] == g.out["visit_counts"]).all(axis=1)
-    assert same.mean() >= GOLDEN_FLOOR.get(name, 0.9), "visit counts differ on %d of %d roots" % ((~same).sum(), g.N)
+    assert same.mean() >= GOLDEN_FLOOR.get(name, GOLDEN_FLOOR_DEFAULT), "visit counts differ on %d of %d roots" % ((~same).sum(), g.N)
     st = eng.stats()
     print("AGREE golden %s %.4f kernel %d" % (name, same.mean(), st["search_kernel"]))
     # the fixtures inside the tcgen05 envelope must really run on the tcgen05 kernels (2: weights in tensor memory,
     # 3: weights streamed by TMA) -- this test must not silently stop covering them
-    if not getattr(g.config, "mask_absorbing_states", False):
+    # (outside: the terminal head of mask_absorbing_states, and MuZeroStochastic's one dynamics MLP per future)
+    if not getattr(g.config, "mask_absorbing_states", False) and getattr(g.config, "network", "") != "stochastic":
         assert st["search_kernel"] in (2, 3), (name, st["search_kernel"])
     assert close(got["root_hidden"], g.out["root_hidden"]).all()
     assert_close_quantised(got["trace_root"], g.out["root_record"], what="root record")
     assert_close_quantised(got["root_value"][same], g.out["root_value"][same], min_fraction=0.85, what="root value")
     assert_close_quantised(got["child_value"][same], g.out["child_value"][same], min_fraction=0.85, what="child value")
     assert close(got["child_prior"][same], g.out["child_prior"][same]).all()
-    for b in numpy.nonzero(same)[0]:
-        n = g.out["n_records"][b]
-        assert got["num_records"][b] == n
-        ref_rec = g.out["records"] if g.P == 1 else g.out["records"][-1]
-        assert_records_close(drop_terminal(got["trace_records"][b, :n], g.config),
-                             drop_terminal(ref_rec[b, :n], g.config), getattr(g.config, "n_futures", 1), what="records")
+    # every record of every agreeing tree at once: priors / probabilities within 1e-5 on each entry, value / reward entries
+    # within the quantisation step; the SHARE of quantised entries off by a step is judged over the whole fixture (a tree
+    # of 25 records has 50 of them: two steps -- ~1.3 % of the evaluations take one -- would already read as 4 %)
+    idx = numpy.nonzero(same)[0]
+    assert (got["num_records"][idx] == g.out["n_records"][idx]).all()
+    ref_rec = g.out["records"] if g.P == 1 else g.out["records"][-1]
+    m = min(got["trace_records"].shape[1], ref_rec.shape[1])
+    live = numpy.arange(m)[None, :] < g.out["n_records"][idx][:, None]
+    assert_records_close(drop_terminal(got["trace_records"][idx, :m], g.config), drop_terminal(ref_rec[idx, :m], g.config),
+                         getattr(g.config, "n_futures", 1), live=live, what="records")
 
 
-@pytest.mark.parametrize("name", ["highway_s25", "cross_merge_s200", "stochastic_s25"])
+@pytest.mark.parametrize("name", ["highway_s25", "cross_merge_s200", "stochastic_s25", "stochastic_sep_s25", "stochastic_sep_s25_legal"])
 def test_network_parity_against_torch_golden(name):
     g = Golden(name)
     eng = engine_for(g)
@@ -194,6 +201,8 @@ def seeded_inputs(cfg, B, S, seed, legal=False):
 
 
 def check_against_oracle(cfg, B, S, seed, legal=False, min_agree=0.985, **run_opts):
+    """`min_agree`: floor of the visit-count agreement AND 1 - ceiling of the share of disturbed trees. The BASELINE-size
+    tests pin it half a point under what the B200 run measured (AGREE lines of profiles/r2_gpu_tests.log)."""
     sd = random_state_dict(cfg, seed)
     eng = tsp.Engine(cfg, max_roots=B, max_simulations=S, state_dict=sd)
     orc = Oracle(cfg, sd)
@@ -222,7 +231,9 @@ def check_against_oracle(cfg, B, S, seed, legal=False, min_agree=0.985, **run_op
     err = numpy.abs(a - w) / numpy.maximum(1.0, numpy.abs(w))
     live = numpy.arange(a.shape[1])[None, :] < numpy.minimum(want["n_records"], got["num_records"])[:, None]
     err = err * live[:, :, None]
-    diverged = (err.max(axis=(1, 2)) > 2e-3) | (want["n_records"] != got["num_records"])
+    # trees whose evaluation order was disturbed by a flipped near-tie (golden_util.undisturbed_trees) are bounded, the
+    # others hold 1e-5 on every prior / probability entry
+    diverged = ~undisturbed_trees(a, w, getattr(cfg, "n_futures", 1), live=live) | (want["n_records"] != got["num_records"])
     assert diverged.mean() <= 1.0 - min_agree, "%.4f of the trees diverged" % diverged.mean()
     keep = ~diverged
     if keep.any():
@@ -238,22 +249,31 @@ def check_against_oracle(cfg, B, S, seed, legal=False, min_agree=0.985, **run_op
 
 def test_config2_roundabout_4096_roots_50_sims():
     cfg = tsp.get_config("roundabout_env_ttc_flat", num_simulations=50)
-    check_against_oracle(cfg, 4096, 50, seed=11)
+    check_against_oracle(cfg, 4096, 50, seed=11, min_agree=0.989)  # measured 0.9990 / 0.59 % disturbed
 
 
 def test_config3_stochastic_16384_roots():
     cfg = tsp.get_config("roundabout_env_ttc_flat_stochastic_concat")
-    check_against_oracle(cfg, 16384, 25, seed=12)
+    check_against_oracle(cfg, 16384, 25, seed=12, min_agree=0.994)  # measured 0.9998 / 0.05 % disturbed
 
 
 def test_config4_risk_sensitive_16384_roots():
     cfg = tsp.get_config("roundabout_env_ttc_flat_risk_sensitive")
-    check_against_oracle(cfg, 16384, 25, seed=13)
+    check_against_oracle(cfg, 16384, 25, seed=13, min_agree=0.994)  # measured 0.9999 / 0.02 % disturbed
+
+
+def test_separate_heads_stochastic_network():
+    """models.MuZeroStochastic (one dynamics MLP per future, models.py:298-462; 4 futures in
+    roundabout_env_ttc_flat_stochastic.py:66, 2 in highway_env_ttc_flat_stochastic.py)."""
+    cfg = tsp.get_config("roundabout_env_ttc_flat_stochastic")
+    check_against_oracle(cfg, 2048, 25, seed=41)
+    cfg = tsp.get_config("highway_env_ttc_flat_stochastic")
+    check_against_oracle(cfg, 777, 25, seed=42, legal=True, min_agree=0.97)
 
 
 def test_config5_cross_merge_200_sims_slice():
     cfg = tsp.get_config("cross_merge_env", num_simulations=200)
-    check_against_oracle(cfg, 1024, 200, seed=14, min_agree=0.9)
+    check_against_oracle(cfg, 1024, 200, seed=14, min_agree=0.96)  # measured 0.9980 / 3.1 % disturbed (200 simulations deep)
 
 
 def _full_size_properties(game, B, S, seed, monkeypatch, slice_roots=192):

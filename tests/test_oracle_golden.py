@@ -54,7 +54,7 @@ def _close(a, b, tol=1e-5):
     return numpy.abs(a - b) <= tol * numpy.maximum(1.0, numpy.abs(b))
 
 
-@pytest.mark.parametrize("name", ["highway_s25", "cross_merge_s200", "stochastic_s25"])
+@pytest.mark.parametrize("name", ["highway_s25", "cross_merge_s200", "stochastic_s25", "stochastic_sep_s25", "stochastic_sep_s25_legal"])
 def test_network_parity_batched(name):
     g = Golden(name)
     orc = Oracle(g.config, g.state_dict)

@@ -19,7 +19,7 @@ torch = pytest.importorskip("torch")
 import tree_search_planning_b200 as tsp  # noqa: E402
 from tree_search_planning_b200.synthetic import random_state_dict, synthetic_inputs  # noqa: E402
 from test_gpu_parity import check_against_oracle  # noqa: E402
-from golden_util import assert_records_close  # noqa: E402
+from golden_util import assert_records_close, undisturbed_trees  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 
@@ -46,10 +46,20 @@ def test_dispatch_runs_the_tcgen05_kernel(B, shape):
 
 
 def test_outside_the_envelope_keeps_the_mma_sync_kernels(monkeypatch):
-    for name, opts in (("roundabout_env_ttc_flat", dict(mask_absorbing_states=True)), ("cross_merge_env", {})):
+    for name, opts in (("roundabout_env_ttc_flat", dict(mask_absorbing_states=True)),
+                       ("cross_merge_env", dict(mask_absorbing_states=True)),
+                       ("roundabout_env_ttc_flat_stochastic", {})):  # terminal head; one dynamics MLP per future
         cfg = tsp.get_config(name, num_simulations=10, **opts)
         st, _ = search_kernel_of(cfg, 256, 10)
         assert st["search_kernel"] in (0, 1), name
+    # cross-merge (weights beyond tensor memory): tcgen05 with the weights streamed by TMA, unless switched off
+    cfg = tsp.get_config("cross_merge_env", num_simulations=10)
+    st, out = search_kernel_of(cfg, 256, 10)
+    assert st["search_kernel"] == 3 and (st["trees_per_cta"], st["threads_per_cta"]) == (64, 576)
+    assert (out["visit_counts"].sum(1) == 10).all()
+    st, _ = search_kernel_of(cfg, 256, 10, monkeypatch, TSP_NO_TCS="1")
+    assert st["search_kernel"] in (0, 1)
+    monkeypatch.delenv("TSP_NO_TCS")
     cfg = tsp.get_config("roundabout_env_ttc_flat", num_simulations=10)
     st, _ = search_kernel_of(cfg, 256, 10, monkeypatch, TSP_NO_TC="1")
     assert st["search_kernel"] == 1
@@ -67,8 +77,11 @@ def test_agrees_with_the_mma_sync_kernel(B, S, monkeypatch):
     b = mm["trace_records"][same].astype(numpy.float64)
     err = numpy.abs(a - b) / numpy.maximum(1.0, numpy.abs(b))
     assert numpy.median(err) <= 1e-6
-    # priors within 1e-5 on every entry; only value / reward get the quantisation allowance
-    assert_records_close(a, b, 1, what="tcgen05 vs mma.sync records")
+    # priors within 1e-5 on every entry of every tree whose evaluation order was not disturbed (golden_util.undisturbed_trees),
+    # and those are nearly all; only value / reward get the quantisation allowance
+    keep = undisturbed_trees(a, b, 1)
+    assert keep.mean() >= 0.98, keep.mean()
+    assert_records_close(a[keep], b[keep], 1, what="tcgen05 vs mma.sync records")
 
 
 @pytest.mark.parametrize("B", [2048, 8192])

@@ -50,10 +50,13 @@ def test_exported_tree_equals_the_reference_node_graph(name):
                 assert numpy.float64(r[3]) == w["prior"] and numpy.float64(r[4]) == w["reward"], (key, n, r, w)
             assert numpy.float64(r[5]) == w["value"] or (r[5] == 0 and w["value"] == 0), (key, n, r, w)
     # a later search on the engine invalidates the device tree: deeper levels then read as unexpanded, depth 1 stays
-    root = batch.root(0)
+    # (a tree exported BEFORE the next search is a host copy and stays readable: root 0 was walked above)
+    last = g.N - 1
+    root, root0 = batch.root(last), batch.root(0)
     eng.run(g.S, fed_root=g.out["root_record"], fed_records=g.out["records"], **g.run_kwargs())
-    assert [c.visit_count for c in root.children.values()] == [int(g.out["visit_counts"][0][a]) for a in legal[0]]
+    assert [c.visit_count for c in root.children.values()] == [int(g.out["visit_counts"][last][a]) for a in legal[last]]
     assert all(c.children == {} for c in root.children.values())
+    assert any(len(c.children) > 0 for c in root0.children.values())
     eng.close()
 
 
@@ -116,3 +119,46 @@ def test_device_tree_views_on_a_hand_built_tree():
     top = tree.children_of(0, 0)
     assert numpy.array_equal(top[3].hidden_state, hidden[1][None]) and top[1].hidden_state is None
     assert top[3].prior == 0.75 and top[3].value() == 0.75
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("game,B,S,kernel", [("cross_merge_env", 200, 120, 3), ("highway_env_ttc_flat", 4096, 50, 2),
+                                             ("highway_env_ttc_flat", 20000, 30, 2)])
+def test_every_expansion_of_the_search_kernel_against_the_oracle_network(game, B, S, kernel):
+    """Path-independent check of the network INSIDE the search kernels (tcgen05 with weights in tensor memory / streamed
+    by TMA): for every node the search expanded, the stored hidden state, reward and child priors must be what the
+    oracle's float32 network (models.py:233-257, 283-287) returns for (the parent's stored hidden state, the action) --
+    whatever order the two searches evaluated their leaves in. Hidden states and priors within 1e-5, the reward within
+    the quantum of the reference's float32 inverse transform."""
+    from oracle.oracle import Oracle
+    from tree_search_planning_b200.synthetic import random_state_dict, synthetic_inputs
+    cfg = tsp.get_config(game, num_simulations=S)
+    sd = random_state_dict(cfg, 21)
+    eng = tsp.Engine(cfg, max_roots=B, max_simulations=S, state_dict=sd)
+    obs, kw = synthetic_inputs(cfg, B, S, seed=22)
+    eng.run(S, observations=obs, **kw)
+    assert eng.stats()["search_kernel"] == kernel
+    A = len(cfg.action_space)
+    ph, act, ch, rew, pri = [], [], [], [], []
+    rng = numpy.random.default_rng(5)
+    for i in sorted(rng.choice(B, size=12, replace=False)):
+        t = eng.export_tree(int(i))
+        blocks, hidden, info = t["blocks"], t["hidden"], t["info"]
+        assert info.n_blocks == S + 1 and len(hidden) == S + 1  # one expansion per simulation (no terminal head)
+        for k in range(1, info.n_blocks):
+            parent, slot = int(blocks[k]["parent"]), int(blocks[k]["aux"]) & 0xFF
+            assert int(blocks[parent]["child"][slot]) == k
+            ph.append(hidden[parent]); ch.append(hidden[k])
+            act.append(int(info.root_action[slot]) if parent == 0 else slot)
+            rew.append(float(blocks[parent]["reward"][slot])); pri.append(blocks[k]["prior"][:A].copy())
+    want = Oracle(cfg, sd).recurrent_inference(numpy.stack(ph), numpy.array(act, numpy.int32))
+    lg = want["policy_logits"].astype(numpy.float32)
+    e = numpy.exp(lg - lg.max(axis=1, keepdims=True))
+    want_prior = e / e.sum(axis=1, keepdims=True)
+    err_h = numpy.abs(numpy.stack(ch) - want["hidden"]).max()
+    err_p = numpy.abs(numpy.stack(pri) - want_prior).max()
+    err_r = (numpy.abs(numpy.array(rew) - want["reward"]) / (1 + numpy.abs(want["reward"]))).max()
+    print("EXPANSIONS %s B=%d S=%d: %d nodes, max |hidden err| %.2e, max |prior err| %.2e, max reward err %.2e" % (
+        game, B, S, len(ph), err_h, err_p, err_r))
+    assert err_h <= 1e-5 and err_p <= 1e-5 and err_r <= 2e-4
+    eng.close()

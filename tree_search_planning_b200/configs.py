@@ -11,6 +11,9 @@ Sources (reference file:line):
       muzero-general/games/highway_env_ttc_flat.py:29-32,44-57,63,79-85,105
   roundabout_env_ttc_flat_stochastic_concat:
       muzero-general/games/roundabout_env_ttc_flat_stochastic_concat.py:30-33,45-55,60-68,82-87
+  roundabout_env_ttc_flat_stochastic / highway_env_ttc_flat_stochastic (MuZeroStochastic: one dynamics MLP per future):
+      muzero-general/games/roundabout_env_ttc_flat_stochastic.py:30-33,45-55,60-68,82-87
+      muzero-general/games/highway_env_ttc_flat_stochastic.py (same constants)
   roundabout_env_ttc_flat_risk_sensitive:
       muzero-general/games/roundabout_env_ttc_flat_risk_sensitive.py:30-33,45-55,60-69,83-88
   cross_merge_env (cfg "one"):
@@ -80,6 +83,34 @@ _PRESETS = {
         network="stochastic_concat",
         stochastic_dynamics=True,
         n_futures=2,
+        fc_prior_layers=[32],
+        fc_posterior_layers=[32],
+        observation_shape=(1, 1, _TTC_OBS),
+        support_size=10,
+        encoding_size=64,
+        fc_representation_layers=[64, 64, 32],
+        fc_dynamics_layers=[32],
+    ),
+    "highway_env_ttc_flat_stochastic": dict(
+        _COMMON,
+        name="highway_env_ttc_flat_stochastic",
+        network="stochastic",
+        stochastic_dynamics=True,
+        n_futures=2,
+        fc_prior_layers=[32],
+        fc_posterior_layers=[32],
+        observation_shape=(1, 1, _TTC_OBS),
+        support_size=10,
+        encoding_size=64,
+        fc_representation_layers=[64, 64, 32],
+        fc_dynamics_layers=[32],
+    ),
+    "roundabout_env_ttc_flat_stochastic": dict(
+        _COMMON,
+        name="roundabout_env_ttc_flat_stochastic",
+        network="stochastic",
+        stochastic_dynamics=True,
+        n_futures=4,
         fc_prior_layers=[32],
         fc_posterior_layers=[32],
         observation_shape=(1, 1, _TTC_OBS),

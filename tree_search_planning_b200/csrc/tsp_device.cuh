@@ -84,6 +84,9 @@ struct Schedule {
     int row_stride;  // floats per row strip, == 4 (mod 32): conflict-free LDS.128 across rows
     int in_dim;
     short off_in, off_hidden, off_pl, off_vl, off_rl, off_tl, off_tp, pad0;
+    int f_stride;    // MuZeroStochastic (one dynamics MLP per future, models.py:334-345): the weights of the transition
+                     // expansion of future z start z * f_stride floats further on (same layout per future); else 0
+    int pad1[3];
     Stage st[MAX_STAGES];
 };
 
@@ -754,7 +757,7 @@ __global__ void __launch_bounds__(TM * GW) net_kernel(const __grid_constant__ Ne
     __syncthreads();
     const int nz = (p.mode == 2) ? p.nf : 1;
     for (int z = 0; z < nz; ++z) {
-        if (!fed) run_schedule<TM, THREADS, false>(sc, p.W, act, row_action, row_active, p.A, z);
+        if (!fed) run_schedule<TM, THREADS, false>(sc, p.W + (size_t)z * sc.f_stride, act, row_action, row_active, p.A, z);
         if (valid && !fed) {
             const float* r = act + row * rs;
             const int V = 2 * p.support + 1;
@@ -1059,7 +1062,7 @@ __global__ void __launch_bounds__(TM * GW * XW) search_kernel(const __grid_const
                     if (j == 0 && row < TM) row_active[row] = (kind == 2) ? 1 : 0;
                     __syncthreads();
                     for (int z = 0; z < nf; ++z) {
-                        run_schedule<TM, THREADS, WSMEM>(sched_a, Wp, act, row_action, row_active, A, z);
+                        run_schedule<TM, THREADS, WSMEM>(sched_a, Wp + z * sched_a.f_stride, act, row_action, row_active, A, z);
                         if (kind == 2) {
                             const float* r = act + row * rs;
                             const float rw = support_to_scalar_group(r + sched_a.off_rl, p.support, j, gmask);

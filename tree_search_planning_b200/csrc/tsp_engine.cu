@@ -122,11 +122,13 @@ struct tsp_engine {
     bool no_tc = false;   // TSP_NO_TC: keep the mma.sync kernels
     bool tc_nofold = false;  // TSP_TC_NOFOLD: evaluate the first reward layer as its own MMA on the un-normalised state
     // streamed tcgen05 search MLP (tsp_stream.cuh): networks too large for tensor memory (cross-merge). fp16-split weight
-    // image in global memory (tiles in TMA order), bias / one-hot table, tile / epilogue tables, one tensor map per box height
+    // image in global memory (16 KB tiles in TMA order), bias / one-hot table, tile / epilogue tables, the image's tensor map
     TsSched tss{};
     DevBuf ts_img, ts_ctab;
-    CUtensorMap ts_map[3]{};
+    CUtensorMap ts_map{};
     bool has_tcs = false;
+    bool separate_heads = false;  // MuZeroStochastic: one dynamics MLP per future (TSP_MLP_DYNAMICS_F1..)
+    int f_stride = 0;             // floats between the per-future weight groups {dynamics z, reward, prior} of the arena
     bool no_tcs = false;  // TSP_NO_TCS: keep the mma.sync kernels for these networks
     DevBuf blocks, hidden, hdr, rootprior, rootact, pbtable, phase;
     bool phase_timing = false;
@@ -409,7 +411,7 @@ int pack_fast_arena(tsp_engine* e) {
     e->farena_floats = 0;
     const bool chance = c.variant != TSP_VARIANT_MUZERO;
     auto skipped = [&](int m) {
-        if (m == TSP_MLP_REPRESENTATION) return true;
+        if (m == TSP_MLP_REPRESENTATION || m >= TSP_MLP_DYNAMICS_F1) return true;
         if (m == TSP_MLP_PRIOR) return !chance;
         if (m == TSP_MLP_TERMINAL) return chance || !c.mask_absorbing_states;
         return false;
@@ -736,13 +738,16 @@ int build_tcs(tsp_engine* e) {
     memset(&ts, 0, sizeof(ts));
     // ---- B-operand arena: the gathered state X0 (K-major, LBO 144) shares its space with the normalised state XN (MN-major;
     // X0 is dead once dynamics layer 1 has completed), then the dynamics hidden layer XD and the heads' hidden layers XH
-    // (policy at inputs [0, 32), value at [32, 64), reward at [64, 96)), all MN-major ----
+    // (policy at inputs [0, 32), value at [32, 64), reward at [64, 96)), all MN-major. (Measured: letting XD and XH take
+    // turns in the same region as well -- folded reward tile issued first, its epilogue deferred -- frees 56 KB for an
+    // 8-slot ring, but the ring is not what limits the stream (shared-memory bandwidth is) and the longer critical path
+    // cost 8 %.) ----
     auto mn_sbo = [](int K) { return (K / 8) * 128; };
-    const int x0_sbo = (H / 8) * 144, xn_sbo = mn_sbo(H);
+    const int x0_sbo = (H / 8) * TS_X0_LBO, xn_sbo = mn_sbo(H);
+    const int HK = 96;
     int o = 0;
     const int x0 = o; o += 16 * std::max(x0_sbo, xn_sbo);  // X1 image (8 groups of 8 trees) + X2 image
     const int xd = o; o += 16 * mn_sbo(DH);
-    const int HK = 96;
     const int xh = o; o += 16 * mn_sbo(HK);
     ts.arena_bytes = (o + 127) & ~127;
     ts.x0_off = x0; ts.x0_sbo = x0_sbo; ts.x0_lo = 8 * x0_sbo; ts.H = H;
@@ -790,23 +795,25 @@ int build_tcs(tsp_engine* e) {
     for (int i = 0; i < 128; ++i) ctab.push_back(0.0f);  // lanes past `rows` still form an address
     if ((int)ctab.size() > TS_MAX_CTAB) return TSP_OK;
     ts.ctab_floats = (int)ctab.size();
-    // ---- weight image: tiles of `rows` x 64 inputs, element (m, k) of a tile at ((m / 8) * 8 + k / 8) * 64 + (m % 8) * 8 + k % 8
-    // (K-major core matrices: LBO 128, SBO 1024); a tile is `rows` image rows of 128 bytes ----
+    // ---- weight image: tiles of 16 KB = `rows` x KT inputs (128 x 64, 64 x 128 or 32 x 256), element (m, k) of a tile at
+    // ((m / 8) * (KT / 8) + k / 8) * 64 + (m % 8) * 8 + k % 8 (K-major core matrices: LBO 128, SBO 128 * KT / 8); a tile is
+    // 128 image rows of 128 bytes ----
     std::vector<__half> img;
     int n_tiles = 0, n_acc = 0;
     bool overflow = false;
     // W(m, k): weight of row m, input k of the layer group; rows x K
-    auto add_layer = [&](int rows_valid, int rows_box, int K, auto W, int b_off, int b_lo, int b_sbo, bool b_mn, int d_col) {
-        // one accumulator tile: K chunks of 64 inputs, per chunk the W1 tile then the W2 tile
-        for (int k0 = 0; k0 < K; k0 += 64) {
-            const int kw = std::min(64, K - k0);
+    auto add_layer = [&](int acc, int rows_valid, int rows_box, int K, auto W, int b_off, int b_lo, int b_sbo, bool b_mn, int d_col) {
+        // one accumulator tile: K chunks of KT inputs, per chunk the W1 tile then the W2 tile
+        const int KT = 8192 / rows_box;
+        for (int k0 = 0; k0 < K; k0 += KT) {
+            const int kw = std::min(KT, K - k0);
             for (int part = 0; part < 2; ++part) {
                 if (n_tiles >= TS_MAX_TILES) { overflow = true; return; }
                 TsTile& tl = ts.tile[n_tiles++];
                 tl.img_row = (int)(img.size() / 64);
-                tl.rows = (short)rows_box;
+                tl.a_sbo = (short)(128 * (KT / 8));
                 tl.ksteps = (short)(kw / 16);
-                const int lbo = b_mn ? 128 : 144;
+                const int lbo = b_mn ? 128 : TS_X0_LBO;
                 tl.b_off = b_off + (k0 / 8) * lbo;
                 tl.b_lo = b_lo;
                 tl.b_sbo = b_sbo;
@@ -816,54 +823,58 @@ int build_tcs(tsp_engine* e) {
                 tl.kind = (char)part;
                 tl.first = (char)(k0 == 0 && part == 0);
                 tl.b_mn = (char)(b_mn ? 1 : 0);
-                tl.acc_done = (char)((k0 + 64 >= K && part == 1) ? n_acc + 1 : 0);
+                tl.acc_done = (char)((k0 + KT >= K && part == 1) ? acc + 1 : 0);
                 const size_t base = img.size();
-                img.resize(base + (size_t)rows_box * 64, __float2half_rn(0.0f));
+                img.resize(base + 8192, __float2half_rn(0.0f));
                 for (int m = 0; m < rows_valid; ++m)
                     for (int kk = 0; kk < kw; ++kk) {
                         __half h1, h2;
                         ts_split_host(W(m, k0 + kk), h1, h2);
-                        img[base + ((size_t)(m >> 3) * 8 + (kk >> 3)) * 64 + (m & 7) * 8 + (kk & 7)] = part == 0 ? h1 : h2;
+                        img[base + ((size_t)(m >> 3) * (KT / 8) + (kk >> 3)) * 64 + (m & 7) * 8 + (kk & 7)] = part == 0 ? h1 : h2;
                     }
             }
         }
     };
-    auto add_acc = [&](int d_col, int rows, int kind, int feat0, int dst, int dst_sbo, int cidx, int eidx, int e_ld) {
-        TsEpi& a = ts.acc[n_acc++];
+    auto add_acc = [&](int idx, int d_col, int rows, int kind, int feat0, int dst, int dst_sbo, int cidx, int eidx, int e_ld) {
+        n_acc = std::max(n_acc, idx + 1);
+        TsEpi& a = ts.acc[idx];
         a.d_col = (short)d_col; a.rows = (short)rows; a.kind = (short)kind; a.feat0 = (short)feat0;
         a.dst = dst; a.dst_sbo = dst_sbo; a.dst_lo = 8 * dst_sbo; a.cidx = cidx; a.eidx = eidx; a.e_ld = e_ld;
     };
     auto box = [](int rows) { return rows > 64 ? 128 : (rows > 32 ? 64 : 32); };
-    // stage 0: dynamics layer 1 (the one-hot action input is a gathered row in the epilogue, models.py:236-243)
-    ts.stage_tile[0] = 0; ts.stage_acc[0] = 0;
-    add_layer(DH, box(DH), H, [&](int m, int k) { return D1.W[(size_t)m * D1.in_dim + k]; }, x0, ts.x0_lo, x0_sbo, false, 0);
-    add_acc(0, DH, 0, 0, xd, mn_sbo(DH), t_b1, t_e1, 128);
-    // stage 1: dynamics layer 2 -> the un-normalised next state in tiles of 128 features, then the folded reward layer 1
-    ts.stage_tile[1] = n_tiles; ts.stage_acc[1] = n_acc;
     const int n_xs = (H + 127) / 128;
+    const int A_D1 = 0, A_XS = 1, A_FOLD = 1 + n_xs, A_PV = 2 + n_xs, A_OUT = 3 + n_xs;
+    if (A_OUT >= TS_MAX_ACC) return TSP_OK;
+    // stage 0: dynamics layer 1 (the one-hot action input is a gathered row in the epilogue, models.py:236-243)
+    ts.stage_tile[0] = 0; ts.stage_acc[0] = A_D1;
+    add_layer(A_D1, DH, box(DH), H, [&](int m, int k) { return D1.W[(size_t)m * D1.in_dim + k]; }, x0, ts.x0_lo, x0_sbo, false, 0);
+    add_acc(A_D1, 0, DH, 0, 0, xd, mn_sbo(DH), t_b1, t_e1, 128);
+    // stage 1: dynamics layer 2 -> the un-normalised next state in tiles of 128 features (first: they are on the critical
+    // path), then the folded reward layer 1
+    ts.stage_tile[1] = n_tiles; ts.stage_acc[1] = A_XS;
     for (int t = 0; t < n_xs; ++t) {
         const int rows = std::min(128, H - 128 * t);
-        add_layer(rows, box(rows), DH, [&](int m, int k) { return D2.W[(size_t)(128 * t + m) * DH + k]; }, xd, 8 * mn_sbo(DH), mn_sbo(DH),
-                  true, 128 * t);
-        add_acc(128 * t, rows, 1, 128 * t, x0, xn_sbo, t_b2 + 128 * t, -1, 0);
+        add_layer(A_XS + t, rows, box(rows), DH, [&](int m, int k) { return D2.W[(size_t)(128 * t + m) * DH + k]; }, xd, 8 * mn_sbo(DH),
+                  mn_sbo(DH), true, 128 * t);
+        add_acc(A_XS + t, 128 * t, rows, 1, 128 * t, x0, xn_sbo, t_b2 + 128 * t, -1, 0);
     }
-    add_layer(RH, 32, DH, [&](int m, int k) { return FW[(size_t)m * DH + k]; }, xd, 8 * mn_sbo(DH), mn_sbo(DH), true, 256);
-    add_acc(256, RH, 0, 64, xh, mn_sbo(HK), t_bf, -1, 0);
+    add_layer(A_FOLD, RH, 32, DH, [&](int m, int k) { return FW[(size_t)m * DH + k]; }, xd, 8 * mn_sbo(DH), mn_sbo(DH), true, 256);
+    add_acc(A_FOLD, 256, RH, 0, 64, xh, mn_sbo(HK), t_bf, -1, 0);
     // stage 2: policy layer 1 (rows 0..31) | value layer 1 (rows 32..63) on the normalised state
-    ts.stage_tile[2] = n_tiles; ts.stage_acc[2] = n_acc;
-    add_layer(64, 64, H, [&](int m, int k) {
+    ts.stage_tile[2] = n_tiles; ts.stage_acc[2] = A_PV;
+    add_layer(A_PV, 64, 64, H, [&](int m, int k) {
         if (m < 32) return m < PH ? P1.W[(size_t)m * H + k] : 0.0f;
         return m - 32 < VH ? V1.W[(size_t)(m - 32) * H + k] : 0.0f;
     }, x0, 8 * xn_sbo, xn_sbo, true, 384);
-    add_acc(384, 64, 0, 0, xh, mn_sbo(HK), t_bpv, -1, 0);
+    add_acc(A_PV, 384, 64, 0, 0, xh, mn_sbo(HK), t_bpv, -1, 0);
     // stage 3: the three output layers as one block-diagonal layer over the 96 hidden inputs; rows == out-strip columns
-    ts.stage_tile[3] = n_tiles; ts.stage_acc[3] = n_acc;
-    add_layer(NV + NR + A, 32, HK, [&](int m, int k) {
+    ts.stage_tile[3] = n_tiles; ts.stage_acc[3] = A_OUT;
+    add_layer(A_OUT, NV + NR + A, 32, HK, [&](int m, int k) {
         if (m >= ts.off_pl) return (k < PH) ? P2.W[(size_t)(m - ts.off_pl) * PH + k] : 0.0f;
         if (m >= ts.off_rl) return (k >= 64 && k - 64 < RH) ? R2.W[(size_t)(m - ts.off_rl) * RH + (k - 64)] : 0.0f;
         return (k >= 32 && k - 32 < VH) ? V2.W[(size_t)m * VH + (k - 32)] : 0.0f;
-    }, xh, 8 * mn_sbo(HK), mn_sbo(HK), true, 256);
-    add_acc(256, NV + NR + A, 2, 0, 0, 0, t_bo, -1, 0);
+    }, xh, 8 * mn_sbo(HK), mn_sbo(HK), true, 0);
+    add_acc(A_OUT, 0, NV + NR + A, 2, 0, 0, 0, t_bo, -1, 0);
     ts.stage_tile[4] = n_tiles; ts.stage_acc[4] = n_acc;
     if (overflow || n_acc > TS_MAX_ACC) return TSP_OK;
     ts.n_tiles = n_tiles; ts.n_acc = n_acc;
@@ -882,14 +893,11 @@ int build_tcs(tsp_engine* e) {
     const cuuint64_t gdim[2] = {64, (cuuint64_t)ts.img_rows};
     const cuuint64_t gstr[1] = {128};
     const cuuint32_t estr[2] = {1, 1};
-    const int heights[3] = {128, 64, 32};
-    for (int i = 0; i < 3; ++i) {
-        const cuuint32_t bx[2] = {64, (cuuint32_t)heights[i]};
-        const CUresult cr = encode(&e->ts_map[i], CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, e->ts_img.p, gdim, gstr, bx, estr,
-                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (cr != CUDA_SUCCESS) return fail(e, TSP_ECUDA, "cuTensorMapEncodeTiled failed (%d)", (int)cr);
-    }
+    const cuuint32_t bx[2] = {64, 128};  // one box == one 16 KB tile
+    const CUresult cr = encode(&e->ts_map, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, e->ts_img.p, gdim, gstr, bx, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) return fail(e, TSP_ECUDA, "cuTensorMapEncodeTiled failed (%d)", (int)cr);
     if ((rc = ensure(e, e->tc_status, sizeof(int)))) return rc;
     CK(e, cudaMemset(e->tc_status.p, 0, sizeof(int)));
     e->has_tcs = true;
@@ -1074,7 +1082,7 @@ int build_schedules(tsp_engine* e) {
     const int V = 2 * c.support_size + 1;
     int rc;
     if ((rc = check_io(TSP_MLP_REPRESENTATION, c.obs_dim, H, "representation"))) return rc;
-    if ((rc = check_io(TSP_MLP_DYNAMICS, H + A + (stochastic ? c.n_futures : 0), H, "dynamics"))) return rc;
+    if ((rc = check_io(TSP_MLP_DYNAMICS, H + A + (stochastic && !e->separate_heads ? c.n_futures : 0), H, "dynamics"))) return rc;
     if ((rc = check_io(TSP_MLP_REWARD, H, V, "reward"))) return rc;
     if ((rc = check_io(TSP_MLP_POLICY, H, A, "policy"))) return rc;
     if ((rc = check_io(TSP_MLP_VALUE, H, V, "value"))) return rc;
@@ -1131,17 +1139,21 @@ int build_schedules(tsp_engine* e) {
         HSched hs;
         hs.in_dim = H;
         hs.in_buf = hs.new_buf(H, 0);
-        const int raw = add_chain(e, hs, TSP_MLP_DYNAMICS, hs.in_buf, 2);
+        // (separate heads: [h | onehot(a)] into the dynamics MLP of future z, whose weights sit z * f_stride further on)
+        const int raw = add_chain(e, hs, TSP_MLP_DYNAMICS, hs.in_buf, e->separate_heads ? 1 : 2);
         hs.rl = add_chain(e, hs, TSP_MLP_REWARD, raw, 0);
         hs.hidden = add_normalise(hs, raw, H);
         hs.tp = add_chain(e, hs, TSP_MLP_PRIOR, hs.in_buf, 0);
         if ((rc = lower(e, hs, e->sch_trans, true))) return rc;
+        e->sch_trans.f_stride = e->separate_heads ? e->f_stride : 0;
         e->has_trans = true;
         // the search kernel addresses both schedules with one row stride
         const int rs = std::max(e->sch_trans.row_stride, e->sch_pred.row_stride);
         e->sch_trans.row_stride = rs;
         e->sch_pred.row_stride = rs;
-        if (e->nc == 5 && e->farena_floats > 0 && H % 16 == 0) {  // the chance-node searches on the fast kernel's structure
+        e->has_fast = false;
+        // (the separate-heads network runs on the generic kernel: the fast / tcgen05 tables hold one dynamics MLP)
+        if (e->nc == 5 && e->farena_floats > 0 && H % 16 == 0 && !e->separate_heads) {  // the chance-node searches on the fast kernel's structure
             HSched hp;
             hp.in_dim = H;
             hp.in_buf = hp.new_buf(H, 0);
@@ -1166,7 +1178,8 @@ int build_schedules(tsp_engine* e) {
             }
             e->has_fast = ok;
         }
-        if ((rc = build_tc_variant(e))) return rc;
+        e->has_tc = false;
+        if (!e->separate_heads && (rc = build_tc_variant(e))) return rc;
     }
     for (Schedule* s : {&e->sch_root, &e->sch_pred, &e->sch_recur, &e->sch_trans})
         if (s->n_stages && s->off_in != 0) return fail(e, TSP_EINVAL, "internal: schedule input not at offset 0");
@@ -1364,7 +1377,7 @@ int launch_tcs(tsp_engine* e, const FastParams& p) {
     if (rc) return rc;
     const int grid = (p.B + TS_N - 1) / TS_N;
     constexpr int THREADS = TS_N * 8 + TS_SERVICE_THREADS;
-    search_tcs_kernel<<<grid, THREADS, smem, e->stream>>>(p, ts, e->ts_map[0], e->ts_map[1], e->ts_map[2]);
+    search_tcs_kernel<<<grid, THREADS, smem, e->stream>>>(p, ts, e->ts_map);
     CK(e, cudaGetLastError());
     e->stats.kernel_launches++;
     e->stats.search_ctas = grid;
@@ -1789,11 +1802,34 @@ int tsp_finalize_weights(tsp_handle e) {
     // The leading dimension wld is == 8 (mod 32) words so that the B fragments of mma.m16n8k8
     // (rows k0 + lane % 4, columns n0 + lane / 4) hit 32 distinct shared-memory banks.
     int64_t total = 0;
-    const int order[TSP_NUM_MLP] = {TSP_MLP_DYNAMICS, TSP_MLP_REWARD, TSP_MLP_TERMINAL, TSP_MLP_POLICY, TSP_MLP_VALUE,
-                                    TSP_MLP_PRIOR, TSP_MLP_REPRESENTATION};
+    // MuZeroStochastic (models.py:298-462): one dynamics MLP per future. The arena then starts with n_futures weight
+    // groups of identical layout, {dynamics of future z, reward head, prior head} (the shared heads are repeated), so
+    // that the transition schedule of future z is the schedule of future 0 on a base pointer z * f_stride further on.
+    const int nf = e->cfg.n_futures;
+    e->separate_heads = !e->mlp[TSP_MLP_DYNAMICS_F1].empty();
+    e->f_stride = 0;
+    if (e->separate_heads) {
+        if (e->cfg.variant == TSP_VARIANT_MUZERO || nf < 2 || nf > 4)
+            return fail(e, TSP_EINVAL, "per-future dynamics heads need a chance-node variant with 2..4 futures");
+        const auto& d0 = e->mlp[TSP_MLP_DYNAMICS];
+        for (int z = 1; z < 4; ++z) {
+            const auto& dz = e->mlp[TSP_MLP_DYNAMICS_F1 + z - 1];
+            if (z >= nf) {
+                if (!dz.empty()) return fail(e, TSP_EINVAL, "dynamics head of future %d set, but n_futures is %d", z, nf);
+                continue;
+            }
+            if (dz.size() != d0.size()) return fail(e, TSP_EINVAL, "dynamics head of future %d: %zu layers, future 0 has %zu", z, dz.size(), d0.size());
+            for (size_t l = 0; l < dz.size(); ++l)
+                if (dz[l].out_dim != d0[l].out_dim || dz[l].in_dim != d0[l].in_dim)
+                    return fail(e, TSP_EINVAL, "dynamics head of future %d: layer %zu shape differs from future 0", z, l);
+        }
+    }
+    const int order[TSP_NUM_MLP] = {TSP_MLP_DYNAMICS, TSP_MLP_REWARD, TSP_MLP_PRIOR, TSP_MLP_DYNAMICS_F1, TSP_MLP_DYNAMICS_F2,
+                                    TSP_MLP_DYNAMICS_F3, TSP_MLP_TERMINAL, TSP_MLP_POLICY, TSP_MLP_VALUE, TSP_MLP_REPRESENTATION};
     for (int oi = 0; oi < TSP_NUM_MLP; ++oi) {
         auto& v = e->mlp[order[oi]];
         if (order[oi] == TSP_MLP_REPRESENTATION) e->search_floats = total;
+        if (order[oi] == TSP_MLP_DYNAMICS_F1 && e->separate_heads) e->f_stride = (int)total;  // == size of group 0
         for (size_t l = 0; l < v.size(); ++l) {
             HostLayer& L = v[l];
             if (L.out_dim == 0) return fail(e, TSP_ESTATE, "a Linear layer is missing (set every layer index)");
@@ -1806,6 +1842,11 @@ int tsp_finalize_weights(tsp_handle e) {
             L.b_off = (int)total;
             total += L.npad;
         }
+        // group z >= 1: the dynamics MLP of future z is followed by room for the repeated reward / prior heads
+        if (e->separate_heads && order[oi] >= TSP_MLP_DYNAMICS_F1 && order[oi] <= TSP_MLP_DYNAMICS_F3 && !v.empty()) {
+            const int z = order[oi] - TSP_MLP_DYNAMICS_F1 + 1;
+            total = (int64_t)(z + 1) * e->f_stride;
+        }
     }
     if (total == 0) return fail(e, TSP_ESTATE, "no weights loaded");
     std::vector<float> host((size_t)total, 0.0f);
@@ -1815,6 +1856,11 @@ int tsp_finalize_weights(tsp_handle e) {
                 for (int i = 0; i < L.in_dim; ++i) host[(size_t)L.w_off + (size_t)i * L.wld + o] = L.W[(size_t)o * L.in_dim + i];
             for (int o = 0; o < L.out_dim; ++o) host[(size_t)L.b_off + o] = L.b[o];
         }
+    if (e->separate_heads) {  // repeat the shared heads of group 0 behind every other future's dynamics MLP
+        const int64_t heads0 = e->mlp[TSP_MLP_REWARD].front().w_off;
+        for (int z = 1; z < nf; ++z)
+            std::copy(host.begin() + heads0, host.begin() + e->f_stride, host.begin() + (int64_t)z * e->f_stride + heads0);
+    }
     int rc = ensure(e, e->arena, (size_t)total * sizeof(float));
     if (rc) return rc;
     CK(e, cudaMemcpyAsync(e->arena.p, host.data(), (size_t)total * sizeof(float), cudaMemcpyHostToDevice, e->stream));

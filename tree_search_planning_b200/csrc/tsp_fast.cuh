@@ -442,7 +442,7 @@ namespace tsp {
 // what the streamed tcgen05 path (TC == 2, tsp_stream.cuh) needs besides FastParams: all kernel parameters (constant bank)
 struct TsArgs {
     const TsSched* ts;
-    const CUtensorMap *m128, *m64, *m32;  // weight image as boxes of 128 / 64 / 32 rows x 64 inputs
+    const CUtensorMap* tmap;  // the weight image as boxes of 128 rows of 128 bytes: one 16 KB tile
 };
 constexpr int TS_SERVICE_THREADS = 64;    // TC == 2: one TMA producer warp and one MMA issuer warp behind the tree threads
 
@@ -510,7 +510,7 @@ __device__ __forceinline__ void search_fast_body(const FastParams& p, const TcSc
     [[maybe_unused]] float4 hq[2];
     [[maybe_unused]] bool tc_ok = true;
     [[maybe_unused]] TsCtl* ts_ctl = nullptr;
-    [[maybe_unused]] bool ts_range_ok = true;
+    [[maybe_unused]] float ts_amax = 0.0f;  // largest |activation| that went through the fp16 split
     [[maybe_unused]] uint32_t ts_ring = 0;
     if constexpr (TC == 2) {
         // ---- streamed tcgen05 path: constant table, control block, weight ring, B-operand arena, out strip, row tables ----
@@ -675,10 +675,10 @@ __device__ __forceinline__ void search_fast_body(const FastParams& p, const TcSc
             if (elect_one()) {
                 const uint32_t full0 = smem_u32(&ts_ctl->full[0]), empty0 = smem_u32(&ts_ctl->empty[0]);
                 if (gw_u == THREADS / 32)
-                    ok = ts_producer(*sx->ts, sx->m128, sx->m64, sx->m32, ts_ring, full0, empty0, p.S, &ts_ctl->abort);
+                    ok = ts_producer(*sx->ts, sx->tmap, ts_ring, full0, empty0, p.S, &ts_ctl->abort, p.phase_cycles);
                 else
                     ok = ts_issuer(*sx->ts, tmem_base, smem_u32(tc_arena), ts_ring, full0, empty0, smem_u32(&ts_ctl->acc[0]),
-                                   smem_u32(&ts_ctl->bready), p.S, &ts_ctl->abort);
+                                   smem_u32(&ts_ctl->bready), p.S, &ts_ctl->abort, p.phase_cycles);
             }
             __syncwarp();
             tc_ok = ok;
@@ -712,7 +712,12 @@ __device__ __forceinline__ void search_fast_body(const FastParams& p, const TcSc
                 const double vs = blk->vsum[jc];
                 const float rw = blk->reward[jc];
                 const float prf = (node == 0) ? root_prior_f : blk->prior[jc];
-                // (prefetching the children's blocks / the node's hidden state towards L1 here was measured: no effect)
+                // (prefetching the children's blocks / the node's hidden state towards L1 here was measured: no effect while
+                // the pools are L2-resident; the streamed path's large batches of 201-node trees are not: the five candidate
+                // blocks of the next level are requested while this level is scored)
+                if constexpr (TC == 2) {
+                    if (ch >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(blocks + ch));
+                }
                 // ---- float32 filter: score_j +- E_j encloses the reference's float64 ucb_score; when one
                 // interval lies strictly above all others, the exact arg-max is that child and it is not tied.
                 const float ps = pbf[Np] * rcp_approx((float)(vis + 1)) * prf;
@@ -812,12 +817,12 @@ __device__ __forceinline__ void search_fast_body(const FastParams& p, const TcSc
                     const float y[8] = {u.x, u.y, u.z, u.w, v.x, v.y, v.z, v.w};
                     uint4 hi, lo;
                     ts_split8(y, hi, lo);
-                    *reinterpret_cast<uint4*>(d + c * 144) = hi;
-                    *reinterpret_cast<uint4*>(d + c * 144 + tx.x0_lo) = lo;
+                    *reinterpret_cast<uint4*>(d + c * TS_X0_LBO) = hi;
+                    *reinterpret_cast<uint4*>(d + c * TS_X0_LBO + tx.x0_lo) = lo;
                 }
             }
             if (p.phase_cycles && tid == 0) tc1 = tc2 = clock64();
-            tc_ok = ts_mlp<THREADS>(tx, ts_ctl, tmem_base, tc_arena, tc_outs, ctab, row_action, gw_u, lane, it, ts_range_ok, p.phase_cycles) && tc_ok;
+            tc_ok = ts_mlp<THREADS>(tx, ts_ctl, tmem_base, tc_arena, tc_outs, ctab, row_action, gw_u, lane, it, ts_amax, p.phase_cycles) && tc_ok;
             if (p.phase_cycles && tid == 0) tc3 = clock64();
             const float* o = tc_outs + n * tx.out_pitch;
             decode_row<LPT, true>(o + tx.off_vl, o + tx.off_rl, o + tx.off_pl, p.support, A, p.uniform_policy != 0, j, value, reward,
@@ -1056,7 +1061,7 @@ __device__ __forceinline__ void search_fast_body(const FastParams& p, const TcSc
     }
     if constexpr (TC) {
         if (!tc_ok && p.tc_status) atomicExch(p.tc_status, 1);  // an MMA commit never arrived (bounded mbarrier wait)
-        if (!ts_range_ok && p.tc_status) atomicCAS(p.tc_status, 0, 2);  // an activation left the fp16 range of the streamed path
+        if (!(ts_amax <= TS_FP16_MAX) && p.tc_status) atomicCAS(p.tc_status, 0, 2);  // an activation left the fp16 range of the streamed path
         tc_fence_before();
         __syncthreads();
         if (__shfl_sync(FULL, tid >> 5, 0) == 0)
@@ -1079,9 +1084,8 @@ __global__ void __launch_bounds__(G * GT * LPT, 1) search_tc_kernel(const __grid
 // The same search with the MLP on tcgen05 and the weights streamed by TMA (tsp_stream.cuh): 64 trees per CTA (8 lanes
 // per tree, 16 tree warps) + the TMA producer warp + the MMA issuer warp. One CTA per SM.
 __global__ void __launch_bounds__(TS_N * 8 + TS_SERVICE_THREADS, 1)
-search_tcs_kernel(const __grid_constant__ FastParams p, const __grid_constant__ TsSched ts, const __grid_constant__ CUtensorMap m128,
-                  const __grid_constant__ CUtensorMap m64, const __grid_constant__ CUtensorMap m32) {
-    const TsArgs sx{&ts, &m128, &m64, &m32};
+search_tcs_kernel(const __grid_constant__ FastParams p, const __grid_constant__ TsSched ts, const __grid_constant__ CUtensorMap tmap) {
+    const TsArgs sx{&ts, &tmap};
     search_fast_body<TS_N / GT, 8, false, 2>(p, nullptr, &sx);
 }
 

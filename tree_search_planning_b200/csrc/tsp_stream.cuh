@@ -5,16 +5,20 @@
 //
 // TRANSPOSED formulation like tsp_tc.cuh -- D^T[feature][tree] = W[feature][k] X^T[k][tree] -- with
 //   * N = 64: the 64 trees of the CTA are the MMA's N dimension and run the network evaluation in lock step;
-//   * A = weight tiles of <= 128 rows x 64 inputs (fp16, 16 KB), host-arranged in the K-major no-swizzle core-matrix
-//     order and streamed from global memory / L2 through a ring of TS_NS shared-memory slots by TMA
-//     (cp.async.bulk.tensor.2d + mbarrier complete_tx); one elected lane of a PRODUCER warp runs ahead of the MMAs by
-//     the depth of the ring, across layer and simulation boundaries;
+//   * A = weight tiles of 16 KB (fp16: 128 rows x 64 inputs, 64 x 128 or 32 x 256 -- narrow layers get long tiles so that
+//     the bytes in flight do not shrink with the layer), host-arranged in the K-major no-swizzle core-matrix order and
+//     streamed from global memory / L2 through a ring of TS_NS shared-memory slots by TMA (cp.async.bulk.tensor.2d +
+//     mbarrier complete_tx); one elected lane of a PRODUCER warp runs ahead of the MMAs by the depth of the ring, across
+//     layer and simulation boundaries;
 //   * B = the activations in shared memory: the gathered hidden state K-major (written by the trees' lanes, 16-byte
-//     chunks of 8 inputs, LBO = 144 against bank conflicts), every later operand MN-major (written by the epilogue,
-//     thread = feature, 16-byte chunks of 8 trees);
+//     chunks of 8 inputs), every later operand MN-major (written by the epilogue, thread = feature, 16-byte chunks of 8
+//     trees);
 //   * float32-level accuracy by the SCALED fp16 split on kind::f16 (K = 16 per MMA, half the MMAs of 3xTF32):
 //         v = v1 + v2 / 2048,  v1 = fp16(v),  v2 = fp16((v - v1) * 2048)          (22 significant bits)
 //         acc0 += W1 X1,  acc1 += W1 X2 + W2 X1,  D = acc0 + acc1 / 2048          (fp32 accumulators in TMEM)
+//     The X2 image of an operand follows its X1 image, so [X1 | X2] is ONE B operand of N = 128 columns and acc0 | acc1
+//     one accumulator of 128 columns: a W1 tile issues one N = 128 MMA per 16 inputs, a W2 tile one N = 64 MMA --
+//     two MMAs per 16 inputs instead of three, and the W1 tile is read from shared memory once;
 //     the dropped term W2 X2 / 2048^2 is 2^-22 relative (tools/tcs_gemm_test.cu: 5.8e-7 of max |D| at K = 256);
 //     activations beyond fp16's range (|x| > 6e4) raise the status flag instead of overflowing silently;
 //   * one elected lane of an ISSUER warp issues the MMAs of a tile when its slot is full (and, at a layer boundary, when
@@ -26,9 +30,9 @@
 //     per-tree minimum / maximum by REDUX + shared-memory atomics on order-preserving integer keys, then a second pass
 //     over the accumulator writes the normalised state as the B operand of the prediction heads and straight into the
 //     hidden-state pool (thread = feature: a warp stores 128 contiguous bytes per tree).
-// Stages (cross-merge): dynamics 1 (8 tiles) -> dynamics 2 (+ the first reward layer folded in like tsp_tc.cuh: 12
-// tiles) -> policy 1 | value 1 (8 tiles) -> the three output layers as one block-diagonal K = 96 layer (4 tiles):
-// 32 tiles = 352 KB and 186 MMAs per simulation of 64 trees.
+// Stages (cross-merge): dynamics 1 (8 tiles) -> dynamics 2 (+ the first reward layer folded in like tsp_tc.cuh: 10
+// tiles) -> policy 1 | value 1 (4 tiles) -> the three output layers as one block-diagonal K = 96 layer (2 tiles):
+// 24 tiles = 384 KB and 124 MMAs per simulation of 64 trees.
 #pragma once
 #include <cuda.h>
 #include <cuda_fp16.h>
@@ -37,7 +41,9 @@
 namespace tsp {
 
 constexpr int TS_N = 64;          // trees per CTA == N of every MMA
-constexpr int TS_NS = 4;          // ring slots
+constexpr int TS_NS = 4;          // ring slots (8 were measured: no gain -- the stream is bound by shared-memory bandwidth, not latency)
+constexpr int TS_X0_LBO = 144;    // gathered state, K-major: bytes between core matrices along K (128 + 16 of padding: the
+                                  // 16-byte stores of a tree's 8 lanes hit different banks; dense 128 cost 1k cycles per simulation)
 constexpr int TS_SLOT = 16384;    // bytes per slot: 128 rows x 64 inputs fp16
 constexpr int TS_MAX_TILES = 40;
 constexpr int TS_MAX_ACC = 8;
@@ -48,13 +54,13 @@ constexpr float TS_SPLIT = 2048.0f, TS_INV_SPLIT = 1.0f / 2048.0f;
 constexpr float TS_FP16_MAX = 6.0e4f;
 
 struct TsTile {       // one weight tile: one ring slot fill and the MMAs that consume it
-    int img_row;      // first 128-byte row of the tile in the weight image (TMA coordinate)
-    short rows;       // 128 / 64 / 32 rows -> tensor map 0 / 1 / 2
-    short ksteps;     // K of the tile / 16, <= 4
+    int img_row;      // first 128-byte row of the tile in the weight image (TMA coordinate); a tile is 128 image rows
+    short a_sbo;      // bytes between 8-row groups of the tile: 128 * (inputs of the tile / 8) = 1024 / 2048 / 4096
+    short ksteps;     // valid inputs of the tile / 16, <= 16
     int b_off;        // B operand (X1 image) at the tile's first input: byte offset in the arena
-    int b_lo;         // distance X1 -> X2 image of that operand
+    int b_lo;         // distance X1 -> X2 image of that operand: always 8 * b_sbo ([X1 | X2] is one operand of 128 columns)
     int b_sbo;        // bytes between 8-tree groups
-    short b_lbo;      // bytes between core matrices along K: 144 (K-major) or 128 (MN-major)
+    short b_lbo;      // bytes between core matrices along K: TS_X0_LBO (K-major) or 128 (MN-major)
     short b_step;     // descriptor units (16 bytes) per k-step
     short d_col;      // accumulator: acc0 at d_col, acc1 at d_col + 64
     char kind;        // 0: W1 tile (acc0 += W1 X1, acc1 += W1 X2), 1: W2 tile (acc1 += W2 X1)
@@ -82,7 +88,7 @@ static_assert(sizeof(TsEpi) == 32, "TsEpi");
 struct TsSched {
     int n_tiles, n_acc, arena_bytes, out_pitch;
     int off_vl, off_rl, off_pl, ctab_floats;
-    int x0_off, x0_sbo, x0_lo, H;       // gathered hidden state: K-major, LBO 144
+    int x0_off, x0_sbo, x0_lo, H;       // gathered hidden state: K-major, LBO TS_X0_LBO
     int stage_tile[TS_STAGES + 1];      // tiles [stage_tile[s], stage_tile[s + 1]) read the B operand published before stage s
     int stage_acc[TS_STAGES + 1];
     int img_rows, pad;
@@ -98,6 +104,7 @@ struct TsCtl {
     int abort;
     int mmk[2][TS_N][2];                 // [simulation parity][tree]{min key, max key} of the next state
     unsigned long long hdst[TS_N];       // where the hidden state of the tree's new node goes (0: nowhere)
+    float2 mnv[16][16];                  // per tree warp: {minimum, 1 / scale} of its 16 trees' next states
 };
 
 __device__ __forceinline__ uint32_t ts_desc_lo(uint32_t saddr, uint32_t lbo) { return ((saddr & 0x3FFFF) >> 4) | ((lbo >> 4) << 16); }
@@ -110,6 +117,7 @@ __device__ __forceinline__ void ts_mma(uint32_t d, uint32_t a_lo, uint32_t a_hi,
         : "memory");
 }
 constexpr uint32_t TS_IDESC = (1u << 4) | ((uint32_t)(TS_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);  // D f32, A / B f16, A K-major
+constexpr uint32_t TS_IDESC128 = (1u << 4) | ((uint32_t)(2 * TS_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);  // N = 128: [X1 | X2]
 
 // Bounded wait that gives up at once when another thread of the CTA has already timed out (a lost TMA / commit must
 // neither hang the GPU nor stretch into minutes of serial time-outs).
@@ -130,64 +138,87 @@ __device__ __forceinline__ void ts_commit(uint32_t mbar) {
 }
 
 // TMA producer: one elected lane; the whole search (S simulations x n_tiles tiles) in ring order.
-__device__ __forceinline__ bool ts_producer(const TsSched& ts, const CUtensorMap* m128, const CUtensorMap* m64, const CUtensorMap* m32,
-                                            uint32_t ring, uint32_t full0, uint32_t empty0, int S, volatile int* abort) {
+__device__ __forceinline__ bool ts_producer(const TsSched& ts, const CUtensorMap* tmap, uint32_t ring, uint32_t full0, uint32_t empty0, int S, volatile int* abort,
+                                            unsigned long long* dbg) {
     bool ok = true;
     int g = 0;
+    long long w_empty = 0;
+    const long long t_begin = dbg ? clock64() : 0;
     for (int it = 0; it < S && ok; ++it)
         for (int t = 0; t < ts.n_tiles; ++t, ++g) {
             const int s = g & (TS_NS - 1);
+            const long long c0 = dbg ? clock64() : 0;
             if (g >= TS_NS) ok = ts_wait(empty0 + 8 * s, (uint32_t)(((g / TS_NS) - 1) & 1), abort) && ok;
-            const int rows = ts.tile[t].rows;
-            const CUtensorMap* mp = rows == 128 ? m128 : (rows == 64 ? m64 : m32);
+            if (dbg) w_empty += clock64() - c0;
             const uint32_t dst = ring + s * TS_SLOT, mb = full0 + 8 * s;
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(rows * 128) : "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "n"(TS_SLOT) : "memory");
             asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                         ::"r"(dst), "l"(mp), "r"(0), "r"(ts.tile[t].img_row), "r"(mb) : "memory");
+                         ::"r"(dst), "l"(tmap), "r"(0), "r"(ts.tile[t].img_row), "r"(mb) : "memory");
         }
+    if (dbg) {  // [24] producer: waiting for a free slot, [25] producer: total
+        atomicAdd(dbg + 24, (unsigned long long)w_empty);
+        atomicAdd(dbg + 25, (unsigned long long)(clock64() - t_begin));
+    }
     return ok;
 }
 
 // MMA issuer: one elected lane.
 __device__ __forceinline__ bool ts_issuer(const TsSched& ts, uint32_t tmem, uint32_t arena_s, uint32_t ring, uint32_t full0,
-                                          uint32_t empty0, uint32_t acc0, uint32_t bready, int S, volatile int* abort) {
+                                          uint32_t empty0, uint32_t acc0, uint32_t bready, int S, volatile int* abort,
+                                          unsigned long long* dbg) {
     bool ok = true;
     int g = 0;
     uint32_t br = 0;
-    const uint32_t a_hi = ts_desc_hi(1024);  // A tile: core matrices of 8 rows x 8 inputs, 8 of them (64 inputs) per 8-row group
+    long long w_b[TS_STAGES] = {0, 0, 0, 0}, w_full = 0, c0 = 0, c1 = 0;
+    const long long t_begin = dbg ? clock64() : 0;
     for (int it = 0; it < S && ok; ++it)
         for (int st = 0; st < TS_STAGES; ++st) {
+            if (dbg) c0 = clock64();
             ok = ts_wait(bready, br, abort) && ok;  // all tree warps have published this stage's B operand
+            if (dbg) w_b[st] += clock64() - c0;
             br ^= 1u;
             tc_fence_after();
             for (int t = ts.stage_tile[st]; t < ts.stage_tile[st + 1]; ++t, ++g) {
                 const TsTile& tl = ts.tile[t];
                 const int s = g & (TS_NS - 1);
+                if (dbg) c1 = clock64();
                 ok = ts_wait(full0 + 8 * s, (uint32_t)((g / TS_NS) & 1), abort) && ok;
+                if (dbg) w_full += clock64() - c1;
                 tc_fence_after();
-                const uint32_t a_lo = ts_desc_lo(ring + s * TS_SLOT, 128);
-                const uint32_t b1 = ts_desc_lo(arena_s + tl.b_off, (uint32_t)tl.b_lbo);
-                const uint32_t b2 = ts_desc_lo(arena_s + tl.b_off + tl.b_lo, (uint32_t)tl.b_lbo);
+                // A tile: core matrices of 8 rows x 8 inputs (128 bytes), a_sbo bytes per 8-row group
+                uint32_t a_lo = ts_desc_lo(ring + s * TS_SLOT, 128);
+                const uint32_t a_hi = ts_desc_hi((uint32_t)tl.a_sbo);
+                uint32_t b1 = ts_desc_lo(arena_s + tl.b_off, (uint32_t)tl.b_lbo);
                 const uint32_t b_hi = ts_desc_hi((uint32_t)tl.b_sbo);
-                const uint32_t idesc = TS_IDESC | ((uint32_t)tl.b_mn << 16);
-                const uint32_t d = tmem + (uint32_t)tl.d_col, bstep = (uint32_t)tl.b_step;
-                const uint32_t fresh = tl.first ? 0u : 1u;
-                if (tl.kind == 0) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (j < tl.ksteps) {
-                            ts_mma(d, a_lo + 16 * j, a_hi, b1 + bstep * j, b_hi, idesc, j == 0 ? fresh : 1u);
-                            ts_mma(d + 64, a_lo + 16 * j, a_hi, b2 + bstep * j, b_hi, idesc, j == 0 ? fresh : 1u);
-                        }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (j < tl.ksteps) ts_mma(d + 64, a_lo + 16 * j, a_hi, b1 + bstep * j, b_hi, idesc, 1u);
+                const uint32_t bstep = (uint32_t)tl.b_step;
+                const int ks = tl.ksteps;
+                if (tl.kind == 0) {  // W1 [X1 | X2] -> acc0 | acc1: one MMA of N = 128
+                    const uint32_t idesc = TS_IDESC128 | ((uint32_t)tl.b_mn << 16);
+                    const uint32_t d = tmem + (uint32_t)tl.d_col;
+                    uint32_t acc = tl.first ? 0u : 1u;
+#pragma unroll 4
+                    for (int j = 0; j < ks; ++j) {
+                        ts_mma(d, a_lo, a_hi, b1, b_hi, idesc, acc);
+                        a_lo += 16; b1 += bstep; acc = 1u;
+                    }
+                } else {             // W2 X1 -> acc1
+                    const uint32_t idesc = TS_IDESC | ((uint32_t)tl.b_mn << 16);
+                    const uint32_t d = tmem + (uint32_t)tl.d_col + 64;
+#pragma unroll 4
+                    for (int j = 0; j < ks; ++j) {
+                        ts_mma(d, a_lo, a_hi, b1, b_hi, idesc, 1u);
+                        a_lo += 16; b1 += bstep;
+                    }
                 }
                 ts_commit(empty0 + 8 * s);
                 if (tl.acc_done) ts_commit(acc0 + 8 * (tl.acc_done - 1));
             }
         }
+    if (dbg) {  // issuer: [16 + s] waiting for the B operand of stage s, [20] waiting for full slots, [21] total
+        for (int st = 0; st < TS_STAGES; ++st) atomicAdd(dbg + 16 + st, (unsigned long long)w_b[st]);
+        atomicAdd(dbg + 20, (unsigned long long)w_full);
+        atomicAdd(dbg + 21, (unsigned long long)(clock64() - t_begin));
+    }
     return ok;
 }
 
@@ -201,12 +232,10 @@ __device__ __forceinline__ void ts_ld_wait() { asm volatile("tcgen05.wait::ld.sy
 __device__ __forceinline__ void ts_split8(const float (&y)[8], uint4& hi, uint4& lo) {
     __half2 h[4], l[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const __half a1 = __float2half_rn(y[2 * i]), b1 = __float2half_rn(y[2 * i + 1]);
-        const __half a2 = __float2half_rn((y[2 * i] - __half2float(a1)) * TS_SPLIT);
-        const __half b2 = __float2half_rn((y[2 * i + 1] - __half2float(b1)) * TS_SPLIT);
-        h[i] = __halves2half2(a1, b1);
-        l[i] = __halves2half2(a2, b2);
+    for (int i = 0; i < 4; ++i) {  // (packed conversions: one cvt.rn.f16x2.f32 per pair)
+        h[i] = __floats2half2_rn(y[2 * i], y[2 * i + 1]);
+        const float2 f = __half22float2(h[i]);
+        l[i] = __floats2half2_rn((y[2 * i] - f.x) * TS_SPLIT, (y[2 * i + 1] - f.y) * TS_SPLIT);
     }
     hi = make_uint4(*reinterpret_cast<uint32_t*>(&h[0]), *reinterpret_cast<uint32_t*>(&h[1]), *reinterpret_cast<uint32_t*>(&h[2]),
                     *reinterpret_cast<uint32_t*>(&h[3]));
@@ -219,7 +248,7 @@ __device__ __forceinline__ void ts_split8(const float (&y)[8], uint4& hi, uint4&
 __device__ __forceinline__ bool ts_epi_warp(const TsEpi& ep, uint32_t tmem_q, int q, int c0, int lane, unsigned char* __restrict__ arena,
                                             float* __restrict__ outs, int out_pitch, const float* __restrict__ ctab,
                                             const int* __restrict__ row_action, uint32_t accbar, uint32_t parity, volatile int* abort,
-                                            bool& range_ok) {
+                                            float& amax) {
     if (32 * q >= ep.rows) return true;  // this quarter holds no row of the tile (warp-uniform)
     const int r = 32 * q + lane;
     const bool on = r < ep.rows;
@@ -257,7 +286,7 @@ __device__ __forceinline__ bool ts_epi_warp(const TsEpi& ep, uint32_t tmem_q, in
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 y[i] = elu_fast(y[i]);
-                range_ok = range_ok && fabsf(y[i]) <= TS_FP16_MAX;
+                amax = fmaxf(amax, fabsf(y[i]));  // (NaN-free inputs; an overflow shows as inf)
             }
             uint4 hi, lo;
             ts_split8(y, hi, lo);
@@ -281,7 +310,7 @@ __device__ __forceinline__ float ts_unkey(int k) { return __int_as_float(k ^ ((k
 template <int TREE_THREADS>
 __device__ __forceinline__ bool ts_mlp(const TsSched& ts, TsCtl* __restrict__ ctl, uint32_t tmem_base, unsigned char* __restrict__ arena,
                                        float* __restrict__ outs, const float* __restrict__ ctab, const int* __restrict__ row_action, int w,
-                                       int lane, int it, bool& range_ok, unsigned long long* dbg) {
+                                       int lane, int it, float& amax, unsigned long long* dbg) {
     const int q = w & 3, c0 = 16 * (w >> 2);
     const uint32_t tmem_q = tmem_base + ((uint32_t)(32 * q) << 16);
     const uint32_t acc0 = smem_u32(&ctl->acc[0]), bready = smem_u32(&ctl->bready);
@@ -301,6 +330,9 @@ __device__ __forceinline__ bool ts_mlp(const TsSched& ts, TsCtl* __restrict__ ct
         for (int a = a_begin; a < a_end; ++a) has_xs = has_xs || ts.acc[a].kind == 1;
         if (has_xs) {  // (the next-state tiles are issued first: they are on the critical path)
             // ---- pass 1: minimum / maximum of every tree's next state (models.py:248-250) ----
+            // (the second pass reads the accumulators again: keeping the 32 values per thread in registers instead was
+            // measured -- at the 96 registers this CTA shape allows it spills, and the spills slow the selection down more
+            // than the 2k cycles of tensor-memory reads it saves)
             int kmn[16], kmx[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) { kmn[i] = INT_MAX; kmx[i] = INT_MIN; }
@@ -330,6 +362,8 @@ __device__ __forceinline__ bool ts_mlp(const TsSched& ts, TsCtl* __restrict__ ct
                     }
                 }
             }
+            long long u0 = 0, u1 = 0, u2 = 0;
+            if (tm) u0 = clock64();
             int mine = 0;
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
@@ -340,7 +374,9 @@ __device__ __forceinline__ bool ts_mlp(const TsSched& ts, TsCtl* __restrict__ ct
             int (*mmk)[2] = ctl->mmk[it & 1];
             if (lane < 16) atomicMin(&mmk[c0 + lane][0], mine);
             else atomicMax(&mmk[c0 + lane - 16][1], mine);
+            if (tm) u1 = clock64();
             asm volatile("bar.sync 1, %0;" ::"n"(TREE_THREADS) : "memory");
+            if (tm) u2 = clock64();
             {   // the other parity's keys are free again: reset them for the next simulation
                 const int t = threadIdx.x;
                 if (t < TS_N) {
@@ -349,6 +385,15 @@ __device__ __forceinline__ bool ts_mlp(const TsSched& ts, TsCtl* __restrict__ ct
                 }
             }
             // ---- pass 2: normalise -> B operand of the prediction heads + hidden-state pool ----
+            float2* mnv = ctl->mnv[w];  // {minimum, 1 / scale} of this warp's 16 trees: computed once, by lanes 0..15
+            if (lane < 16) {
+                const int2 kk = *reinterpret_cast<const int2*>(&mmk[c0 + lane][0]);
+                const float mn = ts_unkey(kk.x);
+                float sc = __fsub_rn(ts_unkey(kk.y), mn);
+                if (sc < 1e-5f) sc = __fadd_rn(sc, 1e-5f);  // scale += 1e-5 only where scale < 1e-5
+                mnv[lane] = make_float2(mn, __frcp_rn(sc));
+            }
+            __syncwarp();
             for (int a = a_begin; a < a_end; ++a) {
                 const TsEpi& ep = ts.acc[a];
                 if (ep.kind != 1 || 32 * q >= ep.rows) continue;
@@ -365,14 +410,8 @@ __device__ __forceinline__ bool ts_mlp(const TsSched& ts, TsCtl* __restrict__ ct
                     float mn[8], inv[8];
 #pragma unroll
                     for (int i = 0; i < 8; i += 2) {
-                        const int4 kk = *reinterpret_cast<const int4*>(&mmk[n0 + i][0]);
-                        mn[i] = ts_unkey(kk.x);
-                        mn[i + 1] = ts_unkey(kk.z);
-                        float s0 = __fsub_rn(ts_unkey(kk.y), mn[i]), s1 = __fsub_rn(ts_unkey(kk.w), mn[i + 1]);
-                        if (s0 < 1e-5f) s0 = __fadd_rn(s0, 1e-5f);  // scale += 1e-5 only where scale < 1e-5
-                        if (s1 < 1e-5f) s1 = __fadd_rn(s1, 1e-5f);
-                        inv[i] = __frcp_rn(s0);
-                        inv[i + 1] = __frcp_rn(s1);
+                        const float4 m2 = *reinterpret_cast<const float4*>(&mnv[8 * h + i]);
+                        mn[i] = m2.x; inv[i] = m2.y; mn[i + 1] = m2.z; inv[i + 1] = m2.w;
                     }
                     ts_ld_wait();
                     if (!on) continue;
@@ -390,16 +429,22 @@ __device__ __forceinline__ bool ts_mlp(const TsSched& ts, TsCtl* __restrict__ ct
 #pragma unroll
                     for (int i = 0; i < 8; i += 2) {
                         const ulonglong2 hp = *reinterpret_cast<const ulonglong2*>(&ctl->hdst[n0 + i]);
-                        if (hp.x) reinterpret_cast<float*>(hp.x)[k] = y[i];
-                        if (hp.y) reinterpret_cast<float*>(hp.y)[k] = y[i + 1];
+                        if (hp.x) asm volatile("st.global.f32 [%0], %1;" ::"l"(reinterpret_cast<float*>(hp.x) + k), "f"(y[i]) : "memory");
+                        if (hp.y) asm volatile("st.global.f32 [%0], %1;" ::"l"(reinterpret_cast<float*>(hp.y) + k), "f"(y[i + 1]) : "memory");
                     }
                 }
+            }
+            if (tm) {  // [28] accumulators + minimum / maximum, [29] REDUX + atomics, [30] barrier, [31] second pass
+                atomicAdd(dbg + 28, (unsigned long long)(u0 - t0));
+                atomicAdd(dbg + 29, (unsigned long long)(u1 - u0));
+                atomicAdd(dbg + 30, (unsigned long long)(u2 - u1));
+                atomicAdd(dbg + 31, (unsigned long long)(clock64() - u2));
             }
         }
         for (int a = a_begin; a < a_end; ++a)
             if (ts.acc[a].kind != 1)
                 ok = ts_epi_warp(ts.acc[a], tmem_q, q, c0, lane, arena, outs, ts.out_pitch, ctab, row_action, acc0 + 8 * a, parity, abort,
-                                 range_ok) && ok;
+                                 amax) && ok;
         if (st + 1 < TS_STAGES) {  // this warp's share of the next stage's B operand is in place
             fence_async_smem();
             tc_fence_before();

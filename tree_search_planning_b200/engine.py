@@ -426,6 +426,13 @@ class Engine:
         return dict(select=v[0] / n, wait=v[1] / n, mlp=v[2] / n, backup=v[3] / n, samples=v[4],
                     stages_work_wait=stages, tile_init_kloop_store=(round(v[40] / nt), round(v[41] / nt), round(v[42] / nt)),
                     tiles_per_iter=v[43] / n, exact_selects=v[5], select_levels=v[6],
+                    # streamed tcgen05 kernel (tsp_stream.cuh), cycles per simulation: issuer waiting for the B operand of
+                    # stage 0..3, for full slots, issuer total; producer waiting for a free slot, total; next-state stage:
+                    # accumulators + min / max, REDUX + atomics, barrier, second pass
+                    stream=dict(issuer_wait_b=[round(v[16 + i] / n) for i in range(4)], issuer_wait_full=round(v[20] / n),
+                                issuer_total=round(v[21] / n), producer_wait_empty=round(v[24] / n), producer_total=round(v[25] / n),
+                                xs_pass1=round(v[28] / n), xs_redux=round(v[29] / n), xs_barrier=round(v[30] / n),
+                                xs_pass2=round(v[31] / n)) if v[21] else None,
                     tc_issue_wait_epilogue=[tuple(round(v[44 + 4 * s + i] / n) for i in range(3)) for s in range(5)
                                             if any(v[44 + 4 * s: 47 + 4 * s])])
 

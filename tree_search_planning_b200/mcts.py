@@ -121,15 +121,17 @@ class DeviceTree:
             vsum = float(b["value_sum"][slot])
             prior = float(self.info.root_prior[slot]) if block == 0 else float(b["prior"][slot])
             value = vsum if self.variant == 2 else (vsum / visits if visits > 0 else 0.0)
-            node = ChildView(visits, prior, float(b["reward"][slot]), value, self.variant == 2, tree=self, block=child,
-                             depth=depth + 1)
-            # hidden state: deterministic -- the expanded child's own block id is its slot; chance-node variants -- the
-            # StateNode children of a TransitionNode get theirs when the transition is expanded (slot 1 + ordinal * nf + z,
-            # self_play_stochastic.py:535-557), TransitionNodes carry none
+            # a StateNode below a TransitionNode receives its reward and hidden state when it is expanded itself
+            # (StateNode.expand, self_play_stochastic.py:453-469); until then the transition keeps them
+            # (child_rewards / child_hidden_states, :550-551) and the node reads reward 0, hidden_state None
+            reward = float(b["reward"][slot]) if not (transition and child < 0) else 0.0
+            node = ChildView(visits, prior, reward, value, self.variant == 2, tree=self, block=child, depth=depth + 1)
+            # hidden state: deterministic -- the expanded child's own block id is its slot; chance-node variants -- slot
+            # 1 + ordinal of the transition * nf + z; TransitionNodes carry none
             hs = -1
             if self.variant == 0:
                 hs = child
-            elif transition:
+            elif transition and child >= 0:
                 hs = 1 + (int(b["aux"]) >> 8) * self.nf + slot
             if self.hidden is not None and 0 <= hs < len(self.hidden):
                 node.hidden_state = self.hidden[hs][None]

@@ -11,10 +11,11 @@ def random_state_dict(config, seed=0):
     rng = numpy.random.default_rng(seed)
     A, H, V = len(config.action_space), config.encoding_size, 2 * config.support_size + 1
     stochastic = variant_of(config) != 0
+    separate = stochastic and getattr(config, "network", "") == "stochastic"  # MuZeroStochastic: one dynamics MLP per future
     nets = {
         "representation_network": [observation_dim(config)] + list(config.fc_representation_layers) + [H],
         "dynamics_encoded_state_network":
-            [H + A + (config.n_futures if stochastic else 0)] + list(config.fc_dynamics_layers) + [H],
+            [H + A + (config.n_futures if stochastic and not separate else 0)] + list(config.fc_dynamics_layers) + [H],
         "dynamics_reward_network": [H] + list(config.fc_reward_layers) + [V],
         "dynamics_terminal_network": [H] + list(config.fc_reward_layers) + [1],
         "prediction_policy_network": [H] + list(config.fc_policy_layers) + [A],
@@ -22,6 +23,10 @@ def random_state_dict(config, seed=0):
     }
     if stochastic:
         nets["transition_prior_network"] = [H] + list(config.fc_prior_layers) + [config.n_futures]
+    if separate:  # models.py:334-345: keys dynamics_encoded_state_network.<z>.module.<i>
+        sizes = nets.pop("dynamics_encoded_state_network")
+        for z in range(config.n_futures):
+            nets["dynamics_encoded_state_network.%d" % z] = sizes
     sd = {}
     for name, sizes in nets.items():
         for i in range(len(sizes) - 1):

@@ -18,6 +18,11 @@ MLP_IDS = {
     "policy": 4,
     "value": 5,
     "prior": 6,
+    # MuZeroStochastic (models.py:334-345): dynamics_encoded_state_network is a ModuleList with one MLP per future;
+    # future 0 is "dynamics", futures 1..3 follow
+    "dynamics_f1": 7,
+    "dynamics_f2": 8,
+    "dynamics_f3": 9,
 }
 
 _PREFIX = {
@@ -42,7 +47,16 @@ def extract_mlps(state_dict):
     The reconstruction and posterior heads are never evaluated by MCTS and are skipped."""
     out = {}
     items = dict(state_dict.items())
-    for name, prefix in _PREFIX.items():
+    prefixes = dict(_PREFIX)
+    # separate dynamics heads: keys "dynamics_encoded_state_network.<z>.module.<i>.weight"
+    sep = re.compile(r"^dynamics_encoded_state_network\.(\d+)\.module\.\d+\.weight$")
+    futures = sorted({int(m.group(1)) for m in map(sep.match, items) if m})
+    if futures:
+        if futures != list(range(len(futures))) or len(futures) > 4:
+            raise ValueError("separate dynamics heads: expected futures 0..n-1 with n <= 4, got %s" % futures)
+        for z in futures:
+            prefixes["dynamics" if z == 0 else "dynamics_f%d" % z] = "dynamics_encoded_state_network.%d" % z
+    for name, prefix in prefixes.items():
         layers = {}
         pat = re.compile(r"^" + re.escape(prefix) + r"\.(?:module\.)?(\d+)\.(weight|bias)$")
         for k, v in items.items():
