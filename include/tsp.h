@@ -165,6 +165,7 @@ typedef struct {
     int32_t trees_per_cta;
     int32_t threads_per_cta;
     int32_t search_kernel;         /* last search: 3 = tsp::search_tcs_kernel (tcgen05, weights streamed by TMA), 2 = tsp::search_tc_kernel (tcgen05, weights in tensor memory), 1 = tsp::search_fast_kernel (weights in shared memory), 0 = tsp::search_kernel */
+    int32_t root_kernel;           /* last initial inference: 1 = tsp::root_tcs_kernel (tcgen05, weights streamed by TMA), 0 = tsp::net_kernel */
 } tsp_stats;
 
 int tsp_abi_version(void);

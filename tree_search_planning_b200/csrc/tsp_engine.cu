@@ -127,6 +127,12 @@ struct tsp_engine {
     DevBuf ts_img, ts_ctab;
     CUtensorMap ts_map{};
     bool has_tcs = false;
+    // streamed tcgen05 root network (root_tcs_kernel): initial_inference for every fully-connected network of the reference
+    TsSched rts{};
+    DevBuf rts_img, rts_ctab, rts_hidden;
+    CUtensorMap rts_map{};
+    bool has_rtcs = false;
+    bool no_rtcs = false;  // TSP_NO_RTCS: keep net_kernel (mma.sync) for the root
     bool separate_heads = false;  // MuZeroStochastic: one dynamics MLP per future (TSP_MLP_DYNAMICS_F1..)
     int f_stride = 0;             // floats between the per-future weight groups {dynamics z, reward, prior} of the arena
     bool no_tcs = false;  // TSP_NO_TCS: keep the mma.sync kernels for these networks
@@ -718,6 +724,90 @@ void ts_split_host(float v, __half& h1, __half& h2) {
     h2 = __float2half_rn((v - __half2float(h1)) * TS_SPLIT);
 }
 
+size_t root_tcs_smem(const TsSched& ts) {
+    return (size_t)((ts.ctab_floats + 3) & ~3) * 4 + sizeof(TsCtl) + 256 + (size_t)TS_NS * TS_SLOT + (size_t)ts.arena_bytes +
+           (size_t)TR_N * ts.out_pitch * 4;
+}
+
+// Tables and weight image of a streamed tcgen05 MLP (tsp_stream.cuh): tiles of 16 KB = `rows` x KT inputs (128 x 64, 64 x 128
+// or 32 x 256), element (m, k) of a tile at ((m / 8) * (KT / 8) + k / 8) * 64 + (m % 8) * 8 + k % 8 (K-major core matrices:
+// LBO 128, SBO 128 * KT / 8); a tile is 128 image rows of 128 bytes.
+struct TsBuilder {
+    TsSched& ts;
+    int nt;  // columns of the MMAs: trees / rows per CTA
+    std::vector<__half> img;
+    int n_tiles = 0, n_acc = 0;
+    bool overflow = false;
+    static int box(int rows) { return rows > 64 ? 128 : (rows > 32 ? 64 : 32); }
+    static int mn_sbo(int K) { return (K / 8) * 128; }
+    // One accumulator tile `acc` of `rows_valid` rows over K inputs: K chunks of KT inputs, per chunk the W1 tile then the
+    // W2 tile. W(m, k): weight of row m, input k. The B operand starts at b_off (X1 image; X2 follows (nt / 8) * b_sbo on).
+    template <typename WF>
+    void add_layer(int acc, int rows_valid, int rows_box, int K, WF W, int b_off, int b_sbo, bool b_mn, int d_col) {
+        const int KT = 8192 / rows_box;
+        for (int k0 = 0; k0 < K; k0 += KT) {
+            const int kw = std::min(KT, K - k0);
+            for (int part = 0; part < 2; ++part) {
+                if (n_tiles >= TS_MAX_TILES) { overflow = true; return; }
+                TsTile& tl = ts.tile[n_tiles++];
+                tl.img_row = (int)(img.size() / 64);
+                tl.a_sbo = (short)(128 * (KT / 8));
+                tl.ksteps = (short)((kw + 15) / 16);
+                const int lbo = b_mn ? 128 : TS_X0_LBO;
+                tl.b_off = b_off + (k0 / 8) * lbo;
+                tl.b_lo = (nt / 8) * b_sbo;
+                tl.b_sbo = b_sbo;
+                tl.b_lbo = (short)lbo;
+                tl.b_step = (short)((2 * lbo) >> 4);
+                tl.d_col = (short)d_col;
+                tl.kind = (char)part;
+                tl.first = (char)(k0 == 0 && part == 0);
+                tl.b_mn = (char)(b_mn ? 1 : 0);
+                tl.acc_done = (char)((k0 + KT >= K && part == 1) ? acc + 1 : 0);
+                const size_t base = img.size();
+                img.resize(base + 8192, __float2half_rn(0.0f));
+                for (int m = 0; m < rows_valid; ++m)
+                    for (int kk = 0; kk < kw; ++kk) {
+                        __half h1, h2;
+                        ts_split_host(W(m, k0 + kk), h1, h2);
+                        img[base + ((size_t)(m >> 3) * (KT / 8) + (kk >> 3)) * 64 + (m & 7) * 8 + (kk & 7)] = part == 0 ? h1 : h2;
+                    }
+            }
+        }
+    }
+    void add_acc(int idx, int d_col, int rows, int kind, int feat0, int dst, int dst_sbo, int cidx, int eidx, int e_ld) {
+        n_acc = std::max(n_acc, idx + 1);
+        TsEpi& a = ts.acc[idx];
+        a.d_col = (short)d_col; a.rows = (short)rows; a.kind = (short)kind; a.feat0 = (short)feat0;
+        a.dst = dst; a.dst_sbo = dst_sbo; a.dst_lo = (nt / 8) * dst_sbo; a.cidx = cidx; a.eidx = eidx; a.e_ld = e_ld;
+    }
+};
+
+// upload + tensor map (cuTensorMapEncodeTiled through the runtime: no link against libcuda)
+int ts_upload(tsp_engine* e, const std::vector<__half>& img, const std::vector<float>& ctab, DevBuf& d_img, DevBuf& d_ctab,
+              CUtensorMap& map, int img_rows) {
+    int rc;
+    if ((rc = ensure(e, d_img, img.size() * sizeof(__half)))) return rc;
+    if ((rc = ensure(e, d_ctab, ctab.size() * sizeof(float)))) return rc;
+    CK(e, cudaMemcpyAsync(d_img.p, img.data(), img.size() * sizeof(__half), cudaMemcpyHostToDevice, e->stream));
+    CK(e, cudaMemcpyAsync(d_ctab.p, ctab.data(), ctab.size() * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+    CK(e, cudaStreamSynchronize(e->stream));
+    TspEncodeTiled encode = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", (void**)&encode, cudaEnableDefault, &qres) != cudaSuccess || !encode)
+        return fail(e, TSP_ECUDA, "cuTensorMapEncodeTiled is not available from this driver (TMA weight streaming needs it)");
+    const cuuint64_t gdim[2] = {64, (cuuint64_t)img_rows};
+    const cuuint64_t gstr[1] = {128};
+    const cuuint32_t estr[2] = {1, 1};
+    const cuuint32_t bx[2] = {64, 128};  // one box == one 16 KB tile
+    const CUresult cr = encode(&map, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, d_img.p, gdim, gstr, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) return fail(e, TSP_ECUDA, "cuTensorMapEncodeTiled failed (%d)", (int)cr);
+    if ((rc = ensure(e, e->tc_status, sizeof(int)))) return rc;
+    CK(e, cudaMemset(e->tc_status.p, 0, sizeof(int)));
+    return TSP_OK;
+}
+
 int build_tcs(tsp_engine* e) {
     e->has_tcs = false;
     const tsp_config& c = e->cfg;
@@ -795,112 +885,161 @@ int build_tcs(tsp_engine* e) {
     for (int i = 0; i < 128; ++i) ctab.push_back(0.0f);  // lanes past `rows` still form an address
     if ((int)ctab.size() > TS_MAX_CTAB) return TSP_OK;
     ts.ctab_floats = (int)ctab.size();
-    // ---- weight image: tiles of 16 KB = `rows` x KT inputs (128 x 64, 64 x 128 or 32 x 256), element (m, k) of a tile at
-    // ((m / 8) * (KT / 8) + k / 8) * 64 + (m % 8) * 8 + k % 8 (K-major core matrices: LBO 128, SBO 128 * KT / 8); a tile is
-    // 128 image rows of 128 bytes ----
-    std::vector<__half> img;
-    int n_tiles = 0, n_acc = 0;
-    bool overflow = false;
-    // W(m, k): weight of row m, input k of the layer group; rows x K
-    auto add_layer = [&](int acc, int rows_valid, int rows_box, int K, auto W, int b_off, int b_lo, int b_sbo, bool b_mn, int d_col) {
-        // one accumulator tile: K chunks of KT inputs, per chunk the W1 tile then the W2 tile
-        const int KT = 8192 / rows_box;
-        for (int k0 = 0; k0 < K; k0 += KT) {
-            const int kw = std::min(KT, K - k0);
-            for (int part = 0; part < 2; ++part) {
-                if (n_tiles >= TS_MAX_TILES) { overflow = true; return; }
-                TsTile& tl = ts.tile[n_tiles++];
-                tl.img_row = (int)(img.size() / 64);
-                tl.a_sbo = (short)(128 * (KT / 8));
-                tl.ksteps = (short)(kw / 16);
-                const int lbo = b_mn ? 128 : TS_X0_LBO;
-                tl.b_off = b_off + (k0 / 8) * lbo;
-                tl.b_lo = b_lo;
-                tl.b_sbo = b_sbo;
-                tl.b_lbo = (short)lbo;
-                tl.b_step = (short)((2 * lbo) >> 4);
-                tl.d_col = (short)d_col;
-                tl.kind = (char)part;
-                tl.first = (char)(k0 == 0 && part == 0);
-                tl.b_mn = (char)(b_mn ? 1 : 0);
-                tl.acc_done = (char)((k0 + KT >= K && part == 1) ? acc + 1 : 0);
-                const size_t base = img.size();
-                img.resize(base + 8192, __float2half_rn(0.0f));
-                for (int m = 0; m < rows_valid; ++m)
-                    for (int kk = 0; kk < kw; ++kk) {
-                        __half h1, h2;
-                        ts_split_host(W(m, k0 + kk), h1, h2);
-                        img[base + ((size_t)(m >> 3) * (KT / 8) + (kk >> 3)) * 64 + (m & 7) * 8 + (kk & 7)] = part == 0 ? h1 : h2;
-                    }
-            }
-        }
-    };
-    auto add_acc = [&](int idx, int d_col, int rows, int kind, int feat0, int dst, int dst_sbo, int cidx, int eidx, int e_ld) {
-        n_acc = std::max(n_acc, idx + 1);
-        TsEpi& a = ts.acc[idx];
-        a.d_col = (short)d_col; a.rows = (short)rows; a.kind = (short)kind; a.feat0 = (short)feat0;
-        a.dst = dst; a.dst_sbo = dst_sbo; a.dst_lo = 8 * dst_sbo; a.cidx = cidx; a.eidx = eidx; a.e_ld = e_ld;
-    };
-    auto box = [](int rows) { return rows > 64 ? 128 : (rows > 32 ? 64 : 32); };
+    TsBuilder tb{ts, TS_N};
+    ts.nt = TS_N; ts.n_stages = TS_STAGES;
+    auto box = [](int rows) { return TsBuilder::box(rows); };
     const int n_xs = (H + 127) / 128;
     const int A_D1 = 0, A_XS = 1, A_FOLD = 1 + n_xs, A_PV = 2 + n_xs, A_OUT = 3 + n_xs;
     if (A_OUT >= TS_MAX_ACC) return TSP_OK;
     // stage 0: dynamics layer 1 (the one-hot action input is a gathered row in the epilogue, models.py:236-243)
     ts.stage_tile[0] = 0; ts.stage_acc[0] = A_D1;
-    add_layer(A_D1, DH, box(DH), H, [&](int m, int k) { return D1.W[(size_t)m * D1.in_dim + k]; }, x0, ts.x0_lo, x0_sbo, false, 0);
-    add_acc(A_D1, 0, DH, 0, 0, xd, mn_sbo(DH), t_b1, t_e1, 128);
+    tb.add_layer(A_D1, DH, box(DH), H, [&](int m, int k) { return D1.W[(size_t)m * D1.in_dim + k]; }, x0, x0_sbo, false, 0);
+    tb.add_acc(A_D1, 0, DH, 0, 0, xd, mn_sbo(DH), t_b1, t_e1, 128);
     // stage 1: dynamics layer 2 -> the un-normalised next state in tiles of 128 features (first: they are on the critical
     // path), then the folded reward layer 1
-    ts.stage_tile[1] = n_tiles; ts.stage_acc[1] = A_XS;
+    ts.stage_tile[1] = tb.n_tiles; ts.stage_acc[1] = A_XS;
     for (int t = 0; t < n_xs; ++t) {
         const int rows = std::min(128, H - 128 * t);
-        add_layer(A_XS + t, rows, box(rows), DH, [&](int m, int k) { return D2.W[(size_t)(128 * t + m) * DH + k]; }, xd, 8 * mn_sbo(DH),
-                  mn_sbo(DH), true, 128 * t);
-        add_acc(A_XS + t, 128 * t, rows, 1, 128 * t, x0, xn_sbo, t_b2 + 128 * t, -1, 0);
+        tb.add_layer(A_XS + t, rows, box(rows), DH, [&](int m, int k) { return D2.W[(size_t)(128 * t + m) * DH + k]; }, xd, mn_sbo(DH),
+                     true, 128 * t);
+        tb.add_acc(A_XS + t, 128 * t, rows, 1, 128 * t, x0, xn_sbo, t_b2 + 128 * t, -1, 0);
     }
-    add_layer(A_FOLD, RH, 32, DH, [&](int m, int k) { return FW[(size_t)m * DH + k]; }, xd, 8 * mn_sbo(DH), mn_sbo(DH), true, 256);
-    add_acc(A_FOLD, 256, RH, 0, 64, xh, mn_sbo(HK), t_bf, -1, 0);
+    tb.add_layer(A_FOLD, RH, 32, DH, [&](int m, int k) { return FW[(size_t)m * DH + k]; }, xd, mn_sbo(DH), true, 256);
+    tb.add_acc(A_FOLD, 256, RH, 0, 64, xh, mn_sbo(HK), t_bf, -1, 0);
     // stage 2: policy layer 1 (rows 0..31) | value layer 1 (rows 32..63) on the normalised state
-    ts.stage_tile[2] = n_tiles; ts.stage_acc[2] = A_PV;
-    add_layer(A_PV, 64, 64, H, [&](int m, int k) {
+    ts.stage_tile[2] = tb.n_tiles; ts.stage_acc[2] = A_PV;
+    tb.add_layer(A_PV, 64, 64, H, [&](int m, int k) {
         if (m < 32) return m < PH ? P1.W[(size_t)m * H + k] : 0.0f;
         return m - 32 < VH ? V1.W[(size_t)(m - 32) * H + k] : 0.0f;
-    }, x0, 8 * xn_sbo, xn_sbo, true, 384);
-    add_acc(A_PV, 384, 64, 0, 0, xh, mn_sbo(HK), t_bpv, -1, 0);
+    }, x0, xn_sbo, true, 384);
+    tb.add_acc(A_PV, 384, 64, 0, 0, xh, mn_sbo(HK), t_bpv, -1, 0);
     // stage 3: the three output layers as one block-diagonal layer over the 96 hidden inputs; rows == out-strip columns
-    ts.stage_tile[3] = n_tiles; ts.stage_acc[3] = A_OUT;
-    add_layer(A_OUT, NV + NR + A, 32, HK, [&](int m, int k) {
+    ts.stage_tile[3] = tb.n_tiles; ts.stage_acc[3] = A_OUT;
+    tb.add_layer(A_OUT, NV + NR + A, 32, HK, [&](int m, int k) {
         if (m >= ts.off_pl) return (k < PH) ? P2.W[(size_t)(m - ts.off_pl) * PH + k] : 0.0f;
         if (m >= ts.off_rl) return (k >= 64 && k - 64 < RH) ? R2.W[(size_t)(m - ts.off_rl) * RH + (k - 64)] : 0.0f;
         return (k >= 32 && k - 32 < VH) ? V2.W[(size_t)m * VH + (k - 32)] : 0.0f;
-    }, xh, 8 * mn_sbo(HK), mn_sbo(HK), true, 0);
-    add_acc(A_OUT, 0, NV + NR + A, 2, 0, 0, 0, t_bo, -1, 0);
-    ts.stage_tile[4] = n_tiles; ts.stage_acc[4] = n_acc;
-    if (overflow || n_acc > TS_MAX_ACC) return TSP_OK;
-    ts.n_tiles = n_tiles; ts.n_acc = n_acc;
-    ts.img_rows = (int)(img.size() / 64);
-    // ---- upload + tensor maps (cuTensorMapEncodeTiled through the runtime: no link against libcuda) ----
+    }, xh, mn_sbo(HK), true, 0);
+    tb.add_acc(A_OUT, 0, NV + NR + A, 2, 0, 0, 0, t_bo, -1, 0);
+    ts.stage_tile[4] = tb.n_tiles; ts.stage_acc[4] = tb.n_acc;
+    if (tb.overflow || tb.n_acc > TS_MAX_ACC) return TSP_OK;
+    ts.n_tiles = tb.n_tiles; ts.n_acc = tb.n_acc;
+    ts.img_rows = (int)(tb.img.size() / 64);
     int rc;
-    if ((rc = ensure(e, e->ts_img, img.size() * sizeof(__half)))) return rc;
-    if ((rc = ensure(e, e->ts_ctab, ctab.size() * sizeof(float)))) return rc;
-    CK(e, cudaMemcpyAsync(e->ts_img.p, img.data(), img.size() * sizeof(__half), cudaMemcpyHostToDevice, e->stream));
-    CK(e, cudaMemcpyAsync(e->ts_ctab.p, ctab.data(), ctab.size() * sizeof(float), cudaMemcpyHostToDevice, e->stream));
-    CK(e, cudaStreamSynchronize(e->stream));
-    TspEncodeTiled encode = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", (void**)&encode, cudaEnableDefault, &qres) != cudaSuccess || !encode)
-        return fail(e, TSP_ECUDA, "cuTensorMapEncodeTiled is not available from this driver (TMA weight streaming needs it)");
-    const cuuint64_t gdim[2] = {64, (cuuint64_t)ts.img_rows};
-    const cuuint64_t gstr[1] = {128};
-    const cuuint32_t estr[2] = {1, 1};
-    const cuuint32_t bx[2] = {64, 128};  // one box == one 16 KB tile
-    const CUresult cr = encode(&e->ts_map, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, e->ts_img.p, gdim, gstr, bx, estr,
-                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (cr != CUDA_SUCCESS) return fail(e, TSP_ECUDA, "cuTensorMapEncodeTiled failed (%d)", (int)cr);
-    if ((rc = ensure(e, e->tc_status, sizeof(int)))) return rc;
-    CK(e, cudaMemset(e->tc_status.p, 0, sizeof(int)));
+    if ((rc = ts_upload(e, tb.img, ctab, e->ts_img, e->ts_ctab, e->ts_map, ts.img_rows))) return rc;
     e->has_tcs = true;
+    return TSP_OK;
+}
+
+// Streamed tcgen05 root network (root_tcs_kernel, tsp_stream.cuh): initial_inference (models.py:259-281) = the representation
+// MLP (any depth; widths <= 256, multiples of 16) -> min-max scale -> policy | value heads (one hidden layer <= 32 each).
+// TR_N = 32 observation rows per CTA are the MMAs' columns. Stages: one per representation layer (the last one has no
+// activation: its tiles are the hidden state, normalised in the epilogue), policy 1 | value 1, the two output layers
+// as one block-diagonal layer. Anything else keeps net_kernel (e->has_rtcs == false).
+int build_root_tcs(tsp_engine* e) {
+    e->has_rtcs = false;
+    const tsp_config& c = e->cfg;
+    if (e->nc != 5) return TSP_OK;
+    const auto& R = e->mlp[TSP_MLP_REPRESENTATION];
+    if (R.empty() || e->mlp[TSP_MLP_POLICY].size() != 2 || e->mlp[TSP_MLP_VALUE].size() != 2) return TSP_OK;
+    const HostLayer &P1 = e->mlp[TSP_MLP_POLICY][0], &P2 = e->mlp[TSP_MLP_POLICY][1];
+    const HostLayer &V1 = e->mlp[TSP_MLP_VALUE][0], &V2 = e->mlp[TSP_MLP_VALUE][1];
+    const int H = c.encoding_size, A = c.num_actions, L = (int)R.size();
+    const int PH = P1.out_dim, VH = V1.out_dim, NV = V2.out_dim;
+    if (L + 2 > TS_MAX_STAGES || H % 16 || H > 256 || R.back().out_dim != H || R.front().in_dim != c.obs_dim) return TSP_OK;
+    if (PH % 16 || VH % 16 || PH > 32 || VH > 32 || PH < 16 || VH < 16 || NV + A > 32) return TSP_OK;
+    int wmax = 64, n_acc_need = 2;
+    for (int l = 0; l < L; ++l) {
+        if (R[l].out_dim % 16 || R[l].out_dim > 256) return TSP_OK;
+        wmax = std::max(wmax, R[l].out_dim);
+        n_acc_need += (R[l].out_dim + 127) / 128;
+    }
+    if (n_acc_need > TS_MAX_ACC) return TSP_OK;
+    TsSched& ts = e->rts;
+    memset(&ts, 0, sizeof(ts));
+    TsBuilder tb{ts, TR_N};
+    ts.nt = TR_N; ts.n_stages = L + 2; ts.in_dim = c.obs_dim; ts.H = H;
+    auto mn_sbo = [](int K) { return TsBuilder::mn_sbo(K); };
+    // ---- B operands: X0 = the observation rows (K-major, inputs padded to 16), then two MN-major buffers used alternately by
+    // the layers; the second one takes X0's place (X0 is dead once the first layer has completed) ----
+    const int K0 = (c.obs_dim + 15) & ~15;
+    const int x0_sbo = (K0 / 8) * TS_X0_LBO;
+    const int buf_bytes = 2 * (TR_N / 8) * mn_sbo(wmax);
+    const int x0_bytes = 2 * (TR_N / 8) * x0_sbo;
+    const int bufA = (std::max(x0_bytes, buf_bytes) + 127) & ~127, bufB = 0;
+    ts.arena_bytes = (bufA + buf_bytes + 127) & ~127;
+    ts.x0_off = 0; ts.x0_sbo = x0_sbo; ts.x0_lo = (TR_N / 8) * x0_sbo;
+    // ---- out strip: value logits, then policy logits ----
+    ts.off_vl = 0; ts.off_rl = 0; ts.off_pl = NV;
+    int pitch = NV + A;
+    while (pitch % 32 != 8 && pitch % 32 != 24) ++pitch;
+    ts.out_pitch = pitch;
+    // ---- constant table ----
+    std::vector<float> ctab;
+    auto put = [&](const std::vector<float>& v, int n) {
+        const int at = (int)ctab.size();
+        for (int i = 0; i < n; ++i) ctab.push_back(v[(size_t)i]);
+        while (ctab.size() % 32) ctab.push_back(0.0f);
+        return at;
+    };
+    std::vector<int> t_b((size_t)L);
+    for (int l = 0; l < L; ++l) t_b[(size_t)l] = put(R[l].b, R[l].out_dim);
+    std::vector<float> bpv(64, 0.0f);
+    for (int r = 0; r < PH; ++r) bpv[(size_t)r] = P1.b[(size_t)r];
+    for (int r = 0; r < VH; ++r) bpv[(size_t)(32 + r)] = V1.b[(size_t)r];
+    const int t_bpv = put(bpv, 64);
+    std::vector<float> bout(32, 0.0f);
+    for (int r = 0; r < NV; ++r) bout[(size_t)(ts.off_vl + r)] = V2.b[(size_t)r];
+    for (int r = 0; r < A; ++r) bout[(size_t)(ts.off_pl + r)] = P2.b[(size_t)r];
+    const int t_bo = put(bout, 32);
+    for (int i = 0; i < 128; ++i) ctab.push_back(0.0f);
+    if ((int)ctab.size() > TS_MAX_CTAB) return TSP_OK;
+    ts.ctab_floats = (int)ctab.size();
+    // ---- stages ----
+    int acc = 0;
+    int in_off = 0, in_sbo = x0_sbo;
+    bool in_mn = false;
+    for (int l = 0; l < L; ++l) {
+        const HostLayer& Ly = R[l];
+        const int K = l == 0 ? K0 : Ly.in_dim;  // (inputs past obs_dim: zero weights against the zero padding of X0)
+        const int out_off = (l % 2 == 0) ? bufA : bufB, out_sbo = mn_sbo(Ly.out_dim);
+        ts.stage_tile[l] = tb.n_tiles; ts.stage_acc[l] = acc;
+        for (int t = 0; t < (Ly.out_dim + 127) / 128; ++t) {
+            const int rows = std::min(128, Ly.out_dim - 128 * t);
+            tb.add_layer(acc, rows, TsBuilder::box(rows), K,
+                         [&](int m, int k) { return k < Ly.in_dim ? Ly.W[(size_t)(128 * t + m) * Ly.in_dim + k] : 0.0f; }, in_off, in_sbo,
+                         in_mn, 2 * TR_N * acc);
+            // hidden layers: ELU -> operand of the next layer; the last layer (Identity, models.py:1150-1162): min-max scaled
+            tb.add_acc(acc, 2 * TR_N * acc, rows, l + 1 < L ? 0 : 1, 128 * t, out_off, out_sbo, t_b[(size_t)l] + 128 * t, -1, 0);
+            ++acc;
+        }
+        in_off = out_off; in_sbo = out_sbo; in_mn = true;
+    }
+    // policy layer 1 (rows 0..31) | value layer 1 (rows 32..63) on the normalised state
+    const int hh_off = (L % 2 == 0) ? bufA : bufB, hh_sbo = mn_sbo(64);
+    ts.stage_tile[L] = tb.n_tiles; ts.stage_acc[L] = acc;
+    tb.add_layer(acc, 64, 64, H, [&](int m, int k) {
+        if (m < 32) return m < PH ? P1.W[(size_t)m * H + k] : 0.0f;
+        return m - 32 < VH ? V1.W[(size_t)(m - 32) * H + k] : 0.0f;
+    }, in_off, in_sbo, true, 2 * TR_N * acc);
+    tb.add_acc(acc, 2 * TR_N * acc, 64, 0, 0, hh_off, hh_sbo, t_bpv, -1, 0);
+    ++acc;
+    // the two output layers as one block-diagonal layer over the 64 hidden inputs; rows == out-strip columns
+    ts.stage_tile[L + 1] = tb.n_tiles; ts.stage_acc[L + 1] = acc;
+    tb.add_layer(acc, NV + A, 32, 64, [&](int m, int k) {
+        if (m >= ts.off_pl) return (k < PH) ? P2.W[(size_t)(m - ts.off_pl) * PH + k] : 0.0f;
+        return (k >= 32 && k - 32 < VH) ? V2.W[(size_t)m * VH + (k - 32)] : 0.0f;
+    }, hh_off, hh_sbo, true, 2 * TR_N * acc);
+    tb.add_acc(acc, 2 * TR_N * acc, NV + A, 2, 0, 0, 0, t_bo, -1, 0);
+    ++acc;
+    ts.stage_tile[L + 2] = tb.n_tiles; ts.stage_acc[L + 2] = acc;
+    if (tb.overflow || acc > TS_MAX_ACC || 2 * TR_N * acc > TS_TMEM_COLS) return TSP_OK;
+    ts.n_tiles = tb.n_tiles; ts.n_acc = acc;
+    ts.img_rows = (int)(tb.img.size() / 64);
+    if (root_tcs_smem(ts) > 227 * 1024) return TSP_OK;
+    int rc;
+    if ((rc = ts_upload(e, tb.img, ctab, e->rts_img, e->rts_ctab, e->rts_map, ts.img_rows))) return rc;
+    e->has_rtcs = true;
     return TSP_OK;
 }
 
@@ -1099,6 +1238,7 @@ int build_schedules(tsp_engine* e) {
         hs.vl = add_chain(e, hs, TSP_MLP_VALUE, hs.hidden, 0);
         if ((rc = lower(e, hs, e->sch_root))) return rc;
         e->has_root = true;
+        if ((rc = build_root_tcs(e))) return rc;
     }
     {  // prediction: models.py:209-212
         HSched hs;
@@ -1264,7 +1404,41 @@ int launch_net(tsp_engine* e, const NetParams& p_in) {
     return TSP_OK;
 }
 
+// initial_inference (+ the root of the search) on tcgen05 with the weights streamed by TMA (root_tcs_kernel)
+int launch_root_tcs(tsp_engine* e, const NetParams& np) {
+    RootTcsParams p;
+    memset(&p, 0, sizeof(p));
+    const tsp_config& c = e->cfg;
+    p.B = np.B; p.b0 = np.b0; p.A = np.A; p.H = np.H; p.support = np.support; p.in_dim = c.obs_dim;
+    p.in = np.in;
+    p.ctab = reinterpret_cast<const float*>(e->rts_ctab.p);
+    p.status = reinterpret_cast<int*>(e->tc_status.p);
+    p.value = np.value; p.policy_logits = np.policy_logits; p.hidden_out = np.hidden_out; p.value_logits = np.value_logits;
+    p.tree_init = np.tree_init; p.add_noise = np.add_noise; p.uniform_policy = np.uniform_policy;
+    p.blocks_per_tree = np.blocks_per_tree; p.hidden_per_tree = np.hidden_per_tree;
+    p.one_minus_frac = np.one_minus_frac; p.frac = np.frac;
+    p.blocks = np.blocks; p.hidden_pool = np.hidden_pool; p.hdr = np.hdr; p.rootprior = np.rootprior; p.rootact = np.rootact;
+    p.legal = np.legal; p.num_legal = np.num_legal; p.noise = np.noise;
+    p.trace_root = np.trace_root; p.root_pred = np.root_pred; p.root_hidden = np.root_hidden;
+    if (!p.tree_init && !p.hidden_out) {  // the epilogue writes the hidden state somewhere: a scratch array
+        int rc = ensure(e, e->rts_hidden, (size_t)np.B * np.H * sizeof(float));
+        if (rc) return rc;
+        p.hidden_out = reinterpret_cast<float*>(e->rts_hidden.p);
+    }
+    const size_t smem = std::max(root_tcs_smem(e->rts), (size_t)120 * 1024);  // one CTA per SM (it owns the SM's tensor memory)
+    int rc = set_smem(e, root_tcs_kernel, smem);
+    if (rc) return rc;
+    const int grid = (np.B - np.b0 + TR_N - 1) / TR_N;
+    root_tcs_kernel<<<grid, TR_THREADS, smem, e->stream>>>(p, e->rts, e->rts_map);
+    CK(e, cudaGetLastError());
+    e->stats.kernel_launches++;
+    e->stats.root_kernel = 1;
+    return TSP_OK;
+}
+
 int launch_net_any(tsp_engine* e, const NetParams& p) {
+    if (p.mode == 0 && !p.fed_root && e->has_rtcs && !e->no_rtcs && e->nc == 5) return launch_root_tcs(e, p);
+    if (p.mode == 0) e->stats.root_kernel = 0;
     // wide observation strips: fewer rows per CTA keep the strip under the shared-memory limit
     const int TM = (net_smem(p.sched, 32) <= 100 * 1024) ? 32 : 16;
     if (e->nc == 5) return TM == 32 ? launch_net<5, 32>(e, p) : launch_net<5, 16>(e, p);
@@ -1688,6 +1862,7 @@ int tsp_create(const tsp_config* cfg, tsp_handle* out) {
     if (const char* t = getenv("TSP_NO_WLO")) e->no_wlo = atoi(t) != 0;
     if (const char* t = getenv("TSP_NO_TC")) e->no_tc = atoi(t) != 0;
     if (const char* t = getenv("TSP_NO_TCS")) e->no_tcs = atoi(t) != 0;
+    if (const char* t = getenv("TSP_NO_RTCS")) e->no_rtcs = atoi(t) != 0;
     if (const char* t = getenv("TSP_NO_OVERLAP")) e->no_overlap = atoi(t) != 0;
     if (const char* t = getenv("TSP_TC_NOFOLD")) e->tc_nofold = atoi(t) != 0;
     if (const char* t = getenv("TSP_NO_WGLOBAL")) e->no_wglobal = atoi(t) != 0;
@@ -1761,7 +1936,7 @@ int tsp_destroy(tsp_handle e) {
                       &e->s_legal, &e->s_nlegal, &e->s_noise, &e->s_tie, &e->s_chance, &e->s_fedroot, &e->s_fed,
                       &e->s_visits, &e->s_rootv, &e->s_cval, &e->s_cprior, &e->s_crew, &e->s_depth, &e->s_rpred,
                       &e->s_rhid, &e->s_nrec, &e->s_troot, &e->s_trace, &e->s_tdepth, &e->n_in, &e->n_act, &e->tc_img[0],
-                      &e->tc_img[1], &e->tc_ctab[0], &e->tc_ctab[1], &e->tc_status, &e->ts_img, &e->ts_ctab})
+                      &e->tc_img[1], &e->tc_ctab[0], &e->tc_ctab[1], &e->tc_status, &e->ts_img, &e->ts_ctab, &e->rts_img, &e->rts_ctab, &e->rts_hidden})
         release(*b);
     for (auto& b : e->n_o) release(b);
     for (auto& ev : e->ev)
@@ -2276,14 +2451,14 @@ int tsp_export_tree(tsp_handle e, int32_t root_index, tsp_tree_info* info, void*
 }
 
 static int check_tc_status(tsp_engine* e) {
-    if ((!e->has_tc && !e->has_tcs) || !e->tc_status.p) return TSP_OK;
+    if ((!e->has_tc && !e->has_tcs && !e->has_rtcs) || !e->tc_status.p) return TSP_OK;
     int st = 0;
     CK(e, cudaMemcpy(&st, e->tc_status.p, sizeof(int), cudaMemcpyDeviceToHost));
     if (st) {  // report once: the flag is cleared so that later searches are judged on their own
         cudaMemset(e->tc_status.p, 0, sizeof(int));
         if (st == 2)
-            return fail(e, TSP_ECUDA, "tcgen05 search kernel (streamed weights): an activation left the fp16-split range (|x| > 6e4); "
-                                      "the results of that search are invalid -- set TSP_NO_TCS=1 to search this network on the mma.sync kernels");
+            return fail(e, TSP_ECUDA, "tcgen05 kernels with streamed weights: an observation or activation left the fp16-split range (|x| > 6e4); "
+                                      "the results of that call are invalid -- set TSP_NO_TCS=1 / TSP_NO_RTCS=1 to run this network on the mma.sync kernels");
         return fail(e, TSP_ECUDA, "tcgen05 search kernel: mbarrier wait timed out (the results of that search are invalid)");
     }
     return TSP_OK;

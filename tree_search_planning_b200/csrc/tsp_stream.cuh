@@ -40,14 +40,15 @@
 
 namespace tsp {
 
-constexpr int TS_N = 64;          // trees per CTA == N of every MMA
+constexpr int TS_N = 64;          // trees per CTA == N of every MMA of the search kernel (the root kernel runs 32 rows per CTA)
 constexpr int TS_NS = 4;          // ring slots (8 were measured: no gain -- the stream is bound by shared-memory bandwidth, not latency)
 constexpr int TS_X0_LBO = 144;    // gathered state, K-major: bytes between core matrices along K (128 + 16 of padding: the
                                   // 16-byte stores of a tree's 8 lanes hit different banks; dense 128 cost 1k cycles per simulation)
 constexpr int TS_SLOT = 16384;    // bytes per slot: 128 rows x 64 inputs fp16
-constexpr int TS_MAX_TILES = 40;
+constexpr int TS_MAX_TILES = 72;
 constexpr int TS_MAX_ACC = 8;
-constexpr int TS_STAGES = 4;
+constexpr int TS_STAGES = 4;      // stages of the recurrent inference (search kernel)
+constexpr int TS_MAX_STAGES = 7;  // the root network: representation layers + 2
 constexpr int TS_TMEM_COLS = 512;
 constexpr int TS_MAX_CTAB = 2048;  // floats: biases and one-hot rows
 constexpr float TS_SPLIT = 2048.0f, TS_INV_SPLIT = 1.0f / 2048.0f;
@@ -62,7 +63,7 @@ struct TsTile {       // one weight tile: one ring slot fill and the MMAs that c
     int b_sbo;        // bytes between 8-tree groups
     short b_lbo;      // bytes between core matrices along K: TS_X0_LBO (K-major) or 128 (MN-major)
     short b_step;     // descriptor units (16 bytes) per k-step
-    short d_col;      // accumulator: acc0 at d_col, acc1 at d_col + 64
+    short d_col;      // accumulator: acc0 at d_col, acc1 at d_col + nt
     char kind;        // 0: W1 tile (acc0 += W1 X1, acc1 += W1 X2), 1: W2 tile (acc1 += W2 X1)
     char first;       // first tile of its accumulator: k-step 0 overwrites
     char b_mn;        // B operand major: 0 K, 1 MN
@@ -89,13 +90,14 @@ struct TsSched {
     int n_tiles, n_acc, arena_bytes, out_pitch;
     int off_vl, off_rl, off_pl, ctab_floats;
     int x0_off, x0_sbo, x0_lo, H;       // gathered hidden state: K-major, LBO TS_X0_LBO
-    int stage_tile[TS_STAGES + 1];      // tiles [stage_tile[s], stage_tile[s + 1]) read the B operand published before stage s
-    int stage_acc[TS_STAGES + 1];
-    int img_rows, pad;
+    int stage_tile[TS_MAX_STAGES + 1];  // tiles [stage_tile[s], stage_tile[s + 1]) read the B operand published before stage s
+    int stage_acc[TS_MAX_STAGES + 1];
+    int img_rows, n_stages;
+    int nt, in_dim;                     // columns of the MMAs (trees / rows per CTA: 64 or 32); root network: observation width
     TsTile tile[TS_MAX_TILES];
     TsEpi acc[TS_MAX_ACC];
 };
-static_assert(sizeof(TsSched) <= 2048, "TsSched travels as a kernel parameter (constant bank: uniform reads)");
+static_assert(sizeof(TsSched) <= 3072, "TsSched travels as a kernel parameter (constant bank: uniform reads)");
 
 // shared-memory control block of the streamed path
 struct TsCtl {
@@ -116,8 +118,8 @@ __device__ __forceinline__ void ts_mma(uint32_t d, uint32_t a_lo, uint32_t a_hi,
         "tcgen05.mma.cta_group::1.kind::f16 [%0], ad, bd, %5, p;\n\t}\n" ::"r"(d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc)
         : "memory");
 }
-constexpr uint32_t TS_IDESC = (1u << 4) | ((uint32_t)(TS_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);  // D f32, A / B f16, A K-major
-constexpr uint32_t TS_IDESC128 = (1u << 4) | ((uint32_t)(2 * TS_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);  // N = 128: [X1 | X2]
+// instruction descriptor: D f32, A / B f16, A K-major, M = 128, N columns
+__device__ __forceinline__ uint32_t ts_idesc(int n) { return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24); }
 
 // Bounded wait that gives up at once when another thread of the CTA has already timed out (a lost TMA / commit must
 // neither hang the GPU nor stretch into minutes of serial time-outs).
@@ -169,10 +171,12 @@ __device__ __forceinline__ bool ts_issuer(const TsSched& ts, uint32_t tmem, uint
     bool ok = true;
     int g = 0;
     uint32_t br = 0;
-    long long w_b[TS_STAGES] = {0, 0, 0, 0}, w_full = 0, c0 = 0, c1 = 0;
+    long long w_b[TS_MAX_STAGES] = {0, 0, 0, 0, 0, 0, 0}, w_full = 0, c0 = 0, c1 = 0;
+    const int n_stages = ts.n_stages, nt = ts.nt;
+    const uint32_t idesc_w1 = ts_idesc(2 * nt), idesc_w2 = ts_idesc(nt);  // W1 [X1 | X2]: 2 nt columns; W2 X1: nt
     const long long t_begin = dbg ? clock64() : 0;
     for (int it = 0; it < S && ok; ++it)
-        for (int st = 0; st < TS_STAGES; ++st) {
+        for (int st = 0; st < n_stages; ++st) {
             if (dbg) c0 = clock64();
             ok = ts_wait(bready, br, abort) && ok;  // all tree warps have published this stage's B operand
             if (dbg) w_b[st] += clock64() - c0;
@@ -193,7 +197,7 @@ __device__ __forceinline__ bool ts_issuer(const TsSched& ts, uint32_t tmem, uint
                 const uint32_t bstep = (uint32_t)tl.b_step;
                 const int ks = tl.ksteps;
                 if (tl.kind == 0) {  // W1 [X1 | X2] -> acc0 | acc1: one MMA of N = 128
-                    const uint32_t idesc = TS_IDESC128 | ((uint32_t)tl.b_mn << 16);
+                    const uint32_t idesc = idesc_w1 | ((uint32_t)tl.b_mn << 16);
                     const uint32_t d = tmem + (uint32_t)tl.d_col;
                     uint32_t acc = tl.first ? 0u : 1u;
 #pragma unroll 4
@@ -202,8 +206,8 @@ __device__ __forceinline__ bool ts_issuer(const TsSched& ts, uint32_t tmem, uint
                         a_lo += 16; b1 += bstep; acc = 1u;
                     }
                 } else {             // W2 X1 -> acc1
-                    const uint32_t idesc = TS_IDESC | ((uint32_t)tl.b_mn << 16);
-                    const uint32_t d = tmem + (uint32_t)tl.d_col + 64;
+                    const uint32_t idesc = idesc_w2 | ((uint32_t)tl.b_mn << 16);
+                    const uint32_t d = tmem + (uint32_t)(tl.d_col + nt);
 #pragma unroll 4
                     for (int j = 0; j < ks; ++j) {
                         ts_mma(d, a_lo, a_hi, b1, b_hi, idesc, 1u);
@@ -215,7 +219,7 @@ __device__ __forceinline__ bool ts_issuer(const TsSched& ts, uint32_t tmem, uint
             }
         }
     if (dbg) {  // issuer: [16 + s] waiting for the B operand of stage s, [20] waiting for full slots, [21] total
-        for (int st = 0; st < TS_STAGES; ++st) atomicAdd(dbg + 16 + st, (unsigned long long)w_b[st]);
+        for (int st = 0; st < TS_STAGES; ++st) atomicAdd(dbg + 16 + st, (unsigned long long)w_b[st]);  // (search kernel: 4 stages)
         atomicAdd(dbg + 20, (unsigned long long)w_full);
         atomicAdd(dbg + 21, (unsigned long long)(clock64() - t_begin));
     }
@@ -248,8 +252,12 @@ __device__ __forceinline__ void ts_split8(const float (&y)[8], uint4& hi, uint4&
 __device__ __forceinline__ bool ts_epi_warp(const TsEpi& ep, uint32_t tmem_q, int q, int c0, int lane, unsigned char* __restrict__ arena,
                                             float* __restrict__ outs, int out_pitch, const float* __restrict__ ctab,
                                             const int* __restrict__ row_action, uint32_t accbar, uint32_t parity, volatile int* abort,
-                                            float& amax) {
-    if (32 * q >= ep.rows) return true;  // this quarter holds no row of the tile (warp-uniform)
+                                            float& amax, int nt) {
+    // A warp whose lane quarter holds no row of the tile still waits for the tile: a warp must not publish the NEXT stage's
+    // operand (mbarrier arrival) before the CURRENT stage has started, or its arrival would be counted in the phase that
+    // is still collecting the other warps' arrivals and release the MMAs early. The accumulator barrier of this stage
+    // cannot complete before that phase has.
+    if (32 * q >= ep.rows) return ts_wait(accbar, parity, abort);  // (warp-uniform)
     const int r = 32 * q + lane;
     const bool on = r < ep.rows;
     const float bias = on ? ctab[ep.cidx + r] : 0.0f;
@@ -264,7 +272,7 @@ __device__ __forceinline__ bool ts_epi_warp(const TsEpi& ep, uint32_t tmem_q, in
         const int n0 = c0 + 8 * h;
         uint32_t v0[8], v1[8];
         ts_ld8(tmem_q + (uint32_t)(ep.d_col + n0), v0);
-        ts_ld8(tmem_q + (uint32_t)(ep.d_col + 64 + n0), v1);
+        ts_ld8(tmem_q + (uint32_t)(ep.d_col + nt + n0), v1);
         float add[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) add[i] = bias;
@@ -323,7 +331,8 @@ __device__ __forceinline__ bool ts_mlp(const TsSched& ts, TsCtl* __restrict__ ct
     fence_async_smem();
     __syncwarp();
     if (lane == 0) ts_arrive(bready);
-    for (int st = 0; st < TS_STAGES; ++st) {
+    const int n_stages = ts.n_stages;
+    for (int st = 0; st < n_stages; ++st) {
         if (tm) t0 = clock64();
         const int a_begin = ts.stage_acc[st], a_end = ts.stage_acc[st + 1];
         bool has_xs = false;
@@ -349,7 +358,7 @@ __device__ __forceinline__ bool ts_mlp(const TsSched& ts, TsCtl* __restrict__ ct
                 for (int h = 0; h < 2; ++h) {
                     uint32_t v0[8], v1[8];
                     ts_ld8(tmem_q + (uint32_t)(ep.d_col + c0 + 8 * h), v0);
-                    ts_ld8(tmem_q + (uint32_t)(ep.d_col + 64 + c0 + 8 * h), v1);
+                    ts_ld8(tmem_q + (uint32_t)(ep.d_col + ts.nt + c0 + 8 * h), v1);
                     ts_ld_wait();
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
@@ -406,7 +415,7 @@ __device__ __forceinline__ bool ts_mlp(const TsSched& ts, TsCtl* __restrict__ ct
                     const int n0 = c0 + 8 * h;
                     uint32_t v0[8], v1[8];
                     ts_ld8(tmem_q + (uint32_t)(ep.d_col + n0), v0);
-                    ts_ld8(tmem_q + (uint32_t)(ep.d_col + 64 + n0), v1);
+                    ts_ld8(tmem_q + (uint32_t)(ep.d_col + ts.nt + n0), v1);
                     float mn[8], inv[8];
 #pragma unroll
                     for (int i = 0; i < 8; i += 2) {
@@ -444,8 +453,8 @@ __device__ __forceinline__ bool ts_mlp(const TsSched& ts, TsCtl* __restrict__ ct
         for (int a = a_begin; a < a_end; ++a)
             if (ts.acc[a].kind != 1)
                 ok = ts_epi_warp(ts.acc[a], tmem_q, q, c0, lane, arena, outs, ts.out_pitch, ctab, row_action, acc0 + 8 * a, parity, abort,
-                                 amax) && ok;
-        if (st + 1 < TS_STAGES) {  // this warp's share of the next stage's B operand is in place
+                                 amax, ts.nt) && ok;
+        if (st + 1 < n_stages) {  // this warp's share of the next stage's B operand is in place
             fence_async_smem();
             tc_fence_before();
             __syncwarp();
@@ -456,6 +465,184 @@ __device__ __forceinline__ bool ts_mlp(const TsSched& ts, TsCtl* __restrict__ ct
     tc_fence_before();
     asm volatile("bar.sync 1, %0;" ::"n"(TREE_THREADS) : "memory");  // the logits of every tree are in the out strip
     return ok;
+}
+
+// ------------------------------------------------------------------------------------------------ root network ----
+// initial_inference (models.py:259-281: representation -> min-max scale -> policy / value heads) + support_to_scalar +
+// the root of the search (self_play.py:335-376: softmax over the ordered legal list, exploration noise, root block and
+// tree header) for TR_N observation rows per CTA on the same streamed tcgen05 machinery: the rows are the MMAs' columns,
+// every Linear layer streams its fp16-split weight tiles by TMA, the min-max scaling runs in the accumulator layout and
+// writes the hidden state straight to where it is kept (the tree's hidden-state slot 0, or the caller's array).
+constexpr int TR_N = 32;           // rows per CTA: the K-major image of 32 observation rows (up to ~1,000 inputs) fits beside the ring
+constexpr int TR_THREADS = TR_N * GW + 64;
+
+struct RootTcsParams {
+    int B, b0;                 // rows [b0, B) of this launch
+    int A, H, support, in_dim;
+    const float* in;           // observations [B][in_dim]
+    const float* ctab;
+    int* status;
+    // outputs of tsp_initial_inference (device, may be null)
+    float* value; float* policy_logits; float* hidden_out; float* value_logits;
+    // the root of the search (tree_init != 0)
+    int tree_init, add_noise, uniform_policy, blocks_per_tree, hidden_per_tree;
+    double one_minus_frac, frac;
+    void* blocks; float* hidden_pool; TreeHeader* hdr; double* rootprior; int* rootact;
+    const int* legal; const int* num_legal; const double* noise;
+    float* trace_root; float* root_pred; float* root_hidden;
+};
+
+__global__ void __launch_bounds__(TR_THREADS, 1)
+root_tcs_kernel(const __grid_constant__ RootTcsParams p, const __grid_constant__ TsSched ts, const __grid_constant__ CUtensorMap tmap) {
+    extern __shared__ __align__(16) float smem[];
+    constexpr int ROW_THREADS = TR_N * GW;
+    const int tid = threadIdx.x;
+    float* ctab = smem;
+    const int ctab_n = (ts.ctab_floats + 3) & ~3;
+    TsCtl* ctl = reinterpret_cast<TsCtl*>(smem + ctab_n);
+    const uint32_t base_s = smem_u32(smem);
+    const int goff = (int)(((base_s + (uint32_t)(reinterpret_cast<unsigned char*>(ctl + 1) - reinterpret_cast<unsigned char*>(smem)) + 127u) & ~127u) - base_s);
+    unsigned char* gbase = reinterpret_cast<unsigned char*>(smem) + goff;  // TMA destinations: 128-byte aligned
+    const uint32_t ring = base_s + (uint32_t)goff;
+    unsigned char* arena = gbase + TS_NS * TS_SLOT;
+    float* outs = reinterpret_cast<float*>(arena + ts.arena_bytes);
+    __builtin_assume(__isShared(arena));
+    __builtin_assume(__isShared(outs));
+    __builtin_assume(__isShared(ctab));
+    __builtin_assume(__isShared(ctl));
+    const int warp_u = __shfl_sync(FULL, tid >> 5, 0);
+    for (int i = tid; i < ts.ctab_floats; i += TR_THREADS) ctab[i] = p.ctab[i];
+    for (int i = tid; i < (ts.arena_bytes >> 4); i += TR_THREADS) reinterpret_cast<uint4*>(arena)[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (tid == 0) {
+        for (int i = 0; i < TS_NS; ++i) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&ctl->full[i])));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&ctl->empty[i])));
+        }
+        for (int i = 0; i < TS_MAX_ACC; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&ctl->acc[i])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&ctl->bready)), "n"(ROW_THREADS / 32));
+        ctl->abort = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (tid < TS_N) {
+        ctl->mmk[0][tid][0] = INT_MAX; ctl->mmk[0][tid][1] = INT_MIN;
+        ctl->mmk[1][tid][0] = INT_MAX; ctl->mmk[1][tid][1] = INT_MIN;
+        ctl->hdst[tid] = 0ull;
+    }
+    if (warp_u == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&ctl->tmem_slot)), "n"(TS_TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = ctl->tmem_slot;
+    bool ok = true;
+    float amax = 0.0f;
+    const int n = tid >> 3, j = tid & 7;          // row of the CTA, lane of the row
+    const int b = p.b0 + blockIdx.x * TR_N + n;
+    const bool valid = tid < ROW_THREADS && b < p.B;
+    float* hid = nullptr;                          // where this row's hidden state is kept
+    if (valid) hid = p.tree_init ? p.hidden_pool + (size_t)b * p.hidden_per_tree * p.H : p.hidden_out + (size_t)b * p.H;
+    if (warp_u >= ROW_THREADS / 32) {  // service warps: TMA producer, MMA issuer
+        if (elect_one()) {
+            const uint32_t full0 = smem_u32(&ctl->full[0]), empty0 = smem_u32(&ctl->empty[0]);
+            if (warp_u == ROW_THREADS / 32)
+                ok = ts_producer(ts, &tmap, ring, full0, empty0, 1, &ctl->abort, nullptr);
+            else
+                ok = ts_issuer(ts, tmem_base, smem_u32(arena), ring, full0, empty0, smem_u32(&ctl->acc[0]), smem_u32(&ctl->bready), 1,
+                               &ctl->abort, nullptr);
+        }
+        __syncwarp();
+    } else {
+        // ---- the observation row as the K-major B operand of the first layer: chunks of 8 inputs, zero padded ----
+        if (j == 0) ctl->hdst[n] = valid ? (unsigned long long)hid : 0ull;
+        {
+            const int nchunks = ts.x0_sbo / TS_X0_LBO;  // padded input width / 8
+            unsigned char* d = arena + ts.x0_off + (n >> 3) * ts.x0_sbo + (n & 7) * 16;
+            const float* src = p.in + (size_t)(valid ? b : 0) * p.in_dim;
+            for (int c = j; c < nchunks; c += GW) {
+                float y[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int k = 8 * c + i;
+                    y[i] = (valid && k < p.in_dim) ? __ldg(src + k) : 0.0f;
+                    amax = fmaxf(amax, fabsf(y[i]));
+                }
+                uint4 hi, lo;
+                ts_split8(y, hi, lo);
+                *reinterpret_cast<uint4*>(d + c * TS_X0_LBO) = hi;
+                *reinterpret_cast<uint4*>(d + c * TS_X0_LBO + ts.x0_lo) = lo;
+            }
+        }
+        ok = ts_mlp<ROW_THREADS>(ts, ctl, tmem_base, arena, outs, ctab, nullptr, warp_u, tid & 31, 0, amax, nullptr);
+        // ---- the row's outputs: 8 lanes per row ----
+        const unsigned gmask = 0xFFu << ((tid & 31) & 24);
+        if (valid) {
+            const float* o = outs + n * ts.out_pitch;
+            const int V = 2 * p.support + 1;
+            const float value = support_to_scalar_group(o + ts.off_vl, p.support, j, gmask);
+            if (p.value && j == 0) p.value[b] = value;
+            if (p.policy_logits && j < p.A) p.policy_logits[(size_t)b * p.A + j] = o[ts.off_pl + j];
+            if (p.value_logits)
+                for (int i = j; i < V; i += GW) p.value_logits[(size_t)b * V + i] = o[ts.off_vl + i];
+            if (p.tree_init) {
+                // ---- root of the search: self_play.py:335-376 ----
+                const int nl = p.num_legal ? p.num_legal[b] : p.A;
+                const int a_j = (j < nl) ? (p.legal ? p.legal[(size_t)b * p.A + j] : j) : 0;
+                const float lg = (j < nl && !p.uniform_policy) ? o[ts.off_pl + a_j] : 0.0f;
+                const float prior = softmax_group(lg, j < nl, gmask);  // Node.expand, self_play.py:532-538
+                if (p.trace_root) {
+                    float* tr = p.trace_root + (size_t)b * REC;
+                    for (int i = j; i < REC; i += GW) tr[i] = 0.0f;
+                    __syncwarp(gmask);
+                    if (j == 0) { tr[0] = 1.0f; tr[1] = value; }
+                    if (j < nl) tr[4 + j] = prior;
+                }
+                double pr64 = (double)prior;
+                if (p.add_noise && j < nl)  // add_exploration_noise, self_play.py:540-549
+                    pr64 = __dadd_rn(__dmul_rn(pr64, p.one_minus_frac), __dmul_rn(p.noise[(size_t)b * p.A + j], p.frac));
+                p.rootprior[(size_t)b * GW + j] = (j < nl) ? pr64 : 0.0;
+                p.rootact[(size_t)b * GW + j] = a_j;
+                NodeBlock<5>* blk = reinterpret_cast<NodeBlock<5>*>(p.blocks) + (size_t)b * p.blocks_per_tree;
+                if (j < 5) {
+                    blk->visit[j] = 0;
+                    blk->child[j] = -1;
+                    blk->prior[j] = prior;
+                    blk->reward[j] = 0.0f;
+                    blk->vsum[j] = 0.0;
+                }
+                if (j == 0) {
+                    blk->parent = -1;
+                    blk->aux = 0;
+                    TreeHeader h;
+                    h.mm_min = CUDART_INF;
+                    h.mm_max = -CUDART_INF;
+                    h.root_vsum = 0.0;
+                    h.root_visit = 0;
+                    h.n_blocks = 1;
+                    h.n_tgroups = 0;
+                    h.max_depth = 0;
+                    h.n_sims = 0;
+                    h.k_tie = 0;
+                    h.k_chance = 0;
+                    h.n_rec = 0;
+                    h.root_pred = value;
+                    h.n_root = nl;
+                    p.hdr[b] = h;
+                    if (p.root_pred) p.root_pred[b] = value;
+                }
+                // (the epilogue of the last representation layer has written the hidden state into slot 0 of the tree)
+                if (p.root_hidden)
+                    for (int i = j; i < p.H; i += GW) p.root_hidden[(size_t)b * p.H + i] = hid[i];
+            }
+        }
+    }
+    if (!ok && p.status) atomicExch(p.status, 1);
+    if (!(amax <= TS_FP16_MAX) && p.status) atomicCAS(p.status, 0, 2);
+    tc_fence_before();
+    __syncthreads();
+    if (warp_u == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TS_TMEM_COLS));
 }
 
 }  // namespace tsp

@@ -56,7 +56,7 @@ class Stats(ctypes.Structure):
         ("last_root_ms", ctypes.c_float), ("sum_search_ms", ctypes.c_double), ("sum_root_ms", ctypes.c_double),
         ("timed_runs", ctypes.c_int64), ("sm_count", ctypes.c_int32), ("search_ctas", ctypes.c_int32),
         ("search_smem_bytes", ctypes.c_int32), ("trees_per_cta", ctypes.c_int32),
-        ("threads_per_cta", ctypes.c_int32), ("search_kernel", ctypes.c_int32),
+        ("threads_per_cta", ctypes.c_int32), ("search_kernel", ctypes.c_int32), ("root_kernel", ctypes.c_int32),
     ]
 
     def as_dict(self):
