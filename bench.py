@@ -362,7 +362,8 @@ def root_roofline(cfg, B, ex, peak):
     from tree_search_planning_b200.configs import observation_dim
     bpr = 4.0 * observation_dim(cfg) + 4.0 * cfg.encoding_size + 128.0
     achieved = bpr * B / max(ex["root_ms"] * 1e-3, 1e-9) / 1e9
-    return {"bound": "hbm", "kernel": "tsp::net_kernel (root)", "kernel_ms": ex["root_ms"], "achieved": achieved, "peak": peak,
+    name = "tsp::root_tcs_kernel" if ex["stats"].get("root_kernel") == 1 else "tsp::net_kernel (root)"
+    return {"bound": "hbm", "kernel": name, "kernel_ms": ex["root_ms"], "achieved": achieved, "peak": peak,
             "unit": "GB/s", "frac": achieved / peak, "algorithmic_bytes_per_root": bpr}
 
 

@@ -561,18 +561,29 @@ root_tcs_kernel(const __grid_constant__ RootTcsParams p, const __grid_constant__
             const int nchunks = ts.x0_sbo / TS_X0_LBO;  // padded input width / 8
             unsigned char* d = arena + ts.x0_off + (n >> 3) * ts.x0_sbo + (n & 7) * 16;
             const float* src = p.in + (size_t)(valid ? b : 0) * p.in_dim;
-            for (int c = j; c < nchunks; c += GW) {
-                float y[8];
+            // (four chunks = 32 independent loads in flight per lane: the row comes from HBM, and one chunk at a time made
+            // this loop a chain of eight memory latencies -- a quarter of the kernel)
+            for (int c0 = j; c0 < nchunks; c0 += 4 * GW) {
+                float y[4][8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int k = 8 * c + i;
-                    y[i] = (valid && k < p.in_dim) ? __ldg(src + k) : 0.0f;
-                    amax = fmaxf(amax, fabsf(y[i]));
+                for (int u = 0; u < 4; ++u)
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int k = 8 * (c0 + u * GW) + i;
+                        y[u][i] = (valid && k < p.in_dim) ? __ldg(src + k) : 0.0f;
+                    }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int c = c0 + u * GW;
+                    if (c < nchunks) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) amax = fmaxf(amax, fabsf(y[u][i]));
+                        uint4 hi, lo;
+                        ts_split8(y[u], hi, lo);
+                        *reinterpret_cast<uint4*>(d + c * TS_X0_LBO) = hi;
+                        *reinterpret_cast<uint4*>(d + c * TS_X0_LBO + ts.x0_lo) = lo;
+                    }
                 }
-                uint4 hi, lo;
-                ts_split8(y, hi, lo);
-                *reinterpret_cast<uint4*>(d + c * TS_X0_LBO) = hi;
-                *reinterpret_cast<uint4*>(d + c * TS_X0_LBO + ts.x0_lo) = lo;
             }
         }
         ok = ts_mlp<ROW_THREADS>(ts, ctl, tmem_base, arena, outs, ctab, nullptr, warp_u, tid & 31, 0, amax, nullptr);
