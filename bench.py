@@ -14,8 +14,9 @@ GPU (configs[1]); weak scaling: every rank searches its own 4,096 roots.
   e2e     the same metric through the C ABI call with HOST (pinned) buffers: the host->device copy
           of observations / noise / tie stream and the device->host read of the root statistics are
           inside the timed region.
-  roofline  dominant kernel = tsp::search_tc_kernel (MLP on tcgen05, weights in tensor memory; tsp::search_fast_kernel /
-          tsp::search_kernel for networks outside its envelope); achieved = algorithmic bytes per launch
+  roofline  dominant kernel = tsp::search_tc_kernel (MLP on tcgen05, weights in tensor memory; cross-merge rows:
+          tsp::search_tcs_kernel, weights streamed by TMA; tsp::search_fast_kernel / tsp::search_kernel for networks
+          outside both envelopes); `kernels` adds the root kernel (tsp::root_tcs_kernel); achieved = algorithmic bytes per launch
           ((108*D + 8*H + 112) B per simulation, SURVEY 8d, D = measured mean selection depth)
           / its mean launch duration (CUDA events recorded by the engine around every launch).
   cpu_baseline  the CPU oracle (C restatement of the reference algorithm, oracle/) timed on the
@@ -382,7 +383,8 @@ def measure_row(torch, dist, tsp, tag, game, B_total, S, steps, warmup, device, 
         row.update(value=B_total * S * steps / t, unit=UNIT, ms_per_step=1e3 * t / steps, roots_per_gpu=se.n_local,
                    kernel=kernel_name(ex["stats"], tsp.variant_of(cfg)), kernel_ms=ex["search_ms"], root_ms=ex["root_ms"],
                    trees_per_cta=ex["stats"]["trees_per_cta"], search_ctas=ex["stats"]["search_ctas"],
-                   roofline=roofline_of(cfg, se.n_local, S, ex, peak, peak_src), root_roofline=root_roofline(cfg, se.n_local, ex, peak))
+                   roofline=roofline_of(cfg, se.n_local, S, ex, peak, peak_src, tag="%s_B%d_S%d" % (game, se.n_local, S)),
+                   root_roofline=root_roofline(cfg, se.n_local, ex, peak))
         if e2e:
             t2, ex2 = time_config(torch, dist, se, cfg, S, steps, warmup, device, world, rank, True, flush, 2000)
             row["e2e"] = {"value": B_total * S * steps / t2, "unit": UNIT, "ms_per_step": 1e3 * t2 / steps,
