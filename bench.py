@@ -477,6 +477,10 @@ def main():
         "clocks": clocks,
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": ex_e2e["h2d"], "d2h_bytes_per_step": ex_e2e["d2h"],
                 "ms_per_step": 1e3 * t_e2e / args.steps, "wall_ms_per_step": ex_e2e["wall_ms"] / args.steps,
+                # where an end-to-end step goes (CUDA events of the engine around its launches): `upload_wait_and_root_ms` is
+                # the interval from the start of tsp_run's device work to the end of the root kernel, i.e. what is left of
+                # the host->device copy after its overlap with the previous search + the root kernel
+                "search_kernel_ms": ex_e2e["search_ms"], "upload_wait_and_root_ms": ex_e2e["root_ms"],
                 "note": "sum of per-step CUDA-event intervals on the engine's stream; wall_ms_per_step is the host clock over the "
                         "same steps (includes the untimed L2 flushes); the upload of step i + 1 overlaps the search of step i"},
         "gpu_launches": ex_dev["launches"],

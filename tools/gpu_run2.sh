@@ -1,9 +1,9 @@
-timeout 1200 python -m pytest tests/ -q -m gpu -x -o faulthandler_timeout=300 2>&1 | grep -v "^$" | tail -8
-timeout 280 python bench.py > gpurun_out/r2j_bench.json 2> gpurun_out/r2j_bench.err; echo "bench rc=$?"
+timeout 600 python bench.py --no-configs --no-cpu-baseline --steps 300 > gpurun_out/r2k_a.json 2>/dev/null
+TSP_NO_ZERO_COPY=1 timeout 600 python bench.py --no-configs --no-cpu-baseline --steps 300 > gpurun_out/r2k_b.json 2>/dev/null
 python - <<'PY'
 import json
-d=json.loads(open('gpurun_out/r2j_bench.json').read().strip().splitlines()[-1])
-print({k:d[k] for k in ('value','ms_per_step','e2e','roofline','root_roofline','gpu_launches') if k in d})
-for r in d.get('configs',[]):
-    print(r['tag'], '%.3e'%r['value'], 'ms', round(r['ms_per_step'],3), 'kernel_ms', round(r['kernel_ms'],3), 'root_ms', round(r['root_ms'],4), r['kernel'], 'frac', round(r['roofline']['frac'],4), 'e2e %.3e'%r['e2e']['value'])
+for f in ("a","b"):
+    d=json.loads(open('gpurun_out/r2k_%s.json'%f).read().strip().splitlines()[-1])
+    print(f, "value %.4e (%.4f ms) e2e %.4e" % (d['value'], d['ms_per_step'], d['e2e']['value']), {k:round(v,4) for k,v in d['e2e'].items() if k.endswith('ms') or k.endswith('ms_per_step')})
 PY
+timeout 900 python -m pytest tests/ -q -m gpu -x -o faulthandler_timeout=300 2>&1 | tail -3

@@ -81,6 +81,7 @@ struct tsp_engine {
     InSet in_set[2];
     int in_flip = 0;
     bool no_overlap = false;  // TSP_NO_OVERLAP
+    bool no_zero_copy = false;  // TSP_NO_ZERO_COPY: stage + copy HOST outputs even when they are pinned
     // ring of event triples (before root kernel, between, after search kernel), drained lazily
     static constexpr int EV_RING = 1024;
     std::vector<cudaEvent_t> ev;
@@ -1765,6 +1766,24 @@ int stage_in(tsp_engine* e, int memory, const T* src, size_t count, DevBuf& buf,
     return TSP_OK;
 }
 
+// A HOST output array in pinned (page-locked) memory is written by the kernels directly: under unified addressing such
+// memory is mapped into the device's address space, the few hundred KB of root statistics leave as posted PCIe writes while
+// the kernel's tail still runs, and no device->host copy is queued behind the search (each one costs ~8 us of stream
+// time). Pageable host arrays get a staging buffer and a copy. Returns the device alias or nullptr.
+// (Only arrays up to 4 MB -- the root statistics; a pinned trace buffer of many MB written word by word from inside the
+// simulation loop is better off staged.)
+template <typename T>
+T* pinned_alias(tsp_engine* e, T* host, size_t count) {
+    if (e->no_zero_copy || count * sizeof(T) > ((size_t)4 << 20)) return nullptr;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, host) != cudaSuccess) {
+        cudaGetLastError();  // (pageable memory on older drivers: an error, not a type)
+        return nullptr;
+    }
+    if (at.type != cudaMemoryTypeHost || !at.devicePointer) return nullptr;
+    return reinterpret_cast<T*>(at.devicePointer);
+}
+
 template <typename T>
 int stage_out(tsp_engine* e, int memory, T* dst, size_t count, DevBuf& buf, T** out) {
     if (!dst) {
@@ -1773,6 +1792,11 @@ int stage_out(tsp_engine* e, int memory, T* dst, size_t count, DevBuf& buf, T** 
     }
     if (memory == TSP_MEM_DEVICE) {
         *out = dst;
+        return TSP_OK;
+    }
+    if (T* alias = pinned_alias(e, dst, count)) {
+        *out = alias;
+        e->stats.bytes_d2h += (int64_t)(count * sizeof(T));
         return TSP_OK;
     }
     int rc = ensure(e, buf, count * sizeof(T));
@@ -1784,6 +1808,7 @@ int stage_out(tsp_engine* e, int memory, T* dst, size_t count, DevBuf& buf, T** 
 template <typename T>
 int copy_out(tsp_engine* e, int memory, T* dst, const T* dev, size_t count) {
     if (!dst || memory == TSP_MEM_DEVICE) return TSP_OK;
+    if (reinterpret_cast<const void*>(dev) == reinterpret_cast<const void*>(pinned_alias(e, dst, count))) return TSP_OK;  // written in place
     CK(e, cudaMemcpyAsync(dst, dev, count * sizeof(T), cudaMemcpyDeviceToHost, e->stream));
     e->stats.bytes_d2h += (int64_t)(count * sizeof(T));
     return TSP_OK;
@@ -1864,6 +1889,7 @@ int tsp_create(const tsp_config* cfg, tsp_handle* out) {
     if (const char* t = getenv("TSP_NO_TCS")) e->no_tcs = atoi(t) != 0;
     if (const char* t = getenv("TSP_NO_RTCS")) e->no_rtcs = atoi(t) != 0;
     if (const char* t = getenv("TSP_NO_OVERLAP")) e->no_overlap = atoi(t) != 0;
+    if (const char* t = getenv("TSP_NO_ZERO_COPY")) e->no_zero_copy = atoi(t) != 0;
     if (const char* t = getenv("TSP_TC_NOFOLD")) e->tc_nofold = atoi(t) != 0;
     if (const char* t = getenv("TSP_NO_WGLOBAL")) e->no_wglobal = atoi(t) != 0;
     if (const char* t = getenv("TSP_FORCE_WGLOBAL")) e->force_wglobal = atoi(t) != 0;
