@@ -72,6 +72,7 @@ struct tsp_engine {
     cudaStream_t copy_stream = nullptr;
     static constexpr int OBS_CHUNKS = 4;
     cudaEvent_t ev_chunk[OBS_CHUNKS] = {};
+    cudaEvent_t ev_root_out = nullptr;  // the root kernel's HOST outputs have left on the copy stream
     // Two sets of input staging buffers, used alternately: the inputs of run i + 1 cross PCIe on the copy stream while
     // the search of run i (which still reads its own set: tie / chance streams, noise) is running.
     struct InSet {
@@ -1784,8 +1785,11 @@ T* pinned_alias(tsp_engine* e, T* host, size_t count) {
     return reinterpret_cast<T*>(at.devicePointer);
 }
 
+// `in_place`: false for the outputs of the ROOT kernel -- its few scattered words per row would leave as thousands of
+// small PCIe writes the kernel has to drain before the search can start (measured: +24 us); they are staged and copied on
+// the copy stream while the search runs instead.
 template <typename T>
-int stage_out(tsp_engine* e, int memory, T* dst, size_t count, DevBuf& buf, T** out) {
+int stage_out(tsp_engine* e, int memory, T* dst, size_t count, DevBuf& buf, T** out, bool in_place = true) {
     if (!dst) {
         *out = nullptr;
         return TSP_OK;
@@ -1794,7 +1798,7 @@ int stage_out(tsp_engine* e, int memory, T* dst, size_t count, DevBuf& buf, T** 
         *out = dst;
         return TSP_OK;
     }
-    if (T* alias = pinned_alias(e, dst, count)) {
+    if (T* alias = in_place ? pinned_alias(e, dst, count) : nullptr) {
         *out = alias;
         e->stats.bytes_d2h += (int64_t)(count * sizeof(T));
         return TSP_OK;
@@ -1806,10 +1810,17 @@ int stage_out(tsp_engine* e, int memory, T* dst, size_t count, DevBuf& buf, T** 
 }
 
 template <typename T>
-int copy_out(tsp_engine* e, int memory, T* dst, const T* dev, size_t count) {
+int copy_out(tsp_engine* e, int memory, T* dst, const T* dev, size_t count, cudaStream_t stream = nullptr) {
     if (!dst || memory == TSP_MEM_DEVICE) return TSP_OK;
-    if (reinterpret_cast<const void*>(dev) == reinterpret_cast<const void*>(pinned_alias(e, dst, count))) return TSP_OK;  // written in place
-    CK(e, cudaMemcpyAsync(dst, dev, count * sizeof(T), cudaMemcpyDeviceToHost, e->stream));
+    {   // written in place: `dev` is the device alias of a pinned HOST array (stage_out)
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, dev) == cudaSuccess) {
+            if (at.type == cudaMemoryTypeHost) return TSP_OK;
+        } else {
+            cudaGetLastError();
+        }
+    }
+    CK(e, cudaMemcpyAsync(dst, dev, count * sizeof(T), cudaMemcpyDeviceToHost, stream ? stream : e->stream));
     e->stats.bytes_d2h += (int64_t)(count * sizeof(T));
     return TSP_OK;
 }
@@ -1907,6 +1918,7 @@ int tsp_create(const tsp_config* cfg, tsp_handle* out) {
         return bail(fail(e, TSP_ECUDA, "cudaStreamCreate failed"));
     for (auto& ce : e->ev_chunk)
         if (cudaEventCreateWithFlags(&ce, cudaEventDisableTiming) != cudaSuccess) return bail(fail(e, TSP_ECUDA, "cudaEventCreate failed"));
+    if (cudaEventCreateWithFlags(&e->ev_root_out, cudaEventDisableTiming) != cudaSuccess) return bail(fail(e, TSP_ECUDA, "cudaEventCreate failed"));
     for (auto& is : e->in_set)
         if (cudaEventCreateWithFlags(&is.done, cudaEventDisableTiming) != cudaSuccess) return bail(fail(e, TSP_ECUDA, "cudaEventCreate failed"));
     e->ev.resize(3 * tsp_engine::EV_RING, nullptr);
@@ -1967,6 +1979,7 @@ int tsp_destroy(tsp_handle e) {
     for (auto& b : e->n_o) release(b);
     for (auto& ev : e->ev)
         if (ev) cudaEventDestroy(ev);
+    if (e->ev_root_out) cudaEventDestroy(e->ev_root_out);
     for (auto& ce : e->ev_chunk)
         if (ce) cudaEventDestroy(ce);
     for (auto& is : e->in_set) {
@@ -2183,9 +2196,9 @@ int tsp_run(tsp_handle e, const tsp_run_args* a) {
         if ((rc = stage_in(e, mem, a->noise, nb * A, e->s_noise, &np.noise))) return rc;
     }
     if ((rc = stage_in(e, mem, a->fed_root, nb * REC, e->s_fedroot, &np.fed_root))) return rc;
-    if ((rc = stage_out(e, omem, a->trace_root, nb * REC, e->s_troot, &np.trace_root))) return rc;
-    if ((rc = stage_out(e, omem, a->root_predicted_value, nb, e->s_rpred, &np.root_pred))) return rc;
-    if ((rc = stage_out(e, omem, a->root_hidden, nb * H, e->s_rhid, &np.root_hidden))) return rc;
+    if ((rc = stage_out(e, omem, a->trace_root, nb * REC, e->s_troot, &np.trace_root, false))) return rc;
+    if ((rc = stage_out(e, omem, a->root_predicted_value, nb, e->s_rpred, &np.root_pred, false))) return rc;
+    if ((rc = stage_out(e, omem, a->root_hidden, nb * H, e->s_rhid, &np.root_hidden, false))) return rc;
 
     SearchParams sp;
     memset(&sp, 0, sizeof(sp));
@@ -2283,12 +2296,23 @@ int tsp_run(tsp_handle e, const tsp_run_args* a) {
         return rc;
     }
     CK(e, cudaEventRecord(ev[1], e->stream));
+    // the root kernel's HOST outputs leave on the copy stream while the search runs (HOST batches with the overlapped upload)
+    const bool root_out_early = overlap && !resume && omem == TSP_MEM_HOST && (a->trace_root || a->root_predicted_value || a->root_hidden);
+    if (root_out_early) {
+        CK(e, cudaStreamWaitEvent(e->copy_stream, ev[1], 0));
+        if ((rc = copy_out(e, omem, a->trace_root, np.trace_root, nb * REC, e->copy_stream))) return rc;
+        if ((rc = copy_out(e, omem, a->root_predicted_value, np.root_pred, nb, e->copy_stream))) return rc;
+        if ((rc = copy_out(e, omem, a->root_hidden, np.root_hidden, nb * H, e->copy_stream))) return rc;
+        CK(e, cudaEventRecord(e->ev_root_out, e->copy_stream));
+    }
     if ((rc = launch_search_any(e, sp))) return rc;
     CK(e, cudaEventRecord(ev[2], e->stream));
     if (is) CK(e, cudaEventRecord(is->done, e->stream));
     e->ev_pending++;
 
-    if (!resume) {  // the root is not evaluated again on resume (root_predicted_value is None in the reference)
+    if (root_out_early) {
+        CK(e, cudaStreamWaitEvent(e->stream, e->ev_root_out, 0));  // (long done: keeps "the engine's stream orders everything")
+    } else if (!resume) {  // the root is not evaluated again on resume (root_predicted_value is None in the reference)
         if ((rc = copy_out(e, omem, a->trace_root, np.trace_root, nb * REC))) return rc;
         if ((rc = copy_out(e, omem, a->root_predicted_value, np.root_pred, nb))) return rc;
         if ((rc = copy_out(e, omem, a->root_hidden, np.root_hidden, nb * H))) return rc;
