@@ -149,3 +149,22 @@ def test_odd_number_of_roots(game, B):
     assert st["search_kernel"] == 2
     assert (out["visit_counts"].sum(1) == 25).all()
     check_against_oracle(cfg, B, 25, seed=40 + B, min_agree=0.9)
+
+
+def test_streamed_kernel_envelope_is_decided_at_weight_load():
+    """The streamed tcgen05 kernels split operands into fp16 pairs: a network whose activations COULD leave fp16's range
+    (worst case over all normalised states, from the weights alone) is searched by the mma.sync kernels instead, so the
+    overflow flag of the streamed search kernel can never fire."""
+    cfg = tsp.get_config("cross_merge_env", num_simulations=10)
+    sd = random_state_dict(cfg, 3)
+    key = "dynamics_encoded_state_network.module.2.weight"
+    big = dict(sd)
+    big[key] = sd[key] * 3.0e3  # un-normalised next states of magnitude ~1e5
+    obs, kw = synthetic_inputs(cfg, 128, 10, seed=3)
+    for weights, want_streamed in ((sd, True), (big, False)):
+        eng = tsp.Engine(cfg, max_roots=128, max_simulations=10, state_dict=weights)
+        out = eng.run(10, observations=obs, **kw)
+        st = eng.stats()
+        eng.close()
+        assert (st["search_kernel"] == 3) == want_streamed, st["search_kernel"]
+        assert (out["visit_counts"].sum(1) == 10).all()

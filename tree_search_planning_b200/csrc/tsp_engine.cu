@@ -826,6 +826,27 @@ int build_tcs(tsp_engine* e) {
     if (H % 64 || H <= 64 || H > 256 || DH % 64 || DH > 128 || DH < 64) return TSP_OK;
     if (RH % 16 || PH % 16 || VH % 16 || RH > 32 || PH > 32 || VH > 32 || RH < 16 || PH < 16 || VH < 16) return TSP_OK;
     if (NR + NV + A > 32 || D1.in_dim != H + A || D2.out_dim != H || D2.in_dim != DH) return TSP_OK;
+    {   // fp16-split range, decided at weight load: every input of the search MLP is a min-max normalised state in [0, 1]
+        // plus a one-hot action, so worst-case magnitudes of all activations follow from the weights alone. If none can reach
+        // fp16's range the kernel's overflow flag can never fire for this network; otherwise the mma.sync kernels search it.
+        auto bound = [](const HostLayer& L, double in_max, int dense, bool elu) {
+            double worst = 0.0;
+            for (int r = 0; r < L.out_dim; ++r) {
+                double acc = std::fabs((double)L.b[(size_t)r]), onehot = 0.0;
+                for (int k = 0; k < L.in_dim; ++k) {
+                    const double w = std::fabs((double)L.W[(size_t)r * L.in_dim + k]);
+                    if (k < dense) acc += w * in_max;
+                    else onehot = std::max(onehot, w);  // one of the one-hot inputs is 1
+                }
+                worst = std::max(worst, acc + onehot);
+            }
+            return elu ? std::max(worst, 1.0) : worst;  // ELU: (-1, x]
+        };
+        const double d1 = bound(D1, 1.0, H, true), xs = bound(D2, d1, DH, false);
+        const double r1 = bound(R1, xs, H, true), p1 = bound(P1, 1.0, H, true), v1 = bound(V1, 1.0, H, true);
+        const double worst = std::max(std::max(d1, xs), std::max(r1, std::max(p1, v1)));
+        if (!(worst < 0.5 * TS_FP16_MAX)) return TSP_OK;
+    }
     TsSched& ts = e->tss;
     memset(&ts, 0, sizeof(ts));
     // ---- B-operand arena: the gathered state X0 (K-major, LBO 144) shares its space with the normalised state XN (MN-major;
