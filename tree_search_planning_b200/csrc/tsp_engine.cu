@@ -82,6 +82,7 @@ struct tsp_engine {
     InSet in_set[2];
     int in_flip = 0;
     bool no_overlap = false;  // TSP_NO_OVERLAP
+    bool no_balance = false;  // TSP_NO_BALANCE: G groups per CTA in every wave
     bool no_zero_copy = false;  // TSP_NO_ZERO_COPY: stage + copy HOST outputs even when they are pinned
     // ring of event triples (before root kernel, between, after search kernel), drained lazily
     static constexpr int EV_RING = 1024;
@@ -1517,12 +1518,30 @@ size_t fast_smem(const FastSched& fs, int G, int S, bool w_lo = false, int n_sch
            (size_t)G * ((w_global ? GT / 2 : GT) * fs.row_stride + 2 * GT + GT * PATH_LEVELS) * 4;
 }
 
+// Groups of 16 trees per CTA. One wave (or kernels that may share an SM): G per CTA. Several waves of a one-CTA-per-SM
+// kernel (`balance`): the groups are spread evenly over full waves -- sm_count x rounds CTAs with floor / ceil of the
+// average -- so that no SM idles through a short last wave while others run G groups.
+int groups_per_cta(tsp_engine* e, FastParams& p, int G, bool balance) {
+    const int NG = (p.B + GT - 1) / GT;
+    int grid = (NG + G - 1) / G;
+    p.grp_base = G;
+    p.grp_extra = 0;
+    if (balance && grid > e->sm_count && !e->no_balance) {
+        const int rounds = (grid + e->sm_count - 1) / e->sm_count;
+        grid = e->sm_count * rounds;
+        p.grp_base = NG / grid;
+        p.grp_extra = NG % grid;
+    }
+    return grid;
+}
+
 template <int G, int LPT, bool WG = false>
-int launch_fast(tsp_engine* e, const FastParams& p) {
+int launch_fast(tsp_engine* e, const FastParams& p_in) {
+    FastParams p = p_in;
+    const int grid = groups_per_cta(e, p, G, false);
     const size_t smem = fast_smem(e->fsched[LPT == 16 ? 0 : 1][0], G, p.S_tab, p.w_lo != 0, 1, WG);
     int rc = set_smem(e, search_fast_kernel<G, LPT, WG>, smem);
     if (rc) return rc;
-    const int grid = (p.B + G * GT - 1) / (G * GT);
     constexpr int GTHREADS = GT * LPT;
     search_fast_kernel<G, LPT, WG><<<grid, G * GTHREADS, smem, e->stream>>>(p);
     CK(e, cudaGetLastError());
@@ -1542,12 +1561,13 @@ size_t tc_smem(const TcSched& ts, int G, int S) {
 }
 
 template <int G, int LPT>
-int launch_tc(tsp_engine* e, const FastParams& p, const TcSched& ts) {
+int launch_tc(tsp_engine* e, const FastParams& p_in, const TcSched& ts) {
+    FastParams p = p_in;
+    const int grid = groups_per_cta(e, p, G, true);
     // at least half of an SM's shared memory: one CTA per SM, which owns all of the SM's tensor memory
     const size_t smem = std::max(tc_smem(ts, G, p.S_tab), (size_t)120 * 1024);
     int rc = set_smem(e, search_tc_kernel<G, LPT>, smem);
     if (rc) return rc;
-    const int grid = (p.B + G * GT - 1) / (G * GT);
     constexpr int GTHREADS = GT * LPT;
     search_tc_kernel<G, LPT><<<grid, G * GTHREADS, smem, e->stream>>>(p, ts);
     CK(e, cudaGetLastError());
@@ -1567,7 +1587,10 @@ size_t tcs_smem(const TsSched& ts, int S) {
 }
 
 // The search with the MLP on tcgen05 and the weights streamed by TMA (tsp_stream.cuh): 64 trees per CTA, one CTA per SM.
-int launch_tcs(tsp_engine* e, const FastParams& p) {
+int launch_tcs(tsp_engine* e, const FastParams& p_in) {
+    FastParams p = p_in;
+    p.grp_base = TS_N / GT;  // the CTA's 64 trees are one lock-stepped group of four 16-tree slots
+    p.grp_extra = 0;
     const TsSched& ts = e->tss;
     const size_t smem = std::max(tcs_smem(ts, p.S_tab), (size_t)120 * 1024);
     int rc = set_smem(e, search_tcs_kernel, smem);
@@ -1592,11 +1615,12 @@ size_t tc_variant_smem(const TcSched& ts, int G, int S) {
 }
 
 template <int G, int LPT, int VARIANT>
-int launch_tc_variant(tsp_engine* e, const FastParams& p, const TcSched& ts) {
+int launch_tc_variant(tsp_engine* e, const FastParams& p_in, const TcSched& ts) {
+    FastParams p = p_in;
+    const int grid = groups_per_cta(e, p, G, true);
     const size_t smem = std::max(tc_variant_smem(ts, G, p.S_tab), (size_t)120 * 1024);  // one CTA per SM (it owns the SM's tensor memory)
     int rc = set_smem(e, search_tc_variant_kernel<G, LPT, VARIANT>, smem);
     if (rc) return rc;
-    const int grid = (p.B + G * GT - 1) / (G * GT);
     constexpr int GTHREADS = GT * LPT;
     search_tc_variant_kernel<G, LPT, VARIANT><<<grid, G * GTHREADS, smem, e->stream>>>(p, ts);
     CK(e, cudaGetLastError());
@@ -1610,11 +1634,12 @@ int launch_tc_variant(tsp_engine* e, const FastParams& p, const TcSched& ts) {
 }
 
 template <int G, int LPT, int VARIANT>
-int launch_fast_variant(tsp_engine* e, const FastParams& p) {
+int launch_fast_variant(tsp_engine* e, const FastParams& p_in) {
+    FastParams p = p_in;
+    const int grid = groups_per_cta(e, p, G, false);
     const size_t smem = fast_smem(e->fsched[LPT == 16 ? 0 : 1][0], G, p.S_tab, p.w_lo != 0, 2);
     int rc = set_smem(e, search_fast_variant_kernel<G, LPT, VARIANT>, smem);
     if (rc) return rc;
-    const int grid = (p.B + G * GT - 1) / (G * GT);
     constexpr int GTHREADS = GT * LPT;
     search_fast_variant_kernel<G, LPT, VARIANT><<<grid, G * GTHREADS, smem, e->stream>>>(p);
     CK(e, cudaGetLastError());
@@ -1637,6 +1662,7 @@ int launch_fast_any(tsp_engine* e, const SearchParams& sp) {
     p.max_rec = sp.max_rec; p.T = sp.T; p.pb_stride = sp.pb_stride;
     p.discount = sp.discount; p.pb_table = sp.pb_table;
     p.two_player = sp.two_player;
+    p.grp_base = 0; p.grp_extra = 0;  // set per launch (groups_per_cta)
     p.S_tab = sp.S_tab; p.resume = sp.resume; p.add_noise = sp.add_noise; p.one_minus_frac = sp.one_minus_frac; p.frac = sp.frac; p.noise = sp.noise;
     p.discount_f = sp.two_player ? -(float)sp.discount : (float)sp.discount;
     p.blocks = sp.blocks; p.hidden_pool = sp.hidden_pool; p.hdr = sp.hdr; p.rootprior = sp.rootprior; p.rootact = sp.rootact;
@@ -1922,6 +1948,7 @@ int tsp_create(const tsp_config* cfg, tsp_handle* out) {
     if (const char* t = getenv("TSP_NO_RTCS")) e->no_rtcs = atoi(t) != 0;
     if (const char* t = getenv("TSP_NO_OVERLAP")) e->no_overlap = atoi(t) != 0;
     if (const char* t = getenv("TSP_NO_ZERO_COPY")) e->no_zero_copy = atoi(t) != 0;
+    if (const char* t = getenv("TSP_NO_BALANCE")) e->no_balance = atoi(t) != 0;
     if (const char* t = getenv("TSP_TC_NOFOLD")) e->tc_nofold = atoi(t) != 0;
     if (const char* t = getenv("TSP_NO_WGLOBAL")) e->no_wglobal = atoi(t) != 0;
     if (const char* t = getenv("TSP_FORCE_WGLOBAL")) e->force_wglobal = atoi(t) != 0;

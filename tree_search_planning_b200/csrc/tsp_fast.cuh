@@ -71,6 +71,9 @@ struct FastParams {
     int B, S, A, H, support, mask_absorbing, uniform_policy;
     int blocks_per_tree, hidden_per_tree, max_rec, T, pb_stride, w_lo, two_player;
     int S_tab;                // simulations the trees hold after this run (size of the visit-count tables)
+    int grp_base, grp_extra;  // groups of 16 trees per CTA: grp_base, one more in the first grp_extra CTAs (multi-wave launches of
+                              // the one-CTA-per-SM kernels spread the groups evenly over full waves instead of leaving the last
+                              // wave short: 7 groups per SM as 4 + 3 rather than 4 + 4 on three quarters of the SMs)
     int resume, add_noise;    // resume: continue the trees of the previous run (override_root_with, self_play.py:331-333)
     double one_minus_frac, frac;
     const double* noise;      // [B][A], mixed into the root priors again on resume
@@ -625,8 +628,10 @@ __device__ __forceinline__ void search_fast_body(const FastParams& p, const TcSc
 
     const int lane = tid & 31, j = tid % LPT;
     const int gl0 = lane & (32 - LPT);  // first lane of this tree inside the warp
-    const int b = (blockIdx.x * G + grp) * GT + row;
-    const bool valid = b < p.B && (TC != 2 || tid < THREADS);  // (the service warps of the streamed path own no tree)
+    const int cta = blockIdx.x;
+    const bool grp_on = grp < p.grp_base + (cta < p.grp_extra ? 1 : 0);
+    const int b = (cta * p.grp_base + min(cta, p.grp_extra) + grp) * GT + row;
+    const bool valid = grp_on && b < p.B && (TC != 2 || tid < THREADS);  // (the service warps of the streamed path own no tree)
     const int A = p.A, H = p.H;
     const double discount = p.discount;
 
@@ -667,7 +672,7 @@ __device__ __forceinline__ void search_fast_body(const FastParams& p, const TcSc
     __syncthreads();
     if constexpr (TC) tc_fence_after();
 
-    int n_it = p.S;
+    int n_it = grp_on ? p.S : 0;  // (a group slot this CTA does not use sits the search out)
     if constexpr (TC == 2) {
         if (gw_u >= THREADS / 32) {  // service warps: the TMA producer and the MMA issuer of the whole search
             n_it = 0;
@@ -1279,8 +1284,10 @@ __device__ __forceinline__ void search_fast_variant_body(const FastParams& p, co
 
     const int lane = tid & 31, j = tid % LPT;
     const int gl0 = lane & (32 - LPT);
-    const int b = (blockIdx.x * G + grp) * GT + row;
-    const bool valid = b < p.B;
+    const int cta = blockIdx.x;
+    const bool grp_on = grp < p.grp_base + (cta < p.grp_extra ? 1 : 0);
+    const int b = (cta * p.grp_base + min(cta, p.grp_extra) + grp) * GT + row;
+    const bool valid = grp_on && b < p.B;  // (an unused group slot has no active tree: it leaves the loop at once)
     const int A = p.A, H = p.H, nf = p.nf;
     const double discount = p.discount;
 
