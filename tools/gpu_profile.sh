@@ -20,4 +20,4 @@ for f in r2_search_tc r2_root_tcs r2_search_tcs; do
   rm -f $O/$f.ncu-rep $O/$f.raw.csv   # (gpurun_out travels back only below 64 MiB; the summaries are what is kept)
   gzip -f $O/$f.src.csv
 done
-ls -la $O
+timeout 900 python -m pytest tests/ -q -m gpu -s -o faulthandler_timeout=300 2>&1 | grep -v "^$" > $O/r2_gpu_tests.log; tail -2 $O/r2_gpu_tests.log

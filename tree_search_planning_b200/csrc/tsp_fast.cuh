@@ -818,7 +818,9 @@ __device__ __forceinline__ void search_fast_body(const FastParams& p, const TcSc
                 const float4* src = reinterpret_cast<const float4*>(hpool + (size_t)node * H);
                 unsigned char* d = tc_arena + tx.x0_off + (n >> 3) * tx.x0_sbo + (n & 7) * 16;
                 for (int c = j; c < (H >> 3); c += LPT) {
-                    const float4 u = src[2 * c], v = src[2 * c + 1];
+                    // (hidden states are written once and read once or twice: streaming accesses keep them from pushing the
+                    // node blocks, which every simulation walks again, out of L2 -- 1 % at the HBM-resident sizes of this kernel)
+                    const float4 u = __ldcs(src + 2 * c), v = __ldcs(src + 2 * c + 1);
                     const float y[8] = {u.x, u.y, u.z, u.w, v.x, v.y, v.z, v.w};
                     uint4 hi, lo;
                     ts_split8(y, hi, lo);
@@ -841,7 +843,7 @@ __device__ __forceinline__ void search_fast_body(const FastParams& p, const TcSc
                 const float4* src = reinterpret_cast<const float4*>(hpool + (size_t)node * H);
                 unsigned char* d = tc_arena + ts.xh_off + (row >> 3) * ts.xh_sbo + (row & 7) * 16;
                 for (int i = j; i < (H >> 2); i += LPT) {
-                    const float4 h4 = src[i];
+                    const float4 h4 = src[i];  // (streaming loads / stores were measured here: 2-3 % slower while the pools fit L2)
                     *reinterpret_cast<float4*>(d + i * TC_LBO) = h4;
                     *reinterpret_cast<float4*>(d + i * TC_LBO + ts.b_lo) =
                         make_float4(tf32_lo(h4.x), tf32_lo(h4.y), tf32_lo(h4.z), tf32_lo(h4.w));

@@ -438,8 +438,9 @@ __device__ __forceinline__ bool ts_mlp(const TsSched& ts, TsCtl* __restrict__ ct
 #pragma unroll
                     for (int i = 0; i < 8; i += 2) {
                         const ulonglong2 hp = *reinterpret_cast<const ulonglong2*>(&ctl->hdst[n0 + i]);
-                        if (hp.x) asm volatile("st.global.f32 [%0], %1;" ::"l"(reinterpret_cast<float*>(hp.x) + k), "f"(y[i]) : "memory");
-                        if (hp.y) asm volatile("st.global.f32 [%0], %1;" ::"l"(reinterpret_cast<float*>(hp.y) + k), "f"(y[i + 1]) : "memory");
+                        // (streaming stores: see the gather in search_fast_body)
+                        if (hp.x) asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(reinterpret_cast<float*>(hp.x) + k), "f"(y[i]) : "memory");
+                        if (hp.y) asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(reinterpret_cast<float*>(hp.y) + k), "f"(y[i + 1]) : "memory");
                     }
                 }
             }

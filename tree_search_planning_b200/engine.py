@@ -98,6 +98,7 @@ def load_library(path=None):
     global _lib
     if _lib is not None and path is None:
         return _lib
+    path = path or os.environ.get("TSP_LIBRARY")  # (developer A/B runs: another build of the same ABI)
     p = path or _build.LIB_PATH
     if path is None and (not os.path.exists(p) or (os.environ.get("TSP_AUTOBUILD") == "1" and _build.needs_build())):
         try:
