@@ -254,6 +254,13 @@ typedef struct tsp_tree_info {
 int tsp_export_tree(tsp_handle h, int32_t root_index, tsp_tree_info *info, void *blocks, int32_t max_blocks, float *hidden,
                     int32_t max_hidden);
 
+/* Multi-GPU: the all-gather of a rank's packed root statistics ("NCCL ... to gather root visit distributions",
+ * BASELINE.json north_star) as ONE kernel of peer stores over NVLink / NVSwitch: `src` (DEVICE, num_bytes, 16-byte
+ * granular) is written to peers[0..n_peers) -- device pointers into the other ranks' (and this rank's own) symmetric
+ * buffers at this rank's offset, obtained by the caller (torch symmetric memory / cudaIpc). Asynchronous on the
+ * engine's stream; the cross-GPU barrier that publishes the writes is the caller's. */
+int tsp_peer_put(tsp_handle h, const void *src, int64_t num_bytes, void *const *peers, int32_t n_peers);
+
 int tsp_synchronize(tsp_handle h);
 int tsp_get_stats(tsp_handle h, tsp_stats *out);
 /* zero sum_search_ms / sum_root_ms / timed_runs (synchronizes the stream) */

@@ -25,8 +25,9 @@ def _free_port():
     return port
 
 
-def _worker(rank, world, port, game, B, S, out_dir):
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+def _worker(rank, world, port, game, B, S, out_dir, p2p):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      TSP_NO_P2P_GATHER="0" if p2p else "1")
     import torch.distributed as dist
     import tree_search_planning_b200 as tsp
     from tree_search_planning_b200.sharding import ShardedEngine
@@ -41,8 +42,11 @@ def _worker(rank, world, port, game, B, S, out_dir):
     obs, kw = synthetic_inputs(cfg, B, S, seed=5)  # the same global inputs on every rank; each uses its block
     lo, hi = se.lo, se.hi
     dev = lambda x: torch.from_numpy(numpy.ascontiguousarray(x[lo:hi])).to(device)  # noqa: E731
-    res = se.run_batch(S, dev(obs), noise=dev(kw["noise"]), tie_stream=dev(kw["tie"]),
-                       chance_stream=dev(kw["chance"]) if tsp.variant_of(cfg) else None)
+    # the gather as peer stores into symmetric buffers (tsp_peer_put + barrier) or as ncclAllGather
+    assert (se.pack.p2p is not None) == bool(p2p), "symmetric memory unavailable between these GPUs" if p2p else "unexpected"
+    for _ in range(3):  # (several searches: the gathered buffers are double-buffered)
+        res = se.run_batch(S, dev(obs), noise=dev(kw["noise"]), tie_stream=dev(kw["tie"]),
+                           chance_stream=dev(kw["chance"]) if tsp.variant_of(cfg) else None)
     numpy.savez(os.path.join(out_dir, "rank%d.npz" % rank), lo=lo, hi=hi,
                 **{k: v.cpu().numpy() for k, v in res.items()})
     se.close()
@@ -51,12 +55,12 @@ def _worker(rank, world, port, game, B, S, out_dir):
 
 
 @pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs two GPUs")
-@pytest.mark.parametrize("game,B,S", [("roundabout_env_ttc_flat", 1001, 20),
-                                      ("roundabout_env_ttc_flat_stochastic_concat", 513, 10)])
-def test_two_nccl_ranks_match_one_gpu_bit_exactly(tmp_path, game, B, S):
+@pytest.mark.parametrize("game,B,S,p2p", [("roundabout_env_ttc_flat", 1001, 20, True), ("roundabout_env_ttc_flat", 1001, 20, False),
+                                          ("roundabout_env_ttc_flat_stochastic_concat", 513, 10, True)])
+def test_two_nccl_ranks_match_one_gpu_bit_exactly(tmp_path, game, B, S, p2p):
     world, port = 2, _free_port()
     ctx = mp.get_context("spawn")
-    procs = [ctx.Process(target=_worker, args=(r, world, port, game, B, S, str(tmp_path))) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, game, B, S, str(tmp_path), p2p)) for r in range(world)]
     for p in procs:
         p.start()
     for p in procs:

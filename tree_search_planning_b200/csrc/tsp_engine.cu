@@ -2509,6 +2509,24 @@ int tsp_search_statistics(tsp_handle e, int32_t memory, int32_t B, const int32_t
     return copy_out(e, memory, child_visits, d_c, nb * A);
 }
 
+int tsp_peer_put(tsp_handle e, const void* src, int64_t num_bytes, void* const* peers, int32_t n_peers) {
+    if (!e) return TSP_EINVAL;
+    if (!src || !peers || n_peers < 1 || n_peers > 16 || num_bytes < 16 || num_bytes % 16 || ((uintptr_t)src & 15))
+        return fail(e, TSP_EINVAL, "tsp_peer_put: 1..16 peers, a 16-byte aligned source, a multiple of 16 bytes");
+    CK(e, cudaSetDevice(e->device));
+    PeerPtrs pp;
+    memset(&pp, 0, sizeof(pp));
+    for (int r = 0; r < n_peers; ++r) {
+        if (!peers[r] || ((uintptr_t)peers[r] & 15)) return fail(e, TSP_EINVAL, "tsp_peer_put: peer %d: null or misaligned", r);
+        pp.p[r] = reinterpret_cast<unsigned char*>(peers[r]);
+    }
+    const long long n16 = num_bytes / 16;
+    peer_put_kernel<<<(unsigned)((n16 + 255) / 256), 256, 0, e->stream>>>(reinterpret_cast<const uint4*>(src), n16, pp, n_peers);
+    CK(e, cudaGetLastError());
+    e->stats.kernel_launches++;
+    return TSP_OK;
+}
+
 // tcgen05 path: a bounded mbarrier wait timed out (an MMA commit never arrived) -- the results are invalid
 int tsp_export_tree(tsp_handle e, int32_t root_index, tsp_tree_info* info, void* blocks, int32_t max_blocks, float* hidden,
                     int32_t max_hidden) {

@@ -91,4 +91,17 @@ __global__ void search_statistics_kernel(int B, int A, const int* __restrict__ v
     for (int a = 0; a < A; ++a) child_visits[(size_t)b * A + a] = __ddiv_rn((double)visits[(size_t)b * A + a], den);
 }
 
+// The all-gather of the packed root statistics as peer stores (NVLink / NVSwitch): every rank writes its slice into the
+// same offset of every rank's symmetric buffer -- one kernel, no ring, no protocol; the cross-GPU barrier behind it is the
+// caller's (torch symmetric memory). Independent roots shard across GPUs, so this is the only exchange of a search.
+struct PeerPtrs {
+    unsigned char* p[16];
+};
+__global__ void peer_put_kernel(const uint4* __restrict__ src, long long n16, PeerPtrs peers, int n_peers) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n16) return;
+    const uint4 v = src[i];
+    for (int r = 0; r < n_peers; ++r) reinterpret_cast<uint4*>(peers.p[r])[i] = v;
+}
+
 }  // namespace tsp

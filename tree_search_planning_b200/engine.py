@@ -85,7 +85,7 @@ ABI_SYMBOLS = (
     "tsp_abi_version", "tsp_create", "tsp_destroy", "tsp_last_error", "tsp_set_layer", "tsp_finalize_weights",
     "tsp_weight_arena", "tsp_run", "tsp_initial_inference", "tsp_recurrent_inference", "tsp_stochastic_dynamics",
     "tsp_prediction", "tsp_synchronize", "tsp_get_stats", "tsp_reset_timing", "tsp_debug_phase_cycles", "tsp_stream",
-    "tsp_stack_observations", "tsp_select_action", "tsp_search_statistics", "tsp_export_tree",
+    "tsp_stack_observations", "tsp_select_action", "tsp_search_statistics", "tsp_export_tree", "tsp_peer_put",
 )
 
 _lib = None
@@ -129,6 +129,7 @@ def load_library(path=None):
     lib.tsp_stack_observations.argtypes = [_P] + [ctypes.c_int32] * 5 + [_P] * 4
     lib.tsp_select_action.argtypes = [_P, ctypes.c_int32, ctypes.c_int32, _P, _P, _P, ctypes.c_double, _P, _P]
     lib.tsp_search_statistics.argtypes = [_P, ctypes.c_int32, ctypes.c_int32, _P, _P]
+    lib.tsp_peer_put.argtypes = [_P, _P, ctypes.c_int64, ctypes.POINTER(ctypes.c_void_p), ctypes.c_int32]
     lib.tsp_export_tree.argtypes = [_P, ctypes.c_int32, ctypes.POINTER(TreeInfo), _P, ctypes.c_int32, _P, ctypes.c_int32]
     if path is None:
         _lib = lib
@@ -406,6 +407,11 @@ class Engine:
         self._check(self.lib.tsp_export_tree(self.handle, int(root_index), ctypes.byref(info), _ptr(blocks), info.n_blocks,
                                              _ptr(hidden) if hidden is not None else None, info.n_hidden if hidden is not None else 0))
         return dict(info=info, blocks=blocks, hidden=hidden)
+
+    def peer_put(self, src, num_bytes, peer_ptrs):
+        """tsp_peer_put: `src` (device tensor / pointer) -> every device pointer of `peer_ptrs`, on the engine's stream."""
+        arr = (ctypes.c_void_p * len(peer_ptrs))(*[int(p) for p in peer_ptrs])
+        self._check(self.lib.tsp_peer_put(self.handle, _ptr(src), int(num_bytes), arr, len(peer_ptrs)))
 
     def synchronize(self):
         self._check(self.lib.tsp_synchronize(self.handle))
