@@ -168,3 +168,45 @@ def test_streamed_kernel_envelope_is_decided_at_weight_load():
         eng.close()
         assert (st["search_kernel"] == 3) == want_streamed, st["search_kernel"]
         assert (out["visit_counts"].sum(1) == 10).all()
+
+
+@pytest.mark.parametrize("widths", [dict(encoding_size=128, fc_dynamics_layers=[64], fc_reward_layers=[16], fc_value_layers=[16],
+                                         fc_policy_layers=[32], support_size=5),
+                                    dict(encoding_size=192, fc_dynamics_layers=[128], fc_reward_layers=[32], fc_value_layers=[32],
+                                         fc_policy_layers=[16], support_size=10),
+                                    dict(encoding_size=256, fc_dynamics_layers=[64], fc_reward_layers=[32], fc_value_layers=[16],
+                                         fc_policy_layers=[16], support_size=1)])
+def test_streamed_kernel_other_layer_widths(widths):
+    """The envelope of search_tcs_kernel beyond the cross-merge shapes: 64 < H <= 256 in steps of 64 (one or two
+    next-state tiles, a partial second tile at H = 192), dynamics hidden width 64 / 128, head widths 16 / 32."""
+    cfg = tsp.get_config("cross_merge_env", num_simulations=20, **widths)
+    eng = tsp.Engine(cfg, max_roots=300, max_simulations=20, state_dict=random_state_dict(cfg, 5))
+    obs, kw = synthetic_inputs(cfg, 16, 20, seed=5)
+    eng.run(20, observations=obs, **kw)
+    st = eng.stats()
+    eng.close()
+    assert st["search_kernel"] == 3 and st["root_kernel"] == 1
+    check_against_oracle(cfg, 300, 20, seed=31, legal=True)
+
+
+@pytest.mark.parametrize("over", [dict(fc_representation_layers=[64, 64, 32]), dict(fc_representation_layers=[128]),
+                                  dict(fc_representation_layers=[32]), dict(encoding_size=128, fc_representation_layers=[64, 64, 32]),
+                                  dict(encoding_size=256, fc_representation_layers=[256, 128, 128], fc_value_layers=[16]),
+                                  dict(fc_representation_layers=[]), dict(encoding_size=48, fc_representation_layers=[80, 16])])
+def test_root_kernel_shapes_against_the_oracle(over):
+    """root_tcs_kernel (initial_inference on the streamed tcgen05 machinery) for representation networks of other depths /
+    widths, rows that do not fill a CTA, against the oracle's float32 network."""
+    from oracle.oracle import Oracle
+    cfg = tsp.get_config("highway_env_ttc_flat", **over)
+    sd = random_state_dict(cfg, 7)
+    B = 333
+    eng = tsp.Engine(cfg, max_roots=B, max_simulations=5, state_dict=sd)
+    obs, _ = synthetic_inputs(cfg, B, 5, seed=7)
+    got = eng.initial_inference(obs)
+    st = eng.stats()
+    eng.close()
+    assert st["root_kernel"] == 1, over
+    want = Oracle(cfg, sd).initial_inference(obs)
+    for k in ("hidden", "policy_logits", "value_logits"):
+        err = numpy.abs(got[k] - want[k]).max()
+        assert err <= 1e-5, (over, k, err)

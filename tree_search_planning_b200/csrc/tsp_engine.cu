@@ -826,7 +826,7 @@ int build_tcs(tsp_engine* e) {
     const int NR = R2.out_dim, NV = V2.out_dim;
     if (H % 64 || H <= 64 || H > 256 || DH % 64 || DH > 128 || DH < 64) return TSP_OK;
     if (RH % 16 || PH % 16 || VH % 16 || RH > 32 || PH > 32 || VH > 32 || RH < 16 || PH < 16 || VH < 16) return TSP_OK;
-    if (NR + NV + A > 32 || D1.in_dim != H + A || D2.out_dim != H || D2.in_dim != DH) return TSP_OK;
+    if (NR + NV + A > 64 || D1.in_dim != H + A || D2.out_dim != H || D2.in_dim != DH) return TSP_OK;
     {   // fp16-split range, decided at weight load: every input of the search MLP is a min-max normalised state in [0, 1]
         // plus a one-hot action, so worst-case magnitudes of all activations follow from the weights alone. If none can reach
         // fp16's range the kernel's overflow flag can never fire for this network; otherwise the mma.sync kernels search it.
@@ -901,11 +901,11 @@ int build_tcs(tsp_engine* e) {
     for (int r = 0; r < PH; ++r) bpv[(size_t)r] = P1.b[(size_t)r];
     for (int r = 0; r < VH; ++r) bpv[(size_t)(32 + r)] = V1.b[(size_t)r];
     const int t_bpv = put(bpv, 64);
-    std::vector<float> bout(32, 0.0f);  // rows of the output tile: value | reward | policy == columns of the out strip
+    std::vector<float> bout(64, 0.0f);  // rows of the output tile: value | reward | policy == columns of the out strip
     for (int r = 0; r < NV; ++r) bout[(size_t)(ts.off_vl + r)] = V2.b[(size_t)r];
     for (int r = 0; r < NR; ++r) bout[(size_t)(ts.off_rl + r)] = R2.b[(size_t)r];
     for (int r = 0; r < A; ++r) bout[(size_t)(ts.off_pl + r)] = P2.b[(size_t)r];
-    const int t_bo = put(bout, 32);
+    const int t_bo = put(bout, 64);
     for (int i = 0; i < 128; ++i) ctab.push_back(0.0f);  // lanes past `rows` still form an address
     if ((int)ctab.size() > TS_MAX_CTAB) return TSP_OK;
     ts.ctab_floats = (int)ctab.size();
@@ -939,7 +939,7 @@ int build_tcs(tsp_engine* e) {
     tb.add_acc(A_PV, 384, 64, 0, 0, xh, mn_sbo(HK), t_bpv, -1, 0);
     // stage 3: the three output layers as one block-diagonal layer over the 96 hidden inputs; rows == out-strip columns
     ts.stage_tile[3] = tb.n_tiles; ts.stage_acc[3] = A_OUT;
-    tb.add_layer(A_OUT, NV + NR + A, 32, HK, [&](int m, int k) {
+    tb.add_layer(A_OUT, NV + NR + A, box(NV + NR + A), HK, [&](int m, int k) {
         if (m >= ts.off_pl) return (k < PH) ? P2.W[(size_t)(m - ts.off_pl) * PH + k] : 0.0f;
         if (m >= ts.off_rl) return (k >= 64 && k - 64 < RH) ? R2.W[(size_t)(m - ts.off_rl) * RH + (k - 64)] : 0.0f;
         return (k >= 32 && k - 32 < VH) ? V2.W[(size_t)m * VH + (k - 32)] : 0.0f;
@@ -971,7 +971,7 @@ int build_root_tcs(tsp_engine* e) {
     const int H = c.encoding_size, A = c.num_actions, L = (int)R.size();
     const int PH = P1.out_dim, VH = V1.out_dim, NV = V2.out_dim;
     if (L + 2 > TS_MAX_STAGES || H % 16 || H > 256 || R.back().out_dim != H || R.front().in_dim != c.obs_dim) return TSP_OK;
-    if (PH % 16 || VH % 16 || PH > 32 || VH > 32 || PH < 16 || VH < 16 || NV + A > 32) return TSP_OK;
+    if (PH % 16 || VH % 16 || PH > 32 || VH > 32 || PH < 16 || VH < 16 || NV + A > 64) return TSP_OK;
     int wmax = 64, n_acc_need = 2;
     for (int l = 0; l < L; ++l) {
         if (R[l].out_dim % 16 || R[l].out_dim > 256) return TSP_OK;
@@ -1012,10 +1012,10 @@ int build_root_tcs(tsp_engine* e) {
     for (int r = 0; r < PH; ++r) bpv[(size_t)r] = P1.b[(size_t)r];
     for (int r = 0; r < VH; ++r) bpv[(size_t)(32 + r)] = V1.b[(size_t)r];
     const int t_bpv = put(bpv, 64);
-    std::vector<float> bout(32, 0.0f);
+    std::vector<float> bout(64, 0.0f);
     for (int r = 0; r < NV; ++r) bout[(size_t)(ts.off_vl + r)] = V2.b[(size_t)r];
     for (int r = 0; r < A; ++r) bout[(size_t)(ts.off_pl + r)] = P2.b[(size_t)r];
-    const int t_bo = put(bout, 32);
+    const int t_bo = put(bout, 64);
     for (int i = 0; i < 128; ++i) ctab.push_back(0.0f);
     if ((int)ctab.size() > TS_MAX_CTAB) return TSP_OK;
     ts.ctab_floats = (int)ctab.size();
@@ -1050,7 +1050,7 @@ int build_root_tcs(tsp_engine* e) {
     ++acc;
     // the two output layers as one block-diagonal layer over the 64 hidden inputs; rows == out-strip columns
     ts.stage_tile[L + 1] = tb.n_tiles; ts.stage_acc[L + 1] = acc;
-    tb.add_layer(acc, NV + A, 32, 64, [&](int m, int k) {
+    tb.add_layer(acc, NV + A, TsBuilder::box(NV + A), 64, [&](int m, int k) {
         if (m >= ts.off_pl) return (k < PH) ? P2.W[(size_t)(m - ts.off_pl) * PH + k] : 0.0f;
         return (k >= 32 && k - 32 < VH) ? V2.W[(size_t)m * VH + (k - 32)] : 0.0f;
     }, hh_off, hh_sbo, true, 2 * TR_N * acc);
