@@ -389,12 +389,14 @@ def test_generic_kernel_fallback_bit_exact(name, monkeypatch):
     eng.close()
 
 
-def test_continued_search_large_batch_vs_oracle():
-    """resume (override_root_with) at batch scale: 3 x 20 simulations on 2,048 roots, every phase with fresh noise
-    and streams; the engine's traces replayed through the oracle must give bit-identical root statistics."""
-    cfg = tsp.get_config("roundabout_env_ttc_flat", num_simulations=20)
+@pytest.mark.parametrize("game,B,kernel", [("roundabout_env_ttc_flat", 2048, 2), ("cross_merge_env", 333, 3)])
+def test_continued_search_large_batch_vs_oracle(game, B, kernel):
+    """resume (override_root_with) at batch scale: 3 x 20 simulations on 2,048 roots (tensor-memory kernel) / 333 roots
+    (streamed kernel), every phase with fresh noise and streams; the engine's traces replayed through the oracle must
+    give bit-identical root statistics."""
+    cfg = tsp.get_config(game, num_simulations=20)
     sd = random_state_dict(cfg, 41)
-    B, S, P = 2048, 20, 3
+    S, P = 20, 3
     eng = tsp.Engine(cfg, max_roots=B, max_simulations=S * P, state_dict=sd)
     obs, kw0 = seeded_inputs(cfg, B, S, 42)
     phases = [kw0] + [seeded_inputs(cfg, B, S, 43 + i)[1] for i in range(P - 1)]
@@ -406,6 +408,7 @@ def test_continued_search_large_batch_vs_oracle():
         if ph == 0:
             troot = got["trace_root"]
     assert (got["visit_counts"].sum(1) == S * P).all()
+    assert eng.stats()["search_kernel"] == kernel
     stack = lambda k: numpy.stack([kw[k] for kw in phases])
     replay = Oracle(cfg, sd).run(S, fed_root=troot, fed_records=numpy.stack(traces), B=B, n_phases=P,
                                  noise=stack("noise"), tie=stack("tie"))

@@ -1,1 +1,1 @@
-timeout 900 python -m pytest tests/test_tc.py -q -m gpu -x -k "other_layer_widths or root_kernel_shapes or envelope" -o faulthandler_timeout=300 2>&1 | grep -v "^$" | tail -25
+timeout 900 python -m pytest tests/test_gpu_parity.py -q -m gpu -x -k "continued" -o faulthandler_timeout=300 2>&1 | grep -v "^$" | tail -15
