@@ -137,6 +137,36 @@ def test_chance_node_searches_agree_with_the_mma_sync_kernel(game, monkeypatch):
     assert same.mean() >= 0.97, same.mean()
 
 
+@pytest.mark.parametrize("game", ["roundabout_env_ttc_flat_stochastic_concat", "roundabout_env_ttc_flat_risk_sensitive"])
+@pytest.mark.parametrize("B", [600, 9000])
+def test_both_futures_in_one_pass_match_one_future_per_pass(game, B, monkeypatch):
+    """Two futures: the transition expansion evaluates both side by side (MMA columns 16..31) together with the prediction of the
+    state expansions, three stages per iteration; TSP_TC_NOMERGE=1 keeps one future per pass. Same arithmetic per column:
+    the searches must agree."""
+    cfg = tsp.get_config(game)
+    st_m, m = search_kernel_of(cfg, B, 25)
+    st_s, s = search_kernel_of(cfg, B, 25, monkeypatch, TSP_TC_NOMERGE="1")
+    assert st_m["search_kernel"] == 2 and st_s["search_kernel"] == 2
+    same = (m["visit_counts"] == s["visit_counts"]).all(axis=1)
+    assert same.mean() >= 0.995, same.mean()
+    a = m["trace_records"][same].astype(numpy.float64)
+    b = s["trace_records"][same].astype(numpy.float64)
+    assert numpy.median(numpy.abs(a - b)) <= 1e-7
+    # the accumulators may differ in the last bit between the two MMA shapes: priors / probabilities within 1e-5 everywhere,
+    # value / reward with the one-step allowance of the float32 inverse value transform (golden_util.quantised_columns)
+    keep = undisturbed_trees(a, b, cfg.n_futures)
+    assert keep.mean() >= 0.98, keep.mean()
+    assert_records_close(a[keep], b[keep], cfg.n_futures, min_fraction=0.995, what="both futures per pass vs one future per pass")
+
+
+def test_three_futures_keep_one_future_per_pass():
+    cfg = tsp.get_config("roundabout_env_ttc_flat_stochastic_concat", n_futures=3)
+    st, out = search_kernel_of(cfg, 700, 25)
+    assert st["search_kernel"] == 2
+    assert (out["visit_counts"].sum(1) == 25).all()
+    check_against_oracle(cfg, 700, 25, seed=33)
+
+
 @pytest.mark.parametrize("game", ["roundabout_env_ttc_flat", "roundabout_env_ttc_flat_stochastic_concat",
                                   "roundabout_env_ttc_flat_risk_sensitive"])
 @pytest.mark.parametrize("B", [1, 17, 33])

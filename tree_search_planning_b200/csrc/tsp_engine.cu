@@ -83,6 +83,7 @@ struct tsp_engine {
     int in_flip = 0;
     bool no_overlap = false;  // TSP_NO_OVERLAP
     bool no_balance = false;  // TSP_NO_BALANCE: G groups per CTA in every wave
+    bool no_merge = false;    // TSP_TC_NOMERGE: chance-node searches evaluate the futures of a transition expansion one by one
     bool no_zero_copy = false;  // TSP_NO_ZERO_COPY: stage + copy HOST outputs even when they are pinned
     // ring of event triples (before root kernel, between, after search kernel), drained lazily
     static constexpr int EV_RING = 1024;
@@ -1109,18 +1110,27 @@ int build_tc_variant(tsp_engine* e) {
         memset(&ts, 0, sizeof(ts));
         const int G = shape == 0 ? 2 : 4;
         const int parts = shape == 0 ? 2 : 1;  // 8 warps per group: warps q and q + 4 split the trees of lane quarter q
+        const int h_q = (H + 31) / 32;         // lane quarters of the next state; the folded reward layer sits behind them
         const int c1 = 0, c2 = c1 + H, c4 = c2 + DH, hi_cols = c4 + HK;
         ts.a_lo = hi_cols;
         ts.n_cols = 2 * hi_cols;
         ts.d_col0 = ts.n_cols;
-        ts.d_cols_group = 48;
+        // Two futures: BOTH in one pass -- the second future's trees are the MMA columns 16..31 (N = 32) from the second dynamics
+        // layer on (the first one differs between futures by one gathered weight row only), the prediction's layers ride in
+        // the same three stages: 3 commit round trips per iteration instead of 10.
+        const bool merged = nf == 2 && !e->no_merge && ts.n_cols + G * 64 <= TC_TMEM_COLS;
+        ts.merged = merged ? 1 : 0;
+        ts.d_cols_group = merged ? 64 : 48;
         if (ts.n_cols % 8 || ts.d_col0 + G * ts.d_cols_group > TC_TMEM_COLS) return TSP_OK;
         int o = 0;
         const int xh = o; o += bufsz(H);
-        const int xd = o; o += bufsz(DH);
+        const int xd = o; o += bufsz(DH) * (merged ? 2 : 1);
         const int xq = o; o += bufsz(QH);
-        const int xs = o; o += bufsz(H);
-        const int xr = o; o += bufsz(RH);
+        // merged: the un-normalised next states (32 columns, no lo twin) reuse the gathered state and the dynamics hidden
+        // layer -- both are dead once the second stage's MMAs have completed
+        const int xs = (merged && 2 * bufsz(H) <= bufsz(H) + 2 * bufsz(DH)) ? xh : o;
+        if (xs == o) o += bufsz(H) * (merged ? 2 : 1);
+        const int xr = o; o += bufsz(RH) * (merged ? 2 : 1);
         const int xp = o; o += bufsz(PH);
         const int xv = o; o += bufsz(VH);
         ts.b_lo = o;
@@ -1130,7 +1140,8 @@ int build_tc_variant(tsp_engine* e) {
         ts.xn_off = -1; ts.xn_sbo = 0;  // no layer reads the normalised state of a future: it goes to the hidden-state pool only
         ts.H = H;
         ts.off_vl = 0; ts.off_rl = NV; ts.off_pl = NV + NR; ts.off_tp = NV + NR + A;
-        int pitch = NV + NR + A + nf;
+        ts.off_rl2 = NV + NR + A + nf;  // merged: reward logits of future 1
+        int pitch = NV + NR + A + nf + (merged ? NR : 0);
         if (shape == 0) while (pitch % 32 != 16) ++pitch;
         else while (pitch % 32 != 8 && pitch % 32 != 24) ++pitch;
         ts.out_pitch = pitch;
@@ -1157,7 +1168,6 @@ int build_tc_variant(tsp_engine* e) {
             for (int r = 0; r < L.out_dim; ++r)
                 for (int k = 0; k < K; ++k) img[(size_t)(col0 + k) * 128 + lane0 + r] = L.W[(size_t)r * L.in_dim + k];
         };
-        const int h_q = (H + 31) / 32;
         place(D1, c1, 0, H); place(Q1, c1, 32, H); place(P1, c1, 64, H); place(V1, c1, 96, H);
         place(D2, c2, 0, DH);
         for (int r = 0; r < RH; ++r)
@@ -1173,9 +1183,46 @@ int build_tc_variant(tsp_engine* e) {
                 memcpy(&hi, &bits, 4);
                 img[(size_t)(hi_cols + col) * 128 + l] = w - hi;
             }
-        auto mma = [&](int i, int a_col, int b_off, int K, int d_col) {
+        auto mma = [&](int i, int a_col, int b_off, int K, int d_col, int n = 16) {
             ts.mma[i].a_col = a_col; ts.mma[i].b_off = b_off; ts.mma[i].ksteps = K / 8; ts.mma[i].sbo = sbo(K); ts.mma[i].d_col = d_col;
+            ts.mma[i].n = n;
         };
+        auto stage = [&](int s, int mma0, int n_mma, int commit, int row_op, int epi0, int n_epi) {
+            ts.stage[s].mma0 = mma0; ts.stage[s].n_mma = n_mma; ts.stage[s].commit = commit; ts.stage[s].row_op = row_op;
+            ts.stage[s].epi0 = epi0; ts.stage[s].n_epi = n_epi;
+        };
+        if (merged) {
+            const int DA = 0, DB = 32;
+            mma(0, c1, xh, H, DA);           // dynamics 1 | prior 1 | policy 1 | value 1 of the gathered state
+            mma(1, c2, xd, DH, DB, 32);      // dynamics 2 | folded reward 1, both futures
+            mma(2, c4, xp, PH, DA);          // policy 2 (lanes 64..95)
+            mma(3, c4, xv, VH, DA + 16);     // value 2 (lanes 96..127)
+            mma(4, c4, xr, RH, DB, 32);      // reward 2 (lanes 0..31), both futures
+            mma(5, c4, xq, QH, DA);          // prior 2 (lanes 32..63)
+            auto epi = [&](int pass, int q, int d_col, int ncols, int rows, int dst, int dst_sbo, int feat0, int cidx, int eidx, int zidx,
+                           int flags) {
+                for (int h = 0; h < parts; ++h) {
+                    TcEpi& x = ts.epi[pass][q + 4 * h];
+                    x.d_col = (short)d_col; x.n0 = (short)(h * (ncols / parts)); x.ncnt = (short)(ncols / parts); x.rows = (short)rows;
+                    x.dst = dst; x.dst_sbo = dst_sbo; x.feat0 = feat0; x.cidx = cidx; x.eidx = eidx; x.e_ld = 32; x.zidx = zidx; x.flags = flags;
+                }
+            };
+            epi(0, 0, DA, 16, DH, xd, sbo(DH), 0, t_b1, t_e1, t_e1 + A * 32, 1 | 4);
+            epi(0, 1, DA, 16, QH, xq, sbo(QH), 0, t_bq1, -1, -1, 1);
+            epi(0, 2, DA, 16, PH, xp, sbo(PH), 0, t_bp1, -1, -1, 1);
+            epi(0, 3, DA, 16, VH, xv, sbo(VH), 0, t_bv1, -1, -1, 1);
+            for (int q = 0; q < h_q; ++q) epi(1, q, DB, 32, std::min(32, H - 32 * q), xs, sbo(H), 32 * q, t_b2 + 32 * q, -1, -1, 8);
+            epi(1, h_q, DB, 32, RH, xr, sbo(RH), 0, t_bf, -1, -1, 1);
+            epi(1, 3, DA + 16, 16, NV, ts.off_vl, ts.off_vl, 0, t_bv2, -1, -1, 2);
+            epi(2, 2, DA, 16, A, ts.off_pl, ts.off_pl, 0, t_bp2, -1, -1, 2);
+            epi(3, 0, DB, 32, NR, ts.off_rl, ts.off_rl2, 0, t_br2, -1, -1, 2);
+            epi(3, 1, DA, 16, nf, ts.off_tp, ts.off_tp, 0, t_bq2, -1, -1, 2);
+            ts.n_stages = 3;
+            stage(0, 0, 1, 1, 0, 0, 1);
+            stage(1, 1, 3, 1, 0, 1, 2);
+            stage(2, 4, 2, 1, 1, 3, 1);
+            for (int s2 = 0; s2 < 3; ++s2) ts.stage[s2].issuer = parts == 2 ? 7 : 3;
+        } else {
         const int DA = 0, DB = 16;
         mma(0, c1, xh, H, DA);    // dynamics 1 | prior 1
         mma(1, c2, xd, DH, DB);   // dynamics 2 | folded reward 1
@@ -1201,10 +1248,6 @@ int build_tc_variant(tsp_engine* e) {
         epi(3, 3, DA, VH, xv, sbo(VH), 0, t_bv1, -1, -1, 1);
         epi(4, 2, DA, A, ts.off_pl, 0, 0, t_bp2, -1, -1, 2);
         epi(4, 3, DB, NV, ts.off_vl, 0, 0, t_bv2, -1, -1, 2);
-        auto stage = [&](int s, int mma0, int n_mma, int commit, int row_op, int epi0, int n_epi) {
-            ts.stage[s].mma0 = mma0; ts.stage[s].n_mma = n_mma; ts.stage[s].commit = commit; ts.stage[s].row_op = row_op;
-            ts.stage[s].epi0 = epi0; ts.stage[s].n_epi = n_epi;
-        };
         ts.n_stages = 6;
         stage(0, 0, 1, 1, 0, 0, 1);
         stage(1, 1, 1, 1, 0, 1, 1);
@@ -1216,6 +1259,7 @@ int build_tc_variant(tsp_engine* e) {
         // future, quarter 0 in those of the prediction
         for (int s2 = 0; s2 < 4; ++s2) ts.stage[s2].issuer = parts == 2 ? 7 : 3;
         for (int s2 = 4; s2 < 6; ++s2) ts.stage[s2].issuer = parts == 2 ? 4 : 0;
+        }
         int rc;
         if ((rc = ensure(e, e->tc_img[shape], img.size() * sizeof(float)))) return rc;
         if ((rc = ensure(e, e->tc_ctab[shape], ctab.size() * sizeof(float)))) return rc;
@@ -1614,15 +1658,15 @@ size_t tc_variant_smem(const TcSched& ts, int G, int S) {
            (size_t)G * (ts.arena_bytes + (GT * ts.out_pitch + GT + GT / 4) * 4);
 }
 
-template <int G, int LPT, int VARIANT>
+template <int G, int LPT, int VARIANT, bool MERGED>
 int launch_tc_variant(tsp_engine* e, const FastParams& p_in, const TcSched& ts) {
     FastParams p = p_in;
     const int grid = groups_per_cta(e, p, G, true);
     const size_t smem = std::max(tc_variant_smem(ts, G, p.S_tab), (size_t)120 * 1024);  // one CTA per SM (it owns the SM's tensor memory)
-    int rc = set_smem(e, search_tc_variant_kernel<G, LPT, VARIANT>, smem);
+    int rc = set_smem(e, search_tc_variant_kernel<G, LPT, VARIANT, MERGED>, smem);
     if (rc) return rc;
     constexpr int GTHREADS = GT * LPT;
-    search_tc_variant_kernel<G, LPT, VARIANT><<<grid, G * GTHREADS, smem, e->stream>>>(p, ts);
+    search_tc_variant_kernel<G, LPT, VARIANT, MERGED><<<grid, G * GTHREADS, smem, e->stream>>>(p, ts);
     CK(e, cudaGetLastError());
     e->stats.kernel_launches++;
     e->stats.search_ctas = grid;
@@ -1706,7 +1750,9 @@ int launch_fast_any(tsp_engine* e, const SearchParams& sp) {
         p.tc_img = reinterpret_cast<const float*>(e->tc_img[which].p);
         p.tc_ctab = reinterpret_cast<const float*>(e->tc_ctab[which].p);
         p.tc_status = reinterpret_cast<int*>(e->tc_status.p);
-#define TSP_LAUNCH_TV(GG, LL) (variant == 1 ? launch_tc_variant<GG, LL, 1>(e, p, ts) : launch_tc_variant<GG, LL, 2>(e, p, ts))
+#define TSP_LAUNCH_TV(GG, LL)                                                                                                   \
+    (ts.merged ? (variant == 1 ? launch_tc_variant<GG, LL, 1, true>(e, p, ts) : launch_tc_variant<GG, LL, 2, true>(e, p, ts))  \
+               : (variant == 1 ? launch_tc_variant<GG, LL, 1, false>(e, p, ts) : launch_tc_variant<GG, LL, 2, false>(e, p, ts)))
         if (lpt == 16 && tc_variant_smem(ts, 2, p.S_tab) <= 227 * 1024) return TSP_LAUNCH_TV(2, 16);
         if (lpt == 8 && tc_variant_smem(ts, 4, p.S_tab) <= 227 * 1024) return TSP_LAUNCH_TV(4, 8);
         if (lpt == 8 && tc_variant_smem(ts, 2, p.S_tab) <= 227 * 1024) return TSP_LAUNCH_TV(2, 8);
@@ -1949,6 +1995,7 @@ int tsp_create(const tsp_config* cfg, tsp_handle* out) {
     if (const char* t = getenv("TSP_NO_OVERLAP")) e->no_overlap = atoi(t) != 0;
     if (const char* t = getenv("TSP_NO_ZERO_COPY")) e->no_zero_copy = atoi(t) != 0;
     if (const char* t = getenv("TSP_NO_BALANCE")) e->no_balance = atoi(t) != 0;
+    if (const char* t = getenv("TSP_TC_NOMERGE")) e->no_merge = atoi(t) != 0;
     if (const char* t = getenv("TSP_TC_NOFOLD")) e->tc_nofold = atoi(t) != 0;
     if (const char* t = getenv("TSP_NO_WGLOBAL")) e->no_wglobal = atoi(t) != 0;
     if (const char* t = getenv("TSP_FORCE_WGLOBAL")) e->force_wglobal = atoi(t) != 0;

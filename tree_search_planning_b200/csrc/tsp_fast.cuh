@@ -1217,7 +1217,7 @@ __device__ __noinline__ int select_exact_v(double pbN, double sqN, int vis, doub
 // the prediction of a state expansion), the reference's backups walked by one lane per tree.
 // TC: both networks on tcgen05 with the weights resident in tensor memory (tsp_tc.cuh): stages [0, 4) of the TcSched are
 // one future of a transition expansion, stages [4, 6) the prediction of a state expansion.
-template <int G, int LPT, int VARIANT, bool TC>
+template <int G, int LPT, int VARIANT, bool TC, bool MERGED = false>
 __device__ __forceinline__ void search_fast_variant_body(const FastParams& p, const TcSched* __restrict__ tsp_) {
     extern __shared__ __align__(16) float smem[];
     constexpr int GTHREADS = GT * LPT;
@@ -1334,6 +1334,8 @@ __device__ __forceinline__ void search_fast_variant_body(const FastParams& p, co
         if (fed && n_rec >= p.max_rec) n_sims = p.S;
         const bool active = valid && n_sims < p.S;
         if (!group_any<GTHREADS>(barid, active)) break;
+        [[maybe_unused]] long long tc0 = 0, tc1 = 0, tc2 = 0, tc3 = 0;
+        if (TC && p.phase_cycles && tid == 0) tc0 = clock64();
 
         // ================= selection: StateNode levels pUCT, TransitionNode levels chance =================
         int node = 0, slot = 0, depth = 0, Np = root_visit;
@@ -1446,15 +1448,34 @@ __device__ __forceinline__ void search_fast_variant_body(const FastParams& p, co
                 row_action[row] = action;
                 row_active[row] = active ? 1 : 0;
             }
+            if (p.phase_cycles && tid == 0) tc1 = clock64();
             if (active) tc_gather_hidden<LPT>(ts, tc.arena, hpool + (size_t)hslot * H, H, row, j);
             fence_async_smem();
             const bool any_t = group_any<GTHREADS>(barid, kind == 2);  // (also orders the gather before the MMAs)
-            const bool any_s = group_any<GTHREADS>(barid, kind == 1);
+            const bool any_s = MERGED ? true : group_any<GTHREADS>(barid, kind == 1);
+            if (p.phase_cycles && tid == 0) tc2 = clock64();
             const int lane_ = tid & 31;
             const float* o = tc.outs + row * ts.out_pitch;
+            if constexpr (MERGED) {
+                // both futures of a transition expansion AND the prediction of a state expansion in one pass of three stages
+                // (the trees of a group are rarely all of one kind; what a tree does not need is computed and dropped)
+                float* hst = (kind == 2) ? hpool + (size_t)(1 + n_tgroups * nf) * H : nullptr;
+                tc_ok = tc_mlp<LPT, 2>(ts, tc.tmem_base, tc.d_group, tc.arena, tc.outs, tc.ctab, row_action, tc.mbar, tc.parity, tc.gw,
+                                    lane_, row, j, barid, hq, p.phase_cycles, 0, -1, 0, hst) && tc_ok;
+                float v1, rw0, p1, dv, rw1, tp;
+                decode_row<LPT, true>(o + ts.off_vl, o + ts.off_rl, o + ts.off_pl, p.support, A, false, j, v1, rw0, p1);
+                decode_row<LPT, true>(o + ts.off_rl2, o + ts.off_rl2, o + ts.off_tp, p.support, nf, false, j, dv, rw1, tp);
+                if (kind == 2) {
+                    treward = (j == 0) ? rw0 : (j == 1 ? rw1 : 0.0f);
+                    tprior = tp;  // softmax of the prior logits, self_play_stochastic.py:553-554
+                } else if (kind == 1) {
+                    value = v1;
+                    prior = p1;
+                }
+            } else {
             if (any_t) {
                 for (int z = 0; z < nf; ++z) {
-                    tc_ok = tc_mlp<LPT>(ts, tc.tmem_base, tc.d_group, tc.arena, tc.outs, tc.ctab, row_action, tc.mbar, tc.parity, tc.gw,
+                    tc_ok = tc_mlp<LPT, 1>(ts, tc.tmem_base, tc.d_group, tc.arena, tc.outs, tc.ctab, row_action, tc.mbar, tc.parity, tc.gw,
                                         lane_, row, j, barid, hq, nullptr, 0, 4, z) && tc_ok;
                     float dv, rwz, tp;
                     decode_row<LPT, true>(o + ts.off_rl, o + ts.off_rl, o + ts.off_tp, p.support, nf, false, j, dv, rwz, tp);
@@ -1469,7 +1490,7 @@ __device__ __forceinline__ void search_fast_variant_body(const FastParams& p, co
                 }
             }
             if (any_s) {
-                tc_ok = tc_mlp<LPT>(ts, tc.tmem_base, tc.d_group, tc.arena, tc.outs, tc.ctab, row_action, tc.mbar, tc.parity, tc.gw,
+                tc_ok = tc_mlp<LPT, 1>(ts, tc.tmem_base, tc.d_group, tc.arena, tc.outs, tc.ctab, row_action, tc.mbar, tc.parity, tc.gw,
                                     lane_, row, j, barid, hq, nullptr, 4, 6, 0) && tc_ok;
                 float dr, v1, p1;
                 decode_row<LPT, true>(o + ts.off_vl, o + ts.off_vl, o + ts.off_pl, p.support, A, false, j, v1, dr, p1);
@@ -1477,6 +1498,7 @@ __device__ __forceinline__ void search_fast_variant_body(const FastParams& p, co
                     value = v1;
                     prior = p1;
                 }
+            }
             }
         } else if (!fed) {
             if (j == 0) {
@@ -1534,6 +1556,7 @@ __device__ __forceinline__ void search_fast_variant_body(const FastParams& p, co
             }
         }
 
+        if (TC && p.phase_cycles && tid == 0) tc3 = clock64();
         // ================= expansion + backup =================
         {
 #pragma unroll
@@ -1676,6 +1699,14 @@ __device__ __forceinline__ void search_fast_variant_body(const FastParams& p, co
             if (kind == 1) n_sims++;
         }
         __syncwarp();
+        if (TC && p.phase_cycles && tid == 0) {
+            const long long tc4 = clock64();
+            atomicAdd(p.phase_cycles + 0, (unsigned long long)(tc1 - tc0));
+            atomicAdd(p.phase_cycles + 1, (unsigned long long)(tc2 - tc1));
+            atomicAdd(p.phase_cycles + 2, (unsigned long long)(tc3 - tc2));
+            atomicAdd(p.phase_cycles + 3, (unsigned long long)(tc4 - tc3));
+            atomicAdd(p.phase_cycles + 4, 1ull);
+        }
     }
 
     if (valid) {
@@ -1727,10 +1758,10 @@ __global__ void __launch_bounds__(G * GT * LPT, 512 / (G * GT * LPT)) search_fas
     search_fast_variant_body<G, LPT, VARIANT, false>(p, nullptr);
 }
 
-template <int G, int LPT, int VARIANT>
+template <int G, int LPT, int VARIANT, bool MERGED>
 __global__ void __launch_bounds__(G * GT * LPT, 1) search_tc_variant_kernel(const __grid_constant__ FastParams p,
                                                                             const __grid_constant__ TcSched ts) {
-    search_fast_variant_body<G, LPT, VARIANT, true>(p, &ts);
+    search_fast_variant_body<G, LPT, VARIANT, true, MERGED>(p, &ts);
 }
 
 }  // namespace tsp

@@ -39,27 +39,30 @@ struct TcMma {
     int ksteps;   // K / 8
     int sbo;      // bytes between 8-tree groups of the B operand
     int d_col;    // accumulator column, relative to the group's accumulator base
-    int pad[3];
+    int n;        // MMA columns: 16 trees (0 reads as 16), or 32 = both futures of a transition expansion side by side
+    int pad[2];
 };
 struct TcEpi {        // one warp (TMEM lane quarter) of one epilogue pass
     short d_col;      // accumulator column (group-relative) of tree 0
-    short n0, ncnt;   // trees handled by this warp: n0 .. n0 + ncnt - 1, ncnt in {0, 4, 8, 16}
+    short n0, ncnt;   // columns handled by this warp: n0 .. n0 + ncnt - 1, ncnt in {0, 2, 4, 8, 16, 32}; column n = tree n % 16
+                      // (columns 16..31: the second future of a merged transition expansion)
     short rows;       // valid lanes: lane < rows holds feature feat0 + lane
     int dst;          // B destination: byte offset of the hi buffer in the arena; RAW: column of lane 0 in the out strip
-    int dst_sbo;
+    int dst_sbo;      // (RAW: out-strip column of lane 0 for the columns 16..31)
     int feat0;        // B destination: k of lane 0
     int cidx;         // ctab offset of lane 0's bias
     int eidx;         // ctab offset of the one-hot rows (row a at eidx + a * e_ld), -1: none
     int e_ld;
     int zidx;         // ctab offset of the one-hot FUTURE rows of MuZeroStochasticConcat (models.py:568-580; row z at zidx + z * e_ld), -1: none
-    int flags;        // 1: ELU, 2: RAW (float32 logits to the out strip)
+    int flags;        // 1: ELU, 2: RAW (float32 logits to the out strip), 4: BOTH futures from one accumulator (rows zidx and
+                      // zidx + e_ld; the second future's operand 16 columns further), 8: no lo twin (no MMA reads this buffer)
 };
 static_assert(sizeof(TcEpi) == 40, "TcEpi: four shorts and eight ints");
 struct TcStage {
     int mma0, n_mma;  // MMAs issued at the start of the stage
     int commit;       // commit them (and everything issued before) to the group's mbarrier
     int row_op;       // 1: min-max normalise xs -> xn (models.py:248-255) while the MMAs run
-    int epi0, n_epi;  // epilogue pass (n_epi <= 1) after the mbarrier wait
+    int epi0, n_epi;  // epilogue passes after the mbarrier wait (a lane quarter with two accumulators to read: two passes)
     int issuer;       // warp of the group that issues the MMAs: one WITHOUT a share of this stage's epilogue, so that the
                       // epilogue warps fetch their operands while the MMAs are issued instead of after
     int pad;
@@ -70,6 +73,7 @@ struct TcSched {
     int off_vl, off_rl, off_pl, ctab_floats;
     int xh_off, xh_sbo, xs_off, xs_sbo;
     int xn_off, xn_sbo, H, off_tp;
+    int merged, off_rl2;  // chance-node searches: both futures in one pass (columns 16..31 = future 1); its reward logits
     TcStage stage[TC_MAX_STAGES];
     TcMma mma[TC_MAX_MMA];
     TcEpi epi[TC_MAX_PASS][8];  // [pass][warp of the group]: warps w and w + 4 share TMEM lane quarter w % 4
@@ -95,7 +99,8 @@ __device__ __forceinline__ void tc_mma(uint32_t d, uint32_t a, uint32_t bdesc_lo
         "r"(idesc), "r"(acc)
         : "memory");
 }
-constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+constexpr uint32_t TC_IDESC0 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(128 >> 4) << 24);
+__device__ __forceinline__ uint32_t tc_idesc(int n) { return TC_IDESC0 | ((uint32_t)(n >> 3) << 17); }
 
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -140,20 +145,31 @@ __device__ __forceinline__ void tmem_ld<16>(uint32_t taddr, uint32_t (&v)[16]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// One warp's share of an epilogue pass: NCNT trees (n0 a multiple of NCNT, or 0) of the lanes' features. Everything
-// that does not depend on the accumulator (bias, the trees' one-hot rows, addresses) is fetched BEFORE the wait on
-// the MMAs' mbarrier; all per-tree addresses are the pass's base plus compile-time offsets.
-template <int NCNT>
-__device__ __forceinline__ bool tc_epi_warp(const TcEpi& ep, uint32_t d_tmem, unsigned char* __restrict__ arena, int b_lo,
+// One warp's share of an epilogue pass: NCNT columns n0 .. n0 + NCNT - 1 (n0 a multiple of NCNT) of the lanes' features.
+// Everything that does not depend on the accumulator (bias, the trees' one-hot rows, addresses) is fetched BEFORE the
+// wait on the MMAs' mbarrier; all per-tree addresses are the pass's base plus compile-time offsets.
+// MODE 0: MuZero; 1: chance-node searches, one future per pass (the future's one-hot row joins the bias); 2: chance-node searches,
+// both futures side by side (columns 16..31, two passes per stage, operands without a lo twin). What a mode does not need is compiled out.
+template <int NCNT, int MODE>
+__device__ __forceinline__ bool tc_epi_warp(const TcEpi& ep, int n0, uint32_t d_tmem, unsigned char* __restrict__ arena, int b_lo,
                                             float* __restrict__ outs, int out_pitch, const float* __restrict__ ctab,
-                                            const int* __restrict__ row_action, int lane, uint32_t mbar, uint32_t parity, int z) {
-    const int n0 = ep.n0;
+                                            const int* __restrict__ row_action, int lane, uint32_t mbar, uint32_t parity, int z,
+                                            bool wait) {
     const bool on = lane < ep.rows;
     const int flags = ep.flags;
+    const int t0 = n0 & 15;  // first tree
     float add[NCNT];
+    float z0 = 0.0f, z1 = 0.0f;
     {
         float bias = on ? ctab[ep.cidx + lane] : 0.0f;
-        if (ep.zidx >= 0 && on) bias += ctab[ep.zidx + z * ep.e_ld + lane];  // the same future for every tree of the pass
+        if (MODE >= 1 && ep.zidx >= 0 && on) {
+            if (MODE == 2 && (flags & 4)) {
+                z0 = ctab[ep.zidx + lane];
+                z1 = ctab[ep.zidx + ep.e_ld + lane];
+            } else {
+                bias += ctab[ep.zidx + z * ep.e_ld + lane];  // the same future for every tree of the pass
+            }
+        }
 #pragma unroll
         for (int i = 0; i < NCNT; ++i) add[i] = bias;
         if (ep.eidx >= 0 && on) {  // one-hot action input == one gathered weight row per tree (models.py:236-243)
@@ -163,11 +179,11 @@ __device__ __forceinline__ bool tc_epi_warp(const TcEpi& ep, uint32_t d_tmem, un
             if constexpr (NCNT >= 4) {
 #pragma unroll
                 for (int i = 0; i < NCNT; i += 4) {
-                    const int4 a4 = *reinterpret_cast<const int4*>(row_action + n0 + i);
+                    const int4 a4 = *reinterpret_cast<const int4*>(row_action + t0 + i);
                     act[i] = a4.x; act[i + 1] = a4.y; act[i + 2] = a4.z; act[i + 3] = a4.w;
                 }
             } else {
-                const int2 a2 = *reinterpret_cast<const int2*>(row_action + n0);
+                const int2 a2 = *reinterpret_cast<const int2*>(row_action + t0);
                 act[0] = a2.x; act[1] = a2.y;
             }
 #pragma unroll
@@ -175,13 +191,16 @@ __device__ __forceinline__ bool tc_epi_warp(const TcEpi& ep, uint32_t d_tmem, un
         }
     }
     const int k = ep.feat0 + lane;
-    unsigned char* hi = (flags & 2) ? reinterpret_cast<unsigned char*>(outs + n0 * out_pitch + ep.dst + lane)
+    unsigned char* hi = (flags & 2) ? reinterpret_cast<unsigned char*>(outs + t0 * out_pitch + ((MODE == 2 && n0 >= 16) ? ep.dst_sbo : ep.dst) + lane)
                                     : arena + ep.dst + (k >> 2) * TC_LBO + (k & 3) * 4 + (n0 >> 3) * ep.dst_sbo + (n0 & 7) * 16;
     const int sbo = ep.dst_sbo;
     const uint32_t taddr = d_tmem + (uint32_t)(ep.d_col + n0);
     // ---- the accumulator
-    const bool ok = mbar_wait(mbar, parity);
-    tc_fence_after();
+    bool ok = true;
+    if (MODE != 2 || wait) {
+        ok = mbar_wait(mbar, parity);
+        tc_fence_after();
+    }
     uint32_t v[NCNT];
     tmem_ld<NCNT>(taddr, v);
     if (!on) return ok;
@@ -197,9 +216,31 @@ __device__ __forceinline__ bool tc_epi_warp(const TcEpi& ep, uint32_t d_tmem, un
         }
         return ok;
     }
+    if (MODE == 2 && (flags & 4)) {  // the hidden layer of the dynamics for both futures: they differ by one gathered weight row
+        unsigned char* lo = hi + b_lo;
+#pragma unroll
+        for (int f = 0; f < 2; ++f) {
+            const float zr = f ? z1 : z0;
+#pragma unroll
+            for (int i = 0; i < NCNT; ++i) {
+                const float e = elu_fast(y[i] + zr);
+                const int off = (NCNT == 16 && i >= 8) ? sbo + 16 * (i - 8) : 16 * i;
+                *reinterpret_cast<float*>(hi + off) = e;
+                *reinterpret_cast<float*>(lo + off) = tf32_lo(e);
+            }
+            hi += 2 * sbo;
+            lo += 2 * sbo;
+        }
+        return ok;
+    }
     if (flags & 1) {
 #pragma unroll
         for (int i = 0; i < NCNT; ++i) y[i] = elu_fast(y[i]);
+    }
+    if (MODE == 2 && (flags & 8)) {
+#pragma unroll
+        for (int i = 0; i < NCNT; ++i) *reinterpret_cast<float*>(hi + ((NCNT == 16 && i >= 8) ? sbo + 16 * (i - 8) : 16 * i)) = y[i];
+        return ok;
     }
     unsigned char* lo = hi + b_lo;
 #pragma unroll
@@ -222,19 +263,19 @@ __device__ __forceinline__ bool tc_epi_warp(const TcEpi& ep, uint32_t d_tmem, un
 // The 3 * KS MMAs of one layer (3xTF32), fully unrolled: one thread issues them.
 template <int KS>
 __device__ __forceinline__ void tc_issue_layer(uint32_t d, uint32_t a_hi, uint32_t a_lo, uint32_t bh_lo, uint32_t bl_lo, uint32_t b_hi,
-                                               int ksteps) {
+                                               int ksteps, uint32_t idesc) {
 #pragma unroll
     for (int ks = 0; ks < (KS ? KS : 1); ++ks) {
         if (KS == 0 && ks == 0) {
             for (int q = 0; q < ksteps; ++q) {
-                tc_mma(d, a_hi + 8 * q, bh_lo + q * ((2 * TC_LBO) >> 4), b_hi, TC_IDESC, q > 0 ? 1u : 0u);
-                tc_mma(d, a_lo + 8 * q, bh_lo + q * ((2 * TC_LBO) >> 4), b_hi, TC_IDESC, 1u);
-                tc_mma(d, a_hi + 8 * q, bl_lo + q * ((2 * TC_LBO) >> 4), b_hi, TC_IDESC, 1u);
+                tc_mma(d, a_hi + 8 * q, bh_lo + q * ((2 * TC_LBO) >> 4), b_hi, idesc, q > 0 ? 1u : 0u);
+                tc_mma(d, a_lo + 8 * q, bh_lo + q * ((2 * TC_LBO) >> 4), b_hi, idesc, 1u);
+                tc_mma(d, a_hi + 8 * q, bl_lo + q * ((2 * TC_LBO) >> 4), b_hi, idesc, 1u);
             }
         } else if (KS) {
-            tc_mma(d, a_hi + 8 * ks, bh_lo + ks * ((2 * TC_LBO) >> 4), b_hi, TC_IDESC, ks > 0 ? 1u : 0u);
-            tc_mma(d, a_lo + 8 * ks, bh_lo + ks * ((2 * TC_LBO) >> 4), b_hi, TC_IDESC, 1u);
-            tc_mma(d, a_hi + 8 * ks, bl_lo + ks * ((2 * TC_LBO) >> 4), b_hi, TC_IDESC, 1u);
+            tc_mma(d, a_hi + 8 * ks, bh_lo + ks * ((2 * TC_LBO) >> 4), b_hi, idesc, ks > 0 ? 1u : 0u);
+            tc_mma(d, a_lo + 8 * ks, bh_lo + ks * ((2 * TC_LBO) >> 4), b_hi, idesc, 1u);
+            tc_mma(d, a_hi + 8 * ks, bl_lo + ks * ((2 * TC_LBO) >> 4), b_hi, idesc, 1u);
         }
     }
 }
@@ -242,12 +283,12 @@ __device__ __forceinline__ void tc_issue_layer(uint32_t d, uint32_t a_hi, uint32
 // All stages of the recurrent inference for the 16 trees of one group (models.py:233-257, 283-287); called by every
 // thread of the group. gw: warp of the group (provably warp-uniform); hq: the normalised hidden state quads of this
 // lane's tree (quad i = j + q * LPT), returned for the expansion's hidden-state store.
-template <int LPT>
+template <int LPT, int MODE = 0>
 __device__ __forceinline__ bool tc_mlp(const TcSched& ts, uint32_t tmem_base, uint32_t d_group, unsigned char* __restrict__ arena,
                                        float* __restrict__ outs, const float* __restrict__ ctab,
                                        const int* __restrict__ row_action, uint32_t mbar, uint32_t& parity, int gw, int lane,
                                        int row, int j, int barid, float4 (&hq)[2], unsigned long long* dbg = nullptr,
-                                       int s_begin = 0, int s_end = -1, int z = 0) {
+                                       int s_begin = 0, int s_end = -1, int z = 0, float* __restrict__ hst = nullptr) {
     constexpr int GTHREADS = GT * LPT;
     const uint32_t arena_s = smem_u32(arena);
     const uint32_t lane_q = (uint32_t)(32 * (gw & 3)) << 16;
@@ -267,9 +308,10 @@ __device__ __forceinline__ bool tc_mlp(const TcSched& ts, uint32_t tmem_base, ui
                     const uint32_t bh_lo = tc_desc_lo(arena_s + mm.b_off), bl_lo = tc_desc_lo(arena_s + mm.b_off + ts.b_lo);
                     const uint32_t b_hi = tc_desc_hi(mm.sbo);
                     const uint32_t d = d_group + mm.d_col;
-                    if (mm.ksteps == 8) tc_issue_layer<8>(d, a_hi, a_lo, bh_lo, bl_lo, b_hi, 8);
-                    else if (mm.ksteps == 4) tc_issue_layer<4>(d, a_hi, a_lo, bh_lo, bl_lo, b_hi, 4);
-                    else tc_issue_layer<0>(d, a_hi, a_lo, bh_lo, bl_lo, b_hi, mm.ksteps);
+                    const uint32_t idesc = tc_idesc((MODE == 2 && mm.n) ? mm.n : 16);
+                    if (mm.ksteps == 8) tc_issue_layer<8>(d, a_hi, a_lo, bh_lo, bl_lo, b_hi, 8, idesc);
+                    else if (mm.ksteps == 4) tc_issue_layer<4>(d, a_hi, a_lo, bh_lo, bl_lo, b_hi, 4, idesc);
+                    else tc_issue_layer<0>(d, a_hi, a_lo, bh_lo, bl_lo, b_hi, mm.ksteps, idesc);
                 }
                 if (st.commit)
                     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
@@ -281,52 +323,70 @@ __device__ __forceinline__ bool tc_mlp(const TcSched& ts, uint32_t tmem_base, ui
             // models.py:248-255: (x - min) / scale, scale += 1e-5 only where scale < 1e-5; the tree's lanes each own
             // quads of 4 consecutive features == one 16-byte row of a core matrix
             const int nq = ts.H >> 2;
-            const unsigned char* src = arena + ts.xs_off + (row >> 3) * ts.xs_sbo + (row & 7) * 16;
-            float mn = CUDART_INF_F, mx = -CUDART_INF_F;
+            const int nz = MODE == 2 ? 2 : 1;  // merged transition expansion: future 1 of tree `row` is column row + 16
+            for (int zz = 0; zz < nz; ++zz) {
+                const int r2 = row + 16 * zz;
+                const unsigned char* src = arena + ts.xs_off + (r2 >> 3) * ts.xs_sbo + (r2 & 7) * 16;
+                float mn = CUDART_INF_F, mx = -CUDART_INF_F;
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                const int i = j + q * LPT;
-                if (i < nq) {
-                    hq[q] = *reinterpret_cast<const float4*>(src + i * TC_LBO);
-                    mn = fminf(mn, fminf(fminf(hq[q].x, hq[q].y), fminf(hq[q].z, hq[q].w)));
-                    mx = fmaxf(mx, fmaxf(fmaxf(hq[q].x, hq[q].y), fmaxf(hq[q].z, hq[q].w)));
+                for (int q = 0; q < 2; ++q) {
+                    const int i = j + q * LPT;
+                    if (i < nq) {
+                        hq[q] = *reinterpret_cast<const float4*>(src + i * TC_LBO);
+                        mn = fminf(mn, fminf(fminf(hq[q].x, hq[q].y), fminf(hq[q].z, hq[q].w)));
+                        mx = fmaxf(mx, fmaxf(fmaxf(hq[q].x, hq[q].y), fmaxf(hq[q].z, hq[q].w)));
+                    }
                 }
-            }
 #pragma unroll
-            for (int d = 1; d < LPT; d <<= 1) {
-                mn = fminf(mn, __shfl_xor_sync(FULL, mn, d));
-                mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, d));
-            }
-            float scale = __fsub_rn(mx, mn);
-            if (scale < 1e-5f) scale = __fadd_rn(scale, 1e-5f);
-            const float inv = __frcp_rn(scale);
-            unsigned char* dst = arena + ts.xn_off + (row >> 3) * ts.xn_sbo + (row & 7) * 16;
+                for (int d = 1; d < LPT; d <<= 1) {
+                    mn = fminf(mn, __shfl_xor_sync(FULL, mn, d));
+                    mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, d));
+                }
+                float scale = __fsub_rn(mx, mn);
+                if (scale < 1e-5f) scale = __fadd_rn(scale, 1e-5f);
+                const float inv = __frcp_rn(scale);
+                unsigned char* dst = arena + ts.xn_off + (row >> 3) * ts.xn_sbo + (row & 7) * 16;
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                const int i = j + q * LPT;
-                if (i < nq) {
-                    float4 v = hq[q];
-                    v.x = __fmul_rn(__fsub_rn(v.x, mn), inv); v.y = __fmul_rn(__fsub_rn(v.y, mn), inv);
-                    v.z = __fmul_rn(__fsub_rn(v.z, mn), inv); v.w = __fmul_rn(__fsub_rn(v.w, mn), inv);
-                    hq[q] = v;
-                    if (ts.xn_off >= 0) {  // (no layer of a transition expansion reads the normalised state)
-                        *reinterpret_cast<float4*>(dst + i * TC_LBO) = v;
-                        *reinterpret_cast<float4*>(dst + i * TC_LBO + ts.b_lo) = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
+                for (int q = 0; q < 2; ++q) {
+                    const int i = j + q * LPT;
+                    if (i < nq) {
+                        float4 v = hq[q];
+                        v.x = __fmul_rn(__fsub_rn(v.x, mn), inv); v.y = __fmul_rn(__fsub_rn(v.y, mn), inv);
+                        v.z = __fmul_rn(__fsub_rn(v.z, mn), inv); v.w = __fmul_rn(__fsub_rn(v.w, mn), inv);
+                        hq[q] = v;
+                        if (MODE == 2) {  // straight into the hidden-state slots of the new futures
+                            if (hst) reinterpret_cast<float4*>(hst + (size_t)zz * ts.H)[i] = v;
+                        } else if (ts.xn_off >= 0) {  // (no layer of a transition expansion reads the normalised state)
+                            *reinterpret_cast<float4*>(dst + i * TC_LBO) = v;
+                            *reinterpret_cast<float4*>(dst + i * TC_LBO + ts.b_lo) = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
+                        }
                     }
                 }
             }
             fence_async_smem();
         }
-        if (st.n_epi > 0) {  // one pass per stage: every warp of the group waits on the stage's commit
-            const TcEpi& ep = ts.epi[st.epi0][gw];
+        if (st.n_epi > 0) {  // every warp of the group waits on the stage's commit, once
             const uint32_t d_tmem = d_group + lane_q;
-            bool w;
-            if (ep.ncnt == 2) w = tc_epi_warp<2>(ep, d_tmem, arena, ts.b_lo, outs, ts.out_pitch, ctab, row_action, lane, mbar, parity, z);
-            else if (ep.ncnt == 4) w = tc_epi_warp<4>(ep, d_tmem, arena, ts.b_lo, outs, ts.out_pitch, ctab, row_action, lane, mbar, parity, z);
-            else if (ep.ncnt == 8) w = tc_epi_warp<8>(ep, d_tmem, arena, ts.b_lo, outs, ts.out_pitch, ctab, row_action, lane, mbar, parity, z);
-            else if (ep.ncnt == 16) w = tc_epi_warp<16>(ep, d_tmem, arena, ts.b_lo, outs, ts.out_pitch, ctab, row_action, lane, mbar, parity, z);
-            else w = mbar_wait(mbar, parity);
-            ok = ok && w;
+            const int n_epi = MODE == 2 ? st.n_epi : 1;
+            for (int e = 0; e < n_epi; ++e) {
+                const TcEpi& ep = ts.epi[st.epi0 + e][gw];
+                const bool wt = e == 0;
+                bool w = true;
+                if (MODE != 2 && ep.ncnt == 2) w = tc_epi_warp<2, MODE>(ep, ep.n0, d_tmem, arena, ts.b_lo, outs, ts.out_pitch, ctab, row_action, lane, mbar, parity, z, wt);
+                else if (MODE != 2 && ep.ncnt == 4) w = tc_epi_warp<4, MODE>(ep, ep.n0, d_tmem, arena, ts.b_lo, outs, ts.out_pitch, ctab, row_action, lane, mbar, parity, z, wt);
+                else if (ep.ncnt == 8) w = tc_epi_warp<8, MODE>(ep, ep.n0, d_tmem, arena, ts.b_lo, outs, ts.out_pitch, ctab, row_action, lane, mbar, parity, z, wt);
+                else if (ep.ncnt >= 16) {
+                    const int reps = (MODE == 2 && ep.ncnt == 32) ? 2 : 1;  // 32 columns: two rounds of 16 through one copy of the code
+#pragma unroll 1
+                    for (int h = 0; h < reps; ++h)
+                        w = tc_epi_warp<16, MODE>(ep, ep.n0 + 16 * h, d_tmem, arena, ts.b_lo, outs, ts.out_pitch, ctab, row_action, lane, mbar,
+                                                  parity, z, wt && h == 0) && w;
+                } else if (wt) {
+                    w = mbar_wait(mbar, parity);
+                    if (MODE == 2) tc_fence_after();
+                }
+                ok = ok && w;
+            }
             parity ^= 1u;
             if (tm) q2 = clock64();
             fence_async_smem();
