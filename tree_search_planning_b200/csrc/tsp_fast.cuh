@@ -1356,6 +1356,10 @@ __device__ __forceinline__ void search_fast_variant_body(const FastParams& p, co
                 const int jc = j < NC ? j : 0;
                 const int vis = blk->visit[jc];
                 const int ch = blk->child[jc];
+                int sl = 0;
+                // (the trees of a warp descend in step -- state levels on even rounds, transition levels on odd ones -- so a
+                // transition round skips the whole pUCT evaluation)
+                if (__any_sync(FULL, state_lvl)) {
                 const double vs = blk->vsum[jc];
                 const float rw = blk->reward[jc];
                 const float prf = (node == 0) ? root_prior_f : blk->prior[jc];
@@ -1387,7 +1391,7 @@ __device__ __forceinline__ void search_fast_variant_body(const FastParams& p, co
                     const unsigned bad = __ballot_sync(FULL, on && !(fabsf(sc) <= 3.0e38f));
                     if ((bad >> gl0) & 0xFFu) cand = 0;
                 }
-                int sl = __ffs(cand) - 1;
+                sl = __ffs(cand) - 1;
                 const bool need = state_lvl && __popc(cand) != 1;
                 if (__any_sync(FULL, need)) {
                     int k2 = k_tie;
@@ -1399,6 +1403,7 @@ __device__ __forceinline__ void search_fast_variant_body(const FastParams& p, co
                         k_tie = k2;
                         n_exact++;
                     }
+                }
                 }
                 if (walking && !parent_is_state) {  // TransitionNode.select_child, self_play_stochastic.py:517-533
                     sl = 0;
