@@ -11,8 +11,11 @@ ncu --set full --clock-control none --import-source on -k regex:root_tcs -s 4 -c
 python tools/gpu_tune.py cross_merge_env 8192 200 > $O/r2_tcs_plain.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:search_tcs -s 3 -c 1 -o $O/r2_search_tcs python tools/gpu_tune.py cross_merge_env 8192 200 > $O/r2_ncu4.log 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 40 --csv --log-file $O/r2_launches_cross_merge_8192x200.csv python tools/gpu_tune.py cross_merge_env 8192 200 > $O/r2_ncu5.log 2>&1
+# the chance-node kernel (both futures per pass): stochastic search, 16,384 roots x 25 simulations
+python tools/gpu_tune.py roundabout_env_ttc_flat_stochastic_concat 16384 25 > $O/r2_variant_plain.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:search_tc_variant -s 3 -c 1 -o $O/r2_search_tc_variant python tools/gpu_tune.py roundabout_env_ttc_flat_stochastic_concat 16384 25 > $O/r2_ncu6.log 2>&1
 python -c "import __graft_entry__ as g; g.smoke()" > $O/r2_smoke.txt 2>&1
-for f in r2_search_tc r2_root_tcs r2_search_tcs; do
+for f in r2_search_tc r2_root_tcs r2_search_tcs r2_search_tc_variant; do
   ncu -i $O/$f.ncu-rep --page raw --csv > $O/$f.raw.csv 2>/dev/null
   python tools/ncu_summary.py $O/$f.raw.csv > $O/${f}_ncu_full_summary.json
   ncu -i $O/$f.ncu-rep --page source --csv --print-source sass > $O/$f.src.csv 2>/dev/null
