@@ -334,51 +334,50 @@ __device__ __forceinline__ void fast_mlp(const FastSched& fs, const float* __res
     }
 }
 
-// value and reward decode (models.py:1180-1201) and the policy softmax (self_play.py:532-538) of one row
-// by the 16 lanes of its tree, with the three max-reductions and the five sum-reductions sharing their
-// shuffle rounds. vl / rl / pl point at column 0 of the row inside the interleaved strip (column k at kofs(k)).
-// LIN: the logits are plain arrays (tcgen05 path) instead of columns of the interleaved strip.
+// value and reward decode (models.py:1180-1201) and the policy softmax (self_play.py:532-538) of one row by the LPT
+// lanes of its tree. The lanes split by DISTRIBUTION: the first half of the tree's lanes decodes the value support, the
+// second half the reward support -- one softmax-expectation and ONE inverse value transform (a float32 square root and two
+// divisions in IEEE rounding) per lane instead of two, reductions over LPT / 2 lanes; the policy softmax (at most 8 logits,
+// one per lane) rides in the same shuffle rounds. vl / rl / pl point at column 0 of the row inside the interleaved strip
+// (column k at kofs(k)). LIN: the logits are plain arrays (tcgen05 path) instead of columns of the interleaved strip.
 template <int LPT, bool LIN = false>
 __device__ __forceinline__ void decode_row(const float* __restrict__ vl, const float* __restrict__ rl,
                                            const float* __restrict__ pl, int support, int A, bool uniform, int j,
                                            float& value, float& reward, float& prior) {
     auto kofs = [](int k) { return LIN ? k : ((k >> 1) << 2) + ((k & 1) << 1); };
+    constexpr int HL = LPT / 2;
     const int n = 2 * support + 1;
-    float mv = -CUDART_INF_F, mr = -CUDART_INF_F;
-    for (int i = j; i < n; i += LPT) {
-        mv = fmaxf(mv, vl[kofs(i)]);
-        mr = fmaxf(mr, rl[kofs(i)]);
-    }
+    const float* sl = (j >= HL) ? rl : vl;
+    const int jj = j & (HL - 1);
+    float m = -CUDART_INF_F;
+    for (int i = jj; i < n; i += HL) m = fmaxf(m, sl[kofs(i)]);
     const bool pon = j < A;
     const float lg = (pon && !uniform) ? pl[kofs(j)] : 0.0f;
     float mp = pon ? lg : -CUDART_INF_F;
 #pragma unroll
-    for (int d = 1; d < LPT; d <<= 1) {
-        mv = fmaxf(mv, __shfl_xor_sync(FULL, mv, d));
-        mr = fmaxf(mr, __shfl_xor_sync(FULL, mr, d));
+    for (int d = 1; d < HL; d <<= 1) {
+        m = fmaxf(m, __shfl_xor_sync(FULL, m, d));
         mp = fmaxf(mp, __shfl_xor_sync(FULL, mp, d));
     }
-    float sv = 0.f, xv = 0.f, sr = 0.f, xr = 0.f;
-    for (int i = j; i < n; i += LPT) {
-        const float ev = __expf(__fsub_rn(vl[kofs(i)], mv));
-        const float er = __expf(__fsub_rn(rl[kofs(i)], mr));
-        sv = __fadd_rn(sv, ev);
-        xv = fmaf((float)(i - support), ev, xv);
-        sr = __fadd_rn(sr, er);
-        xr = fmaf((float)(i - support), er, xr);
+    mp = fmaxf(mp, __shfl_xor_sync(FULL, mp, HL));
+    float sm = 0.f, xm = 0.f;
+    for (int i = jj; i < n; i += HL) {
+        const float e = __expf(__fsub_rn(sl[kofs(i)], m));
+        sm = __fadd_rn(sm, e);
+        xm = fmaf((float)(i - support), e, xm);
     }
     const float ep = pon ? __expf(__fsub_rn(lg, mp)) : 0.0f;
     float sp = ep;
 #pragma unroll
-    for (int d = 1; d < LPT; d <<= 1) {
-        sv = __fadd_rn(sv, __shfl_xor_sync(FULL, sv, d));
-        xv = __fadd_rn(xv, __shfl_xor_sync(FULL, xv, d));
-        sr = __fadd_rn(sr, __shfl_xor_sync(FULL, sr, d));
-        xr = __fadd_rn(xr, __shfl_xor_sync(FULL, xr, d));
+    for (int d = 1; d < HL; d <<= 1) {
+        sm = __fadd_rn(sm, __shfl_xor_sync(FULL, sm, d));
+        xm = __fadd_rn(xm, __shfl_xor_sync(FULL, xm, d));
         sp = __fadd_rn(sp, __shfl_xor_sync(FULL, sp, d));
     }
-    value = inverse_value_transform(__fdiv_rn(xv, sv));
-    reward = inverse_value_transform(__fdiv_rn(xr, sr));
+    sp = __fadd_rn(sp, __shfl_xor_sync(FULL, sp, HL));
+    const float sc = inverse_value_transform(__fdiv_rn(xm, sm));  // the value in the first half of the lanes, the reward in the second
+    value = __shfl_sync(FULL, sc, 0, LPT);
+    reward = __shfl_sync(FULL, sc, HL, LPT);
     prior = __fdiv_rn(ep, sp);
 }
 
