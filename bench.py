@@ -500,11 +500,12 @@ def main():
             for tag, game, Bx, Sx, steps in EXTRA_CONFIGS:
                 if only and tag not in only:
                     continue
-                rows.append(measure_row(torch, dist, tsp, tag, game, Bx, Sx, steps, 2, *common, scaling="single-gpu"))
+                rows.append(measure_row(torch, dist, tsp, tag, game, Bx, Sx, steps, 3, *common, scaling="single-gpu"))
         for tag, game, Bx, Sx, steps in STRONG_CONFIGS:
             if only and tag not in only:
                 continue
-            rows.append(measure_row(torch, dist, tsp, tag, game, Bx, Sx, steps, 2, *common, scaling="strong"))
+            # (a rank's share shrinks with the world size: the same timed work per row at every N)
+            rows.append(measure_row(torch, dist, tsp, tag, game, Bx, Sx, steps * world, 3, *common, scaling="strong"))
         line["configs"] = rows
     if rank == 0:
         emit(line)
