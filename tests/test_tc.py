@@ -159,6 +159,26 @@ def test_both_futures_in_one_pass_match_one_future_per_pass(game, B, monkeypatch
     assert_records_close(a[keep], b[keep], cfg.n_futures, min_fraction=0.995, what="both futures per pass vs one future per pass")
 
 
+@pytest.mark.parametrize("widths", [dict(encoding_size=32, fc_dynamics_layers=[16], fc_reward_layers=[16], fc_value_layers=[24],
+                                         fc_policy_layers=[8], fc_prior_layers=[16], support_size=5),
+                                    dict(encoding_size=32, fc_dynamics_layers=[8], fc_reward_layers=[8], fc_value_layers=[8],
+                                         fc_policy_layers=[8], fc_prior_layers=[8], support_size=2),
+                                    dict(encoding_size=48, fc_dynamics_layers=[24], fc_reward_layers=[32], fc_value_layers=[16],
+                                         fc_policy_layers=[32], fc_prior_layers=[24], support_size=15),
+                                    dict(encoding_size=64, fc_dynamics_layers=[16], fc_reward_layers=[32], fc_value_layers=[32],
+                                         fc_policy_layers=[32], fc_prior_layers=[32], support_size=10)])
+@pytest.mark.parametrize("game", ["roundabout_env_ttc_flat_stochastic_concat", "roundabout_env_ttc_flat_risk_sensitive"])
+@pytest.mark.parametrize("B", [300, 9000])
+def test_chance_node_searches_other_layer_widths(widths, game, B):
+    """The merged schedule's tables depend on the widths: one or two lane quarters of next state, the un-normalised states
+    aliased onto the dead gathered-state + hidden-layer buffers or in a buffer of their own (H > 2 x dynamics width)."""
+    cfg = tsp.get_config(game, **widths)
+    st, out = search_kernel_of(cfg, B, 25)
+    assert st["search_kernel"] == 2
+    assert (out["visit_counts"].sum(1) == 25).all()
+    check_against_oracle(cfg, B, 25, seed=34, legal=(B == 300))
+
+
 def test_three_futures_keep_one_future_per_pass():
     cfg = tsp.get_config("roundabout_env_ttc_flat_stochastic_concat", n_futures=3)
     st, out = search_kernel_of(cfg, 700, 25)
