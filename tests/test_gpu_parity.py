@@ -389,7 +389,8 @@ def test_generic_kernel_fallback_bit_exact(name, monkeypatch):
     eng.close()
 
 
-@pytest.mark.parametrize("game,B,kernel", [("roundabout_env_ttc_flat", 2048, 2), ("cross_merge_env", 333, 3)])
+@pytest.mark.parametrize("game,B,kernel", [("roundabout_env_ttc_flat", 2048, 2), ("cross_merge_env", 333, 3),
+                                           ("roundabout_env_ttc_flat_risk_sensitive", 1024, 2)])
 def test_continued_search_large_batch_vs_oracle(game, B, kernel):
     """resume (override_root_with) at batch scale: 3 x 20 simulations on 2,048 roots (tensor-memory kernel) / 333 roots
     (streamed kernel), every phase with fresh noise and streams; the engine's traces replayed through the oracle must
@@ -410,8 +411,10 @@ def test_continued_search_large_batch_vs_oracle(game, B, kernel):
     assert (got["visit_counts"].sum(1) == S * P).all()
     assert eng.stats()["search_kernel"] == kernel
     stack = lambda k: numpy.stack([kw[k] for kw in phases])
-    replay = Oracle(cfg, sd).run(S, fed_root=troot, fed_records=numpy.stack(traces), B=B, n_phases=P,
-                                 noise=stack("noise"), tie=stack("tie"))
+    streams = dict(noise=stack("noise"), tie=stack("tie"))
+    if "chance" in phases[0]:  # the risk-sensitive search continues a tree too (self_play_risk_sensitive.py has no sims assert)
+        streams["chance"] = stack("chance")
+    replay = Oracle(cfg, sd).run(S, fed_root=troot, fed_records=numpy.stack(traces), B=B, n_phases=P, **streams)
     assert_tree_outputs_bit_exact(got, replay, what="continued search replayed through the oracle")
     with pytest.raises(tsp.TspError, match="exceed max_simulations"):
         eng.run(S, resume=True, num_roots=B, **phases[0])
