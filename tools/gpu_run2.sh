@@ -1,1 +1,5 @@
-timeout 900 python -m pytest tests/test_gpu_parity.py -q -m gpu -x -k "continued_search_large" -o faulthandler_timeout=300 2>&1 | tail -15
+for nb in 0 1 0 1; do
+TSP_NO_BALANCE=$nb timeout 300 python tools/gpu_tune.py roundabout_env_ttc_flat_stochastic_concat 16384 25 2>&1 | tail -1 | cut -c1-190
+done
+TSP_NO_BALANCE=1 timeout 300 python tools/gpu_tune.py roundabout_env_ttc_flat_risk_sensitive 16384 25 2>&1 | tail -1 | cut -c1-190
+TSP_NO_BALANCE=0 timeout 300 python tools/gpu_tune.py roundabout_env_ttc_flat_risk_sensitive 16384 25 2>&1 | tail -1 | cut -c1-190
